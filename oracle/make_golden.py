@@ -1,0 +1,310 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference on CPU.
+
+Run in the build container only (needs /root/reference):
+
+    python oracle/make_golden.py
+
+Each fixture stores seeded inputs and the reference's own outputs for one row of
+SURVEY.md section 8(a).  The fixtures are small (KBs) and are committed; the GPU box
+has no /root/reference, so tests read only these files.
+"""
+
+import copy
+import os
+import re
+import sys
+import tempfile
+import types
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle import reference_shim as rs  # noqa: E402
+
+warnings.filterwarnings("ignore")
+rs.install()
+
+from mineral.agents.diffrl.shac import SHAC  # noqa: E402
+from mineral.agents.diffrl.utils import CriticDataset  # noqa: E402
+from mineral.agents.ppo.experience import ExperienceBuffer  # noqa: E402
+from mineral.agents.ppo.ppo import PPO, actor_loss, bounds_loss, critic_loss, policy_kl  # noqa: E402
+from mineral.buffers import NStepReplay, ReplayBuffer  # noqa: E402
+from mineral.common.normalizers import RunningMeanStd  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def save(name, obj):
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(obj, path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KB")
+
+
+def clone_tree(x):
+    if isinstance(x, dict):
+        return {k: clone_tree(v) for k, v in x.items()}
+    if torch.is_tensor(x):
+        return x.detach().clone()
+    return copy.deepcopy(x)
+
+
+# ---- K1a + K3a: ExperienceBuffer.compute_return / prepare_training -------------------------
+def gen_experience():
+    cases = []
+    for seed, (T, N, O, A), done_p in [
+        (0, (8, 24, 5, 3), 0.1),
+        (1, (16, 12, 37, 8), 0.0),
+        (2, (4, 20, 7, 2), 1.0),
+        (3, (32, 8, 3, 1), 0.3),
+    ]:
+        g = torch.Generator().manual_seed(seed)
+        buf = ExperienceBuffer(N, T, N * T, N * T // 4, {"obs": (O,)}, A, "cpu", re.compile("$^"))
+        sd = buf.storage_dict
+        sd["rewards"].copy_(torch.randn(T, N, 1, generator=g))
+        sd["values"].copy_(3 * torch.randn(T, N, 1, generator=g))
+        sd["neglogp"].copy_(torch.randn(T, N, generator=g))
+        sd["dones"].copy_((torch.rand(T, N, generator=g) < done_p).to(torch.uint8))
+        for k in ("actions", "mu", "sigma"):
+            sd[k].copy_(torch.randn(T, N, A, generator=g))
+        sd["obses"]["obs"].copy_(torch.randn(T, N, O, generator=g) * 4 + 1)
+        last_values = 3 * torch.randn(N, 1, generator=g)
+        inputs = clone_tree({k: v for k, v in sd.items() if k != "returns"})
+        buf.compute_return(last_values, 0.99, 0.95)
+        returns_tm = sd["returns"].clone()
+        data = buf.prepare_training()
+        mb1 = buf[1]
+        cases.append(
+            dict(
+                shape=(T, N, O, A), gamma=0.99, tau=0.95, inputs=inputs, last_values=last_values,
+                returns_time_major=returns_tm, data=clone_tree(data), minibatch_size=N * T // 4,
+                minibatch1=clone_tree({k: v for k, v in zip(("values", "neglogp", "advantages", "mu", "sigma", "returns", "actions", "obses"), mb1)}),
+                length=len(buf),
+            )
+        )
+    save("experience", cases)
+
+
+# ---- K2: RunningMeanStd ---------------------------------------------------------------------
+def gen_rms():
+    cases = []
+    cfgs = {
+        "ppo_f64": dict(eps=1e-5, with_clamp=True, initial_count=1, dtype=torch.float64),
+        "sac_f32": dict(eps=1e-4, with_clamp=True, initial_count="eps"),
+        "shac_legacy": dict(eps=1e-5, correction=0, initial_count=1e-4, dtype=torch.float32),
+        "shac_f64_noclamp": dict(eps=1e-5, initial_count=1, dtype=torch.float64),
+    }
+    for ci, (name, kw) in enumerate(cfgs.items()):
+        g = torch.Generator().manual_seed(10 + ci)
+        for shape in [(37,), (1,), (4, 3)]:
+            rms = RunningMeanStd(shape, **kw)
+            steps = []
+            for rows in (32, 7, 90):
+                x = torch.randn(rows, *shape, generator=g) * torch.linspace(0.1, 9.0, int(np.prod(shape))).view(shape) + 2.5
+                rms.update(x)
+                y = rms.normalize(x)
+                z = rms.unnormalize(y * 1.3)
+                steps.append(dict(x=x, mean=rms.running_mean.clone(), var=rms.running_var.clone(), count=rms.running_count.clone(), normalized=y, unnormalized=z))
+            cases.append(dict(name=name, kwargs={k: (str(v) if isinstance(v, torch.dtype) else v) for k, v in kw.items()}, shape=shape, steps=steps, state_dict_keys=list(rms.state_dict().keys())))
+    save("rms", cases)
+
+
+# ---- K1b: SHAC target values ------------------------------------------------------------------
+def gen_tdlambda():
+    cases = []
+    for seed, (T, N), done_p in [(0, (8, 10), 0.1), (1, (32, 6), 0.0), (2, (5, 9), 0.5)]:
+        g = torch.Generator().manual_seed(seed)
+        rew = torch.randn(T, N, generator=g)
+        dm = (torch.rand(T, N, generator=g) < done_p).float()
+        dm[T - 1] = 1.0  # shac.py:789-792
+        nv = 2 * torch.randn(T, N, generator=g)
+        ent = torch.randn(T, N, generator=g) + 3
+        lp = torch.randn(T, N, generator=g) - 3
+        for method in ("td-lambda", "one-step"):
+            ns = types.SimpleNamespace(critic_method=method, num_envs=N, device="cpu", horizon_len=T, lam=0.95, gamma=0.99,
+                                       done_mask=dm, rew_buf=rew, next_values=nv, target_values=torch.zeros(T, N))
+            SHAC.compute_target_values(ns)
+            plain = ns.target_values.clone()
+            variants = []
+            for use_distr_ent, offset, scale, alpha in [(True, False, False, 0.2), (False, True, True, 0.05), (True, True, False, 0.7)]:
+                ns2 = types.SimpleNamespace(critic_method=method, num_envs=N, device="cpu", horizon_len=T, lam=0.95, gamma=0.99,
+                                            done_mask=dm, rew_buf=rew, next_values=nv, target_values=torch.zeros(T, N),
+                                            distr_ent=ent, logprobs=lp, use_distr_ent=use_distr_ent, offset_by_target_entropy=offset,
+                                            scale_by_target_entropy=scale, target_entropy=-4.0, with_autoent=False, entropy_coef=alpha)
+                SHAC.compute_target_values_with_entropy(ns2)
+                variants.append(dict(use_distr_ent=use_distr_ent, offset=offset, scale=scale, alpha=alpha, target=ns2.target_values.clone()))
+            cases.append(dict(method=method, gamma=0.99, lam=0.95, rew=rew, done_mask=dm, next_values=nv, distr_ent=ent, logprobs=lp,
+                              target_entropy=-4.0, target=plain, entropy_variants=variants))
+    save("tdlambda", cases)
+
+
+# ---- K3f: CriticDataset -------------------------------------------------------------------------
+def gen_critic_dataset():
+    cases = []
+    g = torch.Generator().manual_seed(5)
+    T, B, O = 6, 7, 4
+    obs = {"obs": torch.randn(T, B, O, generator=g)}
+    tv = torch.randn(T, B, generator=g)
+    for bs, shuffle, drop_last in [(10, False, False), (10, False, True), (8, True, False)]:
+        if shuffle:
+            np.random.seed(123)
+        ds = CriticDataset(bs, obs, tv, shuffle=shuffle, drop_last=drop_last)
+        batches = [clone_tree(dict(obs=ds[i][0], target=ds[i][1])) for i in range(len(ds))]
+        cases.append(dict(batch_size=bs, shuffle=shuffle, drop_last=drop_last, np_seed=123 if shuffle else None, obs=obs, target_values=tv, length=len(ds), batches=batches))
+    save("critic_dataset", cases)
+
+
+# ---- K3c/K3d: ReplayBuffer --------------------------------------------------------------------------
+def gen_replay():
+    g = torch.Generator().manual_seed(7)
+    O, A, C = 5, 2, 50
+    rb = ReplayBuffer({"obs": (O,)}, A, C, device="cpu")
+    for k in rb.buf_obs:
+        rb.buf_obs[k].zero_(); rb.buf_next_obs[k].zero_()
+    rb.buf_action.zero_(); rb.buf_reward.zero_(); rb.buf_done.zero_()
+    events = []
+    for rows in (12, 30, 20, 50, 3, 49):
+        tr = ({"obs": torch.randn(rows, O, generator=g)}, torch.randn(rows, A, generator=g), torch.randn(rows, 1, generator=g),
+              {"obs": torch.randn(rows, O, generator=g)}, (torch.rand(rows, 1, generator=g) < 0.3))
+        rb.add_to_buffer(tr)
+        torch.manual_seed(1000 + rows)
+        idx = torch.randint(rb.cur_capacity, size=(16,), device="cpu")
+        torch.manual_seed(1000 + rows)
+        obs, act, rew, nobs, done = rb.sample_batch(16, device="cpu")
+        events.append(dict(insert=clone_tree(dict(obs=tr[0]["obs"], act=tr[1], rew=tr[2], nobs=tr[3]["obs"], done=tr[4])),
+                           next_p=rb.next_p, if_full=rb.if_full, cur_capacity=rb.cur_capacity,
+                           buf=clone_tree(dict(obs=rb.buf_obs["obs"], act=rb.buf_action, rew=rb.buf_reward, nobs=rb.buf_next_obs["obs"], done=rb.buf_done)),
+                           idx=idx, sample=clone_tree(dict(obs=obs["obs"], act=act, rew=rew, nobs=nobs["obs"], done=done))))
+    save("replay", dict(obs_dim=O, act_dim=A, capacity=C, events=events))
+
+
+# ---- K3e: NStepReplay -----------------------------------------------------------------------------------
+def gen_nstep():
+    cases = []
+    for seed, (N, O, A, n, S_list, done_p) in enumerate([(6, 4, 2, 3, (4, 1, 5), 0.25), (5, 3, 1, 2, (1, 1, 3), 0.5), (4, 2, 2, 4, (2, 8), 0.1), (3, 2, 1, 1, (3,), 0.2)]):
+        g = torch.Generator().manual_seed(20 + seed)
+        ns = NStepReplay({"obs": (O,)}, A, N, n, device="cpu")
+        ns.nstep_buf_obs["obs"].zero_(); ns.nstep_buf_next_obs["obs"].zero_()
+        ns.nstep_buf_action.zero_(); ns.nstep_buf_reward.zero_(); ns.nstep_buf_done.zero_()
+        calls = []
+        for S in S_list:
+            obs = torch.randn(N, S, O, generator=g); act = torch.randn(N, S, A, generator=g)
+            rew = torch.randn(N, S, 1, generator=g); nobs = torch.randn(N, S, O, generator=g)
+            done = (torch.rand(N, S, 1, generator=g) < done_p).float()  # sac.py:150 stores dones in a float tensor
+            try:
+                o, a, r, no, d = ns.add_to_buffer({"obs": obs}, act, rew, {"obs": nobs}, done.bool())
+                out = clone_tree(dict(obs=o["obs"], act=a, rew=r, nobs=no["obs"], done=d))
+            except (RuntimeError, ValueError):  # reference raises (torch.cat of an empty list) while the window warms up
+                out = None
+            calls.append(dict(inp=dict(obs=obs, act=act, rew=rew, nobs=nobs, done=done.bool()), out=out))
+        cases.append(dict(N=N, O=O, A=A, nstep=n, gamma=0.99, calls=calls))
+    save("nstep", cases)
+
+
+# ---- K4: loss functions + autograd gradients ------------------------------------------------------------
+def gen_losses():
+    cases = []
+    for seed, (mb, A) in enumerate([(64, 8), (33, 3), (128, 16)]):
+        g = torch.Generator().manual_seed(30 + seed)
+        for e_clip, smooth, clip_v, btype in [(0.2, False, False, "bound"), (0.2, False, True, "bound"), (0.1, True, False, "reg")]:
+            old_nlp = torch.randn(mb, generator=g) + 8
+            nlp = (old_nlp + 0.3 * torch.randn(mb, generator=g)).requires_grad_(True)
+            adv = torch.randn(mb, generator=g)
+            vold = torch.randn(mb, 1, generator=g)
+            v = (vold + 0.4 * torch.randn(mb, 1, generator=g)).requires_grad_(True)
+            ret = torch.randn(mb, 1, generator=g)
+            mu = (1.5 * torch.randn(mb, A, generator=g)).requires_grad_(True)
+            sigma = torch.rand(mb, A, generator=g) + 0.1
+            old_mu = mu.detach() + 0.1 * torch.randn(mb, A, generator=g)
+            old_sigma = sigma * (1 + 0.1 * torch.rand(mb, A, generator=g))
+            a, frac = actor_loss(old_nlp, nlp, adv, e_clip, smooth)
+            c, ev = critic_loss(vold, v, e_clip, ret, clip_v)
+            b = bounds_loss(mu, btype)
+            kl = policy_kl(mu.detach(), sigma, old_mu, old_sigma)
+            total = a.mean() + 0.5 * c.mean() * 4 + b.mean() * 1e-4
+            total.backward()
+            cases.append(dict(e_clip=e_clip, smooth=smooth, clip_value=clip_v, bounds_type=btype,
+                              old_nlp=old_nlp, nlp=nlp.detach(), adv=adv, vold=vold, v=v.detach(), ret=ret, mu=mu.detach(), sigma=sigma, old_mu=old_mu, old_sigma=old_sigma,
+                              a_loss=a.detach(), clip_frac=frac, c_loss=c.detach(), explained_var=ev, b_loss=b.detach(), kl=kl, total=total.detach(),
+                              g_nlp=nlp.grad.clone(), g_v=v.grad.clone(), g_mu=mu.grad.clone()))
+    save("losses", cases)
+
+
+# ---- a8 + a9: the real PPO agent, play_steps tail + train_epoch -------------------------------------------
+def ppo_cfg(N, T, mb, units, variant, mini_epochs):
+    if variant == "elu_normal_fixed":
+        ack = dict(separate_value_mlp=True, mlp_kwargs=dict(units=units, act_type="ELU"), fixed_sigma=True, actor_dist_kwargs=dict(dist_type="normal"))
+        optim_type, mgn = "Adam", 1.0
+    else:  # DFlexAntPPO.yaml:14-26,59-66
+        ack = dict(separate_value_mlp=True, mlp_kwargs=dict(units=units, norm_type="LayerNorm", act_type="SiLU"), fixed_sigma=False,
+                   actor_dist_kwargs=dict(dist_type="dreamerv3_normal", minstd=0.1, maxstd=1.0))
+        optim_type, mgn = "AdamW", 0.5
+    return rs.to_attr(dict(
+        rl_device="cpu", multi_gpu=False, env_render=False, run="train", seed=0, task=dict(env_autoresets=True),
+        agent=dict(tracker_len=100, metrics_kwargs={}, print_every=-1, ckpt_every=-1,
+                   network=dict(normalize_input=True, actor_critic="ActorCritic", actor_critic_kwargs=ack),
+                   ppo=dict(multi_gpu=False, num_actors=N, reward_shaper=dict(fn="scale", scale=1.0), max_agent_steps=1e6, horizon_len=T, minibatch_size=mb,
+                            normalize_value=True, value_bootstrap=True, clip_value_loss=False, normalize_advantage=True, gamma=0.99, tau=0.95,
+                            entropy_coef=0.0 if variant == "elu_normal_fixed" else 0.001, e_clip=0.2, use_smooth_clamp=False, critic_coef=4,
+                            bounds_loss_coef=0.0001, bounds_type="bound", mini_epochs=mini_epochs, optim_type=optim_type, optim_kwargs=dict(lr=5e-4, eps=1e-5),
+                            lr_schedule="kl", kl_threshold=0.008, max_grad_norm=mgn, truncate_grads=True))))
+
+
+def gen_ppo_e2e():
+    cases = []
+    for variant in ("elu_normal_fixed", "ln_silu_dreamer_learned"):
+        N, T, O, A, mb, units, epochs = 16, 8, 11, 3, 32, [32, 16], 3
+        torch.manual_seed(40)
+        env = rs.SynthEnv(N, O, A, T, seed=41, done_p=0.08, timeout_p=0.05)
+        cfg = ppo_cfg(N, T, mb, units, variant, epochs)
+        with open(os.devnull, "w") as devnull:
+            stdout, sys.stdout = sys.stdout, devnull
+            try:
+                agent = PPO(cfg, logdir=tempfile.mkdtemp(), env=env)
+            finally:
+                sys.stdout = stdout
+        agent.obs = agent._convert_obs(env.reset())
+        agent.dones = torch.zeros(N, dtype=torch.bool)
+        agent.epoch = 0
+        init_sd = clone_tree(agent.model.state_dict())
+        rec = {}
+        orig = agent.storage.compute_return
+
+        def spy(last_values, gamma, tau):
+            rec["last_values"] = last_values.clone()
+            rec["storage"] = clone_tree({k: v for k, v in agent.storage.storage_dict.items() if k != "returns"})
+            rec["value_rms_before"] = clone_tree(agent.value_rms.state_dict())
+            return orig(last_values, gamma, tau)
+
+        agent.storage.compute_return = spy
+        agent.set_eval()
+        agent.play_steps()
+        rec["data_after_play"] = clone_tree(agent.storage.data_dict)
+        rec["value_rms_after_play"] = clone_tree(agent.value_rms.state_dict())
+        rec["obs_rms_before"] = clone_tree(agent.obs_rms.state_dict())
+        agent.set_train()
+        res = agent.train_epoch()
+        cases.append(dict(
+            variant=variant, shape=(T, N, O, A), minibatch_size=mb, units=units, mini_epochs=epochs, cfg=rs.to_plain(cfg),
+            init_state_dict=init_sd, **rec,
+            results={k: torch.stack(v) for k, v in res.items() if v[0].dim() == 0},
+            results_mu_mean=torch.cat(res["mu"]).mean(0), results_sigma_mean=torch.cat(res["sigma"]).mean(0),
+            final_state_dict=clone_tree(agent.model.state_dict()), obs_rms_after=clone_tree(agent.obs_rms.state_dict()),
+            value_rms_after=clone_tree(agent.value_rms.state_dict()), data_after_train=clone_tree({k: agent.storage.data_dict[k] for k in ("mu", "sigma")}),
+            last_lr=agent.last_lr, optim_state={i: clone_tree(s) for i, s in enumerate(agent.optim.state_dict()["state"].values())},
+        ))
+    save("ppo_e2e", cases)
+
+
+if __name__ == "__main__":
+    gen_experience()
+    gen_rms()
+    gen_tdlambda()
+    gen_critic_dataset()
+    gen_replay()
+    gen_nstep()
+    gen_losses()
+    gen_ppo_e2e()
