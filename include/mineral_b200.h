@@ -1,0 +1,331 @@
+/*
+ * mineral_b200 C ABI  —  B200 (sm_100a) kernels for the rollout->update data path
+ * of jacr13/mineral.
+ *
+ * The reference (pure Python, /root/reference) has no FFI: its extension points are
+ * Python name look-ups (mineral/scripts/run.py:142, mineral/agents/ppo/ppo.py:47).
+ * This header is therefore the boundary *underneath* the Python call surface that
+ * `mineral_b200/` mirrors; every entry point cites the reference code it replaces
+ * (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer into caller-owned memory unless it says "host";
+ *     the library never allocates, frees or retains pointers;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*): no
+ *     host synchronisation, no allocation, safe under CUDA-graph capture;
+ *   - return 0 on success, >0 = cudaError_t of the launch, <0 = MNR_E* argument error;
+ *     there is no CPU fallback: an unsupported argument is an error;
+ *   - layouts are the reference's: time-major (T,N,..) rollout storage, env-major
+ *     (N*T,..) training rows (row = n*T + t), u8 dones (PPO), f32 done_mask (SHAC),
+ *     bool done (replay), int64 indices;
+ *   - "state" = RunningMeanStd buffers running_mean[cols], running_var[cols],
+ *     running_count[1], all f32 (state_f64 = 0) or all f64 (state_f64 = 1).
+ */
+#ifndef MINERAL_B200_H
+#define MINERAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MNR_ABI_VERSION 1
+
+#define MNR_OK 0
+#define MNR_ENULL (-1)    /* required pointer is NULL */
+#define MNR_ESHAPE (-2)   /* non-positive or unsupported size */
+#define MNR_EALIGN (-3)   /* pointer not aligned as the kernel needs */
+#define MNR_EUNSUP (-4)   /* unsupported mode / enum value */
+#define MNR_EWORKSPACE (-5) /* workspace too small */
+
+typedef void* mnr_stream_t;
+
+int mnr_abi_version(void);
+/* Static string for a code returned by any mnr_* call (host). */
+const char* mnr_error_string(int code);
+/* Number of SMs of the current device (host query, cached). */
+int mnr_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1a  GAE reverse scan.  Replaces ExperienceBuffer.compute_return
+ *      (mineral/agents/ppo/experience.py:96-108).  Bit-exact with the reference:
+ *      delta = (r + (g*nv)*alive) - V;  A = delta + ((g*tau)*alive)*A';  ret = A + V.
+ *      rewards/values/returns/advantages: (T,N) f32 time-major; dones (T,N) u8;
+ *      last_values (N).  gamma_tau = (float)(double gamma * double tau).
+ *      `advantages` may be NULL.
+ * ------------------------------------------------------------------------------------ */
+int mnr_gae_f32(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                float* returns, float* advantages, int T, int N, float gamma, float gamma_tau,
+                mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K1b  SHAC / SAPO critic targets.  Replaces SHAC.compute_target_values and
+ *      compute_target_values_with_entropy (mineral/agents/diffrl/shac.py:877-916).
+ *      rew/done_mask/next_values/target: (T,N) f32; entropy (T,N) f32 or NULL.
+ *      method: 0 = one-step, 1 = td-lambda.
+ *      ent_flags: bit0 negate entropy input (use -logprobs), bit1 offset by |H_t| then *0.5,
+ *                 bit2 scale by 1/|H_t|.  abs_target_entropy = |H_t|,
+ *      inv_abs_target_entropy = (float)(1.0/|H_t|).  Scalars are the reference's Python
+ *      doubles rounded to f32: one_minus_lam = (float)(1.0-lam), lam_gamma = (float)(lam*gamma).
+ * ------------------------------------------------------------------------------------ */
+int mnr_critic_targets_f32(const float* rew, const float* done_mask, const float* next_values,
+                           const float* entropy, float* target, int T, int N, int method,
+                           float gamma, float lam, float one_minus_lam, float lam_gamma, float alpha,
+                           int ent_flags, float abs_target_entropy, float inv_abs_target_entropy,
+                           mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K1a+K3a fused post-rollout pass.  Replaces compute_return + transform_op +
+ *      prepare_training (experience.py:7-14,96-121) and produces the batch statistics that
+ *      the advantage normalisation (experience.py:119-120) and PPO's value-RMS block
+ *      (mineral/agents/ppo/ppo.py:175-183) need, in ONE pass over the rollout.
+ *
+ *      wide fields: n_wide descriptors (host array) of (T,N,width) f32 -> (N*T,width) f32.
+ *      scalars: rewards, values, neglogp (T,N) f32, dones (T,N) u8, last_values (N).
+ *      do_gae = 1: run the GAE scan in-kernel and (if returns_tm != NULL) also store the
+ *                  time-major returns (storage_dict['returns']); do_gae = 0: read returns_tm.
+ *      outputs env-major: rewards_em, values_em, returns_em, neglogp_em, adv_em (B) f32,
+ *      dones_em (B) u8, B = N*T.  adv_em = returns - values, NOT yet normalised.
+ *      partials: workspace of mnr_post_rollout_workspace_bytes(T,N) bytes holding per-CTA
+ *      (count, mean, M2) for adv / values / returns, consumed by mnr_post_rollout_finalize.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* src; /* (T,N,width) time-major */
+  float* dst;       /* (N*T,width) env-major  */
+  int32_t width;    /* floats per (t,n) */
+  int32_t _pad;
+} mnr_wide_field_t;
+
+#define MNR_MAX_WIDE_FIELDS 8
+
+size_t mnr_post_rollout_workspace_bytes(int T, int N);
+
+int mnr_post_rollout_fused(const mnr_wide_field_t* wide /*host*/, int n_wide,
+                           const float* rewards, const float* values, const uint8_t* dones,
+                           const float* neglogp, const float* last_values, float* returns_tm,
+                           float* rewards_em, float* values_em, float* returns_em, float* neglogp_em,
+                           uint8_t* dones_em, float* adv_em,
+                           int T, int N, int do_gae, float gamma, float gamma_tau,
+                           void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* Finalise: merge the per-CTA partials in index order (deterministic), then
+ *   adv   <- (adv - mean(adv)) / (std_unbiased(adv) + 1e-8)          (experience.py:119-120)
+ *   if value_mean != NULL (normalize_value):                          (ppo.py:177-181)
+ *     state.update(values); values <- normalize(values); state.update(returns);
+ *     returns <- normalize(returns)   with RunningMeanStd semantics (normalizers.py:44-68)
+ *   value state is updated IN PLACE.  clamp_lo > clamp_hi disables the clamp.
+ * stats_out (10 doubles, may be NULL): adv mean,std; values batch mean,var; returns batch mean,var;
+ *   state mean,var after 1st update; state mean,var after 2nd update. */
+int mnr_post_rollout_finalize(float* adv_em, float* values_em, float* returns_em, int64_t B,
+                              void* value_mean, void* value_var, void* value_count, int state_f64,
+                              float eps, float clamp_lo, float clamp_hi, double* stats_out,
+                              void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  RunningMeanStd.  Replaces mineral/common/normalizers.py:44-78.
+ * ------------------------------------------------------------------------------------ */
+size_t mnr_rms_moments_workspace_bytes(int64_t rows, int cols, int64_t group_rows);
+
+/* Per-column batch moments of x (rows, cols) f32 for each row group
+ * g = [g*group_rows, min((g+1)*group_rows, rows)):  mean_out/var_out (n_groups, cols) f32,
+ * var with `correction` (x.mean(0), x.var(0, correction), normalizers.py:58-59).
+ * Welford per thread, Chan merges in f64 in a fixed order (deterministic).
+ * Every `workspace` in this API must be zero-filled once before its first use; kernels leave the
+ * ticket counters they keep there at zero again. */
+int mnr_rms_batch_moments_f32(const float* x, int64_t rows, int cols, int64_t group_rows, int correction,
+                              float* mean_out, float* var_out, void* workspace, size_t workspace_bytes,
+                              mnr_stream_t stream);
+
+/* In-place Chan merge of one batch's moments into the running state, op-for-op the
+ * reference's _update_from_moments (normalizers.py:44-55) in the state dtype. */
+int mnr_rms_merge(void* mean, void* var, void* count, int state_f64, const float* batch_mean,
+                  const float* batch_var, double batch_count, int cols, mnr_stream_t stream);
+
+/* Pre-compute the whole normaliser schedule of one PPO update: for step s = 0..n_steps-1 merge
+ * row-group (s % n_groups)'s moments (as produced by mnr_rms_batch_moments_f32 with the same rows /
+ * group_rows; the last group may be short) into the state, exactly what obs_rms.update does once
+ * per minibatch (ppo.py:258-262), and record mean_tab/denom_tab (n_steps, cols) f32 =
+ * running_mean.float(), sqrt(running_var.float() + eps) after that step.  State updated in place. */
+int mnr_rms_schedule(void* mean, void* var, void* count, int state_f64, const float* group_mean,
+                     const float* group_var, int64_t group_rows, int64_t rows, int n_steps, int cols,
+                     float eps, float* mean_tab, float* denom_tab, mnr_stream_t stream);
+
+/* mean_f32/denom_f32 (cols) <- running_mean.float(), sqrt(running_var.float()+eps). */
+int mnr_rms_prepare(const void* mean, const void* var, int state_f64, int cols, float eps,
+                    float* mean_f32, float* denom_f32, mnr_stream_t stream);
+
+/* y = clamp((x - mean)/denom) (normalize, normalizers.py:65-68) or, inverse = 1,
+ * y = denom*clamp(x) + mean (unnormalize, :70-73).  x,y (rows, cols) f32, may alias.
+ * clamp_lo > clamp_hi disables the clamp. */
+int mnr_rms_apply_f32(const float* x, float* y, int64_t rows, int cols, const float* mean_f32,
+                      const float* denom_f32, float clamp_lo, float clamp_hi, int inverse,
+                      mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K3  indexed row movement: minibatch gather, replay insert / sample.
+ * ------------------------------------------------------------------------------------ */
+#define MNR_ROW_F32 0        /* copy f32 rows */
+#define MNR_ROW_U8 1         /* copy 1-byte rows (u8 / bool) */
+#define MNR_ROW_BOOL_TO_F32 2 /* src bool/u8 -> dst f32 (done.float(), simple_replay.py:84) */
+#define MNR_ROW_F32_TO_BOOL 3 /* src f32 -> dst bool (x != 0; dones.bool(), simple_replay.py:39) */
+#define MNR_ROW_F32_NORMALIZE 4 /* dst = clamp((src - mean)/denom), fused obs normalisation */
+
+typedef struct {
+  const void* src;
+  void* dst;
+  int32_t width;      /* elements per row */
+  int32_t kind;       /* MNR_ROW_* */
+  const float* mean;  /* kind 4 only */
+  const float* denom; /* kind 4 only */
+  float clamp_lo, clamp_hi;
+} mnr_row_field_t;
+
+#define MNR_MAX_ROW_FIELDS 12
+
+/* dst[i] = src[idx[i]] for every field, i < n_idx.  idx int64 in [0, src_rows).  Serves the
+ * PPO minibatch gather (identity / permutation index), CriticDataset.shuffle
+ * (mineral/agents/diffrl/utils.py:55-58) and ReplayBuffer.sample_batch
+ * (mineral/buffers/simple_replay.py:73-85).  idx == NULL means rows [row0, row0+n_idx). */
+int mnr_gather_rows(const mnr_row_field_t* fields /*host*/, int n_fields, const int64_t* idx,
+                    int64_t row0, int64_t n_idx, mnr_stream_t stream);
+
+/* dst[idx[i]] = src[i] (scatter; update_mu_sigma, experience.py:83-87). */
+int mnr_scatter_rows(const mnr_row_field_t* fields /*host*/, int n_fields, const int64_t* idx,
+                     int64_t row0, int64_t n_idx, mnr_stream_t stream);
+
+/* Ring insert with the reference's wrap rule (simple_replay.py:32-71): n_rows incoming rows at
+ * next_p into a ring of `capacity` rows; head [next_p,C) takes the first C-next_p rows, tail
+ * [0,p) takes the LAST p rows.  Pointer bookkeeping (next_p, if_full) stays on the host. */
+int mnr_replay_insert(const mnr_row_field_t* fields /*host*/, int n_fields, int64_t n_rows,
+                      int64_t next_p, int64_t capacity, mnr_stream_t stream);
+
+/* N-step FIFO push (mineral/buffers/nstep_replay.py:29-94) as a true window, no re-concatenation.
+ * in_*: (N,S,..) this call's transitions (obs/next_obs width O, action width A, reward 1, done 1).
+ * win_*_in: previous window (N,n,..) oldest first; win_*_out: window after the call (distinct memory).
+ * out_*: ((S-skip)*N, ..) step-major rows, skip = max(0, n-1-count_before) warm-up steps.
+ * gammas: (n) f32 = (float)(gamma**k). */
+typedef struct {
+  const float *obs, *act, *rew, *nobs;
+  const void* done;     /* u8/bool, or f32 when done_is_f32 (sac.py:150 keeps dones in a float tensor) */
+  int32_t done_is_f32;
+  int32_t _pad;
+} mnr_nstep_in_t;
+typedef struct {
+  float *obs, *act, *rew, *nobs;
+  uint8_t* done;
+} mnr_nstep_out_t;
+int mnr_nstep_push(const mnr_nstep_in_t* in /*host*/, const mnr_nstep_in_t* win_in /*host*/,
+                   const mnr_nstep_out_t* win_out /*host*/, const mnr_nstep_out_t* out /*host*/,
+                   const float* gammas, int N, int S, int O, int A, int nstep, int64_t count_before,
+                   mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K4  fused PPO loss forward + backward.  Replaces, per minibatch, Dist.forward + entropy +
+ *     neglogp (mineral/nets/dist.py:31-47, mineral/agents/ppo/models.py:93-108), actor_loss /
+ *     critic_loss / bounds_loss / policy_kl (ppo.py:449-498), the means and the total
+ *     (ppo.py:283-285), autograd's backward of all of it, and update_mu_sigma
+ *     (experience.py:83-87).
+ * ------------------------------------------------------------------------------------ */
+#define MNR_DIST_NORMAL 0
+#define MNR_DIST_DREAMERV3_NORMAL 1
+#define MNR_BOUNDS_BOUND 0
+#define MNR_BOUNDS_REG 1
+
+typedef struct {
+  int32_t dist_type;      /* MNR_DIST_* */
+  int32_t bounds_type;    /* MNR_BOUNDS_* */
+  int32_t use_smooth_clamp;
+  int32_t clip_value_loss;
+  float minstd, maxstd;   /* dreamerv3_normal */
+  float e_clip;
+  float critic_coef, entropy_coef, bounds_loss_coef;
+  float soft_bound;       /* 1.1 */
+  float grad_scale;       /* d(total)/d(loss): 1.0, or 1/world_size before a SUM gradient all-reduce */
+  float metric_scale;     /* metrics_out *= metric_scale (1.0, or 1/world_size before a SUM all-reduce) */
+  float _pad;
+} mnr_ppo_loss_cfg_t;
+
+#define MNR_PPO_METRICS 10
+/* metrics_out (MNR_PPO_METRICS f32): 0 total loss, 1 actor, 2 critic, 3 bounds, 4 entropy,
+ * 5 clip_frac, 6 explained_var, 7 kl(new||old), 8 mean(mu) [unused], 9 reserved. */
+
+size_t mnr_ppo_loss_workspace_bytes(int64_t mb, int A);
+
+/* Inputs (mb rows): mu_raw, logstd (mb,A) network outputs BEFORE Dist; logstd_row_stride = A, or 0
+ * when one (A) vector is shared by all rows (fixed sigma, models.py:151); value (mb);
+ * actions (mb,A); old_neglogp, advantages, old_values, returns (mb).
+ * old_mu / old_sigma (mb,A): read for the KL, then OVERWRITTEN with the fresh mu / sigma if
+ * write_back != 0.  Outputs: g_mu_raw, g_logstd (mb,A), g_value (mb) = d total / d input (means
+ * included); mu_mean_out/sigma_mean_out (A) column means of the fresh mu/sigma (may be NULL). */
+int mnr_ppo_loss_fwd_bwd(const float* mu_raw, const float* logstd, int logstd_row_stride,
+                         const float* value, const float* actions, const float* old_neglogp,
+                         const float* advantages, const float* old_values, const float* returns,
+                         float* old_mu, float* old_sigma, int write_back,
+                         float* g_mu_raw, float* g_logstd, float* g_value,
+                         float* metrics_out, float* mu_mean_out, float* sigma_mean_out,
+                         int64_t mb, int A, const mnr_ppo_loss_cfg_t* cfg /*host*/,
+                         void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* Un-reduced module-level twins of the reference's loss functions (ppo.py:453-498): per-row value
+ * and per-row derivative.  clip_count_out / ev_out single f32 (clip_frac, explained_var). */
+int mnr_actor_loss_rows(const float* old_neglogp, const float* neglogp, const float* advantages,
+                        int64_t n, float e_clip, int use_smooth_clamp, float* loss_out,
+                        float* dloss_dneglogp_out, float* clip_frac_out, void* workspace,
+                        size_t workspace_bytes, mnr_stream_t stream);
+int mnr_critic_loss_rows(const float* old_values, const float* values, const float* returns, int64_t n,
+                         float e_clip, int clip_value_loss, float* loss_out, float* dloss_dvalues_out,
+                         float* explained_var_out, void* workspace, size_t workspace_bytes,
+                         mnr_stream_t stream);
+int mnr_bounds_loss_rows(const float* mu, int64_t n, int A, int bounds_type, float soft_bound,
+                         float* loss_out, float* dloss_dmu_out, mnr_stream_t stream);
+int mnr_policy_kl_rows(const float* p0_mu, const float* p0_sigma, const float* p1_mu,
+                       const float* p1_sigma, int64_t n, int A, float* kl_rows_out, float* kl_mean_out,
+                       void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+size_t mnr_rows_reduce_workspace_bytes(int64_t n);
+
+/* ------------------------------------------------------------------------------------
+ * a12  gradient-norm clip + Adam/AdamW with DEVICE-resident learning rate and step count, and
+ *      the KL-adaptive LR rule (ppo.py:291-300,338-345; mineral/agents/ppo/utils.py:14-20), so
+ *      the optimizer step needs no host round trip and is CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  double lr;          /* current learning rate (Python double in the reference) */
+  double kl_sum;      /* running sum of per-step KL within the mini-epoch */
+  int32_t kl_count;
+  int32_t step;       /* Adam step count */
+  float grad_norm;    /* last total norm */
+  float clip_coef;    /* last clip coefficient (<= 1) */
+  float step_size;    /* lr / (1 - beta1^step) */
+  float bc2_sqrt;     /* sqrt(1 - beta2^step) */
+  float lr_f32;
+  float _pad;
+} mnr_optim_state_t;
+
+size_t mnr_grad_norm_workspace_bytes(int64_t n);
+
+/* total_norm = ||g||_2 (torch clip_grad_norm_), clip_coef = min(1, max_norm/(norm+1e-6)) (1 if
+ * max_norm <= 0), st->step += 1 and the Adam scalars for that step.  If kl != NULL its value is
+ * added to st->kl_sum (kl_count += 1).  grad_norm_out (f32, may be NULL) receives the norm. */
+int mnr_grad_norm_prepare(const float* grad, int64_t n, float max_norm, float beta1, float beta2,
+                          mnr_optim_state_t* st, const float* kl, float* grad_norm_out,
+                          void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* torch.optim.Adam (decoupled = 0: grad += wd*p) / AdamW (decoupled = 1: p *= 1 - lr*wd) single
+ * step over a flat parameter buffer; grads are scaled by st->clip_coef first; zero_grad != 0
+ * clears `grad` afterwards (optim.zero_grad, ppo.py:291). */
+int mnr_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float beta1,
+                  float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
+                  const mnr_optim_state_t* st, mnr_stream_t stream);
+
+/* End of a mini-epoch: avg_kl = kl_sum/kl_count (as f32); lr /= 1.5 if avg_kl > 2*thr (floor
+ * min_lr), lr *= 1.5 if avg_kl < thr/2 (cap max_lr); reset the KL accumulator.
+ * avg_kl_out / lr_out (f32 / f64 device, may be NULL) record the values for the host. */
+int mnr_kl_lr_update(mnr_optim_state_t* st, double kl_threshold, double min_lr, double max_lr,
+                     float* avg_kl_out, double* lr_out, mnr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MINERAL_B200_H */

@@ -1,0 +1,166 @@
+"""ctypes binding of the C-ABI library `libmineral_b200.so` (include/mineral_b200.h).
+
+Plumbing only: PyTorch owns device memory and streams; every compute call goes through the
+`mnr_*` entry points with raw device pointers.  There is NO fallback: if the library is missing
+the import fails, and if a tensor is not a contiguous CUDA tensor of the expected dtype the call
+raises.
+"""
+
+import ctypes as C
+import os
+import subprocess
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmineral_b200.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+c_f32p = C.c_void_p
+c_ptr = C.c_void_p
+
+
+class MineralB200Error(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile the CUDA sources for sm_100a into lib/libmineral_b200.so (nvcc cross-compiles on CPU)."""
+    out = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout[-4000:], out.stderr[-4000:])
+    if out.returncode != 0:
+        raise MineralB200Error("building libmineral_b200.so failed")
+    return LIB_PATH
+
+
+# ---- structs (mirror include/mineral_b200.h) ------------------------------------------------
+class WideField(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("_pad", C.c_int32)]
+
+
+class RowField(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("kind", C.c_int32),
+                ("mean", C.c_void_p), ("denom", C.c_void_p), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float)]
+
+
+class NStepIn(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("nobs", C.c_void_p),
+                ("done", C.c_void_p), ("done_is_f32", C.c_int32), ("_pad", C.c_int32)]
+
+
+class NStepOut(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("nobs", C.c_void_p), ("done", C.c_void_p)]
+
+
+class PPOLossCfg(C.Structure):
+    _fields_ = [("dist_type", C.c_int32), ("bounds_type", C.c_int32), ("use_smooth_clamp", C.c_int32),
+                ("clip_value_loss", C.c_int32), ("minstd", C.c_float), ("maxstd", C.c_float), ("e_clip", C.c_float),
+                ("critic_coef", C.c_float), ("entropy_coef", C.c_float), ("bounds_loss_coef", C.c_float),
+                ("soft_bound", C.c_float), ("grad_scale", C.c_float), ("metric_scale", C.c_float), ("_pad", C.c_float)]
+
+
+class OptimState(C.Structure):
+    _fields_ = [("lr", C.c_double), ("kl_sum", C.c_double), ("kl_count", C.c_int32), ("step", C.c_int32),
+                ("grad_norm", C.c_float), ("clip_coef", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
+                ("lr_f32", C.c_float), ("_pad", C.c_float)]
+
+
+ROW_F32, ROW_U8, ROW_BOOL_TO_F32, ROW_F32_TO_BOOL, ROW_F32_NORMALIZE = 0, 1, 2, 3, 4
+DIST_NORMAL, DIST_DREAMERV3_NORMAL = 0, 1
+BOUNDS_BOUND, BOUNDS_REG = 0, 1
+PPO_METRICS = 10
+MAX_WIDE_FIELDS, MAX_ROW_FIELDS = 8, 12
+
+i32, i64, f32, f64, sz, vp = C.c_int, C.c_int64, C.c_float, C.c_double, C.c_size_t, C.c_void_p
+
+# name -> (restype, argtypes); kept in one table so tests can check it against the header
+SIGNATURES = {
+    "mnr_abi_version": (i32, []),
+    "mnr_error_string": (C.c_char_p, [i32]),
+    "mnr_sm_count": (i32, []),
+    "mnr_gae_f32": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, vp]),
+    "mnr_critic_targets_f32": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, f32, i32, f32, f32, vp]),
+    "mnr_post_rollout_workspace_bytes": (sz, [i32, i32]),
+    "mnr_post_rollout_fused": (i32, [C.POINTER(WideField), i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, vp, sz, vp]),
+    "mnr_post_rollout_finalize": (i32, [vp, vp, vp, i64, vp, vp, vp, i32, f32, f32, f32, vp, vp, sz, vp]),
+    "mnr_rms_moments_workspace_bytes": (sz, [i64, i32, i64]),
+    "mnr_rms_batch_moments_f32": (i32, [vp, i64, i32, i64, i32, vp, vp, vp, sz, vp]),
+    "mnr_rms_merge": (i32, [vp, vp, vp, i32, vp, vp, f64, i32, vp]),
+    "mnr_rms_schedule": (i32, [vp, vp, vp, i32, vp, vp, i64, i64, i32, i32, f32, vp, vp, vp]),
+    "mnr_rms_prepare": (i32, [vp, vp, i32, i32, f32, vp, vp, vp]),
+    "mnr_rms_apply_f32": (i32, [vp, vp, i64, i32, vp, vp, f32, f32, i32, vp]),
+    "mnr_gather_rows": (i32, [C.POINTER(RowField), i32, vp, i64, i64, vp]),
+    "mnr_scatter_rows": (i32, [C.POINTER(RowField), i32, vp, i64, i64, vp]),
+    "mnr_replay_insert": (i32, [C.POINTER(RowField), i32, i64, i64, i64, vp]),
+    "mnr_nstep_push": (i32, [C.POINTER(NStepIn), C.POINTER(NStepIn), C.POINTER(NStepOut), C.POINTER(NStepOut), vp, i32, i32, i32, i32, i32, i64, vp]),
+    "mnr_ppo_loss_workspace_bytes": (sz, [i64, i32]),
+    "mnr_ppo_loss_fwd_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, C.POINTER(PPOLossCfg), vp, sz, vp]),
+    "mnr_actor_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "mnr_critic_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
+    "mnr_bounds_loss_rows": (i32, [vp, i64, i32, i32, f32, vp, vp, vp]),
+    "mnr_policy_kl_rows": (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp]),
+    "mnr_rows_reduce_workspace_bytes": (sz, [i64]),
+    "mnr_grad_norm_workspace_bytes": (sz, [i64]),
+    "mnr_grad_norm_prepare": (i32, [vp, i64, f32, f32, f32, vp, vp, vp, vp, sz, vp]),
+    "mnr_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, i32, vp, vp]),
+    "mnr_kl_lr_update": (i32, [vp, f64, f64, f64, vp, vp, vp]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: mineral_b200 has no CPU or eager fallback. Build it with "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C mineral_b200/csrc`)."
+        )
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if lib.mnr_abi_version() != 1:
+        raise ImportError("libmineral_b200.so ABI version mismatch; rebuild it")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise MineralB200Error(f"{what or 'mnr call'} failed: [{rc}] {lib.mnr_error_string(rc).decode()}")
+
+
+def stream():
+    """cudaStream_t of torch's current stream (so work is ordered with torch ops and graph capture)."""
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t, dtype=None, name="tensor", allow_none=False):
+    """Raw device pointer of a contiguous CUDA tensor; loud failure otherwise."""
+    if t is None:
+        if allow_none:
+            return None
+        raise MineralB200Error(f"{name} is None")
+    if not t.is_cuda:
+        raise MineralB200Error(f"{name} must be a CUDA tensor: mineral_b200 has no CPU path (got device {t.device})")
+    if not t.is_contiguous():
+        raise MineralB200Error(f"{name} must be contiguous")
+    if dtype is not None:
+        ok = t.dtype in dtype if isinstance(dtype, (tuple, list)) else t.dtype == dtype
+        if not ok:
+            raise MineralB200Error(f"{name} has dtype {t.dtype}, expected {dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+_WS = {}
+
+
+def workspace(key, nbytes, device):
+    """Zero-initialised persistent scratch (the kernels leave their ticket counters at zero)."""
+    k = (key, str(device))
+    t = _WS.get(k)
+    if t is None or t.numel() < nbytes:
+        t = torch.zeros(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _WS[k] = t
+    return t

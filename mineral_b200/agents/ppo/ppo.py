@@ -1,0 +1,556 @@
+"""PPO on the B200 kernels.  Mirrors mineral/agents/ppo/ppo.py:19-498: same constructor
+(`PPO(full_cfg, logdir=, accelerator=, datasets=, env=)`), same config keys
+(`full_cfg.agent.{network,ppo}` as in mineral/cfgs/agent/*.yaml), same methods
+(`train / eval / play_steps / train_epoch / model_act / set_train / set_eval / save / load`) and the
+same module-level loss functions, so `getattr(mineral_b200.agents, cfg.agent.algo)` drops in for
+`mineral.agents.PPO` (mineral/scripts/run.py:140-144).
+
+What runs where during an update (reference line -> here):
+  ppo.py:172-183 compute_return + prepare_training + value RMS -> ExperienceBuffer.compute_return_and_prepare
+                                                                  (mnr_post_rollout_fused + _finalize)
+  ppo.py:258-262 obs_rms.update + normalize per minibatch       -> mnr_rms_batch_moments_f32 once per rollout,
+                                                                  mnr_rms_schedule (all steps' statistics up
+                                                                  front), mnr_rms_apply_f32 per step
+  ppo.py:270     model(batch)                                    -> torch/cuBLAS GEMMs (library) up to the
+                                                                  pre-distribution heads
+  ppo.py:271-285,302-303,313 dist/entropy/neglogp/losses/KL/write-back -> mnr_ppo_loss_fwd_bwd (one kernel)
+  ppo.py:291-300 zero_grad/backward/clip/step                    -> autograd through the GEMMs, then
+                                                                  mnr_grad_norm_prepare + mnr_adam_step
+  ppo.py:335-345 avg_kl.item() + AdaptiveScheduler               -> mnr_kl_lr_update (device-resident lr)
+No value is read on the host inside `train_epoch` until the results are assembled at its end.
+"""
+
+import collections
+import os
+import re
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ..._native import PPO_METRICS
+from ...common import normalizers
+from ...common.reward_shaper import RewardShaper
+from ..agent import Agent, cfg_get
+from . import models
+from .experience import ExperienceBuffer
+from .utils import AdaptiveScheduler, LinearScheduler, adjust_learning_rate_cos
+
+
+class FusedAdam:
+    """Adam / AdamW over ONE flat f32 buffer with device-resident lr / step / clip coefficient.
+    Exposes `param_groups`, `state_dict()`, `load_state_dict()` in torch.optim.Adam's format so PPO
+    checkpoints (ppo.py:416-446) stay interchangeable."""
+
+    def __init__(self, params, decoupled, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, **unused):
+        self.params = list(params)
+        dev = self.params[0].device
+        self.decoupled = decoupled
+        self.betas, self.eps = betas, eps
+        self.weight_decay = (1e-2 if decoupled else 0.0) if weight_decay is None else weight_decay
+        sizes = [p.numel() for p in self.params]
+        self.offsets = [0]
+        for s in sizes:
+            self.offsets.append(self.offsets[-1] + ((s + 3) // 4) * 4)  # keep every tensor 16 B aligned
+        n = self.offsets[-1]
+        self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        self.state = ops.optim_state_tensor(lr, dev)
+        self.ws = torch.zeros(ops.lib.mnr_grad_norm_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        self.param_groups = [dict(lr=float(lr), betas=betas, eps=eps, weight_decay=self.weight_decay)]
+
+    def step(self, max_grad_norm, kl=None, grad_norm_out=None):
+        """clip_grad_norm_ + optimizer.step + zero_grad as two launches (no host sync)."""
+        ops.grad_norm_prepare(self.flat_grad, max_grad_norm, self.betas[0], self.betas[1], self.state, kl, grad_norm_out, self.ws)
+        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, self.decoupled, True, self.state)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+
+    def read_state(self):
+        return ops.read_optim_state(self.state)
+
+    def set_lr(self, lr):
+        st = self.read_state()
+        st.lr, st.lr_f32 = float(lr), float(lr)
+        self.state.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+        self.param_groups[0]['lr'] = float(lr)
+
+    def state_dict(self):
+        st = self.read_state()
+        state = {}
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            n = p.numel()
+            state[i] = dict(step=torch.tensor(float(st.step)), exp_avg=self.exp_avg[o:o + n].view_as(p).clone(),
+                            exp_avg_sq=self.exp_avg_sq[o:o + n].view_as(p).clone())
+        group = dict(self.param_groups[0], lr=st.lr, params=list(range(len(self.params))))
+        return dict(state=state, param_groups=[group])
+
+    def load_state_dict(self, sd):
+        step = 0
+        for i, (p, o) in enumerate(zip(self.params, self.offsets)):
+            s = sd['state'].get(i)
+            if s is None:
+                continue
+            n = p.numel()
+            self.exp_avg[o:o + n].copy_(s['exp_avg'].reshape(-1))
+            self.exp_avg_sq[o:o + n].copy_(s['exp_avg_sq'].reshape(-1))
+            step = int(s['step'])
+        st = self.read_state()
+        st.step = step
+        st.lr = st.lr_f32 = float(sd['param_groups'][0]['lr'])
+        self.state.copy_(torch.frombuffer(bytearray(bytes(st)), dtype=torch.uint8))
+        self.param_groups[0]['lr'] = st.lr
+
+
+class PPO(Agent):
+    r"""Proximal Policy Optimization."""
+
+    def __init__(self, full_cfg, **kwargs):
+        self.network_config = full_cfg.agent.network
+        self.ppo_config = full_cfg.agent.ppo
+        self.num_actors = self.ppo_config.num_actors
+        self.max_agent_steps = int(self.ppo_config.max_agent_steps)
+        super().__init__(full_cfg, **kwargs)
+        cfg = self.ppo_config
+        if cfg_get(full_cfg.agent, 'dapg', None) is not None or cfg_get(cfg, 'dapg', None) is not None:
+            raise NotImplementedError('DAPG needs demonstration datasets and is out of scope (SURVEY.md section 2 row 12)')
+        self.dapg_config = None
+
+        # --- Normalizers (ppo.py:29-43) ---
+        rms_config = dict(eps=1e-5, with_clamp=True, initial_count=1, dtype=torch.float64)
+        if self.normalize_input:
+            rms = {}
+            for k, v in self.obs_space.items():
+                rms[k] = normalizers.RunningMeanStd(v, **rms_config) if re.match(self.obs_rms_keys, k) else normalizers.Identity()
+            self.obs_rms = nn.ModuleDict(rms).to(self.device)
+        else:
+            self.obs_rms = None
+        self.value_rms = normalizers.RunningMeanStd((1,), **rms_config).to(self.device)
+
+        # --- Model (ppo.py:45-52) ---
+        ModelCls = getattr(models, cfg_get(self.network_config, 'actor_critic', 'ActorCritic'))
+        model_kwargs = cfg_get(self.network_config, 'actor_critic_kwargs', {})
+        self.model = ModelCls(self.obs_space, self.action_dim, encoder=cfg_get(self.network_config, 'encoder', None),
+                              encoder_kwargs=cfg_get(self.network_config, 'encoder_kwargs', None), **model_kwargs)
+        self.model.to(self.device)
+
+        # --- Optim (ppo.py:54-61): Adam / AdamW re-implemented over a flat buffer ---
+        optim_kwargs = dict(cfg_get(cfg, 'optim_kwargs', {}))
+        self.init_lr = float(optim_kwargs.get('lr', 3e-4))
+        self.last_lr = self.init_lr
+        optim_kwargs['lr'] = self.init_lr
+        if cfg.optim_type not in ('Adam', 'AdamW'):
+            raise NotImplementedError(f'optim_type {cfg.optim_type}: only Adam / AdamW have a fused kernel')
+        self.optim = FusedAdam(self.model.parameters(), decoupled=(cfg.optim_type == 'AdamW'), **optim_kwargs)
+
+        # --- PPO train params (ppo.py:63-76) ---
+        self.e_clip = cfg['e_clip']
+        self.use_smooth_clamp = cfg['use_smooth_clamp']
+        self.clip_value_loss = cfg['clip_value_loss']
+        self.entropy_coef = cfg['entropy_coef']
+        self.critic_coef = cfg['critic_coef']
+        self.bounds_loss_coef = cfg['bounds_loss_coef']
+        self.bounds_type = cfg['bounds_type']
+        self.gamma = cfg['gamma']
+        self.tau = cfg['tau']
+        self.truncate_grads = cfg['truncate_grads']
+        self.max_grad_norm = cfg['max_grad_norm']
+        self.value_bootstrap = cfg['value_bootstrap']
+        self.normalize_advantage = cfg['normalize_advantage']  # read but, as in the reference, never consulted
+        self.normalize_value = cfg['normalize_value']
+
+        # --- Collect params (ppo.py:78-83) ---
+        self.horizon_len = cfg['horizon_len']
+        self.batch_size = self.horizon_len * self.num_actors
+        self.minibatch_size = cfg['minibatch_size']
+        self.mini_epochs = cfg['mini_epochs']
+        assert self.batch_size % self.minibatch_size == 0 or 'train' not in cfg_get(full_cfg, 'run', 'train')
+
+        # --- LR schedule (ppo.py:85-93) ---
+        self.lr_schedule = cfg['lr_schedule']
+        self.min_lr, self.max_lr = cfg_get(cfg, 'min_lr', 1e-6), cfg_get(cfg, 'max_lr', 1e-2)
+        if self.lr_schedule == 'kl':
+            self.kl_threshold = cfg['kl_threshold']
+            self.scheduler = AdaptiveScheduler(self.kl_threshold, self.min_lr, self.max_lr)
+        elif self.lr_schedule == 'linear':
+            self.scheduler = LinearScheduler(self.init_lr, self.min_lr, cfg['max_agent_steps'])
+
+        # --- Storage (ppo.py:95-107) ---
+        self.obs, self.dones = None, None
+        self.storage = ExperienceBuffer(self.num_actors, self.horizon_len, self.batch_size, self.minibatch_size, self.obs_space,
+                                        self.action_dim, self.device, self.cpu_obs_keys)
+        self.reward_shaper = RewardShaper(**cfg['reward_shaper'])
+
+        # --- Multi-GPU: one process per GPU, torch.distributed (NCCL) ---
+        self.world = 1
+        if self.multi_gpu:
+            import torch.distributed as dist
+            assert dist.is_initialized(), 'multi_gpu=True needs torch.distributed initialised (torchrun)'
+            self.world = dist.get_world_size()
+        self._engine = None
+        self.use_cuda_graph = bool(cfg_get(cfg, 'cuda_graph', False))
+
+    # -------------------------------------------------------------------------------------------
+    def model_act(self, obs_dict, sample=True, **kwargs):
+        """ppo.py:125-131."""
+        if self.normalize_input:
+            obs_dict = {k: self.obs_rms[k].normalize(v) for k, v in obs_dict.items()}
+        out = self.model.act(obs_dict, sample=sample, **kwargs)
+        if self.normalize_value and sample:
+            out['values'] = self.value_rms.unnormalize(out['values'])
+        return out
+
+    @torch.no_grad()
+    def play_steps(self):
+        """ppo.py:133-183.  The rollout loop is the reference's (simulator-bound, SURVEY.md section 8f
+        row 1 is the next step); its tail is the fused post-rollout pass."""
+        for n in range(self.horizon_len):
+            if not self.env_autoresets and any(self.dones):
+                done_indices = torch.where(self.dones)[0].tolist()
+                obs_reset = self._convert_obs(self.env.reset_idx(done_indices))
+                for k, v in obs_reset.items():
+                    self.obs[k][done_indices] = v
+            model_out = self.model_act(self.obs)
+            self.storage.update_data('obses', n, self.obs)
+            for k in ['actions', 'neglogp', 'values', 'mu', 'sigma']:
+                self.storage.update_data(k, n, model_out[k])
+            actions = torch.clamp(model_out['actions'], -1.0, 1.0)
+            obs, r, self.dones, infos = self.env.step(actions)
+            self.obs = self._convert_obs(obs)
+            r, self.dones = torch.as_tensor(r, device=self.device), torch.as_tensor(self.dones, device=self.device)
+            rewards = r.reshape(-1, 1)
+            self.storage.update_data('dones', n, self.dones)
+            shaped_rewards = self.reward_shaper(rewards.clone())
+            if self.value_bootstrap and 'time_outs' in infos:
+                time_outs = torch.as_tensor(infos['time_outs'], device=self.device).reshape(-1, 1)
+                shaped_rewards += self.gamma * model_out['values'] * time_outs.float()
+            self.storage.update_data('rewards', n, shaped_rewards)
+            done_indices = torch.where(self.dones)[0].tolist()
+            self.metrics.update(self.epoch, self.env, self.obs, rewards.squeeze(-1), done_indices, infos)
+        self.metrics.flush_video(self.epoch)
+
+        last_values = self.model_act(self.obs)['values']
+        self.finish_rollout(last_values)
+
+    @torch.no_grad()
+    def finish_rollout(self, last_values):
+        """ppo.py:172-183 in one fused pass + one normalise pass."""
+        self.storage.compute_return_and_prepare(last_values, self.gamma, self.tau, self.value_rms if self.normalize_value else None)
+
+    def train(self):
+        """ppo.py:185-246 without the TensorBoard/W&B plumbing."""
+        self.obs = self._convert_obs(self.env.reset())
+        self.dones = torch.zeros((self.num_actors,), dtype=torch.bool, device=self.device)
+        while self.agent_steps < self.max_agent_steps:
+            self.epoch += 1
+            self.set_eval()
+            self.play_steps()
+            self.agent_steps += self.batch_size * self.world
+            self.set_train()
+            results = self.train_epoch()
+            self.storage.data_dict = None
+            if not self.multi_gpu or self.rank == 0:
+                metrics = {f'train_stats/{k}': torch.mean(torch.stack(v)).item() for k, v in results.items() if v[0].dim() == 0}
+                metrics['train_stats/last_lr'] = self.last_lr
+                metrics['train_scores/episode_rewards'] = self.metrics.episode_trackers['rewards'].mean()
+                metrics['train_scores/episode_lengths'] = self.metrics.episode_trackers['lengths'].mean()
+                self.writer.add(self.agent_steps, metrics)
+                self.writer.write()
+                self._checkpoint_save(metrics['train_scores/episode_rewards'])
+                if self.print_every > 0 and (self.epoch + 1) % self.print_every == 0:
+                    print(f'Epochs: {self.epoch + 1} | Agent Steps: {int(self.agent_steps):,} | '
+                          f'ep_rewards {metrics["train_scores/episode_rewards"]:.2f}')
+        self.save(os.path.join(self.ckpt_dir, 'final.pth'))
+
+    # -------------------------------------------------------------------------------------------
+    def train_epoch(self):
+        """ppo.py:248-350: mini_epochs x (B / minibatch) optimizer steps on the prepared data_dict."""
+        if self._engine is None:
+            self._engine = _UpdateEngine(self)
+        results = self._engine.run()
+        self.mini_epoch += self.mini_epochs
+        return results
+
+    def eval(self):
+        raise NotImplementedError('evaluation roll-outs are simulator-bound and out of scope of the update path')
+
+    def set_train(self):
+        self.model.train()
+
+    def set_eval(self):
+        self.model.eval()
+
+    def save(self, f):
+        """ppo.py:416-427, same keys."""
+        ckpt = {
+            'epoch': self.epoch,
+            'mini_epoch': self.mini_epoch,
+            'agent_steps': self.agent_steps,
+            'model': self.model.state_dict(),
+            'optim': self.optim.state_dict(),
+            'obs_rms': self.obs_rms.state_dict() if self.normalize_input else None,
+            'value_rms': self.value_rms.state_dict() if self.normalize_value else None,
+        }
+        torch.save(ckpt, f)
+
+    def load(self, f, ckpt_keys=''):
+        """ppo.py:429-446 (regex filter on the checkpoint keys)."""
+        ckpt = torch.load(f, map_location=self.device, weights_only=False)
+        for k in ('epoch', 'mini_epoch', 'agent_steps', 'model', 'optim', 'obs_rms', 'value_rms'):
+            if not re.match(ckpt_keys, k):
+                print(f'Warning: ckpt skipped loading `{k}`')
+                continue
+            if (k == 'obs_rms' and not self.normalize_input) or (k == 'value_rms' and not self.normalize_value):
+                continue
+            if hasattr(getattr(self, k), 'load_state_dict'):
+                getattr(self, k).load_state_dict(ckpt[k])
+            else:
+                setattr(self, k, ckpt[k])
+        self.last_lr = self.optim.param_groups[0]['lr']
+
+
+class _UpdateEngine:
+    """Pre-allocated buffers + the launch sequence of one PPO update (optionally one CUDA graph)."""
+
+    def __init__(self, agent):
+        a = self.a = agent
+        dev = a.device
+        self.mb, self.B, self.A = a.minibatch_size, a.batch_size, a.action_dim
+        self.num_mb = len(a.storage)
+        self.steps = a.mini_epochs * self.num_mb
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.metrics = torch.zeros(self.steps, PPO_METRICS, **f32)
+        self.mu_mean = torch.zeros(self.steps, self.A, **f32)
+        self.sigma_mean = torch.zeros(self.steps, self.A, **f32)
+        self.grad_norms = torch.zeros(self.steps, **f32)
+        self.avg_kl = torch.zeros(a.mini_epochs, **f32)
+        self.lr_out = torch.zeros(a.mini_epochs, dtype=torch.float64, device=dev)
+        self.g_mu = torch.zeros(self.mb, self.A, **f32)
+        self.g_ls = torch.zeros(self.mb, self.A, **f32)
+        self.g_v = torch.zeros(self.mb, 1, **f32)
+        self.loss_ws = ops.ppo_loss_workspace(self.mb, self.A, dev)
+        dk = a.model.dist
+        self.loss_cfg = ops.make_loss_cfg(
+            dist_type=dk.dist_type, minstd=dk.minstd, maxstd=dk.maxstd, e_clip=a.e_clip, use_smooth_clamp=a.use_smooth_clamp,
+            clip_value_loss=a.clip_value_loss, critic_coef=a.critic_coef, entropy_coef=a.entropy_coef,
+            bounds_loss_coef=a.bounds_loss_coef, bounds_type=a.bounds_type, grad_scale=1.0 / a.world, metric_scale=1.0 / a.world)
+        self.norm_keys = []
+        if a.normalize_input:
+            for k, shape in a.obs_space.items():
+                if not hasattr(a.obs_rms[k], 'running_mean'):
+                    continue
+                cols = a.obs_rms[k]._cols
+                self.norm_keys.append(k)
+                setattr(self, f'_n_{k}', dict(
+                    cols=cols, gm=torch.zeros(self.num_mb, cols, **f32), gv=torch.zeros(self.num_mb, cols, **f32),
+                    mean_tab=torch.zeros(self.steps, cols, **f32), denom_tab=torch.zeros(self.steps, cols, **f32),
+                    x=torch.zeros(self.mb, *shape, **f32), ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
+        self.graph = None
+        self._warm = 0
+
+    # ---- the launch sequence -------------------------------------------------------------------
+    def _enqueue(self):
+        a = self.a
+        d = a.storage.data_dict
+        mb = self.mb
+        # obs-RMS: per-minibatch moments once, then every step's statistics up front (ppo.py:258-262)
+        for k in self.norm_keys:
+            n, rms = getattr(self, f'_n_{k}'), a.obs_rms[k]
+            ops.rms_batch_moments(d['obses'][k].view(self.B, n['cols']), mb, rms.correction, n['ws'], n['gm'], n['gv'])
+            if a.world > 1:
+                self._merge_moments_across_ranks(n)
+            ops.rms_schedule(rms.running_mean, rms.running_var, rms.running_count, n['gm'], n['gv'], mb * a.world,
+                             self.B * a.world, self.steps, rms.eps, n['mean_tab'], n['denom_tab'])
+        max_norm = float(a.max_grad_norm) if a.truncate_grads else 0.0
+        step = 0
+        for ep in range(a.mini_epochs):
+            for i in range(self.num_mb):
+                s, e = i * mb, (i + 1) * mb
+                obs = {}
+                for k, v in d['obses'].items():
+                    if k in self.norm_keys:
+                        n, rms = getattr(self, f'_n_{k}'), a.obs_rms[k]
+                        clamp = tuple(rms.clamp_range) if rms.with_clamp else None
+                        obs[k] = ops.rms_apply(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, out=n['x'])
+                    else:
+                        obs[k] = v[s:e]
+                with torch.enable_grad():
+                    mu_raw, logstd, value = a.model._actor_critic(obs)
+                ops.ppo_loss_fwd_bwd(mu_raw.detach(), logstd.detach().contiguous(), value.detach(), d['actions'][s:e],
+                                     d['neglogp'][s:e], d['advantages'][s:e], d['values'][s:e], d['returns'][s:e],
+                                     d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls, self.g_v, self.metrics[step],
+                                     self.loss_cfg, self.loss_ws, True, self.mu_mean[step], self.sigma_mean[step])
+                torch.autograd.backward([mu_raw, logstd, value], [self.g_mu, self.g_ls, self.g_v])
+                if a.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(a.optim.flat_grad)     # grads were pre-scaled by 1/world in the loss kernel
+                    dist.all_reduce(self.metrics[step])    # metrics pre-scaled likewise
+                a.optim.step(max_norm, kl=self.metrics[step, 7:8], grad_norm_out=self.grad_norms[step:step + 1])
+                step += 1
+            if a.lr_schedule == 'kl':
+                ops.kl_lr_update(a.optim.state, a.kl_threshold, a.min_lr, a.max_lr, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
+            else:
+                # NaN threshold: both comparisons of the rule are false, so it only averages the KL and reports lr
+                ops.kl_lr_update(a.optim.state, float('nan'), 0.0, 1.0, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
+
+    def _merge_moments_across_ranks(self, n):
+        """Global minibatch i = union of the ranks' local minibatch i: combine the
+        per-rank (count, mean, var) with exact sufficient statistics in f64 (tiny, once per rollout)."""
+        import torch.distributed as dist
+        a = self.a
+        cnt = float(self.mb)
+        corr = float(a.obs_rms[self.norm_keys[0]].correction)
+        mean = n['gm'].double()
+        m2 = n['gv'].double() * (cnt - corr)
+        pack = torch.stack([mean * cnt, m2 + cnt * mean * mean])
+        dist.all_reduce(pack)
+        tot = cnt * a.world
+        gmean = pack[0] / tot
+        n['gm'].copy_(gmean.float())
+        n['gv'].copy_(((pack[1] - tot * gmean * gmean) / (tot - corr)).float())
+
+    def run(self):
+        a = self.a
+        if a.lr_schedule == 'cos':
+            raise NotImplementedError("lr_schedule 'cos' changes lr from the host every mini-epoch; use 'kl', 'linear' or 'fixed'")
+        with torch.no_grad():
+            if a.use_cuda_graph and a.world == 1:
+                if self.graph is None and self._warm >= 1:
+                    torch.cuda.synchronize()
+                    self.graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.graph):
+                        self._enqueue()
+                    # the capture itself did not execute anything; fall through to replay
+                if self.graph is not None:
+                    self.graph.replay()
+                else:
+                    self._enqueue()
+                    self._warm += 1
+            else:
+                self._enqueue()
+        return self._results()
+
+    def _results(self):
+        a = self.a
+        st = a.optim.read_state()  # the one device->host read of the update
+        a.last_lr = st.lr
+        a.optim.param_groups[0]['lr'] = st.lr
+        if a.lr_schedule == 'linear':
+            a.last_lr = a.scheduler.update(a.agent_steps)
+            a.optim.set_lr(a.last_lr)
+        m = self.metrics
+        res = collections.defaultdict(list)
+        names = ('loss/total', 'loss/actor', 'loss/critic', 'loss/bounds', 'loss/entropy', 'clip_frac', 'explained_var')
+        for s in range(self.steps):
+            for j, k in enumerate(names):
+                res[k].append(m[s, j])
+            res['kl'].append(m[s, 7])
+            # column means (1, A): torch.cat(...).mean(0) over them equals the reference's value
+            res['mu'].append(self.mu_mean[s:s + 1])
+            res['sigma'].append(self.sigma_mean[s:s + 1])
+            if a.truncate_grads:
+                res['grad_norm/all'].append(self.grad_norms[s])
+        for ep in range(a.mini_epochs):
+            res['avg_kl'].append(self.avg_kl[ep])
+        return res
+
+
+# -----------------------------------------------------------------------------------------------
+# Module-level loss functions with the reference's signatures (ppo.py:449-498), each a thin
+# autograd.Function over the per-row C-ABI kernels.
+# -----------------------------------------------------------------------------------------------
+def _rows_ws(n, dev):
+    from ..._native import lib, workspace
+    return workspace('rows_reduce', lib.mnr_rows_reduce_workspace_bytes(n), dev)
+
+
+class _ActorLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, old_nlp, nlp, adv, e_clip, smooth):
+        from ..._native import check, lib, ptr, stream
+        n = nlp.numel()
+        loss, d = torch.empty_like(nlp), torch.empty_like(nlp)
+        frac = torch.empty((), dtype=torch.float32, device=nlp.device)
+        ws = _rows_ws(n, nlp.device)
+        check(lib.mnr_actor_loss_rows(ptr(old_nlp.contiguous()), ptr(nlp.contiguous()), ptr(adv.contiguous()), n, e_clip,
+                                      int(bool(smooth)), ptr(loss), ptr(d), ptr(frac), ptr(ws), ws.numel(), stream()))
+        ctx.save_for_backward(d)
+        ctx.mark_non_differentiable(frac)
+        return loss, frac
+
+    @staticmethod
+    def backward(ctx, g_loss, g_frac):
+        (d,) = ctx.saved_tensors
+        return None, g_loss * d, None, None, None
+
+
+def actor_loss(old_action_log_probs, action_log_probs, advantage, e_clip, use_smooth_clamp):
+    return _ActorLoss.apply(old_action_log_probs, action_log_probs, advantage, e_clip, use_smooth_clamp)
+
+
+class _CriticLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value_preds, values, e_clip, returns, clip):
+        from ..._native import check, lib, ptr, stream
+        n = values.numel()
+        loss, d = torch.empty_like(values), torch.empty_like(values)
+        ev = torch.empty((), dtype=torch.float32, device=values.device)
+        ws = _rows_ws(n, values.device)
+        check(lib.mnr_critic_loss_rows(ptr(value_preds.contiguous()), ptr(values.contiguous()), ptr(returns.contiguous()), n,
+                                       e_clip, int(bool(clip)), ptr(loss), ptr(d), ptr(ev), ptr(ws), ws.numel(), stream()))
+        ctx.save_for_backward(d)
+        ctx.mark_non_differentiable(ev)
+        return loss, ev
+
+    @staticmethod
+    def backward(ctx, g_loss, g_ev):
+        (d,) = ctx.saved_tensors
+        return None, g_loss * d, None, None, None
+
+
+def critic_loss(value_preds, values, e_clip, returns, clip_value_loss):
+    return _CriticLoss.apply(value_preds, values, e_clip, returns, clip_value_loss)
+
+
+class _BoundsLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, btype, soft_bound):
+        from ..._native import check, lib, ptr, stream
+        n, A = mu.shape
+        loss = torch.empty(n, dtype=torch.float32, device=mu.device)
+        d = torch.empty_like(mu)
+        check(lib.mnr_bounds_loss_rows(ptr(mu.contiguous()), n, A, btype, soft_bound, ptr(loss), ptr(d), stream()))
+        ctx.save_for_backward(d)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d,) = ctx.saved_tensors
+        return g.unsqueeze(-1) * d, None, None
+
+
+def bounds_loss(mu, bounds_type, soft_bound=1.1):
+    bt = {'bound': 0, 'reg': 1}.get(bounds_type)
+    if bt is None:
+        raise NotImplementedError(bounds_type)
+    return _BoundsLoss.apply(mu, bt, soft_bound)
+
+
+@torch.no_grad()
+def policy_kl(p0_mu, p0_sigma, p1_mu, p1_sigma):
+    from ..._native import check, lib, ptr, stream
+    n, A = p0_mu.shape
+    out = torch.empty((), dtype=torch.float32, device=p0_mu.device)
+    ws = _rows_ws(n, p0_mu.device)
+    check(lib.mnr_policy_kl_rows(ptr(p0_mu.contiguous()), ptr(p0_sigma.contiguous()), ptr(p1_mu.contiguous()),
+                                 ptr(p1_sigma.contiguous()), n, A, None, ptr(out), ptr(ws), ws.numel(), stream()))
+    return out

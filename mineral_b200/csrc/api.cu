@@ -1,0 +1,31 @@
+// Host-side odds and ends of the C ABI.
+#include "common.cuh"
+
+extern "C" int mnr_abi_version(void) { return MNR_ABI_VERSION; }
+
+extern "C" const char* mnr_error_string(int code) {
+  switch (code) {
+    case MNR_OK: return "ok";
+    case MNR_ENULL: return "required pointer is NULL";
+    case MNR_ESHAPE: return "non-positive or unsupported size";
+    case MNR_EALIGN: return "pointer not aligned as the kernel needs";
+    case MNR_EUNSUP: return "unsupported mode";
+    case MNR_EWORKSPACE: return "workspace too small";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "unknown mineral_b200 error";
+}
+
+extern "C" int mnr_sm_count(void) {
+  static int cached = 0;
+  if (cached > 0) return cached;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess &&
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) {
+    cached = sms;
+    return sms;
+  }
+  (void)cudaGetLastError();  // no device (CPU-only build box): report the B200's count, do not cache
+  return 148;
+}

@@ -1,0 +1,133 @@
+// Shared device helpers for the mineral_b200 kernels (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mineral_b200.h"
+
+#define MNR_CHECK_PTR(p) \
+  do {                   \
+    if ((p) == nullptr) return MNR_ENULL; \
+  } while (0)
+
+#define MNR_LAUNCH_RESULT()                  \
+  do {                                       \
+    cudaError_t e__ = cudaPeekAtLastError(); \
+    return e__ == cudaSuccess ? MNR_OK : (int)e__; \
+  } while (0)
+
+static inline cudaStream_t mnr_cs(mnr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline bool mnr_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+__device__ __forceinline__ bool mnr_aligned_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+namespace mnr {
+
+constexpr int kWarp = 32;
+
+// separately-rounded arithmetic (no FMA contraction) in f32 / f64
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+// RunningMeanStd._update_from_moments (mineral/common/normalizers.py:44-55), op for op in the
+// state dtype S: batch moments arrive as f32 and are promoted, the count is a Python int.
+template <typename S>
+__device__ __forceinline__ void chan_update(S& mean, S& var, S count, float bmean, float bvar, double bcount) {
+  const S bm = (S)bmean, bv = (S)bvar, bc = (S)bcount;
+  const S delta = sub_rn(bm, mean);
+  const S tot = add_rn(count, bc);
+  const S new_mean = add_rn(mean, div_rn(mul_rn(delta, bc), tot));
+  const S m_a = mul_rn(var, count);
+  const S m_b = mul_rn(bv, bc);
+  const S m2 = add_rn(add_rn(m_a, m_b), div_rn(mul_rn(mul_rn(mul_rn(delta, delta), count), bc), tot));
+  mean = new_mean;
+  var = div_rn(m2, tot);
+}
+
+// ---- (count, mean, M2) moment triple with Chan's parallel merge -----------------------------
+struct Moments {
+  double n, mean, m2;
+};
+
+__device__ __forceinline__ Moments moments_merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const double d = b.mean - a.mean;
+  const double f = b.n / r.n;
+  r.mean = a.mean + d * f;
+  r.m2 = a.m2 + b.m2 + d * d * a.n * f;
+  return r;
+}
+
+__device__ __forceinline__ Moments moments_shfl_down(const Moments& m, int delta) {
+  Moments o;
+  o.n = __shfl_down_sync(0xffffffffu, m.n, delta);
+  o.mean = __shfl_down_sync(0xffffffffu, m.mean, delta);
+  o.m2 = __shfl_down_sync(0xffffffffu, m.m2, delta);
+  return o;
+}
+
+// warp-shuffle Chan merge: lane 0 ends with the merge of all 32 lanes, in a fixed tree order.
+__device__ __forceinline__ Moments moments_warp_reduce(Moments m) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = moments_merge(m, moments_shfl_down(m, d));
+  return m;
+}
+
+// f32 Welford accumulator (one thread's private stream of samples)
+struct Welford {
+  float n, mean, m2;
+  __device__ __forceinline__ void init() { n = 0.f, mean = 0.f, m2 = 0.f; }
+  __device__ __forceinline__ void push(float x) {
+    n += 1.f;
+    const float d = x - mean;
+    mean += __fdividef(d, n);
+    m2 = fmaf(d, x - mean, m2);
+  }
+  __device__ __forceinline__ Moments to_moments() const { return Moments{(double)n, (double)mean, (double)m2}; }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// "last block done" ticket: returns true in exactly one CTA (the last to arrive); that CTA may
+// then read every other CTA's global partials.  Counter must be zero before the launch and is
+// reset to zero by the winner so graphs can replay.
+__device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigned int n_blocks) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == n_blocks - 1);
+    if (is_last) *counter = 0u;
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// streaming global accessors (read-once / write-once data: keep L1 clean)
+__device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float* p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace mnr

@@ -1,0 +1,480 @@
+// K4  fused PPO loss forward + backward (one pass over a minibatch) and the un-reduced per-row
+// twins of the reference's module-level loss functions.
+// Replaces Dist.forward + entropy + neglogp (mineral/nets/dist.py:31-47,
+// mineral/agents/ppo/models.py:93-108), actor_loss / critic_loss / bounds_loss / policy_kl
+// (mineral/agents/ppo/ppo.py:449-498), the means + total (ppo.py:283-285), autograd's backward of
+// all of that, and update_mu_sigma (mineral/agents/ppo/experience.py:83-87).
+//
+// One thread per minibatch row; the A action columns of a row are contiguous, read as float4 when
+// A % 4 == 0 (a warp then covers 32 consecutive rows = one contiguous run per array).  Pass 1 sums
+// the row's neg-log-prob / entropy / bounds / KL, pass 2 (inputs now L1-resident) emits the
+// gradients, which need the row's probability ratio.  Scalars reduce warp-shuffle -> CTA -> f64
+// partials in the workspace -> last CTA (ticket) in a fixed order, so results are deterministic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
+constexpr int kHeader = 256;                             // ticket + padding
+constexpr int kMaxA = 64;
+
+struct LossPartial {
+  double a, c, b, h, clip, kl;
+  mnr::Moments d;    // returns - values
+  mnr::Moments ret;  // returns
+};
+
+__device__ __forceinline__ void dist_fwd(const mnr_ppo_loss_cfg_t& cfg, float mu_raw, float ls, float& mu, float& sigma,
+                                         float& dmu, float& dsigma) {
+  if (cfg.dist_type == MNR_DIST_NORMAL) {  // dist.py:32-34
+    mu = mu_raw, sigma = expf(ls), dmu = 1.f, dsigma = sigma;
+  } else {  // dreamerv3_normal, dist.py:42-47
+    const float s = 1.f / (1.f + expf(-(ls + 2.0f)));
+    const float span = cfg.maxstd - cfg.minstd;
+    mu = tanhf(mu_raw);
+    sigma = span * s + cfg.minstd;
+    dmu = 1.f - mu * mu;
+    dsigma = span * s * (1.f - s);
+  }
+}
+
+__device__ __forceinline__ float smooth_clamp(float x, float lo, float hi, float* dx) {
+  // ppo.py:449-450
+  const float s = 1.f / (1.f + expf((-(x - lo) / (hi - lo) + 0.5f) * 4.f));
+  *dx = 4.f * s * (1.f - s);
+  return s * (hi - lo) + lo;
+}
+
+// d max(a,b): weight of a (1, 0, or 0.5 on ties as torch.max/maximum backward does)
+__device__ __forceinline__ float max_weight(float a, float b) { return a > b ? 1.f : (a < b ? 0.f : 0.5f); }
+
+__device__ __forceinline__ float actor_row(float old_nlp, float nlp, float adv, float e_clip, int smooth, float* dloss_dnlp,
+                                           float* clipped) {
+  const float ratio = expf(old_nlp - nlp);
+  const float lo = 1.0f - e_clip, hi = 1.0f + e_clip;
+  float dclamp, cr;
+  if (smooth) cr = smooth_clamp(ratio, lo, hi, &dclamp);
+  else cr = fminf(fmaxf(ratio, lo), hi), dclamp = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
+  const float s1 = -(adv * ratio), s2 = -(adv * cr);
+  const float w1 = max_weight(s1, s2);
+  const float dl_dratio = -adv * (w1 + (1.f - w1) * dclamp);
+  *dloss_dnlp = -dl_dratio * ratio;
+  *clipped = fabsf(ratio - 1.0f) > e_clip ? 1.f : 0.f;
+  return fmaxf(s1, s2);
+}
+
+__device__ __forceinline__ float critic_row(float v_old, float v, float ret, float e_clip, int clip, float* dloss_dv) {
+  const float d1 = v - ret;
+  const float c1 = d1 * d1;
+  if (!clip) {
+    *dloss_dv = 2.f * d1;
+    return c1;
+  }
+  const float dv = v - v_old;
+  const float d2 = (v_old + fminf(fmaxf(dv, -e_clip), e_clip)) - ret;
+  const float c2 = d2 * d2;
+  const float w1 = max_weight(c1, c2);
+  const float inside = (dv >= -e_clip && dv <= e_clip) ? 1.f : 0.f;
+  *dloss_dv = w1 * 2.f * d1 + (1.f - w1) * 2.f * d2 * inside;
+  return fmaxf(c1, c2);
+}
+
+__device__ __forceinline__ float bounds_elem(float mu, int type, float soft, float* db) {
+  if (type == MNR_BOUNDS_REG) {
+    *db = 2.f * mu;
+    return mu * mu;
+  }
+  const float hi = fmaxf(mu - soft, 0.f), lo = fminf(mu + soft, 0.f);
+  *db = 2.f * hi + 2.f * lo;
+  return lo * lo + hi * hi;
+}
+
+__device__ __forceinline__ float kl_elem(float mu, float sigma, float mu_old, float sigma_old) {
+  // policy_kl(p0 = new, p1 = old), ppo.py:492-497
+  const float dm = mu_old - mu;
+  return logf(sigma_old / sigma + 1e-5f) + (sigma * sigma + dm * dm) / (2.0f * (sigma_old * sigma_old + 1e-5f)) - 0.5f;
+}
+
+template <int VEC>
+struct Vec;
+template <>
+struct Vec<1> {
+  float v[1];
+  __device__ __forceinline__ void load(const float* p) { v[0] = __ldg(p); }
+  __device__ __forceinline__ void load_rw(const float* p) { v[0] = *p; }  // memory this kernel also writes
+  __device__ __forceinline__ void store(float* p) const { p[0] = v[0]; }
+};
+template <>
+struct Vec<4> {
+  float v[4];
+  __device__ __forceinline__ void load(const float* p) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ __forceinline__ void load_rw(const float* p) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(kThreads) ppo_loss_kernel(
+    const float* __restrict__ mu_raw, const float* __restrict__ logstd, int ls_stride, const float* __restrict__ value,
+    const float* __restrict__ actions, const float* __restrict__ old_nlp, const float* __restrict__ adv,
+    const float* __restrict__ old_values, const float* __restrict__ returns, float* __restrict__ old_mu,
+    float* __restrict__ old_sigma, int write_back, float* __restrict__ g_mu_raw, float* __restrict__ g_logstd,
+    float* __restrict__ g_value, float* __restrict__ metrics_out, float* __restrict__ mu_mean_out,
+    float* __restrict__ sigma_mean_out, int64_t mb, int A, mnr_ppo_loss_cfg_t cfg, unsigned char* __restrict__ workspace) {
+  __shared__ float s_col[2 * kMaxA];
+  __shared__ double s_red[6][kThreads / 32];
+  __shared__ mnr::Moments s_mom[2][kThreads / 32];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int j = tid; j < 2 * A; j += kThreads) s_col[j] = 0.f;
+  __syncthreads();
+
+  const float w = cfg.grad_scale / (float)mb;
+  float t_a = 0.f, t_c = 0.f, t_b = 0.f, t_h = 0.f, t_clip = 0.f, t_kl = 0.f;
+  mnr::Welford w_d, w_ret;
+  w_d.init(), w_ret.init();
+
+  for (int64_t row0 = (int64_t)blockIdx.x * kThreads; row0 < mb; row0 += (int64_t)gridDim.x * kThreads) {
+    // warp-uniform trip count (shuffles below need all 32 lanes); out-of-range lanes redo the last row
+    const bool valid = row0 + tid < mb;
+    const int64_t row = valid ? row0 + tid : mb - 1;
+    const size_t base = (size_t)row * A;
+    const float* ls_row = logstd + (size_t)row * ls_stride;
+    // ---- pass 1: row sums ------------------------------------------------------------------
+    float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
+    for (int j = 0; j < A; j += VEC) {
+      Vec<VEC> m, l, a, om, os;
+      m.load(mu_raw + base + j), l.load(ls_row + j), a.load(actions + base + j);
+      om.load_rw(old_mu + base + j), os.load_rw(old_sigma + base + j);
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        float mu, sg, dmu, dsg, db;
+        dist_fwd(cfg, m.v[u], l.v[u], mu, sg, dmu, dsg);
+        const float diff = a.v[u] - mu;
+        const float lsg = logf(sg);
+        nlp += diff * diff / (2.f * sg * sg) + lsg + kLogSqrt2Pi;  // -Normal.log_prob
+        ent += 0.5f + kLogSqrt2Pi + lsg;                           // Normal.entropy
+        bsum += bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
+        kl += kl_elem(mu, sg, om.v[u], os.v[u]);
+      }
+    }
+    float dl_dnlp, clipped, dl_dv;
+    const float advr = __ldg(adv + row), ret = __ldg(returns + row), v = __ldg(value + row);
+    const float a_loss = actor_row(__ldg(old_nlp + row), nlp, advr, cfg.e_clip, cfg.use_smooth_clamp, &dl_dnlp, &clipped);
+    const float c_loss = critic_row(__ldg(old_values + row), v, ret, cfg.e_clip, cfg.clip_value_loss, &dl_dv);
+    if (valid) {
+      t_a += a_loss, t_c += c_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
+      w_d.push(ret - v), w_ret.push(ret);
+      g_value[row] = w * 0.5f * cfg.critic_coef * dl_dv;
+    }
+    const float g_nlp = w * dl_dnlp;
+    __syncwarp();  // pass 1 of every lane has read old_mu/old_sigma before any lane overwrites them
+    // ---- pass 2: gradients, write-back, column sums -------------------------------------------
+    for (int j = 0; j < A; j += VEC) {
+      Vec<VEC> m, l, a, gm, gl, nm, ns;
+      m.load(mu_raw + base + j), l.load(ls_row + j), a.load(actions + base + j);
+#pragma unroll
+      for (int u = 0; u < VEC; ++u) {
+        float mu, sg, dmu, dsg, db;
+        dist_fwd(cfg, m.v[u], l.v[u], mu, sg, dmu, dsg);
+        const float diff = a.v[u] - mu;
+        const float inv_var = 1.f / (sg * sg);
+        bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
+        const float g_mu = g_nlp * (-diff * inv_var) + w * cfg.bounds_loss_coef * db;
+        const float g_sg = g_nlp * (1.f - diff * diff * inv_var) / sg - w * cfg.entropy_coef / sg;
+        gm.v[u] = g_mu * dmu, gl.v[u] = g_sg * dsg;
+        nm.v[u] = mu, ns.v[u] = sg;
+        const float cm = mnr::warp_sum(valid ? mu : 0.f), cs = mnr::warp_sum(valid ? sg : 0.f);
+        if (lane == 0) atomicAdd(&s_col[j + u], cm), atomicAdd(&s_col[A + j + u], cs);
+      }
+      if (valid) {
+        gm.store(g_mu_raw + base + j), gl.store(g_logstd + base + j);
+        if (write_back) nm.store(old_mu + base + j), ns.store(old_sigma + base + j);
+      }
+    }
+  }
+
+  // ---- CTA reduction ---------------------------------------------------------------------------
+  float vals[6] = {t_a, t_c, t_b, t_h, t_clip, t_kl};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const float s = mnr::warp_sum(vals[k]);
+    if (lane == 0) s_red[k][warp] = (double)s;
+  }
+  const mnr::Moments md = mnr::moments_warp_reduce(w_d.to_moments());
+  const mnr::Moments mr = mnr::moments_warp_reduce(w_ret.to_moments());
+  if (lane == 0) s_mom[0][warp] = md, s_mom[1][warp] = mr;
+  __syncthreads();
+  LossPartial* parts = reinterpret_cast<LossPartial*>(workspace + kHeader);
+  float* col_parts = reinterpret_cast<float*>(workspace + kHeader + sizeof(LossPartial) * gridDim.x);
+  if (tid == 0) {
+    LossPartial p;
+    double acc[6];
+    for (int k = 0; k < 6; ++k) {
+      acc[k] = 0;
+      for (int x = 0; x < kThreads / 32; ++x) acc[k] += s_red[k][x];
+    }
+    p.a = acc[0], p.c = acc[1], p.b = acc[2], p.h = acc[3], p.clip = acc[4], p.kl = acc[5];
+    p.d = s_mom[0][0], p.ret = s_mom[1][0];
+    for (int x = 1; x < kThreads / 32; ++x) p.d = mnr::moments_merge(p.d, s_mom[0][x]), p.ret = mnr::moments_merge(p.ret, s_mom[1][x]);
+    parts[blockIdx.x] = p;
+  }
+  for (int j = tid; j < 2 * A; j += kThreads) col_parts[(size_t)blockIdx.x * 2 * A + j] = s_col[j];
+
+  if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return;
+  if (tid == 0) {
+    LossPartial t = parts[0];
+    for (unsigned int x = 1; x < gridDim.x; ++x) {
+      const LossPartial& p = parts[x];
+      t.a += p.a, t.c += p.c, t.b += p.b, t.h += p.h, t.clip += p.clip, t.kl += p.kl;
+      t.d = mnr::moments_merge(t.d, p.d), t.ret = mnr::moments_merge(t.ret, p.ret);
+    }
+    const double n = (double)mb;
+    const float a = (float)(t.a / n), c = (float)(t.c / n), b = (float)(t.b / n), h = (float)(t.h / n);
+    // ppo.py:285
+    metrics_out[0] = a + 0.5f * c * cfg.critic_coef - h * cfg.entropy_coef + b * cfg.bounds_loss_coef;
+    metrics_out[1] = a, metrics_out[2] = c, metrics_out[3] = b, metrics_out[4] = h;
+    metrics_out[5] = (float)(t.clip / n);
+    const float var_d = (float)(t.d.m2 / (t.d.n - 1.0)), var_r = (float)(t.ret.m2 / (t.ret.n - 1.0));
+    metrics_out[6] = fminf(fmaxf(1.f - var_d / (var_r + 1e-8f), 0.f), 1.f);  // ppo.py:475
+    metrics_out[7] = (float)(t.kl / n);
+    metrics_out[8] = 0.f, metrics_out[9] = 0.f;
+    for (int k = 0; k < MNR_PPO_METRICS; ++k) metrics_out[k] *= cfg.metric_scale;
+  }
+  if (mu_mean_out && sigma_mean_out) {
+    for (int j = tid; j < 2 * A; j += kThreads) {
+      double s = 0;
+      for (unsigned int x = 0; x < gridDim.x; ++x) s += (double)col_parts[(size_t)x * 2 * A + j];
+      const float mean = (float)(s / (double)mb);
+      if (j < A) mu_mean_out[j] = mean;
+      else sigma_mean_out[j - A] = mean;
+    }
+  }
+}
+
+int loss_grid(int64_t mb) {
+  int64_t g = (mb + kThreads - 1) / kThreads;
+  const int64_t cap = (int64_t)mnr_sm_count() * 4;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+// ---- generic "rows -> scalar" helpers for the module-level twins -------------------------------------
+constexpr int kRowThreads = 256;
+
+struct RowsPartial {
+  double s;
+  mnr::Moments m0, m1;
+};
+
+// true (in every thread of the block) only in the last CTA to finish; there thread 0 gets the totals
+__device__ bool block_finish(double my_sum, const mnr::Welford& w0, const mnr::Welford& w1, unsigned char* workspace,
+                             RowsPartial* total) {
+  __shared__ double s_s[kRowThreads / 32];
+  __shared__ mnr::Moments s_m[2][kRowThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double s = mnr::warp_sum(my_sum);
+  const mnr::Moments a = mnr::moments_warp_reduce(w0.to_moments()), b = mnr::moments_warp_reduce(w1.to_moments());
+  if (lane == 0) s_s[warp] = s, s_m[0][warp] = a, s_m[1][warp] = b;
+  __syncthreads();
+  RowsPartial* parts = reinterpret_cast<RowsPartial*>(workspace + kHeader);
+  if (threadIdx.x == 0) {
+    RowsPartial p{s_s[0], s_m[0][0], s_m[1][0]};
+    for (int x = 1; x < kRowThreads / 32; ++x) {
+      p.s += s_s[x];
+      p.m0 = mnr::moments_merge(p.m0, s_m[0][x]), p.m1 = mnr::moments_merge(p.m1, s_m[1][x]);
+    }
+    parts[blockIdx.x] = p;
+  }
+  if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return false;
+  if (threadIdx.x == 0) {
+    RowsPartial t = parts[0];
+    for (unsigned int x = 1; x < gridDim.x; ++x) {
+      t.s += parts[x].s;
+      t.m0 = mnr::moments_merge(t.m0, parts[x].m0), t.m1 = mnr::moments_merge(t.m1, parts[x].m1);
+    }
+    *total = t;
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(kRowThreads) actor_rows_kernel(const float* __restrict__ old_nlp,
+                                                                 const float* __restrict__ nlp,
+                                                                 const float* __restrict__ adv, int64_t n, float e_clip,
+                                                                 int smooth, float* __restrict__ loss,
+                                                                 float* __restrict__ dloss, float* __restrict__ clip_frac,
+                                                                 unsigned char* __restrict__ workspace) {
+  double cnt = 0;
+  mnr::Welford z0, z1;
+  z0.init(), z1.init();
+  for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRowThreads) {
+    float d, c;
+    loss[i] = actor_row(old_nlp[i], nlp[i], adv[i], e_clip, smooth, &d, &c);
+    if (dloss) dloss[i] = d;
+    cnt += c;
+  }
+  RowsPartial t;
+  const bool won = block_finish(cnt, z0, z1, workspace, &t);
+  if (won && threadIdx.x == 0 && clip_frac) *clip_frac = (float)(t.s / (double)n);
+}
+
+__global__ void __launch_bounds__(kRowThreads) critic_rows_kernel(const float* __restrict__ v_old,
+                                                                  const float* __restrict__ v,
+                                                                  const float* __restrict__ ret, int64_t n, float e_clip,
+                                                                  int clip, float* __restrict__ loss,
+                                                                  float* __restrict__ dloss, float* __restrict__ ev,
+                                                                  unsigned char* __restrict__ workspace) {
+  mnr::Welford wd, wr;
+  wd.init(), wr.init();
+  for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRowThreads) {
+    float d;
+    loss[i] = critic_row(v_old[i], v[i], ret[i], e_clip, clip, &d);
+    if (dloss) dloss[i] = d;
+    wd.push(ret[i] - v[i]), wr.push(ret[i]);
+  }
+  RowsPartial t;
+  const bool won = block_finish(0.0, wd, wr, workspace, &t);
+  if (won && threadIdx.x == 0 && ev) {
+    const float var_d = (float)(t.m0.m2 / (t.m0.n - 1.0)), var_r = (float)(t.m1.m2 / (t.m1.n - 1.0));
+    *ev = fminf(fmaxf(1.f - var_d / (var_r + 1e-8f), 0.f), 1.f);
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads) bounds_rows_kernel(const float* __restrict__ mu, int64_t n, int A, int type,
+                                                                  float soft, float* __restrict__ loss,
+                                                                  float* __restrict__ dmu) {
+  for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRowThreads) {
+    float s = 0.f;
+    for (int j = 0; j < A; ++j) {
+      float d;
+      s += bounds_elem(mu[i * A + j], type, soft, &d);
+      if (dmu) dmu[i * A + j] = d;
+    }
+    loss[i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kRowThreads) kl_rows_kernel(const float* __restrict__ p0_mu,
+                                                              const float* __restrict__ p0_sigma,
+                                                              const float* __restrict__ p1_mu,
+                                                              const float* __restrict__ p1_sigma, int64_t n, int A,
+                                                              float* __restrict__ kl_rows, float* __restrict__ kl_mean,
+                                                              unsigned char* __restrict__ workspace) {
+  double acc = 0;
+  mnr::Welford z0, z1;
+  z0.init(), z1.init();
+  for (int64_t i = (int64_t)blockIdx.x * kRowThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kRowThreads) {
+    float s = 0.f;
+    for (int j = 0; j < A; ++j) s += kl_elem(p0_mu[i * A + j], p0_sigma[i * A + j], p1_mu[i * A + j], p1_sigma[i * A + j]);
+    if (kl_rows) kl_rows[i] = s;
+    acc += s;
+  }
+  RowsPartial t;
+  const bool won = block_finish(acc, z0, z1, workspace, &t);
+  if (won && threadIdx.x == 0 && kl_mean) *kl_mean = (float)(t.s / (double)n);
+}
+
+int rows_grid(int64_t n) {
+  int64_t g = (n + kRowThreads - 1) / kRowThreads;
+  const int64_t cap = (int64_t)mnr_sm_count() * 4;
+  if (g > cap) g = cap;
+  return (int)(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+extern "C" size_t mnr_ppo_loss_workspace_bytes(int64_t mb, int A) {
+  if (mb <= 0 || A <= 0) return 0;
+  const size_t grid = (size_t)mnr_sm_count() * 4;
+  return kHeader + grid * (sizeof(LossPartial) + sizeof(float) * 2 * (size_t)A);
+}
+
+extern "C" int mnr_ppo_loss_fwd_bwd(const float* mu_raw, const float* logstd, int logstd_row_stride, const float* value,
+                                    const float* actions, const float* old_neglogp, const float* advantages,
+                                    const float* old_values, const float* returns, float* old_mu, float* old_sigma,
+                                    int write_back, float* g_mu_raw, float* g_logstd, float* g_value, float* metrics_out,
+                                    float* mu_mean_out, float* sigma_mean_out, int64_t mb, int A,
+                                    const mnr_ppo_loss_cfg_t* cfg, void* workspace, size_t workspace_bytes,
+                                    mnr_stream_t stream) {
+  MNR_CHECK_PTR(mu_raw); MNR_CHECK_PTR(logstd); MNR_CHECK_PTR(value); MNR_CHECK_PTR(actions); MNR_CHECK_PTR(old_neglogp);
+  MNR_CHECK_PTR(advantages); MNR_CHECK_PTR(old_values); MNR_CHECK_PTR(returns); MNR_CHECK_PTR(old_mu); MNR_CHECK_PTR(old_sigma);
+  MNR_CHECK_PTR(g_mu_raw); MNR_CHECK_PTR(g_logstd); MNR_CHECK_PTR(g_value); MNR_CHECK_PTR(metrics_out); MNR_CHECK_PTR(cfg);
+  MNR_CHECK_PTR(workspace);
+  if (mb <= 0 || A <= 0 || A > kMaxA) return MNR_ESHAPE;
+  if (logstd_row_stride != 0 && logstd_row_stride != A) return MNR_ESHAPE;
+  if (cfg->dist_type != MNR_DIST_NORMAL && cfg->dist_type != MNR_DIST_DREAMERV3_NORMAL) return MNR_EUNSUP;
+  if (cfg->bounds_type != MNR_BOUNDS_BOUND && cfg->bounds_type != MNR_BOUNDS_REG) return MNR_EUNSUP;
+  if (workspace_bytes < mnr_ppo_loss_workspace_bytes(mb, A)) return MNR_EWORKSPACE;
+  if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
+  const bool vec4 = (A % 4 == 0) && mnr_aligned(mu_raw, 16) && mnr_aligned(logstd, 16) && mnr_aligned(actions, 16) &&
+                    mnr_aligned(old_mu, 16) && mnr_aligned(old_sigma, 16) && mnr_aligned(g_mu_raw, 16) &&
+                    mnr_aligned(g_logstd, 16);
+  const int grid = loss_grid(mb);
+  if (vec4)
+    ppo_loss_kernel<4><<<grid, kThreads, 0, mnr_cs(stream)>>>(
+        mu_raw, logstd, logstd_row_stride, value, actions, old_neglogp, advantages, old_values, returns, old_mu,
+        old_sigma, write_back, g_mu_raw, g_logstd, g_value, metrics_out, mu_mean_out, sigma_mean_out, mb, A, *cfg,
+        (unsigned char*)workspace);
+  else
+    ppo_loss_kernel<1><<<grid, kThreads, 0, mnr_cs(stream)>>>(
+        mu_raw, logstd, logstd_row_stride, value, actions, old_neglogp, advantages, old_values, returns, old_mu,
+        old_sigma, write_back, g_mu_raw, g_logstd, g_value, metrics_out, mu_mean_out, sigma_mean_out, mb, A, *cfg,
+        (unsigned char*)workspace);
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" size_t mnr_rows_reduce_workspace_bytes(int64_t n) {
+  (void)n;
+  return kHeader + (size_t)mnr_sm_count() * 4 * sizeof(RowsPartial);
+}
+
+extern "C" int mnr_actor_loss_rows(const float* old_neglogp, const float* neglogp, const float* advantages, int64_t n,
+                                   float e_clip, int use_smooth_clamp, float* loss_out, float* dloss_dneglogp_out,
+                                   float* clip_frac_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
+  MNR_CHECK_PTR(old_neglogp); MNR_CHECK_PTR(neglogp); MNR_CHECK_PTR(advantages); MNR_CHECK_PTR(loss_out); MNR_CHECK_PTR(workspace);
+  if (n <= 0) return MNR_ESHAPE;
+  if (workspace_bytes < mnr_rows_reduce_workspace_bytes(n)) return MNR_EWORKSPACE;
+  actor_rows_kernel<<<rows_grid(n), kRowThreads, 0, mnr_cs(stream)>>>(old_neglogp, neglogp, advantages, n, e_clip,
+                                                                      use_smooth_clamp, loss_out, dloss_dneglogp_out,
+                                                                      clip_frac_out, (unsigned char*)workspace);
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_critic_loss_rows(const float* old_values, const float* values, const float* returns, int64_t n,
+                                    float e_clip, int clip_value_loss, float* loss_out, float* dloss_dvalues_out,
+                                    float* explained_var_out, void* workspace, size_t workspace_bytes,
+                                    mnr_stream_t stream) {
+  MNR_CHECK_PTR(old_values); MNR_CHECK_PTR(values); MNR_CHECK_PTR(returns); MNR_CHECK_PTR(loss_out); MNR_CHECK_PTR(workspace);
+  if (n <= 0) return MNR_ESHAPE;
+  if (workspace_bytes < mnr_rows_reduce_workspace_bytes(n)) return MNR_EWORKSPACE;
+  critic_rows_kernel<<<rows_grid(n), kRowThreads, 0, mnr_cs(stream)>>>(old_values, values, returns, n, e_clip,
+                                                                       clip_value_loss, loss_out, dloss_dvalues_out,
+                                                                       explained_var_out, (unsigned char*)workspace);
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_bounds_loss_rows(const float* mu, int64_t n, int A, int bounds_type, float soft_bound, float* loss_out,
+                                    float* dloss_dmu_out, mnr_stream_t stream) {
+  MNR_CHECK_PTR(mu); MNR_CHECK_PTR(loss_out);
+  if (n <= 0 || A <= 0) return MNR_ESHAPE;
+  if (bounds_type != MNR_BOUNDS_BOUND && bounds_type != MNR_BOUNDS_REG) return MNR_EUNSUP;
+  bounds_rows_kernel<<<rows_grid(n), kRowThreads, 0, mnr_cs(stream)>>>(mu, n, A, bounds_type, soft_bound, loss_out,
+                                                                       dloss_dmu_out);
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_policy_kl_rows(const float* p0_mu, const float* p0_sigma, const float* p1_mu, const float* p1_sigma,
+                                  int64_t n, int A, float* kl_rows_out, float* kl_mean_out, void* workspace,
+                                  size_t workspace_bytes, mnr_stream_t stream) {
+  MNR_CHECK_PTR(p0_mu); MNR_CHECK_PTR(p0_sigma); MNR_CHECK_PTR(p1_mu); MNR_CHECK_PTR(p1_sigma); MNR_CHECK_PTR(workspace);
+  if (n <= 0 || A <= 0) return MNR_ESHAPE;
+  if (workspace_bytes < mnr_rows_reduce_workspace_bytes(n)) return MNR_EWORKSPACE;
+  kl_rows_kernel<<<rows_grid(n), kRowThreads, 0, mnr_cs(stream)>>>(p0_mu, p0_sigma, p1_mu, p1_sigma, n, A, kl_rows_out,
+                                                                   kl_mean_out, (unsigned char*)workspace);
+  MNR_LAUNCH_RESULT();
+}

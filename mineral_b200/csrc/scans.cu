@@ -1,0 +1,101 @@
+// K1a GAE and K1b SHAC/SAPO critic-target reverse scans over the horizon, parallel across envs.
+// One lane per environment: at every step t a warp reads 32 consecutive envs of the time-major
+// (T,N) arrays (one 128 B line per array), so every sector fetched is fully used.  The scan's
+// loop-carried dependency is arithmetic only; loads of later steps are independent and are
+// batched by the unrolled loop.  All arithmetic uses explicit round-to-nearest intrinsics so
+// nvcc cannot contract a*b+c into an FMA: the reference rounds after every op and the result
+// must be bit-exact.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kScanThreads = 128;
+
+// mineral/agents/ppo/experience.py:96-108
+__global__ void __launch_bounds__(kScanThreads) gae_kernel(const float* __restrict__ rewards,
+                                                            const float* __restrict__ values,
+                                                            const uint8_t* __restrict__ dones,
+                                                            const float* __restrict__ last_values,
+                                                            float* __restrict__ returns,
+                                                            float* __restrict__ advantages, int T, int N,
+                                                            float gamma, float gamma_tau) {
+  const int n = blockIdx.x * kScanThreads + threadIdx.x;
+  if (n >= N) return;
+  float next_v = last_values[n];
+  float carry = 0.f;
+#pragma unroll 8
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * N + n;
+    const float r = __ldg(rewards + i);
+    const float v = __ldg(values + i);
+    const float alive = __fsub_rn(1.0f, (float)__ldg(dones + i));
+    const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(gamma, next_v), alive)), v);
+    carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_tau, alive), carry));
+    if (advantages) advantages[i] = carry;
+    returns[i] = __fadd_rn(carry, v);
+    next_v = v;
+  }
+}
+
+__device__ __forceinline__ float entropy_term(float h, int flags, float abs_t, float inv_abs_t) {
+  if (flags & 1) h = -h;                                      // -1.0 * logprobs
+  if (flags & 2) h = __fmul_rn(__fadd_rn(h, abs_t), 0.5f);     // (H + |Ht|) * 0.5
+  if (flags & 4) h = __fmul_rn(h, inv_abs_t);                  // H * (1/|Ht|)
+  return h;
+}
+
+// mineral/agents/diffrl/shac.py:877-916
+__global__ void __launch_bounds__(kScanThreads) critic_targets_kernel(
+    const float* __restrict__ rew, const float* __restrict__ done_mask, const float* __restrict__ next_values,
+    const float* __restrict__ entropy, float* __restrict__ target, int T, int N, int method, float gamma,
+    float lam, float one_minus_lam, float lam_gamma, float alpha, int ent_flags, float abs_t, float inv_abs_t) {
+  const int n = blockIdx.x * kScanThreads + threadIdx.x;
+  if (n >= N) return;
+  float Ai = 0.f, Bi = 0.f, w = 1.f;
+#pragma unroll 4
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * N + n;
+    float r = __ldg(rew + i);
+    const float nv = __ldg(next_values + i);
+    if (entropy) r = __fadd_rn(r, __fmul_rn(alpha, entropy_term(__ldg(entropy + i), ent_flags, abs_t, inv_abs_t)));
+    if (method == 0) {  // one-step
+      target[i] = __fadd_rn(r, __fmul_rn(gamma, nv));
+      continue;
+    }
+    const float d = __ldg(done_mask + i);
+    const float live = __fsub_rn(1.0f, d);
+    w = __fadd_rn(__fmul_rn(__fmul_rn(w, lam), live), d);
+    const float adj = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, w), one_minus_lam), r);
+    Ai = __fmul_rn(live, __fadd_rn(__fadd_rn(__fmul_rn(lam_gamma, Ai), __fmul_rn(gamma, nv)), adj));
+    Bi = __fadd_rn(__fmul_rn(gamma, __fadd_rn(__fmul_rn(nv, d), __fmul_rn(Bi, live))), r);
+    target[i] = __fadd_rn(__fmul_rn(one_minus_lam, Ai), __fmul_rn(w, Bi));
+  }
+}
+
+}  // namespace
+
+extern "C" int mnr_gae_f32(const float* rewards, const float* values, const uint8_t* dones, const float* last_values,
+                           float* returns, float* advantages, int T, int N, float gamma, float gamma_tau,
+                           mnr_stream_t stream) {
+  MNR_CHECK_PTR(rewards); MNR_CHECK_PTR(values); MNR_CHECK_PTR(dones); MNR_CHECK_PTR(last_values); MNR_CHECK_PTR(returns);
+  if (T <= 0 || N <= 0) return MNR_ESHAPE;
+  const int grid = (N + kScanThreads - 1) / kScanThreads;
+  gae_kernel<<<grid, kScanThreads, 0, mnr_cs(stream)>>>(rewards, values, dones, last_values, returns, advantages, T, N,
+                                                        gamma, gamma_tau);
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_critic_targets_f32(const float* rew, const float* done_mask, const float* next_values,
+                                      const float* entropy, float* target, int T, int N, int method, float gamma,
+                                      float lam, float one_minus_lam, float lam_gamma, float alpha, int ent_flags,
+                                      float abs_target_entropy, float inv_abs_target_entropy, mnr_stream_t stream) {
+  MNR_CHECK_PTR(rew); MNR_CHECK_PTR(next_values); MNR_CHECK_PTR(target);
+  if (T <= 0 || N <= 0) return MNR_ESHAPE;
+  if (method != 0 && method != 1) return MNR_EUNSUP;
+  if (method == 1) MNR_CHECK_PTR(done_mask);
+  const int grid = (N + kScanThreads - 1) / kScanThreads;
+  critic_targets_kernel<<<grid, kScanThreads, 0, mnr_cs(stream)>>>(rew, done_mask, next_values, entropy, target, T, N,
+                                                                   method, gamma, lam, one_minus_lam, lam_gamma, alpha,
+                                                                   ent_flags, abs_target_entropy, inv_abs_target_entropy);
+  MNR_LAUNCH_RESULT();
+}

@@ -1,0 +1,260 @@
+"""Tensor-level wrappers over the C ABI: one Python function per `mnr_*` entry point.
+
+Everything here enqueues a hand-written sm_100a kernel on torch's current CUDA stream; nothing
+computes with torch ops and nothing runs on the CPU.
+"""
+
+import ctypes as C
+
+import torch
+
+from . import _native as nv
+from ._native import check, lib, ptr, stream
+
+F32, F64, U8, I64, BOOL = torch.float32, torch.float64, torch.uint8, torch.int64, torch.bool
+
+
+# Python-double scalars (gamma * tau, 1.0 - lam, ...) are formed in double precision exactly as the
+# reference forms them and are rounded to f32 by ctypes (c_float) when they cross the ABI - the same
+# rounding torch applies when a Python scalar meets an f32 tensor.
+
+# ---------------------------------------------------------------------------------------------
+# K1  scans
+# ---------------------------------------------------------------------------------------------
+def gae(rewards, values, dones, last_values, gamma, tau, returns=None, advantages=None):
+    """GAE over time-major (T,N[,1]) tensors -> returns (same shape as rewards).
+    mineral/agents/ppo/experience.py:96-108."""
+    T, N = rewards.shape[0], rewards.shape[1]
+    if returns is None:
+        returns = torch.empty_like(rewards)
+    check(lib.mnr_gae_f32(ptr(rewards, F32, "rewards"), ptr(values, F32, "values"), ptr(dones, (U8, BOOL), "dones"),
+                          ptr(last_values, F32, "last_values"), ptr(returns, F32, "returns"),
+                          ptr(advantages, F32, "advantages", allow_none=True), T, N, gamma, gamma * tau, stream()), "mnr_gae_f32")
+    return returns
+
+
+def critic_targets(rew, done_mask, next_values, gamma, lam=0.95, method="td-lambda", alpha=None, entropy=None,
+                   negate_entropy=False, offset_by_target_entropy=False, scale_by_target_entropy=False,
+                   target_entropy=-1.0, out=None):
+    """SHAC/SAPO critic targets, (T,N) f32.  mineral/agents/diffrl/shac.py:877-916."""
+    T, N = rew.shape
+    if out is None:
+        out = torch.empty_like(rew)
+    m = {"one-step": 0, "td-lambda": 1}.get(method)
+    if m is None:
+        raise NotImplementedError(method)
+    flags = (1 if negate_entropy else 0) | (2 if offset_by_target_entropy else 0) | (4 if scale_by_target_entropy else 0)
+    at = abs(target_entropy)
+    check(lib.mnr_critic_targets_f32(
+        ptr(rew, F32, "rew"), ptr(done_mask, F32, "done_mask", allow_none=(m == 0)), ptr(next_values, F32, "next_values"),
+        ptr(entropy, F32, "entropy", allow_none=True) if alpha is not None else None, ptr(out, F32, "target"), T, N, m,
+        gamma, lam, 1.0 - lam, lam * gamma, 0.0 if alpha is None else float(alpha), flags, at, (1.0 / at) if at else 0.0,
+        stream()), "mnr_critic_targets_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K1a+K3a fused post-rollout
+# ---------------------------------------------------------------------------------------------
+def post_rollout_workspace(T, N, device):
+    return torch.zeros(lib.mnr_post_rollout_workspace_bytes(T, N), dtype=U8, device=device)
+
+
+def post_rollout_fused(wide, rewards, values, dones, neglogp, last_values, returns_tm, out, T, N, gamma, tau, ws, do_gae=True):
+    """wide: list of (src (T,N,w), dst (N*T,w)); out: dict with env-major 'rewards','values','returns','neglogp',
+    'dones','advantages'.  One launch: GAE + pack + moment partials."""
+    arr = (nv.WideField * max(len(wide), 1))()
+    for i, (s, d) in enumerate(wide):
+        w = s.numel() // (T * N)
+        arr[i] = nv.WideField(ptr(s, F32, "wide src").value, ptr(d, F32, "wide dst").value, w, 0)
+    check(lib.mnr_post_rollout_fused(
+        arr, len(wide), ptr(rewards, F32, "rewards"), ptr(values, F32, "values"), ptr(dones, (U8, BOOL), "dones"),
+        ptr(neglogp, F32, "neglogp"), ptr(last_values, F32, "last_values", allow_none=not do_gae),
+        ptr(returns_tm, F32, "returns_tm", allow_none=do_gae), ptr(out["rewards"], F32), ptr(out["values"], F32),
+        ptr(out["returns"], F32), ptr(out["neglogp"], F32), ptr(out["dones"], (U8, BOOL)), ptr(out["advantages"], F32),
+        T, N, 1 if do_gae else 0, gamma, gamma * tau, ptr(ws, U8), ws.numel(), stream()), "mnr_post_rollout_fused")
+
+
+def post_rollout_finalize(out, B, value_rms, ws, eps=1e-5, clamp=(-5.0, 5.0), stats_out=None):
+    """Normalise advantages; if value_rms (mean,var,count tensors) is given, run PPO's value block in place."""
+    if value_rms is None:
+        vm = vv = vc = None
+        f64 = 0
+    else:
+        vm, vv, vc = value_rms
+        f64 = 1 if vm.dtype == F64 else 0
+    lo, hi = clamp if clamp is not None else (1.0, -1.0)
+    check(lib.mnr_post_rollout_finalize(
+        ptr(out["advantages"], F32), ptr(out["values"], F32), ptr(out["returns"], F32), B,
+        ptr(vm, (F32, F64), allow_none=True), ptr(vv, (F32, F64), allow_none=True), ptr(vc, (F32, F64), allow_none=True), f64,
+        eps, lo, hi, ptr(stats_out, F64, allow_none=True), ptr(ws, U8), ws.numel(), stream()), "mnr_post_rollout_finalize")
+
+
+# ---------------------------------------------------------------------------------------------
+# K2  RunningMeanStd
+# ---------------------------------------------------------------------------------------------
+def rms_moments_workspace(rows, cols, group_rows, device):
+    return torch.zeros(lib.mnr_rms_moments_workspace_bytes(rows, cols, group_rows), dtype=U8, device=device)
+
+
+def rms_batch_moments(x2d, group_rows=None, correction=1, ws=None, mean_out=None, var_out=None):
+    """x2d (rows, cols) f32 -> per-group column mean/var (n_groups, cols) f32."""
+    rows, cols = x2d.shape
+    group_rows = rows if group_rows is None else group_rows
+    ng = (rows + group_rows - 1) // group_rows
+    if mean_out is None:
+        mean_out = torch.empty(ng, cols, dtype=F32, device=x2d.device)
+    if var_out is None:
+        var_out = torch.empty(ng, cols, dtype=F32, device=x2d.device)
+    if ws is None:
+        ws = nv.workspace("rms_moments", lib.mnr_rms_moments_workspace_bytes(rows, cols, group_rows), x2d.device)
+    check(lib.mnr_rms_batch_moments_f32(ptr(x2d, F32, "x"), rows, cols, group_rows, correction, ptr(mean_out, F32),
+                                        ptr(var_out, F32), ptr(ws, U8), ws.numel(), stream()), "mnr_rms_batch_moments_f32")
+    return mean_out, var_out
+
+
+def rms_merge(mean, var, count, batch_mean, batch_var, batch_count):
+    f64 = 1 if mean.dtype == F64 else 0
+    check(lib.mnr_rms_merge(ptr(mean, (F32, F64)), ptr(var, mean.dtype), ptr(count, mean.dtype), f64, ptr(batch_mean, F32),
+                            ptr(batch_var, F32), float(batch_count), mean.numel(), stream()), "mnr_rms_merge")
+
+
+def rms_schedule(mean, var, count, group_mean, group_var, group_rows, rows, n_steps, eps, mean_tab, denom_tab):
+    f64 = 1 if mean.dtype == F64 else 0
+    check(lib.mnr_rms_schedule(ptr(mean, (F32, F64)), ptr(var, mean.dtype), ptr(count, mean.dtype), f64, ptr(group_mean, F32),
+                               ptr(group_var, F32), group_rows, rows, n_steps, mean.numel(), eps, ptr(mean_tab, F32),
+                               ptr(denom_tab, F32), stream()), "mnr_rms_schedule")
+
+
+def rms_prepare(mean, var, eps, mean_f32=None, denom_f32=None):
+    cols = mean.numel()
+    if mean_f32 is None:
+        mean_f32 = torch.empty(cols, dtype=F32, device=mean.device)
+    if denom_f32 is None:
+        denom_f32 = torch.empty(cols, dtype=F32, device=mean.device)
+    check(lib.mnr_rms_prepare(ptr(mean, (F32, F64)), ptr(var, mean.dtype), 1 if mean.dtype == F64 else 0, cols, eps,
+                              ptr(mean_f32, F32), ptr(denom_f32, F32), stream()), "mnr_rms_prepare")
+    return mean_f32, denom_f32
+
+
+def rms_apply(x, mean_f32, denom_f32, clamp=None, inverse=False, out=None):
+    cols = mean_f32.numel()
+    rows = x.numel() // cols
+    if out is None:
+        out = torch.empty_like(x)
+    lo, hi = clamp if clamp is not None else (1.0, -1.0)
+    check(lib.mnr_rms_apply_f32(ptr(x, F32, "x"), ptr(out, F32, "out"), rows, cols, ptr(mean_f32, F32), ptr(denom_f32, F32),
+                                lo, hi, 1 if inverse else 0, stream()), "mnr_rms_apply_f32")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K3  rows
+# ---------------------------------------------------------------------------------------------
+def _row_fields(fields):
+    """fields: list of (src, dst, width, kind[, mean, denom, lo, hi])."""
+    arr = (nv.RowField * len(fields))()
+    for i, f in enumerate(fields):
+        src, dst, width, kind = f[:4]
+        mean = ptr(f[4], F32).value if len(f) > 4 and f[4] is not None else None
+        denom = ptr(f[5], F32).value if len(f) > 5 and f[5] is not None else None
+        lo, hi = (f[6], f[7]) if len(f) > 7 else (1.0, -1.0)
+        arr[i] = nv.RowField(ptr(src, name="row src").value, ptr(dst, name="row dst").value, width, kind, mean, denom, lo, hi)
+    return arr
+
+
+def gather_rows(fields, idx=None, row0=0, n=None):
+    n = idx.numel() if idx is not None else n
+    check(lib.mnr_gather_rows(_row_fields(fields), len(fields), ptr(idx, I64, "idx", allow_none=True), row0, n, stream()),
+          "mnr_gather_rows")
+
+
+def scatter_rows(fields, idx=None, row0=0, n=None):
+    n = idx.numel() if idx is not None else n
+    check(lib.mnr_scatter_rows(_row_fields(fields), len(fields), ptr(idx, I64, "idx", allow_none=True), row0, n, stream()),
+          "mnr_scatter_rows")
+
+
+def replay_insert(fields, n_rows, next_p, capacity):
+    check(lib.mnr_replay_insert(_row_fields(fields), len(fields), n_rows, next_p, capacity, stream()), "mnr_replay_insert")
+
+
+def nstep_push(inp, win_in, win_out, out, gammas, N, S, O, A, nstep, count_before):
+    def _in(d, f32_done):
+        return nv.NStepIn(ptr(d["obs"], F32).value, ptr(d["act"], F32).value, ptr(d["rew"], F32).value,
+                          ptr(d["nobs"], F32).value, ptr(d["done"], (F32,) if f32_done else (U8, BOOL)).value,
+                          1 if f32_done else 0, 0)
+
+    def _out(d):
+        if d is None:
+            return nv.NStepOut(None, None, None, None, None)
+        return nv.NStepOut(ptr(d["obs"], F32).value, ptr(d["act"], F32).value, ptr(d["rew"], F32).value,
+                           ptr(d["nobs"], F32).value, ptr(d["done"], (U8, BOOL)).value)
+
+    a, b = _in(inp, inp["done"].dtype == F32), _in(win_in, False)
+    c, d = _out(win_out), _out(out)
+    check(lib.mnr_nstep_push(C.byref(a), C.byref(b), C.byref(c), C.byref(d), ptr(gammas, F32), N, S, O, A, nstep,
+                             count_before, stream()), "mnr_nstep_push")
+
+
+# ---------------------------------------------------------------------------------------------
+# K4  PPO loss
+# ---------------------------------------------------------------------------------------------
+def ppo_loss_workspace(mb, A, device):
+    return torch.zeros(lib.mnr_ppo_loss_workspace_bytes(mb, A), dtype=U8, device=device)
+
+
+def make_loss_cfg(dist_type="normal", minstd=1.0, maxstd=1.0, e_clip=0.2, use_smooth_clamp=False, clip_value_loss=False,
+                  critic_coef=1.0, entropy_coef=0.0, bounds_loss_coef=0.0, bounds_type="bound", soft_bound=1.1, grad_scale=1.0, metric_scale=1.0):
+    dt = {"normal": nv.DIST_NORMAL, "dreamerv3_normal": nv.DIST_DREAMERV3_NORMAL}.get(dist_type)
+    if dt is None:
+        raise NotImplementedError(f"dist_type {dist_type!r} is not on the accelerated PPO path")
+    bt = {"bound": nv.BOUNDS_BOUND, "reg": nv.BOUNDS_REG}.get(bounds_type)
+    if bt is None:
+        raise NotImplementedError(bounds_type)
+    return nv.PPOLossCfg(dt, bt, int(bool(use_smooth_clamp)), int(bool(clip_value_loss)), minstd, maxstd, e_clip,
+                         critic_coef, entropy_coef, bounds_loss_coef, soft_bound, grad_scale, metric_scale, 0.0)
+
+
+def ppo_loss_fwd_bwd(mu_raw, logstd, value, actions, old_neglogp, advantages, old_values, returns, old_mu, old_sigma,
+                     g_mu_raw, g_logstd, g_value, metrics, cfg, ws, write_back=True, mu_mean=None, sigma_mean=None):
+    mb, A = mu_raw.shape
+    stride = 0 if logstd.dim() == 1 else A
+    check(lib.mnr_ppo_loss_fwd_bwd(
+        ptr(mu_raw, F32, "mu_raw"), ptr(logstd, F32, "logstd"), stride, ptr(value, F32, "value"), ptr(actions, F32, "actions"),
+        ptr(old_neglogp, F32, "old_neglogp"), ptr(advantages, F32, "advantages"), ptr(old_values, F32, "old_values"),
+        ptr(returns, F32, "returns"), ptr(old_mu, F32, "old_mu"), ptr(old_sigma, F32, "old_sigma"), 1 if write_back else 0,
+        ptr(g_mu_raw, F32), ptr(g_logstd, F32), ptr(g_value, F32), ptr(metrics, F32), ptr(mu_mean, F32, allow_none=True),
+        ptr(sigma_mean, F32, allow_none=True), mb, A, C.byref(cfg), ptr(ws, U8), ws.numel(), stream()), "mnr_ppo_loss_fwd_bwd")
+
+
+# ---------------------------------------------------------------------------------------------
+# a12  optimizer
+# ---------------------------------------------------------------------------------------------
+def optim_state_tensor(lr, device):
+    """Device copy of mnr_optim_state_t (48 bytes) initialised with `lr`."""
+    st = nv.OptimState(lr=float(lr), kl_sum=0.0, kl_count=0, step=0, grad_norm=0.0, clip_coef=1.0, step_size=0.0,
+                       bc2_sqrt=1.0, lr_f32=float(lr), _pad=0.0)
+    host = torch.frombuffer(bytearray(bytes(st)), dtype=U8).clone()
+    return host.to(device)
+
+
+def read_optim_state(t):
+    return nv.OptimState.from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+
+
+def grad_norm_prepare(flat_grad, max_norm, beta1, beta2, st, kl, norm_out, ws):
+    check(lib.mnr_grad_norm_prepare(ptr(flat_grad, F32, "grad"), flat_grad.numel(), max_norm, beta1, beta2, ptr(st, U8),
+                                    ptr(kl, F32, allow_none=True), ptr(norm_out, F32, allow_none=True), ptr(ws, U8), ws.numel(),
+                                    stream()), "mnr_grad_norm_prepare")
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, weight_decay, decoupled, zero_grad, st):
+    check(lib.mnr_adam_step(ptr(param, F32), ptr(grad, F32), ptr(exp_avg, F32), ptr(exp_avg_sq, F32), param.numel(), beta1,
+                            beta2, eps, weight_decay, 1 if decoupled else 0, 1 if zero_grad else 0, ptr(st, U8), stream()),
+          "mnr_adam_step")
+
+
+def kl_lr_update(st, kl_threshold, min_lr, max_lr, avg_kl_out=None, lr_out=None):
+    check(lib.mnr_kl_lr_update(ptr(st, U8), kl_threshold, min_lr, max_lr, ptr(avg_kl_out, F32, allow_none=True),
+                               ptr(lr_out, F64, allow_none=True), stream()), "mnr_kl_lr_update")
