@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: the PPO update (GAE + env-major pack + value/obs
+normalisation + mini_epochs x minibatches of clipped-surrogate optimizer steps) on a synthetic
+Ant-shaped rollout of 4096 envs x 32 steps per GPU.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A "step" is one full PPO update of one rollout.  `value` = samples/s with the rollout already resident
+in HBM; `e2e` = the same through the agent API with the rollout in pinned HOST memory (H2D of the
+rollout and D2H of the loss metrics inside the timed region).  Timing: CUDA events per step on the
+launching stream, L2 flushed (256 MiB write) between steps, max over ranks.  Prints ONE JSON line.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1] at configs[0]'s network / epoch structure (5 epochs x 4 minibatches)
+    "ppo_ant_4096x32": dict(T=32, N=4096, O=37, A=8, units=[256, 128, 64], variant="elu_normal_fixed", minibatches=4, mini_epochs=5),
+    # the reference's shipped Ant recipe (mineral/cfgs/agent/DFlexAntPPO.yaml): LayerNorm+SiLU towers, mb 2048
+    "ppo_ant_4096x32_yaml": dict(T=32, N=4096, O=37, A=8, units=[512, 256, 128], variant="ln_silu_dreamer_learned", minibatches=64, mini_epochs=5),
+    # BASELINE.json configs[4] per-GPU shape
+    "ppo_allegro_16384x16": dict(T=16, N=16384, O=88, A=16, units=[512, 256, 128], variant="ln_silu_dreamer_learned", minibatches=8, mini_epochs=5),
+    "ppo_ant_64x32": dict(T=32, N=64, O=37, A=8, units=[256, 128, 64], variant="elu_normal_fixed", minibatches=4, mini_epochs=5),
+}
+
+
+def make_cfg(w, device, multi_gpu, cuda_graph):
+    from oracle.reference_shim import to_attr
+
+    mb = w["T"] * w["N"] // w["minibatches"]
+    if w["variant"] == "elu_normal_fixed":
+        ack = dict(separate_value_mlp=True, mlp_kwargs=dict(units=w["units"], act_type="ELU"), fixed_sigma=True,
+                   actor_dist_kwargs=dict(dist_type="normal"))
+        optim_type, mgn = "Adam", 1.0
+    else:
+        ack = dict(separate_value_mlp=True, mlp_kwargs=dict(units=w["units"], norm_type="LayerNorm", act_type="SiLU"), fixed_sigma=False,
+                   actor_dist_kwargs=dict(dist_type="dreamerv3_normal", minstd=0.1, maxstd=1.0))
+        optim_type, mgn = "AdamW", 0.5
+    return to_attr(dict(
+        rl_device=device, multi_gpu=multi_gpu, task=dict(env_autoresets=True),
+        agent=dict(network=dict(normalize_input=True, actor_critic="ActorCritic", actor_critic_kwargs=ack),
+                   ppo=dict(num_actors=w["N"], reward_shaper=dict(fn="scale", scale=1.0), max_agent_steps=1e12, horizon_len=w["T"],
+                            minibatch_size=mb, normalize_value=True, value_bootstrap=True, clip_value_loss=False, normalize_advantage=True,
+                            gamma=0.99, tau=0.95, entropy_coef=0.0, e_clip=0.2, use_smooth_clamp=False, critic_coef=4,
+                            bounds_loss_coef=1e-4, bounds_type="bound", mini_epochs=w["mini_epochs"], optim_type=optim_type,
+                            optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008, max_grad_norm=mgn,
+                            truncate_grads=True, cuda_graph=cuda_graph))))
+
+
+def oracle_setup(w, seed=0):
+    """Parameters / optimizer / normaliser states of the CPU port for workload w."""
+    import torch
+
+    from oracle import mineral_oracle as oc
+
+    norm = w["variant"] != "elu_normal_fixed"
+    params = oc.init_actor_critic_params(w["O"], w["A"], w["units"], norm, not norm, seed)
+    params = {k: v.requires_grad_(True) for k, v in params.items()}
+    if norm:
+        optim = torch.optim.AdamW(list(params.values()), lr=5e-4, eps=1e-5)
+        net = dict(n_layers=len(w["units"]), norm=True, act="SiLU", fixed_sigma=False, dist_type="dreamerv3_normal", minstd=0.1, maxstd=1.0)
+        mgn = 0.5
+    else:
+        optim = torch.optim.Adam(list(params.values()), lr=5e-4, eps=1e-5)
+        net = dict(n_layers=len(w["units"]), norm=False, act="ELU", fixed_sigma=True, dist_type="normal")
+        mgn = 1.0
+    hp = dict(gamma=0.99, tau=0.95, e_clip=0.2, critic_coef=4, entropy_coef=0.0, bounds_loss_coef=1e-4, bounds_type="bound",
+              clip_value_loss=False, use_smooth_clamp=False, mini_epochs=w["mini_epochs"], minibatch_size=w["T"] * w["N"] // w["minibatches"],
+              truncate_grads=True, max_grad_norm=mgn, lr_schedule="kl", kl_threshold=0.008)
+    obs_rms = oc.rms_init((w["O"],), 1e-5, 1, torch.float64)
+    value_rms = oc.rms_init((1,), 1e-5, 1, torch.float64)
+    return params, optim, net, hp, obs_rms, value_rms
+
+
+def time_oracle(w, n_updates, warmup, budget_s):
+    """Time the CPU port (the reference's algorithm with the reference's own torch ops) on host cores."""
+    import torch
+
+    from oracle import mineral_oracle as oc
+
+    params, optim, net, hp, obs_rms, value_rms = oracle_setup(w)
+    st0, last = oc.synth_rollout(w["T"], w["N"], w["O"], w["A"], seed=0)
+    lr, times = 5e-4, []
+    t_begin = time.perf_counter()
+    for i in range(warmup + n_updates):
+        st = {k: (dict(v) if isinstance(v, dict) else v.clone()) for k, v in st0.items()}
+        t0 = time.perf_counter()
+        _, _, lr = oc.ppo_update(st, last, params, optim, obs_rms, value_rms, hp, net, lr)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+            break
+    return times
+
+
+def shrink_for_cpu(w, target_s_per_update=4.0):
+    """Bounded CPU sample: same workload structure, fewer envs if one full update would take too long."""
+    probe = dict(w, N=max(64, w["N"] // 16))
+    t = time_oracle(probe, 1, 1, 60)[0]
+    est_full = t * w["N"] / probe["N"]
+    if est_full <= target_s_per_update:
+        return dict(w), est_full
+    n = max(64, int(w["N"] * target_s_per_update / est_full) // 64 * 64)
+    return dict(w, N=n), est_full * n / w["N"]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_ev = index, [], set(), None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self._stop_ev.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_reference(args, w, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (its algorithm restated over the same
+    torch ops, oracle/mineral_oracle.py) on this box's host cores, all threads."""
+    if rank != 0:
+        return
+    import torch
+
+    cores = torch.get_num_threads()
+    ws, est = shrink_for_cpu(w)
+    times = time_oracle(ws, args.steps, args.warmup, budget_s=240)
+    per = statistics.mean(times)
+    samples = ws["T"] * ws["N"]
+    value = samples / per
+    sample = (f"{len(times)} timed full updates of {ws['N']} envs x {ws['T']} steps ({samples} samples, {ws['mini_epochs']} epochs x "
+              f"{ws['minibatches']} minibatches) on {cores} host threads" + ("" if ws["N"] == w["N"] else f"; envs reduced from {w['N']} to bound CPU time"))
+    print(json.dumps({
+        "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "envs_per_gpu": w["N"], "horizon": w["T"], "obs": w["O"], "act": w["A"], "mlp": w["units"],
+                   "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ppo_ant_4096x32", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying one CUDA graph per update")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-sweep", action="store_true", help="also time the fused post-rollout kernel over rollout sizes")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    w = WORKLOADS[args.workload]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        return run_reference(args, w, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device: mineral_b200 has no CPU path"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    from mineral_b200 import _native as nv
+    from mineral_b200.agents import PPO
+    from oracle import mineral_oracle as oc
+    from oracle.reference_shim import SynthEnv
+
+    T, N, O, A = w["T"], w["N"], w["O"], w["A"]
+    B = T * N
+    torch.manual_seed(0)
+    agent = PPO(make_cfg(w, dev, world > 1, cuda_graph=not args.no_graph), env=SynthEnv(4, O, A, 1))
+    agent.set_train()
+    if world > 1:  # identical initial weights on every rank
+        dist.broadcast(agent.optim.flat, 0)
+
+    # synthetic rollout(s): a different seed per rank (each rank owns its own envs)
+    st, last = oc.synth_rollout(T, N, O, A, seed=rank)
+    host = {k: v for k, v in st.items() if k not in ("returns", "obses")}
+    host["obs"] = st["obses"]["obs"]
+    host = {k: v.pin_memory() for k, v in host.items()}
+    host_last = last.pin_memory()
+    dev_last = last.to(dev)
+    sd = agent.storage.storage_dict
+
+    def load_rollout(non_blocking=False):
+        for k, v in host.items():
+            (sd["obses"]["obs"] if k == "obs" else sd[k]).copy_(v, non_blocking=non_blocking)
+
+    load_rollout()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def one_update():
+        agent.finish_rollout(dev_last)
+        return agent.train_epoch()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the CUDA graph) ----
+    for _ in range(args.warmup):
+        one_update()
+    barrier()
+
+    # ---- timed: K updates, HBM-resident inputs ----
+    nv.LAUNCHES = 0
+    replays0 = agent._engine.replays
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s0, s1 in evs:
+        flush.zero_()  # L2 flush between timed iterations (not timed)
+        s0.record()
+        one_update()
+        s1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = nv.LAUNCHES + agent._engine.graph_launches * (agent._engine.replays - replays0)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = total_ms.item()
+    value = B * world * args.steps / (total_ms / 1e3)
+
+    # ---- e2e: rollout in pinned host memory, H2D + update + D2H of the metrics inside the timed region ----
+    h2d = sum(v.numel() * v.element_size() for v in host.values()) + host_last.numel() * 4
+    e_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    d2h = 0
+    barrier()
+    for s0, s1 in e_evs:
+        flush.zero_()
+        s0.record()
+        load_rollout(non_blocking=True)
+        dev_last.copy_(host_last, non_blocking=True)
+        res = one_update()
+        out = torch.stack([torch.stack(res[k]).mean() for k in ("loss/total", "loss/actor", "loss/critic", "avg_kl")]).cpu()
+        d2h = out.numel() * 4 + 48  # + the optimizer-state read (lr) done by train_epoch
+        s1.record()
+    barrier()
+    e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_evs)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / (e_ms.item() / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant hand-written kernel: the fused post-rollout pass (HBM-bound) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks["hbm_gbs"], "measured (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks else (6650.0, "fallback (B200_PROFILING.md)")
+    row = 4 * O + 12 * A + 17
+    alg_bytes = row * B + 4 * N + (row + 8) * B  # read everything once, write env-major once (+ returns, adv)
+
+    def time_fused(agent_, n_iter=20):
+        ts = []
+        for _ in range(n_iter):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            agent_.storage._launch_fused_only(dev_last, agent_.gamma, agent_.tau)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return statistics.mean(sorted(ts)[: max(1, len(ts) * 3 // 4)])
+
+    k_ms = time_fused(agent)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roofline = {"kernel": "post_rollout_kernel<true> (GAE + env-major pack + moment partials)", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes": alg_bytes, "launch_ms": k_ms, "timing": "CUDA events on the launching stream, L2 flushed before each launch"}
+    sweep = None
+    if args.kernel_sweep:
+        from mineral_b200.agents.ppo.experience import ExperienceBuffer
+        sweep = []
+        for n_env in (4096, 16384, 65536):
+            buf = ExperienceBuffer(n_env, T, n_env * T, n_env * T // 4, {"obs": (O,)}, A, dev)
+            lv = torch.zeros(n_env, 1, device=dev)
+
+            class _A:  # minimal holder for time_fused
+                storage, gamma, tau = buf, 0.99, 0.95
+            torch.cuda.synchronize()
+            ms = []
+            for _ in range(12):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); buf._launch_fused_only(lv, 0.99, 0.95); b.record(); torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            m = statistics.mean(sorted(ms)[:9])
+            byts = row * n_env * T + 4 * n_env + (row + 8) * n_env * T
+            sweep.append({"envs": n_env, "ms": m, "GB/s": byts / m / 1e6, "frac": byts / m / 1e6 / peak})
+
+    # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
+    cpu = None
+    if not args.no_cpu_baseline:
+        cores = torch.get_num_threads()
+        ws, _ = shrink_for_cpu(w)
+        times = time_oracle(ws, 3, 1, budget_s=45)
+        per = statistics.mean(times)
+        cpu = {"value": ws["T"] * ws["N"] / per, "unit": "samples/s", "cores": cores, "kind": "port",
+               "sample": f"{len(times)} full updates of {ws['N']} envs x {ws['T']} steps after 1 warm-up, {cores} torch threads, {per:.2f} s each"}
+
+    line = {
+        "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "envs_per_gpu": N, "horizon": T, "obs": O, "act": A, "mlp": w["units"], "variant": w["variant"],
+                   "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "minibatch_rows": B // w["minibatches"],
+                   "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": bool(agent.use_cuda_graph and world == 1),
+                   "l2": "256 MiB flush write between timed steps", "parallelism": f"env-sharded dp{world}"},
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "gae_normalise_hbm_gbs": achieved,
+    }
+    if sweep:
+        line["post_rollout_sweep"] = sweep
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -205,7 +205,8 @@ int mnr_replay_insert(const mnr_row_field_t* fields /*host*/, int n_fields, int6
  * in_*: (N,S,..) this call's transitions (obs/next_obs width O, action width A, reward 1, done 1).
  * win_*_in: previous window (N,n,..) oldest first; win_*_out: window after the call (distinct memory).
  * out_*: ((S-skip)*N, ..) step-major rows, skip = max(0, n-1-count_before) warm-up steps.
- * gammas: (n) f32 = (float)(gamma**k). */
+ * gammas: (n) f32 = (float)(gamma**k).  The reference only works with FLOAT dones (its argmax
+ * rejects bool), and then returns `done` as float; both dtypes are accepted here. */
 typedef struct {
   const float *obs, *act, *rew, *nobs;
   const void* done;     /* u8/bool, or f32 when done_is_f32 (sac.py:150 keeps dones in a float tensor) */
@@ -214,7 +215,9 @@ typedef struct {
 } mnr_nstep_in_t;
 typedef struct {
   float *obs, *act, *rew, *nobs;
-  uint8_t* done;
+  void* done;           /* u8/bool, or f32 (0.0 / 1.0) when done_is_f32 */
+  int32_t done_is_f32;
+  int32_t _pad;
 } mnr_nstep_out_t;
 int mnr_nstep_push(const mnr_nstep_in_t* in /*host*/, const mnr_nstep_in_t* win_in /*host*/,
                    const mnr_nstep_out_t* win_out /*host*/, const mnr_nstep_out_t* out /*host*/,

@@ -50,7 +50,8 @@ class NStepIn(C.Structure):
 
 
 class NStepOut(C.Structure):
-    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("nobs", C.c_void_p), ("done", C.c_void_p)]
+    _fields_ = [("obs", C.c_void_p), ("act", C.c_void_p), ("rew", C.c_void_p), ("nobs", C.c_void_p), ("done", C.c_void_p),
+                ("done_is_f32", C.c_int32), ("_pad", C.c_int32)]
 
 
 class PPOLossCfg(C.Structure):
@@ -126,9 +127,14 @@ def _load():
 lib = _load()
 
 
-def check(rc, what=""):
+LAUNCHES = 0  # kernels enqueued through this binding (each successful mnr_* call launches >= 1 kernel)
+
+
+def check(rc, what="", kernels=1):
+    global LAUNCHES
     if rc != 0:
         raise MineralB200Error(f"{what or 'mnr call'} failed: [{rc}] {lib.mnr_error_string(rc).decode()}")
+    LAUNCHES += kernels
 
 
 def stream():

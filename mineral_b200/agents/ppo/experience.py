@@ -20,9 +20,8 @@ from ... import ops
 
 
 def transform_op(arr):
-    """Reference helper kept for API parity (experience.py:7-14); returns an env-major view/copy via
-    the gather-free pack kernel is not possible for an arbitrary tensor, so this stays a torch view op
-    and is NOT used on the accelerated path."""
+    """(T,N,..) -> (N*T,..) of one arbitrary tensor with torch view ops (experience.py:7-14).  Kept for
+    API parity only; the accelerated path packs every field in one kernel (prepare_training)."""
     if arr is None:
         return arr
     s = arr.size()
@@ -139,6 +138,12 @@ class ExperienceBuffer:
                                self._em, T, N, 0.0, 0.0, self._ws, do_gae=False)
         ops.post_rollout_finalize(self._em, T * N, None, self._ws, stats_out=self.stats)
         return self._publish()
+
+    def _launch_fused_only(self, last_values, gamma, tau):
+        """Just the fused GAE + pack + partial-moments kernel (bench.py times it in isolation)."""
+        sd, T, N = self.storage_dict, self.transitions_per_env, self.num_envs
+        ops.post_rollout_fused(self._wide(), sd['rewards'], sd['values'], sd['dones'], sd['neglogp'], last_values.contiguous(),
+                               sd['returns'], self._em, T, N, gamma, tau, self._ws, do_gae=True)
 
     def compute_return_and_prepare(self, last_values, gamma, tau, value_rms=None):
         """Fused compute_return + prepare_training (+ PPO's value-RMS block when `value_rms`, a

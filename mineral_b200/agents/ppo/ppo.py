@@ -356,6 +356,8 @@ class _UpdateEngine:
                     x=torch.zeros(self.mb, *shape, **f32), ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
         self.graph = None
         self._warm = 0
+        self.graph_launches = 0  # kernels of ours inside one captured update
+        self.replays = 0
 
     # ---- the launch sequence -------------------------------------------------------------------
     def _enqueue(self):
@@ -426,12 +428,17 @@ class _UpdateEngine:
             if a.use_cuda_graph and a.world == 1:
                 if self.graph is None and self._warm >= 1:
                     torch.cuda.synchronize()
+                    from ... import _native as nv
+                    before = nv.LAUNCHES
                     self.graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.graph):
                         self._enqueue()
+                    self.graph_launches = nv.LAUNCHES - before
+                    nv.LAUNCHES = before  # captured, not launched; replays are counted separately
                     # the capture itself did not execute anything; fall through to replay
                 if self.graph is not None:
                     self.graph.replay()
+                    self.replays += 1
                 else:
                     self._enqueue()
                     self._warm += 1

@@ -4,7 +4,9 @@ ctor, `add_to_buffer(obs, actions, rewards, next_obs, dones) -> 5-tuple` with st
 The reference re-concatenates five (N, nstep, ..) FIFO tensors on every env step and calls a
 TorchScript function per step; here a call with S steps is ONE launch that reads each transition's
 window straight from the inputs (or the carried-over window) and also writes the window that
-survives the call.  While the window is still warming up (fewer than nstep steps seen in total) the
+survives the call.  `dones` is a float tensor in the reference's own use (sac.py:150; its argmax rejects
+bool) and `done` then comes back as float 0/1; bool/u8 dones are accepted too and come back as bool.
+While the window is still warming up (fewer than nstep steps seen in total) the
 reference crashes in torch.cat of an empty list; this class returns empty tensors instead."""
 
 import math
@@ -54,7 +56,8 @@ class NStepReplay:
         rows = (S - skip) * N
         f32 = dict(dtype=torch.float32, device=self.device)
         out = dict(obs=torch.empty(rows, *self.obs_space[k], **f32), act=torch.empty(rows, A, **f32), rew=torch.empty(rows, 1, **f32),
-                   nobs=torch.empty(rows, *self.obs_space[k], **f32), done=torch.empty(rows, 1, dtype=torch.bool, device=self.device))
+                   nobs=torch.empty(rows, *self.obs_space[k], **f32),
+                   done=torch.empty(rows, 1, dtype=torch.float32 if dones.dtype == torch.float32 else torch.bool, device=self.device))
         win_in, win_out = self._win[self._cur], self._win[1 - self._cur]
         ops.nstep_push(inp, win_in, win_out, out if rows > 0 else None, self.gamma_array.view(-1), N, S, O, A, n, self.nstep_count)
         self._cur = 1 - self._cur

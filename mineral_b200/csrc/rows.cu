@@ -129,6 +129,11 @@ __device__ __forceinline__ uint8_t read_done(const mnr_nstep_in_t& src, int64_t 
   return src.done_is_f32 ? (static_cast<const float*>(src.done)[t] != 0.0f) : (static_cast<const uint8_t*>(src.done)[t] != 0);
 }
 
+__device__ __forceinline__ void write_done(const mnr_nstep_out_t& dst, int64_t t, uint8_t d) {
+  if (dst.done_is_f32) static_cast<float*>(dst.done)[t] = d ? 1.0f : 0.0f;
+  else static_cast<uint8_t*>(dst.done)[t] = d;
+}
+
 __global__ void __launch_bounds__(kThreads) nstep_kernel(NStepArgs a, const float* __restrict__ gammas, int N, int S, int O,
                                                          int A, int n, int skip) {
   const int W = 2 * O + A + 2;
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) nstep_kernel(NStepArgs a, const floa
       else if (el < O + A) a.win_out.act[wr * A + (el - O)] = src.act[t * A + (el - O)];
       else if (el == O + A) a.win_out.rew[wr] = src.rew[t];
       else if (el < 2 * O + A + 1) a.win_out.nobs[wr * O + (el - O - A - 1)] = src.nobs[t * O + (el - O - A - 1)];
-      else a.win_out.done[wr] = read_done(src, t);
+      else write_done(a.win_out, wr, read_done(src, t));
       continue;
     }
     const int s = skip + (int)(row / N);
@@ -184,7 +189,7 @@ __global__ void __launch_bounds__(kThreads) nstep_kernel(NStepArgs a, const floa
       const int f = el - O - A - 1;
       a.out.nobs[row * O + f] = fw ? a.win_in.nobs[t * O + f] : a.in.nobs[t * O + f];
     } else {
-      a.out.done[row] = first >= 0 ? 1 : 0;  // newest done OR any done (:82-83)
+      write_done(a.out, row, first >= 0 ? 1 : 0);  // newest done OR any done (:82-83)
     }
   }
 }

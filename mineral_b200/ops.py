@@ -87,7 +87,7 @@ def post_rollout_finalize(out, B, value_rms, ws, eps=1e-5, clamp=(-5.0, 5.0), st
     check(lib.mnr_post_rollout_finalize(
         ptr(out["advantages"], F32), ptr(out["values"], F32), ptr(out["returns"], F32), B,
         ptr(vm, (F32, F64), allow_none=True), ptr(vv, (F32, F64), allow_none=True), ptr(vc, (F32, F64), allow_none=True), f64,
-        eps, lo, hi, ptr(stats_out, F64, allow_none=True), ptr(ws, U8), ws.numel(), stream()), "mnr_post_rollout_finalize")
+        eps, lo, hi, ptr(stats_out, F64, allow_none=True), ptr(ws, U8), ws.numel(), stream()), "mnr_post_rollout_finalize", kernels=2)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -187,9 +187,9 @@ def nstep_push(inp, win_in, win_out, out, gammas, N, S, O, A, nstep, count_befor
 
     def _out(d):
         if d is None:
-            return nv.NStepOut(None, None, None, None, None)
+            return nv.NStepOut(None, None, None, None, None, 0, 0)
         return nv.NStepOut(ptr(d["obs"], F32).value, ptr(d["act"], F32).value, ptr(d["rew"], F32).value,
-                           ptr(d["nobs"], F32).value, ptr(d["done"], (U8, BOOL)).value)
+                           ptr(d["nobs"], F32).value, ptr(d["done"], (U8, BOOL, F32)).value, 1 if d["done"].dtype == F32 else 0, 0)
 
     a, b = _in(inp, inp["done"].dtype == F32), _in(win_in, False)
     c, d = _out(win_out), _out(out)

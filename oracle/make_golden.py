@@ -195,11 +195,11 @@ def gen_nstep():
             rew = torch.randn(N, S, 1, generator=g); nobs = torch.randn(N, S, O, generator=g)
             done = (torch.rand(N, S, 1, generator=g) < done_p).float()  # sac.py:150 stores dones in a float tensor
             try:
-                o, a, r, no, d = ns.add_to_buffer({"obs": obs}, act, rew, {"obs": nobs}, done.bool())
+                o, a, r, no, d = ns.add_to_buffer({"obs": obs}, act, rew, {"obs": nobs}, done)
                 out = clone_tree(dict(obs=o["obs"], act=a, rew=r, nobs=no["obs"], done=d))
             except (RuntimeError, ValueError):  # reference raises (torch.cat of an empty list) while the window warms up
                 out = None
-            calls.append(dict(inp=dict(obs=obs, act=act, rew=rew, nobs=nobs, done=done.bool()), out=out))
+            calls.append(dict(inp=dict(obs=obs, act=act, rew=rew, nobs=nobs, done=done), out=out))
         cases.append(dict(N=N, O=O, A=A, nstep=n, gamma=0.99, calls=calls))
     save("nstep", cases)
 

@@ -241,7 +241,9 @@ class NStepOracle:
     done*) where the discounted sum stops after the first done in the window,
     next_obs* is the one at the first done (else the newest) and done* is
     `newest done OR any done` (nstep_replay.py:71-94).  Outputs are concatenated
-    step-major (nstep_replay.py:60-64)."""
+    step-major (nstep_replay.py:60-64).  `done` is FLOAT in and out: the reference's window is
+    promoted to float by the first torch.cat with SAC's float dones (sac.py:150) and its argmax
+    rejects bool input."""
 
     def __init__(self, num_envs, obs_dim, act_dim, nstep=3, gamma=0.99):
         self.n, self.N = nstep, num_envs
@@ -249,7 +251,7 @@ class NStepOracle:
         self.w_act = torch.zeros(num_envs, nstep, act_dim)
         self.w_rew = torch.zeros(num_envs, nstep, 1)
         self.w_nobs = torch.zeros(num_envs, nstep, obs_dim)
-        self.w_done = torch.zeros(num_envs, nstep, 1, dtype=torch.bool)
+        self.w_done = torch.zeros(num_envs, nstep, 1)
         self.count = 0
         # f32 tensor built from python doubles gamma**i (nstep_replay.py:27)
         self.disc = torch.tensor([gamma**i for i in range(nstep)]).view(-1, 1)
@@ -266,13 +268,13 @@ class NStepOracle:
         for s in range(done.shape[1]):
             self.w_obs = self._push(self.w_obs, obs[:, s])
             self.w_nobs = self._push(self.w_nobs, nobs[:, s])
-            self.w_done = self._push(self.w_done, done[:, s].bool() if done.dtype != torch.bool else done[:, s])
+            self.w_done = self._push(self.w_done, done[:, s].float())
             self.w_act = self._push(self.w_act, act[:, s])
             self.w_rew = self._push(self.w_rew, rew[:, s])
             self.count += 1
             if self.count < self.n:
                 continue
-            d = self.w_done.squeeze(-1)  # (N,n)
+            d = self.w_done.squeeze(-1) != 0  # (N,n)
             any_done = d.any(dim=1)
             first = d.float().argmax(dim=1)  # first True, 0 if none
             k = torch.arange(self.n)
@@ -280,7 +282,7 @@ class NStepOracle:
             R = ((self.w_rew * self.disc) * live.unsqueeze(-1)).sum(1)
             pick = torch.where(any_done, first, torch.full_like(first, self.n - 1))
             nob = self.w_nobs[torch.arange(self.N), pick]
-            dn = self.w_done[:, -1] | any_done[:, None]
+            dn = torch.where(any_done[:, None], torch.ones(self.N, 1), self.w_done[:, -1])
             for lst, v in zip(outs, (self.w_obs[:, 0], self.w_act[:, 0], R, nob, dn)):
                 lst.append(v.clone())
         return tuple(torch.cat(x) for x in outs)
