@@ -9,7 +9,7 @@ Ant-shaped rollout of 4096 envs x 32 steps per GPU.
 A "step" is one full PPO update of one rollout.  `value` = samples/s with the rollout already resident
 in HBM; `e2e` = the same through the agent API with the rollout in pinned HOST memory (H2D of the
 rollout and D2H of the loss metrics inside the timed region).  Timing: CUDA events per step on the
-launching stream, L2 flushed (256 MiB write) between steps, max over ranks.  Prints ONE JSON line.
+launching stream, L2 flushed (256 MiB read pass) between steps, max over ranks.  Prints ONE JSON line.
 """
 
 import argparse
@@ -242,7 +242,18 @@ def main():
             (sd["obses"]["obs"] if k == "obs" else sd[k]).copy_(v, non_blocking=non_blocking)
 
     load_rollout()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_buf = torch.zeros(64 << 20, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
+
+    class _Flush:
+        """L2 flush between timed iterations: READ 256 MiB (evicts our data and leaves only CLEAN lines
+        behind; a write-flush would leave the L2 full of dirty lines that the timed kernels then have to
+        write back, charging them for traffic that is not theirs)."""
+
+        @staticmethod
+        def zero_():
+            flush_buf.max()
+
+    flush = _Flush()
 
     def one_update():
         agent.finish_rollout(dev_last)
@@ -370,7 +381,7 @@ def main():
         "config": {"workload": args.workload, "envs_per_gpu": N, "horizon": T, "obs": O, "act": A, "mlp": w["units"], "variant": w["variant"],
                    "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "minibatch_rows": B // w["minibatches"],
                    "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": bool(agent.use_cuda_graph and world == 1),
-                   "l2": "256 MiB flush write between timed steps", "parallelism": f"env-sharded dp{world}"},
+                   "l2": "256 MiB read-flush between timed steps", "parallelism": f"env-sharded dp{world}"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": clocks,

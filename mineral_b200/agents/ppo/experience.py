@@ -76,6 +76,7 @@ class ExperienceBuffer:
             'obses': {k: torch.zeros((B, *v), **f32) for k, v in self.obs_space.items()},
         }
         self._ws = ops.post_rollout_workspace(T, N, device)
+        self._ws_all = None  # combined partials of all ranks (multi-GPU), see mineral_b200/distributed.py
         self.stats = torch.zeros(10, dtype=torch.float64, device=device)  # see mnr_post_rollout_finalize
 
     def __len__(self):
@@ -145,17 +146,24 @@ class ExperienceBuffer:
         ops.post_rollout_fused(self._wide(), sd['rewards'], sd['values'], sd['dones'], sd['neglogp'], last_values.contiguous(),
                                sd['returns'], self._em, T, N, gamma, tau, self._ws, do_gae=True)
 
-    def compute_return_and_prepare(self, last_values, gamma, tau, value_rms=None):
+    def compute_return_and_prepare(self, last_values, gamma, tau, value_rms=None, world=1):
         """Fused compute_return + prepare_training (+ PPO's value-RMS block when `value_rms`, a
         RunningMeanStd over shape (1,), is given; ppo.py:175-183): one pass over the rollout, then one
-        small normalise pass.  Equivalent to calling the two reference methods and the value block."""
+        small normalise pass.  Equivalent to calling the two reference methods and the value block.
+        `world` > 1: the statistics cover every rank's shard (one all-gather of the partial moments)."""
         sd, T, N = self.storage_dict, self.transitions_per_env, self.num_envs
         ops.post_rollout_fused(self._wide(), sd['rewards'], sd['values'], sd['dones'], sd['neglogp'], last_values.contiguous(),
                                sd['returns'], self._em, T, N, gamma, tau, self._ws, do_gae=True)
+        ws = self._ws
+        if world > 1:  # advantage / value statistics over ALL ranks' samples
+            from ... import distributed as mdist
+            if self._ws_all is None:
+                self._ws_all = mdist.combined_workspace(N, world, self.device)
+            ws = mdist.gather_partials(self._ws, self._ws_all, N)
         if value_rms is None:
-            ops.post_rollout_finalize(self._em, T * N, None, self._ws, stats_out=self.stats)
+            ops.post_rollout_finalize(self._em, T * N, None, ws, stats_out=self.stats)
         else:
             clamp = tuple(value_rms.clamp_range) if value_rms.with_clamp else None
             ops.post_rollout_finalize(self._em, T * N, (value_rms.running_mean, value_rms.running_var, value_rms.running_count),
-                                      self._ws, eps=value_rms.eps, clamp=clamp, stats_out=self.stats)
+                                      ws, eps=value_rms.eps, clamp=clamp, stats_out=self.stats)
         return self._publish()

@@ -244,7 +244,8 @@ class PPO(Agent):
     @torch.no_grad()
     def finish_rollout(self, last_values):
         """ppo.py:172-183 in one fused pass + one normalise pass."""
-        self.storage.compute_return_and_prepare(last_values, self.gamma, self.tau, self.value_rms if self.normalize_value else None)
+        self.storage.compute_return_and_prepare(last_values, self.gamma, self.tau, self.value_rms if self.normalize_value else None,
+                                                world=self.world)
 
     def train(self):
         """ppo.py:185-246 without the TensorBoard/W&B plumbing."""
@@ -405,20 +406,9 @@ class _UpdateEngine:
                 ops.kl_lr_update(a.optim.state, float('nan'), 0.0, 1.0, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
 
     def _merge_moments_across_ranks(self, n):
-        """Global minibatch i = union of the ranks' local minibatch i: combine the
-        per-rank (count, mean, var) with exact sufficient statistics in f64 (tiny, once per rollout)."""
-        import torch.distributed as dist
-        a = self.a
-        cnt = float(self.mb)
-        corr = float(a.obs_rms[self.norm_keys[0]].correction)
-        mean = n['gm'].double()
-        m2 = n['gv'].double() * (cnt - corr)
-        pack = torch.stack([mean * cnt, m2 + cnt * mean * mean])
-        dist.all_reduce(pack)
-        tot = cnt * a.world
-        gmean = pack[0] / tot
-        n['gm'].copy_(gmean.float())
-        n['gv'].copy_(((pack[1] - tot * gmean * gmean) / (tot - corr)).float())
+        """Global minibatch i = union of the ranks' local minibatch i."""
+        from ... import distributed as mdist
+        mdist.merge_group_moments(n['gm'], n['gv'], self.mb, self.a.obs_rms[self.norm_keys[0]].correction)
 
     def run(self):
         a = self.a

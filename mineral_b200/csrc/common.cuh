@@ -124,6 +124,35 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
   return is_last;
 }
 
+// CTA-wide sum of one double per thread; the total is returned to thread 0 (others get garbage).
+// blockDim.x <= 1024, multiple of 32.  Fixed tree order => deterministic.
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double s_bs[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect s_bs across back-to-back calls
+  if (lane == 0) s_bs[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < nw; ++w) t += s_bs[w];
+  return t;
+}
+
+// same for a Moments triple (Chan merges)
+__device__ __forceinline__ Moments block_merge(Moments m) {
+  __shared__ Moments s_bm[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  m = moments_warp_reduce(m);
+  __syncthreads();
+  if (lane == 0) s_bm[warp] = m;
+  __syncthreads();
+  Moments t{0, 0, 0};
+  if (threadIdx.x == 0)
+    for (int w = 0; w < nw; ++w) t = moments_merge(t, s_bm[w]);
+  return t;
+}
+
 // streaming global accessors (read-once / write-once data: keep L1 clean)
 __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }

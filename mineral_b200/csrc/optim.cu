@@ -37,9 +37,10 @@ __global__ void __launch_bounds__(kThreads) grad_norm_kernel(const float* __rest
     parts[blockIdx.x] = s;
   }
   if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return;
+  double mine = 0;
+  for (unsigned int x = threadIdx.x; x < gridDim.x; x += kThreads) mine += parts[x];
+  const double s = mnr::block_sum(mine);
   if (threadIdx.x != 0) return;
-  double s = 0;
-  for (unsigned int x = 0; x < gridDim.x; ++x) s += parts[x];
   const float norm = (float)sqrt(s);
   // torch.nn.utils.clip_grad_norm_: coef = max_norm / (norm + 1e-6), clamped to <= 1
   float coef = 1.0f;

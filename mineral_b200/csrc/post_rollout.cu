@@ -23,7 +23,8 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 128;      // post_rollout_kernel CTA
+constexpr int kFinThreads = 256;   // finalize kernels
 constexpr int kHeaderBytes = 128;  // [0] n_tiles, [1] ticket ; +64: FinalStats
 
 struct FinalStats {
@@ -34,11 +35,6 @@ struct FinalStats {
 
 struct TilePartial {
   mnr::Moments adv, val, ret;
-};
-
-struct WideArgs {
-  mnr_wide_field_t f[MNR_MAX_WIDE_FIELDS];
-  int n;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,176 +64,164 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
-// smem carve-up (floats): wide tiles [field][T][nb_pitch*width] | r v ret adv nlp [T][NB] | done [T][NB] u8
-template <bool kBulk>
-__global__ void __launch_bounds__(kThreads) post_rollout_kernel(
-    WideArgs wide, const float* __restrict__ rewards, const float* __restrict__ values,
-    const uint8_t* __restrict__ dones, const float* __restrict__ neglogp, const float* __restrict__ last_values,
-    float* __restrict__ returns_tm, float* __restrict__ rewards_em, float* __restrict__ values_em,
-    float* __restrict__ returns_em, float* __restrict__ neglogp_em, uint8_t* __restrict__ dones_em,
-    float* __restrict__ adv_em, int T, int N, int NB, int do_gae, float gamma, float gamma_tau,
-    unsigned char* __restrict__ workspace) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bar;
+// One launch, two CTA roles (blockIdx.x < n_scalar: scalar role, else wide role).
+//
+//  scalar role: 32 consecutive envs, one lane per env.  Every step t the scanning warp reads 32
+//    consecutive envs of rewards / values / dones / neglogp (one 128 B line each, all T steps'
+//    loads are independent of the recurrence and get batched), runs the GAE recurrence in
+//    registers, accumulates Welford moments of advantages / values / returns, and parks the
+//    per-env series in shared memory [env][T+1] (odd pitch: conflict-free).  All warps then write
+//    the six env-major scalar arrays as linear, fully coalesced runs of 32*T elements.
+//  wide role: one (field, env-tile) work item: T bulk copies of nb*width floats into shared memory
+//    [t][nb*width], then a linear walk of the item's contiguous env-major output run; lane i reads
+//    element i (stride-1 shared-memory reads: no bank conflicts) and stores 4 B (a warp writes one
+//    full 128 B line per instruction).
+struct Params {
+  mnr_wide_field_t f[MNR_MAX_WIDE_FIELDS];
+  int nb[MNR_MAX_WIDE_FIELDS];          // envs per tile of field k (multiple of 4)
+  int item0[MNR_MAX_WIDE_FIELDS + 1];   // prefix sum of item counts
+  int n_wide;
+  int n_scalar;                         // scalar-role CTAs = ceil(N / 32)
+  const float *rewards, *values, *neglogp, *last_values;
+  const uint8_t* dones;
+  float *returns_tm, *rewards_em, *values_em, *returns_em, *neglogp_em, *adv_em;
+  uint8_t* dones_em;
+  int T, N, do_gae;
+  float gamma, gamma_tau;
+  unsigned char* workspace;
+};
 
-  const int tile = blockIdx.x;
-  const int n0 = tile * NB;
-  const int nb = min(NB, N - n0);
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+constexpr int kEnvPerScalarCta = 32;
 
-  float* s_wide = reinterpret_cast<float*>(smem_raw);
-  int wide_floats = 0;
-  for (int k = 0; k < wide.n; ++k) wide_floats += T * NB * wide.f[k].width;
-  float* s_r = s_wide + wide_floats;
-  float* s_v = s_r + T * NB;
-  float* s_ret = s_v + T * NB;
-  float* s_adv = s_ret + T * NB;
-  float* s_nlp = s_adv + T * NB;
-  uint8_t* s_done = reinterpret_cast<uint8_t*>(s_nlp + T * NB);
+// exact floor(q / d) for 0 <= q < 2^22, 1 <= d < 2^22 with inv = 1.0f / d
+__device__ __forceinline__ int fast_div(int q, float inv, int d) {
+  int r = __float2int_rz(__fmul_rn((float)q + 0.5f, inv));
+  r -= (r * d > q);
+  r += ((r + 1) * d <= q);
+  return r;
+}
 
-  if (tile == 0 && tid == 0) reinterpret_cast<unsigned int*>(workspace)[0] = gridDim.x;
+__device__ __forceinline__ void scalar_role(const Params& p, float* smem) {
+  const int T = p.T, N = p.N;
+  const int n0 = blockIdx.x * kEnvPerScalarCta;
+  const int nb = min(kEnvPerScalarCta, N - n0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pitch = T + 1;
+  float* s_r = smem;
+  float* s_v = s_r + kEnvPerScalarCta * pitch;
+  float* s_ret = s_v + kEnvPerScalarCta * pitch;
+  float* s_adv = s_ret + kEnvPerScalarCta * pitch;
+  float* s_nlp = s_adv + kEnvPerScalarCta * pitch;
+  float* s_done = s_nlp + kEnvPerScalarCta * pitch;
 
-  // ---- 1. kick off the wide-field loads -------------------------------------------------------
-  if (kBulk) {
-    if (tid == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (warp == 0) {
-      if (lane == 0) {
-        uint32_t total = 0;
-        for (int k = 0; k < wide.n; ++k) total += (uint32_t)(T * nb * wide.f[k].width) * 4u;
-        mbar_expect_tx(&bar, total);
-      }
-      __syncwarp();
-      float* dst = s_wide;
-      for (int k = 0; k < wide.n; ++k) {
-        const int w = wide.f[k].width;
-        const uint32_t bytes = (uint32_t)(nb * w) * 4u;
-        for (int t = lane; t < T; t += 32)
-          bulk_g2s(dst + (size_t)t * NB * w, wide.f[k].src + ((size_t)t * N + n0) * w, bytes, &bar);
-        dst += (size_t)T * NB * w;
-      }
-    }
-  } else {
-    float* dst = s_wide;
-    for (int k = 0; k < wide.n; ++k) {
-      const int w = wide.f[k].width;
-      const int run = nb * w;
-      for (int q = tid; q < T * run; q += kThreads) {
-        const int t = q / run, j = q - t * run;
-        dst[(size_t)t * NB * w + j] = mnr::ld_stream(wide.f[k].src + ((size_t)t * N + n0) * w + j);
-      }
-      dst += (size_t)T * NB * w;
-    }
-  }
-
-  // ---- 2. stage the scalar fields ----------------------------------------------------------------
-  for (int q = tid; q < T * nb; q += kThreads) {
-    const int t = q / nb, nl = q - t * nb;
-    const size_t g = (size_t)t * N + n0 + nl;
-    const int s = t * NB + nl;
-    s_r[s] = __ldg(rewards + g);
-    s_v[s] = __ldg(values + g);
-    s_nlp[s] = __ldg(neglogp + g);
-    s_done[s] = __ldg(dones + g);
-    if (!do_gae) s_ret[s] = __ldg(returns_tm + g);
-  }
-  __syncthreads();
-
-  // ---- 3. GAE + moment partials: the last warp, one lane per env -----------------------------------
-  if (warp == kThreads / 32 - 1) {
-    mnr::Moments m_adv{0, 0, 0}, m_val{0, 0, 0}, m_ret{0, 0, 0};
-    for (int nl = lane; nl < nb; nl += 32) {
-      mnr::Welford wa, wv, wr;
-      wa.init(), wv.init(), wr.init();
-      float next_v = do_gae ? __ldg(last_values + n0 + nl) : 0.f;
+  if (warp == 0) {
+    mnr::Welford wa, wv, wr;
+    wa.init(), wv.init(), wr.init();
+    if (lane < nb) {
+      const int n = n0 + lane;
+      float next_v = p.do_gae ? __ldg(p.last_values + n) : 0.f;
       float carry = 0.f;
+#pragma unroll 8
       for (int t = T - 1; t >= 0; --t) {
-        const int s = t * NB + nl;
-        const float v = s_v[s];
+        const size_t g = (size_t)t * N + n;
+        const float r = __ldg(p.rewards + g), v = __ldg(p.values + g), nlp = __ldg(p.neglogp + g);
+        const float d = (float)__ldg(p.dones + g);
         float ret;
-        if (do_gae) {  // experience.py:100-108, same association order as scans.cu
-          const float alive = __fsub_rn(1.0f, (float)s_done[s]);
-          const float delta = __fsub_rn(__fadd_rn(s_r[s], __fmul_rn(__fmul_rn(gamma, next_v), alive)), v);
-          carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(gamma_tau, alive), carry));
+        if (p.do_gae) {  // experience.py:100-108, same association order as scans.cu
+          const float alive = __fsub_rn(1.0f, d);
+          const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma, next_v), alive)), v);
+          carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gamma_tau, alive), carry));
           ret = __fadd_rn(carry, v);
-          s_ret[s] = ret;
           next_v = v;
+          if (p.returns_tm) p.returns_tm[g] = ret;
         } else {
-          ret = s_ret[s];
+          ret = __ldg(p.returns_tm + g);
         }
         const float adv = __fsub_rn(ret, v);  // experience.py:119 (returns - values)
-        s_adv[s] = adv;
+        const int s = lane * pitch + t;
+        s_r[s] = r, s_v[s] = v, s_ret[s] = ret, s_adv[s] = adv, s_nlp[s] = nlp, s_done[s] = d;
         wa.push(adv), wv.push(v), wr.push(ret);
       }
-      m_adv = mnr::moments_merge(m_adv, wa.to_moments());
-      m_val = mnr::moments_merge(m_val, wv.to_moments());
-      m_ret = mnr::moments_merge(m_ret, wr.to_moments());
     }
-    m_adv = mnr::moments_warp_reduce(m_adv);
-    m_val = mnr::moments_warp_reduce(m_val);
-    m_ret = mnr::moments_warp_reduce(m_ret);
+    const mnr::Moments m_adv = mnr::moments_warp_reduce(wa.to_moments());
+    const mnr::Moments m_val = mnr::moments_warp_reduce(wv.to_moments());
+    const mnr::Moments m_ret = mnr::moments_warp_reduce(wr.to_moments());
     if (lane == 0) {
-      TilePartial* parts = reinterpret_cast<TilePartial*>(workspace + kHeaderBytes);
-      parts[tile] = TilePartial{m_adv, m_val, m_ret};
+      TilePartial* parts = reinterpret_cast<TilePartial*>(p.workspace + kHeaderBytes);
+      parts[blockIdx.x] = TilePartial{m_adv, m_val, m_ret};
+      if (blockIdx.x == 0) reinterpret_cast<unsigned int*>(p.workspace)[0] = (unsigned int)p.n_scalar;
     }
+  }
+  __syncthreads();
+  const size_t base = (size_t)n0 * T;
+  const float invT = 1.0f / (float)T;
+  for (int q = tid; q < nb * T; q += kThreads) {
+    const int nl = fast_div(q, invT, T), t = q - nl * T;
+    const int s = nl * pitch + t;
+    p.rewards_em[base + q] = s_r[s];
+    p.values_em[base + q] = s_v[s];
+    p.returns_em[base + q] = s_ret[s];
+    p.neglogp_em[base + q] = s_nlp[s];
+    p.adv_em[base + q] = s_adv[s];
+    p.dones_em[base + q] = (uint8_t)s_done[s];
+  }
+}
+
+template <bool kBulk>
+__device__ __forceinline__ void wide_role(const Params& p, float* smem, uint64_t* bar) {
+  const int T = p.T, N = p.N;
+  const int item = blockIdx.x - p.n_scalar;
+  int k = 0;
+#pragma unroll
+  for (int j = 1; j < MNR_MAX_WIDE_FIELDS; ++j) k += (j < p.n_wide && item >= p.item0[j]) ? 1 : 0;
+  const int NB = p.nb[k];
+  const int w = p.f[k].width;
+  const int n0 = (item - p.item0[k]) * NB;
+  const int nb = min(NB, N - n0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int run = nb * w;  // floats per step in this tile
+  const float* src = p.f[k].src;
+
+  if (kBulk) {
+    if (tid == 0) mbar_init(bar, 1);
+    __syncthreads();
+    if (warp == 0) {
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(T * run) * 4u);
+      __syncwarp();
+      for (int t = lane; t < T; t += 32) bulk_g2s(smem + (size_t)t * run, src + ((size_t)t * N + n0) * w, (uint32_t)run * 4u, bar);
+    }
+    mbar_wait(bar, 0);
+  } else {
+    const float inv_run = 1.0f / (float)run;
+    for (int q = tid; q < T * run; q += kThreads) {
+      const int t = fast_div(q, inv_run, run), j = q - t * run;
+      smem[q] = mnr::ld_stream(src + ((size_t)t * N + n0) * w + j);
+    }
+    __syncthreads();
   }
 
-  // ---- 4. wide stores: linear walk of the tile's env-major output run ---------------------------
-  if (kBulk) mbar_wait(&bar, 0);
-  else __syncthreads();
-  {
-    const float* src = s_wide;
-    for (int k = 0; k < wide.n; ++k) {
-      const int w = wide.f[k].width;
-      const int per_env = T * w;
-      const int total = nb * per_env;
-      float* out = wide.f[k].dst + (size_t)n0 * per_env;
-      const int pitch = NB * w;
-      auto pick = [&](int q) {
-        const int nl = q / per_env;
-        const int rem = q - nl * per_env;
-        const int t = rem / w;
-        const int f = rem - t * w;
-        return src[t * pitch + nl * w + f];
-      };
-      if (mnr_aligned_dev(out)) {
-        const int total4 = total >> 2;
-        for (int q4 = tid; q4 < total4; q4 += kThreads) {
-          const int q = q4 << 2;
-          float4 o;
-          o.x = pick(q), o.y = pick(q + 1), o.z = pick(q + 2), o.w = pick(q + 3);
-          mnr::st_stream(reinterpret_cast<float4*>(out) + q4, o);
-        }
-        for (int q = (total4 << 2) + tid; q < total; q += kThreads) mnr::st_stream(out + q, pick(q));
-      } else {
-        for (int q = tid; q < total; q += kThreads) mnr::st_stream(out + q, pick(q));
-      }
-      src += (size_t)T * NB * w;
-    }
+  // out run: [nl][t][f] linear; smem: [t][nl][f]
+  const int per_env = T * w;
+  const int total = nb * per_env;
+  float* out = p.f[k].dst + (size_t)n0 * per_env;
+  const float inv_pe = 1.0f / (float)per_env, inv_w = 1.0f / (float)w;
+#pragma unroll 4
+  for (int q = tid; q < total; q += kThreads) {
+    const int nl = fast_div(q, inv_pe, per_env);
+    const int rem = q - nl * per_env;
+    const int t = fast_div(rem, inv_w, w);
+    const int f = rem - t * w;
+    mnr::st_stream(out + q, smem[t * run + nl * w + f]);
   }
-  __syncthreads();  // s_ret / s_adv complete
+}
 
-  // ---- 5. scalar stores (env-major run of nb*T elements, and time-major returns) --------------------
-  {
-    const size_t base = (size_t)n0 * T;
-    for (int q = tid; q < nb * T; q += kThreads) {
-      const int nl = q / T, t = q - nl * T;
-      const int s = t * NB + nl;
-      rewards_em[base + q] = s_r[s];
-      values_em[base + q] = s_v[s];
-      returns_em[base + q] = s_ret[s];
-      neglogp_em[base + q] = s_nlp[s];
-      adv_em[base + q] = s_adv[s];
-      dones_em[base + q] = s_done[s];
-    }
-    if (do_gae && returns_tm) {
-      for (int q = tid; q < T * nb; q += kThreads) {
-        const int t = q / nb, nl = q - t * nb;
-        returns_tm[(size_t)t * N + n0 + nl] = s_ret[t * NB + nl];
-      }
-    }
-  }
+template <bool kBulk>
+__global__ void __launch_bounds__(kThreads, 6) post_rollout_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar;
+  float* smem = reinterpret_cast<float*>(smem_raw);
+  if ((int)blockIdx.x < p.n_scalar) scalar_role(p, smem);
+  else wide_role<kBulk>(p, smem, &bar);
 }
 
 // ---- finalize: merge partials (fixed order), derive the 6 normalisation scalars, update value RMS ---
@@ -249,24 +233,24 @@ __device__ void chan_update_state(S* mean, S* var, S* count, float bmean, float 
   *mean = m, *var = v, *count = mnr::add_rn(c, (S)bcount);
 }
 
-__global__ void __launch_bounds__(kThreads) finalize_stats_kernel(unsigned char* __restrict__ workspace, void* value_mean,
+__global__ void __launch_bounds__(kFinThreads) finalize_stats_kernel(unsigned char* __restrict__ workspace, void* value_mean,
                                                                   void* value_var, void* value_count, int state_f64,
                                                                   float eps, double* __restrict__ stats_out) {
   const unsigned int n_tiles = reinterpret_cast<const unsigned int*>(workspace)[0];
   const TilePartial* parts = reinterpret_cast<const TilePartial*>(workspace + kHeaderBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   mnr::Moments a{0, 0, 0}, v{0, 0, 0}, r{0, 0, 0};
-  for (unsigned int i = tid; i < n_tiles; i += kThreads) {
+  for (unsigned int i = tid; i < n_tiles; i += kFinThreads) {
     a = mnr::moments_merge(a, parts[i].adv);
     v = mnr::moments_merge(v, parts[i].val);
     r = mnr::moments_merge(r, parts[i].ret);
   }
   a = mnr::moments_warp_reduce(a), v = mnr::moments_warp_reduce(v), r = mnr::moments_warp_reduce(r);
-  __shared__ mnr::Moments sm[3][kThreads / 32];
+  __shared__ mnr::Moments sm[3][kFinThreads / 32];
   if (lane == 0) sm[0][warp] = a, sm[1][warp] = v, sm[2][warp] = r;
   __syncthreads();
   if (tid != 0) return;
-  for (int w = 1; w < kThreads / 32; ++w) {
+  for (int w = 1; w < kFinThreads / 32; ++w) {
     a = mnr::moments_merge(a, sm[0][w]);
     v = mnr::moments_merge(v, sm[1][w]);
     r = mnr::moments_merge(r, sm[2][w]);
@@ -314,15 +298,15 @@ __device__ __forceinline__ float norm1(float x, float mean, float denom, float l
   return y;
 }
 
-__global__ void __launch_bounds__(kThreads) finalize_apply_kernel(float* __restrict__ adv, float* __restrict__ values,
+__global__ void __launch_bounds__(kFinThreads) finalize_apply_kernel(float* __restrict__ adv, float* __restrict__ values,
                                                                   float* __restrict__ returns, int64_t B, float lo,
                                                                   float hi, const unsigned char* __restrict__ workspace) {
   const FinalStats fs = *reinterpret_cast<const FinalStats*>(workspace + 64);
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t stride = (int64_t)gridDim.x * kFinThreads;
   const int64_t B4 = B >> 2;
   const bool vec = mnr_aligned_dev(adv) && mnr_aligned_dev(values) && mnr_aligned_dev(returns);
   if (vec) {
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B4; i += stride) {
+    for (int64_t i = (int64_t)blockIdx.x * kFinThreads + threadIdx.x; i < B4; i += stride) {
       float4 a = reinterpret_cast<float4*>(adv)[i];
       a.x = __fdiv_rn(__fsub_rn(a.x, fs.adv_mean), fs.adv_denom), a.y = __fdiv_rn(__fsub_rn(a.y, fs.adv_mean), fs.adv_denom);
       a.z = __fdiv_rn(__fsub_rn(a.z, fs.adv_mean), fs.adv_denom), a.w = __fdiv_rn(__fsub_rn(a.w, fs.adv_mean), fs.adv_denom);
@@ -338,7 +322,7 @@ __global__ void __launch_bounds__(kThreads) finalize_apply_kernel(float* __restr
       }
     }
   }
-  for (int64_t i = (vec ? (B4 << 2) : 0) + (int64_t)blockIdx.x * kThreads + threadIdx.x; i < B; i += stride) {
+  for (int64_t i = (vec ? (B4 << 2) : 0) + (int64_t)blockIdx.x * kFinThreads + threadIdx.x; i < B; i += stride) {
     adv[i] = __fdiv_rn(__fsub_rn(adv[i], fs.adv_mean), fs.adv_denom);
     if (fs.normalize_value) {
       values[i] = norm1(values[i], fs.v_mean, fs.v_denom, lo, hi);
@@ -347,19 +331,47 @@ __global__ void __launch_bounds__(kThreads) finalize_apply_kernel(float* __restr
   }
 }
 
-size_t tile_smem_bytes(const mnr_wide_field_t* wide, int n_wide, int T, int NB) {
-  size_t floats = 0;
-  for (int k = 0; k < n_wide; ++k) floats += (size_t)T * NB * wide[k].width;
-  floats += (size_t)5 * T * NB;
-  return floats * 4 + (size_t)T * NB + 16;
+struct Plan {
+  int nb[MNR_MAX_WIDE_FIELDS];
+  int item0[MNR_MAX_WIDE_FIELDS + 1];
+  int n_scalar;
+  size_t smem;
+};
+
+// Per-field tile width: bulk copies of >= ~1 KB (nb*width*4 bytes) but tiles of <= ~40 KB so that
+// 5-6 CTAs share an SM (loads of some overlap the stores of others); nb % 4 == 0 keeps every copy
+// 16 B aligned.  Returns false if even a 4-env tile of some field exceeds shared memory.
+bool make_plan(const mnr_wide_field_t* wide, int n_wide, int T, int N, Plan* pl) {
+  const size_t kTileCap = 40 * 1024, kSmemMax = 227 * 1024 - 2048;
+  size_t smem = (size_t)6 * kEnvPerScalarCta * (T + 1) * sizeof(float);
+  pl->item0[0] = 0;
+  for (int k = 0; k < n_wide; ++k) {
+    const size_t row = (size_t)wide[k].width * 4;
+    int nb = (int)((1024 + row - 1) / row);
+    nb = (nb + 3) / 4 * 4;
+    if (nb < 4) nb = 4;
+    while (nb > 4 && (size_t)T * nb * row > kTileCap) nb -= 4;
+    const int n_pad = (N + 3) / 4 * 4;
+    if (nb > n_pad) nb = n_pad;
+    const size_t bytes = (size_t)T * nb * row;
+    if (bytes > kSmemMax) return false;
+    if (bytes > smem) smem = bytes;
+    pl->nb[k] = nb;
+    pl->item0[k + 1] = pl->item0[k] + (N + nb - 1) / nb;
+  }
+  for (int k = n_wide; k < MNR_MAX_WIDE_FIELDS; ++k) pl->nb[k] = 4, pl->item0[k + 1] = pl->item0[n_wide];
+  if (smem > kSmemMax) return false;
+  pl->smem = smem;
+  pl->n_scalar = (N + kEnvPerScalarCta - 1) / kEnvPerScalarCta;
+  return true;
 }
 
 }  // namespace
 
 extern "C" size_t mnr_post_rollout_workspace_bytes(int T, int N) {
   (void)T;
-  const size_t max_tiles = (size_t)(N + 3) / 4 + 1;
-  return kHeaderBytes + max_tiles * sizeof(TilePartial);
+  const size_t max_parts = (size_t)(N + kEnvPerScalarCta - 1) / kEnvPerScalarCta + 1;
+  return kHeaderBytes + max_parts * sizeof(TilePartial);
 }
 
 extern "C" int mnr_post_rollout_fused(const mnr_wide_field_t* wide, int n_wide, const float* rewards,
@@ -374,55 +386,43 @@ extern "C" int mnr_post_rollout_fused(const mnr_wide_field_t* wide, int n_wide, 
   MNR_CHECK_PTR(rewards_em); MNR_CHECK_PTR(values_em); MNR_CHECK_PTR(returns_em); MNR_CHECK_PTR(neglogp_em);
   MNR_CHECK_PTR(dones_em); MNR_CHECK_PTR(adv_em); MNR_CHECK_PTR(workspace);
   if (do_gae) MNR_CHECK_PTR(last_values); else MNR_CHECK_PTR(returns_tm);
-  if (T <= 0 || N <= 0) return MNR_ESHAPE;
+  if (T <= 0 || N <= 0 || (int64_t)T * N >= (1 << 30)) return MNR_ESHAPE;
   if (workspace_bytes < mnr_post_rollout_workspace_bytes(T, N)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
 
-  WideArgs args;
-  args.n = n_wide;
+  Params p;
   bool bulk_ok = (N % 4 == 0);
   for (int k = 0; k < n_wide; ++k) {
     if (!wide[k].src || !wide[k].dst) return MNR_ENULL;
     if (wide[k].width <= 0) return MNR_ESHAPE;
-    args.f[k] = wide[k];
+    p.f[k] = wide[k];
     bulk_ok = bulk_ok && mnr_aligned(wide[k].src, 16);
   }
+  Plan pl;
+  if (!make_plan(wide, n_wide, T, N, &pl)) return MNR_ESHAPE;  // one 4-env tile does not fit in shared memory
+  for (int k = 0; k < MNR_MAX_WIDE_FIELDS; ++k) p.nb[k] = pl.nb[k];
+  for (int k = 0; k <= MNR_MAX_WIDE_FIELDS; ++k) p.item0[k] = pl.item0[k];
+  p.n_wide = n_wide, p.n_scalar = pl.n_scalar;
+  p.rewards = rewards, p.values = values, p.neglogp = neglogp, p.last_values = last_values, p.dones = dones;
+  p.returns_tm = returns_tm, p.rewards_em = rewards_em, p.values_em = values_em, p.returns_em = returns_em;
+  p.neglogp_em = neglogp_em, p.adv_em = adv_em, p.dones_em = dones_em;
+  p.T = T, p.N = N, p.do_gae = do_gae, p.gamma = gamma, p.gamma_tau = gamma_tau;
+  p.workspace = (unsigned char*)workspace;
 
-  // Tile width: minimise (waves x nb) subject to the shared-memory budget; nb % 4 == 0 keeps every
-  // bulk-copy run 16 B aligned.
-  const int sms = mnr_sm_count();
-  const size_t smem_cap = 227 * 1024 - 1024;
-  int best_nb = 0;
-  double best_cost = 1e30;
-  for (int nb = 4; nb <= 32; nb += 4) {
-    const size_t bytes = tile_smem_bytes(wide, n_wide, T, nb);
-    if (bytes > smem_cap) break;
-    int per_sm = (int)((228 * 1024) / (bytes + 1024));
-    if (per_sm > 8) per_sm = 8;  // 256-thread CTAs: 2048 threads / SM
-    if (per_sm < 1) per_sm = 1;
-    const int tiles = (N + nb - 1) / nb;
-    const int waves = (tiles + sms * per_sm - 1) / (sms * per_sm);
-    const double cost = (double)waves * nb + 0.01 * (32 - nb);  // tie-break: wider scalar runs
-    if (cost < best_cost) best_cost = cost, best_nb = nb;
-  }
-  if (best_nb == 0) return MNR_ESHAPE;  // one 4-env tile does not fit in shared memory
-  const int NB = best_nb;
-  const size_t smem = tile_smem_bytes(wide, n_wide, T, NB);
-  const int tiles = (N + NB - 1) / NB;
-
+  const int grid = pl.n_scalar + pl.item0[n_wide];
   cudaError_t e;
   if (bulk_ok) {
-    e = cudaFuncSetAttribute(post_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(post_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(post_rollout_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    post_rollout_kernel<true><<<tiles, kThreads, smem, mnr_cs(stream)>>>(
-        args, rewards, values, dones, neglogp, last_values, returns_tm, rewards_em, values_em, returns_em, neglogp_em,
-        dones_em, adv_em, T, N, NB, do_gae, gamma, gamma_tau, (unsigned char*)workspace);
+    post_rollout_kernel<true><<<grid, kThreads, pl.smem, mnr_cs(stream)>>>(p);
   } else {
-    e = cudaFuncSetAttribute(post_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(post_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(post_rollout_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
-    post_rollout_kernel<false><<<tiles, kThreads, smem, mnr_cs(stream)>>>(
-        args, rewards, values, dones, neglogp, last_values, returns_tm, rewards_em, values_em, returns_em, neglogp_em,
-        dones_em, adv_em, T, N, NB, do_gae, gamma, gamma_tau, (unsigned char*)workspace);
+    post_rollout_kernel<false><<<grid, kThreads, pl.smem, mnr_cs(stream)>>>(p);
   }
   MNR_LAUNCH_RESULT();
 }
@@ -435,11 +435,11 @@ extern "C" int mnr_post_rollout_finalize(float* adv_em, float* values_em, float*
   if (B <= 0) return MNR_ESHAPE;
   if (workspace_bytes < kHeaderBytes) return MNR_EWORKSPACE;
   if (value_mean && (!value_var || !value_count)) return MNR_ENULL;
-  finalize_stats_kernel<<<1, kThreads, 0, mnr_cs(stream)>>>((unsigned char*)workspace, value_mean, value_var,
+  finalize_stats_kernel<<<1, kFinThreads, 0, mnr_cs(stream)>>>((unsigned char*)workspace, value_mean, value_var,
                                                             value_count, state_f64, eps, stats_out);
-  const int64_t want = (B / 4 + kThreads - 1) / kThreads;
+  const int64_t want = (B / 4 + kFinThreads - 1) / kFinThreads;
   const int grid = (int)(want < 1 ? 1 : (want > 4 * mnr_sm_count() ? 4 * mnr_sm_count() : want));
-  finalize_apply_kernel<<<grid, kThreads, 0, mnr_cs(stream)>>>(adv_em, values_em, returns_em, B, clamp_lo, clamp_hi,
+  finalize_apply_kernel<<<grid, kFinThreads, 0, mnr_cs(stream)>>>(adv_em, values_em, returns_em, B, clamp_lo, clamp_hi,
                                                                (const unsigned char*)workspace);
   MNR_LAUNCH_RESULT();
 }

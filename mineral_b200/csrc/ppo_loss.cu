@@ -227,32 +227,48 @@ __global__ void __launch_bounds__(kThreads) ppo_loss_kernel(
   for (int j = tid; j < 2 * A; j += kThreads) col_parts[(size_t)blockIdx.x * 2 * A + j] = s_col[j];
 
   if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return;
+  // last CTA: every thread folds a strided share of the per-CTA partials, then one CTA-wide tree
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  mnr::Moments md2{0, 0, 0}, mr2{0, 0, 0};
+  for (unsigned int x = tid; x < gridDim.x; x += kThreads) {
+    const LossPartial& p = parts[x];
+    acc[0] += p.a, acc[1] += p.c, acc[2] += p.b, acc[3] += p.h, acc[4] += p.clip, acc[5] += p.kl;
+    md2 = mnr::moments_merge(md2, p.d), mr2 = mnr::moments_merge(mr2, p.ret);
+  }
+  double tot[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) tot[k] = mnr::block_sum(acc[k]);
+  const mnr::Moments td = mnr::block_merge(md2), tr = mnr::block_merge(mr2);
   if (tid == 0) {
-    LossPartial t = parts[0];
-    for (unsigned int x = 1; x < gridDim.x; ++x) {
-      const LossPartial& p = parts[x];
-      t.a += p.a, t.c += p.c, t.b += p.b, t.h += p.h, t.clip += p.clip, t.kl += p.kl;
-      t.d = mnr::moments_merge(t.d, p.d), t.ret = mnr::moments_merge(t.ret, p.ret);
-    }
     const double n = (double)mb;
-    const float a = (float)(t.a / n), c = (float)(t.c / n), b = (float)(t.b / n), h = (float)(t.h / n);
+    const float a = (float)(tot[0] / n), c = (float)(tot[1] / n), b = (float)(tot[2] / n), h = (float)(tot[3] / n);
     // ppo.py:285
     metrics_out[0] = a + 0.5f * c * cfg.critic_coef - h * cfg.entropy_coef + b * cfg.bounds_loss_coef;
     metrics_out[1] = a, metrics_out[2] = c, metrics_out[3] = b, metrics_out[4] = h;
-    metrics_out[5] = (float)(t.clip / n);
-    const float var_d = (float)(t.d.m2 / (t.d.n - 1.0)), var_r = (float)(t.ret.m2 / (t.ret.n - 1.0));
+    metrics_out[5] = (float)(tot[4] / n);
+    const float var_d = (float)(td.m2 / (td.n - 1.0)), var_r = (float)(tr.m2 / (tr.n - 1.0));
     metrics_out[6] = fminf(fmaxf(1.f - var_d / (var_r + 1e-8f), 0.f), 1.f);  // ppo.py:475
-    metrics_out[7] = (float)(t.kl / n);
+    metrics_out[7] = (float)(tot[5] / n);
     metrics_out[8] = 0.f, metrics_out[9] = 0.f;
     for (int k = 0; k < MNR_PPO_METRICS; ++k) metrics_out[k] *= cfg.metric_scale;
   }
   if (mu_mean_out && sigma_mean_out) {
-    for (int j = tid; j < 2 * A; j += kThreads) {
-      double s = 0;
-      for (unsigned int x = 0; x < gridDim.x; ++x) s += (double)col_parts[(size_t)x * 2 * A + j];
-      const float mean = (float)(s / (double)mb);
-      if (j < A) mu_mean_out[j] = mean;
-      else sigma_mean_out[j - A] = mean;
+    // column sums: thread (slice, j) folds CTAs slice, slice+S, ...; then S slices per column
+    __shared__ double s_cols[kThreads];
+    const int cols = 2 * A;
+    const int S = kThreads / cols;  // >= 1 (A <= kMaxA = 64)
+    const int sl = tid / cols, j = tid - sl * cols;
+    double sacc = 0;
+    if (sl < S)
+      for (unsigned int x = sl; x < gridDim.x; x += S) sacc += (double)col_parts[(size_t)x * cols + j];
+    s_cols[tid] = sacc;
+    __syncthreads();
+    if (tid < cols) {
+      double t = 0;
+      for (int q = 0; q < S; ++q) t += s_cols[q * cols + tid];
+      const float mean = (float)(t / (double)mb);
+      if (tid < A) mu_mean_out[tid] = mean;
+      else sigma_mean_out[tid - A] = mean;
     }
   }
 }
@@ -292,14 +308,15 @@ __device__ bool block_finish(double my_sum, const mnr::Welford& w0, const mnr::W
     parts[blockIdx.x] = p;
   }
   if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return false;
-  if (threadIdx.x == 0) {
-    RowsPartial t = parts[0];
-    for (unsigned int x = 1; x < gridDim.x; ++x) {
-      t.s += parts[x].s;
-      t.m0 = mnr::moments_merge(t.m0, parts[x].m0), t.m1 = mnr::moments_merge(t.m1, parts[x].m1);
-    }
-    *total = t;
+  double acc = 0;
+  mnr::Moments m0{0, 0, 0}, m1{0, 0, 0};
+  for (unsigned int x = threadIdx.x; x < gridDim.x; x += kRowThreads) {
+    acc += parts[x].s;
+    m0 = mnr::moments_merge(m0, parts[x].m0), m1 = mnr::moments_merge(m1, parts[x].m1);
   }
+  const double ts = mnr::block_sum(acc);
+  const mnr::Moments t0 = mnr::block_merge(m0), t1 = mnr::block_merge(m1);
+  if (threadIdx.x == 0) *total = RowsPartial{ts, t0, t1};
   return true;
 }
 
