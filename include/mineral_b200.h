@@ -289,6 +289,39 @@ int mnr_policy_kl_rows(const float* p0_mu, const float* p0_sigma, const float* p
 size_t mnr_rows_reduce_workspace_bytes(int64_t n);
 
 /* ------------------------------------------------------------------------------------
+ * G  actor/critic MLP towers (mineral/nets/mlp.py:25-77, mineral/agents/ppo/models.py:136-151):
+ *    fused linear-layer kernels that replace nn.Linear + activation + autograd on the update path.
+ *    A "group" is one tower's layer; both towers go in one launch.  act: 0 identity, 1 ELU, 2 ReLU.
+ *      fwd:        c = Y (M,N) = act(a=X (M,K) . b=W (N,K)^T + bias (N))
+ *      bwd_input:  c = dX (M,K) (+)= (a=dY (M,N) * act'(saved=Y)) . b=W (N,K)
+ *      bwd_weight: c = dW (N,K) = (a=dY * act'(saved=Y))^T . b=X (M,K);  bias_grad (N) = column sums
+ *    saved == NULL means identity (no activation).  Exact fp32 FMA accumulation.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* a;
+  const float* b;
+  float* c;
+  const float* bias;   /* fwd only, may be NULL */
+  const float* saved;  /* bwd only: forward output Y, may be NULL */
+  float* bias_grad;    /* bwd_weight only, may be NULL */
+  int32_t N, K;
+} mnr_linear_group_t;
+
+#define MNR_MAX_LINEAR_GROUPS 4
+
+int mnr_linear_fwd(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, mnr_stream_t stream);
+int mnr_linear_bwd_input(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, int accumulate,
+                         mnr_stream_t stream);
+size_t mnr_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K);
+/* all groups must share N and K */
+int mnr_linear_bwd_weight(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
+                          size_t workspace_bytes, mnr_stream_t stream);
+/* out (C) = column sums of x (M,C), C <= 256: gradient of a broadcast parameter (fixed sigma, models.py:151) */
+size_t mnr_colsum_workspace_bytes(int C);
+int mnr_colsum_f32(const float* x, int64_t M, int C, float* out, void* workspace, size_t workspace_bytes,
+                   mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * a12  gradient-norm clip + Adam/AdamW with DEVICE-resident learning rate and step count, and
  *      the KL-adaptive LR rule (ppo.py:291-300,338-345; mineral/agents/ppo/utils.py:14-20), so
  *      the optimizer step needs no host round trip and is CUDA-graph capturable.

@@ -61,6 +61,11 @@ class PPOLossCfg(C.Structure):
                 ("soft_bound", C.c_float), ("grad_scale", C.c_float), ("metric_scale", C.c_float), ("_pad", C.c_float)]
 
 
+class LinearGroup(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("bias", C.c_void_p), ("saved", C.c_void_p),
+                ("bias_grad", C.c_void_p), ("N", C.c_int32), ("K", C.c_int32)]
+
+
 class OptimState(C.Structure):
     _fields_ = [("lr", C.c_double), ("kl_sum", C.c_double), ("kl_count", C.c_int32), ("step", C.c_int32),
                 ("grad_norm", C.c_float), ("clip_coef", C.c_float), ("step_size", C.c_float), ("bc2_sqrt", C.c_float),
@@ -102,6 +107,12 @@ SIGNATURES = {
     "mnr_bounds_loss_rows": (i32, [vp, i64, i32, i32, f32, vp, vp, vp]),
     "mnr_policy_kl_rows": (i32, [vp, vp, vp, vp, i64, i32, vp, vp, vp, sz, vp]),
     "mnr_rows_reduce_workspace_bytes": (sz, [i64]),
+    "mnr_linear_fwd": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp]),
+    "mnr_linear_bwd_input": (i32, [C.POINTER(LinearGroup), i32, i32, i32, i32, vp]),
+    "mnr_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "mnr_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_colsum_workspace_bytes": (sz, [i32]),
+    "mnr_colsum_f32": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "mnr_grad_norm_workspace_bytes": (sz, [i64]),
     "mnr_grad_norm_prepare": (i32, [vp, i64, f32, f32, f32, vp, vp, vp, vp, sz, vp]),
     "mnr_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, i32, vp, vp]),

@@ -355,6 +355,11 @@ class _UpdateEngine:
                     cols=cols, gm=torch.zeros(self.num_mb, cols, **f32), gv=torch.zeros(self.num_mb, cols, **f32),
                     mean_tab=torch.zeros(self.steps, cols, **f32), denom_tab=torch.zeros(self.steps, cols, **f32),
                     x=torch.zeros(self.mb, *shape, **f32), ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
+        # actor/critic towers: explicit fwd/bwd on the hand-written linear kernels when the architecture allows
+        from ...nets.fused_towers import FusedTowers
+        self.towers = None
+        if cfg_get(a.ppo_config, 'fused_mlp', True) and FusedTowers.supported(a.model) and list(a.obs_space) == ['obs']:
+            self.towers = FusedTowers(a.model, self.mb, dev)
         self.graph = None
         self._warm = 0
         self.graph_launches = 0  # kernels of ours inside one captured update
@@ -386,13 +391,19 @@ class _UpdateEngine:
                         obs[k] = ops.rms_apply(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, out=n['x'])
                     else:
                         obs[k] = v[s:e]
-                with torch.enable_grad():
-                    mu_raw, logstd, value = a.model._actor_critic(obs)
+                if self.towers is not None:
+                    mu_raw, logstd, value = self.towers.forward(obs['obs'])
+                else:
+                    with torch.enable_grad():
+                        mu_raw, logstd, value = a.model._actor_critic(obs)
                 ops.ppo_loss_fwd_bwd(mu_raw.detach(), logstd.detach().contiguous(), value.detach(), d['actions'][s:e],
                                      d['neglogp'][s:e], d['advantages'][s:e], d['values'][s:e], d['returns'][s:e],
                                      d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls, self.g_v, self.metrics[step],
                                      self.loss_cfg, self.loss_ws, True, self.mu_mean[step], self.sigma_mean[step])
-                torch.autograd.backward([mu_raw, logstd, value], [self.g_mu, self.g_ls, self.g_v])
+                if self.towers is not None:
+                    self.towers.backward(obs['obs'], self.g_mu, self.g_ls, self.g_v)
+                else:
+                    torch.autograd.backward([mu_raw, logstd, value], [self.g_mu, self.g_ls, self.g_v])
                 if a.world > 1:
                     import torch.distributed as dist
                     dist.all_reduce(a.optim.flat_grad)     # grads were pre-scaled by 1/world in the loss kernel

@@ -1,0 +1,116 @@
+"""Explicit forward / backward of `ActorCritic._actor_critic` on the hand-written linear-layer kernels
+(csrc/mlp.cu): no nn.Linear, no activation kernels, no autograd graph on the PPO update path.
+
+Replaces, for the update, `MLP.forward` (mineral/nets/mlp.py:76-77) of both towers, the `mu` / `sigma` /
+`value` heads (mineral/agents/ppo/models.py:136-151) and torch autograd's backward through them.  The
+module's parameters stay ordinary `nn.Parameter`s (views into FusedAdam's flat buffers); this class
+only reads `.data` and writes `.grad`.
+
+Supported towers: Linear -> {ELU | ReLU | none} stacks without normalisation / dropout, separate value
+tower.  Anything else (LayerNorm + SiLU recipes) keeps the autograd path for now.
+"""
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+_ACT = {nn.ELU: 1, nn.ReLU: 2}
+
+
+def _tower_layers(mlp):
+    """-> (list of nn.Linear, act code) or None if the tower has an unsupported layer."""
+    linears, act = [], None
+    for m in mlp.mlp:
+        if isinstance(m, nn.Linear):
+            linears.append(m)
+        elif type(m) in _ACT:
+            code = _ACT[type(m)]
+            if isinstance(m, nn.ELU) and m.alpha != 1.0:
+                return None
+            if act not in (None, code):
+                return None
+            act = code
+        else:
+            return None
+    return linears, (act or 0)
+
+
+class FusedTowers:
+    @staticmethod
+    def supported(model):
+        if not getattr(model, 'separate_value_mlp', False):
+            return False
+        a, v = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
+        if a is None or v is None or a[1] != v[1] or len(a[0]) != len(v[0]):
+            return False
+        if any(x.weight.shape != y.weight.shape or x.bias is None or y.bias is None for x, y in zip(a[0], v[0])):
+            return False
+        return len(a[0]) == sum(isinstance(m, nn.Linear) for m in model.actor_mlp.mlp)
+
+    def __init__(self, model, rows, device):
+        self.model, self.M = model, rows
+        (self.la, self.act), (self.lv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
+        self.L = len(self.la)
+        self.A = model.mu.weight.shape[0]
+        self.fixed_sigma = model.fixed_sigma
+        f32 = dict(dtype=torch.float32, device=device)
+        widths = [l.weight.shape[0] for l in self.la]
+        self.widths, self.in_dim = widths, self.la[0].weight.shape[1]
+        # saved forward outputs and their gradients, per layer, per tower (0 actor, 1 value)
+        self.Y = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
+        self.dY = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
+        self.mu_raw = torch.empty(rows, self.A, **f32)
+        self.value = torch.empty(rows, 1, **f32)
+        self.ls = None if self.fixed_sigma else torch.empty(rows, self.A, **f32)
+        big = 0
+        for l in self.la + [model.mu]:
+            n, k = l.weight.shape
+            big = max(big, ops.lib.mnr_linear_bwd_weight_workspace_bytes(2, rows, n, k))
+        self.ws = torch.zeros(max(big, 256), dtype=torch.uint8, device=device)
+        self.colsum_ws = torch.zeros(ops.lib.mnr_colsum_workspace_bytes(self.A), dtype=torch.uint8, device=device)
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, x):
+        """x (rows, in_dim) -> (mu_raw (rows,A), logstd ((A,) parameter if fixed sigma else (rows,A)), value (rows,1))."""
+        M, m = self.M, self.model
+        inp = [x, x]
+        for i in range(self.L):
+            n, k = self.la[i].weight.shape
+            ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=self.Y[i][t], bias=l.bias.data, N=n, K=k)
+                            for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+            inp = self.Y[i]
+        h = self.widths[-1]
+        heads = [dict(a=inp[0], b=m.mu.weight.data, c=self.mu_raw, bias=m.mu.bias.data, N=self.A, K=h),
+                 dict(a=inp[1], b=m.value.weight.data, c=self.value, bias=m.value.bias.data, N=1, K=h)]
+        if not self.fixed_sigma:
+            heads.append(dict(a=inp[0], b=m.sigma.weight.data, c=self.ls, bias=m.sigma.bias.data, N=self.A, K=h))
+        ops.linear_fwd(heads, M, 0)
+        return self.mu_raw, (m.sigma.data if self.fixed_sigma else self.ls), self.value
+
+    def backward(self, x, g_mu, g_ls, g_v):
+        """Seeds: d loss / d (mu_raw, logstd, value), each (rows, .).  Writes every parameter's .grad."""
+        M, m, top = self.M, self.model, self.L - 1
+        h = self.widths[-1]
+        ya, yv = self.Y[top]
+        # heads: weight/bias grads, then grads w.r.t. the towers' last outputs
+        wg = [dict(a=g_mu, b=ya, c=m.mu.weight.grad, bias_grad=m.mu.bias.grad, N=self.A, K=h)]
+        if not self.fixed_sigma:
+            wg.append(dict(a=g_ls, b=ya, c=m.sigma.weight.grad, bias_grad=m.sigma.bias.grad, N=self.A, K=h))
+        ops.linear_bwd_weight(wg, M, 0, self.ws)
+        ops.linear_bwd_weight([dict(a=g_v, b=yv, c=m.value.weight.grad, bias_grad=m.value.bias.grad, N=1, K=h)], M, 0, self.ws)
+        if self.fixed_sigma:
+            ops.colsum(g_ls, m.sigma.grad, self.colsum_ws)
+        ops.linear_bwd_input([dict(a=g_mu, b=m.mu.weight.data, c=self.dY[top][0], N=self.A, K=h),
+                              dict(a=g_v, b=m.value.weight.data, c=self.dY[top][1], N=1, K=h)], M, 0)
+        if not self.fixed_sigma:
+            ops.linear_bwd_input([dict(a=g_ls, b=m.sigma.weight.data, c=self.dY[top][0], N=self.A, K=h)], M, 0, accumulate=True)
+        # towers, top layer first; act'(.) is applied on the fly from the saved outputs
+        for i in range(top, -1, -1):
+            n, k = self.la[i].weight.shape
+            src = self.Y[i - 1] if i > 0 else [x, x]
+            ops.linear_bwd_weight([dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=self.Y[i][t], bias_grad=l.bias.grad, N=n, K=k)
+                                   for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act, self.ws)
+            if i > 0:
+                ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=self.Y[i][t], N=n, K=k)
+                                      for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)

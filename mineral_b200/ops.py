@@ -229,6 +229,41 @@ def ppo_loss_fwd_bwd(mu_raw, logstd, value, actions, old_neglogp, advantages, ol
 
 
 # ---------------------------------------------------------------------------------------------
+# G  MLP towers
+# ---------------------------------------------------------------------------------------------
+ACT_CODES = {None: 0, "Identity": 0, "ELU": 1, "ReLU": 2}
+
+
+def _linear_groups(groups):
+    """groups: list of dict(a=, b=, c=, bias=None, saved=None, bias_grad=None, N=, K=)."""
+    arr = (nv.LinearGroup * len(groups))()
+    for i, g in enumerate(groups):
+        def p(name):
+            t = g.get(name)
+            return None if t is None else ptr(t, F32, name).value
+        arr[i] = nv.LinearGroup(p("a"), p("b"), p("c"), p("bias"), p("saved"), p("bias_grad"), g["N"], g["K"])
+    return arr
+
+
+def linear_fwd(groups, M, act):
+    check(lib.mnr_linear_fwd(_linear_groups(groups), len(groups), M, act, stream()), "mnr_linear_fwd")
+
+
+def linear_bwd_input(groups, M, act, accumulate=False):
+    check(lib.mnr_linear_bwd_input(_linear_groups(groups), len(groups), M, act, 1 if accumulate else 0, stream()), "mnr_linear_bwd_input")
+
+
+def linear_bwd_weight(groups, M, act, ws):
+    check(lib.mnr_linear_bwd_weight(_linear_groups(groups), len(groups), M, act, ptr(ws, U8), ws.numel(), stream()),
+          "mnr_linear_bwd_weight", kernels=2)
+
+
+def colsum(x, out, ws):
+    M, Cc = x.shape
+    check(lib.mnr_colsum_f32(ptr(x, F32), M, Cc, ptr(out, F32), ptr(ws, U8), ws.numel(), stream()), "mnr_colsum_f32")
+
+
+# ---------------------------------------------------------------------------------------------
 # a12  optimizer
 # ---------------------------------------------------------------------------------------------
 def optim_state_tensor(lr, device):

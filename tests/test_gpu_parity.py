@@ -584,3 +584,36 @@ def test_ppo_first_step_gradients_vs_oracle():
         torch.autograd.backward([mu_raw, logstd, value], [eng.g_mu, eng.g_ls, eng.g_v])
         for k, prm in a.model.named_parameters():
             scale_close(prm.grad, rec["grads"][k], 1e-5, f"{c['variant']} grad {k}")
+
+
+# ------------------------------------------------------------------------------------------------
+# G: fused MLP towers vs torch autograd on the same module
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,O,A,units,act,fixed_sigma", [(512, 37, 8, [256, 128, 64], "ELU", True), (333, 11, 3, [32, 16], "ELU", False),
+                                                            (2048, 88, 16, [64, 64, 32, 16], "ReLU", True), (130, 5, 2, [8], "ELU", True)])
+def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma):
+    from mineral_b200.agents.ppo.models import ActorCritic
+    from mineral_b200.nets.fused_towers import FusedTowers
+
+    torch.manual_seed(rows)
+    model = ActorCritic({"obs": (O,)}, A, mlp_kwargs=dict(units=units, act_type=act), fixed_sigma=fixed_sigma).to(DEV)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.05 * torch.randn_like(p))  # biases / sigma away from zero
+    assert FusedTowers.supported(model)
+    x = torch.randn(rows, O, device=DEV)
+    g_mu, g_ls, g_v = torch.randn(rows, A, device=DEV), torch.randn(rows, A, device=DEV), torch.randn(rows, 1, device=DEV)
+    mu, ls, v = model._actor_critic({"obs": x})
+    torch.autograd.backward([mu, ls, v], [g_mu, g_ls, g_v])
+    ref = {k: p.grad.clone() for k, p in model.named_parameters()}
+    for p in model.parameters():
+        p.grad = torch.full_like(p, float("nan"))  # every gradient must be (over)written
+    ft = FusedTowers(model, rows, DEV)
+    mu2, ls2, v2 = ft.forward(x)
+    scale_close(mu2, mu.detach(), 1e-5, "mu_raw"), scale_close(v2, v.detach(), 1e-5, "value")
+    scale_close(ls2.expand(rows, A) if fixed_sigma else ls2, ls.detach(), 1e-5, "logstd")
+    ft.backward(x, g_mu, g_ls, g_v)
+    for k, p in model.named_parameters():
+        # bias gradients here are sums of `rows` N(0,1) seeds that cancel to O(sqrt(rows)): both f32 summation orders
+        # carry ~rows * 2^-24 absolute error, so they get a looser bound than the weights
+        scale_close(p.grad, ref[k], 5e-5 if k.endswith("bias") or k == "sigma" else 1e-5, f"grad {k}")
