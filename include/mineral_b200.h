@@ -162,6 +162,9 @@ int mnr_rms_prepare(const void* mean, const void* var, int state_f64, int cols, 
 int mnr_rms_apply_f32(const float* x, float* y, int64_t rows, int cols, const float* mean_f32,
                       const float* denom_f32, float clamp_lo, float clamp_hi, int inverse,
                       mnr_stream_t stream);
+/* same, writing rows of y with a row stride of y_ld >= cols floats (pad columns untouched) */
+int mnr_rms_apply_ld_f32(const float* x, float* y, int64_t rows, int cols, int y_ld, const float* mean_f32,
+                         const float* denom_f32, float clamp_lo, float clamp_hi, mnr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K3  indexed row movement: minibatch gather, replay insert / sample.
@@ -304,7 +307,10 @@ typedef struct {
   const float* bias;   /* fwd only, may be NULL */
   const float* saved;  /* bwd only: forward output Y, may be NULL */
   float* bias_grad;    /* bwd_weight only, may be NULL */
+  const float* b_lo;   /* tensor-core path only: low tf32 part of W (mnr_split_tf32); b is then the high part */
   int32_t N, K;
+  int32_t lda;         /* row stride (floats) of X when it is the `a` operand (fwd); 0 = K */
+  int32_t ldb;         /* row stride (floats) of the `b` operand (W, or X in bwd_weight); 0 = K */
 } mnr_linear_group_t;
 
 #define MNR_MAX_LINEAR_GROUPS 4
@@ -316,6 +322,32 @@ size_t mnr_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K);
 /* all groups must share N and K */
 int mnr_linear_bwd_weight(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
                           size_t workspace_bytes, mnr_stream_t stream);
+/* Tensor-core variants (tcgen05 kind::tf32, 3xTF32 split: fp32-level accuracy, ~1e-6 relative).
+ * Same semantics as the three calls above with these extra requirements, else MNR_ESHAPE / MNR_EALIGN:
+ *   - at most 2 groups, all with the same N and K; N % 16 == 0 (fwd) / N % 4 == 0 (bwd);
+ *   - every matrix base 16 B aligned and every row stride a multiple of 4 floats (TMA); pad K with
+ *     lda / ldb (zero-filled pad columns) when K % 4 != 0;
+ *   - fwd / bwd_input read W as pre-split b (high tf32 part) and b_lo (remainder) from mnr_split_tf32;
+ *   - bwd calls need `saved` (pass act = 0 and saved = a for an identity layer); no accumulate.
+ * mnr_tc_supported() is 0 when the driver entry point for tensor maps is unavailable. */
+int mnr_tc_supported(void);
+int mnr_tc_linear_fwd(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, mnr_stream_t stream);
+int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, mnr_stream_t stream);
+size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K);
+int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
+                             size_t workspace_bytes, mnr_stream_t stream);
+
+/* hi = x with the 13 low mantissa bits cleared (a tf32), lo = x - hi, written to (rows, dst_ld) buffers
+ * with zero-filled pad columns; all jobs in one launch. */
+typedef struct {
+  const float* src;
+  float* hi;
+  float* lo;
+  int32_t rows, cols, src_ld, dst_ld;
+} mnr_split_job_t;
+#define MNR_MAX_SPLIT_JOBS 8
+int mnr_split_tf32(const mnr_split_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
+
 /* out (C) = column sums of x (M,C), C <= 256: gradient of a broadcast parameter (fixed sigma, models.py:151) */
 size_t mnr_colsum_workspace_bytes(int C);
 int mnr_colsum_f32(const float* x, int64_t M, int C, float* out, void* workspace, size_t workspace_bytes,

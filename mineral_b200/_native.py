@@ -63,7 +63,13 @@ class PPOLossCfg(C.Structure):
 
 class LinearGroup(C.Structure):
     _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("c", C.c_void_p), ("bias", C.c_void_p), ("saved", C.c_void_p),
-                ("bias_grad", C.c_void_p), ("N", C.c_int32), ("K", C.c_int32)]
+                ("bias_grad", C.c_void_p), ("b_lo", C.c_void_p), ("N", C.c_int32), ("K", C.c_int32), ("lda", C.c_int32),
+                ("ldb", C.c_int32)]
+
+
+class SplitJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("hi", C.c_void_p), ("lo", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32),
+                ("src_ld", C.c_int32), ("dst_ld", C.c_int32)]
 
 
 class OptimState(C.Structure):
@@ -111,6 +117,13 @@ SIGNATURES = {
     "mnr_linear_bwd_input": (i32, [C.POINTER(LinearGroup), i32, i32, i32, i32, vp]),
     "mnr_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "mnr_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_tc_supported": (i32, []),
+    "mnr_tc_linear_fwd": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp]),
+    "mnr_tc_linear_bwd_input": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp]),
+    "mnr_tc_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
+    "mnr_tc_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
+    "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),
     "mnr_colsum_workspace_bytes": (sz, [i32]),
     "mnr_colsum_f32": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "mnr_grad_norm_workspace_bytes": (sz, [i64]),

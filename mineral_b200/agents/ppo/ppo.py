@@ -354,12 +354,13 @@ class _UpdateEngine:
                 setattr(self, f'_n_{k}', dict(
                     cols=cols, gm=torch.zeros(self.num_mb, cols, **f32), gv=torch.zeros(self.num_mb, cols, **f32),
                     mean_tab=torch.zeros(self.steps, cols, **f32), denom_tab=torch.zeros(self.steps, cols, **f32),
-                    x=torch.zeros(self.mb, *shape, **f32), ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
+                    x=torch.zeros(self.mb, (cols + 3) // 4 * 4, **f32), x_ld=(cols + 3) // 4 * 4,
+                    ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
         # actor/critic towers: explicit fwd/bwd on the hand-written linear kernels when the architecture allows
         from ...nets.fused_towers import FusedTowers
         self.towers = None
         if cfg_get(a.ppo_config, 'fused_mlp', True) and FusedTowers.supported(a.model) and list(a.obs_space) == ['obs']:
-            self.towers = FusedTowers(a.model, self.mb, dev)
+            self.towers = FusedTowers(a.model, self.mb, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
         self.graph = None
         self._warm = 0
         self.graph_launches = 0  # kernels of ours inside one captured update
@@ -380,6 +381,7 @@ class _UpdateEngine:
                              self.B * a.world, self.steps, rms.eps, n['mean_tab'], n['denom_tab'])
         max_norm = float(a.max_grad_norm) if a.truncate_grads else 0.0
         step = 0
+        x_ld = None
         for ep in range(a.mini_epochs):
             for i in range(self.num_mb):
                 s, e = i * mb, (i + 1) * mb
@@ -388,11 +390,17 @@ class _UpdateEngine:
                     if k in self.norm_keys:
                         n, rms = getattr(self, f'_n_{k}'), a.obs_rms[k]
                         clamp = tuple(rms.clamp_range) if rms.with_clamp else None
-                        obs[k] = ops.rms_apply(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, out=n['x'])
+                        if self.towers is not None:  # padded row stride (TMA-friendly); pad columns stay zero
+                            obs[k] = ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, n['x'], n['x_ld'])
+                            x_ld = n['x_ld']
+                        else:
+                            obs[k] = ops.rms_apply(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp,
+                                                   out=n['x'].view(-1)[:self.mb * n['cols']].view(self.mb, *a.obs_space[k]))
                     else:
                         obs[k] = v[s:e]
+                        x_ld = None
                 if self.towers is not None:
-                    mu_raw, logstd, value = self.towers.forward(obs['obs'])
+                    mu_raw, logstd, value = self.towers.forward(obs['obs'], x_ld)
                 else:
                     with torch.enable_grad():
                         mu_raw, logstd, value = a.model._actor_critic(obs)

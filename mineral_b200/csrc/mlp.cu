@@ -31,6 +31,7 @@ struct Group {
   const float* s;     // DX/DW: saved forward output for act' (M,N) or null (identity)
   float* bias_grad;   // DW: db (N) or null
   int N, K;           // layer width (out features), input features
+  int lda, ldb;       // row strides of X (as `a`) and of the `b` operand
 };
 
 struct Groups {
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads, 2) linear_kernel(const __grid_consta
   // element fetchers ---------------------------------------------------------------------------------
   auto fetch_a = [&](int i, int r) -> float {
     if (i >= I || r >= r_end) return 0.f;
-    if (kMode == kFwd) return __ldg(g.a + (size_t)i * g.K + r);            // X[m][k]
+    if (kMode == kFwd) return __ldg(g.a + (size_t)i * g.lda + r);          // X[m][k]
     size_t off;
     if (kMode == kDx) off = (size_t)i * g.N + r;                           // dY[m][n], i=m r=n
     else off = (size_t)r * g.N + i;                                        // dY[m][n], i=n r=m
@@ -89,8 +90,8 @@ __global__ void __launch_bounds__(kThreads, 2) linear_kernel(const __grid_consta
   };
   auto fetch_b = [&](int r, int j) -> float {
     if (j >= J || r >= r_end) return 0.f;
-    if (kMode == kFwd) return __ldg(g.b + (size_t)j * g.K + r);            // W[n][k], j=n r=k
-    return __ldg(g.b + (size_t)r * g.K + j);                               // DX: W[n][k] r=n j=k ; DW: X[m][k] r=m j=k
+    if (kMode == kFwd) return __ldg(g.b + (size_t)j * g.ldb + r);          // W[n][k], j=n r=k
+    return __ldg(g.b + (size_t)r * g.ldb + j);                               // DX: W[n][k] r=n j=k ; DW: X[m][k] r=m j=k
   };
   // thread -> tile element maps: consecutive threads walk the contiguous global dimension
   constexpr bool kAContigR = (kMode != kDw);   // FWD: k contiguous, DX: n contiguous, DW: i(=n) contiguous
@@ -250,7 +251,7 @@ int pack_groups(const mnr_linear_group_t* groups, int n_groups, int mode, Groups
     if (!s.a || !s.b || !s.c) return MNR_ENULL;
     if (s.N <= 0 || s.K <= 0) return MNR_ESHAPE;
     if (mode == kDw && (s.N != groups[0].N || s.K != groups[0].K)) return MNR_ESHAPE;  // shared partial layout
-    out->g[k] = Group{s.a, s.b, s.c, s.bias, s.saved, s.bias_grad, s.N, s.K};
+    out->g[k] = Group{s.a, s.b, s.c, s.bias, s.saved, s.bias_grad, s.N, s.K, s.lda > 0 ? s.lda : s.K, s.ldb > 0 ? s.ldb : s.K};
   }
   return MNR_OK;
 }

@@ -191,6 +191,19 @@ __global__ void __launch_bounds__(kThreads) rms_apply_vec4_kernel(const float4* 
   }
 }
 
+// padded-output variant: y row stride y_ld (feeds TMA, which needs 16 B-multiple row strides)
+__global__ void __launch_bounds__(kThreads) rms_apply_ld_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                int64_t total, int cols, int y_ld,
+                                                                const float* __restrict__ mean,
+                                                                const float* __restrict__ denom, float lo, float hi) {
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    y[r * y_ld + c] = apply1(mnr::ld_stream(x + i), __ldg(mean + c), __ldg(denom + c), lo, hi, 0);
+  }
+}
+
 int apply_grid(int64_t work) {
   int64_t g = (work + kThreads - 1) / kThreads;
   const int64_t cap = (int64_t)mnr_sm_count() * 8;
@@ -286,5 +299,16 @@ extern "C" int mnr_rms_apply_f32(const float* x, float* y, int64_t rows, int col
     rms_apply_kernel<<<apply_grid(total), kThreads, 0, mnr_cs(stream)>>>(x, y, total, cols, mean_f32, denom_f32,
                                                                         clamp_lo, clamp_hi, inverse);
   }
+  MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_rms_apply_ld_f32(const float* x, float* y, int64_t rows, int cols, int y_ld, const float* mean_f32,
+                                    const float* denom_f32, float clamp_lo, float clamp_hi, mnr_stream_t stream) {
+  MNR_CHECK_PTR(x); MNR_CHECK_PTR(y); MNR_CHECK_PTR(mean_f32); MNR_CHECK_PTR(denom_f32);
+  if (rows < 0 || cols <= 0 || y_ld < cols) return MNR_ESHAPE;
+  if (rows == 0) return MNR_OK;
+  const int64_t total = rows * cols;
+  rms_apply_ld_kernel<<<apply_grid(total), kThreads, 0, mnr_cs(stream)>>>(x, y, total, cols, y_ld, mean_f32, denom_f32,
+                                                                         clamp_lo, clamp_hi);
   MNR_LAUNCH_RESULT();
 }

@@ -48,7 +48,7 @@ class FusedTowers:
             return False
         return len(a[0]) == sum(isinstance(m, nn.Linear) for m in model.actor_mlp.mlp)
 
-    def __init__(self, model, rows, device):
+    def __init__(self, model, rows, device, use_tc=True):
         self.model, self.M = model, rows
         (self.la, self.act), (self.lv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
         self.L = len(self.la)
@@ -70,15 +70,53 @@ class FusedTowers:
         self.ws = torch.zeros(max(big, 256), dtype=torch.uint8, device=device)
         self.colsum_ws = torch.zeros(ops.lib.mnr_colsum_workspace_bytes(self.A), dtype=torch.uint8, device=device)
 
+        # tensor-core path (tcgen05 3xTF32, csrc/tc_linear.cu) for the tower layers: needs widths % 16 == 0 and
+        # 16 B-multiple row strides, so W is kept pre-split (hi / lo) in K-padded buffers and the first layer's
+        # input is read through a padded row stride `in_ld`.
+        self.in_ld = (self.in_dim + 3) // 4 * 4
+        self.use_tc = bool(use_tc) and ops.tc_supported() and all(w % 16 == 0 for w in widths)
+        if self.use_tc:
+            self.w_hi, self.w_lo, self.w_ld = [], [], []
+            k = self.in_dim
+            for w in widths:
+                ld = (k + 3) // 4 * 4
+                self.w_ld.append(ld)
+                self.w_hi.append([torch.zeros(w, ld, **f32) for _ in range(2)])
+                self.w_lo.append([torch.zeros(w, ld, **f32) for _ in range(2)])
+                k = w
+            tc_big = max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(2, rows, l.weight.shape[0], l.weight.shape[1]) for l in self.la)
+            self.tc_ws = torch.zeros(max(tc_big, 256), dtype=torch.uint8, device=device)
+
     # ------------------------------------------------------------------------------------------------
-    def forward(self, x):
-        """x (rows, in_dim) -> (mu_raw (rows,A), logstd ((A,) parameter if fixed sigma else (rows,A)), value (rows,1))."""
+    def _split_weights(self):
+        """W -> (hi, lo) tf32 parts for every tower layer, one launch per 8 matrices."""
+        jobs = []
+        for i in range(self.L):
+            n, k = self.la[i].weight.shape
+            for t, l in enumerate((self.la[i], self.lv[i])):
+                jobs.append((l.weight.data, self.w_hi[i][t], self.w_lo[i][t], n, k, k, self.w_ld[i]))
+        for s in range(0, len(jobs), 8):
+            ops.split_tf32(jobs[s:s + 8])
+
+    def forward(self, x, x_ld=None):
+        """x (rows, in_dim) [row stride x_ld floats] -> (mu_raw (rows,A), logstd ((A,) parameter if fixed sigma
+        else (rows,A)), value (rows,1))."""
         M, m = self.M, self.model
+        x_ld = self.in_dim if x_ld is None else x_ld
+        self._x_ld = x_ld
+        tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
+        if self.use_tc:
+            self._split_weights()
         inp = [x, x]
         for i in range(self.L):
             n, k = self.la[i].weight.shape
-            ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=self.Y[i][t], bias=l.bias.data, N=n, K=k)
-                            for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+            lda = x_ld if i == 0 else k
+            if self.use_tc and (i > 0 or tc0):
+                ops.tc_linear_fwd([dict(a=inp[t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=self.Y[i][t], bias=l.bias.data, N=n, K=k,
+                                        lda=lda, ldb=self.w_ld[i]) for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+            else:
+                ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=self.Y[i][t], bias=l.bias.data, N=n, K=k, lda=lda)
+                                for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
             inp = self.Y[i]
         h = self.widths[-1]
         heads = [dict(a=inp[0], b=m.mu.weight.data, c=self.mu_raw, bias=m.mu.bias.data, N=self.A, K=h),
@@ -106,11 +144,22 @@ class FusedTowers:
         if not self.fixed_sigma:
             ops.linear_bwd_input([dict(a=g_ls, b=m.sigma.weight.data, c=self.dY[top][0], N=self.A, K=h)], M, 0, accumulate=True)
         # towers, top layer first; act'(.) is applied on the fly from the saved outputs
+        x_ld = getattr(self, '_x_ld', self.in_dim)
         for i in range(top, -1, -1):
             n, k = self.la[i].weight.shape
             src = self.Y[i - 1] if i > 0 else [x, x]
-            ops.linear_bwd_weight([dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=self.Y[i][t], bias_grad=l.bias.grad, N=n, K=k)
-                                   for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act, self.ws)
+            ldb = x_ld if i == 0 else k
+            tc = self.use_tc and ldb % 4 == 0
+            wg = [dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=self.Y[i][t], bias_grad=l.bias.grad, N=n, K=k, ldb=ldb)
+                  for t, l in enumerate((self.la[i], self.lv[i]))]
+            if tc:
+                ops.tc_linear_bwd_weight(wg, M, self.act, self.tc_ws)
+            else:
+                ops.linear_bwd_weight(wg, M, self.act, self.ws)
             if i > 0:
-                ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=self.Y[i][t], N=n, K=k)
-                                      for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+                if self.use_tc:
+                    ops.tc_linear_bwd_input([dict(a=self.dY[i][t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=self.dY[i - 1][t],
+                                                  saved=self.Y[i][t], N=n, K=k, ldb=self.w_ld[i]) for t in range(2)], M, self.act)
+                else:
+                    ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=self.Y[i][t], N=n, K=k)
+                                          for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)

@@ -241,8 +241,43 @@ def _linear_groups(groups):
         def p(name):
             t = g.get(name)
             return None if t is None else ptr(t, F32, name).value
-        arr[i] = nv.LinearGroup(p("a"), p("b"), p("c"), p("bias"), p("saved"), p("bias_grad"), g["N"], g["K"])
+        arr[i] = nv.LinearGroup(p("a"), p("b"), p("c"), p("bias"), p("saved"), p("bias_grad"), p("b_lo"), g["N"], g["K"],
+                                g.get("lda", 0), g.get("ldb", 0))
     return arr
+
+
+def tc_supported():
+    return bool(lib.mnr_tc_supported())
+
+
+def tc_linear_fwd(groups, M, act):
+    check(lib.mnr_tc_linear_fwd(_linear_groups(groups), len(groups), M, act, stream()), "mnr_tc_linear_fwd")
+
+
+def tc_linear_bwd_input(groups, M, act):
+    check(lib.mnr_tc_linear_bwd_input(_linear_groups(groups), len(groups), M, act, stream()), "mnr_tc_linear_bwd_input")
+
+
+def tc_linear_bwd_weight(groups, M, act, ws):
+    check(lib.mnr_tc_linear_bwd_weight(_linear_groups(groups), len(groups), M, act, ptr(ws, U8), ws.numel(), stream()),
+          "mnr_tc_linear_bwd_weight", kernels=2)
+
+
+def split_tf32(jobs):
+    """jobs: list of (src (rows, cols) view with row stride src_ld, hi, lo (rows, dst_ld))."""
+    arr = (nv.SplitJob * len(jobs))()
+    for i, (src, hi, lo, rows, cols, src_ld, dst_ld) in enumerate(jobs):
+        arr[i] = nv.SplitJob(ptr(src, F32).value, ptr(hi, F32).value, ptr(lo, F32).value, rows, cols, src_ld, dst_ld)
+    check(lib.mnr_split_tf32(arr, len(jobs), stream()), "mnr_split_tf32")
+
+
+def rms_apply_ld(x, mean_f32, denom_f32, clamp, out, out_ld):
+    cols = mean_f32.numel()
+    rows = x.numel() // cols
+    lo, hi = clamp if clamp is not None else (1.0, -1.0)
+    check(lib.mnr_rms_apply_ld_f32(ptr(x, F32, "x"), ptr(out, F32, "out"), rows, cols, out_ld, ptr(mean_f32, F32), ptr(denom_f32, F32),
+                                   lo, hi, stream()), "mnr_rms_apply_ld_f32")
+    return out
 
 
 def linear_fwd(groups, M, act):

@@ -591,7 +591,8 @@ def test_ppo_first_step_gradients_vs_oracle():
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("rows,O,A,units,act,fixed_sigma", [(512, 37, 8, [256, 128, 64], "ELU", True), (333, 11, 3, [32, 16], "ELU", False),
                                                             (2048, 88, 16, [64, 64, 32, 16], "ReLU", True), (130, 5, 2, [8], "ELU", True)])
-def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma):
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, use_tc):
     from mineral_b200.agents.ppo.models import ActorCritic
     from mineral_b200.nets.fused_towers import FusedTowers
 
@@ -608,11 +609,18 @@ def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma):
     ref = {k: p.grad.clone() for k, p in model.named_parameters()}
     for p in model.parameters():
         p.grad = torch.full_like(p, float("nan"))  # every gradient must be (over)written
-    ft = FusedTowers(model, rows, DEV)
-    mu2, ls2, v2 = ft.forward(x)
+    ft = FusedTowers(model, rows, DEV, use_tc=use_tc)
+    if use_tc and ft.use_tc:  # first-layer input through a padded row stride, as the PPO engine provides it
+        x_ld = (O + 3) // 4 * 4
+        xp = torch.zeros(rows, x_ld, device=DEV)
+        xp[:, :O] = x
+        x_in = xp
+    else:
+        x_in, x_ld = x, None
+    mu2, ls2, v2 = ft.forward(x_in, x_ld)
     scale_close(mu2, mu.detach(), 1e-5, "mu_raw"), scale_close(v2, v.detach(), 1e-5, "value")
     scale_close(ls2.expand(rows, A) if fixed_sigma else ls2, ls.detach(), 1e-5, "logstd")
-    ft.backward(x, g_mu, g_ls, g_v)
+    ft.backward(x_in, g_mu, g_ls, g_v)
     for k, p in model.named_parameters():
         # bias gradients here are sums of `rows` N(0,1) seeds that cancel to O(sqrt(rows)): both f32 summation orders
         # carry ~rows * 2^-24 absolute error, so they get a looser bound than the weights
