@@ -274,6 +274,23 @@ int mnr_ppo_loss_fwd_bwd(const float* mu_raw, const float* logstd, int logstd_ro
                          int64_t mb, int A, const mnr_ppo_loss_cfg_t* cfg /*host*/,
                          void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
+/* Fused policy/value HEADS + loss (two launches): reads the towers' last activations y3a / y3v (M,H), applies
+ * the mu / sigma / value heads (mineral/agents/ppo/models.py:136-151: w_mu (A,H), b_mu (A), w_v (H), b_v (1);
+ * learned sigma: w_sig (A,H), b_sig (A); fixed sigma: w_sig = NULL and b_sig = the sigma parameter (A)), runs
+ * everything mnr_ppo_loss_fwd_bwd does, and returns the gradients the towers' backward needs, dy3a / dy3v (M,H),
+ * plus every head parameter gradient (dw_sig = NULL with fixed sigma; db_sig then receives d sigma).
+ * g_mu / g_ls (M,A) and g_v (M) are scratch outputs.  H % 8 == 0, H <= 128, A <= 32. */
+size_t mnr_ppo_heads_workspace_bytes(int64_t M, int A, int H);
+int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, const float* w_mu, const float* b_mu,
+                               const float* w_v, const float* b_v, const float* w_sig, const float* b_sig,
+                               const float* actions, const float* old_neglogp, const float* advantages,
+                               const float* old_values, const float* returns, float* old_mu, float* old_sigma,
+                               int write_back, float* dy3a, float* dy3v, float* g_mu, float* g_ls, float* g_v,
+                               float* dw_mu, float* db_mu, float* dw_v, float* db_v, float* dw_sig, float* db_sig,
+                               float* metrics_out, float* mu_mean_out, float* sigma_mean_out, int64_t M, int A, int H,
+                               const mnr_ppo_loss_cfg_t* cfg /*host*/, void* workspace, size_t workspace_bytes,
+                               mnr_stream_t stream);
+
 /* Un-reduced module-level twins of the reference's loss functions (ppo.py:453-498): per-row value
  * and per-row derivative.  clip_count_out / ev_out single f32 (clip_frac, explained_var). */
 int mnr_actor_loss_rows(const float* old_neglogp, const float* neglogp, const float* advantages,

@@ -108,6 +108,8 @@ SIGNATURES = {
     "mnr_nstep_push": (i32, [C.POINTER(NStepIn), C.POINTER(NStepIn), C.POINTER(NStepOut), C.POINTER(NStepOut), vp, i32, i32, i32, i32, i32, i64, vp]),
     "mnr_ppo_loss_workspace_bytes": (sz, [i64, i32]),
     "mnr_ppo_loss_fwd_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, C.POINTER(PPOLossCfg), vp, sz, vp]),
+    "mnr_ppo_heads_workspace_bytes": (sz, [i64, i32, i32]),
+    "mnr_ppo_heads_loss_fwd_bwd": (i32, [vp] * 15 + [i32] + [vp] * 14 + [i64, i32, i32, C.POINTER(PPOLossCfg), vp, sz, vp]),
     "mnr_actor_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
     "mnr_critic_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
     "mnr_bounds_loss_rows": (i32, [vp, i64, i32, i32, f32, vp, vp, vp]),

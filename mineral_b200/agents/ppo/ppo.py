@@ -361,6 +361,8 @@ class _UpdateEngine:
         self.towers = None
         if cfg_get(a.ppo_config, 'fused_mlp', True) and FusedTowers.supported(a.model) and list(a.obs_space) == ['obs']:
             self.towers = FusedTowers(a.model, self.mb, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
+            if self.towers.fused_heads_ok:
+                self.heads_ws = ops.ppo_heads_workspace(self.mb, self.A, self.towers.widths[-1], dev)
         self.graph = None
         self._warm = 0
         self.graph_launches = 0  # kernels of ours inside one captured update
@@ -399,6 +401,19 @@ class _UpdateEngine:
                     else:
                         obs[k] = v[s:e]
                         x_ld = None
+                if self.towers is not None and self.towers.fused_heads_ok:
+                    # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward: no torch op, no autograd
+                    self.towers.forward_towers(obs['obs'], x_ld)
+                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), self.metrics[step], self.loss_cfg,
+                                                   self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
+                    self.towers.backward_towers(obs['obs'])
+                    if a.world > 1:
+                        import torch.distributed as dist
+                        dist.all_reduce(a.optim.flat_grad)
+                        dist.all_reduce(self.metrics[step])
+                    a.optim.step(max_norm, kl=self.metrics[step, 7:8], grad_norm_out=self.grad_norms[step:step + 1])
+                    step += 1
+                    continue
                 if self.towers is not None:
                     mu_raw, logstd, value = self.towers.forward(obs['obs'], x_ld)
                 else:

@@ -238,13 +238,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       ptx::mbar_arrive(&full_conv[st]);
     }
 
-    // ---- epilogue: TMEM -> registers -> global ---------------------------------------------------------
-    const int q4 = warp - 4;  // this warp may only touch TMEM lanes [32*q4, 32*q4+32)
-    const int row = i0 + 32 * q4 + lane;
+    // ---- epilogue: TMEM -> registers -> shared (row-major staging) -> coalesced global stores -------------
+    // Once tmem_full has fired every MMA has finished reading the pipeline stages and no TMA is in flight, so
+    // the stage memory is reused as a 128 x (BN+4) f32 staging tile.  A warp can only read its own quarter of
+    // the TMEM lanes (= its own 32 rows), writes those rows to its slice of the staging tile and then streams
+    // them out row by row with lanes along the columns: every store instruction writes full 128 B lines.
+    const int q4 = warp - 4;
     if (num_kb > 0) {
       ptx::mbar_wait(&tmem_full, 0);
       ptx::tc_fence_after();
     }
+    const int pitch = BN + 4;  // floats; +4 keeps the per-lane float4 row writes bank-conflict free
+    float* stg = reinterpret_cast<float*>(smem) + (size_t)(32 * q4) * pitch;
     for (int cc = 0; cc < (BN + 31) / 32; ++cc) {
       uint32_t r[32];
       if (num_kb > 0) {
@@ -254,33 +259,43 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = 0u;
       }
-      if (row < p.I) {
-        const int jb = j0 + cc * 32;
-        float* dst;
-        if (MODE == kDw) dst = p.partials + (((size_t)gi * p.splits + split) * p.I + row) * p.J + jb;
-        else dst = g.c + (size_t)row * p.ldc + jb;
-        const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (jb + 32 <= p.J);
-        if (vec) {
+      float* dstrow = stg + (size_t)lane * pitch + cc * 32;
 #pragma unroll
-          for (int q = 0; q < 32; q += 4) {
-            float4 v = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]), __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+      for (int q = 0; q < 32; q += 4)
+        if (cc * 32 + q < BN)
+          *reinterpret_cast<float4*>(dstrow + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
+                                                               __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
+    }
+    __syncwarp();
+    {
+      const int ncols = min(BN, p.J - j0);  // valid columns of this tile
+      float* cbase;
+      size_t ldo;
+      if (MODE == kDw) cbase = p.partials + ((size_t)gi * p.splits + split) * p.I * p.J, ldo = p.J;
+      else cbase = g.c, ldo = p.ldc;
+      const bool vec = (ncols % 4 == 0) && (ldo % 4 == 0) && (j0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
+      for (int rr = 0; rr < 32; ++rr) {
+        const int row = i0 + 32 * q4 + rr;
+        if (row >= p.I) break;
+        const float* src = stg + (size_t)rr * pitch;
+        float* dst = cbase + (size_t)row * ldo + j0;
+        if (vec) {
+          for (int c4 = lane; c4 < ncols / 4; c4 += 32) {
+            float4 v = *reinterpret_cast<const float4*>(src + 4 * c4);
             if (MODE == kFwd) {
               if (g.bias) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + jb + q));
-                v.x += b.x, v.y += b.y, v.z += b.z, v.w += b.w;
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + j0) + c4);
+                v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
               }
               v.x = act_fwd(v.x, act), v.y = act_fwd(v.y, act), v.z = act_fwd(v.z, act), v.w = act_fwd(v.w, act);
             }
-            *reinterpret_cast<float4*>(dst + q) = v;
+            *reinterpret_cast<float4*>(dst + 4 * c4) = v;
           }
         } else {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            if (jb + q < p.J) {
-              float v = __uint_as_float(r[q]);
-              if (MODE == kFwd) v = act_fwd(v + (g.bias ? __ldg(g.bias + jb + q) : 0.f), act);
-              dst[q] = v;
-            }
+          for (int c = lane; c < ncols; c += 32) {
+            float v = src[c];
+            if (MODE == kFwd) v = act_fwd(v + (g.bias ? __ldg(g.bias + j0 + c) : 0.f), act);
+            dst[c] = v;
           }
         }
       }
@@ -321,8 +336,17 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_gro
   const int NK = I * J;
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx < NK) {
+    const float* src = partials + (size_t)gi * splits * NK + idx;
     float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += __ldg(partials + ((size_t)gi * splits + z) * NK + idx);
+    int z = 0;
+    for (; z + 8 <= splits; z += 8) {  // 8 independent loads in flight, summed in a fixed order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(z + u) * NK);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; z < splits; ++z) s += __ldg(src + (size_t)z * NK);
     ra.w[gi][idx] = s;
   } else if (idx < NK + I && ra.b[gi]) {
     const int n = idx - NK;
@@ -468,8 +492,8 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
 
 namespace {
 int tc_dw_splits(int M, int tiles) {
-  int s = (2 * mnr_sm_count() + tiles - 1) / tiles;  // ~2 CTAs worth of work items per SM
-  const int max_s = (M + 255) / 256;                  // >= 256 rows (8 k-blocks) per CTA
+  int s = mnr_sm_count() / tiles;      // one wave: 1 CTA per SM (the kernel's smem footprint allows no more)
+  const int max_s = (M + 255) / 256;   // >= 256 rows (8 k-blocks) per CTA
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
 }

@@ -101,6 +101,11 @@ class FusedTowers:
     def forward(self, x, x_ld=None):
         """x (rows, in_dim) [row stride x_ld floats] -> (mu_raw (rows,A), logstd ((A,) parameter if fixed sigma
         else (rows,A)), value (rows,1))."""
+        self.forward_towers(x, x_ld)
+        return self.heads_forward()
+
+    def forward_towers(self, x, x_ld=None):
+        """Both towers up to their last activation (self.Y[-1])."""
         M, m = self.M, self.model
         x_ld = self.in_dim if x_ld is None else x_ld
         self._x_ld = x_ld
@@ -118,6 +123,10 @@ class FusedTowers:
                 ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=self.Y[i][t], bias=l.bias.data, N=n, K=k, lda=lda)
                                 for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
             inp = self.Y[i]
+
+    def heads_forward(self):
+        M, m = self.M, self.model
+        inp = self.Y[-1]
         h = self.widths[-1]
         heads = [dict(a=inp[0], b=m.mu.weight.data, c=self.mu_raw, bias=m.mu.bias.data, N=self.A, K=h),
                  dict(a=inp[1], b=m.value.weight.data, c=self.value, bias=m.value.bias.data, N=1, K=h)]
@@ -128,6 +137,29 @@ class FusedTowers:
 
     def backward(self, x, g_mu, g_ls, g_v):
         """Seeds: d loss / d (mu_raw, logstd, value), each (rows, .).  Writes every parameter's .grad."""
+        self.heads_backward(g_mu, g_ls, g_v)
+        self.backward_towers(x)
+
+    @property
+    def fused_heads_ok(self):
+        h = self.widths[-1]
+        return h % 8 == 0 and h <= 128 and self.A <= 32
+
+    def heads_loss_fwd_bwd(self, d, s, e, g_mu, g_ls, g_v, metrics, cfg, ws, mu_mean, sigma_mean):
+        """Heads forward + PPO loss + its backward + head parameter gradients + d loss / d Y[-1], two launches
+        (csrc/ppo_loss.cu: ppo_heads_loss_kernel, head_grads_kernel).  `d` is the env-major data dict, [s:e) the
+        minibatch rows."""
+        m = self.model
+        ya, yv = self.Y[-1]
+        fixed = self.fixed_sigma
+        ops.ppo_heads_loss_fwd_bwd(
+            ya, yv, m.mu.weight.data, m.mu.bias.data, m.value.weight.data, m.value.bias.data,
+            None if fixed else m.sigma.weight.data, m.sigma.data if fixed else m.sigma.bias.data,
+            d['actions'][s:e], d['neglogp'][s:e], d['advantages'][s:e], d['values'][s:e], d['returns'][s:e], d['mu'][s:e], d['sigma'][s:e],
+            self.dY[-1][0], self.dY[-1][1], g_mu, g_ls, g_v, m.mu.weight.grad, m.mu.bias.grad, m.value.weight.grad, m.value.bias.grad,
+            None if fixed else m.sigma.weight.grad, m.sigma.grad if fixed else m.sigma.bias.grad, metrics, cfg, ws, True, mu_mean, sigma_mean)
+
+    def heads_backward(self, g_mu, g_ls, g_v):
         M, m, top = self.M, self.model, self.L - 1
         h = self.widths[-1]
         ya, yv = self.Y[top]
@@ -143,7 +175,10 @@ class FusedTowers:
                               dict(a=g_v, b=m.value.weight.data, c=self.dY[top][1], N=1, K=h)], M, 0)
         if not self.fixed_sigma:
             ops.linear_bwd_input([dict(a=g_ls, b=m.sigma.weight.data, c=self.dY[top][0], N=self.A, K=h)], M, 0, accumulate=True)
-        # towers, top layer first; act'(.) is applied on the fly from the saved outputs
+
+    def backward_towers(self, x):
+        """Tower layers, top first, from self.dY[-1]; act'(.) is applied on the fly from the saved outputs."""
+        M, top = self.M, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
         for i in range(top, -1, -1):
             n, k = self.la[i].weight.shape

@@ -228,6 +228,24 @@ def ppo_loss_fwd_bwd(mu_raw, logstd, value, actions, old_neglogp, advantages, ol
         ptr(sigma_mean, F32, allow_none=True), mb, A, C.byref(cfg), ptr(ws, U8), ws.numel(), stream()), "mnr_ppo_loss_fwd_bwd")
 
 
+def ppo_heads_workspace(M, A, H, device):
+    return torch.zeros(lib.mnr_ppo_heads_workspace_bytes(M, A, H), dtype=U8, device=device)
+
+
+def ppo_heads_loss_fwd_bwd(y3a, y3v, w_mu, b_mu, w_v, b_v, w_sig, b_sig, actions, old_neglogp, advantages, old_values, returns,
+                           old_mu, old_sigma, dy3a, dy3v, g_mu, g_ls, g_v, dw_mu, db_mu, dw_v, db_v, dw_sig, db_sig, metrics, cfg, ws,
+                           write_back=True, mu_mean=None, sigma_mean=None):
+    M, H = y3a.shape
+    A = w_mu.shape[0]
+    o = lambda t: ptr(t, F32, allow_none=True)
+    check(lib.mnr_ppo_heads_loss_fwd_bwd(
+        ptr(y3a, F32, "y3a"), ptr(y3v, F32, "y3v"), ptr(w_mu, F32), ptr(b_mu, F32), ptr(w_v, F32), ptr(b_v, F32), o(w_sig), ptr(b_sig, F32),
+        ptr(actions, F32, "actions"), ptr(old_neglogp, F32), ptr(advantages, F32), ptr(old_values, F32), ptr(returns, F32),
+        ptr(old_mu, F32), ptr(old_sigma, F32), 1 if write_back else 0, ptr(dy3a, F32), ptr(dy3v, F32), ptr(g_mu, F32), ptr(g_ls, F32),
+        ptr(g_v, F32), ptr(dw_mu, F32), ptr(db_mu, F32), ptr(dw_v, F32), ptr(db_v, F32), o(dw_sig), ptr(db_sig, F32), ptr(metrics, F32),
+        o(mu_mean), o(sigma_mean), M, A, H, C.byref(cfg), ptr(ws, U8), ws.numel(), stream()), "mnr_ppo_heads_loss_fwd_bwd", kernels=2)
+
+
 # ---------------------------------------------------------------------------------------------
 # G  MLP towers
 # ---------------------------------------------------------------------------------------------

@@ -625,3 +625,65 @@ def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, use_tc):
         # bias gradients here are sums of `rows` N(0,1) seeds that cancel to O(sqrt(rows)): both f32 summation orders
         # carry ~rows * 2^-24 absolute error, so they get a looser bound than the weights
         scale_close(p.grad, ref[k], 5e-5 if k.endswith("bias") or k == "sigma" else 1e-5, f"grad {k}")
+
+
+@pytest.mark.parametrize("rows,A,H,fixed_sigma,dist_type", [(512, 8, 64, True, "normal"), (2048, 8, 64, False, "dreamerv3_normal"),
+                                                             (333, 3, 16, True, "normal"), (1000, 16, 128, False, "dreamerv3_normal"),
+                                                             (32768, 8, 64, True, "normal"), (300, 21, 64, True, "normal")])
+def test_fused_heads_loss_vs_unfused(rows, A, H, fixed_sigma, dist_type):
+    """ppo_heads_loss_kernel + head_grads_kernel == heads forward (SIMT) + ppo_loss_kernel + heads backward."""
+    from mineral_b200 import ops
+    from mineral_b200.agents.ppo.models import ActorCritic
+    from mineral_b200.nets.fused_towers import FusedTowers
+
+    torch.manual_seed(rows + A)
+    O = 12
+    dist_kwargs = dict(dist_type=dist_type, minstd=0.1, maxstd=1.0) if dist_type != "normal" else dict(dist_type="normal")
+    model = ActorCritic({"obs": (O,)}, A, mlp_kwargs=dict(units=[32, H], act_type="ELU"), fixed_sigma=fixed_sigma,
+                        actor_dist_kwargs=dist_kwargs).to(DEV)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(0.1 * torch.randn_like(p))
+    for p in model.parameters():
+        p.grad = torch.zeros_like(p)
+    ft = FusedTowers(model, rows, DEV, use_tc=False)
+    assert ft.fused_heads_ok
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.randn(rows, O, device=DEV, generator=g)
+    d = dict(actions=torch.randn(rows, A, device=DEV, generator=g), neglogp=torch.randn(rows, device=DEV, generator=g) + 8,
+             advantages=torch.randn(rows, device=DEV, generator=g), values=torch.randn(rows, 1, device=DEV, generator=g),
+             returns=torch.randn(rows, 1, device=DEV, generator=g), mu=torch.randn(rows, A, device=DEV, generator=g),
+             sigma=torch.rand(rows, A, device=DEV, generator=g) + 0.2)
+    cfg = ops.make_loss_cfg(dist_type, 0.1, 1.0, 0.2, False, True, 4.0, 0.002, 1e-3, "bound")
+    g_mu, g_ls, g_v = (torch.zeros(rows, A, device=DEV), torch.zeros(rows, A, device=DEV), torch.zeros(rows, 1, device=DEV))
+    ft.forward_towers(x)
+
+    # unfused reference path
+    d1 = {k: v.clone() for k, v in d.items()}
+    mu_raw, ls, value = ft.heads_forward()
+    m1, mm1, sm1 = torch.zeros(10, device=DEV), torch.zeros(A, device=DEV), torch.zeros(A, device=DEV)
+    ops.ppo_loss_fwd_bwd(mu_raw, ls.contiguous(), value, d1["actions"], d1["neglogp"], d1["advantages"], d1["values"], d1["returns"],
+                         d1["mu"], d1["sigma"], g_mu, g_ls, g_v, m1, cfg, ops.ppo_loss_workspace(rows, A, DEV), True, mm1, sm1)
+    ft.heads_backward(g_mu, g_ls, g_v)
+    head_names = [n for n, _ in model.named_parameters() if n.split(".")[0] in ("mu", "sigma", "value")]
+    ref_grads = {n: dict(model.named_parameters())[n].grad.clone() for n in head_names}
+    ref_dy = [t.clone() for t in ft.dY[-1]]
+
+    # fused path
+    for n in head_names:
+        dict(model.named_parameters())[n].grad.fill_(float("nan"))
+    for t in ft.dY[-1]:
+        t.fill_(float("nan"))
+    d2 = {k: v.clone() for k, v in d.items()}
+    m2, mm2, sm2 = torch.zeros(10, device=DEV), torch.zeros(A, device=DEV), torch.zeros(A, device=DEV)
+    ws = ops.ppo_heads_workspace(rows, A, H, DEV)
+    for _ in range(2):  # twice: tickets must self-reset
+        d2 = {k: v.clone() for k, v in d.items()}
+        ft.heads_loss_fwd_bwd(d2, 0, rows, g_mu, g_ls, g_v.view(-1), m2, cfg, ws, mm2, sm2)
+    scale_close(m2[:8], m1[:8], 1e-5, "metrics")
+    scale_close(mm2, mm1, 1e-5, "mu mean"), scale_close(sm2, sm1, 1e-5, "sigma mean")
+    scale_close(d2["mu"], d1["mu"], 1e-5, "mu write-back"), scale_close(d2["sigma"], d1["sigma"], 1e-5, "sigma write-back")
+    for t, r in zip(ft.dY[-1], ref_dy):
+        scale_close(t, r, 1e-5, "dY3")
+    for n in head_names:
+        scale_close(dict(model.named_parameters())[n].grad, ref_grads[n], 2e-5, f"head grad {n}")
