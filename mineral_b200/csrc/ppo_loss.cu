@@ -296,7 +296,7 @@ struct HeadsArgs {
   int A, H, write_back;
 };
 
-template <int AMAX>
+template <int AMAX, int HS>
 __global__ void __launch_bounds__(kHeadThreads) ppo_heads_loss_kernel(const __grid_constant__ HeadsArgs a,
                                                                       const __grid_constant__ mnr_ppo_loss_cfg_t cfg) {
   extern __shared__ float sh[];
@@ -304,7 +304,8 @@ __global__ void __launch_bounds__(kHeadThreads) ppo_heads_loss_kernel(const __gr
   __shared__ double s_red[6][kHeadThreads / 32];
   __shared__ mnr::Moments s_mom[2][kHeadThreads / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int A = a.A, H = a.H, hs = H / kTPR;
+  const int A = a.A, H = a.H;
+  constexpr int hs = HS;  // hidden elements per lane (H == 8 * HS)
   const bool learned = a.w_sig != nullptr;
   float* s_wmu = sh;                    // (A,H)
   float* s_wsig = s_wmu + A * H;        // (A,H) (learned only)
@@ -330,27 +331,33 @@ __global__ void __launch_bounds__(kHeadThreads) ppo_heads_loss_kernel(const __gr
     const bool valid = rraw < a.M;
     const int64_t row = valid ? rraw : a.M - 1;
     // ---- head forward: partial dots over this lane's hidden slice, all-reduced over the 8 lanes ----
-    float ya[kMaxHS], yv[kMaxHS];
+    float ya[HS], yv[HS];
     const float* pa = a.y3a + (size_t)row * H + s * hs;
     const float* pv = a.y3v + (size_t)row * H + s * hs;
+    if (HS % 4 == 0) {
 #pragma unroll
-    for (int u = 0; u < kMaxHS; ++u)
-      if (u < hs) ya[u] = __ldg(pa + u), yv[u] = __ldg(pv + u);
+      for (int u = 0; u < HS; u += 4) {
+        const float4 fa = __ldg(reinterpret_cast<const float4*>(pa + u)), fv = __ldg(reinterpret_cast<const float4*>(pv + u));
+        ya[u] = fa.x, ya[u + 1] = fa.y, ya[u + 2] = fa.z, ya[u + 3] = fa.w;
+        yv[u] = fv.x, yv[u + 1] = fv.y, yv[u + 2] = fv.z, yv[u + 3] = fv.w;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < HS; ++u) ya[u] = __ldg(pa + u), yv[u] = __ldg(pv + u);
+    }
     float mu_raw[AMAX], ls[AMAX];
     float value = 0.f;
 #pragma unroll
-    for (int u = 0; u < kMaxHS; ++u)
-      if (u < hs) value = fmaf(yv[u], s_wv[s * hs + u], value);
+    for (int u = 0; u < HS; ++u) value = fmaf(yv[u], s_wv[s * hs + u], value);
 #pragma unroll
     for (int j = 0; j < AMAX; ++j) {
       float pm = 0.f, pl = 0.f;
       if (j < A) {
 #pragma unroll
-        for (int u = 0; u < kMaxHS; ++u)
-          if (u < hs) {
-            pm = fmaf(ya[u], s_wmu[j * H + s * hs + u], pm);
-            if (learned) pl = fmaf(ya[u], s_wsig[j * H + s * hs + u], pl);
-          }
+        for (int u = 0; u < HS; ++u) {
+          pm = fmaf(ya[u], s_wmu[j * H + s * hs + u], pm);
+          if (learned) pl = fmaf(ya[u], s_wsig[j * H + s * hs + u], pl);
+        }
       }
       mu_raw[j] = pm, ls[j] = pl;
     }
@@ -433,9 +440,9 @@ __global__ void __launch_bounds__(kHeadThreads) ppo_heads_loss_kernel(const __gr
       if (lane < kTPR && j < A) atomicAdd(&s_col[j], cm), atomicAdd(&s_col[A + j], cs);
     }
     // ---- dY3 = g W over this lane's hidden slice (all-gather the row's g over its 8 lanes) ---------------------
-    float da[kMaxHS];
+    float da[HS];
 #pragma unroll
-    for (int u = 0; u < kMaxHS; ++u) da[u] = 0.f;
+    for (int u = 0; u < HS; ++u) da[u] = 0.f;
 #pragma unroll
     for (int j = 0; j < AMAX; ++j) {
       if (j < A) {  // warp-uniform
@@ -447,19 +454,26 @@ __global__ void __launch_bounds__(kHeadThreads) ppo_heads_loss_kernel(const __gr
           if (jj == j / kTPR) gmj = tm, glj = tl;
         }
 #pragma unroll
-        for (int u = 0; u < kMaxHS; ++u)
-          if (u < hs) {
-            da[u] = fmaf(gmj, s_wmu[j * H + s * hs + u], da[u]);
-            if (learned) da[u] = fmaf(glj, s_wsig[j * H + s * hs + u], da[u]);
-          }
+        for (int u = 0; u < HS; ++u) {
+          da[u] = fmaf(gmj, s_wmu[j * H + s * hs + u], da[u]);
+          if (learned) da[u] = fmaf(glj, s_wsig[j * H + s * hs + u], da[u]);
+        }
       }
     }
     if (valid) {
       float* oa = a.dy3a + (size_t)row * H + s * hs;
       float* ov = a.dy3v + (size_t)row * H + s * hs;
+      if (HS % 4 == 0) {
 #pragma unroll
-      for (int u = 0; u < kMaxHS; ++u)
-        if (u < hs) oa[u] = da[u], ov[u] = g_v * s_wv[s * hs + u];
+        for (int u = 0; u < HS; u += 4) {
+          *reinterpret_cast<float4*>(oa + u) = make_float4(da[u], da[u + 1], da[u + 2], da[u + 3]);
+          *reinterpret_cast<float4*>(ov + u) = make_float4(g_v * s_wv[s * hs + u], g_v * s_wv[s * hs + u + 1],
+                                                           g_v * s_wv[s * hs + u + 2], g_v * s_wv[s * hs + u + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < HS; ++u) oa[u] = da[u], ov[u] = g_v * s_wv[s * hs + u];
+      }
     }
   }
 
@@ -565,7 +579,21 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const __grid_constant__
 #pragma unroll
   for (int j = 0; j < AMAX; ++j) am[j] = 0.f, as[j] = 0.f;
   if (rp < rpar) {
-    for (int r = rp; r < nrows; r += rpar) {
+    int r = rp;
+    for (; r + 3 * rpar < nrows; r += 4 * rpar) {  // 8 independent loads in flight
+      float ya[4], yv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ya[q] = __ldg(a.y3a + (r0 + r + q * rpar) * H + h), yv[q] = __ldg(a.y3v + (r0 + r + q * rpar) * H + h);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* g = sg + (r + q * rpar) * GW;
+        av = fmaf(g[2 * A], yv[q], av);
+#pragma unroll
+        for (int j = 0; j < AMAX; ++j)
+          if (j < A) am[j] = fmaf(g[j], ya[q], am[j]), as[j] = fmaf(g[A + j], ya[q], as[j]);
+      }
+    }
+    for (; r < nrows; r += rpar) {
       const float ya = __ldg(a.y3a + (r0 + r) * H + h), yv = __ldg(a.y3v + (r0 + r) * H + h);
       const float* g = sg + r * GW;
       av = fmaf(g[2 * A], yv, av);
@@ -578,7 +606,7 @@ __global__ void __launch_bounds__(256) head_grads_kernel(const __grid_constant__
   const int PW = GW * H + GW;
   float* part = a.partials + (size_t)blockIdx.x * PW;
   __syncthreads();
-  float* red = sg;  // reuse: [rpar][GW][H] needs rpar*GW*H floats <= rows_per_cta*GW (host guarantees)
+  float* red = sg;  // reuse: [rpar][GW][H] needs rpar*GW*H <= 256*GW floats (host sizes the buffer for it)
   // bias sums first (they read sg), by the first GW threads
   float bias_sum = 0.f;
   if (tid < GW)
@@ -855,7 +883,7 @@ extern "C" size_t mnr_ppo_heads_workspace_bytes(int64_t M, int A, int H) {
   if (M <= 0 || A <= 0 || H <= 0) return 0;
   const size_t grid = (size_t)mnr_sm_count() * 4;
   const size_t loss = kHeader + grid * (sizeof(LossPartial) + sizeof(float) * 2 * (size_t)A);
-  const size_t rows_per_cta = 256;
+  const size_t rows_per_cta = 128;
   const size_t ctas = ((size_t)M + rows_per_cta - 1) / rows_per_cta;
   const size_t grads = 256 + ctas * (size_t)((2 * A + 1) * H + (2 * A + 1)) * sizeof(float);
   return ((loss + 255) / 256) * 256 + grads;
@@ -877,6 +905,7 @@ extern "C" int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, co
   MNR_CHECK_PTR(db_v); MNR_CHECK_PTR(db_sig); MNR_CHECK_PTR(metrics_out); MNR_CHECK_PTR(cfg); MNR_CHECK_PTR(workspace);
   if (w_sig && !dw_sig) return MNR_ENULL;
   if (M <= 0 || A <= 0 || A > 32 || H <= 0 || H % kTPR != 0 || H / kTPR > kMaxHS) return MNR_ESHAPE;
+  { const int q = H / kTPR; if (q != 1 && q != 2 && q != 4 && q != 8 && q != 16) return MNR_ESHAPE; }
   if (cfg->dist_type != MNR_DIST_NORMAL && cfg->dist_type != MNR_DIST_DREAMERV3_NORMAL) return MNR_EUNSUP;
   if (cfg->bounds_type != MNR_BOUNDS_BOUND && cfg->bounds_type != MNR_BOUNDS_REG) return MNR_EUNSUP;
   if (workspace_bytes < mnr_ppo_heads_workspace_bytes(M, A, H)) return MNR_EWORKSPACE;
@@ -889,20 +918,25 @@ extern "C" int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, co
                (unsigned char*)workspace, M, A, H, write_back};
   const size_t smem1 = (size_t)((w_sig ? 2 : 1) * A * H + H) * sizeof(float);
   const int grid1 = heads_grid(M);
-  if (A <= 8) ppo_heads_loss_kernel<8><<<grid1, kHeadThreads, smem1, mnr_cs(stream)>>>(ha, *cfg);
-  else if (A <= 16) ppo_heads_loss_kernel<16><<<grid1, kHeadThreads, smem1, mnr_cs(stream)>>>(ha, *cfg);
-  else ppo_heads_loss_kernel<32><<<grid1, kHeadThreads, smem1, mnr_cs(stream)>>>(ha, *cfg);
+#define MNR_HEADS_LAUNCH(AM, HSV) ppo_heads_loss_kernel<AM, HSV><<<grid1, kHeadThreads, smem1, mnr_cs(stream)>>>(ha, *cfg)
+#define MNR_HEADS_BY_HS(AM)                                                        \
+  switch (H / kTPR) {                                                              \
+    case 1: MNR_HEADS_LAUNCH(AM, 1); break;   case 2: MNR_HEADS_LAUNCH(AM, 2); break;   \
+    case 4: MNR_HEADS_LAUNCH(AM, 4); break;   case 8: MNR_HEADS_LAUNCH(AM, 8); break;   \
+    case 16: MNR_HEADS_LAUNCH(AM, 16); break; default: return MNR_ESHAPE;          \
+  }
+  if (A <= 8) { MNR_HEADS_BY_HS(8) } else if (A <= 16) { MNR_HEADS_BY_HS(16) } else { MNR_HEADS_BY_HS(32) }
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) return (int)e;
 
-  const int rows_per_cta = 256;
+  const int rows_per_cta = 128;
   const int GW = 2 * A + 1;
-  if ((256 / H) * GW * H > rows_per_cta * GW) return MNR_ESHAPE;  // reduction scratch must fit the staged g tile
   unsigned char* gws = (unsigned char*)workspace + loss_bytes;
   HeadGradArgs ga{y3a, y3v, g_mu, g_ls, g_v, dw_mu, db_mu, dw_sig, db_sig, dw_v, db_v, (float*)(gws + 256),
                   (unsigned int*)gws, M, A, H, rows_per_cta};
   const int grid2 = (int)((M + rows_per_cta - 1) / rows_per_cta);
-  const size_t smem2 = (size_t)rows_per_cta * GW * sizeof(float);
+  // staged g tile [rows_per_cta][GW], reused as the [256/H][GW][H] cross-phase reduction scratch
+  const size_t smem2 = (size_t)(rows_per_cta > 256 ? rows_per_cta : 256) * GW * sizeof(float);
   if (A <= 8) head_grads_kernel<8><<<grid2, 256, smem2, mnr_cs(stream)>>>(ga);
   else if (A <= 16) head_grads_kernel<16><<<grid2, 256, smem2, mnr_cs(stream)>>>(ga);
   else {
