@@ -344,6 +344,39 @@ def main():
     roofline = {"kernel": "post_rollout_kernel<true> (GAE + env-major pack + moment partials)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes": alg_bytes, "launch_ms": k_ms, "timing": "CUDA events on the launching stream, L2 flushed before each launch"}
+    # traffic of the same kernel from the committed ncu --set full capture (profiles/), per launch
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "post_rollout_traffic.json")))
+        if prof.get("workload") == args.workload:
+            roofline["traffic"] = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+            roofline["traffic_source"] = prof["source"]
+    except Exception:
+        pass
+
+    # ---- tensor-bound leg: the tcgen05 3xTF32 linear kernel on the widest hidden layer (forward) ----
+    roofline_tensor = None
+    tw = getattr(agent._engine, "towers", None)
+    if tw is not None and tw.use_tc and tw.L >= 2:
+        from mineral_b200 import ops
+        n, k = tw.la[1].weight.shape
+        groups = [dict(a=tw.Y[0][t], b=tw.w_hi[1][t], b_lo=tw.w_lo[1][t], c=tw.Y[1][t], bias=l.bias.data, N=n, K=k, lda=k, ldb=tw.w_ld[1])
+                  for t, l in enumerate((tw.la[1], tw.lv[1]))]
+        ts = []
+        for _ in range(20):
+            flush.zero_()
+            torch.cuda._sleep(400_000)
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ea.record(); ops.tc_linear_fwd(groups, tw.M, tw.act); eb.record(); torch.cuda.synchronize()
+            ts.append(ea.elapsed_time(eb))
+        t_ms = statistics.mean(sorted(ts)[:15])
+        flops = 2 * 2.0 * tw.M * n * k
+        tpeak = peaks.get("bf16_tflops", 1590.0)
+        roofline_tensor = {"kernel": f"tc_linear_kernel<FWD> 2 x ({tw.M}x{n}x{k}) tcgen05 kind::tf32, 3 MMAs per product (3xTF32)",
+                           "bound": "tensor", "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                           "frac": flops / (t_ms * 1e-3) / 1e12 / tpeak, "launch_ms": t_ms,
+                           "note": "achieved counts fp32-equivalent FLOPs (2MNK); the tensor pipe executes 3x that in tf32, whose dense "
+                                   "peak is half the bf16 figure used as `peak`"}
+
     sweep = None
     if args.kernel_sweep:
         from mineral_b200.agents.ppo.experience import ExperienceBuffer
@@ -388,6 +421,7 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_tensor": roofline_tensor,
         "cpu_baseline": cpu,
         "gae_normalise_hbm_gbs": achieved,
     }

@@ -91,7 +91,7 @@ struct Params {
   unsigned char* workspace;
 };
 
-constexpr int kEnvPerScalarCta = 32;
+constexpr int kEnvPerScalarCta = 32;  // the staging loops below use q >> 5 / q & 31
 
 // exact floor(q / d) for 0 <= q < 2^22, 1 <= d < 2^22 with inv = 1.0f / d
 __device__ __forceinline__ int fast_div(int q, float inv, int d) {
@@ -114,56 +114,73 @@ __device__ __forceinline__ void scalar_role(const Params& p, float* smem) {
   float* s_nlp = s_adv + kEnvPerScalarCta * pitch;
   float* s_done = s_nlp + kEnvPerScalarCta * pitch;
 
-  if (warp == 0) {
-    mnr::Welford wa, wv, wr;
-    wa.init(), wv.init(), wr.init();
-    if (lane < nb) {
-      const int n = n0 + lane;
-      float next_v = p.do_gae ? __ldg(p.last_values + n) : 0.f;
-      float carry = 0.f;
-#pragma unroll 8
-      for (int t = T - 1; t >= 0; --t) {
-        const size_t g = (size_t)t * N + n;
-        const float r = __ldg(p.rewards + g), v = __ldg(p.values + g), nlp = __ldg(p.neglogp + g);
-        const float d = (float)__ldg(p.dones + g);
-        float ret;
-        if (p.do_gae) {  // experience.py:100-108, same association order as scans.cu
-          const float alive = __fsub_rn(1.0f, d);
-          const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(p.gamma, next_v), alive)), v);
-          carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gamma_tau, alive), carry));
-          ret = __fadd_rn(carry, v);
-          next_v = v;
-          if (p.returns_tm) p.returns_tm[g] = ret;
-        } else {
-          ret = __ldg(p.returns_tm + g);
-        }
-        const float adv = __fsub_rn(ret, v);  // experience.py:119 (returns - values)
-        const int s = lane * pitch + t;
-        s_r[s] = r, s_v[s] = v, s_ret[s] = ret, s_adv[s] = adv, s_nlp[s] = nlp, s_done[s] = d;
-        wa.push(adv), wv.push(v), wr.push(ret);
-      }
-    }
-    const mnr::Moments m_adv = mnr::moments_warp_reduce(wa.to_moments());
-    const mnr::Moments m_val = mnr::moments_warp_reduce(wv.to_moments());
-    const mnr::Moments m_ret = mnr::moments_warp_reduce(wr.to_moments());
-    if (lane == 0) {
-      TilePartial* parts = reinterpret_cast<TilePartial*>(p.workspace + kHeaderBytes);
-      parts[blockIdx.x] = TilePartial{m_adv, m_val, m_ret};
-      if (blockIdx.x == 0) reinterpret_cast<unsigned int*>(p.workspace)[0] = (unsigned int)p.n_scalar;
+  // phase A (all threads): stage the tile's scalars, [t][n0 .. n0+nb) is one coalesced line per array and step;
+  // every load is independent, so they are all in flight together (one DRAM latency, not T of them)
+  for (int q = tid; q < T * kEnvPerScalarCta; q += kThreads) {
+    const int t = q >> 5, nl = q & 31;
+    if (nl < nb) {
+      const size_t g = (size_t)t * N + n0 + nl;
+      const int s = nl * pitch + t;
+      s_r[s] = __ldg(p.rewards + g), s_v[s] = __ldg(p.values + g), s_nlp[s] = __ldg(p.neglogp + g);
+      s_done[s] = (float)__ldg(p.dones + g);
+      if (!p.do_gae) s_ret[s] = __ldg(p.returns_tm + g);
     }
   }
   __syncthreads();
+  // phase B (one warp, one lane per env): the serial GAE recurrence out of shared memory
+  if (warp == 0 && lane < nb) {
+    float next_v = p.do_gae ? __ldg(p.last_values + n0 + lane) : 0.f;
+    float carry = 0.f;
+#pragma unroll 4
+    for (int t = T - 1; t >= 0; --t) {
+      const int s = lane * pitch + t;
+      const float v = s_v[s];
+      float ret;
+      if (p.do_gae) {  // experience.py:100-108, same association order as scans.cu
+        const float alive = __fsub_rn(1.0f, s_done[s]);
+        const float delta = __fsub_rn(__fadd_rn(s_r[s], __fmul_rn(__fmul_rn(p.gamma, next_v), alive)), v);
+        carry = __fadd_rn(delta, __fmul_rn(__fmul_rn(p.gamma_tau, alive), carry));
+        ret = __fadd_rn(carry, v);
+        next_v = v;
+        s_ret[s] = ret;
+      } else {
+        ret = s_ret[s];
+      }
+      s_adv[s] = __fsub_rn(ret, v);  // experience.py:119 (returns - values)
+    }
+  }
+  __syncthreads();
+  // time-major returns (storage_dict['returns']), coalesced along the envs
+  if (p.do_gae && p.returns_tm) {
+    for (int q = tid; q < T * kEnvPerScalarCta; q += kThreads) {
+      const int t = q >> 5, nl = q & 31;
+      if (nl < nb) p.returns_tm[(size_t)t * N + n0 + nl] = s_ret[nl * pitch + t];
+    }
+  }
   const size_t base = (size_t)n0 * T;
   const float invT = 1.0f / (float)T;
+  // parallel part: coalesced env-major write-out by all warps, moments accumulated on the way
+  mnr::Welford wa, wv, wr;
+  wa.init(), wv.init(), wr.init();
   for (int q = tid; q < nb * T; q += kThreads) {
     const int nl = fast_div(q, invT, T), t = q - nl * T;
     const int s = nl * pitch + t;
+    const float v = s_v[s], ret = s_ret[s], adv = s_adv[s];
     p.rewards_em[base + q] = s_r[s];
-    p.values_em[base + q] = s_v[s];
-    p.returns_em[base + q] = s_ret[s];
+    p.values_em[base + q] = v;
+    p.returns_em[base + q] = ret;
     p.neglogp_em[base + q] = s_nlp[s];
-    p.adv_em[base + q] = s_adv[s];
+    p.adv_em[base + q] = adv;
     p.dones_em[base + q] = (uint8_t)s_done[s];
+    wa.push(adv), wv.push(v), wr.push(ret);
+  }
+  const mnr::Moments m_adv = mnr::block_merge(wa.to_moments());
+  const mnr::Moments m_val = mnr::block_merge(wv.to_moments());
+  const mnr::Moments m_ret = mnr::block_merge(wr.to_moments());
+  if (tid == 0) {
+    TilePartial* parts = reinterpret_cast<TilePartial*>(p.workspace + kHeaderBytes);
+    parts[blockIdx.x] = TilePartial{m_adv, m_val, m_ret};
+    if (blockIdx.x == 0) reinterpret_cast<unsigned int*>(p.workspace)[0] = (unsigned int)p.n_scalar;
   }
 }
 
@@ -200,18 +217,18 @@ __device__ __forceinline__ void wide_role(const Params& p, float* smem, uint64_t
     __syncthreads();
   }
 
-  // out run: [nl][t][f] linear; smem: [t][nl][f]
-  const int per_env = T * w;
-  const int total = nb * per_env;
-  float* out = p.f[k].dst + (size_t)n0 * per_env;
-  const float inv_pe = 1.0f / (float)per_env, inv_w = 1.0f / (float)w;
-#pragma unroll 4
-  for (int q = tid; q < total; q += kThreads) {
-    const int nl = fast_div(q, inv_pe, per_env);
-    const int rem = q - nl * per_env;
-    const int t = fast_div(rem, inv_w, w);
-    const int f = rem - t * w;
-    mnr::st_stream(out + q, smem[t * run + nl * w + f]);
+  // smem: [t][nl][f] (pitch `run` per step);  out: [nl][t][f].  A thread owns a fixed (nl, f) pair and walks the T
+  // steps: per element one LDS, one STG and two pointer bumps, no index divisions.  At a given t consecutive lanes
+  // hold consecutive (nl, f) pairs: shared-memory reads are stride-1, global writes are w-float contiguous pieces.
+  float* out = p.f[k].dst + (size_t)n0 * T * w;
+  const int pairs = nb * w;
+  const float inv_w = 1.0f / (float)w;
+  for (int pidx = tid; pidx < pairs; pidx += kThreads) {
+    const int nl = fast_div(pidx, inv_w, w);
+    const float* sp = smem + pidx;
+    float* dp = out + (size_t)nl * (T - 1) * w + pidx;  // = out + (nl*T)*w + f
+#pragma unroll 8
+    for (int t = 0; t < T; ++t) mnr::st_stream(dp + (size_t)t * w, sp[(size_t)t * run]);
   }
 }
 
