@@ -354,6 +354,10 @@ size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int 
 int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
                              size_t workspace_bytes, mnr_stream_t stream);
 
+/* Profiling aid: enable != 0 makes CTA 0 of the tensor-core kernels record clock64() at every role's wait / done
+ * points; host_out (4 roles x 256 events x 2 tags int64, may be NULL) receives the last timeline. Synchronous. */
+int mnr_tc_trace(int enable, long long* host_out);
+
 /* hi = x with the 13 low mantissa bits cleared (a tf32), lo = x - hi, written to (rows, dst_ld) buffers
  * with zero-filled pad columns; all jobs in one launch. */
 typedef struct {

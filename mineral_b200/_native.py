@@ -124,6 +124,7 @@ SIGNATURES = {
     "mnr_tc_linear_bwd_input": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp]),
     "mnr_tc_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "mnr_tc_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_tc_trace": (i32, [i32, vp]),
     "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
     "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),
     "mnr_colsum_workspace_bytes": (sz, [i32]),

@@ -24,7 +24,7 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // 12 warps: producer, MMA, allocator, (idle), 4 converters, 4 epilogue
 constexpr int kBM = 128, kBK = 32;
 constexpr int kTileA = kBM * kBK * 4;  // 16 KiB
 constexpr int kChunk = 32 * 32 * 4;    // 4 KiB: one MN-major chunk (32 reduction rows x 32 floats)
@@ -32,6 +32,14 @@ constexpr int kMaxGroups = 2;
 constexpr int kMaxStages = 4;
 
 enum Mode { kFwd = 0, kDx = 1, kDw = 2 };
+
+// optional timeline of CTA 0 (debug / profiling aid): [role][event][tag] = clock64()
+__device__ long long g_trace[4 * 256 * 2];
+__device__ int g_trace_on = 0;
+#define TC_TRACE(role, idx, tag)                                                      \
+  do {                                                                               \
+    if (g_trace_on && blockIdx.x == 0 && (idx) < 256) g_trace[((role) * 256 + (idx)) * 2 + (tag)] = clock64(); \
+  } while (0)
 
 struct alignas(64) TcGroup {
   CUtensorMap a, s, b0, b1;  // b0: B (hi, or raw when converted in-kernel), b1: B lo (pre-split modes)
@@ -51,6 +59,7 @@ struct TcParams {
   float* partials;     // DW: [groups*splits][I][J] then bias [groups*splits][I]
   int want_bias;
   int n_groups;
+  int tiles_i, tiles_j;
 };
 
 __device__ __forceinline__ float act_fwd(float z, int act) {
@@ -75,33 +84,57 @@ __device__ __forceinline__ void split4(float4 v, float4& hi, float4& lo) {
   lo.x = v.x - hi.x, lo.y = v.y - hi.y, lo.z = v.z - hi.z, lo.w = v.w - hi.w;
 }
 
+// work item -> (group, split, tile row, tile column); consecutive items of one CTA walk the i tiles first
+struct TileCoord {
+  int gi, split, i0, j0, r_begin, num_kb;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int mode) {
+  TileCoord c;
+  const int ti = tile % p.tiles_i;
+  int rest = tile / p.tiles_i;
+  const int tj = rest % p.tiles_j;
+  rest /= p.tiles_j;
+  c.split = rest % p.splits;
+  c.gi = rest / p.splits;
+  c.i0 = ti * kBM, c.j0 = tj * p.BN;
+  int r_begin = 0, r_end = p.R;
+  if (mode == kDw) {
+    r_begin = c.split * p.rows_per_split;
+    r_end = min(p.R, r_begin + p.rows_per_split);
+  }
+  c.r_begin = r_begin;
+  c.num_kb = r_end > r_begin ? (r_end - r_begin + kBK - 1) / kBK : 0;
+  return c;
+}
+
+// PERSISTENT kernel: grid = min(#tiles, #SMs); every role loops over this CTA's tiles.  The fp32 accumulator is
+// double-buffered in TMEM (2 x BN columns) so the epilogue warps drain tile t while TMA / converters / MMA already
+// work on tile t+1.
+//   warp 0      TMA producer        warp 1   MMA issuer        warp 2   TMEM allocator
+//   warps 4-7   converters (fp32 -> hi / lo tf32 tiles in place, act' and bias-gradient sums fused)
+//   warps 8-11  epilogue (tcgen05.ld -> bias + activation -> per-warp 32x32 transpose in smem -> full-line stores)
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_constant__ TcParams p) {
   constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd), CONV_B = (MODE == kDw);
   extern __shared__ uint8_t smem_dyn[];
-  __shared__ __align__(8) uint64_t full_tma[kMaxStages], full_conv[kMaxStages], empty_bar[kMaxStages], tmem_full;
+  __shared__ __align__(8) uint64_t full_tma[kMaxStages], full_conv[kMaxStages], empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int gi = blockIdx.z / p.splits, split = blockIdx.z - gi * p.splits;
-  const TcGroup& g = p.g[gi];
-  const int i0 = blockIdx.x * kBM, j0 = blockIdx.y * p.BN;
   const int BN = p.BN, stages = p.stages;
+  const int n_tiles = p.tiles_i * p.tiles_j * p.n_groups * p.splits;
 
-  // stage layout (1024 B aligned: SWIZZLE_128B atoms are 8 x 128 B)
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-  const int offAlo = kTileA, offS = 2 * kTileA;
-  const int offB = HAS_S ? 3 * kTileA : 2 * kTileA;
+  // stage layout (1024 B aligned).  With a saved-output tile S (DX / DW) the low part of A is written over S:
+  // the converter thread that reads A[q] and S[q] writes hi -> A[q], lo -> S[q].
+  // (offset the extern array itself: integer round-trips make the compiler fall back to generic LD/ST)
+  uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int offAlo = kTileA;  // == offS
+  const int offB = 2 * kTileA;
   const int bytesB = BN * kBK * 4;
   const int offBlo = offB + bytesB;
   const int stage_bytes = offBlo + bytesB;
-
-  int r_begin = 0, r_end = p.R;
-  if (MODE == kDw) {
-    r_begin = split * p.rows_per_split;
-    r_end = min(p.R, r_begin + p.rows_per_split);
-  }
-  const int num_kb = r_end > r_begin ? (r_end - r_begin + kBK - 1) / kBK : 0;
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // 4 warps x [32][33] floats
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -109,13 +142,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       ptx::mbar_init(&full_conv[s], 128);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(&tmem_full, 1);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&tmem_full[b], 1);
+      ptx::mbar_init(&tmem_empty[b], 128);
+    }
     ptx::fence_mbar_init();
-    ptx::prefetch_tmap(&g.a);
-    ptx::prefetch_tmap(&g.b0);
   }
+  const uint32_t acc_stride = (uint32_t)((BN + 31) / 32 * 32);  // TMEM columns per accumulator (tcgen05.ld reads 32 at a time)
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < BN) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;
   if (warp == 2) ptx::tmem_alloc(&tmem_slot, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -126,29 +161,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     // ===== TMA producer ==========================================================================
     if (lane == 0) {
       const uint32_t tx_bytes = kTileA * (HAS_S ? 2 : 1) + bytesB * (CONV_B ? 1 : 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % stages;
-        ptx::mbar_wait(&empty_bar[st], ((kb / stages) & 1) ^ 1);
-        uint8_t* base = smem + (size_t)st * stage_bytes;
-        ptx::mbar_expect_tx(&full_tma[st], tx_bytes);
-        const int r0 = r_begin + kb * kBK;
-        if (!A_MN) {  // box [128 rows][32 floats along the reduction]
-          ptx::tma_load_2d(base, &g.a, r0, i0, &full_tma[st]);
-          if (HAS_S) ptx::tma_load_2d(base + offS, &g.s, r0, i0, &full_tma[st]);
-        } else {      // 4 chunks of [32 reduction rows][32 floats along i]
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(p, tile, MODE);
+        const TcGroup& g = p.g[tc.gi];
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+          const int st = kbg % stages;
+          ptx::mbar_wait(&empty_bar[st], ((kbg / stages) & 1) ^ 1);
+          TC_TRACE(0, kbg, 0);
+          uint8_t* base = smem + (size_t)st * stage_bytes;
+          ptx::mbar_expect_tx(&full_tma[st], tx_bytes);
+          const int r0 = tc.r_begin + kb * kBK;
+          if (!A_MN) {  // box [128 rows][32 floats along the reduction]
+            ptx::tma_load_2d(base, &g.a, r0, tc.i0, &full_tma[st]);
+            if (HAS_S) ptx::tma_load_2d(base + offAlo, &g.s, r0, tc.i0, &full_tma[st]);
+          } else {      // 4 chunks of [32 reduction rows][32 floats along i]
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            ptx::tma_load_2d(base + c * kChunk, &g.a, i0 + 32 * c, r0, &full_tma[st]);
-            ptx::tma_load_2d(base + offS + c * kChunk, &g.s, i0 + 32 * c, r0, &full_tma[st]);
+            for (int c = 0; c < 4; ++c) {
+              ptx::tma_load_2d(base + c * kChunk, &g.a, tc.i0 + 32 * c, r0, &full_tma[st]);
+              ptx::tma_load_2d(base + offAlo + c * kChunk, &g.s, tc.i0 + 32 * c, r0, &full_tma[st]);
+            }
           }
-        }
-        if (!B_MN) {  // box [BN rows][32 floats]
-          ptx::tma_load_2d(base + offB, &g.b0, r0, j0, &full_tma[st]);
-          ptx::tma_load_2d(base + offBlo, &g.b1, r0, j0, &full_tma[st]);
-        } else {
-          for (int c = 0; c < BN / 32; ++c) {
-            ptx::tma_load_2d(base + offB + c * kChunk, &g.b0, j0 + 32 * c, r0, &full_tma[st]);
-            if (!CONV_B) ptx::tma_load_2d(base + offBlo + c * kChunk, &g.b1, j0 + 32 * c, r0, &full_tma[st]);
+          if (!B_MN) {  // box [BN rows][32 floats]
+            ptx::tma_load_2d(base + offB, &g.b0, r0, tc.j0, &full_tma[st]);
+            ptx::tma_load_2d(base + offBlo, &g.b1, r0, tc.j0, &full_tma[st]);
+          } else {
+            for (int c = 0; c < BN / 32; ++c) {
+              ptx::tma_load_2d(base + offB + c * kChunk, &g.b0, tc.j0 + 32 * c, r0, &full_tma[st]);
+              if (!CONV_B) ptx::tma_load_2d(base + offBlo + c * kChunk, &g.b1, tc.j0 + 32 * c, r0, &full_tma[st]);
+            }
           }
         }
       }
@@ -157,173 +198,192 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     // ===== MMA issuer ===============================================================================
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % stages;
-        ptx::mbar_wait(&full_conv[st], (kb / stages) & 1);
+      // K-major: SWIZZLE_128B (layout 2), 8-row groups 1 KiB apart (SBO), LBO unused (16 B).
+      // MN-major (32-bit): SWIZZLE_128B_BASE32B (layout 1), 4-row reduction groups 512 B apart (SBO), 32-float
+      // chunks along M/N one 4 KiB box apart (LBO).
+      const uint64_t a_desc_hi = ptx::smem_desc(0, 0, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+      const uint64_t b_desc_hi = ptx::smem_desc(0, 0, B_MN ? 512 : 1024, B_MN ? 1 : 2);
+      const uint32_t a_desc_lo_const = ((A_MN ? (uint32_t)kChunk : 16u) >> 4) << 16;
+      const uint32_t b_desc_lo_const = ((B_MN ? (uint32_t)kChunk : 16u) >> 4) << 16;
+      uint32_t kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, tile, MODE);
+        const uint32_t acc = it & 1;
+        ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
-        const uint32_t base = ptx::smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t tmem_d = tmem_base + acc * acc_stride;
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+          const int st = kbg % stages;
+          ptx::mbar_wait(&full_conv[st], (kbg / stages) & 1);
+          TC_TRACE(2, kbg, 0);
+          ptx::tc_fence_after();
+          const uint32_t base = ptx::smem_u32(smem + (size_t)st * stage_bytes);
+          // descriptor = constant high word | (start address >> 4) in the low word: only the address changes
+          const uint32_t a_lo32 = (base >> 4) | a_desc_lo_const, alo_lo32 = ((base + offAlo) >> 4) | a_desc_lo_const;
+          const uint32_t b_lo32 = ((base + offB) >> 4) | b_desc_lo_const, blo_lo32 = ((base + offBlo) >> 4) | b_desc_lo_const;
 #pragma unroll
-        for (int k = 0; k < kBK / 8; ++k) {
-          // K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
-          const uint32_t a_off = A_MN ? k * 1024 : k * 32;
-          const uint32_t b_off = B_MN ? k * 1024 : k * 32;
-          // K-major: SWIZZLE_128B, 8-row groups 1 KiB apart.  MN-major (32-bit): SWIZZLE_128B_BASE32B, 4-row
-          // reduction groups 512 B apart, 32-float chunks along M/N one 4 KiB box apart.
-          const uint32_t a_lbo = A_MN ? kChunk : 16, b_lbo = B_MN ? kChunk : 16;
-          const uint32_t a_sbo = A_MN ? 512 : 1024, b_sbo = B_MN ? 512 : 1024;
-          const uint32_t a_lt = A_MN ? 1 : 2, b_lt = B_MN ? 1 : 2;
-          const uint64_t a_hi = ptx::smem_desc(base + a_off, a_lbo, a_sbo, a_lt);
-          const uint64_t a_lo = ptx::smem_desc(base + offAlo + a_off, a_lbo, a_sbo, a_lt);
-          const uint64_t b_hi = ptx::smem_desc(base + offB + b_off, b_lbo, b_sbo, b_lt);
-          const uint64_t b_lo = ptx::smem_desc(base + offBlo + b_off, b_lbo, b_sbo, b_lt);
-          ptx::mma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-          ptx::mma_tf32(tmem_base, a_hi, b_lo, idesc, 1u);
-          ptx::mma_tf32(tmem_base, a_hi, b_hi, idesc, 1u);
+          for (int k = 0; k < kBK / 8; ++k) {
+            // K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
+            const uint32_t a_step = (A_MN ? k * 1024 : k * 32) >> 4, b_step = (B_MN ? k * 1024 : k * 32) >> 4;
+            const uint64_t a_hi = a_desc_hi | (uint64_t)(a_lo32 + a_step), a_lo = a_desc_hi | (uint64_t)(alo_lo32 + a_step);
+            const uint64_t b_hi = b_desc_hi | (uint64_t)(b_lo32 + b_step), b_lo = b_desc_hi | (uint64_t)(blo_lo32 + b_step);
+            ptx::mma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
+            ptx::mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
+            ptx::mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+          }
+          ptx::tc_commit(&empty_bar[st]);  // stage reusable once these MMAs have read it
+          TC_TRACE(2, kbg, 1);
         }
-        ptx::tc_commit(&empty_bar[st]);  // stage reusable once these MMAs have read it
+        ptx::tc_commit(&tmem_full[acc]);   // accumulator complete (fires at once for an empty reduction range)
       }
-      ptx::tc_commit(&tmem_full);
     }
-  } else if (warp >= 4) {
-    // ===== converters, then epilogue ==================================================================
+  } else if (warp >= 4 && warp < 8) {
+    // ===== converters ====================================================================================
     const int t = tid - 128;
     const int act = p.act;
-    (void)0;
-    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int st = kb % stages;
-      ptx::mbar_wait(&full_tma[st], (kb / stages) & 1);
-      uint8_t* base = smem + (size_t)st * stage_bytes;
-      float4* A4 = reinterpret_cast<float4*>(base);
-      float4* Alo4 = reinterpret_cast<float4*>(base + offAlo);
-      const float4* S4 = reinterpret_cast<const float4*>(base + offS);
-      if (MODE != kDw) {
-        // element-wise: the swizzle is irrelevant, walk the tile linearly
+    uint32_t kbg = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(p, tile, MODE);
+      float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+        const int st = kbg % stages;
+        ptx::mbar_wait(&full_tma[st], (kbg / stages) & 1);
+        if (t == 0) TC_TRACE(1, kbg, 0);
+        uint8_t* base = smem + (size_t)st * stage_bytes;
+        float4* A4 = reinterpret_cast<float4*>(base);
+        float4* Alo4 = reinterpret_cast<float4*>(base + offAlo);  // holds S on entry when HAS_S
+        if (MODE != kDw) {
+          // element-wise: the swizzle is irrelevant, walk the tile linearly
 #pragma unroll 4
-        for (int q = t; q < kTileA / 16; q += 128) {
-          float4 a = A4[q];
-          if (HAS_S) {
-            const float4 s = S4[q];
+          for (int q = t; q < kTileA / 16; q += 128) {
+            float4 a = A4[q];
+            if (HAS_S) {
+              const float4 s = Alo4[q];
+              a.x *= act_bwd_from_y(s.x, act), a.y *= act_bwd_from_y(s.y, act);
+              a.z *= act_bwd_from_y(s.z, act), a.w *= act_bwd_from_y(s.w, act);
+            }
+            float4 hi, lo;
+            split4(a, hi, lo);
+            A4[q] = hi, Alo4[q] = lo;
+          }
+        } else {
+          // MN-major A: chunk c = 32 columns of i; thread owns logical 16 B slot j (4 columns) of rows p, p+4, ...
+          // SWIZZLE_128B_ATOM_32B stores the logical 32 B chunk (j >> 1) of row r at physical chunk (j >> 1) ^ (r & 3)
+          const int c = t >> 5, j = t & 7, ph = (t & 31) >> 3;
+#pragma unroll
+          for (int rr = 0; rr < 8; ++rr) {
+            const int r = ph + 4 * rr;
+            const int q = c * (kChunk / 16) + r * 8 + ((((j >> 1) ^ (r & 3)) << 1) | (j & 1));
+            float4 a = A4[q];
+            const float4 s = Alo4[q];
             a.x *= act_bwd_from_y(s.x, act), a.y *= act_bwd_from_y(s.y, act);
             a.z *= act_bwd_from_y(s.z, act), a.w *= act_bwd_from_y(s.w, act);
+            bsum.x += a.x, bsum.y += a.y, bsum.z += a.z, bsum.w += a.w;
+            float4 hi, lo;
+            split4(a, hi, lo);
+            A4[q] = hi, Alo4[q] = lo;
           }
-          float4 hi, lo;
-          split4(a, hi, lo);
-          A4[q] = hi, Alo4[q] = lo;
+          float4* B4 = reinterpret_cast<float4*>(base + offB);
+          float4* Blo4 = reinterpret_cast<float4*>(base + offBlo);
+          for (int q = t; q < bytesB / 16; q += 128) {
+            float4 hi, lo;
+            split4(B4[q], hi, lo);
+            B4[q] = hi, Blo4[q] = lo;
+          }
         }
-      } else {
-        // MN-major A: chunk c = 32 columns of i; thread owns logical 16 B slot j (4 columns) of rows p, p+4, ...
-        // SWIZZLE_128B_ATOM_32B stores the logical 32 B chunk (j >> 1) of row r at physical chunk (j >> 1) ^ (r & 3)
-        const int c = t >> 5, j = t & 7, ph = (t & 31) >> 3;
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_conv[st]);
+        if (t == 0) TC_TRACE(1, kbg, 1);
+      }
+      if (MODE == kDw && p.want_bias && tc.j0 == 0) {
+        // fold the 4 row phases (lanes j, j+8, j+16, j+24); lanes 0..7 then own 4 columns each of chunk c = warp-4
+        bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 8), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 8);
+        bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 8), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 8);
+        bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 16), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 16);
+        bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 16), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 16);
+        if (lane < 8) {
+          float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)tc.gi * p.splits + tc.split) * p.I;
+          const int n = tc.i0 + 32 * (warp - 4) + 4 * lane;
+          const float vals[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
 #pragma unroll
-        for (int rr = 0; rr < 8; ++rr) {
-          const int r = ph + 4 * rr;
-          const int q = c * (kChunk / 16) + r * 8 + ((((j >> 1) ^ (r & 3)) << 1) | (j & 1));
-          float4 a = A4[q];
-          const float4 s = S4[q];
-          a.x *= act_bwd_from_y(s.x, act), a.y *= act_bwd_from_y(s.y, act);
-          a.z *= act_bwd_from_y(s.z, act), a.w *= act_bwd_from_y(s.w, act);
-          bsum.x += a.x, bsum.y += a.y, bsum.z += a.z, bsum.w += a.w;
-          float4 hi, lo;
-          split4(a, hi, lo);
-          A4[q] = hi, Alo4[q] = lo;
-        }
-        float4* B4 = reinterpret_cast<float4*>(base + offB);
-        float4* Blo4 = reinterpret_cast<float4*>(base + offBlo);
-        for (int q = t; q < bytesB / 16; q += 128) {
-          float4 hi, lo;
-          split4(B4[q], hi, lo);
-          B4[q] = hi, Blo4[q] = lo;
+          for (int u = 0; u < 4; ++u)
+            if (n + u < p.I) bp[n + u] = vals[u];
         }
       }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&full_conv[st]);
     }
-
-    const int q4 = warp - 4;
-    if (MODE == kDw && p.want_bias && blockIdx.y == 0) {
-      // fold the 4 row phases (lanes j, j+8, j+16, j+24), then lanes 0..7 own 4 columns each of chunk c = warp-4
-      bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 8), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 8);
-      bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 8), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 8);
-      bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 16), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 16);
-      bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 16), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 16);
-      if (lane < 8) {
-        float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)gi * p.splits + split) * p.I;
-        const int n = i0 + 32 * q4 + 4 * lane;
-        const float vals[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (n + u < p.I) bp[n + u] = vals[u];
-      }
-    }
-  }
-
-  // ===== epilogue, all 8 warps: TMEM -> registers -> shared (row-major staging) -> coalesced global stores ====
-  // Once tmem_full has fired every MMA has finished reading the pipeline stages and no TMA is in flight, so the
-  // stage memory is reused as a 128 x (BN+4) f32 staging tile.  A warp can only read its own quarter (warp % 4)
-  // of the TMEM lanes; the two warps of a quarter take alternate 32-column chunks.  After a CTA barrier the tile
-  // is streamed out 16 rows per warp with lanes along the columns: every store instruction writes full lines.
-  {
+  } else if (warp >= 8) {
+    // ===== epilogue: TMEM -> registers -> (bias, act) -> 32x32 transpose in smem -> full 128 B line stores ========
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*quarter, 32*quarter+32)
     const int act = p.act;
-    if (num_kb > 0) {
-      ptx::mbar_wait(&tmem_full, 0);
+    float* stg = epi_stage + (size_t)(warp - 8) * 32 * 33;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, tile, MODE);
+      const TcGroup& g = p.g[tc.gi];
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      if (tid == 256) TC_TRACE(3, it, 0);
       ptx::tc_fence_after();
-    }
-    const int pitch = BN + 4;  // floats; +4 keeps the per-lane float4 row writes bank-conflict free
-    float* stage_tile = reinterpret_cast<float*>(smem);
-    const int quarter = warp & 3, half = warp >> 2;
-    for (int cc = half; cc < (BN + 31) / 32; cc += 2) {
-      uint32_t r[32];
-      if (num_kb > 0) {
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(cc * 32), r);
-        ptx::tmem_ld_wait();
-      } else {
+      float* cbase;
+      size_t ldo;
+      if (MODE == kDw) cbase = p.partials + ((size_t)tc.gi * p.splits + tc.split) * p.I * p.J, ldo = p.J;
+      else cbase = g.c, ldo = p.ldc;
+      const int row_base = tc.i0 + 32 * quarter;
+      for (int cc = 0; cc < (BN + 31) / 32; ++cc) {
+        uint32_t r[32];
+        if (tc.num_kb > 0) {
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + acc * acc_stride + (uint32_t)(cc * 32), r);
+          ptx::tmem_ld_wait();
+        } else {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) r[q] = 0u;
-      }
-      float* dstrow = stage_tile + (size_t)(32 * quarter + lane) * pitch + cc * 32;
+          for (int q = 0; q < 32; ++q) r[q] = 0u;
+        }
+        const int jb = tc.j0 + cc * 32;
+        // lane = row: bias + activation applied here would need a per-column bias per register; instead park the
+        // raw row (pitch 33: conflict-free both ways) and finish per column below
 #pragma unroll
-      for (int q = 0; q < 32; q += 4)
-        if (cc * 32 + q < BN)
-          *reinterpret_cast<float4*>(dstrow + q) = make_float4(__uint_as_float(r[q]), __uint_as_float(r[q + 1]),
-                                                               __uint_as_float(r[q + 2]), __uint_as_float(r[q + 3]));
-    }
-    ptx::tc_fence_before();
-    __syncthreads();
-    const int ncols = min(BN, p.J - j0);  // valid columns of this tile
-    float* cbase;
-    size_t ldo;
-    if (MODE == kDw) cbase = p.partials + ((size_t)gi * p.splits + split) * p.I * p.J, ldo = p.J;
-    else cbase = g.c, ldo = p.ldc;
-    const bool vec = (ncols % 4 == 0) && (ldo % 4 == 0) && (j0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(cbase) & 15) == 0);
-    for (int rr = 0; rr < 16; ++rr) {
-      const int rl = 16 * warp + rr;
-      const int row = i0 + rl;
-      if (row >= p.I) break;
-      const float* src = stage_tile + (size_t)rl * pitch;
-      float* dst = cbase + (size_t)row * ldo + j0;
-      if (vec) {
-        for (int c4 = lane; c4 < ncols / 4; c4 += 32) {
-          float4 v = *reinterpret_cast<const float4*>(src + 4 * c4);
-          if (MODE == kFwd) {
-            if (g.bias) {
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(g.bias + j0) + c4);
-              v.x += bb.x, v.y += bb.y, v.z += bb.z, v.w += bb.w;
+        for (int q = 0; q < 32; ++q) stg[lane * 33 + q] = __uint_as_float(r[q]);
+        __syncwarp();
+        // lane = column: every store instruction writes one full 128 B line of one output row.  Batches of 8 rows:
+        // 8 independent LDS, then the math, then 8 stores (a guarded one-row-at-a-time loop runs as one long
+        // dependent chain: ~100 cycles per row).
+        const int col = jb + lane;
+        const bool col_ok = col < p.J && cc * 32 + lane < BN;
+        float bias = 0.f;
+        if (MODE == kFwd && col_ok && g.bias) bias = __ldg(g.bias + col);
+        const int rows_valid = min(32, p.I - row_base);
+        float* out = cbase + (size_t)row_base * ldo + col;
+        if (rows_valid == 32) {
+#pragma unroll
+          for (int r0 = 0; r0 < 32; r0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = stg[(r0 + u) * 33 + lane];
+            if (MODE == kFwd) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) v[u] = act_fwd(v[u] + bias, act);
             }
-            v.x = act_fwd(v.x, act), v.y = act_fwd(v.y, act), v.z = act_fwd(v.z, act), v.w = act_fwd(v.w, act);
+            if (col_ok) {
+#pragma unroll
+              for (int u = 0; u < 8; ++u) out[(size_t)(r0 + u) * ldo] = v[u];
+            }
           }
-          *reinterpret_cast<float4*>(dst + 4 * c4) = v;
+        } else {
+          for (int rr = 0; rr < rows_valid; ++rr) {
+            float v = stg[rr * 33 + lane];
+            if (MODE == kFwd) v = act_fwd(v + bias, act);
+            if (col_ok) out[(size_t)rr * ldo] = v;
+          }
         }
-      } else {
-        for (int c = lane; c < ncols; c += 32) {
-          float v = src[c];
-          if (MODE == kFwd) v = act_fwd(v + (g.bias ? __ldg(g.bias + j0 + c) : 0.f), act);
-          dst[c] = v;
-        }
+        __syncwarp();
       }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty[acc]);
+      if (tid == 256) TC_TRACE(3, it, 1);
     }
   }
 
+  ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
@@ -418,17 +478,24 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
   return r == CUDA_SUCCESS ? MNR_OK : MNR_EUNSUP;
 }
 
+constexpr int kEpiStageBytes = 4 * 32 * 33 * 4;
+
 int pick_stages(int mode, int BN) {
-  const int stage = (mode == kFwd ? 2 : 3) * kTileA + 2 * BN * kBK * 4;
-  int s = (227 * 1024 - 2048) / stage;
+  (void)mode;
+  const int stage = 2 * kTileA + 2 * BN * kBK * 4;
+  int s = (227 * 1024 - 2048 - kEpiStageBytes) / stage;
   if (s > kMaxStages) s = kMaxStages;
   return s;
 }
 
 template <int MODE>
-int launch(const TcParams& p, dim3 grid, cudaStream_t stream) {
-  const int stage = (MODE == kFwd ? 2 : 3) * kTileA + 2 * p.BN * kBK * 4;
-  const size_t smem = (size_t)p.stages * stage + 1024;
+int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
+  p.tiles_i = (int)tiles.x, p.tiles_j = (int)tiles.y;
+  const int n_tiles = (int)(tiles.x * tiles.y * tiles.z);
+  const int sms = mnr_sm_count();
+  dim3 grid(n_tiles < sms ? n_tiles : sms);  // persistent: one CTA per SM walks the tiles
+  const int stage = 2 * kTileA + 2 * p.BN * kBK * 4;
+  const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
   cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   tc_linear_kernel<MODE><<<grid, kThreads, smem, stream>>>(p);
@@ -570,4 +637,15 @@ extern "C" int mnr_split_tf32(const mnr_split_job_t* jobs, int n_jobs, mnr_strea
   dim3 grid((max_total + 255) / 256 > 64 ? 64 : (max_total + 255) / 256, n_jobs);
   split_kernel<<<grid, 256, 0, mnr_cs(stream)>>>(js);
   MNR_LAUNCH_RESULT();
+}
+
+// debug: enable / read the CTA-0 timeline (clock64 ticks), 4 roles x 256 events x 2 tags
+extern "C" int mnr_tc_trace(int enable, long long* host_out) {
+  cudaError_t e = cudaMemcpyToSymbol(g_trace_on, &enable, sizeof(int));
+  if (e != cudaSuccess) return (int)e;
+  if (host_out) {
+    e = cudaMemcpyFromSymbol(host_out, g_trace, sizeof(long long) * 4 * 256 * 2);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return MNR_OK;
 }
