@@ -24,7 +24,8 @@
 
 namespace {
 
-constexpr int kThreads = 384;  // 12 warps: producer, MMA, allocator, (idle), 4 converters, 4 epilogue
+constexpr int kThreads = 512;  // 16 warps: producer, MMA, allocator, (idle), 4 converters, 8 epilogue
+constexpr int kEpiWarps = 8;
 constexpr int kBM = 128, kBK = 32;
 constexpr int kTileA = kBM * kBK * 4;  // 16 KiB
 constexpr int kChunk = 32 * 32 * 4;    // 4 KiB: one MN-major chunk (32 reduction rows x 32 floats)
@@ -62,6 +63,18 @@ struct TcParams {
   int tiles_i, tiles_j;
 };
 
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float z) {
+  if (ACT == 1) return z > 0.f ? z : __expf(z) - 1.f;
+  if (ACT == 2) return fmaxf(z, 0.f);
+  return z;
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd_t(float y) {
+  if (ACT == 1) return y > 0.f ? 1.f : y + 1.f;
+  if (ACT == 2) return y > 0.f ? 1.f : 0.f;
+  return 1.f;
+}
 __device__ __forceinline__ float act_fwd(float z, int act) {
   switch (act) {
     case 1: return z > 0.f ? z : __expf(z) - 1.f;  // ex2.approx path: abs error < 1e-6 on (-1, 0], the epilogue is
@@ -112,8 +125,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
 // work on tile t+1.
 //   warp 0      TMA producer        warp 1   MMA issuer        warp 2   TMEM allocator
 //   warps 4-7   converters (fp32 -> hi / lo tf32 tiles in place, act' and bias-gradient sums fused)
-//   warps 8-11  epilogue (tcgen05.ld -> bias + activation -> per-warp 32x32 transpose in smem -> full-line stores)
-template <int MODE>
+//   warps 8-15  epilogue (tcgen05.ld -> bias + activation -> per-warp 32x32 transpose in smem -> full-line stores)
+template <int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_constant__ TcParams p) {
   constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd), CONV_B = (MODE == kDw);
   extern __shared__ uint8_t smem_dyn[];
@@ -134,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   const int bytesB = BN * kBK * 4;
   const int offBlo = offB + bytesB;
   const int stage_bytes = offBlo + bytesB;
-  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // 4 warps x [32][33] floats
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // 8 warps x [32][33] floats
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], 128);
+      ptx::mbar_init(&tmem_empty[b], kEpiWarps * 32);
     }
     ptx::fence_mbar_init();
   }
@@ -240,7 +253,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   } else if (warp >= 4 && warp < 8) {
     // ===== converters ====================================================================================
     const int t = tid - 128;
-    const int act = p.act;
     uint32_t kbg = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile, MODE);
@@ -259,8 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
             float4 a = A4[q];
             if (HAS_S) {
               const float4 s = Alo4[q];
-              a.x *= act_bwd_from_y(s.x, act), a.y *= act_bwd_from_y(s.y, act);
-              a.z *= act_bwd_from_y(s.z, act), a.w *= act_bwd_from_y(s.w, act);
+              a.x *= act_bwd_t<ACT>(s.x), a.y *= act_bwd_t<ACT>(s.y);
+              a.z *= act_bwd_t<ACT>(s.z), a.w *= act_bwd_t<ACT>(s.w);
             }
             float4 hi, lo;
             split4(a, hi, lo);
@@ -276,8 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
             const int q = c * (kChunk / 16) + r * 8 + ((((j >> 1) ^ (r & 3)) << 1) | (j & 1));
             float4 a = A4[q];
             const float4 s = Alo4[q];
-            a.x *= act_bwd_from_y(s.x, act), a.y *= act_bwd_from_y(s.y, act);
-            a.z *= act_bwd_from_y(s.z, act), a.w *= act_bwd_from_y(s.w, act);
+            a.x *= act_bwd_t<ACT>(s.x), a.y *= act_bwd_t<ACT>(s.y);
+            a.z *= act_bwd_t<ACT>(s.z), a.w *= act_bwd_t<ACT>(s.w);
             bsum.x += a.x, bsum.y += a.y, bsum.z += a.z, bsum.w += a.w;
             float4 hi, lo;
             split4(a, hi, lo);
@@ -314,8 +326,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   } else if (warp >= 8) {
     // ===== epilogue: TMEM -> registers -> (bias, act) -> 32x32 transpose in smem -> full 128 B line stores ========
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*quarter, 32*quarter+32)
-    const int act = p.act;
     float* stg = epi_stage + (size_t)(warp - 8) * 32 * 33;
+    const int half = (warp - 8) >> 2;  // the two warps of a TMEM quarter take alternate 32-column chunks
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile, MODE);
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       if (MODE == kDw) cbase = p.partials + ((size_t)tc.gi * p.splits + tc.split) * p.I * p.J, ldo = p.J;
       else cbase = g.c, ldo = p.ldc;
       const int row_base = tc.i0 + 32 * quarter;
-      for (int cc = 0; cc < (BN + 31) / 32; ++cc) {
+      for (int cc = half; cc < (BN + 31) / 32; cc += kEpiWarps / 4) {
         uint32_t r[32];
         if (tc.num_kb > 0) {
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + acc * acc_stride + (uint32_t)(cc * 32), r);
@@ -361,7 +373,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
             for (int u = 0; u < 8; ++u) v[u] = stg[(r0 + u) * 33 + lane];
             if (MODE == kFwd) {
 #pragma unroll
-              for (int u = 0; u < 8; ++u) v[u] = act_fwd(v[u] + bias, act);
+              for (int u = 0; u < 8; ++u) v[u] = act_fwd_t<ACT>(v[u] + bias);
             }
             if (col_ok) {
 #pragma unroll
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
         } else {
           for (int rr = 0; rr < rows_valid; ++rr) {
             float v = stg[rr * 33 + lane];
-            if (MODE == kFwd) v = act_fwd(v + bias, act);
+            if (MODE == kFwd) v = act_fwd_t<ACT>(v + bias);
             if (col_ok) out[(size_t)rr * ldo] = v;
           }
         }
@@ -478,7 +490,7 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
   return r == CUDA_SUCCESS ? MNR_OK : MNR_EUNSUP;
 }
 
-constexpr int kEpiStageBytes = 4 * 32 * 33 * 4;
+constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;
 
 int pick_stages(int mode, int BN) {
   (void)mode;
@@ -496,9 +508,17 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   dim3 grid(n_tiles < sms ? n_tiles : sms);  // persistent: one CTA per SM walks the tiles
   const int stage = 2 * kTileA + 2 * p.BN * kBK * 4;
   const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaSuccess;
+#define MNR_TC_LAUNCH(ACTV)                                                                                              \
+  e = cudaFuncSetAttribute(tc_linear_kernel<MODE, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+  if (e == cudaSuccess) tc_linear_kernel<MODE, ACTV><<<grid, kThreads, smem, stream>>>(p);
+  switch (p.act) {
+    case 1: MNR_TC_LAUNCH(1) break;
+    case 2: MNR_TC_LAUNCH(2) break;
+    default: MNR_TC_LAUNCH(0) break;
+  }
+#undef MNR_TC_LAUNCH
   if (e != cudaSuccess) return (int)e;
-  tc_linear_kernel<MODE><<<grid, kThreads, smem, stream>>>(p);
   e = cudaPeekAtLastError();
   return e == cudaSuccess ? MNR_OK : (int)e;
 }
