@@ -34,7 +34,7 @@ WORKLOADS = {
 }
 
 
-def make_cfg(w, device, multi_gpu, cuda_graph):
+def make_cfg(w, device, multi_gpu, cuda_graph, peer=True):
     from oracle.reference_shim import to_attr
 
     mb = w["T"] * w["N"] // w["minibatches"]
@@ -54,7 +54,7 @@ def make_cfg(w, device, multi_gpu, cuda_graph):
                             gamma=0.99, tau=0.95, entropy_coef=0.0, e_clip=0.2, use_smooth_clamp=False, critic_coef=4,
                             bounds_loss_coef=1e-4, bounds_type="bound", mini_epochs=w["mini_epochs"], optim_type=optim_type,
                             optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008, max_grad_norm=mgn,
-                            truncate_grads=True, cuda_graph=cuda_graph))))
+                            truncate_grads=True, cuda_graph=cuda_graph, peer_allreduce=peer))))
 
 
 def oracle_setup(w, seed=0):
@@ -195,6 +195,8 @@ def main():
     ap.add_argument("--workload", default="ppo_ant_4096x32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying one CUDA graph per update")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: exchange gradients / statistics with torch.distributed (NCCL) calls instead of "
+                                                        "the fused peer-memory kernels (comparison only)")
     ap.add_argument("--kernel-sweep", action="store_true", help="also time the fused post-rollout kernel over rollout sizes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -223,7 +225,7 @@ def main():
     T, N, O, A = w["T"], w["N"], w["O"], w["A"]
     B = T * N
     torch.manual_seed(0)
-    agent = PPO(make_cfg(w, dev, world > 1, cuda_graph=not args.no_graph), env=SynthEnv(4, O, A, 1))
+    agent = PPO(make_cfg(w, dev, world > 1, cuda_graph=not args.no_graph, peer=not args.nccl), env=SynthEnv(4, O, A, 1))
     agent.set_train()
     if world > 1:  # identical initial weights on every rank
         dist.broadcast(agent.optim.flat, 0)
@@ -415,7 +417,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "envs_per_gpu": N, "horizon": T, "obs": O, "act": A, "mlp": w["units"], "variant": w["variant"],
                    "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "minibatch_rows": B // w["minibatches"],
-                   "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": bool(agent.use_cuda_graph and world == 1),
+                   "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": agent._engine.graph is not None,
+                   "exchange": ("none (1 GPU)" if world == 1 else "fused peer-memory all-reduce + clip + Adam kernel over NVLink (csrc/peer.cu)"
+                                if agent.comm is not None else "torch.distributed NCCL all-reduce"),
                    "l2": "256 MiB read-flush between timed steps", "parallelism": f"env-sharded dp{world}"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

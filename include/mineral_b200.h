@@ -414,6 +414,60 @@ int mnr_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int mnr_kl_lr_update(mnr_optim_state_t* st, double kl_threshold, double min_lr, double max_lr,
                      float* avg_kl_out, double* lr_out, mnr_stream_t stream);
 
+/* Single-GPU fused optimizer step: mnr_grad_norm_prepare + mnr_adam_step in ONE launch (grid-wide
+ * barrier between the norm and the update; grid <= #SMs so every CTA is resident).  n % 4 == 0, all
+ * buffers 16 B aligned.  workspace: mnr_fused_adam_workspace_bytes() bytes, zero-filled once. */
+size_t mnr_fused_adam_workspace_bytes(void);
+int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
+                        float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
+                        mnr_optim_state_t* st, const float* kl, float* grad_norm_out, void* workspace,
+                        size_t workspace_bytes, mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * a23  multi-GPU exchange over NVLink / NVSwitch PEER MEMORY (one process per GPU).  Replaces the
+ *      DDP gradient all-reduce inside accelerator.backward and the metric gathers
+ *      (mineral/agents/ppo/ppo.py:116-123,292-311) and, fused behind it, clip_grad_norm_ +
+ *      optimizer.step + zero_grad (ppo.py:291-300).
+ *
+ *      Every rank owns ONE peer buffer: [signal pad (MNR_PEER_SIGNAL_BYTES, zero) | caller-defined
+ *      regions].  mnr_peer_alloc is the one place this library allocates device memory (cudaMalloc +
+ *      CUDA IPC handle, because torch's caching allocator cannot export a whole allocation);
+ *      the 64-byte handle travels to the other ranks by any host channel (torch.distributed
+ *      all_gather_object) and is mapped there with mnr_peer_open.
+ * ------------------------------------------------------------------------------------ */
+#define MNR_MAX_PEERS 8
+#define MNR_PEER_HANDLE_BYTES 64
+#define MNR_PEER_SIGNAL_BYTES 16384
+
+typedef struct {
+  void* base[MNR_MAX_PEERS]; /* rank r's peer buffer as mapped in THIS process; base[rank] is the local one */
+  int32_t rank, world;
+} mnr_peer_comm_t;
+
+int mnr_peer_alloc(size_t bytes, void** ptr_out /*host*/, void* handle_out /*host, 64 B*/);
+int mnr_peer_open(const void* handle /*host, 64 B*/, void** ptr_out /*host*/);
+int mnr_peer_close(void* ptr);
+int mnr_peer_free(void* ptr);
+/* host read (synchronous) of the local error word: != 0 if a cross-GPU wait timed out (20 s) */
+int mnr_peer_error(const mnr_peer_comm_t* comm /*host*/, int* error_out /*host*/);
+
+/* All-gather of a small payload: src (bytes, local) is published through the staging region at
+ * `stage_offset` of the local peer buffer; dst (world*bytes, local) receives every rank's payload in
+ * rank order.  bytes % 16 == 0.  Same call sequence on every rank. */
+int mnr_peer_allgather(const mnr_peer_comm_t* comm /*host*/, size_t stage_offset, const void* src, size_t bytes,
+                       void* dst, mnr_stream_t stream);
+
+/* ONE kernel per optimizer step: barrier -> sum over ranks (rank order: bit-identical on every
+ * rank) of the n gradient floats at `grad_offset` of every peer buffer (+ n_tail metric floats right
+ * behind them -> tail_out) -> global norm -> clip + Adam/AdamW on (param, exp_avg, exp_avg_sq) ->
+ * barrier -> zero the local gradient.  `reduced` = n floats of local scratch.  The metric at
+ * kl_index (or none if < 0) feeds st->kl_sum as in mnr_grad_norm_prepare. */
+int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm /*host*/, size_t grad_offset, int64_t n, int n_tail,
+                              float* reduced, float* param, float* exp_avg, float* exp_avg_sq, float max_norm,
+                              float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
+                              mnr_optim_state_t* st, float* tail_out, int kl_index, float* grad_norm_out,
+                              void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

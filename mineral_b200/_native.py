@@ -78,6 +78,10 @@ class OptimState(C.Structure):
                 ("lr_f32", C.c_float), ("_pad", C.c_float)]
 
 
+class PeerCommStruct(C.Structure):
+    _fields_ = [("base", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
+
+
 ROW_F32, ROW_U8, ROW_BOOL_TO_F32, ROW_F32_TO_BOOL, ROW_F32_NORMALIZE = 0, 1, 2, 3, 4
 DIST_NORMAL, DIST_DREAMERV3_NORMAL = 0, 1
 BOUNDS_BOUND, BOUNDS_REG = 0, 1
@@ -133,6 +137,16 @@ SIGNATURES = {
     "mnr_grad_norm_prepare": (i32, [vp, i64, f32, f32, f32, vp, vp, vp, vp, sz, vp]),
     "mnr_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, i32, vp, vp]),
     "mnr_kl_lr_update": (i32, [vp, f64, f64, f64, vp, vp, vp]),
+    "mnr_fused_adam_workspace_bytes": (sz, []),
+    "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, vp, sz, vp]),
+    "mnr_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),
+    "mnr_peer_open": (i32, [vp, C.POINTER(vp)]),
+    "mnr_peer_close": (i32, [vp]),
+    "mnr_peer_free": (i32, [vp]),
+    "mnr_peer_error": (i32, [C.POINTER(PeerCommStruct), C.POINTER(i32)]),
+    "mnr_peer_allgather": (i32, [C.POINTER(PeerCommStruct), sz, vp, sz, vp, vp]),
+    "mnr_peer_reduce_clip_adam": (i32, [C.POINTER(PeerCommStruct), sz, i64, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, i32, vp,
+                                        vp, i32, vp, vp, sz, vp]),
 }
 
 

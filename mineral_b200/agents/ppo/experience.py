@@ -146,7 +146,7 @@ class ExperienceBuffer:
         ops.post_rollout_fused(self._wide(), sd['rewards'], sd['values'], sd['dones'], sd['neglogp'], last_values.contiguous(),
                                sd['returns'], self._em, T, N, gamma, tau, self._ws, do_gae=True)
 
-    def compute_return_and_prepare(self, last_values, gamma, tau, value_rms=None, world=1):
+    def compute_return_and_prepare(self, last_values, gamma, tau, value_rms=None, world=1, comm=None):
         """Fused compute_return + prepare_training (+ PPO's value-RMS block when `value_rms`, a
         RunningMeanStd over shape (1,), is given; ppo.py:175-183): one pass over the rollout, then one
         small normalise pass.  Equivalent to calling the two reference methods and the value block.
@@ -159,7 +159,7 @@ class ExperienceBuffer:
             from ... import distributed as mdist
             if self._ws_all is None:
                 self._ws_all = mdist.combined_workspace(N, world, self.device)
-            ws = mdist.gather_partials(self._ws, self._ws_all, N)
+            ws = mdist.gather_partials(self._ws, self._ws_all, N, comm=comm)
         if value_rms is None:
             ops.post_rollout_finalize(self._em, T * N, None, ws, stats_out=self.stats)
         else:

@@ -37,13 +37,21 @@ from .experience import ExperienceBuffer
 from .utils import AdaptiveScheduler, LinearScheduler, adjust_learning_rate_cos
 
 
+def peer_tail_floats():
+    from ...peer import TAIL_FLOATS
+    return TAIL_FLOATS
+
+
 class FusedAdam:
     """Adam / AdamW over ONE flat f32 buffer with device-resident lr / step / clip coefficient.
     Exposes `param_groups`, `state_dict()`, `load_state_dict()` in torch.optim.Adam's format so PPO
     checkpoints (ppo.py:416-446) stay interchangeable."""
 
-    def __init__(self, params, decoupled, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, **unused):
+    def __init__(self, params, decoupled, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, comm=None, **unused):
+        """comm: optional `mineral_b200.peer.PeerComm` whose 'grad' region ((n + 32) floats) holds the flat gradient, so
+        the peers can read it over NVLink (multi-GPU); the step is then ONE fused all-reduce + clip + Adam kernel."""
         self.params = list(params)
+        self.comm = comm
         dev = self.params[0].device
         self.decoupled = decoupled
         self.betas, self.eps = betas, eps
@@ -54,7 +62,15 @@ class FusedAdam:
             self.offsets.append(self.offsets[-1] + ((s + 3) // 4) * 4)  # keep every tensor 16 B aligned
         n = self.offsets[-1]
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        if comm is None:
+            self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.tail = self.reduced = None
+        else:
+            region = comm.tensor('grad')
+            assert region.numel() >= n + peer_tail_floats(), 'peer gradient region too small'
+            self.flat_grad = region[:n]
+            self.tail = region[n:n + peer_tail_floats()]   # this rank's loss metrics, summed by the fused kernel
+            self.reduced = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
@@ -64,13 +80,24 @@ class FusedAdam:
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self.state = ops.optim_state_tensor(lr, dev)
         self.ws = torch.zeros(ops.lib.mnr_grad_norm_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        self.fused_ws = torch.zeros(ops.lib.mnr_fused_adam_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.param_groups = [dict(lr=float(lr), betas=betas, eps=eps, weight_decay=self.weight_decay)]
 
-    def step(self, max_grad_norm, kl=None, grad_norm_out=None):
-        """clip_grad_norm_ + optimizer.step + zero_grad as two launches (no host sync)."""
-        ops.grad_norm_prepare(self.flat_grad, max_grad_norm, self.betas[0], self.betas[1], self.state, kl, grad_norm_out, self.ws)
-        ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps,
-                      self.weight_decay, self.decoupled, True, self.state)
+    def step(self, max_grad_norm, kl=None, grad_norm_out=None, metrics_out=None, kl_index=-1, fused=True):
+        """clip_grad_norm_ + optimizer.step + zero_grad with no host sync: ONE launch (csrc/peer.cu), which with a peer
+        communicator also all-reduces the gradient and the metrics tail over NVLink (`metrics_out` receives the sums,
+        the metric at `kl_index` feeds the KL accumulator).  fused=False: the two-launch form (csrc/optim.cu)."""
+        if self.comm is not None:
+            self.comm.reduce_clip_adam(self.flat.numel(), self.reduced, self.flat, self.exp_avg, self.exp_avg_sq, max_grad_norm,
+                                       self.betas[0], self.betas[1], self.eps, self.weight_decay, self.decoupled, True, self.state,
+                                       metrics_out, kl_index, grad_norm_out, self.fused_ws)
+        elif fused:
+            ops.fused_clip_adam(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, max_grad_norm, self.betas[0], self.betas[1],
+                                self.eps, self.weight_decay, self.decoupled, True, self.state, kl, grad_norm_out, self.fused_ws)
+        else:
+            ops.grad_norm_prepare(self.flat_grad, max_grad_norm, self.betas[0], self.betas[1], self.state, kl, grad_norm_out, self.ws)
+            ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps,
+                          self.weight_decay, self.decoupled, True, self.state)
 
     def zero_grad(self):
         self.flat_grad.zero_()
@@ -150,7 +177,19 @@ class PPO(Agent):
         optim_kwargs['lr'] = self.init_lr
         if cfg.optim_type not in ('Adam', 'AdamW'):
             raise NotImplementedError(f'optim_type {cfg.optim_type}: only Adam / AdamW have a fused kernel')
-        self.optim = FusedAdam(self.model.parameters(), decoupled=(cfg.optim_type == 'AdamW'), **optim_kwargs)
+
+        # --- Multi-GPU: one process per GPU; data path over NVLink peer memory (mineral_b200/peer.py), torch.distributed
+        #     (NCCL) only for set-up, or for everything with `ppo.peer_allreduce: False` ---
+        self.world, self.comm = 1, None
+        if self.multi_gpu:
+            import torch.distributed as dist
+            assert dist.is_initialized(), 'multi_gpu=True needs torch.distributed initialised (torchrun)'
+            self.world = dist.get_world_size()
+            if self.world > 1 and cfg_get(cfg, 'peer_allreduce', True):
+                from ...peer import PeerComm, TAIL_FLOATS
+                n_flat = sum((p.numel() + 3) // 4 * 4 for p in self.model.parameters())
+                self.comm = PeerComm({'grad': (n_flat + TAIL_FLOATS) * 4, 'stage': 1 << 20}, self.device)
+        self.optim = FusedAdam(self.model.parameters(), decoupled=(cfg.optim_type == 'AdamW'), comm=self.comm, **optim_kwargs)
 
         # --- PPO train params (ppo.py:63-76) ---
         self.e_clip = cfg['e_clip']
@@ -190,12 +229,6 @@ class PPO(Agent):
                                         self.action_dim, self.device, self.cpu_obs_keys)
         self.reward_shaper = RewardShaper(**cfg['reward_shaper'])
 
-        # --- Multi-GPU: one process per GPU, torch.distributed (NCCL) ---
-        self.world = 1
-        if self.multi_gpu:
-            import torch.distributed as dist
-            assert dist.is_initialized(), 'multi_gpu=True needs torch.distributed initialised (torchrun)'
-            self.world = dist.get_world_size()
         self._engine = None
         self.use_cuda_graph = bool(cfg_get(cfg, 'cuda_graph', False))
 
@@ -245,7 +278,7 @@ class PPO(Agent):
     def finish_rollout(self, last_values):
         """ppo.py:172-183 in one fused pass + one normalise pass."""
         self.storage.compute_return_and_prepare(last_values, self.gamma, self.tau, self.value_rms if self.normalize_value else None,
-                                                world=self.world)
+                                                world=self.world, comm=self.comm)
 
     def train(self):
         """ppo.py:185-246 without the TensorBoard/W&B plumbing."""
@@ -384,6 +417,20 @@ class _UpdateEngine:
         max_norm = float(a.max_grad_norm) if a.truncate_grads else 0.0
         step = 0
         x_ld = None
+        peer = a.comm is not None
+        fused_opt = cfg_get(a.ppo_config, 'fused_optimizer', True)
+
+        def optimizer_step(step):
+            m = self.metrics[step]
+            if peer:      # gradient + metrics all-reduce, clip, Adam: one kernel over peer memory
+                a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7)
+                return
+            if a.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(a.optim.flat_grad)  # grads were pre-scaled by 1/world in the loss kernel
+                dist.all_reduce(m)                  # metrics likewise
+            a.optim.step(max_norm, kl=m[7:8], grad_norm_out=self.grad_norms[step:step + 1], fused=fused_opt)
+
         for ep in range(a.mini_epochs):
             for i in range(self.num_mb):
                 s, e = i * mb, (i + 1) * mb
@@ -404,14 +451,11 @@ class _UpdateEngine:
                 if self.towers is not None and self.towers.fused_heads_ok:
                     # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward: no torch op, no autograd
                     self.towers.forward_towers(obs['obs'], x_ld)
-                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), self.metrics[step], self.loss_cfg,
+                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1),
+                                                   a.optim.tail if peer else self.metrics[step], self.loss_cfg,
                                                    self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
                     self.towers.backward_towers(obs['obs'])
-                    if a.world > 1:
-                        import torch.distributed as dist
-                        dist.all_reduce(a.optim.flat_grad)
-                        dist.all_reduce(self.metrics[step])
-                    a.optim.step(max_norm, kl=self.metrics[step, 7:8], grad_norm_out=self.grad_norms[step:step + 1])
+                    optimizer_step(step)
                     step += 1
                     continue
                 if self.towers is not None:
@@ -421,17 +465,13 @@ class _UpdateEngine:
                         mu_raw, logstd, value = a.model._actor_critic(obs)
                 ops.ppo_loss_fwd_bwd(mu_raw.detach(), logstd.detach().contiguous(), value.detach(), d['actions'][s:e],
                                      d['neglogp'][s:e], d['advantages'][s:e], d['values'][s:e], d['returns'][s:e],
-                                     d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls, self.g_v, self.metrics[step],
-                                     self.loss_cfg, self.loss_ws, True, self.mu_mean[step], self.sigma_mean[step])
+                                     d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls, self.g_v,
+                                     a.optim.tail if peer else self.metrics[step], self.loss_cfg, self.loss_ws, True, self.mu_mean[step], self.sigma_mean[step])
                 if self.towers is not None:
                     self.towers.backward(obs['obs'], self.g_mu, self.g_ls, self.g_v)
                 else:
                     torch.autograd.backward([mu_raw, logstd, value], [self.g_mu, self.g_ls, self.g_v])
-                if a.world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(a.optim.flat_grad)     # grads were pre-scaled by 1/world in the loss kernel
-                    dist.all_reduce(self.metrics[step])    # metrics pre-scaled likewise
-                a.optim.step(max_norm, kl=self.metrics[step, 7:8], grad_norm_out=self.grad_norms[step:step + 1])
+                optimizer_step(step)
                 step += 1
             if a.lr_schedule == 'kl':
                 ops.kl_lr_update(a.optim.state, a.kl_threshold, a.min_lr, a.max_lr, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
@@ -442,14 +482,14 @@ class _UpdateEngine:
     def _merge_moments_across_ranks(self, n):
         """Global minibatch i = union of the ranks' local minibatch i."""
         from ... import distributed as mdist
-        mdist.merge_group_moments(n['gm'], n['gv'], self.mb, self.a.obs_rms[self.norm_keys[0]].correction)
+        mdist.merge_group_moments(n['gm'], n['gv'], self.mb, self.a.obs_rms[self.norm_keys[0]].correction, comm=self.a.comm)
 
     def run(self):
         a = self.a
         if a.lr_schedule == 'cos':
             raise NotImplementedError("lr_schedule 'cos' changes lr from the host every mini-epoch; use 'kl', 'linear' or 'fixed'")
         with torch.no_grad():
-            if a.use_cuda_graph and a.world == 1:
+            if a.use_cuda_graph and (a.world == 1 or a.comm is not None):  # NCCL-free => capturable at any world size
                 if self.graph is None and self._warm >= 1:
                     torch.cuda.synchronize()
                     from ... import _native as nv

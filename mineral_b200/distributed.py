@@ -25,16 +25,21 @@ def world_size(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
-def merge_group_moments(mean, var, count, correction=1, group=None):
+def merge_group_moments(mean, var, count, correction=1, group=None, comm=None):
     """In-place: per-rank (mean, var) of `count` rows each -> moments of the union of all ranks' rows.
-    mean/var: (n_groups, cols) f32.  Exact sufficient statistics (sum x, sum x^2) in f64, one all-reduce."""
-    w = world_size(group)
+    mean/var: (n_groups, cols) f32.  Exact sufficient statistics (sum x, sum x^2) in f64, one exchange:
+    a peer-memory all-gather + rank-order sum when `comm` (mineral_b200.peer.PeerComm) is given, else one
+    all-reduce on `group`."""
+    w = comm.world if comm is not None else world_size(group)
     if w == 1:
         return mean, var
     cnt, corr = float(count), float(correction)
     m = mean.double()
     pack = torch.stack([m * cnt, var.double() * (cnt - corr) + cnt * m * m])
-    dist.all_reduce(pack, group=group)
+    if comm is not None:
+        pack = comm.allgather(pack.contiguous()).sum(0)
+    else:
+        dist.all_reduce(pack, group=group)
     tot = cnt * w
     gmean = pack[0] / tot
     mean.copy_(gmean.float())
@@ -54,10 +59,13 @@ def combined_workspace(num_envs, world, device):
     return ws
 
 
-def gather_partials(ws_local, ws_all, num_envs, group=None):
+def gather_partials(ws_local, ws_all, num_envs, group=None, comm=None):
     """All-gather the local (adv, values, returns) partial moments into `ws_all` (rank-major), which
     mnr_post_rollout_finalize then merges in index order: identical statistics on every rank."""
     n = n_partials(num_envs) * POST_ROLLOUT_PARTIAL
+    if comm is not None and n % 16 == 0:
+        comm.allgather(ws_local[POST_ROLLOUT_HEADER:POST_ROLLOUT_HEADER + n], out=ws_all[POST_ROLLOUT_HEADER:])
+        return ws_all
     dist.all_gather_into_tensor(ws_all[POST_ROLLOUT_HEADER:], ws_local[POST_ROLLOUT_HEADER:POST_ROLLOUT_HEADER + n].contiguous(),
                                 group=group)
     return ws_all

@@ -343,6 +343,15 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, weight_decay,
           "mnr_adam_step")
 
 
+def fused_clip_adam(param, grad, exp_avg, exp_avg_sq, max_norm, beta1, beta2, eps, weight_decay, decoupled, zero_grad, st, kl,
+                    norm_out, ws):
+    """clip_grad_norm_ + Adam(W).step + zero_grad in ONE launch (csrc/peer.cu, world == 1 instance)."""
+    check(lib.mnr_fused_clip_adam(ptr(param, F32), ptr(grad, F32), ptr(exp_avg, F32), ptr(exp_avg_sq, F32), param.numel(), max_norm,
+                                  beta1, beta2, eps, weight_decay, 1 if decoupled else 0, 1 if zero_grad else 0, ptr(st, U8),
+                                  ptr(kl, F32, allow_none=True), ptr(norm_out, F32, allow_none=True), ptr(ws, U8), ws.numel(),
+                                  stream()), "mnr_fused_clip_adam")
+
+
 def kl_lr_update(st, kl_threshold, min_lr, max_lr, avg_kl_out=None, lr_out=None):
     check(lib.mnr_kl_lr_update(ptr(st, U8), kl_threshold, min_lr, max_lr, ptr(avg_kl_out, F32, allow_none=True),
                                ptr(lr_out, F64, allow_none=True), stream()), "mnr_kl_lr_update")

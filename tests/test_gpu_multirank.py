@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 T, NL, O, A, NUM_MB, EPOCHS = 8, 64, 11, 3, 4, 2   # NL envs per rank
 
 
-def _cfg(n_envs, mb, device, multi_gpu):
+def _cfg(n_envs, mb, device, multi_gpu, peer=True, graph=False):
     from oracle.reference_shim import to_attr
 
     return to_attr(dict(
@@ -28,7 +28,7 @@ def _cfg(n_envs, mb, device, multi_gpu):
                             normalize_value=True, value_bootstrap=True, clip_value_loss=True, normalize_advantage=True, gamma=0.99, tau=0.95,
                             entropy_coef=0.001, e_clip=0.2, use_smooth_clamp=False, critic_coef=4, bounds_loss_coef=1e-4, bounds_type="bound",
                             mini_epochs=EPOCHS, optim_type="AdamW", optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008,
-                            max_grad_norm=0.5, truncate_grads=True))))
+                            max_grad_norm=0.5, truncate_grads=True, peer_allreduce=peer, cuda_graph=graph))))
 
 
 def _load(agent, st):
@@ -44,17 +44,39 @@ def _take(st, last, envs):
     return out, last[envs]
 
 
-def _run(agent, last):
-    agent.finish_rollout(last.to(agent.device))
-    agent.set_train()
-    res = agent.train_epoch()
-    torch.cuda.synchronize()
+def _run(agent, last, repeats=1):
+    snap = _snapshot(agent)
+    for rep in range(repeats):   # repeats > 1 (CUDA-graph mode): warm-up, capture, replay -- each from the same initial state
+        if rep > 0:
+            _restore(agent, snap)
+        agent.finish_rollout(last.to(agent.device))
+        agent.set_train()
+        res = agent.train_epoch()
+        torch.cuda.synchronize()
     return dict(loss=torch.stack(res["loss/total"]).cpu(), kl=torch.stack(res["avg_kl"]).cpu(), gn=torch.stack(res["grad_norm/all"]).cpu(),
                 params=agent.optim.flat.cpu(), obs_mean=agent.obs_rms["obs"].running_mean.cpu(), obs_var=agent.obs_rms["obs"].running_var.cpu(),
                 val_mean=agent.value_rms.running_mean.cpu(), val_var=agent.value_rms.running_var.cpu(), lr=agent.last_lr)
 
 
-def _worker(rank, world, port, init_sd, ret):
+def _snapshot(agent):
+    sd = agent.storage.storage_dict
+    return dict(flat=agent.optim.flat.clone(), m=agent.optim.exp_avg.clone(), v=agent.optim.exp_avg_sq.clone(), st=agent.optim.state.clone(),
+                obs={k: v.clone() for k, v in agent.obs_rms["obs"].state_dict().items()},
+                val={k: v.clone() for k, v in agent.value_rms.state_dict().items()},
+                mu=sd["mu"].clone(), sigma=sd["sigma"].clone())
+
+
+def _restore(agent, snap):
+    sd = agent.storage.storage_dict
+    agent.optim.flat.copy_(snap["flat"]), agent.optim.exp_avg.copy_(snap["m"]), agent.optim.exp_avg_sq.copy_(snap["v"])
+    agent.optim.state.copy_(snap["st"])
+    for name, rms in (("obs", agent.obs_rms["obs"]), ("val", agent.value_rms)):
+        for k, v in snap[name].items():
+            getattr(rms, k).copy_(v)
+    sd["mu"].copy_(snap["mu"]), sd["sigma"].copy_(snap["sigma"])
+
+
+def _worker(rank, world, port, init_sd, ret, peer, graph):
     from mineral_b200.agents import PPO
     from oracle import mineral_oracle as oc
     from oracle.reference_shim import SynthEnv
@@ -66,16 +88,23 @@ def _worker(rank, world, port, init_sd, ret):
         st, last = oc.synth_rollout(T, NL * world, O, A, seed=3, done_p=0.05)
         envs = torch.arange(rank * NL, (rank + 1) * NL)
         st_r, last_r = _take(st, last, envs)
-        agent = PPO(_cfg(NL, NL * T // NUM_MB, f"cuda:{rank}", True), env=SynthEnv(4, O, A, 1))
+        agent = PPO(_cfg(NL, NL * T // NUM_MB, f"cuda:{rank}", True, peer, graph), env=SynthEnv(4, O, A, 1))
+        assert (agent.comm is not None) == peer
         agent.model.load_state_dict(init_sd)
         _load(agent, st_r)
-        ret[rank] = _run(agent, last_r)
+        ret[rank] = _run(agent, last_r, repeats=3 if graph else 1)
+        if peer:
+            assert agent.comm.error() == 0
+            assert agent._engine.graph is not None or not graph
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_update_equals_single_rank_on_union():
+@pytest.mark.parametrize("peer,graph", [(True, False), (True, True), (False, False)])
+def test_two_rank_update_equals_single_rank_on_union(peer, graph):
+    """peer=True: gradient/metrics/statistics exchanged by our own kernels over NVLink peer memory (csrc/peer.cu), optionally
+    with the whole update replayed as one CUDA graph; peer=False: the torch.distributed (NCCL) path."""
     from mineral_b200.agents import PPO
     from oracle import mineral_oracle as oc
     from oracle.reference_shim import SynthEnv
@@ -95,7 +124,7 @@ def test_two_rank_update_equals_single_rank_on_union():
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29571, init_sd, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29571 + 2 * int(peer) + int(graph), init_sd, ret, peer, graph), nprocs=world, join=True)
     for r in range(world):
         got = ret[r]
         scale_close(got["loss"], ref["loss"], 2e-5, f"rank{r} losses")

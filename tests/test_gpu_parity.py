@@ -434,11 +434,11 @@ def test_fused_loss_vs_oracle_autograd(dist_type, fixed_sigma, mb, A, clip_value
 # a12
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("decoupled", [False, True])
-def test_fused_adam_vs_torch(decoupled):
+@pytest.mark.parametrize("one_launch,n", [(False, 10_007), (True, 10_008), (True, 427_432)])
+def test_fused_adam_vs_torch(decoupled, one_launch, n):
     from mineral_b200 import ops
 
     g = torch.Generator().manual_seed(2)
-    n = 10_007
     p0 = torch.randn(n, generator=g)
     ref_p = p0.clone().requires_grad_(True)
     Opt = torch.optim.AdamW if decoupled else torch.optim.Adam
@@ -446,6 +446,8 @@ def test_fused_adam_vs_torch(decoupled):
     p, m, v = cu(p0.clone()), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
     st = ops.optim_state_tensor(5e-4, DEV)
     ws = torch.zeros(ops.lib.mnr_grad_norm_workspace_bytes(n), dtype=torch.uint8, device=DEV)
+    fws = torch.zeros(ops.lib.mnr_fused_adam_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    kl = torch.full((1,), 0.25, device=DEV)
     norm_out = torch.zeros(1, device=DEV)
     for step in range(6):
         grad = torch.randn(n, generator=g) * (0.01 if step % 2 else 3.0)
@@ -453,13 +455,17 @@ def test_fused_adam_vs_torch(decoupled):
         ref_norm = torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
         ref_opt.step()
         gd = cu(grad)
-        ops.grad_norm_prepare(gd, 1.0, 0.9, 0.999, st, None, norm_out, ws)
-        ops.adam_step(p, gd, m, v, 0.9, 0.999, 1e-5, 0.01 if decoupled else 0.0, decoupled, True, st)
-        scale_close(norm_out[0], ref_norm, 1e-6, "grad norm")
+        if one_launch:  # csrc/peer.cu, world == 1 instance: norm + clip + Adam + zero_grad behind one grid barrier
+            ops.fused_clip_adam(p, gd, m, v, 1.0, 0.9, 0.999, 1e-5, 0.01 if decoupled else 0.0, decoupled, True, st, kl, norm_out, fws)
+        else:
+            ops.grad_norm_prepare(gd, 1.0, 0.9, 0.999, st, kl, norm_out, ws)
+            ops.adam_step(p, gd, m, v, 0.9, 0.999, 1e-5, 0.01 if decoupled else 0.0, decoupled, True, st)
+        scale_close(norm_out[0], ref_norm, 5e-6, "grad norm")  # torch accumulates its norm in f32
         assert gd.abs().max().item() == 0.0  # zero_grad fused
         scale_close(p, ref_p.detach(), 1e-6, f"params after step {step}")
     s = ops.read_optim_state(st)
     assert s.step == 6 and abs(s.lr - 5e-4) < 1e-18
+    assert s.kl_count == 6 and abs(s.kl_sum - 1.5) < 1e-12
 
 
 def test_kl_lr_rule_on_device():
