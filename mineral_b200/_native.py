@@ -113,6 +113,7 @@ SIGNATURES = {
     "mnr_ppo_loss_workspace_bytes": (sz, [i64, i32]),
     "mnr_ppo_loss_fwd_bwd": (i32, [vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, i32, C.POINTER(PPOLossCfg), vp, sz, vp]),
     "mnr_ppo_heads_workspace_bytes": (sz, [i64, i32, i32]),
+    "mnr_ppo_heads_is_fused": (i32, [i32, i32]),
     "mnr_ppo_heads_loss_fwd_bwd": (i32, [vp] * 15 + [i32] + [vp] * 14 + [i64, i32, i32, C.POINTER(PPOLossCfg), vp, sz, vp]),
     "mnr_actor_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),
     "mnr_critic_loss_rows": (i32, [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp, sz, vp]),

@@ -93,21 +93,6 @@ __device__ __forceinline__ void peer_barrier(const Comm& c, uint32_t flag) {
   __syncthreads();
 }
 
-// Grid-wide barrier among the (co-resident) CTAs of this launch: monotonically increasing 64-bit counter.
-__device__ __forceinline__ void grid_barrier(unsigned long long* counter) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long t = atomicAdd(counter, 1ull);
-    const unsigned long long target = (t / gridDim.x + 1ull) * gridDim.x;
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(counter) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
-}
-
 struct AdamArgs {
   float* param;
   float* m;
@@ -200,7 +185,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     for (int x = 0; x < kThreads / 32; ++x) s += s_w[x];
     a.parts[blockIdx.x] = s;
   }
-  grid_barrier(a.counter);
+  mnr::grid_barrier(a.counter);
 
   // ---- phase 2: every CTA derives the same clip coefficient and Adam scalars ----
   if (tid < 32) {

@@ -11,90 +11,14 @@
 // gradients, which need the row's probability ratio.  Scalars reduce warp-shuffle -> CTA -> f64
 // partials in the workspace -> last CTA (ticket) in a fixed order, so results are deterministic.
 #include "common.cuh"
+#include "loss_math.cuh"
 
 namespace {
 
 constexpr int kThreads = 128;
-constexpr float kLogSqrt2Pi = 0.91893853320467274178f;  // log(sqrt(2*pi))
 constexpr int kHeader = 256;                             // ticket + padding
 constexpr int kMaxA = 64;
-
-struct LossPartial {
-  double a, c, b, h, clip, kl;
-  mnr::Moments d;    // returns - values
-  mnr::Moments ret;  // returns
-};
-
-__device__ __forceinline__ void dist_fwd(const mnr_ppo_loss_cfg_t& cfg, float mu_raw, float ls, float& mu, float& sigma,
-                                         float& dmu, float& dsigma) {
-  if (cfg.dist_type == MNR_DIST_NORMAL) {  // dist.py:32-34
-    mu = mu_raw, sigma = expf(ls), dmu = 1.f, dsigma = sigma;
-  } else {  // dreamerv3_normal, dist.py:42-47
-    const float s = 1.f / (1.f + expf(-(ls + 2.0f)));
-    const float span = cfg.maxstd - cfg.minstd;
-    mu = tanhf(mu_raw);
-    sigma = span * s + cfg.minstd;
-    dmu = 1.f - mu * mu;
-    dsigma = span * s * (1.f - s);
-  }
-}
-
-__device__ __forceinline__ float smooth_clamp(float x, float lo, float hi, float* dx) {
-  // ppo.py:449-450
-  const float s = 1.f / (1.f + expf((-(x - lo) / (hi - lo) + 0.5f) * 4.f));
-  *dx = 4.f * s * (1.f - s);
-  return s * (hi - lo) + lo;
-}
-
-// d max(a,b): weight of a (1, 0, or 0.5 on ties as torch.max/maximum backward does)
-__device__ __forceinline__ float max_weight(float a, float b) { return a > b ? 1.f : (a < b ? 0.f : 0.5f); }
-
-__device__ __forceinline__ float actor_row(float old_nlp, float nlp, float adv, float e_clip, int smooth, float* dloss_dnlp,
-                                           float* clipped) {
-  const float ratio = expf(old_nlp - nlp);
-  const float lo = 1.0f - e_clip, hi = 1.0f + e_clip;
-  float dclamp, cr;
-  if (smooth) cr = smooth_clamp(ratio, lo, hi, &dclamp);
-  else cr = fminf(fmaxf(ratio, lo), hi), dclamp = (ratio >= lo && ratio <= hi) ? 1.f : 0.f;
-  const float s1 = -(adv * ratio), s2 = -(adv * cr);
-  const float w1 = max_weight(s1, s2);
-  const float dl_dratio = -adv * (w1 + (1.f - w1) * dclamp);
-  *dloss_dnlp = -dl_dratio * ratio;
-  *clipped = fabsf(ratio - 1.0f) > e_clip ? 1.f : 0.f;
-  return fmaxf(s1, s2);
-}
-
-__device__ __forceinline__ float critic_row(float v_old, float v, float ret, float e_clip, int clip, float* dloss_dv) {
-  const float d1 = v - ret;
-  const float c1 = d1 * d1;
-  if (!clip) {
-    *dloss_dv = 2.f * d1;
-    return c1;
-  }
-  const float dv = v - v_old;
-  const float d2 = (v_old + fminf(fmaxf(dv, -e_clip), e_clip)) - ret;
-  const float c2 = d2 * d2;
-  const float w1 = max_weight(c1, c2);
-  const float inside = (dv >= -e_clip && dv <= e_clip) ? 1.f : 0.f;
-  *dloss_dv = w1 * 2.f * d1 + (1.f - w1) * 2.f * d2 * inside;
-  return fmaxf(c1, c2);
-}
-
-__device__ __forceinline__ float bounds_elem(float mu, int type, float soft, float* db) {
-  if (type == MNR_BOUNDS_REG) {
-    *db = 2.f * mu;
-    return mu * mu;
-  }
-  const float hi = fmaxf(mu - soft, 0.f), lo = fminf(mu + soft, 0.f);
-  *db = 2.f * hi + 2.f * lo;
-  return lo * lo + hi * hi;
-}
-
-__device__ __forceinline__ float kl_elem(float mu, float sigma, float mu_old, float sigma_old) {
-  // policy_kl(p0 = new, p1 = old), ppo.py:492-497
-  const float dm = mu_old - mu;
-  return logf(sigma_old / sigma + 1e-5f) + (sigma * sigma + dm * dm) / (2.0f * (sigma_old * sigma_old + 1e-5f)) - 0.5f;
-}
+using namespace mnr_loss;
 
 template <int VEC>
 struct Vec;
@@ -879,8 +803,23 @@ extern "C" int mnr_policy_kl_rows(const float* p0_mu, const float* p0_sigma, con
   MNR_LAUNCH_RESULT();
 }
 
+// csrc/heads_fused.cu: the single-kernel path (H in {32, 64, 128}, A <= 16)
+int mnr_heads_fused_grid_cap();
+bool mnr_heads_fused_supported(int A, int H);
+size_t mnr_heads_fused_workspace_bytes(int A, int H);
+int mnr_heads_fused_launch(const float* y3a, const float* y3v, const float* w_mu, const float* b_mu, const float* w_v,
+                           const float* b_v, const float* w_sig, const float* b_sig, const float* actions,
+                           const float* old_neglogp, const float* advantages, const float* old_values, const float* returns,
+                           float* old_mu, float* old_sigma, int write_back, float* dy3a, float* dy3v, float* g_mu, float* g_ls,
+                           float* g_v, float* dw_mu, float* db_mu, float* dw_v, float* db_v, float* dw_sig, float* db_sig,
+                           float* metrics_out, float* mu_mean_out, float* sigma_mean_out, int64_t M, int A, int H,
+                           const mnr_ppo_loss_cfg_t* cfg, void* workspace, cudaStream_t stream);
+
+extern "C" int mnr_ppo_heads_is_fused(int A, int H) { return mnr_heads_fused_supported(A, H) ? 1 : 0; }
+
 extern "C" size_t mnr_ppo_heads_workspace_bytes(int64_t M, int A, int H) {
   if (M <= 0 || A <= 0 || H <= 0) return 0;
+  if (mnr_heads_fused_supported(A, H)) return mnr_heads_fused_workspace_bytes(A, H);
   const size_t grid = (size_t)mnr_sm_count() * 4;
   const size_t loss = kHeader + grid * (sizeof(LossPartial) + sizeof(float) * 2 * (size_t)A);
   const size_t rows_per_cta = 128;
@@ -910,6 +849,11 @@ extern "C" int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, co
   if (cfg->bounds_type != MNR_BOUNDS_BOUND && cfg->bounds_type != MNR_BOUNDS_REG) return MNR_EUNSUP;
   if (workspace_bytes < mnr_ppo_heads_workspace_bytes(M, A, H)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
+  if (mnr_heads_fused_supported(A, H))
+    return mnr_heads_fused_launch(y3a, y3v, w_mu, b_mu, w_v, b_v, w_sig, b_sig, actions, old_neglogp, advantages, old_values,
+                                  returns, old_mu, old_sigma, write_back, dy3a, dy3v, g_mu, g_ls, g_v, dw_mu, db_mu, dw_v, db_v,
+                                  dw_sig, db_sig, metrics_out, mu_mean_out, sigma_mean_out, M, A, H, cfg, workspace,
+                                  mnr_cs(stream));
   const size_t grid_cap = (size_t)mnr_sm_count() * 4;
   const size_t loss_bytes = ((kHeader + grid_cap * (sizeof(LossPartial) + sizeof(float) * 2 * (size_t)A) + 255) / 256) * 256;
 

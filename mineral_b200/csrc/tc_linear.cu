@@ -408,30 +408,49 @@ struct ReduceArgs {
   float* w[kMaxGroups];
   float* b[kMaxGroups];
 };
-__global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_groups, int splits, int I, int J,
+// block = 32 element slots x 8 split slices: every thread sums splits z = slice, slice + 8, .. (independent loads, all in
+// flight), the 8 slices meet in shared memory and are added in slice order -> deterministic, one latency round.
+// blockIdx.x < wblocks: 32 float4 of dW;  else: 32 floats of db.
+__global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_groups, int splits, int I, int J, int wblocks,
                                                         const float* __restrict__ partials) {
+  __shared__ float4 s_part[8][32];
   const int gi = blockIdx.y;
   const int NK = I * J;
-  const int idx = blockIdx.x * 256 + threadIdx.x;
-  if (idx < NK) {
-    const float* src = partials + (size_t)gi * splits * NK + idx;
-    float s = 0.f;
-    int z = 0;
-    for (; z + 8 <= splits; z += 8) {  // 8 independent loads in flight, summed in a fixed order
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(z + u) * NK);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) s += v[u];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((int)blockIdx.x < wblocks) {
+    const int e4 = blockIdx.x * 32 + lane;
+    if (e4 * 4 < NK) {
+      const float4* src = reinterpret_cast<const float4*>(partials + (size_t)gi * splits * NK) + e4;
+      const size_t step = (size_t)NK / 4;
+#pragma unroll 4
+      for (int z = slice; z < splits; z += 8) {
+        const float4 v = __ldcs(src + (size_t)z * step);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
     }
-    for (; z < splits; ++z) s += __ldg(src + (size_t)z * NK);
-    ra.w[gi][idx] = s;
-  } else if (idx < NK + I && ra.b[gi]) {
-    const int n = idx - NK;
-    const float* bp = partials + (size_t)n_groups * splits * NK;
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += __ldg(bp + ((size_t)gi * splits + z) * I + n);
-    ra.b[gi][n] = s;
+  } else {
+    const int n = ((int)blockIdx.x - wblocks) * 32 + lane;
+    if (n < I && ra.b[gi]) {
+      const float* bp = partials + (size_t)n_groups * splits * NK + (size_t)gi * splits * I + n;
+#pragma unroll 4
+      for (int z = slice; z < splits; z += 8) acc.x += __ldcs(bp + (size_t)z * I);
+    }
+  }
+  s_part[slice][lane] = acc;
+  __syncthreads();
+  if (slice != 0) return;
+#pragma unroll
+  for (int q = 1; q < 8; ++q) {
+    const float4 v = s_part[q][lane];
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+  }
+  if ((int)blockIdx.x < wblocks) {
+    const int e4 = blockIdx.x * 32 + lane;
+    if (e4 * 4 < NK) reinterpret_cast<float4*>(ra.w[gi])[e4] = acc;
+  } else {
+    const int n = ((int)blockIdx.x - wblocks) * 32 + lane;
+    if (n < I && ra.b[gi]) ra.b[gi][n] = acc.x;
   }
 }
 
@@ -635,8 +654,10 @@ extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_
   dim3 grid(ti, tj, n_groups * splits);
   const int rc = launch<kDw>(p, grid, mnr_cs(stream));
   if (rc != MNR_OK) return rc;
-  dim3 rgrid((N * K + N + 255) / 256, n_groups);
-  tc_reduce_kernel<<<rgrid, 256, 0, mnr_cs(stream)>>>(ra, n_groups, splits, N, K, (const float*)workspace);
+  // (N % 4 == 0 was checked above, so N*K is a multiple of 4 and every dW / partial slab is 16 B aligned)
+  const int wblocks = (N * K / 4 + 31) / 32;
+  dim3 rgrid(wblocks + (N + 31) / 32, n_groups);
+  tc_reduce_kernel<<<rgrid, 256, 0, mnr_cs(stream)>>>(ra, n_groups, splits, N, K, wblocks, (const float*)workspace);
   MNR_LAUNCH_RESULT();
 }
 

@@ -243,7 +243,8 @@ def ppo_heads_loss_fwd_bwd(y3a, y3v, w_mu, b_mu, w_v, b_v, w_sig, b_sig, actions
         ptr(actions, F32, "actions"), ptr(old_neglogp, F32), ptr(advantages, F32), ptr(old_values, F32), ptr(returns, F32),
         ptr(old_mu, F32), ptr(old_sigma, F32), 1 if write_back else 0, ptr(dy3a, F32), ptr(dy3v, F32), ptr(g_mu, F32), ptr(g_ls, F32),
         ptr(g_v, F32), ptr(dw_mu, F32), ptr(db_mu, F32), ptr(dw_v, F32), ptr(db_v, F32), o(dw_sig), ptr(db_sig, F32), ptr(metrics, F32),
-        o(mu_mean), o(sigma_mean), M, A, H, C.byref(cfg), ptr(ws, U8), ws.numel(), stream()), "mnr_ppo_heads_loss_fwd_bwd", kernels=2)
+        o(mu_mean), o(sigma_mean), M, A, H, C.byref(cfg), ptr(ws, U8), ws.numel(), stream()), "mnr_ppo_heads_loss_fwd_bwd",
+          kernels=1 if lib.mnr_ppo_heads_is_fused(A, H) else 2)
 
 
 # ---------------------------------------------------------------------------------------------
