@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl", action="store_true", help="N > 1: exchange gradients / statistics with torch.distributed (NCCL) calls instead of "
                                                         "the fused peer-memory kernels (comparison only)")
-    ap.add_argument("--kernel-sweep", action="store_true", help="also time the fused post-rollout kernel over rollout sizes")
+    ap.add_argument("--no-kernel-sweep", action="store_true", help="skip timing the fused post-rollout kernel over rollout sizes")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
@@ -380,7 +380,7 @@ def main():
                                    "peak is half the bf16 figure used as `peak`"}
 
     sweep = None
-    if args.kernel_sweep:
+    if not args.no_kernel_sweep:
         from mineral_b200.agents.ppo.experience import ExperienceBuffer
         sweep = []
         for n_env in (4096, 16384, 65536):

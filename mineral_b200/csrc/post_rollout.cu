@@ -19,6 +19,8 @@
 // Tensor-map TMA cannot be used: the (t,n) pitch is width*4 B (148 B for Ant) and tensor maps
 // need 16 B-multiple strides; 1-D bulk copies only need 16 B alignment of each run, which holds
 // when N % 4 == 0 and nb % 4 == 0.  Otherwise a plain coalesced-load variant is launched.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -355,16 +357,19 @@ struct Plan {
   size_t smem;
 };
 
-// Per-field tile width: bulk copies of >= ~1 KB (nb*width*4 bytes) but tiles of <= ~40 KB so that
-// 5-6 CTAs share an SM (loads of some overlap the stores of others); nb % 4 == 0 keeps every copy
+// Per-field tile width: bulk copies of >= ~1 KB (nb*width*4 bytes) but tiles of <= ~32 KB so that
+// 6-7 CTAs share an SM (loads of some overlap the stores of others); nb % 4 == 0 keeps every copy
 // 16 B aligned.  Returns false if even a 4-env tile of some field exceeds shared memory.
 bool make_plan(const mnr_wide_field_t* wide, int n_wide, int T, int N, Plan* pl) {
-  const size_t kTileCap = 40 * 1024, kSmemMax = 227 * 1024 - 2048;
+  size_t kTileCap = 32 * 1024, kMinCopy = 1024;  // measured on B200: 32 KB tiles (7 CTAs/SM) beat 40 KB at >= 16k envs
+  const size_t kSmemMax = 227 * 1024 - 2048;
+  if (const char* e = getenv("MNR_POST_ROLLOUT_TILE_KB")) kTileCap = (size_t)atoi(e) * 1024;     // tuning knobs
+  if (const char* e = getenv("MNR_POST_ROLLOUT_MIN_COPY")) kMinCopy = (size_t)atoi(e);
   size_t smem = (size_t)6 * kEnvPerScalarCta * (T + 1) * sizeof(float);
   pl->item0[0] = 0;
   for (int k = 0; k < n_wide; ++k) {
     const size_t row = (size_t)wide[k].width * 4;
-    int nb = (int)((1024 + row - 1) / row);
+    int nb = (int)((kMinCopy + row - 1) / row);
     nb = (nb + 3) / 4 * 4;
     if (nb < 4) nb = 4;
     while (nb > 4 && (size_t)T * nb * row > kTileCap) nb -= 4;

@@ -129,6 +129,10 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
 template <int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_constant__ TcParams p) {
   constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd), CONV_B = (MODE == kDw);
+  // FWD / DX: the converters write the hi / lo parts of A into TENSOR MEMORY (tcgen05.st) and the MMAs read A from there
+  // (tcgen05.mma [d], [a_tmem], b_desc): the split A never exists in shared memory, which halves the shared-memory
+  // traffic per k-block (the pipe that bounded this kernel: 12 MMAs x (A + B) operand reads + converter writes).
+  constexpr bool A_TMEM = (MODE != kDw);
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_tma[kMaxStages], full_conv[kMaxStages], empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   // (offset the extern array itself: integer round-trips make the compiler fall back to generic LD/ST)
   uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int offAlo = kTileA;  // == offS
-  const int offB = 2 * kTileA;
+  const int offB = (HAS_S || !A_TMEM) ? 2 * kTileA : kTileA;
   const int bytesB = BN * kBK * 4;
   const int offBlo = offB + bytesB;
   const int stage_bytes = offBlo + bytesB;
@@ -162,8 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     ptx::fence_mbar_init();
   }
   const uint32_t acc_stride = (uint32_t)((BN + 31) / 32 * 32);  // TMEM columns per accumulator (tcgen05.ld reads 32 at a time)
+  const uint32_t a_slots = 2 * acc_stride;  // first TMEM column of the A ring: `stages` slots of 64 columns (hi 32 | lo 32)
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2 * acc_stride) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_stride + (A_TMEM ? (uint32_t)stages * 64u : 0u)) tmem_cols <<= 1;
   if (warp == 2) ptx::tmem_alloc(&tmem_slot, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -234,6 +239,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           // descriptor = constant high word | (start address >> 4) in the low word: only the address changes
           const uint32_t a_lo32 = (base >> 4) | a_desc_lo_const, alo_lo32 = ((base + offAlo) >> 4) | a_desc_lo_const;
           const uint32_t b_lo32 = ((base + offB) >> 4) | b_desc_lo_const, blo_lo32 = ((base + offBlo) >> 4) | b_desc_lo_const;
+          if (A_TMEM) {
+            const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              const uint32_t b_step = (B_MN ? k * 1024 : k * 32) >> 4;
+              const uint64_t b_hi = b_desc_hi | (uint64_t)(b_lo32 + b_step), b_lo = b_desc_hi | (uint64_t)(blo_lo32 + b_step);
+              ptx::mma_tf32_ts(tmem_d, a_t + 32u + 8u * k, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
+              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_lo, idesc, 1u);
+              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_hi, idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
             // K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
@@ -265,19 +281,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
         float4* A4 = reinterpret_cast<float4*>(base);
         float4* Alo4 = reinterpret_cast<float4*>(base + offAlo);  // holds S on entry when HAS_S
         if (MODE != kDw) {
-          // element-wise: the swizzle is irrelevant, walk the tile linearly
-#pragma unroll 4
-          for (int q = t; q < kTileA / 16; q += 128) {
+          // thread = row r of the [128][32] tile (TMEM lane r): SWIZZLE_128B keeps its 16 B chunk c at position c ^ (r & 7),
+          // so the 8 lanes of an LDS.128 phase hit 8 different bank groups.  hi -> columns [0,32), lo -> [32,64) of the slot.
+          const int r = t;
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const int q = r * 8 + (c ^ (r & 7));
             float4 a = A4[q];
             if (HAS_S) {
               const float4 s = Alo4[q];
               a.x *= act_bwd_t<ACT>(s.x), a.y *= act_bwd_t<ACT>(s.y);
               a.z *= act_bwd_t<ACT>(s.z), a.w *= act_bwd_t<ACT>(s.w);
             }
-            float4 hi, lo;
-            split4(a, hi, lo);
-            A4[q] = hi, Alo4[q] = lo;
+            float4 h, l;
+            split4(a, h, l);
+            hi[4 * c] = __float_as_uint(h.x), hi[4 * c + 1] = __float_as_uint(h.y), hi[4 * c + 2] = __float_as_uint(h.z), hi[4 * c + 3] = __float_as_uint(h.w);
+            lo[4 * c] = __float_as_uint(l.x), lo[4 * c + 1] = __float_as_uint(l.y), lo[4 * c + 2] = __float_as_uint(l.z), lo[4 * c + 3] = __float_as_uint(l.w);
           }
+          const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u + ((uint32_t)(32 * (warp & 3)) << 16);
+          ptx::tmem_st_32x32(a_t, hi);
+          ptx::tmem_st_32x32(a_t + 32u, lo);
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
         } else {
           // MN-major A: chunk c = 32 columns of i; thread owns logical 16 B slot j (4 columns) of rows p, p+4, ...
           // SWIZZLE_128B_ATOM_32B stores the logical 32 B chunk (j >> 1) of row r at physical chunk (j >> 1) ^ (r & 3)
@@ -303,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
             B4[q] = hi, Blo4[q] = lo;
           }
         }
-        ptx::fence_proxy_async_smem();
+        if (!A_TMEM) ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_conv[st]);
         if (t == 0) TC_TRACE(1, kbg, 1);
       }
@@ -511,9 +537,10 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
 
 constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;
 
+int stage_bytes_of(int mode, int BN) { return (mode == kFwd ? 1 : 2) * kTileA + 2 * BN * kBK * 4; }
+
 int pick_stages(int mode, int BN) {
-  (void)mode;
-  const int stage = 2 * kTileA + 2 * BN * kBK * 4;
+  const int stage = stage_bytes_of(mode, BN);
   int s = (227 * 1024 - 2048 - kEpiStageBytes) / stage;
   if (s > kMaxStages) s = kMaxStages;
   return s;
@@ -525,7 +552,7 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   const int n_tiles = (int)(tiles.x * tiles.y * tiles.z);
   const int sms = mnr_sm_count();
   dim3 grid(n_tiles < sms ? n_tiles : sms);  // persistent: one CTA per SM walks the tiles
-  const int stage = 2 * kTileA + 2 * p.BN * kBK * 4;
+  const int stage = stage_bytes_of(MODE, p.BN);
   const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
   cudaError_t e = cudaSuccess;
 #define MNR_TC_LAUNCH(ACTV)                                                                                              \
@@ -556,8 +583,8 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
   const int N = groups[0].N, K = groups[0].K;
   if (N <= 0 || K <= 0 || N % 16 != 0) return MNR_ESHAPE;
   TcParams p;
-  p.BN = N <= 256 ? N : 128;
-  if (N > 256 && N % 128 != 0) return MNR_ESHAPE;
+  p.BN = N <= 128 ? N : 128;  // 2 accumulators + the A ring share the 512 TMEM columns
+  if (N > 128 && N % 128 != 0) return MNR_ESHAPE;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
     if (!s.a || !s.b || !s.b_lo || !s.c) return MNR_ENULL;
@@ -584,7 +611,7 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
   if (N <= 0 || K <= 0 || N % 4 != 0) return MNR_ESHAPE;
   TcParams p;
   const int Kr = (K + 31) / 32 * 32;
-  p.BN = Kr <= 256 ? Kr : 256;
+  p.BN = Kr <= 128 ? Kr : 128;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
     if (!s.a || !s.b || !s.b_lo || !s.c || !s.saved) return MNR_ENULL;
