@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   // FWD / DX: the converters write the hi / lo parts of A into TENSOR MEMORY (tcgen05.st) and the MMAs read A from there
   // (tcgen05.mma [d], [a_tmem], b_desc): the split A never exists in shared memory, which halves the shared-memory
   // traffic per k-block (the pipe that bounded this kernel: 12 MMAs x (A + B) operand reads + converter writes).
-  constexpr bool A_TMEM = (MODE != kDw);
+  // DW: thread = output feature i (TMEM lane), the 32 reduction rows of the k-block become its 32 columns.
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t full_tma[kMaxStages], full_conv[kMaxStages], empty_bar[kMaxStages];
   __shared__ __align__(8) uint64_t tmem_full[2], tmem_empty[2];
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   // (offset the extern array itself: integer round-trips make the compiler fall back to generic LD/ST)
   uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
   const int offAlo = kTileA;  // == offS
-  const int offB = (HAS_S || !A_TMEM) ? 2 * kTileA : kTileA;
+  const int offB = HAS_S ? 2 * kTileA : kTileA;
   const int bytesB = BN * kBK * 4;
   const int offBlo = offB + bytesB;
   const int stage_bytes = offBlo + bytesB;
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   const uint32_t acc_stride = (uint32_t)((BN + 31) / 32 * 32);  // TMEM columns per accumulator (tcgen05.ld reads 32 at a time)
   const uint32_t a_slots = 2 * acc_stride;  // first TMEM column of the A ring: `stages` slots of 64 columns (hi 32 | lo 32)
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2 * acc_stride + (A_TMEM ? (uint32_t)stages * 64u : 0u)) tmem_cols <<= 1;
+  while (tmem_cols < 2 * acc_stride + (uint32_t)stages * 64u) tmem_cols <<= 1;
   if (warp == 2) ptx::tmem_alloc(&tmem_slot, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -215,13 +215,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   } else if (warp == 1) {
     // ===== MMA issuer ===============================================================================
     if (lane == 0) {
-      const uint32_t idesc = ptx::idesc_tf32(kBM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      // K-major: SWIZZLE_128B (layout 2), 8-row groups 1 KiB apart (SBO), LBO unused (16 B).
+      const uint32_t idesc = ptx::idesc_tf32(kBM, BN, 0, B_MN ? 1 : 0);
+      // B descriptors.  K-major: SWIZZLE_128B (layout 2), 8-row groups 1 KiB apart (SBO), LBO unused (16 B).
       // MN-major (32-bit): SWIZZLE_128B_BASE32B (layout 1), 4-row reduction groups 512 B apart (SBO), 32-float
-      // chunks along M/N one 4 KiB box apart (LBO).
-      const uint64_t a_desc_hi = ptx::smem_desc(0, 0, A_MN ? 512 : 1024, A_MN ? 1 : 2);
+      // chunks along N one 4 KiB box apart (LBO).
       const uint64_t b_desc_hi = ptx::smem_desc(0, 0, B_MN ? 512 : 1024, B_MN ? 1 : 2);
-      const uint32_t a_desc_lo_const = ((A_MN ? (uint32_t)kChunk : 16u) >> 4) << 16;
       const uint32_t b_desc_lo_const = ((B_MN ? (uint32_t)kChunk : 16u) >> 4) << 16;
       uint32_t kbg = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -237,28 +235,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           ptx::tc_fence_after();
           const uint32_t base = ptx::smem_u32(smem + (size_t)st * stage_bytes);
           // descriptor = constant high word | (start address >> 4) in the low word: only the address changes
-          const uint32_t a_lo32 = (base >> 4) | a_desc_lo_const, alo_lo32 = ((base + offAlo) >> 4) | a_desc_lo_const;
           const uint32_t b_lo32 = ((base + offB) >> 4) | b_desc_lo_const, blo_lo32 = ((base + offBlo) >> 4) | b_desc_lo_const;
-          if (A_TMEM) {
-            const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u;
-#pragma unroll
-            for (int k = 0; k < kBK / 8; ++k) {
-              const uint32_t b_step = (B_MN ? k * 1024 : k * 32) >> 4;
-              const uint64_t b_hi = b_desc_hi | (uint64_t)(b_lo32 + b_step), b_lo = b_desc_hi | (uint64_t)(blo_lo32 + b_step);
-              ptx::mma_tf32_ts(tmem_d, a_t + 32u + 8u * k, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_lo, idesc, 1u);
-              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_hi, idesc, 1u);
-            }
-          } else
+          const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u;  // A ring slot: hi at +0, lo at +32
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
-            // K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
-            const uint32_t a_step = (A_MN ? k * 1024 : k * 32) >> 4, b_step = (B_MN ? k * 1024 : k * 32) >> 4;
-            const uint64_t a_hi = a_desc_hi | (uint64_t)(a_lo32 + a_step), a_lo = a_desc_hi | (uint64_t)(alo_lo32 + a_step);
+            // B K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
+            const uint32_t b_step = (B_MN ? k * 1024 : k * 32) >> 4;
             const uint64_t b_hi = b_desc_hi | (uint64_t)(b_lo32 + b_step), b_lo = b_desc_hi | (uint64_t)(blo_lo32 + b_step);
-            ptx::mma_tf32(tmem_d, a_lo, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
-            ptx::mma_tf32(tmem_d, a_hi, b_lo, idesc, 1u);
-            ptx::mma_tf32(tmem_d, a_hi, b_hi, idesc, 1u);
+            ptx::mma_tf32_ts(tmem_d, a_t + 32u + 8u * k, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
+            ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_lo, idesc, 1u);
+            ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_hi, idesc, 1u);
           }
           ptx::tc_commit(&empty_bar[st]);  // stage reusable once these MMAs have read it
           TC_TRACE(2, kbg, 1);
@@ -305,48 +291,42 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           ptx::tmem_st_wait();
           ptx::tc_fence_before();
         } else {
-          // MN-major A: chunk c = 32 columns of i; thread owns logical 16 B slot j (4 columns) of rows p, p+4, ...
-          // SWIZZLE_128B_ATOM_32B stores the logical 32 B chunk (j >> 1) of row r at physical chunk (j >> 1) ^ (r & 3)
-          const int c = t >> 5, j = t & 7, ph = (t & 31) >> 3;
+          // MN-major A tile = 4 chunks of [32 reduction rows][32 features]; thread = feature i = 32 * chunk + lane.
+          // SWIZZLE_128B_ATOM_32B keeps the 32 B piece (l >> 3) of row r at piece (l >> 3) ^ (r & 3): the 32 lanes of a
+          // warp read one whole 128 B row per LDS -> conflict-free.  The bias gradient (column sum of dZ) is a
+          // per-thread scalar now.
+          const int c = warp & 3, l = lane;
+          const float* Af = reinterpret_cast<const float*>(base) + c * (kChunk / 4);
+          const float* Sf = reinterpret_cast<const float*>(base + offAlo) + c * (kChunk / 4);
+          uint32_t hi[32], lo[32];
 #pragma unroll
-          for (int rr = 0; rr < 8; ++rr) {
-            const int r = ph + 4 * rr;
-            const int q = c * (kChunk / 16) + r * 8 + ((((j >> 1) ^ (r & 3)) << 1) | (j & 1));
-            float4 a = A4[q];
-            const float4 s = Alo4[q];
-            a.x *= act_bwd_t<ACT>(s.x), a.y *= act_bwd_t<ACT>(s.y);
-            a.z *= act_bwd_t<ACT>(s.z), a.w *= act_bwd_t<ACT>(s.w);
-            bsum.x += a.x, bsum.y += a.y, bsum.z += a.z, bsum.w += a.w;
-            float4 hi, lo;
-            split4(a, hi, lo);
-            A4[q] = hi, Alo4[q] = lo;
+          for (int r = 0; r < 32; ++r) {
+            const int q = r * 32 + ((((l >> 3) ^ (r & 3)) << 3) | (l & 7));
+            const float a = Af[q] * act_bwd_t<ACT>(Sf[q]);
+            bsum.x += a;
+            const float h = tf32_hi(a);
+            hi[r] = __float_as_uint(h), lo[r] = __float_as_uint(a - h);
           }
+          const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u + ((uint32_t)(32 * c) << 16);
+          ptx::tmem_st_32x32(a_t, hi);
+          ptx::tmem_st_32x32(a_t + 32u, lo);
           float4* B4 = reinterpret_cast<float4*>(base + offB);
           float4* Blo4 = reinterpret_cast<float4*>(base + offBlo);
           for (int q = t; q < bytesB / 16; q += 128) {
-            float4 hi, lo;
-            split4(B4[q], hi, lo);
-            B4[q] = hi, Blo4[q] = lo;
+            float4 h4, l4;
+            split4(B4[q], h4, l4);
+            B4[q] = h4, Blo4[q] = l4;
           }
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
+          ptx::fence_proxy_async_smem();
         }
-        if (!A_TMEM) ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&full_conv[st]);
         if (t == 0) TC_TRACE(1, kbg, 1);
       }
       if (MODE == kDw && p.want_bias && tc.j0 == 0) {
-        // fold the 4 row phases (lanes j, j+8, j+16, j+24); lanes 0..7 then own 4 columns each of chunk c = warp-4
-        bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 8), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 8);
-        bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 8), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 8);
-        bsum.x += __shfl_xor_sync(0xffffffffu, bsum.x, 16), bsum.y += __shfl_xor_sync(0xffffffffu, bsum.y, 16);
-        bsum.z += __shfl_xor_sync(0xffffffffu, bsum.z, 16), bsum.w += __shfl_xor_sync(0xffffffffu, bsum.w, 16);
-        if (lane < 8) {
-          float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)tc.gi * p.splits + tc.split) * p.I;
-          const int n = tc.i0 + 32 * (warp - 4) + 4 * lane;
-          const float vals[4] = {bsum.x, bsum.y, bsum.z, bsum.w};
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (n + u < p.I) bp[n + u] = vals[u];
-        }
+        float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)tc.gi * p.splits + tc.split) * p.I;
+        if (tc.i0 + t < p.I) bp[tc.i0 + t] = bsum.x;
       }
     }
   } else if (warp >= 8) {
@@ -631,8 +611,16 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
 
 namespace {
 int tc_dw_splits(int M, int tiles) {
-  int s = mnr_sm_count() / tiles;      // one wave: 1 CTA per SM (the kernel's smem footprint allows no more)
-  const int max_s = (M + 255) / 256;   // >= 256 rows (8 k-blocks) per CTA
+  // Split the reduction (the minibatch rows) so that (a) one accumulation chain in TMEM covers <= 512 rows: the tensor
+  // core's fp32 accumulate error grows with the chain length and the parity bar is 1e-5; (b) tiles x splits fills whole
+  // waves of the persistent grid (a CTA then walks 2+ work items back to back with double-buffered accumulators).
+  const int sms = mnr_sm_count();
+  int s_min = (M + 511) / 512;
+  if (s_min < 1) s_min = 1;
+  const int waves = (tiles * s_min + sms - 1) / sms;
+  int s = waves * sms / tiles;
+  if (s < s_min) s = s_min;
+  const int max_s = (M + 63) / 64;  // >= 64 rows (2 k-blocks) per work item
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
 }
@@ -640,7 +628,7 @@ int tc_dw_splits(int M, int tiles) {
 
 extern "C" size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K) {
   if (n_groups <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
-  const int Kr = (K + 31) / 32 * 32, BN = Kr <= 256 ? Kr : 256;
+  const int Kr = (K + 31) / 32 * 32, BN = Kr <= 128 ? Kr : 128;
   const int tiles = ((N + kBM - 1) / kBM) * ((K + BN - 1) / BN) * n_groups;
   return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + N) * sizeof(float);
 }
@@ -656,7 +644,7 @@ extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_
   if (workspace_bytes < mnr_tc_linear_bwd_weight_workspace_bytes(n_groups, M, N, K)) return MNR_EWORKSPACE;
   TcParams p;
   const int Kr = (K + 31) / 32 * 32;
-  p.BN = Kr <= 256 ? Kr : 256;
+  p.BN = Kr <= 128 ? Kr : 128;
   ReduceArgs ra;
   bool want_bias = false;
   for (int k = 0; k < n_groups; ++k) {
