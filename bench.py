@@ -361,14 +361,15 @@ def main():
     if tw is not None and tw.use_tc and tw.L >= 2:
         from mineral_b200 import ops
         n, k = tw.la[1].weight.shape
-        groups = [dict(a=tw.Y[0][t], b=tw.w_hi[1][t], b_lo=tw.w_lo[1][t], c=tw.Y[1][t], bias=l.bias.data, N=n, K=k, lda=k, ldb=tw.w_ld[1])
+        out = tw.Z[1] if tw.normed else tw.Y[1]
+        groups = [dict(a=tw.Y[0][t], b=tw.w_hi[1][t], b_lo=tw.w_lo[1][t], c=out[t], bias=l.bias.data, N=n, K=k, lda=k, ldb=tw.w_ld[1])
                   for t, l in enumerate((tw.la[1], tw.lv[1]))]
         ts = []
         for _ in range(20):
             flush.zero_()
             torch.cuda._sleep(400_000)
             ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ea.record(); ops.tc_linear_fwd(groups, tw.M, tw.act); eb.record(); torch.cuda.synchronize()
+            ea.record(); ops.tc_linear_fwd(groups, tw.M, tw.gemm_act); eb.record(); torch.cuda.synchronize()
             ts.append(ea.elapsed_time(eb))
         t_ms = statistics.mean(sorted(ts)[:15])
         flops = 2 * 2.0 * tw.M * n * k

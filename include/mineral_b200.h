@@ -417,6 +417,32 @@ int mnr_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int mnr_kl_lr_update(mnr_optim_state_t* st, double kl_threshold, double min_lr, double max_lr,
                      float* avg_kl_out, double* lr_out, mnr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * a10  LayerNorm + activation between the tower GEMMs (mineral/nets/mlp.py:66-71; the shipped PPO recipes
+ *      mineral/cfgs/agent/DFlexAntPPO.yaml:17-21 and AllegroHandPPO.yaml:18-28 use Linear -> LayerNorm -> SiLU).
+ *      fwd: y = act(gamma * (z - mean) * rstd + beta), mean / rstd (M) saved;  biased variance, eps inside the sqrt.
+ *      bwd: dz from dy (through act' and the normalisation), dgamma / dbeta (N) summed over the M rows
+ *           (deterministic).  act: 0 none, 1 ELU, 2 ReLU, 3 SiLU.  N <= 512.  Up to 2 groups per launch.
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  const float* z;      /* (M,N) pre-normalisation */
+  float* y;            /* fwd out (M,N) */
+  const float* gamma;  /* (N) */
+  const float* beta;   /* (N) */
+  float* mean;         /* (M): fwd out, bwd in */
+  float* rstd;         /* (M) */
+  const float* dy;     /* bwd in (M,N) */
+  float* dz;           /* bwd out (M,N) */
+  float* dgamma;       /* bwd out (N) */
+  float* dbeta;        /* bwd out (N) */
+} mnr_ln_group_t;
+
+int mnr_ln_act_fwd(const mnr_ln_group_t* groups /*host*/, int n_groups, int64_t M, int N, float eps, int act,
+                   mnr_stream_t stream);
+size_t mnr_ln_act_bwd_workspace_bytes(int n_groups, int64_t M, int N);
+int mnr_ln_act_bwd(const mnr_ln_group_t* groups /*host*/, int n_groups, int64_t M, int N, int act, void* workspace,
+                   size_t workspace_bytes, mnr_stream_t stream);
+
 /* Single-GPU fused optimizer step: mnr_grad_norm_prepare + mnr_adam_step in ONE launch (grid-wide
  * barrier between the norm and the update; grid <= #SMs so every CTA is resident).  n % 4 == 0, all
  * buffers 16 B aligned.  workspace: mnr_fused_adam_workspace_bytes() bytes, zero-filled once. */

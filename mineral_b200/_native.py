@@ -78,6 +78,10 @@ class OptimState(C.Structure):
                 ("lr_f32", C.c_float), ("_pad", C.c_float)]
 
 
+class LnGroup(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("z", "y", "gamma", "beta", "mean", "rstd", "dy", "dz", "dgamma", "dbeta")]
+
+
 class PeerCommStruct(C.Structure):
     _fields_ = [("base", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
 
@@ -138,6 +142,9 @@ SIGNATURES = {
     "mnr_grad_norm_prepare": (i32, [vp, i64, f32, f32, f32, vp, vp, vp, vp, sz, vp]),
     "mnr_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, i32, vp, vp]),
     "mnr_kl_lr_update": (i32, [vp, f64, f64, f64, vp, vp, vp]),
+    "mnr_ln_act_fwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, f32, i32, vp]),
+    "mnr_ln_act_bwd_workspace_bytes": (sz, [i32, i64, i32]),
+    "mnr_ln_act_bwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, i32, vp, sz, vp]),
     "mnr_fused_adam_workspace_bytes": (sz, []),
     "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, vp, sz, vp]),
     "mnr_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),

@@ -128,7 +128,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
 //   warps 8-15  epilogue (tcgen05.ld -> bias + activation -> per-warp 32x32 transpose in smem -> full-line stores)
 template <int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_constant__ TcParams p) {
-  constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd), CONV_B = (MODE == kDw);
+  constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd) && (ACT != 0), CONV_B = (MODE == kDw);
+  // (ACT == 0 in DX / DW: the incoming gradient is already dZ, e.g. behind a LayerNorm; no saved-output tile is loaded)
   // FWD / DX: the converters write the hi / lo parts of A into TENSOR MEMORY (tcgen05.st) and the MMAs read A from there
   // (tcgen05.mma [d], [a_tmem], b_desc): the split A never exists in shared memory, which halves the shared-memory
   // traffic per k-block (the pipe that bounded this kernel: 12 MMAs x (A + B) operand reads + converter writes).
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
               ptx::tma_load_2d(base + c * kChunk, &g.a, tc.i0 + 32 * c, r0, &full_tma[st]);
-              ptx::tma_load_2d(base + offAlo + c * kChunk, &g.s, tc.i0 + 32 * c, r0, &full_tma[st]);
+              if (HAS_S) ptx::tma_load_2d(base + offAlo + c * kChunk, &g.s, tc.i0 + 32 * c, r0, &full_tma[st]);
             }
           }
           if (!B_MN) {  // box [BN rows][32 floats]
@@ -302,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
             const int q = r * 32 + ((((l >> 3) ^ (r & 3)) << 3) | (l & 7));
-            const float a = Af[q] * act_bwd_t<ACT>(Sf[q]);
+            const float a = HAS_S ? Af[q] * act_bwd_t<ACT>(Sf[q]) : Af[q];
             bsum.x += a;
             const float h = tf32_hi(a);
             hi[r] = __float_as_uint(h), lo[r] = __float_as_uint(a - h);
@@ -517,10 +518,10 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
 
 constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;
 
-int stage_bytes_of(int mode, int BN) { return (mode == kFwd ? 1 : 2) * kTileA + 2 * BN * kBK * 4; }
+int stage_bytes_of(int mode, int act, int BN) { return ((mode == kFwd || act == 0) ? 1 : 2) * kTileA + 2 * BN * kBK * 4; }
 
-int pick_stages(int mode, int BN) {
-  const int stage = stage_bytes_of(mode, BN);
+int pick_stages(int mode, int act, int BN) {
+  const int stage = stage_bytes_of(mode, act, BN);
   int s = (227 * 1024 - 2048 - kEpiStageBytes) / stage;
   if (s > kMaxStages) s = kMaxStages;
   return s;
@@ -532,7 +533,7 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   const int n_tiles = (int)(tiles.x * tiles.y * tiles.z);
   const int sms = mnr_sm_count();
   dim3 grid(n_tiles < sms ? n_tiles : sms);  // persistent: one CTA per SM walks the tiles
-  const int stage = stage_bytes_of(MODE, p.BN);
+  const int stage = stage_bytes_of(MODE, p.act, p.BN);
   const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
   cudaError_t e = cudaSuccess;
 #define MNR_TC_LAUNCH(ACTV)                                                                                              \
@@ -577,7 +578,7 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
     p.g[k].c = s.c, p.g[k].bias = s.bias;
   }
   p.I = M, p.J = N, p.R = K, p.ldc = N, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
-  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kFwd, p.BN);
+  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kFwd, act, p.BN);
   dim3 grid((M + kBM - 1) / kBM, (N + p.BN - 1) / p.BN, n_groups);
   return launch<kFwd>(p, grid, mnr_cs(stream));
 }
@@ -594,17 +595,17 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
   p.BN = Kr <= 128 ? Kr : 128;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
-    if (!s.a || !s.b || !s.b_lo || !s.c || !s.saved) return MNR_ENULL;
+    if (!s.a || !s.b || !s.b_lo || !s.c || (act != 0 && !s.saved)) return MNR_ENULL;
     if (s.N != N || s.K != K) return MNR_ESHAPE;
     int rc = make_map(&p.g[k].a, s.a, M, N, N, kBM);                                 // dY (M,N), reduction over N
-    if (rc == MNR_OK) rc = make_map(&p.g[k].s, s.saved, M, N, N, kBM);               // Y
+    if (rc == MNR_OK) rc = make_map(&p.g[k].s, act != 0 ? s.saved : s.a, M, N, N, kBM);  // Y
     if (rc == MNR_OK) rc = make_map(&p.g[k].b0, s.b, N, K, ld_or(s.ldb, K), 32, true);  // W (N,K): rows = reduction
     if (rc == MNR_OK) rc = make_map(&p.g[k].b1, s.b_lo, N, K, ld_or(s.ldb, K), 32, true);
     if (rc != MNR_OK) return rc;
     p.g[k].c = s.c, p.g[k].bias = nullptr;
   }
   p.I = M, p.J = K, p.R = N, p.ldc = K, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
-  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kDx, p.BN);
+  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kDx, act, p.BN);
   dim3 grid((M + kBM - 1) / kBM, (K + p.BN - 1) / p.BN, n_groups);
   return launch<kDx>(p, grid, mnr_cs(stream));
 }
@@ -649,10 +650,10 @@ extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_
   bool want_bias = false;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
-    if (!s.a || !s.b || !s.c || !s.saved) return MNR_ENULL;
+    if (!s.a || !s.b || !s.c || (act != 0 && !s.saved)) return MNR_ENULL;
     if (s.N != N || s.K != K) return MNR_ESHAPE;
     int rc = make_map(&p.g[k].a, s.a, M, N, N, 32, true);                            // dY (M,N): rows = reduction
-    if (rc == MNR_OK) rc = make_map(&p.g[k].s, s.saved, M, N, N, 32, true);
+    if (rc == MNR_OK) rc = make_map(&p.g[k].s, act != 0 ? s.saved : s.a, M, N, N, 32, true);
     if (rc == MNR_OK) rc = make_map(&p.g[k].b0, s.b, M, K, ld_or(s.ldb, K), 32, true);  // X (M,K)
     if (rc != MNR_OK) return rc;
     p.g[k].b1 = p.g[k].b0;
@@ -665,7 +666,7 @@ extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_
   const int splits = tc_dw_splits(M, ti * tj * n_groups);
   p.I = N, p.J = K, p.R = M, p.ldc = K, p.act = act, p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 31) / 32 * 32;
-  p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = pick_stages(kDw, p.BN);
+  p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = pick_stages(kDw, act, p.BN);
   dim3 grid(ti, tj, n_groups * splits);
   const int rc = launch<kDw>(p, grid, mnr_cs(stream));
   if (rc != MNR_OK) return rc;

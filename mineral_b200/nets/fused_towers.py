@@ -1,13 +1,19 @@
-"""Explicit forward / backward of `ActorCritic._actor_critic` on the hand-written linear-layer kernels
-(csrc/mlp.cu): no nn.Linear, no activation kernels, no autograd graph on the PPO update path.
+"""Explicit forward / backward of `ActorCritic._actor_critic` on the hand-written kernels: tcgen05 linear layers
+(csrc/tc_linear.cu; SIMT twins in csrc/mlp.cu), LayerNorm + activation passes (csrc/norm_act.cu) and the fused
+heads + loss kernel (csrc/heads_fused.cu).  No nn.Linear / nn.LayerNorm / activation module, no autograd graph on the
+PPO update path.
 
-Replaces, for the update, `MLP.forward` (mineral/nets/mlp.py:76-77) of both towers, the `mu` / `sigma` /
-`value` heads (mineral/agents/ppo/models.py:136-151) and torch autograd's backward through them.  The
-module's parameters stay ordinary `nn.Parameter`s (views into FusedAdam's flat buffers); this class
-only reads `.data` and writes `.grad`.
+Replaces, for the update, `MLP.forward` (mineral/nets/mlp.py:76-77) of both towers, the `mu` / `sigma` / `value`
+heads (mineral/agents/ppo/models.py:136-151) and torch autograd's backward through them.  The module's parameters
+stay ordinary `nn.Parameter`s (views into FusedAdam's flat buffers); this class only reads `.data` and writes `.grad`.
 
-Supported towers: Linear -> {ELU | ReLU | none} stacks without normalisation / dropout, separate value
-tower.  Anything else (LayerNorm + SiLU recipes) keeps the autograd path for now.
+Supported towers (separate value tower, both towers of the same shape, no dropout):
+  * Linear -> {ELU | ReLU | none}                      bias + activation fused into the GEMM epilogue, act' into the
+                                                       backward GEMMs' operand load;
+  * Linear -> LayerNorm -> {SiLU | ELU | ReLU | none}  the shipped PPO recipes (mineral/cfgs/agent/DFlexAntPPO.yaml:17-21,
+                                                       AllegroHandPPO.yaml:18-28): GEMM (+bias) -> one LN+act pass;
+                                                       backward: one LN+act backward pass (dgamma, dbeta, dZ in place) ->
+                                                       GEMMs on dZ.
 """
 
 import torch
@@ -15,25 +21,43 @@ import torch.nn as nn
 
 from .. import ops
 
-_ACT = {nn.ELU: 1, nn.ReLU: 2}
+_ACT = {nn.ELU: 1, nn.ReLU: 2, nn.SiLU: 3}
 
 
 def _tower_layers(mlp):
-    """-> (list of nn.Linear, act code) or None if the tower has an unsupported layer."""
-    linears, act = [], None
+    """-> (list of (nn.Linear, nn.LayerNorm | None), act code) or None if the tower has an unsupported layer."""
+    blocks, act = [], None
     for m in mlp.mlp:
         if isinstance(m, nn.Linear):
-            linears.append(m)
+            blocks.append([m, None, False])
+        elif isinstance(m, nn.LayerNorm):
+            if not blocks or blocks[-1][1] is not None or blocks[-1][2] or not m.elementwise_affine or m.bias is None:
+                return None
+            if tuple(m.normalized_shape) != (blocks[-1][0].weight.shape[0],):
+                return None
+            blocks[-1][1] = m
         elif type(m) in _ACT:
             code = _ACT[type(m)]
             if isinstance(m, nn.ELU) and m.alpha != 1.0:
                 return None
-            if act not in (None, code):
+            if not blocks or blocks[-1][2] or act not in (None, code):
                 return None
-            act = code
+            act, blocks[-1][2] = code, True
+        elif isinstance(m, nn.Identity):
+            continue
         else:
             return None
-    return linears, (act or 0)
+    if not blocks:
+        return None
+    normed = [b[1] is not None for b in blocks]
+    acted = [b[2] for b in blocks]
+    if any(normed) != all(normed) or (act is not None and not all(acted)):
+        return None
+    if act == 3 and not all(normed):  # SiLU' needs the pre-activation: only behind a LayerNorm (recomputed from z)
+        return None
+    if any(b[0].bias is None for b in blocks):
+        return None
+    return [(b[0], b[1]) for b in blocks], (act or 0)
 
 
 class FusedTowers:
@@ -44,13 +68,21 @@ class FusedTowers:
         a, v = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
         if a is None or v is None or a[1] != v[1] or len(a[0]) != len(v[0]):
             return False
-        if any(x.weight.shape != y.weight.shape or x.bias is None or y.bias is None for x, y in zip(a[0], v[0])):
-            return False
-        return len(a[0]) == sum(isinstance(m, nn.Linear) for m in model.actor_mlp.mlp)
+        for (la, na), (lv, nv_) in zip(a[0], v[0]):
+            if la.weight.shape != lv.weight.shape or (na is None) != (nv_ is None):
+                return False
+            if na is not None and (na.eps != nv_.eps or la.weight.shape[0] > 512):
+                return False
+        return True
 
     def __init__(self, model, rows, device, use_tc=True):
         self.model, self.M = model, rows
-        (self.la, self.act), (self.lv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
+        (ba, self.act), (bv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
+        self.la, self.lv = [b[0] for b in ba], [b[0] for b in bv]
+        self.na, self.nv = [b[1] for b in ba], [b[1] for b in bv]
+        self.normed = self.na[0] is not None
+        # activation applied by the GEMM kernels themselves (epilogue / operand load); behind a LayerNorm it is 0
+        self.gemm_act = 0 if self.normed else self.act
         self.L = len(self.la)
         self.A = model.mu.weight.shape[0]
         self.fixed_sigma = model.fixed_sigma
@@ -60,6 +92,11 @@ class FusedTowers:
         # saved forward outputs and their gradients, per layer, per tower (0 actor, 1 value)
         self.Y = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
         self.dY = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
+        if self.normed:  # pre-normalisation GEMM outputs and the row statistics
+            self.Z = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
+            self.mean = [[torch.empty(rows, **f32) for _ in range(2)] for _ in widths]
+            self.rstd = [[torch.empty(rows, **f32) for _ in range(2)] for _ in widths]
+            self.ln_ws = [ops.ln_act_bwd_workspace(2, rows, w, device) for w in widths]
         self.mu_raw = torch.empty(rows, self.A, **f32)
         self.value = torch.empty(rows, 1, **f32)
         self.ls = None if self.fixed_sigma else torch.empty(rows, self.A, **f32)
@@ -74,7 +111,7 @@ class FusedTowers:
         # 16 B-multiple row strides, so W is kept pre-split (hi / lo) in K-padded buffers and the first layer's
         # input is read through a padded row stride `in_ld`.
         self.in_ld = (self.in_dim + 3) // 4 * 4
-        self.use_tc = bool(use_tc) and ops.tc_supported() and all(w % 16 == 0 for w in widths)
+        self.use_tc = bool(use_tc) and ops.tc_supported() and all(w % 16 == 0 and (w <= 128 or w % 128 == 0) for w in widths)
         if self.use_tc:
             self.w_hi, self.w_lo, self.w_ld = [], [], []
             k = self.in_dim
@@ -106,7 +143,7 @@ class FusedTowers:
 
     def forward_towers(self, x, x_ld=None):
         """Both towers up to their last activation (self.Y[-1])."""
-        M, m = self.M, self.model
+        M = self.M
         x_ld = self.in_dim if x_ld is None else x_ld
         self._x_ld = x_ld
         tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
@@ -116,12 +153,16 @@ class FusedTowers:
         for i in range(self.L):
             n, k = self.la[i].weight.shape
             lda = x_ld if i == 0 else k
+            out = self.Z[i] if self.normed else self.Y[i]
             if self.use_tc and (i > 0 or tc0):
-                ops.tc_linear_fwd([dict(a=inp[t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=self.Y[i][t], bias=l.bias.data, N=n, K=k,
-                                        lda=lda, ldb=self.w_ld[i]) for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+                ops.tc_linear_fwd([dict(a=inp[t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=out[t], bias=l.bias.data, N=n, K=k,
+                                        lda=lda, ldb=self.w_ld[i]) for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)
             else:
-                ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=self.Y[i][t], bias=l.bias.data, N=n, K=k, lda=lda)
-                                for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+                ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=out[t], bias=l.bias.data, N=n, K=k, lda=lda)
+                                for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)
+            if self.normed:
+                ops.ln_act_fwd([dict(z=self.Z[i][t], y=self.Y[i][t], gamma=nm.weight.data, beta=nm.bias.data, mean=self.mean[i][t],
+                                     rstd=self.rstd[i][t]) for t, nm in enumerate((self.na[i], self.nv[i]))], M, n, self.na[i].eps, self.act)
             inp = self.Y[i]
 
     def heads_forward(self):
@@ -146,9 +187,9 @@ class FusedTowers:
         return h % 8 == 0 and h <= 128 and self.A <= 32
 
     def heads_loss_fwd_bwd(self, d, s, e, g_mu, g_ls, g_v, metrics, cfg, ws, mu_mean, sigma_mean):
-        """Heads forward + PPO loss + its backward + head parameter gradients + d loss / d Y[-1], two launches
-        (csrc/ppo_loss.cu: ppo_heads_loss_kernel, head_grads_kernel).  `d` is the env-major data dict, [s:e) the
-        minibatch rows."""
+        """Heads forward + PPO loss + its backward + head parameter gradients + d loss / d Y[-1] (csrc/heads_fused.cu,
+        one persistent kernel; csrc/ppo_loss.cu two-kernel form for odd shapes).  `d` is the env-major data dict,
+        [s:e) the minibatch rows."""
         m = self.model
         ya, yv = self.Y[-1]
         fixed = self.fixed_sigma
@@ -177,7 +218,8 @@ class FusedTowers:
             ops.linear_bwd_input([dict(a=g_ls, b=m.sigma.weight.data, c=self.dY[top][0], N=self.A, K=h)], M, 0, accumulate=True)
 
     def backward_towers(self, x):
-        """Tower layers, top first, from self.dY[-1]; act'(.) is applied on the fly from the saved outputs."""
+        """Tower layers, top first, from self.dY[-1].  Without a norm, act'(.) is applied on the fly from the saved outputs
+        inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta) first."""
         M, top = self.M, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
         for i in range(top, -1, -1):
@@ -185,16 +227,21 @@ class FusedTowers:
             src = self.Y[i - 1] if i > 0 else [x, x]
             ldb = x_ld if i == 0 else k
             tc = self.use_tc and ldb % 4 == 0
-            wg = [dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=self.Y[i][t], bias_grad=l.bias.grad, N=n, K=k, ldb=ldb)
+            if self.normed:
+                ops.ln_act_bwd([dict(z=self.Z[i][t], gamma=nm.weight.data, beta=nm.bias.data, mean=self.mean[i][t], rstd=self.rstd[i][t],
+                                     dy=self.dY[i][t], dz=self.dY[i][t], dgamma=nm.weight.grad, dbeta=nm.bias.grad)
+                                for t, nm in enumerate((self.na[i], self.nv[i]))], M, n, self.act, self.ln_ws[i])
+            saved = [None, None] if self.normed else self.Y[i]
+            wg = [dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=saved[t], bias_grad=l.bias.grad, N=n, K=k, ldb=ldb)
                   for t, l in enumerate((self.la[i], self.lv[i]))]
             if tc:
-                ops.tc_linear_bwd_weight(wg, M, self.act, self.tc_ws)
+                ops.tc_linear_bwd_weight(wg, M, self.gemm_act, self.tc_ws)
             else:
-                ops.linear_bwd_weight(wg, M, self.act, self.ws)
+                ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
             if i > 0:
                 if self.use_tc:
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=self.dY[i - 1][t],
-                                                  saved=self.Y[i][t], N=n, K=k, ldb=self.w_ld[i]) for t in range(2)], M, self.act)
+                                                  saved=saved[t], N=n, K=k, ldb=self.w_ld[i]) for t in range(2)], M, self.gemm_act)
                 else:
-                    ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=self.Y[i][t], N=n, K=k)
-                                          for t, l in enumerate((self.la[i], self.lv[i]))], M, self.act)
+                    ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=saved[t], N=n, K=k)
+                                          for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)

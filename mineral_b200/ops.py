@@ -312,6 +312,31 @@ def linear_bwd_weight(groups, M, act, ws):
           "mnr_linear_bwd_weight", kernels=2)
 
 
+def _ln_groups(groups):
+    """groups: list of dict(z=, y=, gamma=, beta=, mean=, rstd=, dy=, dz=, dgamma=, dbeta=) (missing -> NULL)."""
+    arr = (nv.LnGroup * len(groups))()
+    for i, g in enumerate(groups):
+        def p(name):
+            t = g.get(name)
+            return None if t is None else ptr(t, F32, name).value
+        arr[i] = nv.LnGroup(p("z"), p("y"), p("gamma"), p("beta"), p("mean"), p("rstd"), p("dy"), p("dz"), p("dgamma"), p("dbeta"))
+    return arr
+
+
+def ln_act_fwd(groups, M, N, eps, act):
+    """y = act(LayerNorm(z)) for up to 2 (M,N) matrices in one launch; saves mean / rstd (csrc/norm_act.cu)."""
+    check(lib.mnr_ln_act_fwd(_ln_groups(groups), len(groups), M, N, eps, act, stream()), "mnr_ln_act_fwd")
+
+
+def ln_act_bwd_workspace(n_groups, M, N, device):
+    return torch.zeros(lib.mnr_ln_act_bwd_workspace_bytes(n_groups, M, N), dtype=U8, device=device)
+
+
+def ln_act_bwd(groups, M, N, act, ws):
+    """dz, dgamma, dbeta from dy through act' and the normalisation (dz may alias dy)."""
+    check(lib.mnr_ln_act_bwd(_ln_groups(groups), len(groups), M, N, act, ptr(ws, U8), ws.numel(), stream()), "mnr_ln_act_bwd")
+
+
 def colsum(x, out, ws):
     M, Cc = x.shape
     check(lib.mnr_colsum_f32(ptr(x, F32), M, Cc, ptr(out, F32), ptr(ws, U8), ws.numel(), stream()), "mnr_colsum_f32")

@@ -595,15 +595,19 @@ def test_ppo_first_step_gradients_vs_oracle():
 # ------------------------------------------------------------------------------------------------
 # G: fused MLP towers vs torch autograd on the same module
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rows,O,A,units,act,fixed_sigma", [(512, 37, 8, [256, 128, 64], "ELU", True), (333, 11, 3, [32, 16], "ELU", False),
-                                                            (2048, 88, 16, [64, 64, 32, 16], "ReLU", True), (130, 5, 2, [8], "ELU", True)])
+@pytest.mark.parametrize("rows,O,A,units,act,fixed_sigma,norm", [
+    (512, 37, 8, [256, 128, 64], "ELU", True, None), (333, 11, 3, [32, 16], "ELU", False, None),
+    (2048, 88, 16, [64, 64, 32, 16], "ReLU", True, None), (130, 5, 2, [8], "ELU", True, None),
+    # the shipped PPO recipes: Linear -> LayerNorm -> SiLU (DFlexAntPPO.yaml / AllegroHandPPO.yaml), plus odd widths
+    (1024, 37, 8, [512, 256, 128], "SiLU", False, "LayerNorm"), (700, 88, 16, [512, 256, 128], "SiLU", False, "LayerNorm"),
+    (333, 11, 3, [48, 16], "ELU", True, "LayerNorm"), (257, 9, 4, [160, 32], None, True, "LayerNorm")])
 @pytest.mark.parametrize("use_tc", [False, True])
-def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, use_tc):
+def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, norm, use_tc):
     from mineral_b200.agents.ppo.models import ActorCritic
     from mineral_b200.nets.fused_towers import FusedTowers
 
     torch.manual_seed(rows)
-    model = ActorCritic({"obs": (O,)}, A, mlp_kwargs=dict(units=units, act_type=act), fixed_sigma=fixed_sigma).to(DEV)
+    model = ActorCritic({"obs": (O,)}, A, mlp_kwargs=dict(units=units, act_type=act, norm_type=norm), fixed_sigma=fixed_sigma).to(DEV)
     with torch.no_grad():
         for p in model.parameters():
             p.add_(0.05 * torch.randn_like(p))  # biases / sigma away from zero
