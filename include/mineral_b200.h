@@ -445,12 +445,29 @@ int mnr_ln_act_bwd(const mnr_ln_group_t* groups /*host*/, int n_groups, int64_t 
 
 /* Single-GPU fused optimizer step: mnr_grad_norm_prepare + mnr_adam_step in ONE launch (grid-wide
  * barrier between the norm and the update; grid <= #SMs so every CTA is resident).  n % 4 == 0, all
- * buffers 16 B aligned.  workspace: mnr_fused_adam_workspace_bytes() bytes, zero-filled once. */
+ * buffers 16 B aligned.  workspace: mnr_fused_adam_workspace_bytes() bytes, zero-filled once.
+ * nan_to_num != 0: non-finite gradient entries count as 0 (SHAC's grad.nan_to_num_(0,0,0),
+ * mineral/agents/diffrl/shac.py:841-843); clipped_norm_out (may be NULL) = norm * clip coefficient, the
+ * "grad_norm_after_clip" SHAC logs (shac.py:846-856). */
 size_t mnr_fused_adam_workspace_bytes(void);
 int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
                         float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
-                        mnr_optim_state_t* st, const float* kl, float* grad_norm_out, void* workspace,
-                        size_t workspace_bytes, mnr_stream_t stream);
+                        mnr_optim_state_t* st, const float* kl, float* grad_norm_out, int nan_to_num,
+                        float* clipped_norm_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * a16  SHAC / SAPO critic regression loss (SHAC.compute_critic_loss, mineral/agents/diffrl/shac.py:869-875):
+ *      loss = mean_k mean_rows (pred_k - target)^2 and its gradient g_k = 2 (pred_k - target) / (rows * n_critics).
+ *      preds / grads: up to MNR_MAX_CRITICS device pointers (rows) each.  loss_out: 1 float.  Deterministic.
+ * ------------------------------------------------------------------------------------ */
+#define MNR_MAX_CRITICS 4
+typedef struct {
+  const float* pred[MNR_MAX_CRITICS];
+  float* grad[MNR_MAX_CRITICS];
+} mnr_critic_set_t;
+size_t mnr_critic_mse_workspace_bytes(int64_t rows);
+int mnr_critic_mse_fwd_bwd(const mnr_critic_set_t* set /*host*/, int n_critics, const float* target, int64_t rows,
+                           float* loss_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * a23  multi-GPU exchange over NVLink / NVSwitch PEER MEMORY (one process per GPU).  Replaces the

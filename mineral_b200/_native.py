@@ -82,6 +82,10 @@ class LnGroup(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("z", "y", "gamma", "beta", "mean", "rstd", "dy", "dz", "dgamma", "dbeta")]
 
 
+class CriticSet(C.Structure):
+    _fields_ = [("pred", C.c_void_p * 4), ("grad", C.c_void_p * 4)]
+
+
 class PeerCommStruct(C.Structure):
     _fields_ = [("base", C.c_void_p * 8), ("rank", C.c_int32), ("world", C.c_int32)]
 
@@ -146,7 +150,9 @@ SIGNATURES = {
     "mnr_ln_act_bwd_workspace_bytes": (sz, [i32, i64, i32]),
     "mnr_ln_act_bwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, i32, vp, sz, vp]),
     "mnr_fused_adam_workspace_bytes": (sz, []),
-    "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, vp, sz, vp]),
+    "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),
+    "mnr_critic_mse_workspace_bytes": (sz, [i64]),
+    "mnr_critic_mse_fwd_bwd": (i32, [C.POINTER(CriticSet), i32, vp, i64, vp, vp, sz, vp]),
     "mnr_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),
     "mnr_peer_open": (i32, [vp, C.POINTER(vp)]),
     "mnr_peer_close": (i32, [vp]),

@@ -83,7 +83,8 @@ class FusedAdam:
         self.fused_ws = torch.zeros(ops.lib.mnr_fused_adam_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.param_groups = [dict(lr=float(lr), betas=betas, eps=eps, weight_decay=self.weight_decay)]
 
-    def step(self, max_grad_norm, kl=None, grad_norm_out=None, metrics_out=None, kl_index=-1, fused=True):
+    def step(self, max_grad_norm, kl=None, grad_norm_out=None, metrics_out=None, kl_index=-1, fused=True, nan_to_num=False,
+             clipped_norm_out=None):
         """clip_grad_norm_ + optimizer.step + zero_grad with no host sync: ONE launch (csrc/peer.cu), which with a peer
         communicator also all-reduces the gradient and the metrics tail over NVLink (`metrics_out` receives the sums,
         the metric at `kl_index` feeds the KL accumulator).  fused=False: the two-launch form (csrc/optim.cu)."""
@@ -93,7 +94,8 @@ class FusedAdam:
                                        metrics_out, kl_index, grad_norm_out, self.fused_ws)
         elif fused:
             ops.fused_clip_adam(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, max_grad_norm, self.betas[0], self.betas[1],
-                                self.eps, self.weight_decay, self.decoupled, True, self.state, kl, grad_norm_out, self.fused_ws)
+                                self.eps, self.weight_decay, self.decoupled, True, self.state, kl, grad_norm_out, self.fused_ws,
+                                nan_to_num=nan_to_num, clipped_norm_out=clipped_norm_out)
         else:
             ops.grad_norm_prepare(self.flat_grad, max_grad_norm, self.betas[0], self.betas[1], self.state, kl, grad_norm_out, self.ws)
             ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps,

@@ -107,8 +107,10 @@ struct AdamArgs {
   const float* kl; // world == 1 alternative: pointer to the step's KL (may be NULL)
   float max_norm, beta1, beta2, eps, wd;
   int decoupled, zero_grad;
+  int nan_to_num;          // world == 1: grad.nan_to_num_(0, 0, 0) before the norm (mineral/agents/diffrl/shac.py:841-843)
   mnr_optim_state_t* st;
   float* norm_out;
+  float* clipped_norm_out; // norm * clip coefficient (the "after clip" norm SHAC logs), may be NULL
   double* parts;                // gridDim.x doubles
   unsigned long long* counter;  // grid barrier
 };
@@ -124,6 +126,11 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, flo
   v = v * beta2 + (1.0f - beta2) * g * g;
   const float denom = sqrtf(v) / bc2_sqrt + eps;
   p -= step_size * (m / denom);
+}
+
+__device__ __forceinline__ float4 finite4(float4 v) {
+  v.x = isfinite(v.x) ? v.x : 0.f, v.y = isfinite(v.y) ? v.y : 0.f, v.z = isfinite(v.z) ? v.z : 0.f, v.w = isfinite(v.w) ? v.w : 0.f;
+  return v;
 }
 
 template <int WORLD>  // 0 = runtime world (any), 1 = single GPU (no peers)
@@ -154,7 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   if (WORLD == 1) {
     const float4* g4 = reinterpret_cast<const float4*>(a.grad);
     for (int64_t i = first; i < n4; i += stride) {
-      const float4 s = g4[i];
+      float4 s = g4[i];
+      if (a.nan_to_num) s = finite4(s);
       acc += s.x * s.x + s.y * s.y + s.z * s.z + s.w * s.w;
     }
   } else {
@@ -211,6 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
           st->kl_sum += (double)s_tail[a.kl_index], st->kl_count += 1;
         }
         if (a.norm_out) *a.norm_out = norm;
+        if (a.clipped_norm_out) *a.clipped_norm_out = norm * coef;
       }
     }
   }
@@ -224,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   const float4* gsrc = WORLD == 1 ? reinterpret_cast<const float4*>(a.grad) : red4;
   for (int64_t i = first; i < n4; i += stride) {
     float4 P = p4[i], G = gsrc[i], M = m4[i], V = v4[i];
+    if (WORLD == 1 && a.nan_to_num) G = finite4(G);
     adam1(P.x, G.x, M.x, V.x, clip, a.beta1, a.beta2, a.eps, a.wd, a.decoupled, lr32, step_size, bc2s);
     adam1(P.y, G.y, M.y, V.y, clip, a.beta1, a.beta2, a.eps, a.wd, a.decoupled, lr32, step_size, bc2s);
     adam1(P.z, G.z, M.z, V.z, clip, a.beta1, a.beta2, a.eps, a.wd, a.decoupled, lr32, step_size, bc2s);
@@ -370,7 +380,7 @@ int fill_adam(AdamArgs& a, float* param, float* exp_avg, float* exp_avg_sq, int6
     return MNR_EALIGN;
   a.param = param, a.m = exp_avg, a.v = exp_avg_sq, a.n = n;
   a.max_norm = max_norm, a.beta1 = beta1, a.beta2 = beta2, a.eps = eps, a.wd = wd, a.decoupled = decoupled, a.zero_grad = zero_grad;
-  a.st = st, a.norm_out = norm_out;
+  a.st = st, a.norm_out = norm_out, a.nan_to_num = 0, a.clipped_norm_out = nullptr;
   a.counter = reinterpret_cast<unsigned long long*>(workspace);
   a.parts = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + kWsHeader);
   a.reduced = nullptr, a.grad = nullptr, a.grad_offset = 0, a.n_tail = 0, a.tail_out = nullptr, a.kl_index = -1, a.kl = nullptr;
@@ -380,15 +390,15 @@ int fill_adam(AdamArgs& a, float* param, float* exp_avg, float* exp_avg_sq, int6
 
 extern "C" int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
                                    float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
-                                   mnr_optim_state_t* st, const float* kl, float* grad_norm_out, void* workspace,
-                                   size_t workspace_bytes, mnr_stream_t stream) {
+                                   mnr_optim_state_t* st, const float* kl, float* grad_norm_out, int nan_to_num,
+                                   float* clipped_norm_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
   AdamArgs a;
   const int rc = fill_adam(a, param, exp_avg, exp_avg_sq, n, max_norm, beta1, beta2, eps, weight_decay, decoupled, zero_grad, st,
                            grad_norm_out, workspace, workspace_bytes);
   if (rc != MNR_OK) return rc;
   MNR_CHECK_PTR(grad);
   if (!mnr_aligned(grad, 16)) return MNR_EALIGN;
-  a.grad = grad, a.kl = kl;
+  a.grad = grad, a.kl = kl, a.nan_to_num = nan_to_num, a.clipped_norm_out = clipped_norm_out;
   Comm c;
   for (int r = 0; r < kMaxPeers; ++r) c.base[r] = nullptr;
   c.rank = 0, c.world = 1;

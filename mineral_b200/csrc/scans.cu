@@ -99,3 +99,53 @@ extern "C" int mnr_critic_targets_f32(const float* rew, const float* done_mask, 
                                                                    ent_flags, abs_target_entropy, inv_abs_target_entropy);
   MNR_LAUNCH_RESULT();
 }
+
+// ---- a16  SHAC / SAPO critic regression loss + gradient (mineral/agents/diffrl/shac.py:869-875) ----------------
+namespace {
+constexpr int kMseThreads = 256;
+__global__ void __launch_bounds__(kMseThreads) critic_mse_kernel(const mnr_critic_set_t set, int n_critics, const float* __restrict__ target,
+                                                                 int64_t rows, float* __restrict__ loss_out, unsigned char* __restrict__ workspace) {
+  const float gscale = 2.0f / ((float)rows * (float)n_critics);
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kMseThreads + threadIdx.x; i < rows; i += (int64_t)gridDim.x * kMseThreads) {
+    const float t = __ldg(target + i);
+    float s = 0.f;
+    for (int k = 0; k < n_critics; ++k) {
+      const float d = __ldg(set.pred[k] + i) - t;
+      set.grad[k][i] = gscale * d;
+      s = fmaf(d, d, s);
+    }
+    acc += (double)s;
+  }
+  double* parts = reinterpret_cast<double*>(workspace + 256);
+  const double tot = mnr::block_sum(acc);
+  if (threadIdx.x == 0) parts[blockIdx.x] = tot;
+  if (!mnr::last_block_ticket(reinterpret_cast<unsigned int*>(workspace), gridDim.x)) return;
+  double mine = 0.0;
+  for (unsigned int x = threadIdx.x; x < gridDim.x; x += kMseThreads) mine += parts[x];
+  const double all = mnr::block_sum(mine);
+  if (threadIdx.x == 0) *loss_out = (float)(all / ((double)rows * (double)n_critics));
+}
+int mse_grid(int64_t rows) {
+  int64_t g = (rows + kMseThreads - 1) / kMseThreads;
+  const int64_t cap = (int64_t)mnr_sm_count() * 4;
+  return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+}  // namespace
+
+extern "C" size_t mnr_critic_mse_workspace_bytes(int64_t rows) {
+  (void)rows;
+  return 256 + (size_t)mnr_sm_count() * 4 * sizeof(double);
+}
+
+extern "C" int mnr_critic_mse_fwd_bwd(const mnr_critic_set_t* set, int n_critics, const float* target, int64_t rows, float* loss_out,
+                                      void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
+  MNR_CHECK_PTR(set); MNR_CHECK_PTR(target); MNR_CHECK_PTR(loss_out); MNR_CHECK_PTR(workspace);
+  if (n_critics <= 0 || n_critics > MNR_MAX_CRITICS || rows <= 0) return MNR_ESHAPE;
+  if (workspace_bytes < mnr_critic_mse_workspace_bytes(rows)) return MNR_EWORKSPACE;
+  if (!mnr_aligned(workspace, 8)) return MNR_EALIGN;
+  for (int k = 0; k < n_critics; ++k)
+    if (!set->pred[k] || !set->grad[k]) return MNR_ENULL;
+  critic_mse_kernel<<<mse_grid(rows), kMseThreads, 0, mnr_cs(stream)>>>(*set, n_critics, target, rows, loss_out, (unsigned char*)workspace);
+  MNR_LAUNCH_RESULT();
+}

@@ -24,8 +24,10 @@ from .. import ops
 _ACT = {nn.ELU: 1, nn.ReLU: 2, nn.SiLU: 3}
 
 
-def _tower_layers(mlp):
-    """-> (list of (nn.Linear, nn.LayerNorm | None), act code) or None if the tower has an unsupported layer."""
+def _tower_layers(mlp, plain_last=False):
+    """-> (list of (nn.Linear, nn.LayerNorm | None), act code) or None if the tower has an unsupported layer.
+    plain_last: the final Linear carries neither norm nor activation (MLP(..., plain_last=True), mlp.py:55-56); it is
+    returned as the last entry and excluded from the uniformity checks."""
     blocks, act = [], None
     for m in mlp.mlp:
         if isinstance(m, nn.Linear):
@@ -49,6 +51,11 @@ def _tower_layers(mlp):
             return None
     if not blocks:
         return None
+    last = None
+    if plain_last:
+        last = blocks.pop()
+        if last[1] is not None or last[2] or last[0].bias is None or not blocks:
+            return None
     normed = [b[1] is not None for b in blocks]
     acted = [b[2] for b in blocks]
     if any(normed) != all(normed) or (act is not None and not all(acted)):
@@ -57,59 +64,42 @@ def _tower_layers(mlp):
         return None
     if any(b[0].bias is None for b in blocks):
         return None
-    return [(b[0], b[1]) for b in blocks], (act or 0)
+    out = [(b[0], b[1]) for b in blocks]
+    if last is not None:
+        out.append((last[0], None))
+    return out, (act or 0)
 
 
-class FusedTowers:
-    @staticmethod
-    def supported(model):
-        if not getattr(model, 'separate_value_mlp', False):
-            return False
-        a, v = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
-        if a is None or v is None or a[1] != v[1] or len(a[0]) != len(v[0]):
-            return False
-        for (la, na), (lv, nv_) in zip(a[0], v[0]):
-            if la.weight.shape != lv.weight.shape or (na is None) != (nv_ is None):
-                return False
-            if na is not None and (na.eps != nv_.eps or la.weight.shape[0] > 512):
-                return False
-        return True
+class TowerStack:
+    """G (1 or 2) towers of identical shape run side by side: every launch serves all of them.
+    towers[g] = list of (nn.Linear, nn.LayerNorm | None); all towers read the same input."""
 
-    def __init__(self, model, rows, device, use_tc=True):
-        self.model, self.M = model, rows
-        (ba, self.act), (bv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
-        self.la, self.lv = [b[0] for b in ba], [b[0] for b in bv]
-        self.na, self.nv = [b[1] for b in ba], [b[1] for b in bv]
-        self.normed = self.na[0] is not None
+    def __init__(self, towers, act, rows, device, use_tc=True):
+        self.G, self.M, self.act = len(towers), rows, act
+        assert 1 <= self.G <= 2
+        self.lin = [[b[0] for b in t] for t in towers]    # [g][i]
+        self.norm = [[b[1] for b in t] for t in towers]
+        self.normed = self.norm[0][0] is not None
         # activation applied by the GEMM kernels themselves (epilogue / operand load); behind a LayerNorm it is 0
-        self.gemm_act = 0 if self.normed else self.act
-        self.L = len(self.la)
-        self.A = model.mu.weight.shape[0]
-        self.fixed_sigma = model.fixed_sigma
+        self.gemm_act = 0 if self.normed else act
+        self.L = len(self.lin[0])
         f32 = dict(dtype=torch.float32, device=device)
-        widths = [l.weight.shape[0] for l in self.la]
-        self.widths, self.in_dim = widths, self.la[0].weight.shape[1]
-        # saved forward outputs and their gradients, per layer, per tower (0 actor, 1 value)
-        self.Y = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
-        self.dY = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
+        widths = [l.weight.shape[0] for l in self.lin[0]]
+        self.widths, self.in_dim = widths, self.lin[0][0].weight.shape[1]
+        G = self.G
+        # saved forward outputs and their gradients, per layer, per tower
+        self.Y = [[torch.empty(rows, w, **f32) for _ in range(G)] for w in widths]
+        self.dY = [[torch.empty(rows, w, **f32) for _ in range(G)] for w in widths]
         if self.normed:  # pre-normalisation GEMM outputs and the row statistics
-            self.Z = [[torch.empty(rows, w, **f32) for _ in range(2)] for w in widths]
-            self.mean = [[torch.empty(rows, **f32) for _ in range(2)] for _ in widths]
-            self.rstd = [[torch.empty(rows, **f32) for _ in range(2)] for _ in widths]
-            self.ln_ws = [ops.ln_act_bwd_workspace(2, rows, w, device) for w in widths]
-        self.mu_raw = torch.empty(rows, self.A, **f32)
-        self.value = torch.empty(rows, 1, **f32)
-        self.ls = None if self.fixed_sigma else torch.empty(rows, self.A, **f32)
-        big = 0
-        for l in self.la + [model.mu]:
-            n, k = l.weight.shape
-            big = max(big, ops.lib.mnr_linear_bwd_weight_workspace_bytes(2, rows, n, k))
+            self.Z = [[torch.empty(rows, w, **f32) for _ in range(G)] for w in widths]
+            self.mean = [[torch.empty(rows, **f32) for _ in range(G)] for _ in widths]
+            self.rstd = [[torch.empty(rows, **f32) for _ in range(G)] for _ in widths]
+            self.ln_ws = [ops.ln_act_bwd_workspace(G, rows, w, device) for w in widths]
+        big = max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape) for l in self.lin[0])
         self.ws = torch.zeros(max(big, 256), dtype=torch.uint8, device=device)
-        self.colsum_ws = torch.zeros(ops.lib.mnr_colsum_workspace_bytes(self.A), dtype=torch.uint8, device=device)
-
-        # tensor-core path (tcgen05 3xTF32, csrc/tc_linear.cu) for the tower layers: needs widths % 16 == 0 and
-        # 16 B-multiple row strides, so W is kept pre-split (hi / lo) in K-padded buffers and the first layer's
-        # input is read through a padded row stride `in_ld`.
+        # tensor-core path (tcgen05 3xTF32, csrc/tc_linear.cu): needs widths % 16 == 0 (and whole 128-column tiles above
+        # 128) and 16 B-multiple row strides, so W is kept pre-split (hi / lo) in K-padded buffers and the first layer's
+        # input is read through a padded row stride.
         self.in_ld = (self.in_dim + 3) // 4 * 4
         self.use_tc = bool(use_tc) and ops.tc_supported() and all(w % 16 == 0 and (w <= 128 or w % 128 == 0) for w in widths)
         if self.use_tc:
@@ -118,23 +108,121 @@ class FusedTowers:
             for w in widths:
                 ld = (k + 3) // 4 * 4
                 self.w_ld.append(ld)
-                self.w_hi.append([torch.zeros(w, ld, **f32) for _ in range(2)])
-                self.w_lo.append([torch.zeros(w, ld, **f32) for _ in range(2)])
+                self.w_hi.append([torch.zeros(w, ld, **f32) for _ in range(G)])
+                self.w_lo.append([torch.zeros(w, ld, **f32) for _ in range(G)])
                 k = w
-            tc_big = max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(2, rows, l.weight.shape[0], l.weight.shape[1]) for l in self.la)
+            tc_big = max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape) for l in self.lin[0])
             self.tc_ws = torch.zeros(max(tc_big, 256), dtype=torch.uint8, device=device)
 
-    # ------------------------------------------------------------------------------------------------
     def _split_weights(self):
-        """W -> (hi, lo) tf32 parts for every tower layer, one launch per 8 matrices."""
+        """W -> (hi, lo) tf32 parts for every layer of every tower, one launch per 8 matrices."""
         jobs = []
         for i in range(self.L):
-            n, k = self.la[i].weight.shape
-            for t, l in enumerate((self.la[i], self.lv[i])):
-                jobs.append((l.weight.data, self.w_hi[i][t], self.w_lo[i][t], n, k, k, self.w_ld[i]))
+            n, k = self.lin[0][i].weight.shape
+            for g in range(self.G):
+                jobs.append((self.lin[g][i].weight.data, self.w_hi[i][g], self.w_lo[i][g], n, k, k, self.w_ld[i]))
         for s in range(0, len(jobs), 8):
             ops.split_tf32(jobs[s:s + 8])
 
+    def forward(self, x, x_ld=None, rows=None):
+        """x (rows, in_dim) [row stride x_ld floats] -> self.Y[-1][g] for every tower g."""
+        M = self.M if rows is None else rows
+        G = self.G
+        x_ld = self.in_dim if x_ld is None else x_ld
+        self._x_ld = x_ld
+        tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
+        if self.use_tc:
+            self._split_weights()
+        inp = [x] * G
+        for i in range(self.L):
+            n, k = self.lin[0][i].weight.shape
+            lda = x_ld if i == 0 else k
+            out = self.Z[i] if self.normed else self.Y[i]
+            if self.use_tc and (i > 0 or tc0):
+                ops.tc_linear_fwd([dict(a=inp[g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=out[g], bias=self.lin[g][i].bias.data, N=n, K=k,
+                                        lda=lda, ldb=self.w_ld[i]) for g in range(G)], M, self.gemm_act)
+            else:
+                ops.linear_fwd([dict(a=inp[g], b=self.lin[g][i].weight.data, c=out[g], bias=self.lin[g][i].bias.data, N=n, K=k, lda=lda)
+                                for g in range(G)], M, self.gemm_act)
+            if self.normed:
+                ops.ln_act_fwd([dict(z=self.Z[i][g], y=self.Y[i][g], gamma=self.norm[g][i].weight.data, beta=self.norm[g][i].bias.data,
+                                     mean=self.mean[i][g], rstd=self.rstd[i][g]) for g in range(G)], M, n, self.norm[0][i].eps, self.act)
+            inp = self.Y[i]
+
+    def backward(self, x, rows=None):
+        """Layers top first, from self.dY[-1]; writes every .grad.  Without a norm, act'(.) is applied on the fly from the
+        saved outputs inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta)."""
+        M = self.M if rows is None else rows
+        G, top = self.G, self.L - 1
+        x_ld = getattr(self, '_x_ld', self.in_dim)
+        for i in range(top, -1, -1):
+            n, k = self.lin[0][i].weight.shape
+            src = self.Y[i - 1] if i > 0 else [x] * G
+            ldb = x_ld if i == 0 else k
+            tc = self.use_tc and ldb % 4 == 0
+            if self.normed:
+                ops.ln_act_bwd([dict(z=self.Z[i][g], gamma=self.norm[g][i].weight.data, beta=self.norm[g][i].bias.data, mean=self.mean[i][g],
+                                     rstd=self.rstd[i][g], dy=self.dY[i][g], dz=self.dY[i][g], dgamma=self.norm[g][i].weight.grad,
+                                     dbeta=self.norm[g][i].bias.grad) for g in range(G)], M, n, self.act, self.ln_ws[i])
+            saved = [None] * G if self.normed else self.Y[i]
+            wg = [dict(a=self.dY[i][g], b=src[g], c=self.lin[g][i].weight.grad, saved=saved[g], bias_grad=self.lin[g][i].bias.grad, N=n, K=k,
+                       ldb=ldb) for g in range(G)]
+            if tc:
+                ops.tc_linear_bwd_weight(wg, M, self.gemm_act, self.tc_ws)
+            else:
+                ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
+            if i > 0:
+                if self.use_tc:
+                    ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],
+                                                  saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, self.gemm_act)
+                else:
+                    ops.linear_bwd_input([dict(a=self.dY[i][g], b=self.lin[g][i].weight.data, c=self.dY[i - 1][g], saved=saved[g], N=n, K=k)
+                                          for g in range(G)], M, self.gemm_act)
+
+
+def _same_shape(a, v):
+    if a is None or v is None or a[1] != v[1] or len(a[0]) != len(v[0]):
+        return False
+    for (la, na), (lv, nv_) in zip(a[0], v[0]):
+        if la.weight.shape != lv.weight.shape or (na is None) != (nv_ is None):
+            return False
+        if na is not None and (na.eps != nv_.eps or la.weight.shape[0] > 512):
+            return False
+    return True
+
+
+class FusedTowers:
+    """PPO actor + value towers (TowerStack with G = 2) plus the policy / value heads."""
+
+    @staticmethod
+    def supported(model):
+        if not getattr(model, 'separate_value_mlp', False):
+            return False
+        return _same_shape(_tower_layers(model.actor_mlp), _tower_layers(model.value_mlp))
+
+    def __init__(self, model, rows, device, use_tc=True):
+        self.model, self.M = model, rows
+        (ba, self.act), (bv, _) = _tower_layers(model.actor_mlp), _tower_layers(model.value_mlp)
+        self.stack = st = TowerStack([ba, bv], self.act, rows, device, use_tc)
+        # aliases (bench.py and the PPO engine read these)
+        self.la, self.lv = st.lin
+        self.normed, self.gemm_act, self.L, self.widths, self.in_dim = st.normed, st.gemm_act, st.L, st.widths, st.in_dim
+        self.Y, self.dY, self.use_tc, self.in_ld = st.Y, st.dY, st.use_tc, st.in_ld
+        if st.normed:
+            self.Z = st.Z
+        if st.use_tc:
+            self.w_hi, self.w_lo, self.w_ld = st.w_hi, st.w_lo, st.w_ld
+        self.A = model.mu.weight.shape[0]
+        self.fixed_sigma = model.fixed_sigma
+        f32 = dict(dtype=torch.float32, device=device)
+        self.mu_raw = torch.empty(rows, self.A, **f32)
+        self.value = torch.empty(rows, 1, **f32)
+        self.ls = None if self.fixed_sigma else torch.empty(rows, self.A, **f32)
+        n, k = model.mu.weight.shape
+        self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(2, rows, n, k), 256), dtype=torch.uint8, device=device)
+        self.colsum_ws = torch.zeros(ops.lib.mnr_colsum_workspace_bytes(self.A), dtype=torch.uint8, device=device)
+
+    # ------------------------------------------------------------------------------------------------
     def forward(self, x, x_ld=None):
         """x (rows, in_dim) [row stride x_ld floats] -> (mu_raw (rows,A), logstd ((A,) parameter if fixed sigma
         else (rows,A)), value (rows,1))."""
@@ -143,27 +231,10 @@ class FusedTowers:
 
     def forward_towers(self, x, x_ld=None):
         """Both towers up to their last activation (self.Y[-1])."""
-        M = self.M
-        x_ld = self.in_dim if x_ld is None else x_ld
-        self._x_ld = x_ld
-        tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
-        if self.use_tc:
-            self._split_weights()
-        inp = [x, x]
-        for i in range(self.L):
-            n, k = self.la[i].weight.shape
-            lda = x_ld if i == 0 else k
-            out = self.Z[i] if self.normed else self.Y[i]
-            if self.use_tc and (i > 0 or tc0):
-                ops.tc_linear_fwd([dict(a=inp[t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=out[t], bias=l.bias.data, N=n, K=k,
-                                        lda=lda, ldb=self.w_ld[i]) for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)
-            else:
-                ops.linear_fwd([dict(a=inp[t], b=l.weight.data, c=out[t], bias=l.bias.data, N=n, K=k, lda=lda)
-                                for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)
-            if self.normed:
-                ops.ln_act_fwd([dict(z=self.Z[i][t], y=self.Y[i][t], gamma=nm.weight.data, beta=nm.bias.data, mean=self.mean[i][t],
-                                     rstd=self.rstd[i][t]) for t, nm in enumerate((self.na[i], self.nv[i]))], M, n, self.na[i].eps, self.act)
-            inp = self.Y[i]
+        self.stack.forward(x, x_ld)
+
+    def backward_towers(self, x):
+        self.stack.backward(x)
 
     def heads_forward(self):
         M, m = self.M, self.model
@@ -217,31 +288,46 @@ class FusedTowers:
         if not self.fixed_sigma:
             ops.linear_bwd_input([dict(a=g_ls, b=m.sigma.weight.data, c=self.dY[top][0], N=self.A, K=h)], M, 0, accumulate=True)
 
-    def backward_towers(self, x):
-        """Tower layers, top first, from self.dY[-1].  Without a norm, act'(.) is applied on the fly from the saved outputs
-        inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta) first."""
-        M, top = self.M, self.L - 1
-        x_ld = getattr(self, '_x_ld', self.in_dim)
-        for i in range(top, -1, -1):
-            n, k = self.la[i].weight.shape
-            src = self.Y[i - 1] if i > 0 else [x, x]
-            ldb = x_ld if i == 0 else k
-            tc = self.use_tc and ldb % 4 == 0
-            if self.normed:
-                ops.ln_act_bwd([dict(z=self.Z[i][t], gamma=nm.weight.data, beta=nm.bias.data, mean=self.mean[i][t], rstd=self.rstd[i][t],
-                                     dy=self.dY[i][t], dz=self.dY[i][t], dgamma=nm.weight.grad, dbeta=nm.bias.grad)
-                                for t, nm in enumerate((self.na[i], self.nv[i]))], M, n, self.act, self.ln_ws[i])
-            saved = [None, None] if self.normed else self.Y[i]
-            wg = [dict(a=self.dY[i][t], b=src[t], c=l.weight.grad, saved=saved[t], bias_grad=l.bias.grad, N=n, K=k, ldb=ldb)
-                  for t, l in enumerate((self.la[i], self.lv[i]))]
-            if tc:
-                ops.tc_linear_bwd_weight(wg, M, self.gemm_act, self.tc_ws)
-            else:
-                ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
-            if i > 0:
-                if self.use_tc:
-                    ops.tc_linear_bwd_input([dict(a=self.dY[i][t], b=self.w_hi[i][t], b_lo=self.w_lo[i][t], c=self.dY[i - 1][t],
-                                                  saved=saved[t], N=n, K=k, ldb=self.w_ld[i]) for t in range(2)], M, self.gemm_act)
-                else:
-                    ops.linear_bwd_input([dict(a=self.dY[i][t], b=l.weight.data, c=self.dY[i - 1][t], saved=saved[t], N=n, K=k)
-                                          for t, l in enumerate((self.la[i], self.lv[i]))], M, self.gemm_act)
+
+class FusedCritics:
+    """1 or 2 state-value MLPs with a plain last Linear (SHAC `Critic`, SAPO `EnsembleCritic`,
+    mineral/agents/diffrl/models.py:149-256) trained on the MSE of SHAC.compute_critic_loss (shac.py:869-875):
+    hidden layers through a TowerStack, the 1-wide output layer and its backward on the SIMT linear kernels, loss and
+    its gradient in one small kernel."""
+
+    @staticmethod
+    def parse(mlps):
+        parsed = [_tower_layers(m, plain_last=True) for m in mlps]
+        if not 1 <= len(parsed) <= 2 or any(p is None for p in parsed):
+            return None
+        if any(not _same_shape(parsed[0], p) for p in parsed[1:]):
+            return None
+        if parsed[0][0][-1][0].weight.shape[0] != 1:
+            return None
+        return parsed
+
+    def __init__(self, mlps, rows, device, use_tc=True):
+        parsed = self.parse(mlps)
+        assert parsed is not None, 'unsupported critic architecture'
+        self.G, self.M = len(mlps), rows
+        self.stack = TowerStack([p[0][:-1] for p in parsed], parsed[0][1], rows, device, use_tc)
+        self.last = [p[0][-1][0] for p in parsed]
+        f32 = dict(dtype=torch.float32, device=device)
+        self.pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
+        self.g_pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
+        h = self.stack.widths[-1]
+        self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(self.G, rows, 1, h), 256), dtype=torch.uint8, device=device)
+        self.mse_ws = torch.zeros(ops.lib.mnr_critic_mse_workspace_bytes(rows), dtype=torch.uint8, device=device)
+
+    def loss_fwd_bwd(self, x, target, loss_out, x_ld=None):
+        """x (rows, in_dim), target (rows) -> loss_out (1 float), every critic parameter's .grad."""
+        rows, G, st = target.numel(), self.G, self.stack
+        h = st.widths[-1]
+        st.forward(x, x_ld, rows)
+        ops.linear_fwd([dict(a=st.Y[-1][g], b=self.last[g].weight.data, c=self.pred[g], bias=self.last[g].bias.data, N=1, K=h)
+                        for g in range(G)], rows, 0)
+        ops.critic_mse_fwd_bwd([p.view(-1)[:rows] for p in self.pred], target, [g_.view(-1)[:rows] for g_ in self.g_pred], loss_out, self.mse_ws)
+        ops.linear_bwd_weight([dict(a=self.g_pred[g], b=st.Y[-1][g], c=self.last[g].weight.grad, bias_grad=self.last[g].bias.grad, N=1, K=h)
+                               for g in range(G)], rows, 0, self.ws)
+        ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=1, K=h) for g in range(G)], rows, 0)
+        st.backward(x, rows)

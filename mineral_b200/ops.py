@@ -370,12 +370,21 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, beta1, beta2, eps, weight_decay,
 
 
 def fused_clip_adam(param, grad, exp_avg, exp_avg_sq, max_norm, beta1, beta2, eps, weight_decay, decoupled, zero_grad, st, kl,
-                    norm_out, ws):
-    """clip_grad_norm_ + Adam(W).step + zero_grad in ONE launch (csrc/peer.cu, world == 1 instance)."""
+                    norm_out, ws, nan_to_num=False, clipped_norm_out=None):
+    """[grad.nan_to_num_ +] clip_grad_norm_ + Adam(W).step + zero_grad in ONE launch (csrc/peer.cu, world == 1 instance)."""
     check(lib.mnr_fused_clip_adam(ptr(param, F32), ptr(grad, F32), ptr(exp_avg, F32), ptr(exp_avg_sq, F32), param.numel(), max_norm,
                                   beta1, beta2, eps, weight_decay, 1 if decoupled else 0, 1 if zero_grad else 0, ptr(st, U8),
-                                  ptr(kl, F32, allow_none=True), ptr(norm_out, F32, allow_none=True), ptr(ws, U8), ws.numel(),
-                                  stream()), "mnr_fused_clip_adam")
+                                  ptr(kl, F32, allow_none=True), ptr(norm_out, F32, allow_none=True), 1 if nan_to_num else 0,
+                                  ptr(clipped_norm_out, F32, allow_none=True), ptr(ws, U8), ws.numel(), stream()), "mnr_fused_clip_adam")
+
+
+def critic_mse_fwd_bwd(preds, target, grads, loss_out, ws):
+    """SHAC.compute_critic_loss (shac.py:869-875) + its gradient w.r.t. every critic's prediction, one launch."""
+    cs = nv.CriticSet()
+    for k, (p_, g_) in enumerate(zip(preds, grads)):
+        cs.pred[k], cs.grad[k] = ptr(p_, F32, "pred").value, ptr(g_, F32, "grad").value
+    check(lib.mnr_critic_mse_fwd_bwd(C.byref(cs), len(preds), ptr(target, F32, "target"), target.numel(), ptr(loss_out, F32),
+                                     ptr(ws, U8), ws.numel(), stream()), "mnr_critic_mse_fwd_bwd")
 
 
 def kl_lr_update(st, kl_threshold, min_lr, max_lr, avg_kl_out=None, lr_out=None):

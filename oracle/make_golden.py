@@ -157,6 +157,37 @@ def gen_critic_dataset():
     save("critic_dataset", cases)
 
 
+# ---- a16: SHAC.update_critic on the reference's Critic / EnsembleCritic (Humanoid shape, cfg3) ----------------
+def gen_shac_critic():
+    from mineral.agents.diffrl import models as ref_models
+
+    cases = []
+    T, B, O = 32, 64, 76  # BASELINE.json configs[2]
+    for seed, n_critics, iters, n_batches in [(0, 1, 16, 4), (1, 2, 4, 4), (2, 1, 3, 3)]:
+        torch.manual_seed(seed)
+        mlp_kwargs = dict(units=[64, 64], norm_type="LayerNorm", act_type="ELU")
+        if n_critics == 1:
+            critic = ref_models.Critic(O, 21, mlp_kwargs=mlp_kwargs)
+        else:
+            critic = ref_models.EnsembleCritic(O, 21, n_critics=n_critics, mlp_kwargs=mlp_kwargs)
+        from oracle.mineral_oracle import shac_critic_inputs
+        o_, tv = shac_critic_inputs(seed, T, B, O, wild=(seed == 2))
+        obs = {"obs": o_}
+        bs = T * B // n_batches if seed != 2 else 700  # seed 2: ragged last batch (2048 = 700 + 700 + 648)
+        init = clone_tree(critic.state_dict())
+        optim = torch.optim.Adam(critic.parameters(), lr=2e-3, betas=(0.7, 0.95))  # DFlexAntSHAC.yaml:46-47
+        cfg = rs.to_attr(dict(truncate_grads=True, max_grad_norm=1.0))
+        ns = types.SimpleNamespace(critic_iterations=iters, critic=critic, critic_optim=optim, shac_config=cfg, encoder=lambda o: o["obs"])
+        ns.compute_critic_loss = lambda o, t: SHAC.compute_critic_loss(ns, o, t)
+        ds = CriticDataset(bs, obs, tv, shuffle=False, drop_last=False)
+        res = SHAC.update_critic(ns, ds)
+        cases.append(dict(n_critics=n_critics, iterations=iters, batch_size=bs, shape=(T, B, O), seed=seed, wild=(seed == 2),
+                          init_state_dict=init, final_state_dict=clone_tree(critic.state_dict()),
+                          results={k: torch.stack([x.detach() for x in v]) for k, v in res.items()}, lr=2e-3, betas=(0.7, 0.95),
+                          max_grad_norm=1.0))
+    save("shac_critic", cases)
+
+
 # ---- K3c/K3d: ReplayBuffer --------------------------------------------------------------------------
 def gen_replay():
     g = torch.Generator().manual_seed(7)
@@ -304,6 +335,7 @@ if __name__ == "__main__":
     gen_rms()
     gen_tdlambda()
     gen_critic_dataset()
+    gen_shac_critic()
     gen_replay()
     gen_nstep()
     gen_losses()

@@ -184,6 +184,66 @@ def critic_dataset_slices(n_rows, batch_size, drop_last=False):
 
 
 # --------------------------------------------------------------------------
+# a16  SHAC / SAPO critic regression   mineral/agents/diffrl/shac.py:824-875,
+#      Critic / EnsembleCritic mineral/agents/diffrl/models.py:149-256,
+#      grad_norm mineral/agents/diffrl/utils.py:31-36
+# --------------------------------------------------------------------------
+
+
+def shac_critic_inputs(seed, T, B, O, wild=False):
+    """Seeded (obs (T,B,O), target_values (T,B)) of the critic-regression goldens (oracle/make_golden.py:gen_shac_critic);
+    regenerated from the seed in the tests so the fixture stays small."""
+    g = torch.Generator().manual_seed(100 + seed)
+    obs = torch.randn(T, B, O, generator=g)
+    tv = 3 * torch.randn(T, B, generator=g)
+    if wild:
+        tv[3, 5] = 1e4  # one wild target: exercises the clip
+    return obs, tv
+
+
+def critic_forward(params, prefix, x, n_hidden, norm, act):
+    """MLP(state_dim, out_dim=1, plain_last=True): n_hidden x (Linear -> [LayerNorm] -> act), then a plain Linear."""
+    h = mlp_tower(params, prefix, x, n_hidden, norm, act)
+    j = n_hidden * (1 + (1 if norm else 0) + (1 if act else 0))
+    return F.linear(h, params[f"{prefix}.mlp.{j}.weight"], params[f"{prefix}.mlp.{j}.bias"])
+
+
+def shac_critic_loss(params, prefixes, obs, target, n_hidden, norm, act):
+    """compute_critic_loss (shac.py:869-875): mean over critics of F.mse_loss(pred.squeeze(-1), target)."""
+    losses = [F.mse_loss(critic_forward(params, pf, obs, n_hidden, norm, act).squeeze(-1), target) for pf in prefixes]
+    return torch.stack(losses).mean()
+
+
+def shac_update_critic(params, prefixes, optim, obs_flat, target_flat, batch_size, iterations, n_hidden, norm, act,
+                       truncate_grads=True, max_grad_norm=1.0):
+    """update_critic (shac.py:824-867) over the time-major flattened dataset (CriticDataset, no shuffle, keep the
+    short last batch).  params: dict name -> leaf tensor (requires_grad) that `optim` steps.  Returns the results dict."""
+    results = {"value_loss": [], "grad_norm_before_clip/critic": [], "grad_norm_after_clip/critic": []}
+    leaves = list(params.values())
+    for _ in range(iterations):
+        total, before, after = 0.0, [], []
+        slices = critic_dataset_slices(target_flat.shape[0], batch_size, drop_last=False)
+        for s, e in slices:
+            optim.zero_grad()
+            loss = shac_critic_loss(params, prefixes, obs_flat[s:e], target_flat[s:e], n_hidden, norm, act)
+            loss.backward()
+            for p in leaves:
+                p.grad.nan_to_num_(0.0, 0.0, 0.0)
+            if truncate_grads:
+                before.append(torch.sqrt(sum(torch.sum(p.grad ** 2) for p in leaves)))
+                if max_grad_norm is not None:
+                    torch.nn.utils.clip_grad_norm_(leaves, max_grad_norm)
+                after.append(torch.sqrt(sum(torch.sum(p.grad ** 2) for p in leaves)))
+            optim.step()
+            total = total + loss
+        results["value_loss"].append((total / len(slices)).detach())
+        if truncate_grads:
+            results["grad_norm_before_clip/critic"].append(torch.mean(torch.stack(before)))
+            results["grad_norm_after_clip/critic"].append(torch.mean(torch.stack(after)))
+    return results
+
+
+# --------------------------------------------------------------------------
 # K3c/K3d  circular replay          mineral/buffers/simple_replay.py:19-85
 # --------------------------------------------------------------------------
 
@@ -356,12 +416,14 @@ def mlp_tower(params, prefix, x, n_layers, norm, act):
         if norm:
             w = params[f"{prefix}.mlp.{j + 1}.weight"]
             x = F.layer_norm(x, (w.shape[0],), w, params[f"{prefix}.mlp.{j + 1}.bias"], 1e-5)
+        # the reference builds its activations with inplace=True (mlp.py:37): the in-place ELU backward is evaluated from
+        # the OUTPUT, one ulp away from the out-of-place formula, so the oracle does the same
         if act == "ELU":
-            x = F.elu(x)
+            x = F.elu(x, inplace=True)
         elif act == "SiLU":
-            x = F.silu(x)
+            x = F.silu(x, inplace=True)
         elif act == "ReLU":
-            x = F.relu(x)
+            x = F.relu(x, inplace=True)
         elif act is not None:
             raise NotImplementedError(act)
     return x

@@ -256,6 +256,33 @@ def test_td_lambda_humanoid_shape_vs_oracle():
         eq(out, oc.td_lambda_targets(rew, dm, nv, 0.99, 0.95), f"td-lambda {T}x{N}")
 
 
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_shac_update_critic_matches_reference_golden(cuda_graph):
+    """a16: SHAC.update_critic on our kernels (critic MLP fwd/bwd, MSE + gradient, nan_to_num + clip + Adam; optionally one
+    CUDA graph) against the reference's own run on its Critic / EnsembleCritic, Humanoid shape (cfg3)."""
+    from mineral_b200.agents.diffrl.shac import SHAC
+
+    for c in load_golden("shac_critic"):
+        T, B, O = c["shape"]
+        obs, tv = oc.shac_critic_inputs(c["seed"], T, B, O, c["wild"])
+        ag = SHAC(B, O, 21, T, DEV, critic_iterations=c["iterations"], num_critics=c["n_critics"], critic_lr=c["lr"],
+                  critic_betas=c["betas"], max_grad_norm=c["max_grad_norm"], cuda_graph=cuda_graph)
+        assert ag.fused
+        ag.critic_batch_size = c["batch_size"]
+        ag.obs_buf["obs"].copy_(obs), ag.target_values.copy_(tv)
+        snap = ag.critic_optim.state_dict()
+        for rep in range(3 if cuda_graph else 1):  # eager warm-up, capture + replay, replay: each from the same state
+            ag.critic.load_state_dict(c["init_state_dict"])
+            ag.critic_optim.load_state_dict(snap)
+            res = ag.update_critic()
+            tag = f"critics={c['n_critics']} graph={cuda_graph} rep={rep}"
+            for k, v in c["results"].items():
+                scale_close(torch.stack(res[k]), v, 2e-5, f"{tag} {k}")
+            for k, v in c["final_state_dict"].items():
+                scale_close(ag.critic.state_dict()[k], v, 1e-4, f"{tag} param {k}")
+        assert (ag._critic_engine.graph is not None) == cuda_graph
+
+
 def test_critic_dataset_matches_reference_golden():
     from mineral_b200.agents.diffrl.utils import CriticDataset
 

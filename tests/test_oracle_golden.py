@@ -154,3 +154,19 @@ def test_ppo_update_matches_reference_agent():
             scale_close(vr[i], c["value_rms_after"][k], 1e-12, k)
         scale_close(data["mu"], c["data_after_train"]["mu"], 1e-6)
         scale_close(data["sigma"], c["data_after_train"]["sigma"], 1e-6)
+
+
+def test_shac_update_critic_matches_reference():
+    """a16: oracle restatement of SHAC.update_critic == the reference's own run (Critic and EnsembleCritic)."""
+    for c in load_golden("shac_critic"):
+        T, B, O = c["shape"]
+        obs, tv = oc.shac_critic_inputs(c["seed"], T, B, O, c["wild"])
+        params = {k: v.clone().requires_grad_(True) for k, v in c["init_state_dict"].items()}
+        prefixes = ["critic_mlp"] if c["n_critics"] == 1 else [f"critics.{k}" for k in range(c["n_critics"])]
+        optim = torch.optim.Adam(list(params.values()), lr=c["lr"], betas=c["betas"])
+        res = oc.shac_update_critic(params, prefixes, optim, obs.view(-1, O), tv.view(-1), c["batch_size"], c["iterations"], 2, True, "ELU",
+                                    True, c["max_grad_norm"])
+        for k, v in c["results"].items():
+            assert torch.equal(torch.stack(res[k]), v), k
+        for k, v in c["final_state_dict"].items():
+            assert torch.equal(params[k].detach(), v), k
