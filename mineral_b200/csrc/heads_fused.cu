@@ -8,12 +8,12 @@
 //   dWmu = g_mu^T Y3a, dbmu, dWsig / dsigma, dWv = g_v^T Y3v, dbv                         (head parameter gradients)
 //   mu / sigma write-back (mineral/agents/ppo/experience.py:83-87) and their column means (results['mu'|'sigma'])
 //
-// Layout of the work.  A CTA = 128 threads owns tiles of 128 rows; a tile of Y3a and Y3v is staged ONCE in shared
-// memory (coalesced float4 loads, row pitch H+4 floats so that "thread = row" LDS.128 sweeps are conflict-free) and is
-// used three times: (1) thread-per-row dot products with the head weights (broadcast LDS.128 from shared memory),
-// (2) the weight-gradient outer products with thread = (hidden column u, row group) walking the 128 rows of the
-// tile, accumulating in registers ACROSS tiles, (3) it is overwritten in place by dY3 and leaves through coalesced
-// float4 stores.  After the tile loop the per-CTA partials go to the workspace, the grid (all CTAs resident) meets at
+// Layout of the work.  A CTA = 128 threads owns tiles of 128 rows; the Y3a tile (and afterwards, in the same buffer, the
+// Y3v tile) is staged ONCE in shared memory (coalesced float4 loads, row pitch H+4 floats so that "thread = row" LDS.128
+// sweeps are conflict-free) and is used three times: (1) thread-per-row dot products with the head weights (broadcast
+// LDS.128 from shared memory), (2) the weight-gradient outer products with thread = (4 hidden columns, row group)
+// walking its rows of the tile, accumulating in registers ACROSS tiles, (3) it is overwritten in place by dY3 and leaves
+// through coalesced float4 stores.  After the tile loop the per-CTA partials go to the workspace, the grid (all CTAs resident) meets at
 // a grid barrier and every CTA reduces its share of the outputs over all CTAs' partials in a fixed order
 // (deterministic, no atomics); CTA 0 also finalises the ten loss metrics.
 #include "common.cuh"
@@ -46,32 +46,37 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return acc;
 }
 
-template <int AMAX, int H, bool LEARNED>
+// A, H compile-time (no guards in the unrolled dot products); one shared-memory tile buffer serves the actor tower
+// and then the value tower of the same 128 rows, so a CTA needs ~55 KB and 4 CTAs share an SM.
+template <int A, int H, bool LEARNED>
 __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constant__ FusedHeadsArgs a,
                                                             const __grid_constant__ mnr_ppo_loss_cfg_t cfg) {
   constexpr int P = H + 4, P4 = P / 4, H4 = H / 4;
-  constexpr int G = kRows / H;                               // row groups of the weight-gradient phase
-  constexpr int NYMAX = (LEARNED ? 2 : 1) * AMAX;            // gradient rows fed by Y3a
-  constexpr int JR = (NYMAX + G - 1) / G;                    // of which one thread owns at most JR
+  constexpr int NY = (LEARNED ? 2 : 1) * A;          // gradient rows fed by Y3a: g_mu | g_ls
+  constexpr int GP = 4 * A + 4;                      // s_g pitch: g_mu | g_ls | mu | sigma | g_v | pad  (float4-aligned groups,
+                                                     // GP mod 32 == 4 or 20: "thread = row" float4 accesses are conflict-free)
+  constexpr int GW = 4 * A + 1;                      // columns that get summed over rows
+  constexpr int UV = NY * 4 <= 64 ? 4 : 2;           // hidden columns per thread in the weight-gradient phase
+  constexpr int HU = H / UV, NRG = kRows / HU, RPG = kRows / NRG;  // threads per row group, row groups, rows per group
+  static_assert(A % 4 == 0 && A <= 16 && NRG >= 1 && NY * UV <= 64, "unsupported head shape");
   extern __shared__ __align__(16) float sh[];
   __shared__ double s_red[6][kRows / 32];
   __shared__ mnr::Moments s_mom[2][kRows / 32];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int A = a.A;
-  const int GW = 4 * A + 1;  // s_g columns: g_mu | g_ls | g_v | mu | sigma   (odd pitch: conflict-free both ways)
-  const int NY = (LEARNED ? 2 : 1) * A;
-  float* s_ya = sh;
-  float* s_yv = s_ya + kRows * P;
-  float* s_wmu = s_yv + kRows * P;                 // (A,H)
-  float* s_wsig = s_wmu + AMAX * H;                // (A,H), learned only
-  float* s_wv = s_wsig + (LEARNED ? AMAX * H : 0); // (H)
-  float* s_g = s_wv + H;                           // [128][GW]
+  float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a, then Y3v tile, then dY3v
+  float* s_wmu = s_y + kRows * P;                    // (A,H)
+  float* s_wsig = s_wmu + A * H;                     // (A,H), learned only
+  float* s_wv = s_wsig + (LEARNED ? A * H : 0);      // (H)
+  float* s_g = s_wv + H;                             // [128][GP]
 
   for (int i = tid; i < A * H; i += kRows) {
     s_wmu[i] = __ldg(a.w_mu + i);
     if (LEARNED) s_wsig[i] = __ldg(a.w_sig + i);
   }
   for (int i = tid; i < H; i += kRows) s_wv[i] = __ldg(a.w_v + i);
+  float b_mu[A], b_sig[A];
+#pragma unroll
+  for (int j = 0; j < A; ++j) b_mu[j] = __ldg(a.b_mu + j), b_sig[j] = __ldg(a.b_sig + j);
 
   const float w = cfg.grad_scale / (float)a.M;
   const float b_v = __ldg(a.b_v);
@@ -79,16 +84,17 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   mnr::Welford w_d, w_ret;
   w_d.init(), w_ret.init();
 
-  // weight-gradient accumulators (live across tiles): thread = (hidden column u, row group grp)
-  const int u = tid % H, grp = tid / H;
-  float acc[JR], acc_v = 0.f, acc_col = 0.f;
+  // weight-gradient accumulators, live across tiles: thread = (UV hidden columns from uu, row group rg)
+  const int uu = (tid % HU) * UV, rg = tid / HU;
+  float accw[NY][UV], accv[UV], acc_col = 0.f;
 #pragma unroll
-  for (int jj = 0; jj < JR; ++jj) acc[jj] = 0.f;
+  for (int j = 0; j < NY; ++j)
+#pragma unroll
+    for (int q = 0; q < UV; ++q) accw[j][q] = 0.f;
+#pragma unroll
+  for (int q = 0; q < UV; ++q) accv[q] = 0.f;
 
-  const float4* gya = reinterpret_cast<const float4*>(a.y3a);
-  const float4* gyv = reinterpret_cast<const float4*>(a.y3v);
-  float4* s_ya4 = reinterpret_cast<float4*>(s_ya);
-  float4* s_yv4 = reinterpret_cast<float4*>(s_yv);
+  float4* s_y4 = reinterpret_cast<float4*>(s_y);
   const float4* s_wmu4 = reinterpret_cast<const float4*>(s_wmu);
   const float4* s_wsig4 = reinterpret_cast<const float4*>(s_wsig);
   const float4* s_wv4 = reinterpret_cast<const float4*>(s_wv);
@@ -96,160 +102,220 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kRows;
     const int rows_here = (int)min((int64_t)kRows, a.M - row0);
-    __syncthreads();  // previous tile's stores out of s_ya / s_yv are done (and the weights are staged)
-    // ---- stage the tile: [r][H] -> pitch P ------------------------------------------------------------------
-#pragma unroll 8
-    for (int i = tid; i < kRows * H4; i += kRows) {
-      const int r = i / H4, c = i - r * H4;
-      float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vv = va;
-      if (r < rows_here) va = __ldg(gya + (row0 + r) * H4 + c), vv = __ldg(gyv + (row0 + r) * H4 + c);
-      s_ya4[r * P4 + c] = va, s_yv4[r * P4 + c] = vv;
-    }
-    __syncthreads();
-
-    // ---- (1) thread = row: head forward --------------------------------------------------------------------
     const int r = tid;
     const bool valid = r < rows_here;
     const int64_t row = valid ? row0 + r : a.M - 1;
-    float mu_raw[AMAX], ls[AMAX], value = 0.f;
+    float* grow = s_g + r * GP;
+
+    // =========================== actor tower ===========================================================
+    __syncthreads();  // previous tile's stores out of s_y are done (and the weights are staged)
+    {
+      const float4* gy = reinterpret_cast<const float4*>(a.y3a);
+#pragma unroll 8
+      for (int i = tid; i < kRows * H4; i += kRows) {
+        const int rr = i / H4, c = i - rr * H4;
+        s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    // ---- thread = row: mu / logstd heads -------------------------------------------------------------
+    float mu_raw[A], ls[A];
 #pragma unroll
-    for (int j = 0; j < AMAX; ++j) mu_raw[j] = 0.f, ls[j] = 0.f;
+    for (int j = 0; j < A; ++j) mu_raw[j] = 0.f, ls[j] = 0.f;
 #pragma unroll 2
     for (int c = 0; c < H4; ++c) {
-      const float4 ya = s_ya4[r * P4 + c], yv = s_yv4[r * P4 + c];
-      value = dot4(yv, s_wv4[c], value);
+      const float4 ya = s_y4[r * P4 + c];
 #pragma unroll
-      for (int j = 0; j < AMAX; ++j) {
-        if (j < A) {
-          mu_raw[j] = dot4(ya, s_wmu4[j * H4 + c], mu_raw[j]);
-          if (LEARNED) ls[j] = dot4(ya, s_wsig4[j * H4 + c], ls[j]);
-        }
+      for (int j = 0; j < A; ++j) {
+        mu_raw[j] = dot4(ya, s_wmu4[j * H4 + c], mu_raw[j]);
+        if (LEARNED) ls[j] = dot4(ya, s_wsig4[j * H4 + c], ls[j]);
       }
     }
-    value += b_v;
-
-    // ---- per-element loss terms ----------------------------------------------------------------------------------
+    // ---- per-element loss terms.  ROLLED loops over the action columns with the row's values parked in its own s_g
+    //      row (slots [0,A) raw mu, [A,2A) raw logstd -> later g_mu, g_ls; [2A,3A) mu; [3A,4A) sigma): keeps the
+    //      transcendental-heavy body in the code once instead of A times (the kernel runs each instruction only a few
+    //      times per warp, so instruction-cache misses were a top stall) and frees ~100 registers.
+#pragma unroll
+    for (int j = 0; j < A; ++j) grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
     float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
-    float e_mu[AMAX], e_sg[AMAX], e_dmu[AMAX], e_dsg[AMAX], e_diff[AMAX];
-#pragma unroll
-    for (int j = 0; j < AMAX; ++j) {
-      e_mu[j] = 0.f, e_sg[j] = 1.f, e_dmu[j] = 0.f, e_dsg[j] = 0.f, e_diff[j] = 0.f;
-      if (j < A) {
-        const float m = mu_raw[j] + __ldg(a.b_mu + j);
-        const float l = LEARNED ? ls[j] + __ldg(a.b_sig + j) : __ldg(a.b_sig + j);
-        float mu, sg, dmu, dsg, db;
-        dist_fwd(cfg, m, l, mu, sg, dmu, dsg);
-        const float diff = __ldg(a.actions + (size_t)row * A + j) - mu;
-        const float lsg = logf(sg);
-        nlp += diff * diff / (2.f * sg * sg) + lsg + kLogSqrt2Pi;
-        ent += 0.5f + kLogSqrt2Pi + lsg;
-        bsum += bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
-        kl += kl_elem(mu, sg, a.old_mu[(size_t)row * A + j], a.old_sigma[(size_t)row * A + j]);
-        e_mu[j] = mu, e_sg[j] = sg, e_dmu[j] = dmu, e_dsg[j] = dsg, e_diff[j] = diff;
-      }
+    const float* act_row = a.actions + (size_t)row * A;
+#pragma unroll 1
+    for (int j = 0; j < A; ++j) {
+      float mu, sg, dmu, dsg, db;
+      dist_fwd(cfg, grow[j], grow[A + j], mu, sg, dmu, dsg);
+      const float diff = __ldg(act_row + j) - mu;
+      const float lsg = logf(sg);
+      nlp += diff * diff / (2.f * sg * sg) + lsg + kLogSqrt2Pi;
+      ent += 0.5f + kLogSqrt2Pi + lsg;
+      bsum += bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
+      kl += kl_elem(mu, sg, a.old_mu[(size_t)row * A + j], a.old_sigma[(size_t)row * A + j]);
+      grow[2 * A + j] = mu, grow[3 * A + j] = sg;
     }
-    float dl_dnlp, clipped, dl_dv;
-    const float ret = __ldg(a.returns + row);
+    float dl_dnlp, clipped;
     const float a_loss = actor_row(__ldg(a.old_nlp + row), nlp, __ldg(a.adv + row), cfg.e_clip, cfg.use_smooth_clamp, &dl_dnlp, &clipped);
-    const float c_loss = critic_row(__ldg(a.old_values + row), value, ret, cfg.e_clip, cfg.clip_value_loss, &dl_dv);
-    const float g_v = valid ? w * 0.5f * cfg.critic_coef * dl_dv : 0.f;
-    if (valid) {
-      t_a += a_loss, t_c += c_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
-      w_d.push(ret - value), w_ret.push(ret);
-      if (a.g_v) a.g_v[row] = g_v;
-    }
+    if (valid) t_a += a_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
     const float g_nlp = w * dl_dnlp;
-    float* grow = s_g + r * GW;
+    const float span = cfg.maxstd - cfg.minstd;
+#pragma unroll 1
+    for (int j = 0; j < A; ++j) {
+      const float mu = grow[2 * A + j], sg = grow[3 * A + j];
+      const float diff = __ldg(act_row + j) - mu;
+      float dmu = 1.f, dsg = sg;                                  // d mu / d mu_raw, d sigma / d logstd (dist.py:32-47)
+      if (cfg.dist_type != MNR_DIST_NORMAL) {
+        const float sgm = (sg - cfg.minstd) / span;               // the sigmoid value dist_fwd produced
+        dmu = 1.f - mu * mu, dsg = span * sgm * (1.f - sgm);
+      }
+      const float inv_var = 1.f / (sg * sg);
+      float db;
+      bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
+      const float g_m = g_nlp * (-diff * inv_var) + w * cfg.bounds_loss_coef * db;
+      const float g_s = g_nlp * (1.f - diff * diff * inv_var) / sg - w * cfg.entropy_coef / sg;
+      const float gm = valid ? g_m * dmu : 0.f, gl = valid ? g_s * dsg : 0.f;
+      grow[j] = gm, grow[A + j] = gl;
+      if (!valid) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;
+    }
+    if (valid) {  // row-contiguous float4 copies of the finished row pieces
 #pragma unroll
-    for (int j = 0; j < AMAX; ++j) {
-      if (j < A) {
-        const float mu = e_mu[j], sg = e_sg[j], diff = e_diff[j];
-        const float inv_var = 1.f / (sg * sg);
-        float db;
-        bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
-        const float g_m = g_nlp * (-diff * inv_var) + w * cfg.bounds_loss_coef * db;
-        const float g_s = g_nlp * (1.f - diff * diff * inv_var) / sg - w * cfg.entropy_coef / sg;
-        const float gm = valid ? g_m * e_dmu[j] : 0.f, gl = valid ? g_s * e_dsg[j] : 0.f;
-        grow[j] = gm, grow[A + j] = gl;
-        grow[2 * A + 1 + j] = valid ? mu : 0.f, grow[3 * A + 1 + j] = valid ? sg : 0.f;
-        if (valid) {
-          if (a.g_mu) a.g_mu[(size_t)row * A + j] = gm;
-          if (a.g_ls) a.g_ls[(size_t)row * A + j] = gl;
-          if (a.write_back) a.old_mu[(size_t)row * A + j] = mu, a.old_sigma[(size_t)row * A + j] = sg;
+      for (int j4 = 0; j4 < A / 4; ++j4) {
+        const float4 gm4 = reinterpret_cast<const float4*>(grow)[j4], gl4 = reinterpret_cast<const float4*>(grow + A)[j4];
+        if (a.g_mu) reinterpret_cast<float4*>(a.g_mu + (size_t)row * A)[j4] = gm4;
+        if (a.g_ls) reinterpret_cast<float4*>(a.g_ls + (size_t)row * A)[j4] = gl4;
+        if (a.write_back) {
+          reinterpret_cast<float4*>(a.old_mu + (size_t)row * A)[j4] = reinterpret_cast<const float4*>(grow + 2 * A)[j4];
+          reinterpret_cast<float4*>(a.old_sigma + (size_t)row * A)[j4] = reinterpret_cast<const float4*>(grow + 3 * A)[j4];
         }
       }
     }
-    grow[2 * A] = g_v;
     __syncthreads();
-
-    // ---- (2) thread = (u, grp): weight-gradient outer products over the tile's rows; column sums ------------
-#pragma unroll 4
-    for (int rr = 0; rr < kRows; ++rr) {
-      const float ya = s_ya[rr * P + u];
-      const float* g = s_g + rr * GW;
-#pragma unroll
-      for (int jj = 0; jj < JR; ++jj) {
-        const int jrow = grp + jj * G;
-        if (jrow < NY) acc[jj] = fmaf(g[jrow], ya, acc[jj]);
+    // ---- thread = (uu, rg): dW_mu / dW_sig outer products over this group's rows -----------------------------------
+#pragma unroll 2
+    for (int k = 0; k < RPG; ++k) {
+      const int rr = rg * RPG + k;
+      float yv_[UV];
+      if (UV == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(s_y + rr * P + uu);
+        yv_[0] = t.x, yv_[1] = t.y, yv_[2] = t.z, yv_[3] = t.w;
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(s_y + rr * P + uu);
+        yv_[0] = t.x, yv_[1] = t.y;
       }
-      if (grp == G - 1) acc_v = fmaf(g[2 * A], s_yv[rr * P + u], acc_v);
-    }
-    if (tid < GW) {
-      float s = 0.f;
-#pragma unroll 8
-      for (int rr = 0; rr < kRows; ++rr) s += s_g[rr * GW + tid];
-      acc_col += s;
+      const float4* g4 = reinterpret_cast<const float4*>(s_g + rr * GP);
+#pragma unroll
+      for (int j4 = 0; j4 < NY / 4; ++j4) {
+        const float4 g = g4[j4];
+        const float gq[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int x = 0; x < UV; ++x) accw[4 * j4 + q][x] = fmaf(gq[q], yv_[x], accw[4 * j4 + q][x]);
+      }
     }
     __syncthreads();
-
-    // ---- (3) thread = row again: dY3 over the tile in place, then coalesced stores ---------------------------
+    // ---- thread = row: dY3a = g_mu Wmu + g_ls Wsig over the tile in place, then coalesced stores ------------------------
     {
-      float gm[AMAX], gl[AMAX];
+      float gm[A], gl[A];
 #pragma unroll
-      for (int j = 0; j < AMAX; ++j) {
-        gm[j] = 0.f, gl[j] = 0.f;
-        if (j < A) gm[j] = grow[j], gl[j] = LEARNED ? grow[A + j] : 0.f;
-      }
+      for (int j = 0; j < A; ++j) gm[j] = grow[j], gl[j] = LEARNED ? grow[A + j] : 0.f;
 #pragma unroll 2
       for (int c = 0; c < H4; ++c) {
         float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < AMAX; ++j) {
-          if (j < A) {
-            const float4 wm = s_wmu4[j * H4 + c];
-            da.x = fmaf(gm[j], wm.x, da.x), da.y = fmaf(gm[j], wm.y, da.y), da.z = fmaf(gm[j], wm.z, da.z), da.w = fmaf(gm[j], wm.w, da.w);
-            if (LEARNED) {
-              const float4 ws = s_wsig4[j * H4 + c];
-              da.x = fmaf(gl[j], ws.x, da.x), da.y = fmaf(gl[j], ws.y, da.y), da.z = fmaf(gl[j], ws.z, da.z), da.w = fmaf(gl[j], ws.w, da.w);
-            }
+        for (int j = 0; j < A; ++j) {
+          const float4 wm = s_wmu4[j * H4 + c];
+          da.x = fmaf(gm[j], wm.x, da.x), da.y = fmaf(gm[j], wm.y, da.y), da.z = fmaf(gm[j], wm.z, da.z), da.w = fmaf(gm[j], wm.w, da.w);
+          if (LEARNED) {
+            const float4 ws = s_wsig4[j * H4 + c];
+            da.x = fmaf(gl[j], ws.x, da.x), da.y = fmaf(gl[j], ws.y, da.y), da.z = fmaf(gl[j], ws.z, da.z), da.w = fmaf(gl[j], ws.w, da.w);
           }
         }
-        const float4 wv = s_wv4[c];
-        s_ya4[r * P4 + c] = da;
-        s_yv4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
+        s_y4[r * P4 + c] = da;
       }
     }
     __syncthreads();
-    float4* oa = reinterpret_cast<float4*>(a.dy3a);
-    float4* ov = reinterpret_cast<float4*>(a.dy3v);
+    {
+      float4* oa = reinterpret_cast<float4*>(a.dy3a);
+      const float4* gy = reinterpret_cast<const float4*>(a.y3v);
 #pragma unroll 8
-    for (int i = tid; i < kRows * H4; i += kRows) {
-      const int rr = i / H4, c = i - rr * H4;
-      if (rr < rows_here) oa[(row0 + rr) * H4 + c] = s_ya4[rr * P4 + c], ov[(row0 + rr) * H4 + c] = s_yv4[rr * P4 + c];
+      for (int i = tid; i < kRows * H4; i += kRows) {  // dY3a out, Y3v in: every thread reuses exactly the slots it just read
+        const int rr = i / H4, c = i - rr * H4;
+        if (rr < rows_here) oa[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
+        s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    __syncthreads();
+    // =========================== value tower ===========================================================
+    float value = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < H4; ++c) value = dot4(s_y4[r * P4 + c], s_wv4[c], value);
+    value += b_v;
+    float dl_dv;
+    const float ret = __ldg(a.returns + row);
+    const float c_loss = critic_row(__ldg(a.old_values + row), value, ret, cfg.e_clip, cfg.clip_value_loss, &dl_dv);
+    const float g_v = valid ? w * 0.5f * cfg.critic_coef * dl_dv : 0.f;
+    if (valid) {
+      t_c += c_loss;
+      w_d.push(ret - value), w_ret.push(ret);
+      if (a.g_v) a.g_v[row] = g_v;
+    }
+    grow[4 * A] = g_v;
+    __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < RPG; ++k) {
+      const int rr = rg * RPG + k;
+      const float gv = s_g[rr * GP + 4 * A];
+      if (UV == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(s_y + rr * P + uu);
+        accv[0] = fmaf(gv, t.x, accv[0]), accv[1] = fmaf(gv, t.y, accv[1]), accv[2] = fmaf(gv, t.z, accv[2]), accv[3] = fmaf(gv, t.w, accv[3]);
+      } else {
+        const float2 t = *reinterpret_cast<const float2*>(s_y + rr * P + uu);
+        accv[0] = fmaf(gv, t.x, accv[0]), accv[1] = fmaf(gv, t.y, accv[1]);
+      }
+    }
+    if (tid < GW) {  // column sums of the g tile: db_mu | colsum g_ls | mu, sigma sums | db_v
+      float sum = 0.f;
+#pragma unroll 8
+      for (int rr = 0; rr < kRows; ++rr) sum += s_g[rr * GP + tid];
+      acc_col += sum;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int c = 0; c < H4; ++c) {
+      const float4 wv = s_wv4[c];
+      s_y4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
+    }
+    __syncthreads();
+    {
+      float4* ov = reinterpret_cast<float4*>(a.dy3v);
+#pragma unroll 8
+      for (int i = tid; i < kRows * H4; i += kRows) {
+        const int rr = i / H4, c = i - rr * H4;
+        if (rr < rows_here) ov[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
+      }
     }
   }
 
-  // ---- per-CTA partials -> workspace ----------------------------------------------------------------------------
+  // ---- fold the row groups (through the tile buffer), park the per-CTA partials ------------------------------------------
   const int PW = (2 * A + 1) * H + GW;
   float* part = a.partials + (size_t)blockIdx.x * PW;
+  float* s_fold = s_y;  // [NRG][H]
 #pragma unroll
-  for (int jj = 0; jj < JR; ++jj) {
-    const int jrow = grp + jj * G;
-    if (jrow < NY) part[jrow * H + u] = acc[jj];
+  for (int j = 0; j <= NY; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int x = 0; x < UV; ++x) s_fold[rg * H + uu + x] = j < NY ? accw[j < NY ? j : 0][x] : accv[x];
+    __syncthreads();
+    if (rg == 0) {
+#pragma unroll
+      for (int x = 0; x < UV; ++x) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < NRG; ++q) t += s_fold[q * H + uu + x];
+        part[(j < NY ? j : 2 * A) * H + uu + x] = t;
+      }
+    }
   }
   if (!LEARNED)  // sigma rows of the layout stay defined
-    for (int i = tid; i < A * H; i += kRows) part[(A + i / H) * H + i % H] = 0.f;
-  if (grp == G - 1) part[2 * A * H + u] = acc_v;
+    for (int i = tid; i < A * H; i += kRows) part[A * H + i] = 0.f;
   if (tid < GW) part[(2 * A + 1) * H + tid] = acc_col;
 
   float vals[6] = {t_a, t_c, t_b, t_h, t_clip, t_kl};
@@ -280,23 +346,23 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   // ---- every CTA reduces its share of the PW outputs over all CTAs (warp per output, fixed order) ----------------
   const int n_cta = gridDim.x;
   for (int o = blockIdx.x * (kRows / 32) + warp; o < PW; o += n_cta * (kRows / 32)) {
-    float s = 0.f;
-    for (int x = lane; x < n_cta; x += 32) s += __ldcg(a.partials + (size_t)x * PW + o);
+    float sum = 0.f;
+    for (int x = lane; x < n_cta; x += 32) sum += __ldcg(a.partials + (size_t)x * PW + o);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
     if (lane == 0) {
       if (o < (2 * A + 1) * H) {
-        const int jrow = o / H, uu = o - jrow * H;
-        if (jrow < A) a.dw_mu[jrow * H + uu] = s;
-        else if (jrow < 2 * A) { if (LEARNED) a.dw_sig[(jrow - A) * H + uu] = s; }
-        else a.dw_v[uu] = s;
+        const int jrow = o / H, u2 = o - jrow * H;
+        if (jrow < A) a.dw_mu[jrow * H + u2] = sum;
+        else if (jrow < 2 * A) { if (LEARNED) a.dw_sig[(jrow - A) * H + u2] = sum; }
+        else a.dw_v[u2] = sum;
       } else {
         const int j = o - (2 * A + 1) * H;
-        if (j < A) a.db_mu[j] = s;
-        else if (j < 2 * A) a.db_sig[j - A] = s;           // learned: bias gradient; fixed: d sigma = colsum g_ls
-        else if (j == 2 * A) a.db_v[0] = s;
-        else if (j < 3 * A + 1) { if (a.mu_mean) a.mu_mean[j - 2 * A - 1] = s / (float)a.M; }
-        else if (a.sigma_mean) a.sigma_mean[j - 3 * A - 1] = s / (float)a.M;
+        if (j < A) a.db_mu[j] = sum;
+        else if (j < 2 * A) a.db_sig[j - A] = sum;          // learned: bias gradient; fixed: d sigma = colsum g_ls
+        else if (j < 3 * A) { if (a.mu_mean) a.mu_mean[j - 2 * A] = sum / (float)a.M; }
+        else if (j < 4 * A) { if (a.sigma_mean) a.sigma_mean[j - 3 * A] = sum / (float)a.M; }
+        else a.db_v[0] = sum;
       }
     }
   }
@@ -329,25 +395,24 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   }
 }
 
-template <int AMAX, int H, bool LEARNED>
-size_t fused_smem_bytes(int A) {
-  return (size_t)(2 * kRows * (H + 4) + (LEARNED ? 2 : 1) * AMAX * H + H + kRows * (4 * A + 1)) * sizeof(float);
+template <int A, int H, bool LEARNED>
+size_t fused_smem_bytes() {
+  return (size_t)(kRows * (H + 4) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
 }
 
-template <int AMAX, int H, bool LEARNED>
+template <int A, int H, bool LEARNED>
 int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
-  const size_t smem = fused_smem_bytes<AMAX, H, LEARNED>(a.A);
-  auto kern = heads_fused_kernel<AMAX, H, LEARNED>;
-  static int occ_cached = -1;   // per instantiation; the smem size only varies with A <= AMAX (use the worst case)
-  static size_t smem_cached = 0;
-  if (occ_cached < 0 || smem > smem_cached) {
+  const size_t smem = fused_smem_bytes<A, H, LEARNED>();
+  auto kern = heads_fused_kernel<A, H, LEARNED>;
+  static int occ_cached = -1;   // per instantiation
+  if (occ_cached < 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int occ = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRows, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) return MNR_EUNSUP;
-    occ_cached = occ, smem_cached = smem;
+    occ_cached = occ;
   }
   int grid = mnr_sm_count() * occ_cached;  // every CTA resident: the grid barrier needs it
   if (grid > grid_cap) grid = grid_cap;
@@ -357,12 +422,23 @@ int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap,
   return e == cudaSuccess ? MNR_OK : (int)e;
 }
 
-template <int AMAX, bool LEARNED>
+template <int A, bool LEARNED>
 int launch_by_h(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
   switch (H) {
-    case 32: return launch_fused<AMAX, 32, LEARNED>(a, cfg, grid_cap, stream);
-    case 64: return launch_fused<AMAX, 64, LEARNED>(a, cfg, grid_cap, stream);
-    case 128: return launch_fused<AMAX, 128, LEARNED>(a, cfg, grid_cap, stream);
+    case 32: return launch_fused<A, 32, LEARNED>(a, cfg, grid_cap, stream);
+    case 64: return launch_fused<A, 64, LEARNED>(a, cfg, grid_cap, stream);
+    case 128: return launch_fused<A, 128, LEARNED>(a, cfg, grid_cap, stream);
+    default: return MNR_EUNSUP;
+  }
+}
+
+template <bool LEARNED>
+int launch_by_a(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
+  switch (a.A) {
+    case 4: return launch_by_h<4, LEARNED>(a, H, cfg, grid_cap, stream);
+    case 8: return launch_by_h<8, LEARNED>(a, H, cfg, grid_cap, stream);
+    case 12: return launch_by_h<12, LEARNED>(a, H, cfg, grid_cap, stream);
+    case 16: return launch_by_h<16, LEARNED>(a, H, cfg, grid_cap, stream);
     default: return MNR_EUNSUP;
   }
 }
@@ -370,9 +446,9 @@ int launch_by_h(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int gri
 }  // namespace
 
 // ---- internal interface used by mnr_ppo_heads_loss_fwd_bwd (csrc/ppo_loss.cu) ----------------------------------------
-int mnr_heads_fused_grid_cap() { return mnr_sm_count() * 2; }
+int mnr_heads_fused_grid_cap() { return mnr_sm_count() * 4; }
 
-bool mnr_heads_fused_supported(int A, int H) { return (H == 32 || H == 64 || H == 128) && A >= 1 && A <= 16; }
+bool mnr_heads_fused_supported(int A, int H) { return (H == 32 || H == 64 || H == 128) && A >= 4 && A <= 16 && A % 4 == 0; }
 
 size_t mnr_heads_fused_workspace_bytes(int A, int H) {
   const size_t cap = (size_t)mnr_heads_fused_grid_cap();
@@ -400,7 +476,8 @@ int mnr_heads_fused_launch(const float* y3a, const float* y3v, const float* w_mu
   a.loss_parts = reinterpret_cast<mnr_loss::LossPartial*>(ws + 256);
   a.partials = reinterpret_cast<float*>(ws + 256 + (((size_t)cap * sizeof(mnr_loss::LossPartial) + 255) / 256) * 256);
   a.M = M, a.A = A, a.write_back = write_back, a.n_tiles = (int)((M + kRows - 1) / kRows);
-  const bool learned = w_sig != nullptr;
-  if (A <= 8) return learned ? launch_by_h<8, true>(a, H, *cfg, cap, stream) : launch_by_h<8, false>(a, H, *cfg, cap, stream);
-  return learned ? launch_by_h<16, true>(a, H, *cfg, cap, stream) : launch_by_h<16, false>(a, H, *cfg, cap, stream);
+  if (!mnr_aligned(actions, 16) || !mnr_aligned(old_mu, 16) || !mnr_aligned(old_sigma, 16) || (g_mu && !mnr_aligned(g_mu, 16)) ||
+      (g_ls && !mnr_aligned(g_ls, 16)))
+    return MNR_EALIGN;
+  return w_sig != nullptr ? launch_by_a<true>(a, H, *cfg, cap, stream) : launch_by_a<false>(a, H, *cfg, cap, stream);
 }
