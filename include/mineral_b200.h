@@ -356,6 +356,19 @@ int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups /*host*/, int n_gro
 size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K);
 int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
                              size_t workspace_bytes, mnr_stream_t stream);
+/* The same in two steps, so that the split-reduce of several layers runs as ONE launch at the end of the backward
+ * pass: _partials runs only the tensor-core kernel (per-split dW / db partials stay in `workspace`, one workspace per
+ * layer); mnr_tc_reduce_partials then sums the splits of up to 4 such layers (same groups / M as given to _partials)
+ * into their dW (groups[].c) and db (groups[].bias_grad), in a fixed order. */
+int mnr_tc_linear_bwd_weight_partials(const mnr_linear_group_t* groups /*host*/, int n_groups, int M, int act, void* workspace,
+                                      size_t workspace_bytes, mnr_stream_t stream);
+typedef struct {
+  const mnr_linear_group_t* groups; /* host */
+  int32_t n_groups, M;
+  void* workspace;
+  size_t workspace_bytes;
+} mnr_tc_reduce_job_t;
+int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
 
 /* Profiling aid: enable != 0 makes CTA 0 of the tensor-core kernels record clock64() at every role's wait / done
  * points; host_out (4 roles x 256 events x 2 tags int64, may be NULL) receives the last timeline. Synchronous. */

@@ -82,6 +82,11 @@ class LnGroup(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("z", "y", "gamma", "beta", "mean", "rstd", "dy", "dz", "dgamma", "dbeta")]
 
 
+class TcReduceJob(C.Structure):
+    _fields_ = [("groups", C.POINTER(LinearGroup)), ("n_groups", C.c_int32), ("M", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
 class CriticSet(C.Structure):
     _fields_ = [("pred", C.c_void_p * 4), ("grad", C.c_void_p * 4)]
 
@@ -137,6 +142,8 @@ SIGNATURES = {
     "mnr_tc_linear_bwd_input": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp]),
     "mnr_tc_linear_bwd_weight_workspace_bytes": (sz, [i32, i32, i32, i32]),
     "mnr_tc_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_tc_linear_bwd_weight_partials": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
+    "mnr_tc_reduce_partials": (i32, [C.POINTER(TcReduceJob), i32, vp]),
     "mnr_tc_trace": (i32, [i32, vp]),
     "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
     "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),

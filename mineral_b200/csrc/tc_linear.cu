@@ -340,6 +340,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       const TileCoord tc = decode_tile(p, tile, MODE);
       const TcGroup& g = p.g[tc.gi];
       const uint32_t acc = it & 1;
+      // FWD: this warp's bias values (one column per lane, <= 2 chunks since BN <= 128) are requested BEFORE the wait on
+      // the accumulator: the global-load latency used to sit on every chunk's critical path (top stall of the kernel)
+      float bias_c[2] = {0.f, 0.f};
+      if (MODE == kFwd && g.bias) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int cc = half + k * (kEpiWarps / 4);
+          const int col = tc.j0 + cc * 32 + lane;
+          if (cc * 32 + lane < BN && col < p.J) bias_c[k] = __ldg(g.bias + col);
+        }
+      }
       ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
       if (tid == 256) TC_TRACE(3, it, 0);
       ptx::tc_fence_after();
@@ -368,8 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
         // dependent chain: ~100 cycles per row).
         const int col = jb + lane;
         const bool col_ok = col < p.J && cc * 32 + lane < BN;
-        float bias = 0.f;
-        if (MODE == kFwd && col_ok && g.bias) bias = __ldg(g.bias + col);
+        const float bias = cc == half ? bias_c[0] : bias_c[1];
         const int rows_valid = min(32, p.I - row_base);
         float* out = cbase + (size_t)row_base * ldo + col;
         if (rows_valid == 32) {
@@ -411,18 +421,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 }
 
 // dW / db = sum over splits (fixed order)
-struct ReduceArgs {
-  float* w[kMaxGroups];
-  float* b[kMaxGroups];
-};
 // block = 32 element slots x 8 split slices: every thread sums splits z = slice, slice + 8, .. (independent loads, all in
 // flight), the 8 slices meet in shared memory and are added in slice order -> deterministic, one latency round.
-// blockIdx.x < wblocks: 32 float4 of dW;  else: 32 floats of db.
-__global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_groups, int splits, int I, int J, int wblocks,
-                                                        const float* __restrict__ partials) {
+// blockIdx.y = (job, group): up to 4 layers' partials are reduced by ONE launch.  blockIdx.x < wblocks: 32 float4 of
+// dW;  else: 32 floats of db.
+struct ReduceJob {
+  float* w[kMaxGroups];
+  float* b[kMaxGroups];
+  const float* partials;
+  int n_groups, splits, I, J, wblocks;
+};
+constexpr int kMaxReduceJobs = 4;
+struct ReduceJobs {
+  ReduceJob j[kMaxReduceJobs];
+};
+__global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
   __shared__ float4 s_part[8][32];
-  const int gi = blockIdx.y;
-  const int NK = I * J;
+  const ReduceJob& jb = jobs.j[blockIdx.y / kMaxGroups];
+  const int gi = blockIdx.y % kMaxGroups;
+  if (gi >= jb.n_groups || (int)blockIdx.x >= jb.wblocks + (jb.I + 31) / 32) return;
+  const int splits = jb.splits, I = jb.I, wblocks = jb.wblocks;
+  const int NK = I * jb.J;
+  const float* __restrict__ partials = jb.partials;
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   if ((int)blockIdx.x < wblocks) {
@@ -438,8 +458,8 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_gro
     }
   } else {
     const int n = ((int)blockIdx.x - wblocks) * 32 + lane;
-    if (n < I && ra.b[gi]) {
-      const float* bp = partials + (size_t)n_groups * splits * NK + (size_t)gi * splits * I + n;
+    if (n < I && jb.b[gi]) {
+      const float* bp = partials + (size_t)jb.n_groups * splits * NK + (size_t)gi * splits * I + n;
 #pragma unroll 4
       for (int z = slice; z < splits; z += 8) acc.x += __ldcs(bp + (size_t)z * I);
     }
@@ -454,10 +474,10 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(ReduceArgs ra, int n_gro
   }
   if ((int)blockIdx.x < wblocks) {
     const int e4 = blockIdx.x * 32 + lane;
-    if (e4 * 4 < NK) reinterpret_cast<float4*>(ra.w[gi])[e4] = acc;
+    if (e4 * 4 < NK) reinterpret_cast<float4*>(jb.w[gi])[e4] = acc;
   } else {
     const int n = ((int)blockIdx.x - wblocks) * 32 + lane;
-    if (n < I && ra.b[gi]) ra.b[gi][n] = acc.x;
+    if (n < I && jb.b[gi]) jb.b[gi][n] = acc.x;
   }
 }
 
@@ -634,8 +654,10 @@ extern "C" size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, 
   return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + N) * sizeof(float);
 }
 
-extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_groups, int M, int act, void* workspace,
-                                        size_t workspace_bytes, mnr_stream_t stream) {
+namespace {
+// the DW launch of one layer: tile / split plan + tensor maps; `job` receives what the split reduce needs
+int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, void* workspace, size_t workspace_bytes, bool launch_it,
+              ReduceJob* job, cudaStream_t stream) {
   if (n_groups <= 0 || n_groups > kMaxGroups) return MNR_ESHAPE;
   MNR_CHECK_PTR(groups); MNR_CHECK_PTR(workspace);
   if (M <= 0) return MNR_ESHAPE;
@@ -643,38 +665,77 @@ extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_
   const int N = groups[0].N, K = groups[0].K;
   if (N <= 0 || K <= 0 || N % 4 != 0) return MNR_ESHAPE;
   if (workspace_bytes < mnr_tc_linear_bwd_weight_workspace_bytes(n_groups, M, N, K)) return MNR_EWORKSPACE;
+  if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
   TcParams p;
   const int Kr = (K + 31) / 32 * 32;
   p.BN = Kr <= 128 ? Kr : 128;
-  ReduceArgs ra;
   bool want_bias = false;
+  for (int k = 0; k < kMaxGroups; ++k) job->w[k] = nullptr, job->b[k] = nullptr;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
     if (!s.a || !s.b || !s.c || (act != 0 && !s.saved)) return MNR_ENULL;
     if (s.N != N || s.K != K) return MNR_ESHAPE;
-    int rc = make_map(&p.g[k].a, s.a, M, N, N, 32, true);                            // dY (M,N): rows = reduction
-    if (rc == MNR_OK) rc = make_map(&p.g[k].s, act != 0 ? s.saved : s.a, M, N, N, 32, true);
-    if (rc == MNR_OK) rc = make_map(&p.g[k].b0, s.b, M, K, ld_or(s.ldb, K), 32, true);  // X (M,K)
-    if (rc != MNR_OK) return rc;
-    p.g[k].b1 = p.g[k].b0;
-    p.g[k].c = s.c, p.g[k].bias = nullptr;
-    ra.w[k] = s.c, ra.b[k] = s.bias_grad;
+    if (!mnr_aligned(s.c, 16)) return MNR_EALIGN;
+    if (launch_it) {
+      int rc = make_map(&p.g[k].a, s.a, M, N, N, 32, true);                            // dY (M,N): rows = reduction
+      if (rc == MNR_OK) rc = make_map(&p.g[k].s, act != 0 ? s.saved : s.a, M, N, N, 32, true);
+      if (rc == MNR_OK) rc = make_map(&p.g[k].b0, s.b, M, K, ld_or(s.ldb, K), 32, true);  // X (M,K)
+      if (rc != MNR_OK) return rc;
+      p.g[k].b1 = p.g[k].b0;
+      p.g[k].c = s.c, p.g[k].bias = nullptr;
+    }
+    job->w[k] = s.c, job->b[k] = s.bias_grad;
     want_bias = want_bias || s.bias_grad != nullptr;
   }
-  for (int k = n_groups; k < kMaxGroups; ++k) ra.w[k] = nullptr, ra.b[k] = nullptr;
   const int ti = (N + kBM - 1) / kBM, tj = (K + p.BN - 1) / p.BN;
   const int splits = tc_dw_splits(M, ti * tj * n_groups);
+  // (N % 4 == 0 was checked above, so N*K is a multiple of 4 and every dW / partial slab is 16 B aligned)
+  job->partials = (const float*)workspace, job->n_groups = n_groups, job->splits = splits, job->I = N, job->J = K;
+  job->wblocks = (N * K / 4 + 31) / 32;
+  if (!launch_it) return MNR_OK;
   p.I = N, p.J = K, p.R = M, p.ldc = K, p.act = act, p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 31) / 32 * 32;
   p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = pick_stages(kDw, act, p.BN);
   dim3 grid(ti, tj, n_groups * splits);
-  const int rc = launch<kDw>(p, grid, mnr_cs(stream));
-  if (rc != MNR_OK) return rc;
-  // (N % 4 == 0 was checked above, so N*K is a multiple of 4 and every dW / partial slab is 16 B aligned)
-  const int wblocks = (N * K / 4 + 31) / 32;
-  dim3 rgrid(wblocks + (N + 31) / 32, n_groups);
-  tc_reduce_kernel<<<rgrid, 256, 0, mnr_cs(stream)>>>(ra, n_groups, splits, N, K, wblocks, (const float*)workspace);
+  return launch<kDw>(p, grid, stream);
+}
+
+int reduce_launch(const ReduceJobs& jobs, int n_jobs, cudaStream_t stream) {
+  int max_x = 1;
+  for (int q = 0; q < n_jobs; ++q) {
+    const int x = jobs.j[q].wblocks + (jobs.j[q].I + 31) / 32;
+    max_x = x > max_x ? x : max_x;
+  }
+  dim3 rgrid(max_x, n_jobs * kMaxGroups);
+  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(jobs);
   MNR_LAUNCH_RESULT();
+}
+}  // namespace
+
+extern "C" int mnr_tc_linear_bwd_weight(const mnr_linear_group_t* groups, int n_groups, int M, int act, void* workspace,
+                                        size_t workspace_bytes, mnr_stream_t stream) {
+  ReduceJobs jobs;
+  int rc = dw_launch(groups, n_groups, M, act, workspace, workspace_bytes, true, &jobs.j[0], mnr_cs(stream));
+  if (rc != MNR_OK) return rc;
+  return reduce_launch(jobs, 1, mnr_cs(stream));
+}
+
+extern "C" int mnr_tc_linear_bwd_weight_partials(const mnr_linear_group_t* groups, int n_groups, int M, int act, void* workspace,
+                                                 size_t workspace_bytes, mnr_stream_t stream) {
+  ReduceJob job;
+  return dw_launch(groups, n_groups, M, act, workspace, workspace_bytes, true, &job, mnr_cs(stream));
+}
+
+extern "C" int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs_in, int n_jobs, mnr_stream_t stream) {
+  MNR_CHECK_PTR(jobs_in);
+  if (n_jobs <= 0 || n_jobs > kMaxReduceJobs) return MNR_ESHAPE;
+  ReduceJobs jobs;
+  for (int q = 0; q < n_jobs; ++q) {
+    const mnr_tc_reduce_job_t& in = jobs_in[q];
+    const int rc = dw_launch(in.groups, in.n_groups, in.M, 0, in.workspace, in.workspace_bytes, false, &jobs.j[q], mnr_cs(stream));
+    if (rc != MNR_OK) return rc;
+  }
+  return reduce_launch(jobs, n_jobs, mnr_cs(stream));
 }
 
 extern "C" int mnr_split_tf32(const mnr_split_job_t* jobs, int n_jobs, mnr_stream_t stream) {

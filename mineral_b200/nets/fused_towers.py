@@ -111,8 +111,9 @@ class TowerStack:
                 self.w_hi.append([torch.zeros(w, ld, **f32) for _ in range(G)])
                 self.w_lo.append([torch.zeros(w, ld, **f32) for _ in range(G)])
                 k = w
-            tc_big = max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape) for l in self.lin[0])
-            self.tc_ws = torch.zeros(max(tc_big, 256), dtype=torch.uint8, device=device)
+            # one split-partials workspace per layer: the split reduce of all layers is ONE launch after the last layer
+            self.tc_ws = [torch.zeros(max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape), 256),
+                                      dtype=torch.uint8, device=device) for l in self.lin[0]]
 
     def _split_weights(self):
         """W -> (hi, lo) tf32 parts for every layer of every tower, one launch per 8 matrices."""
@@ -155,6 +156,7 @@ class TowerStack:
         M = self.M if rows is None else rows
         G, top = self.G, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
+        pending = []  # tensor-core dW layers whose split partials still wait for the (single) reduce launch
         for i in range(top, -1, -1):
             n, k = self.lin[0][i].weight.shape
             src = self.Y[i - 1] if i > 0 else [x] * G
@@ -168,7 +170,10 @@ class TowerStack:
             wg = [dict(a=self.dY[i][g], b=src[g], c=self.lin[g][i].weight.grad, saved=saved[g], bias_grad=self.lin[g][i].bias.grad, N=n, K=k,
                        ldb=ldb) for g in range(G)]
             if tc:
-                ops.tc_linear_bwd_weight(wg, M, self.gemm_act, self.tc_ws)
+                pending.append(ops.tc_linear_bwd_weight_partials(wg, M, self.gemm_act, self.tc_ws[i]))
+                if len(pending) == 4:
+                    ops.tc_reduce_partials(pending)
+                    pending = []
             else:
                 ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
             if i > 0:
@@ -178,6 +183,8 @@ class TowerStack:
                 else:
                     ops.linear_bwd_input([dict(a=self.dY[i][g], b=self.lin[g][i].weight.data, c=self.dY[i - 1][g], saved=saved[g], N=n, K=k)
                                           for g in range(G)], M, self.gemm_act)
+        if pending:
+            ops.tc_reduce_partials(pending)
 
 
 def _same_shape(a, v):

@@ -282,6 +282,22 @@ def tc_linear_bwd_weight(groups, M, act, ws):
           "mnr_tc_linear_bwd_weight", kernels=2)
 
 
+def tc_linear_bwd_weight_partials(groups, M, act, ws):
+    """Tensor-core dW / db split partials into `ws` (no reduce); returns the job record for tc_reduce_partials."""
+    arr = _linear_groups(groups)
+    check(lib.mnr_tc_linear_bwd_weight_partials(arr, len(groups), M, act, ptr(ws, U8), ws.numel(), stream()),
+          "mnr_tc_linear_bwd_weight_partials")
+    return (arr, len(groups), M, ws)
+
+
+def tc_reduce_partials(jobs):
+    """One launch: sum the split partials of up to 4 layers (records from tc_linear_bwd_weight_partials)."""
+    arr = (nv.TcReduceJob * len(jobs))()
+    for i, (groups, n_groups, M, ws) in enumerate(jobs):
+        arr[i] = nv.TcReduceJob(groups, n_groups, M, ptr(ws, U8).value, ws.numel())
+    check(lib.mnr_tc_reduce_partials(arr, len(jobs), stream()), "mnr_tc_reduce_partials")
+
+
 def split_tf32(jobs):
     """jobs: list of (src (rows, cols) view with row stride src_ld, hi, lo (rows, dst_ld))."""
     arr = (nv.SplitJob * len(jobs))()

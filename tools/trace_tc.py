@@ -1,28 +1,52 @@
-import sys, ctypes, torch
-sys.path.insert(0, "/root/repo")
-from mineral_b200 import ops
-from mineral_b200._native import lib
-DEV="cuda:0"
-M,N,K=32768,128,256
-g=torch.Generator(device=DEV).manual_seed(0)
-groups=[]
-for t in range(2):
-    x=torch.randn(M,K,device=DEV,generator=g); w=torch.randn(N,K,device=DEV,generator=g)/16; b=torch.randn(N,device=DEV,generator=g)
-    hi=torch.empty(N,K,device=DEV); lo=torch.empty(N,K,device=DEV)
-    ops.split_tf32([(w,hi,lo,N,K,K,K)])
-    groups.append(dict(a=x,b=hi,b_lo=lo,c=torch.empty(M,N,device=DEV),bias=b,N=N,K=K))
-for _ in range(3): ops.tc_linear_fwd(groups,M,1)
-torch.cuda.synchronize()
-lib.mnr_tc_trace(1,None)
-ops.tc_linear_fwd(groups,M,1); torch.cuda.synchronize()
-buf=(ctypes.c_longlong*(4*256*2))()
-lib.mnr_tc_trace(0,buf)
+"""CTA-0 timeline of tc_linear_kernel (debug aid, csrc/tc_linear.cu TC_TRACE): per k-block the TMA issue, converter
+start / end, MMA start / issue-end; per tile the epilogue start / end.  usage: trace_tc.py [fwd|dx] M N K"""
+import ctypes
+import sys
+
 import numpy as np
-tr=np.array(buf[:]).reshape(4,256,2)
-t0=tr[0,0,0]
-def rel(x): return (x-t0)/1.9  # ~ns at 1.9 GHz
+import torch
+
+sys.path.insert(0, "/root/repo")
+from mineral_b200 import ops  # noqa: E402
+from mineral_b200._native import lib  # noqa: E402
+
+DEV = "cuda:0"
+mode = sys.argv[1] if len(sys.argv) > 1 else "fwd"
+M, N, K = (int(v) for v in sys.argv[2:5]) if len(sys.argv) > 4 else (32768, 128, 256)
+g = torch.Generator(device=DEV).manual_seed(0)
+ld = (K + 3) // 4 * 4
+groups = []
+for t in range(2):
+    w = torch.randn(N, K, device=DEV, generator=g) / 16
+    hi, lo = torch.zeros(N, ld, device=DEV), torch.zeros(N, ld, device=DEV)
+    ops.split_tf32([(w, hi, lo, N, K, K, ld)])
+    if mode == "fwd":
+        x = torch.zeros(M, ld, device=DEV)
+        x[:, :K] = torch.randn(M, K, device=DEV, generator=g)
+        groups.append(dict(a=x, b=hi, b_lo=lo, c=torch.empty(M, N, device=DEV), bias=torch.randn(N, device=DEV, generator=g), N=N, K=K, lda=ld, ldb=ld))
+    else:
+        dy, y = torch.randn(M, N, device=DEV, generator=g), torch.randn(M, N, device=DEV, generator=g)
+        groups.append(dict(a=dy, saved=y, b=hi, b_lo=lo, c=torch.empty(M, ld, device=DEV), N=N, K=ld, ldb=ld))
+run = (lambda: ops.tc_linear_fwd(groups, M, 1)) if mode == "fwd" else (lambda: ops.tc_linear_bwd_input(groups, M, 1))
+for _ in range(3):
+    run()
+torch.cuda.synchronize()
+lib.mnr_tc_trace(1, None)
+run()
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * (4 * 256 * 2))()
+lib.mnr_tc_trace(0, buf)
+tr = np.array(buf[:]).reshape(4, 256, 2)
+t0 = tr[0, 0, 0]
+rel = lambda x: (x - t0) / 1.9  # ~ns at 1.9 GHz
+print(f"{mode} M={M} N={N} K={K}")
 print("kb : prod_issue | conv_start conv_done | mma_start mma_issued   (ns from first TMA issue)")
-for kb in range(34):
+for kb in range(40):
+    if tr[2, kb, 1] <= 0:
+        break
     print(f"{kb:3d}: {rel(tr[0,kb,0]):8.0f} | {rel(tr[1,kb,0]):8.0f} {rel(tr[1,kb,1]):8.0f} | {rel(tr[2,kb,0]):8.0f} {rel(tr[2,kb,1]):8.0f}")
 print("tile: epi_start epi_done")
-for it in range(5): print(it, f"{rel(tr[3,it,0]):8.0f} {rel(tr[3,it,1]):8.0f}")
+for it in range(16):
+    if tr[3, it, 1] <= 0:
+        break
+    print(it, f"{rel(tr[3,it,0]):8.0f} {rel(tr[3,it,1]):8.0f}")
