@@ -22,7 +22,8 @@
 namespace {
 using namespace mnr_loss;
 
-constexpr int kRows = 128;  // rows per tile == threads per CTA
+constexpr int kRows = 128;     // rows per tile
+constexpr int kThreadsHF = 256;  // 2 threads per row: thread (r, h) takes the float4 columns c = h, h + 2, ... of row r
 
 struct FusedHeadsArgs {
   const float *y3a, *y3v;                // (M,H)
@@ -47,21 +48,25 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 }
 
 // A, H compile-time (no guards in the unrolled dot products); one shared-memory tile buffer serves the actor tower
-// and then the value tower of the same 128 rows, so a CTA needs ~55 KB and 4 CTAs share an SM.
+// and then the value tower of the same 128 rows, so a CTA needs ~58 KB and 3 CTAs (24 warps) share an SM.  The kernel is
+// bound by per-thread instruction latency (every instruction runs once or twice per warp), hence TWO threads per row:
+// each takes every other float4 column of the row in the dot-product / dY3 sweeps and every other action column in the
+// loss loops; partial sums meet through one __shfl_xor.
 template <int A, int H, bool LEARNED>
-__global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constant__ FusedHeadsArgs a,
+__global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid_constant__ FusedHeadsArgs a,
                                                             const __grid_constant__ mnr_ppo_loss_cfg_t cfg) {
-  constexpr int P = H + 4, P4 = P / 4, H4 = H / 4;
+  constexpr int P = H + 8, P4 = P / 4, H4 = H / 4;  // pitch == 8 (mod 32): the 4 rows x 2 halves of an LDS.128 phase never collide
   constexpr int NY = (LEARNED ? 2 : 1) * A;          // gradient rows fed by Y3a: g_mu | g_ls
   constexpr int GP = 4 * A + 4;                      // s_g pitch: g_mu | g_ls | mu | sigma | g_v | pad  (float4-aligned groups,
                                                      // GP mod 32 == 4 or 20: "thread = row" float4 accesses are conflict-free)
   constexpr int GW = 4 * A + 1;                      // columns that get summed over rows
   constexpr int UV = NY * 4 <= 64 ? 4 : 2;           // hidden columns per thread in the weight-gradient phase
-  constexpr int HU = H / UV, NRG = kRows / HU, RPG = kRows / NRG;  // threads per row group, row groups, rows per group
-  static_assert(A % 4 == 0 && A <= 16 && NRG >= 1 && NY * UV <= 64, "unsupported head shape");
+  constexpr int HU = H / UV, NRG = kThreadsHF / HU, RPG = kRows / NRG;  // threads per row group, row groups, rows per group
+  constexpr int kWarpsHF = kThreadsHF / 32;
+  static_assert(A % 4 == 0 && A <= 16 && NRG >= 1 && RPG >= 1 && NY * UV <= 64, "unsupported head shape");
   extern __shared__ __align__(16) float sh[];
-  __shared__ double s_red[6][kRows / 32];
-  __shared__ mnr::Moments s_mom[2][kRows / 32];
+  __shared__ double s_red[6][kWarpsHF];
+  __shared__ mnr::Moments s_mom[2][kWarpsHF];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a, then Y3v tile, then dY3v
   float* s_wmu = s_y + kRows * P;                    // (A,H)
@@ -69,11 +74,11 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   float* s_wv = s_wsig + (LEARNED ? A * H : 0);      // (H)
   float* s_g = s_wv + H;                             // [128][GP]
 
-  for (int i = tid; i < A * H; i += kRows) {
+  for (int i = tid; i < A * H; i += kThreadsHF) {
     s_wmu[i] = __ldg(a.w_mu + i);
     if (LEARNED) s_wsig[i] = __ldg(a.w_sig + i);
   }
-  for (int i = tid; i < H; i += kRows) s_wv[i] = __ldg(a.w_v + i);
+  for (int i = tid; i < H; i += kThreadsHF) s_wv[i] = __ldg(a.w_v + i);
   float b_mu[A], b_sig[A];
 #pragma unroll
   for (int j = 0; j < A; ++j) b_mu[j] = __ldg(a.b_mu + j), b_sig[j] = __ldg(a.b_sig + j);
@@ -102,7 +107,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kRows;
     const int rows_here = (int)min((int64_t)kRows, a.M - row0);
-    const int r = tid;
+    const int r = tid >> 1, h = tid & 1;
     const bool valid = r < rows_here;
     const int64_t row = valid ? row0 + r : a.M - 1;
     float* grow = s_g + r * GP;
@@ -112,18 +117,18 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     {
       const float4* gy = reinterpret_cast<const float4*>(a.y3a);
 #pragma unroll 8
-      for (int i = tid; i < kRows * H4; i += kRows) {
+      for (int i = tid; i < kRows * H4; i += kThreadsHF) {
         const int rr = i / H4, c = i - rr * H4;
         s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     __syncthreads();
-    // ---- thread = row: mu / logstd heads -------------------------------------------------------------
+    // ---- thread = (row, half): mu / logstd heads ------------------------------------------------------------
     float mu_raw[A], ls[A];
 #pragma unroll
     for (int j = 0; j < A; ++j) mu_raw[j] = 0.f, ls[j] = 0.f;
 #pragma unroll 2
-    for (int c = 0; c < H4; ++c) {
+    for (int c = h; c < H4; c += 2) {
       const float4 ya = s_y4[r * P4 + c];
 #pragma unroll
       for (int j = 0; j < A; ++j) {
@@ -131,16 +136,21 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
         if (LEARNED) ls[j] = dot4(ya, s_wsig4[j * H4 + c], ls[j]);
       }
     }
-    // ---- per-element loss terms.  ROLLED loops over the action columns with the row's values parked in its own s_g
-    //      row (slots [0,A) raw mu, [A,2A) raw logstd -> later g_mu, g_ls; [2A,3A) mu; [3A,4A) sigma): keeps the
-    //      transcendental-heavy body in the code once instead of A times (the kernel runs each instruction only a few
-    //      times per warp, so instruction-cache misses were a top stall) and frees ~100 registers.
 #pragma unroll
-    for (int j = 0; j < A; ++j) grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
+    for (int j = 0; j < A; ++j) {
+      mu_raw[j] += __shfl_xor_sync(0xffffffffu, mu_raw[j], 1);
+      if (LEARNED) ls[j] += __shfl_xor_sync(0xffffffffu, ls[j], 1);
+    }
+    // ---- per-element loss terms.  ROLLED loops over the action columns (half h takes j = h, h + 2, ..) with the row's
+    //      values parked in its own s_g row (slots [0,A) raw mu, [A,2A) raw logstd -> later g_mu, g_ls; [2A,3A) mu;
+    //      [3A,4A) sigma): keeps the transcendental-heavy body in the code once instead of A times.
+#pragma unroll
+    for (int j = 0; j < A; ++j)
+      if ((j & 1) == h) grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
     float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
     const float* act_row = a.actions + (size_t)row * A;
 #pragma unroll 1
-    for (int j = 0; j < A; ++j) {
+    for (int j = h; j < A; j += 2) {
       float mu, sg, dmu, dsg, db;
       dist_fwd(cfg, grow[j], grow[A + j], mu, sg, dmu, dsg);
       const float diff = __ldg(act_row + j) - mu;
@@ -151,13 +161,15 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
       kl += kl_elem(mu, sg, a.old_mu[(size_t)row * A + j], a.old_sigma[(size_t)row * A + j]);
       grow[2 * A + j] = mu, grow[3 * A + j] = sg;
     }
+    nlp += __shfl_xor_sync(0xffffffffu, nlp, 1), ent += __shfl_xor_sync(0xffffffffu, ent, 1);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 1), kl += __shfl_xor_sync(0xffffffffu, kl, 1);
     float dl_dnlp, clipped;
     const float a_loss = actor_row(__ldg(a.old_nlp + row), nlp, __ldg(a.adv + row), cfg.e_clip, cfg.use_smooth_clamp, &dl_dnlp, &clipped);
-    if (valid) t_a += a_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
+    if (valid && h == 0) t_a += a_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
     const float g_nlp = w * dl_dnlp;
     const float span = cfg.maxstd - cfg.minstd;
 #pragma unroll 1
-    for (int j = 0; j < A; ++j) {
+    for (int j = h; j < A; j += 2) {
       const float mu = grow[2 * A + j], sg = grow[3 * A + j];
       const float diff = __ldg(act_row + j) - mu;
       float dmu = 1.f, dsg = sg;                                  // d mu / d mu_raw, d sigma / d logstd (dist.py:32-47)
@@ -174,9 +186,11 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
       grow[j] = gm, grow[A + j] = gl;
       if (!valid) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;
     }
-    if (valid) {  // row-contiguous float4 copies of the finished row pieces
+    __syncwarp();  // the pair's halves of the row are both in shared memory now
+    if (valid) {  // row-contiguous float4 copies of the finished row pieces (half h takes every other piece)
 #pragma unroll
       for (int j4 = 0; j4 < A / 4; ++j4) {
+        if ((j4 & 1) != h) continue;
         const float4 gm4 = reinterpret_cast<const float4*>(grow)[j4], gl4 = reinterpret_cast<const float4*>(grow + A)[j4];
         if (a.g_mu) reinterpret_cast<float4*>(a.g_mu + (size_t)row * A)[j4] = gm4;
         if (a.g_ls) reinterpret_cast<float4*>(a.g_ls + (size_t)row * A)[j4] = gl4;
@@ -211,13 +225,13 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
       }
     }
     __syncthreads();
-    // ---- thread = row: dY3a = g_mu Wmu + g_ls Wsig over the tile in place, then coalesced stores ------------------------
+    // ---- thread = (row, half): dY3a = g_mu Wmu + g_ls Wsig over the tile in place, then coalesced stores --------------
     {
       float gm[A], gl[A];
 #pragma unroll
       for (int j = 0; j < A; ++j) gm[j] = grow[j], gl[j] = LEARNED ? grow[A + j] : 0.f;
 #pragma unroll 2
-      for (int c = 0; c < H4; ++c) {
+      for (int c = h; c < H4; c += 2) {
         float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < A; ++j) {
@@ -236,7 +250,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
       float4* oa = reinterpret_cast<float4*>(a.dy3a);
       const float4* gy = reinterpret_cast<const float4*>(a.y3v);
 #pragma unroll 8
-      for (int i = tid; i < kRows * H4; i += kRows) {  // dY3a out, Y3v in: every thread reuses exactly the slots it just read
+      for (int i = tid; i < kRows * H4; i += kThreadsHF) {  // dY3a out, Y3v in: every thread reuses exactly the slots it just read
         const int rr = i / H4, c = i - rr * H4;
         if (rr < rows_here) oa[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
         s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -246,18 +260,19 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     // =========================== value tower ===========================================================
     float value = 0.f;
 #pragma unroll 4
-    for (int c = 0; c < H4; ++c) value = dot4(s_y4[r * P4 + c], s_wv4[c], value);
+    for (int c = h; c < H4; c += 2) value = dot4(s_y4[r * P4 + c], s_wv4[c], value);
+    value += __shfl_xor_sync(0xffffffffu, value, 1);
     value += b_v;
     float dl_dv;
     const float ret = __ldg(a.returns + row);
     const float c_loss = critic_row(__ldg(a.old_values + row), value, ret, cfg.e_clip, cfg.clip_value_loss, &dl_dv);
     const float g_v = valid ? w * 0.5f * cfg.critic_coef * dl_dv : 0.f;
-    if (valid) {
+    if (valid && h == 0) {
       t_c += c_loss;
       w_d.push(ret - value), w_ret.push(ret);
       if (a.g_v) a.g_v[row] = g_v;
     }
-    grow[4 * A] = g_v;
+    if (h == 0) grow[4 * A] = g_v;
     __syncthreads();
 #pragma unroll 4
     for (int k = 0; k < RPG; ++k) {
@@ -279,7 +294,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     }
     __syncthreads();
 #pragma unroll 4
-    for (int c = 0; c < H4; ++c) {
+    for (int c = h; c < H4; c += 2) {
       const float4 wv = s_wv4[c];
       s_y4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
     }
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     {
       float4* ov = reinterpret_cast<float4*>(a.dy3v);
 #pragma unroll 8
-      for (int i = tid; i < kRows * H4; i += kRows) {
+      for (int i = tid; i < kRows * H4; i += kThreadsHF) {
         const int rr = i / H4, c = i - rr * H4;
         if (rr < rows_here) ov[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
       }
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     }
   }
   if (!LEARNED)  // sigma rows of the layout stay defined
-    for (int i = tid; i < A * H; i += kRows) part[A * H + i] = 0.f;
+    for (int i = tid; i < A * H; i += kThreadsHF) part[A * H + i] = 0.f;
   if (tid < GW) part[(2 * A + 1) * H + tid] = acc_col;
 
   float vals[6] = {t_a, t_c, t_b, t_h, t_clip, t_kl};
@@ -333,11 +348,11 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
     double ac[6];
     for (int k = 0; k < 6; ++k) {
       ac[k] = 0;
-      for (int x = 0; x < kRows / 32; ++x) ac[k] += s_red[k][x];
+      for (int x = 0; x < kWarpsHF; ++x) ac[k] += s_red[k][x];
     }
     p.a = ac[0], p.c = ac[1], p.b = ac[2], p.h = ac[3], p.clip = ac[4], p.kl = ac[5];
     p.d = s_mom[0][0], p.ret = s_mom[1][0];
-    for (int x = 1; x < kRows / 32; ++x) p.d = mnr::moments_merge(p.d, s_mom[0][x]), p.ret = mnr::moments_merge(p.ret, s_mom[1][x]);
+    for (int x = 1; x < kWarpsHF; ++x) p.d = mnr::moments_merge(p.d, s_mom[0][x]), p.ret = mnr::moments_merge(p.ret, s_mom[1][x]);
     a.loss_parts[blockIdx.x] = p;
   }
 
@@ -345,7 +360,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
 
   // ---- every CTA reduces its share of the PW outputs over all CTAs (warp per output, fixed order) ----------------
   const int n_cta = gridDim.x;
-  for (int o = blockIdx.x * (kRows / 32) + warp; o < PW; o += n_cta * (kRows / 32)) {
+  for (int o = blockIdx.x * kWarpsHF + warp; o < PW; o += n_cta * kWarpsHF) {
     float sum = 0.f;
     for (int x = lane; x < n_cta; x += 32) sum += __ldcg(a.partials + (size_t)x * PW + o);
 #pragma unroll
@@ -371,7 +386,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
   // ---- CTA 0: the ten loss metrics ---------------------------------------------------------------------------------
   double acc2[6] = {0, 0, 0, 0, 0, 0};
   mnr::Moments md2{0, 0, 0}, mr2{0, 0, 0};
-  for (int x = tid; x < n_cta; x += kRows) {
+  for (int x = tid; x < n_cta; x += kThreadsHF) {
     const LossPartial p = a.loss_parts[x];
     acc2[0] += p.a, acc2[1] += p.c, acc2[2] += p.b, acc2[3] += p.h, acc2[4] += p.clip, acc2[5] += p.kl;
     md2 = mnr::moments_merge(md2, p.d), mr2 = mnr::moments_merge(mr2, p.ret);
@@ -397,7 +412,7 @@ __global__ void __launch_bounds__(kRows) heads_fused_kernel(const __grid_constan
 
 template <int A, int H, bool LEARNED>
 size_t fused_smem_bytes() {
-  return (size_t)(kRows * (H + 4) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
+  return (size_t)(kRows * (H + 8) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
 }
 
 template <int A, int H, bool LEARNED>
@@ -409,7 +424,7 @@ int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap,
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int occ = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kRows, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreadsHF, smem);
     if (e != cudaSuccess) return (int)e;
     if (occ < 1) return MNR_EUNSUP;
     occ_cached = occ;
@@ -417,7 +432,7 @@ int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap,
   int grid = mnr_sm_count() * occ_cached;  // every CTA resident: the grid barrier needs it
   if (grid > grid_cap) grid = grid_cap;
   if (grid > a.n_tiles) grid = a.n_tiles;
-  kern<<<grid, kRows, smem, stream>>>(a, cfg);
+  kern<<<grid, kThreadsHF, smem, stream>>>(a, cfg);
   const cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? MNR_OK : (int)e;
 }
