@@ -404,7 +404,7 @@ def main():
 
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only (the reference arm covers every N)
         cores = torch.get_num_threads()
         ws, _ = shrink_for_cpu(w)
         times = time_oracle(ws, 3, 1, budget_s=45)
