@@ -30,6 +30,8 @@ WORKLOADS = {
     "ppo_ant_4096x32_yaml": dict(T=32, N=4096, O=37, A=8, units=[512, 256, 128], variant="ln_silu_dreamer_learned", minibatches=64, mini_epochs=5),
     # BASELINE.json configs[4] per-GPU shape
     "ppo_allegro_16384x16": dict(T=16, N=16384, O=88, A=16, units=[512, 256, 128], variant="ln_silu_dreamer_learned", minibatches=8, mini_epochs=5),
+    # Humanoid-shaped rollout (BASELINE.json configs[2] shape: obs 76, act 21) through the PPO update
+    "ppo_humanoid_4096x32": dict(T=32, N=4096, O=76, A=21, units=[256, 128, 64], variant="elu_normal_fixed", minibatches=4, mini_epochs=5),
     "ppo_ant_64x32": dict(T=32, N=64, O=37, A=8, units=[256, 128, 64], variant="elu_normal_fixed", minibatches=4, mini_epochs=5),
 }
 
@@ -341,11 +343,49 @@ def main():
             ts.append(a.elapsed_time(b))
         return statistics.mean(sorted(ts)[: max(1, len(ts) * 3 // 4)])
 
-    k_ms = time_fused(agent)
+    k_ms_single = time_fused(agent)
+
+    def time_fused_rotating(n_buf=4, n_launch=24):
+        """Average launch duration over back-to-back launches that rotate over `n_buf` rollouts (n_buf x (in + out) =
+        4 x 69 MB at cfg2 > 126 MB L2, so every launch finds its inputs evicted): one event pair around the whole batch,
+        so the ~5 us of event-record + launch latency that a single 15 us launch carries is amortised."""
+        from mineral_b200.agents.ppo.experience import ExperienceBuffer
+        bufs = [agent.storage]
+        for _ in range(n_buf - 1):
+            b = ExperienceBuffer(N, T, B, B // w["minibatches"], {"obs": (O,)}, A, dev)
+            for k, v in agent.storage.storage_dict.items():
+                if isinstance(v, dict):
+                    for kk, vv in v.items():
+                        b.storage_dict[k][kk].copy_(vv)
+                else:
+                    b.storage_dict[k].copy_(v)
+            bufs.append(b)
+        for b in bufs:
+            b._launch_fused_only(dev_last, agent.gamma, agent.tau)
+        ts = []
+        for _ in range(5):
+            flush.zero_()
+            torch.cuda._sleep(4_000_000)  # ~2 ms: the CPU enqueues the whole batch behind this spin
+            a, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for i in range(n_launch):
+                bufs[i % n_buf]._launch_fused_only(dev_last, agent.gamma, agent.tau)
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(e) / n_launch)
+        return statistics.median(ts)
+
+    k_ms = time_fused_rotating()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     roofline = {"kernel": "post_rollout_kernel<true> (GAE + env-major pack + moment partials)", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes": alg_bytes, "launch_ms": k_ms, "timing": "CUDA events on the launching stream, L2 flushed before each launch"}
+                "algorithmic_bytes": alg_bytes, "launch_ms": k_ms,
+                "timing": "CUDA events on the launching stream around 24 back-to-back launches rotating over 4 rollouts (276 MB > L2: "
+                          "every launch reads cold inputs); average per launch",
+                "single_launch": {"launch_ms": k_ms_single, "achieved": alg_bytes / (k_ms_single * 1e-3) / 1e9,
+                                  "frac": alg_bytes / (k_ms_single * 1e-3) / 1e9 / peak,
+                                  "timing": "one launch per event pair, L2 flushed before it: includes ~5 us of event-record and "
+                                            "launch latency (an empty launch of the same grid measures 6.2 us this way)"}}
     # traffic of the same kernel from the committed ncu --set full capture (profiles/), per launch
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "post_rollout_traffic.json")))

@@ -91,6 +91,7 @@ struct Params {
   int T, N, do_gae;
   float gamma, gamma_tau;
   unsigned char* workspace;
+  int debug_skip;  // tuning aid (MNR_POST_ROLLOUT_SKIP): bit 0 skips the scalar role, bit 1 the wide role
 };
 
 constexpr int kEnvPerScalarCta = 32;  // the staging loops below use q >> 5 / q & 31
@@ -239,8 +240,11 @@ __global__ void __launch_bounds__(kThreads, 6) post_rollout_kernel(const __grid_
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar;
   float* smem = reinterpret_cast<float*>(smem_raw);
-  if ((int)blockIdx.x < p.n_scalar) scalar_role(p, smem);
-  else wide_role<kBulk>(p, smem, &bar);
+  if ((int)blockIdx.x < p.n_scalar) {
+    if (!(p.debug_skip & 1)) scalar_role(p, smem);
+  } else if (!(p.debug_skip & 2)) {
+    wide_role<kBulk>(p, smem, &bar);
+  }
 }
 
 // ---- finalize: merge partials (fixed order), derive the 6 normalisation scalars, update value RMS ---
@@ -430,6 +434,8 @@ extern "C" int mnr_post_rollout_fused(const mnr_wide_field_t* wide, int n_wide, 
   p.neglogp_em = neglogp_em, p.adv_em = adv_em, p.dones_em = dones_em;
   p.T = T, p.N = N, p.do_gae = do_gae, p.gamma = gamma, p.gamma_tau = gamma_tau;
   p.workspace = (unsigned char*)workspace;
+  p.debug_skip = 0;
+  if (const char* e = getenv("MNR_POST_ROLLOUT_SKIP")) p.debug_skip = atoi(e);
 
   const int grid = pl.n_scalar + pl.item0[n_wide];
   cudaError_t e;

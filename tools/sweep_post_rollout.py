@@ -20,7 +20,8 @@ if len(sys.argv) > 1:
     byts = row * N * T + 4 * N + (row + 8) * N * T
     print(f"N={N} tile_kb={os.environ.get('MNR_POST_ROLLOUT_TILE_KB')} min_copy={os.environ.get('MNR_POST_ROLLOUT_MIN_COPY')} {m*1e3:.2f} us {byts/m/1e6:.0f} GB/s frac {byts/m/1e6/6532.9:.3f}", flush=True)
 else:
-    for n in (4096, 16384):
-        for kb, mc in ((40, 1024), (32, 1024), (24, 1024), (20, 512), (16, 512), (56, 1024), (56, 2048), (76, 2048), (110, 2048)):
-            env = dict(os.environ, MNR_POST_ROLLOUT_TILE_KB=str(kb), MNR_POST_ROLLOUT_MIN_COPY=str(mc))
+    for n in (4096, 8192, 16384):
+        for skip in (0, 1, 2, 3):
+            env = dict(os.environ, MNR_POST_ROLLOUT_SKIP=str(skip))
+            print(f"skip={skip} (1: no scalar role, 2: no wide role, 3: empty kernel)", end=" ", flush=True)
             subprocess.run([sys.executable, __file__, str(n)], env=env)
