@@ -527,6 +527,27 @@ int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm /*host*/, size_t grad_
                               mnr_optim_state_t* st, float* tail_out, int kl_index, float* grad_norm_out,
                               void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * 8(f)-1  rollout-side policy step (between two simulator steps).  mnr_policy_step: policy / value heads on the
+ *      towers' last activations y3a / y3v (N,H) (weights as in mnr_ppo_heads_loss_fwd_bwd), Dist
+ *      (mineral/nets/dist.py:31-47), actions = mu + sigma * eps (Normal.sample, eps (N,A) standard normal noise
+ *      drawn by the caller), neglogp = -sum_j log_prob (ActorCritic.act, mineral/agents/ppo/models.py:117-133),
+ *      values un-normalised with the prepared f32 (mean, denom) of the value RunningMeanStd
+ *      (PPO.model_act, mineral/agents/ppo/ppo.py:125-131; NULL,NULL: left normalised; clamp_lo > clamp_hi: no clamp)
+ *      - all written straight into the time-major storage rows of step t (replaces 5 update_data copies,
+ *      ppo.py:146-150) plus the clamped actions the simulator consumes (ppo.py:151, may be NULL).
+ *      mnr_post_step: rewards_t = scale * r (+ gamma * values_t * time_out, ppo.py:158-160), dones_t = dones
+ *      (u8 / bool in, u8 out; ppo.py:154,161).  A <= 32, H <= 512.
+ * ------------------------------------------------------------------------------------ */
+int mnr_policy_step(const float* y3a, const float* y3v, const float* w_mu, const float* b_mu, const float* w_v,
+                    const float* b_v, const float* w_sig, const float* b_sig, const float* eps,
+                    const float* value_mean_f32, const float* value_denom_f32, float clamp_lo, float clamp_hi,
+                    float* actions_t, float* neglogp_t, float* values_t, float* mu_t, float* sigma_t,
+                    float* actions_clamped, int N, int A, int H, const mnr_ppo_loss_cfg_t* cfg /*host*/,
+                    mnr_stream_t stream);
+int mnr_post_step(const float* rewards, const void* dones, const void* time_outs, const float* values_t,
+                  float reward_scale, float gamma, float* rewards_t, uint8_t* dones_t, int N, mnr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

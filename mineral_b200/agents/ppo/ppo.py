@@ -232,6 +232,7 @@ class PPO(Agent):
         self.reward_shaper = RewardShaper(**cfg['reward_shaper'])
 
         self._engine = None
+        self._rollout = None
         self.use_cuda_graph = bool(cfg_get(cfg, 'cuda_graph', False))
 
     # -------------------------------------------------------------------------------------------
@@ -246,8 +247,14 @@ class PPO(Agent):
 
     @torch.no_grad()
     def play_steps(self):
-        """ppo.py:133-183.  The rollout loop is the reference's (simulator-bound, SURVEY.md section 8f
-        row 1 is the next step); its tail is the fused post-rollout pass."""
+        """ppo.py:133-183.  Agent side of every env step on our kernels when the network allows it (`_RolloutEngine`:
+        obs normalise -> tower GEMMs -> one policy-step kernel writing into the storage rows -> env.step -> one
+        post-step kernel), else the reference's torch op sequence; the tail is the fused
+        post-rollout pass either way."""
+        if self._rollout is None and cfg_get(self.ppo_config, 'fused_rollout', True) and _RolloutEngine.supported(self):
+            self._rollout = _RolloutEngine(self)
+        if self._rollout is not None:
+            return self._play_steps_fused()
         for n in range(self.horizon_len):
             if not self.env_autoresets and any(self.dones):
                 done_indices = torch.where(self.dones)[0].tolist()
@@ -275,6 +282,27 @@ class PPO(Agent):
 
         last_values = self.model_act(self.obs)['values']
         self.finish_rollout(last_values)
+
+    @torch.no_grad()
+    def _play_steps_fused(self):
+        ro = self._rollout
+        ro.begin_rollout()
+        for n in range(self.horizon_len):
+            if not self.env_autoresets and any(self.dones):
+                done_indices = torch.where(self.dones)[0].tolist()
+                obs_reset = self._convert_obs(self.env.reset_idx(done_indices))
+                for k, v in obs_reset.items():
+                    self.obs[k][done_indices] = v
+            self.storage.update_data('obses', n, self.obs)      # a contiguous device copy (plumbing)
+            actions = ro.act(n, self.obs)                          # heads / sample / neglogp / values -> storage rows of step n
+            obs, r, self.dones, infos = self.env.step(actions)
+            self.obs = self._convert_obs(obs)
+            r, self.dones = torch.as_tensor(r, device=self.device), torch.as_tensor(self.dones, device=self.device)
+            ro.after_env_step(n, r, self.dones, infos)             # shaped reward (+ time-out bootstrap), dones -> storage rows
+            done_indices = torch.where(self.dones)[0].tolist()
+            self.metrics.update(self.epoch, self.env, self.obs, r.reshape(-1), done_indices, infos)
+        self.metrics.flush_video(self.epoch)
+        self.finish_rollout(ro.values_only(self.obs))
 
     @torch.no_grad()
     def finish_rollout(self, last_values):
@@ -352,6 +380,95 @@ class PPO(Agent):
             else:
                 setattr(self, k, ckpt[k])
         self.last_lr = self.optim.param_groups[0]['lr']
+
+
+class _RolloutEngine:
+    """Agent side of one env step (ppo.py:144-163 minus env.step and the host-side episode metrics) on our kernels:
+    `mnr_rms_apply_ld_f32` (obs normalise) -> tower GEMMs (`TowerStack.forward`, hi / lo weights split once per rollout) ->
+    `mnr_policy_step` -> [env.step] -> `mnr_post_step`.  ~7 launches per env step instead of ~50 torch ops."""
+
+    @staticmethod
+    def supported(agent):
+        from ...nets.fused_towers import FusedTowers
+        return (FusedTowers.supported(agent.model) and list(agent.obs_space) == ['obs'] and len(agent.obs_space['obs']) == 1 and
+                agent.action_dim <= 32 and agent.model.mu.weight.shape[1] <= 512 and agent.reward_shaper.fn == 'scale')
+
+    def __init__(self, agent):
+        from ...nets.fused_towers import FusedTowers
+        a = self.a = agent
+        dev, N, A = a.device, a.num_actors, a.action_dim
+        self.N, self.A = N, A
+        self.towers = FusedTowers(a.model, N, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.in_dim = a.obs_space['obs'][0]
+        self.x_ld = (self.in_dim + 3) // 4 * 4
+        self.x = torch.zeros(N, self.x_ld, **f32)       # normalised obs, TMA-friendly row stride (pad columns stay zero)
+        self.eps = torch.empty(N, A, **f32)
+        self.clamped = torch.empty(N, A, **f32)
+        self.scratch = [torch.empty(N, A, **f32) for _ in range(3)] + [torch.empty(N, **f32)]   # values_only() sinks
+        self.last_values = torch.empty(N, 1, **f32)
+        dk = a.model.dist
+        self.cfg = ops.make_loss_cfg(dist_type=dk.dist_type, minstd=dk.minstd, maxstd=dk.maxstd)
+        self.eps_source = None   # tests inject recorded noise: callable(step) -> (N, A) tensor; default torch's generator
+
+    def begin_rollout(self):
+        a = self.a
+        self.obs_tab = a.obs_rms['obs']._prepare() if (a.normalize_input and hasattr(a.obs_rms['obs'], 'running_mean')) else None
+        self.val_tab = a.value_rms._prepare() if a.normalize_value else (None, None)
+        st = self.towers.stack
+        if st.use_tc:
+            st._split_weights()    # the weights are frozen for the whole rollout
+
+    def _forward(self, obs):
+        a, tw = self.a, self.towers
+        o = obs['obs']
+        if self.obs_tab is not None:
+            rms = a.obs_rms['obs']
+            ops.rms_apply_ld(o.contiguous(), self.obs_tab[0], self.obs_tab[1], tuple(rms.clamp_range) if rms.with_clamp else None,
+                             self.x, self.x_ld)
+        else:
+            self.x[:, :self.in_dim].copy_(o)
+        tw.stack.forward(self.x, self.x_ld, rows=self.N, split=False)
+
+    def _policy(self, eps, actions, neglogp, values, mu, sigma, clamped):
+        a, m, tw = self.a, self.a.model, self.towers
+        fixed = m.fixed_sigma
+        clamp = tuple(a.value_rms.clamp_range) if (a.normalize_value and a.value_rms.with_clamp) else None
+        ops.policy_step(tw.Y[-1][0], tw.Y[-1][1], m.mu.weight.data, m.mu.bias.data, m.value.weight.data, m.value.bias.data,
+                        None if fixed else m.sigma.weight.data, m.sigma.data if fixed else m.sigma.bias.data, eps,
+                        self.val_tab[0], self.val_tab[1], clamp, actions, neglogp, values, mu, sigma, clamped, self.cfg, rows=self.N)
+
+    def act(self, t, obs):
+        sd = self.a.storage.storage_dict
+        self._forward(obs)
+        if self.eps_source is not None:
+            self.eps.copy_(self.eps_source(t))
+        else:
+            self.eps.normal_()   # the reference's Normal.sample() draws the same way: randn, then * sigma + mu
+        self._policy(self.eps, sd['actions'][t], sd['neglogp'][t], sd['values'][t].view(-1), sd['mu'][t], sd['sigma'][t], self.clamped)
+        return self.clamped
+
+    def after_env_step(self, t, rewards, dones, infos):
+        a = self.a
+        sd = a.storage.storage_dict
+        tout = None
+        if a.value_bootstrap and 'time_outs' in infos:
+            tout = torch.as_tensor(infos['time_outs'], device=a.device).reshape(-1).contiguous()
+            if tout.dtype not in (torch.bool, torch.uint8):
+                tout = tout != 0
+        d = dones.reshape(-1).contiguous()
+        if d.dtype not in (torch.bool, torch.uint8):
+            d = d != 0
+        ops.post_step(rewards.reshape(-1).float().contiguous(), d, tout, sd['values'][t].view(-1), float(a.reward_shaper.scale), float(a.gamma),
+                      sd['rewards'][t].view(-1), sd['dones'][t])
+
+    def values_only(self, obs):
+        """Bootstrap values of the final observation (ppo.py:169-171): same kernels, the other outputs go to scratch."""
+        self._forward(obs)
+        self.eps.zero_()
+        s = self.scratch
+        self._policy(self.eps, s[0], s[3], self.last_values.view(-1), s[1], s[2], None)
+        return self.last_values
 
 
 class _UpdateEngine:

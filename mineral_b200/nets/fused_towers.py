@@ -125,14 +125,15 @@ class TowerStack:
         for s in range(0, len(jobs), 8):
             ops.split_tf32(jobs[s:s + 8])
 
-    def forward(self, x, x_ld=None, rows=None):
-        """x (rows, in_dim) [row stride x_ld floats] -> self.Y[-1][g] for every tower g."""
+    def forward(self, x, x_ld=None, rows=None, split=True):
+        """x (rows, in_dim) [row stride x_ld floats] -> self.Y[-1][g] for every tower g.  split=False: the hi / lo weight
+        copies are current (the weights did not change since the last forward, e.g. inside a rollout)."""
         M = self.M if rows is None else rows
         G = self.G
         x_ld = self.in_dim if x_ld is None else x_ld
         self._x_ld = x_ld
         tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
-        if self.use_tc:
+        if self.use_tc and split:
             self._split_weights()
         inp = [x] * G
         for i in range(self.L):

@@ -406,3 +406,27 @@ def critic_mse_fwd_bwd(preds, target, grads, loss_out, ws):
 def kl_lr_update(st, kl_threshold, min_lr, max_lr, avg_kl_out=None, lr_out=None):
     check(lib.mnr_kl_lr_update(ptr(st, U8), kl_threshold, min_lr, max_lr, ptr(avg_kl_out, F32, allow_none=True),
                                ptr(lr_out, F64, allow_none=True), stream()), "mnr_kl_lr_update")
+
+
+# ---------------------------------------------------------------------------------------------
+# 8(f)-1  rollout-side policy step
+# ---------------------------------------------------------------------------------------------
+def policy_step(y3a, y3v, w_mu, b_mu, w_v, b_v, w_sig, b_sig, eps, value_mean, value_denom, clamp, actions_t, neglogp_t, values_t,
+                mu_t, sigma_t, actions_clamped, cfg, rows=None):
+    """Heads + Dist + sample + neglogp + value un-normalise into the storage rows of one rollout step (csrc/rollout.cu)."""
+    N = eps.shape[0] if rows is None else rows
+    A, H = w_mu.shape
+    lo, hi = clamp if clamp is not None else (1.0, -1.0)
+    o = lambda t: ptr(t, F32, allow_none=True)
+    check(lib.mnr_policy_step(ptr(y3a, F32, "y3a"), ptr(y3v, F32, "y3v"), ptr(w_mu, F32), ptr(b_mu, F32), ptr(w_v, F32), ptr(b_v, F32),
+                              o(w_sig), ptr(b_sig, F32), ptr(eps, F32, "eps"), o(value_mean), o(value_denom), lo, hi,
+                              ptr(actions_t, F32), ptr(neglogp_t, F32), ptr(values_t, F32), ptr(mu_t, F32), ptr(sigma_t, F32),
+                              o(actions_clamped), N, A, H, C.byref(cfg), stream()), "mnr_policy_step")
+
+
+def post_step(rewards, dones, time_outs, values_t, scale, gamma, rewards_t, dones_t):
+    """Shaped reward (+ time-out value bootstrap) and dones into the storage rows of one rollout step."""
+    N = rewards.numel()
+    check(lib.mnr_post_step(ptr(rewards, F32, "rewards"), ptr(dones, (U8, BOOL), "dones"),
+                            ptr(time_outs, (U8, BOOL), "time_outs", allow_none=True), ptr(values_t, F32, allow_none=True), scale, gamma,
+                            ptr(rewards_t, F32), ptr(dones_t, (U8, BOOL)), N, stream()), "mnr_post_step")

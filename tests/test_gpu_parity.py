@@ -581,6 +581,84 @@ def test_ppo_update_matches_reference_agent(cuda_graph):
             scale_close(data["sigma"], c["data_after_train"]["sigma"], 1e-4, "sigma write-back")
 
 
+@pytest.mark.parametrize("fused", [True, False])
+def test_play_steps_matches_reference_rollout(fused):
+    """PPO.play_steps on our kernels (obs normalise -> tower GEMMs -> mnr_policy_step -> env.step ->
+    mnr_post_step, then the fused post-rollout pass) against the REAL reference agent's rollout recorded in the ppo_e2e
+    golden: same synthetic env streams, the reference's own sampling noise (recovered from its stored actions / mu /
+    sigma) injected step by step.  fused=False runs the reference's torch op sequence on the same inputs."""
+    from mineral_b200.agents import PPO
+    from mineral_b200.agents.ppo.ppo import _RolloutEngine
+    from oracle.reference_shim import SynthEnv, to_attr
+
+    for c in load_golden("ppo_e2e"):
+        T, N, O, A = c["shape"]
+        cfg = to_attr(c["cfg"])
+        cfg.rl_device = DEV
+        cfg.agent.ppo["fused_rollout"] = fused
+        cpu_env = SynthEnv(N, O, A, T, seed=41, done_p=0.08, timeout_p=0.05)  # oracle/make_golden.py:gen_ppo_e2e
+
+        class OnDevice:  # the agents expect the simulator to hand out device tensors (mineral/agents/agent.py:144-156)
+            observation_space, action_space = cpu_env.observation_space, cpu_env.action_space
+
+            def reset(self):
+                return cu(cpu_env.reset())
+
+            def step(self, actions):
+                o, r, d, info = cpu_env.step(actions)
+                return cu(o), cu(r), cu(d), cu(info)
+
+        env = OnDevice()
+        agent = PPO(cfg, env=env)
+        agent.model.load_state_dict(c["init_state_dict"])
+        agent.value_rms.load_state_dict(c["value_rms_before"])
+        agent.obs_rms.load_state_dict(c["obs_rms_before"])
+        ref = c["storage"]
+        eps = (ref["actions"] - ref["mu"]) / ref["sigma"]
+        if fused:
+            assert _RolloutEngine.supported(agent)
+            agent._rollout = _RolloutEngine(agent)
+            agent._rollout.eps_source = lambda t: cu(eps[t])
+        else:  # torch path: make Normal.sample() return the reference's actions
+            step = {"t": 0}
+            orig_act = agent.model.act
+
+            def act(obs_dict, sample=True, **kw):
+                out = orig_act(obs_dict, sample=sample, **kw)
+                if sample and step["t"] < T:
+                    out["actions"] = out["mu"] + out["sigma"] * cu(eps[step["t"]])
+                    out["neglogp"] = -out["distr"].log_prob(out["actions"]).sum(1)
+                    step["t"] += 1
+                return out
+
+            agent.model.act = act
+        seen = {}
+        orig_finish = agent.finish_rollout
+
+        def finish(last_values):
+            seen["last_values"] = last_values.clone()
+            return orig_finish(last_values)
+
+        agent.finish_rollout = finish
+        agent.obs = agent._convert_obs(env.reset())
+        agent.dones = torch.zeros(N, dtype=torch.bool, device=DEV)
+        agent.epoch = 0
+        agent.set_eval()
+        agent.play_steps()
+        sd = agent.storage.storage_dict
+        tag = f"{c['variant']} fused={fused}"
+        eq(sd["obses"]["obs"], ref["obses"]["obs"], f"{tag} obs")
+        eq(sd["dones"], ref["dones"], f"{tag} dones")
+        for k in ("actions", "mu", "sigma", "values", "rewards"):
+            scale_close(sd[k], ref[k], 1e-5, f"{tag} storage {k}")
+        scale_close(sd["neglogp"], ref["neglogp"], 2e-5, f"{tag} storage neglogp")
+        scale_close(seen["last_values"], c["last_values"], 1e-5, f"{tag} last_values")
+        data = agent.storage.data_dict
+        for k in ("advantages", "values", "returns"):
+            scale_close(data[k], c["data_after_play"][k], 2e-5, f"{tag} data {k}")
+        assert (agent._rollout is not None) == fused
+
+
 def test_ppo_first_step_gradients_vs_oracle():
     """Gradients of the first optimizer step (before any parameter moved) within 1e-5 of scale."""
     for c in load_golden("ppo_e2e"):
