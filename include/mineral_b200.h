@@ -548,6 +548,14 @@ int mnr_policy_step(const float* y3a, const float* y3v, const float* w_mu, const
 int mnr_post_step(const float* rewards, const void* dones, const void* time_outs, const float* values_t,
                   float reward_scale, float gamma, float* rewards_t, uint8_t* dones_t, int N, mnr_stream_t stream);
 
+/* 8(f)-4  episode accounting on the device (Metrics._update_scores, mineral/common/metrics.py:59-67; Tracker,
+ *      mineral/common/tracker.py:9-22): cur_rewards (N) f32 += rewards, cur_lengths (N) i64 += 1; every finished env
+ *      (dones u8/bool, in env order) appends (reward, length) to the windows of the last `window` finished episodes
+ *      (win_rewards / win_lengths (window) f32, ring slot = episode count mod window, zero-initialised like the
+ *      reference's deque) and resets; counters[0] (i64) counts finished episodes.  One launch, no host read. */
+int mnr_episode_scores(const float* rewards, const void* dones, float* cur_rewards, int64_t* cur_lengths,
+                       float* win_rewards, float* win_lengths, int64_t* counters, int N, int window, mnr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

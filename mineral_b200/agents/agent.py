@@ -22,16 +22,57 @@ def cfg_get(cfg, key, default=None):
 
 
 class Tracker:
-    """Windowed mean of finished-episode statistics (mineral/common/tracker.py:9)."""
+    """Windowed statistics of finished episodes (mineral/common/tracker.py:9-22): like the reference, the window starts
+    as `max_len` zeros, so the mean ramps up until `max_len` episodes have finished."""
 
     def __init__(self, max_len):
-        self.window = deque(maxlen=max_len)
+        self.max_len = max_len
+        self.window = deque([0 for _ in range(max_len)], maxlen=max_len)
 
     def update(self, values):
         self.window.extend(values)
 
     def mean(self):
-        return float(np.mean(self.window)) if len(self.window) else 0.0
+        return float(np.mean(self.window))
+
+
+class DeviceTracker:
+    """Tracker whose window lives on the GPU (filled by mnr_episode_scores); reading a statistic is the only sync."""
+
+    def __init__(self, window):
+        self.window = window   # (max_len,) f32, zero-initialised; order inside the ring does not matter for mean / std / ...
+
+    def mean(self):
+        return float(self.window.mean().item())
+
+
+class DeviceMetrics:
+    """Metrics._update_scores (mineral/common/metrics.py:59-67) without the per-step host round trip: ONE kernel per env
+    step keeps the per-env accumulators and the windows of the last `tracker_len` finished episodes on the device."""
+
+    def __init__(self, current_scores, tracker_len):
+        from .. import ops
+        self._ops = ops
+        self.current = current_scores
+        dev = current_scores['rewards'].device
+        self.win = {k: torch.zeros(tracker_len, dtype=torch.float32, device=dev) for k in ('rewards', 'lengths')}
+        self.episode_trackers = {k: DeviceTracker(v) for k, v in self.win.items()}
+        self.counters = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    @property
+    def num_episodes(self):
+        return int(self.counters.item())
+
+    def update(self, epoch, env, obs, rewards, dones, infos):
+        """`dones`: the (N,) bool / u8 done flags of this step (NOT a host list of indices)."""
+        self._ops.episode_scores(rewards.contiguous(), dones.contiguous(), self.current['rewards'], self.current['lengths'],
+                                 self.win['rewards'], self.win['lengths'], self.counters)
+
+    def flush_video(self, epoch):
+        return
+
+    def result(self, prefix=''):
+        return {}
 
 
 class Metrics:

@@ -288,7 +288,7 @@ class PPO(Agent):
         ro = self._rollout
         ro.begin_rollout()
         for n in range(self.horizon_len):
-            if not self.env_autoresets and any(self.dones):
+            if not self.env_autoresets and any(self.dones):   # simulators without auto-reset need the indices on the host
                 done_indices = torch.where(self.dones)[0].tolist()
                 obs_reset = self._convert_obs(self.env.reset_idx(done_indices))
                 for k, v in obs_reset.items():
@@ -299,8 +299,7 @@ class PPO(Agent):
             self.obs = self._convert_obs(obs)
             r, self.dones = torch.as_tensor(r, device=self.device), torch.as_tensor(self.dones, device=self.device)
             ro.after_env_step(n, r, self.dones, infos)             # shaped reward (+ time-out bootstrap), dones -> storage rows
-            done_indices = torch.where(self.dones)[0].tolist()
-            self.metrics.update(self.epoch, self.env, self.obs, r.reshape(-1), done_indices, infos)
+            ro.metrics.update(self.epoch, self.env, self.obs, r.reshape(-1).float(), self.dones.reshape(-1), infos)  # no host sync
         self.metrics.flush_video(self.epoch)
         self.finish_rollout(ro.values_only(self.obs))
 
@@ -410,6 +409,11 @@ class _RolloutEngine:
         dk = a.model.dist
         self.cfg = ops.make_loss_cfg(dist_type=dk.dist_type, minstd=dk.minstd, maxstd=dk.maxstd)
         self.eps_source = None   # tests inject recorded noise: callable(step) -> (N, A) tensor; default torch's generator
+        # episode accounting on the device; the agent's `metrics` keeps the reference's attributes (`episode_trackers`, ...)
+        from ..agent import DeviceMetrics, Metrics
+        if type(a.metrics) is Metrics:
+            a.metrics = DeviceMetrics(a.metrics.current, a.tracker_len)
+        self.metrics = a.metrics
 
     def begin_rollout(self):
         a = self.a

@@ -131,3 +131,82 @@ extern "C" int mnr_post_step(const float* rewards, const void* dones, const void
                                                                reward_scale, gamma, rewards_t, dones_t, N);
   MNR_LAUNCH_RESULT();
 }
+
+// ---- 8(f)-4  episode accounting on the device (mineral/common/metrics.py:59-67, tracker.py:9-22) ----------------------
+// current_rewards += r; current_lengths += 1; the finished envs (in env order, as the reference's boolean indexing
+// yields them) push (reward, length) into the two windows of the last L finished episodes (a deque(maxlen=L): ring
+// slot = running episode count mod L) and reset.  ONE CTA: block-wide exclusive scan of the done flags gives every
+// finished env its deterministic slot, so the per-step `torch.where(dones)[0].tolist()` host sync of the reference
+// (ppo.py:165) disappears from the rollout.
+namespace {
+constexpr int kEpiThreads = 1024;
+__global__ void __launch_bounds__(kEpiThreads) episode_scores_kernel(const float* __restrict__ rewards, const uint8_t* __restrict__ dones,
+                                                                     float* __restrict__ cur_rewards, int64_t* __restrict__ cur_lengths,
+                                                                     float* __restrict__ win_rewards, float* __restrict__ win_lengths,
+                                                                     int64_t* __restrict__ counters /* [0] episodes so far */, int N, int L) {
+  __shared__ int s_warp[kEpiThreads / 32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  const int64_t total0 = counters[0];
+  // pass 1: count the finished envs (needed to drop all but the last L of them when more than L finish at once)
+  int mine = 0;
+  for (int n = tid; n < N; n += kEpiThreads) mine += dones[n] ? 1 : 0;
+  mine = (int)mnr::warp_sum((float)mine);
+  if (lane == 0) s_warp[warp] = mine;
+  __syncthreads();
+  int n_done = 0;
+  for (int w = 0; w < kEpiThreads / 32; ++w) n_done += s_warp[w];
+  __syncthreads();
+  // pass 2: chunk by chunk in env order, exclusive scan inside the chunk
+  for (int c0 = 0; c0 < N; c0 += kEpiThreads) {
+    const int n = c0 + tid;
+    const bool in = n < N;
+    float r = 0.f;
+    int64_t len = 0;
+    bool d = false;
+    if (in) {
+      r = cur_rewards[n] + __ldg(rewards + n);
+      len = cur_lengths[n] + 1;
+      d = dones[n] != 0;
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, d);
+    const int in_warp = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(ballot);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int rank = before + in_warp;   // how many finished envs precede this one in this step
+    if (in) {
+      if (d) {
+        if (rank >= n_done - L) {   // a deque(maxlen=L) keeps only the last L pushed
+          const int slot = (int)((total0 + rank) % L);
+          win_rewards[slot] = r, win_lengths[slot] = (float)len;
+        }
+        r = 0.f, len = 0;
+      }
+      cur_rewards[n] = r, cur_lengths[n] = len;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int t = s_base;
+      for (int w = 0; w < kEpiThreads / 32; ++w) t += s_warp[w];
+      s_base = t;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) counters[0] = total0 + n_done;
+}
+}  // namespace
+
+extern "C" int mnr_episode_scores(const float* rewards, const void* dones, float* cur_rewards, int64_t* cur_lengths,
+                                  float* win_rewards, float* win_lengths, int64_t* counters, int N, int window,
+                                  mnr_stream_t stream) {
+  MNR_CHECK_PTR(rewards); MNR_CHECK_PTR(dones); MNR_CHECK_PTR(cur_rewards); MNR_CHECK_PTR(cur_lengths);
+  MNR_CHECK_PTR(win_rewards); MNR_CHECK_PTR(win_lengths); MNR_CHECK_PTR(counters);
+  if (N <= 0 || window <= 0) return MNR_ESHAPE;
+  episode_scores_kernel<<<1, kEpiThreads, 0, mnr_cs(stream)>>>(rewards, (const uint8_t*)dones, cur_rewards, cur_lengths, win_rewards,
+                                                               win_lengths, counters, N, window);
+  MNR_LAUNCH_RESULT();
+}

@@ -430,3 +430,10 @@ def post_step(rewards, dones, time_outs, values_t, scale, gamma, rewards_t, done
     check(lib.mnr_post_step(ptr(rewards, F32, "rewards"), ptr(dones, (U8, BOOL), "dones"),
                             ptr(time_outs, (U8, BOOL), "time_outs", allow_none=True), ptr(values_t, F32, allow_none=True), scale, gamma,
                             ptr(rewards_t, F32), ptr(dones_t, (U8, BOOL)), N, stream()), "mnr_post_step")
+
+
+def episode_scores(rewards, dones, cur_rewards, cur_lengths, win_rewards, win_lengths, counters):
+    """Metrics._update_scores + Tracker.update on the device, one launch, no host sync (csrc/rollout.cu)."""
+    check(lib.mnr_episode_scores(ptr(rewards, F32, "rewards"), ptr(dones, (U8, BOOL), "dones"), ptr(cur_rewards, F32), ptr(cur_lengths, I64),
+                                 ptr(win_rewards, F32), ptr(win_lengths, F32), ptr(counters, I64), rewards.numel(), win_rewards.numel(),
+                                 stream()), "mnr_episode_scores")

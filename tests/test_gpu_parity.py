@@ -659,6 +659,41 @@ def test_play_steps_matches_reference_rollout(fused):
         assert (agent._rollout is not None) == fused
 
 
+@pytest.mark.parametrize("N,L,done_p", [(300, 20, 0.03), (4096, 100, 0.02), (64, 8, 0.6), (2500, 100, 0.0)])
+def test_episode_accounting_on_device(N, L, done_p):
+    """8(f)-4: mnr_episode_scores == Metrics._update_scores + Tracker (mineral/common/metrics.py:59-67, tracker.py:9-22),
+    including steps in which more episodes finish than the window holds."""
+    import collections
+
+    from mineral_b200 import ops
+
+    g = torch.Generator().manual_seed(N + L)
+    cur_r, cur_l = torch.zeros(N), torch.zeros(N, dtype=torch.int64)
+    win_r, win_l = collections.deque([0] * L, maxlen=L), collections.deque([0] * L, maxlen=L)
+    d_cur_r, d_cur_l = cu(cur_r.clone()), cu(cur_l.clone())
+    d_win_r, d_win_l, cnt = torch.zeros(L, device=DEV), torch.zeros(L, device=DEV), torch.zeros(1, dtype=torch.int64, device=DEV)
+    total = 0
+    for step in range(40):
+        r = torch.randn(N, generator=g)
+        dones = torch.rand(N, generator=g) < done_p
+        # reference semantics on the CPU
+        cur_r += r
+        cur_l += 1
+        idx = torch.where(dones)[0].tolist()
+        if idx:
+            total += len(idx)
+            win_r.extend(cur_r[idx].tolist()), win_l.extend(cur_l[idx].tolist())
+            cur_r[idx] = 0
+            cur_l[idx] = 0
+        ops.episode_scores(cu(r), cu(dones), d_cur_r, d_cur_l, d_win_r, d_win_l, cnt)
+    eq(d_cur_r, cur_r, "current rewards"), eq(d_cur_l, cur_l, "current lengths")
+    assert cnt.item() == total
+    ring_r, ring_l = d_win_r.cpu().tolist(), d_win_l.cpu().tolist()
+    order = [(total + i) % L for i in range(L)]  # deque order = ring rotated by the running episode count
+    assert [ring_r[i] for i in order] == [float(torch.tensor(v, dtype=torch.float32)) for v in win_r]
+    assert [ring_l[i] for i in order] == [float(v) for v in win_l]
+
+
 def test_ppo_first_step_gradients_vs_oracle():
     """Gradients of the first optimizer step (before any parameter moved) within 1e-5 of scale."""
     for c in load_golden("ppo_e2e"):

@@ -50,7 +50,8 @@ def run(workload, fused, reps=5):
     env = DeviceEnv(w["N"], w["O"], w["A"], w["T"], dev)
     torch.manual_seed(0)
     agent = PPO(cfg, env=env)
-    agent.metrics.update = lambda *a, **k: None   # host-side episode bookkeeping (a .tolist() sync per step) is not what is timed
+    # episode bookkeeping stays ON: the fused path keeps it on the device (mnr_episode_scores), the torch path pays the
+    # reference's per-step `torch.where(dones)[0].tolist()` host sync
     agent.obs = agent._convert_obs(env.reset())
     agent.dones = torch.zeros(w["N"], dtype=torch.bool, device=dev)
     agent.set_eval()
