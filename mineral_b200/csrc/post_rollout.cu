@@ -365,10 +365,11 @@ struct Plan {
 // 6-7 CTAs share an SM (loads of some overlap the stores of others); nb % 4 == 0 keeps every copy
 // 16 B aligned.  Returns false if even a 4-env tile of some field exceeds shared memory.
 bool make_plan(const mnr_wide_field_t* wide, int n_wide, int T, int N, Plan* pl) {
-  size_t kTileCap = 32 * 1024, kMinCopy = 1024;  // measured on B200: 32 KB tiles (7 CTAs/SM) beat 40 KB at >= 16k envs
+  // measured on B200: 32 KB tiles (7 CTAs/SM) beat 40 KB at >= 16k envs.  The environment knobs are tuning aids
+  // (tools/sweep_post_rollout.py), read once per process.
+  static const size_t kTileCap = [] { const char* e = getenv("MNR_POST_ROLLOUT_TILE_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)32 * 1024; }();
+  static const size_t kMinCopy = [] { const char* e = getenv("MNR_POST_ROLLOUT_MIN_COPY"); return e ? (size_t)atoi(e) : (size_t)1024; }();
   const size_t kSmemMax = 227 * 1024 - 2048;
-  if (const char* e = getenv("MNR_POST_ROLLOUT_TILE_KB")) kTileCap = (size_t)atoi(e) * 1024;     // tuning knobs
-  if (const char* e = getenv("MNR_POST_ROLLOUT_MIN_COPY")) kMinCopy = (size_t)atoi(e);
   size_t smem = (size_t)6 * kEnvPerScalarCta * (T + 1) * sizeof(float);
   pl->item0[0] = 0;
   for (int k = 0; k < n_wide; ++k) {
@@ -434,8 +435,8 @@ extern "C" int mnr_post_rollout_fused(const mnr_wide_field_t* wide, int n_wide, 
   p.neglogp_em = neglogp_em, p.adv_em = adv_em, p.dones_em = dones_em;
   p.T = T, p.N = N, p.do_gae = do_gae, p.gamma = gamma, p.gamma_tau = gamma_tau;
   p.workspace = (unsigned char*)workspace;
-  p.debug_skip = 0;
-  if (const char* e = getenv("MNR_POST_ROLLOUT_SKIP")) p.debug_skip = atoi(e);
+  static const int kDebugSkip = [] { const char* e = getenv("MNR_POST_ROLLOUT_SKIP"); return e ? atoi(e) : 0; }();
+  p.debug_skip = kDebugSkip;
 
   const int grid = pl.n_scalar + pl.item0[n_wide];
   cudaError_t e;

@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(&tmem_full[b], 1);
-      ptx::mbar_init(&tmem_empty[b], kEpiWarps * 32);
+      ptx::mbar_init(&tmem_empty[b], (MODE == kDw ? 4 : kEpiWarps) * 32);
     }
     ptx::fence_mbar_init();
   }
@@ -253,14 +253,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
         ptx::tc_commit(&tmem_full[acc]);   // accumulator complete (fires at once for an empty reduction range)
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < (MODE == kDw ? 12 : 8)) {
     // ===== converters ====================================================================================
-    const int t = tid - 128;
+    // DW is bound by this role (a [32][128] tile of dY and of Y per k-block, element-wise transposed into TMEM lanes by one
+    // warp per scheduler), and its epilogue is small: warps 8-11 form a SECOND converter group there; the groups take
+    // alternate k-blocks and each keeps its own bias-gradient partial.
+    const int cgroup = (warp - 4) >> 2;  // 0: warps 4-7, 1: warps 8-11 (DW only)
+    const int t = tid - 128 - 128 * cgroup;
     uint32_t kbg = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(p, tile, MODE);
       float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+        if (MODE == kDw && (int)(kbg & 1u) != cgroup) continue;
         const int st = kbg % stages;
         ptx::mbar_wait(&full_tma[st], (kbg / stages) & 1);
         if (t == 0) TC_TRACE(1, kbg, 0);
@@ -325,16 +330,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
         ptx::mbar_arrive(&full_conv[st]);
         if (t == 0) TC_TRACE(1, kbg, 1);
       }
-      if (MODE == kDw && p.want_bias && tc.j0 == 0) {
-        float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)tc.gi * p.splits + tc.split) * p.I;
+      if (MODE == kDw && p.want_bias && tc.j0 == 0) {  // bias partials: [group][split][converter group][I]
+        float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + (((size_t)tc.gi * p.splits + tc.split) * 2 + cgroup) * p.I;
         if (tc.i0 + t < p.I) bp[tc.i0 + t] = bsum.x;
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= (MODE == kDw ? 12 : 8)) {
     // ===== epilogue: TMEM -> registers -> (bias, act) -> 32x32 transpose in smem -> full 128 B line stores ========
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*quarter, 32*quarter+32)
-    float* stg = epi_stage + (size_t)(warp - 8) * 32 * 33;
-    const int half = (warp - 8) >> 2;  // the two warps of a TMEM quarter take alternate 32-column chunks
+    constexpr int kEpi = (MODE == kDw) ? 4 : kEpiWarps, kEpi0 = (MODE == kDw) ? 12 : 8;
+    float* stg = epi_stage + (size_t)(warp - kEpi0) * 32 * 33;
+    const int half = (warp - kEpi0) >> 2;  // the warps of a TMEM quarter take alternate 32-column chunks
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile, MODE);
@@ -346,20 +352,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       if (MODE == kFwd && g.bias) {
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
-          const int cc = half + k * (kEpiWarps / 4);
+          const int cc = half + k * (kEpi / 4);
           const int col = tc.j0 + cc * 32 + lane;
           if (cc * 32 + lane < BN && col < p.J) bias_c[k] = __ldg(g.bias + col);
         }
       }
       ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
-      if (tid == 256) TC_TRACE(3, it, 0);
+      if (tid == kEpi0 * 32) TC_TRACE(3, it, 0);
       ptx::tc_fence_after();
       float* cbase;
       size_t ldo;
       if (MODE == kDw) cbase = p.partials + ((size_t)tc.gi * p.splits + tc.split) * p.I * p.J, ldo = p.J;
       else cbase = g.c, ldo = p.ldc;
       const int row_base = tc.i0 + 32 * quarter;
-      for (int cc = half; cc < (BN + 31) / 32; cc += kEpiWarps / 4) {
+      for (int cc = half; cc < (BN + 31) / 32; cc += kEpi / 4) {
         uint32_t r[32];
         if (tc.num_kb > 0) {
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + acc * acc_stride + (uint32_t)(cc * 32), r);
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tmem_empty[acc]);
-      if (tid == 256) TC_TRACE(3, it, 1);
+      if (tid == kEpi0 * 32) TC_TRACE(3, it, 1);
     }
   }
 
@@ -459,9 +465,9 @@ __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ 
   } else {
     const int n = ((int)blockIdx.x - wblocks) * 32 + lane;
     if (n < I && jb.b[gi]) {
-      const float* bp = partials + (size_t)jb.n_groups * splits * NK + (size_t)gi * splits * I + n;
+      const float* bp = partials + (size_t)jb.n_groups * splits * NK + (size_t)gi * 2 * splits * I + n;  // 2 converter groups
 #pragma unroll 4
-      for (int z = slice; z < splits; z += 8) acc.x += __ldcs(bp + (size_t)z * I);
+      for (int z = slice; z < 2 * splits; z += 8) acc.x += __ldcs(bp + (size_t)z * I);
     }
   }
   s_part[slice][lane] = acc;
@@ -651,7 +657,7 @@ extern "C" size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, 
   if (n_groups <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
   const int Kr = (K + 31) / 32 * 32, BN = Kr <= 128 ? Kr : 128;
   const int tiles = ((N + kBM - 1) / kBM) * ((K + BN - 1) / BN) * n_groups;
-  return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + N) * sizeof(float);
+  return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + 2 * (size_t)N) * sizeof(float);  // dW + 2 db slabs per split
 }
 
 namespace {
