@@ -167,9 +167,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     ptx::fence_mbar_init();
   }
   const uint32_t acc_stride = (uint32_t)((BN + 31) / 32 * 32);  // TMEM columns per accumulator (tcgen05.ld reads 32 at a time)
-  const uint32_t a_slots = 2 * acc_stride;  // first TMEM column of the A ring: `stages` slots of 64 columns (hi 32 | lo 32)
+  // BN > 128 (DW with a 256-wide weight-gradient tile: the dY / Y tiles are then loaded and converted ONCE per k-block
+  // instead of once per 128-column half) leaves room for a single accumulator only: the epilogue of a work item is then
+  // not overlapped with the next item's main loop, which DW (one or two items per CTA) does not need.
+  const bool single_acc = BN > 128;
+  const uint32_t n_acc = single_acc ? 1u : 2u;
+  const uint32_t a_slots = n_acc * acc_stride;  // first TMEM column of the A ring: `stages` slots of 64 columns (hi 32 | lo 32)
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2 * acc_stride + (uint32_t)stages * 64u) tmem_cols <<= 1;
+  while (tmem_cols < n_acc * acc_stride + (uint32_t)stages * 64u) tmem_cols <<= 1;
   if (warp == 2) ptx::tmem_alloc(&tmem_slot, tmem_cols);
   ptx::tc_fence_before();
   __syncthreads();
@@ -225,8 +230,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       uint32_t kbg = 0, it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(p, tile, MODE);
-        const uint32_t acc = it & 1;
-        ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        const uint32_t acc = single_acc ? 0u : (it & 1);
+        ptx::mbar_wait(&tmem_empty[acc], ((single_acc ? it : (it >> 1)) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * acc_stride;
         for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const TileCoord tc = decode_tile(p, tile, MODE);
       const TcGroup& g = p.g[tc.gi];
-      const uint32_t acc = it & 1;
+      const uint32_t acc = single_acc ? 0u : (it & 1);
       // FWD: this warp's bias values (one column per lane, <= 2 chunks since BN <= 128) are requested BEFORE the wait on
       // the accumulator: the global-load latency used to sit on every chunk's critical path (top stall of the kernel)
       float bias_c[2] = {0.f, 0.f};
@@ -357,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           if (cc * 32 + lane < BN && col < p.J) bias_c[k] = __ldg(g.bias + col);
         }
       }
-      ptx::mbar_wait(&tmem_full[acc], (it >> 1) & 1);
+      ptx::mbar_wait(&tmem_full[acc], (single_acc ? it : (it >> 1)) & 1);
       if (tid == kEpi0 * 32) TC_TRACE(3, it, 0);
       ptx::tc_fence_after();
       float* cbase;
@@ -637,6 +642,12 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
 }
 
 namespace {
+// DW tile width along K_in: up to 256 columns in one tile (single accumulator), 128-column tiles beyond that
+int dw_bn(int K) {
+  const int Kr = (K + 31) / 32 * 32;
+  return Kr <= 256 ? Kr : 128;
+}
+
 int tc_dw_splits(int M, int tiles) {
   // Split the reduction (the minibatch rows) so that (a) one accumulation chain in TMEM covers <= 512 rows: the tensor
   // core's fp32 accumulate error grows with the chain length and the parity bar is 1e-5; (b) tiles x splits fills whole
@@ -655,7 +666,7 @@ int tc_dw_splits(int M, int tiles) {
 
 extern "C" size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K) {
   if (n_groups <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
-  const int Kr = (K + 31) / 32 * 32, BN = Kr <= 128 ? Kr : 128;
+  const int BN = dw_bn(K);
   const int tiles = ((N + kBM - 1) / kBM) * ((K + BN - 1) / BN) * n_groups;
   return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + 2 * (size_t)N) * sizeof(float);  // dW + 2 db slabs per split
 }
@@ -673,8 +684,7 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
   if (workspace_bytes < mnr_tc_linear_bwd_weight_workspace_bytes(n_groups, M, N, K)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
   TcParams p;
-  const int Kr = (K + 31) / 32 * 32;
-  p.BN = Kr <= 128 ? Kr : 128;
+  p.BN = dw_bn(K);
   bool want_bias = false;
   for (int k = 0; k < kMaxGroups; ++k) job->w[k] = nullptr, job->b[k] = nullptr;
   for (int k = 0; k < n_groups; ++k) {
