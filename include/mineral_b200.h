@@ -280,7 +280,7 @@ int mnr_ppo_loss_fwd_bwd(const float* mu_raw, const float* logstd, int logstd_ro
  * everything mnr_ppo_loss_fwd_bwd does, and returns the gradients the towers' backward needs, dy3a / dy3v (M,H),
  * plus every head parameter gradient (dw_sig = NULL with fixed sigma; db_sig then receives d sigma).
  * g_mu / g_ls (M,A) and g_v (M) are scratch outputs.  H % 8 == 0, H <= 128, A <= 32. */
-/* 1 if (A, H) takes the single persistent kernel (csrc/heads_fused.cu: H in {32,64,128}, A <= 16), 0 if the
+/* 1 if (A, H) takes the single persistent kernel (csrc/heads_fused.cu: H in {32,64,128}, A <= 32), 0 if the
  * two-kernel form (heads+loss, then head gradients) is used. */
 int mnr_ppo_heads_is_fused(int A, int H);
 size_t mnr_ppo_heads_workspace_bytes(int64_t M, int A, int H);

@@ -195,11 +195,19 @@ lib = _load()
 LAUNCHES = 0  # kernels enqueued through this binding (each successful mnr_* call launches >= 1 kernel)
 
 
+_DEBUG_SYNC = bool(os.environ.get("MNR_DEBUG_SYNC"))  # debugging aid: synchronise after every call so a device fault names its launch
+
+
 def check(rc, what="", kernels=1):
     global LAUNCHES
     if rc != 0:
         raise MineralB200Error(f"{what or 'mnr call'} failed: [{rc}] {lib.mnr_error_string(rc).decode()}")
     LAUNCHES += kernels
+    if _DEBUG_SYNC:
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:
+            raise MineralB200Error(f"device fault surfaced after {what} (launch #{LAUNCHES})") from e
 
 
 def stream():

@@ -47,7 +47,9 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
   return acc;
 }
 
-// A, H compile-time (no guards in the unrolled dot products); one shared-memory tile buffer serves the actor tower
+// A (the action dimension padded to a multiple of 4; the real one is a.A at run time: pad rows of the head weights are
+// zero in shared memory and the rolled loss loops stop at a.A), H compile-time (no guards in the unrolled dot products);
+// one shared-memory tile buffer serves the actor tower
 // and then the value tower of the same 128 rows, so a CTA needs ~58 KB and 3 CTAs (24 warps) share an SM.  The kernel is
 // bound by per-thread instruction latency (every instruction runs once or twice per warp), hence TWO threads per row:
 // each takes every other float4 column of the row in the dot-product / dY3 sweeps and every other action column in the
@@ -60,10 +62,11 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   constexpr int GP = 4 * A + 4;                      // s_g pitch: g_mu | g_ls | mu | sigma | g_v | pad  (float4-aligned groups,
                                                      // GP mod 32 == 4 or 20: "thread = row" float4 accesses are conflict-free)
   constexpr int GW = 4 * A + 1;                      // columns that get summed over rows
-  constexpr int UV = NY * 4 <= 64 ? 4 : 2;           // hidden columns per thread in the weight-gradient phase
+  constexpr int UV = NY * 4 <= 64 ? 4 : (NY * 2 <= 64 ? 2 : 1);  // hidden columns per thread in the weight-gradient phase
   constexpr int HU = H / UV, NRG = kThreadsHF / HU, RPG = kRows / NRG;  // threads per row group, row groups, rows per group
   constexpr int kWarpsHF = kThreadsHF / 32;
-  static_assert(A % 4 == 0 && A <= 16 && NRG >= 1 && RPG >= 1 && NY * UV <= 64, "unsupported head shape");
+  static_assert(A % 4 == 0 && A <= 32 && NRG >= 1 && RPG >= 1 && NY * UV <= 64, "unsupported head shape");
+  const int Ar = a.A;  // real action dimension, Ar <= A
   extern __shared__ __align__(16) float sh[];
   __shared__ double s_red[6][kWarpsHF];
   __shared__ mnr::Moments s_mom[2][kWarpsHF];
@@ -75,13 +78,14 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   float* s_g = s_wv + H;                             // [128][GP]
 
   for (int i = tid; i < A * H; i += kThreadsHF) {
-    s_wmu[i] = __ldg(a.w_mu + i);
-    if (LEARNED) s_wsig[i] = __ldg(a.w_sig + i);
+    const bool real = i < Ar * H;
+    s_wmu[i] = real ? __ldg(a.w_mu + i) : 0.f;
+    if (LEARNED) s_wsig[i] = real ? __ldg(a.w_sig + i) : 0.f;
   }
   for (int i = tid; i < H; i += kThreadsHF) s_wv[i] = __ldg(a.w_v + i);
   float b_mu[A], b_sig[A];
 #pragma unroll
-  for (int j = 0; j < A; ++j) b_mu[j] = __ldg(a.b_mu + j), b_sig[j] = __ldg(a.b_sig + j);
+  for (int j = 0; j < A; ++j) b_mu[j] = j < Ar ? __ldg(a.b_mu + j) : 0.f, b_sig[j] = j < Ar ? __ldg(a.b_sig + j) : 0.f;
 
   const float w = cfg.grad_scale / (float)a.M;
   const float b_v = __ldg(a.b_v);
@@ -146,11 +150,14 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     //      [3A,4A) sigma): keeps the transcendental-heavy body in the code once instead of A times.
 #pragma unroll
     for (int j = 0; j < A; ++j)
-      if ((j & 1) == h) grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
+      if ((j & 1) == h) {
+        grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
+        if (j >= Ar) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;  // pad columns: defined (and ignored) in the column sums
+      }
     float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
-    const float* act_row = a.actions + (size_t)row * A;
+    const float* act_row = a.actions + (size_t)row * Ar;
 #pragma unroll 1
-    for (int j = h; j < A; j += 2) {
+    for (int j = h; j < Ar; j += 2) {
       float mu, sg, dmu, dsg, db;
       dist_fwd(cfg, grow[j], grow[A + j], mu, sg, dmu, dsg);
       const float diff = __ldg(act_row + j) - mu;
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       nlp += diff * diff / (2.f * sg * sg) + lsg + kLogSqrt2Pi;
       ent += 0.5f + kLogSqrt2Pi + lsg;
       bsum += bounds_elem(mu, cfg.bounds_type, cfg.soft_bound, &db);
-      kl += kl_elem(mu, sg, a.old_mu[(size_t)row * A + j], a.old_sigma[(size_t)row * A + j]);
+      kl += kl_elem(mu, sg, a.old_mu[(size_t)row * Ar + j], a.old_sigma[(size_t)row * Ar + j]);
       grow[2 * A + j] = mu, grow[3 * A + j] = sg;
     }
     nlp += __shfl_xor_sync(0xffffffffu, nlp, 1), ent += __shfl_xor_sync(0xffffffffu, ent, 1);
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     const float g_nlp = w * dl_dnlp;
     const float span = cfg.maxstd - cfg.minstd;
 #pragma unroll 1
-    for (int j = h; j < A; j += 2) {
+    for (int j = h; j < Ar; j += 2) {
       const float mu = grow[2 * A + j], sg = grow[3 * A + j];
       const float diff = __ldg(act_row + j) - mu;
       float dmu = 1.f, dsg = sg;                                  // d mu / d mu_raw, d sigma / d logstd (dist.py:32-47)
@@ -187,17 +194,23 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       if (!valid) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;
     }
     __syncwarp();  // the pair's halves of the row are both in shared memory now
-    if (valid) {  // row-contiguous float4 copies of the finished row pieces (half h takes every other piece)
+    if (valid && (Ar & 3) == 0) {  // row-contiguous float4 copies of the finished row pieces (half h takes every other piece)
 #pragma unroll
       for (int j4 = 0; j4 < A / 4; ++j4) {
-        if ((j4 & 1) != h) continue;
+        if ((j4 & 1) != h || 4 * j4 >= Ar) continue;
         const float4 gm4 = reinterpret_cast<const float4*>(grow)[j4], gl4 = reinterpret_cast<const float4*>(grow + A)[j4];
-        if (a.g_mu) reinterpret_cast<float4*>(a.g_mu + (size_t)row * A)[j4] = gm4;
-        if (a.g_ls) reinterpret_cast<float4*>(a.g_ls + (size_t)row * A)[j4] = gl4;
+        if (a.g_mu) reinterpret_cast<float4*>(a.g_mu + (size_t)row * Ar)[j4] = gm4;
+        if (a.g_ls) reinterpret_cast<float4*>(a.g_ls + (size_t)row * Ar)[j4] = gl4;
         if (a.write_back) {
-          reinterpret_cast<float4*>(a.old_mu + (size_t)row * A)[j4] = reinterpret_cast<const float4*>(grow + 2 * A)[j4];
-          reinterpret_cast<float4*>(a.old_sigma + (size_t)row * A)[j4] = reinterpret_cast<const float4*>(grow + 3 * A)[j4];
+          reinterpret_cast<float4*>(a.old_mu + (size_t)row * Ar)[j4] = reinterpret_cast<const float4*>(grow + 2 * A)[j4];
+          reinterpret_cast<float4*>(a.old_sigma + (size_t)row * Ar)[j4] = reinterpret_cast<const float4*>(grow + 3 * A)[j4];
         }
+      }
+    } else if (valid) {  // action dimension not a multiple of 4: rows are not 16 B aligned, element-wise copies
+      for (int j = h; j < Ar; j += 2) {
+        if (a.g_mu) a.g_mu[(size_t)row * Ar + j] = grow[j];
+        if (a.g_ls) a.g_ls[(size_t)row * Ar + j] = grow[A + j];
+        if (a.write_back) a.old_mu[(size_t)row * Ar + j] = grow[2 * A + j], a.old_sigma[(size_t)row * Ar + j] = grow[3 * A + j];
       }
     }
     __syncthreads();
@@ -368,15 +381,15 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     if (lane == 0) {
       if (o < (2 * A + 1) * H) {
         const int jrow = o / H, u2 = o - jrow * H;
-        if (jrow < A) a.dw_mu[jrow * H + u2] = sum;
-        else if (jrow < 2 * A) { if (LEARNED) a.dw_sig[(jrow - A) * H + u2] = sum; }
+        if (jrow < A) { if (jrow < Ar) a.dw_mu[jrow * H + u2] = sum; }
+        else if (jrow < 2 * A) { if (LEARNED && jrow - A < Ar) a.dw_sig[(jrow - A) * H + u2] = sum; }
         else a.dw_v[u2] = sum;
       } else {
         const int j = o - (2 * A + 1) * H;
-        if (j < A) a.db_mu[j] = sum;
-        else if (j < 2 * A) a.db_sig[j - A] = sum;          // learned: bias gradient; fixed: d sigma = colsum g_ls
-        else if (j < 3 * A) { if (a.mu_mean) a.mu_mean[j - 2 * A] = sum / (float)a.M; }
-        else if (j < 4 * A) { if (a.sigma_mean) a.sigma_mean[j - 3 * A] = sum / (float)a.M; }
+        if (j < A) { if (j < Ar) a.db_mu[j] = sum; }
+        else if (j < 2 * A) { if (j - A < Ar) a.db_sig[j - A] = sum; }  // learned: bias gradient; fixed: d sigma = colsum g_ls
+        else if (j < 3 * A) { if (a.mu_mean && j - 2 * A < Ar) a.mu_mean[j - 2 * A] = sum / (float)a.M; }
+        else if (j < 4 * A) { if (a.sigma_mean && j - 3 * A < Ar) a.sigma_mean[j - 3 * A] = sum / (float)a.M; }
         else a.db_v[0] = sum;
       }
     }
@@ -447,13 +460,21 @@ int launch_by_h(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int gri
   }
 }
 
+// padded action dimension the kernel is instantiated for: 4, 8, 12, 16, 24, 32
+int mnr_heads_fused_apad(int A) {
+  const int p = (A + 3) / 4 * 4;
+  return p <= 16 ? p : (p <= 24 ? 24 : 32);
+}
+
 template <bool LEARNED>
 int launch_by_a(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
-  switch (a.A) {
+  switch (mnr_heads_fused_apad(a.A)) {
     case 4: return launch_by_h<4, LEARNED>(a, H, cfg, grid_cap, stream);
     case 8: return launch_by_h<8, LEARNED>(a, H, cfg, grid_cap, stream);
     case 12: return launch_by_h<12, LEARNED>(a, H, cfg, grid_cap, stream);
     case 16: return launch_by_h<16, LEARNED>(a, H, cfg, grid_cap, stream);
+    case 24: return launch_by_h<24, LEARNED>(a, H, cfg, grid_cap, stream);
+    case 32: return launch_by_h<32, LEARNED>(a, H, cfg, grid_cap, stream);
     default: return MNR_EUNSUP;
   }
 }
@@ -463,10 +484,11 @@ int launch_by_a(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int gri
 // ---- internal interface used by mnr_ppo_heads_loss_fwd_bwd (csrc/ppo_loss.cu) ----------------------------------------
 int mnr_heads_fused_grid_cap() { return mnr_sm_count() * 4; }
 
-bool mnr_heads_fused_supported(int A, int H) { return (H == 32 || H == 64 || H == 128) && A >= 4 && A <= 16 && A % 4 == 0; }
+bool mnr_heads_fused_supported(int A, int H) { return (H == 32 || H == 64 || H == 128) && A >= 1 && A <= 32; }
 
-size_t mnr_heads_fused_workspace_bytes(int A, int H) {
+size_t mnr_heads_fused_workspace_bytes(int A_real, int H) {
   const size_t cap = (size_t)mnr_heads_fused_grid_cap();
+  const size_t A = (size_t)mnr_heads_fused_apad(A_real);
   const size_t PW = (size_t)(2 * A + 1) * H + 4 * A + 1;
   return 256 + ((cap * sizeof(mnr_loss::LossPartial) + 255) / 256) * 256 + cap * PW * sizeof(float);
 }
@@ -491,8 +513,8 @@ int mnr_heads_fused_launch(const float* y3a, const float* y3v, const float* w_mu
   a.loss_parts = reinterpret_cast<mnr_loss::LossPartial*>(ws + 256);
   a.partials = reinterpret_cast<float*>(ws + 256 + (((size_t)cap * sizeof(mnr_loss::LossPartial) + 255) / 256) * 256);
   a.M = M, a.A = A, a.write_back = write_back, a.n_tiles = (int)((M + kRows - 1) / kRows);
-  if (!mnr_aligned(actions, 16) || !mnr_aligned(old_mu, 16) || !mnr_aligned(old_sigma, 16) || (g_mu && !mnr_aligned(g_mu, 16)) ||
-      (g_ls && !mnr_aligned(g_ls, 16)))
+  if (A % 4 == 0 && (!mnr_aligned(actions, 16) || !mnr_aligned(old_mu, 16) || !mnr_aligned(old_sigma, 16) ||
+                     (g_mu && !mnr_aligned(g_mu, 16)) || (g_ls && !mnr_aligned(g_ls, 16))))
     return MNR_EALIGN;
   return w_sig != nullptr ? launch_by_a<true>(a, H, *cfg, cap, stream) : launch_by_a<false>(a, H, *cfg, cap, stream);
 }

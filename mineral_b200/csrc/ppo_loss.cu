@@ -803,7 +803,7 @@ extern "C" int mnr_policy_kl_rows(const float* p0_mu, const float* p0_sigma, con
   MNR_LAUNCH_RESULT();
 }
 
-// csrc/heads_fused.cu: the single-kernel path (H in {32, 64, 128}, A <= 16)
+// csrc/heads_fused.cu: the single-kernel path (H in {32, 64, 128}, A <= 32)
 int mnr_heads_fused_grid_cap();
 bool mnr_heads_fused_supported(int A, int H);
 size_t mnr_heads_fused_workspace_bytes(int A, int H);

@@ -270,9 +270,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       const TileCoord tc = decode_tile(p, tile, MODE);
       float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
-        if (MODE == kDw && (int)(kbg & 1u) != cgroup) continue;
         const int st = kbg % stages;
         ptx::mbar_wait(&full_tma[st], (kbg / stages) & 1);
+        // the other converter group's k-block.  The wait above is NOT optional: a parity wait only distinguishes
+        // consecutive phases, and with an odd stage count a group that skipped a use of the stage would mistake the
+        // phase before it for the one after it (and convert a stage whose TMA has not landed).
+        if (MODE == kDw && (int)(kbg & 1u) != cgroup) continue;
         if (t == 0) TC_TRACE(1, kbg, 0);
         uint8_t* base = smem + (size_t)st * stage_bytes;
         float4* A4 = reinterpret_cast<float4*>(base);
