@@ -6,19 +6,21 @@
 //                                                 the dropped lo*lo term is < 2^-20 relative)
 //
 // One kernel, three modes, C[i][j] = sum_r A(i,r) B(r,j), tile 128 x BN, 32-wide reduction blocks:
-//   FWD  Y  = act(X W^T + b)          A = X  (K-major)            B = W pre-split hi/lo (K-major)
-//   DX   dX = (dY * act'(Y)) W        A = dY,Y (K-major, fused)   B = W pre-split hi/lo (MN-major: no W^T copy)
-//   DW   dW = (dY * act'(Y))^T X      A = dY,Y (MN-major, fused)  B = X (MN-major, split in-kernel); + db
-// so neither transposed activations nor a dZ tensor ever exist in HBM.
+//   FWD  Y  = act(X W^T + b)          A = X  (K-major tile)             B = W pre-split hi/lo (K-major)
+//   DX   dX = (dY * act'(Y)) W        A = dY,Y (K-major tiles, fused)   B = W pre-split hi/lo (MN-major: no W^T copy)
+//   DW   dW = (dY * act'(Y))^T X      A = dY,Y (MN-major tiles, fused)  B = X (MN-major, split in shared memory); + db
+// so neither transposed activations nor a dZ tensor ever exist in HBM.  The A operand never exists in shared memory in
+// split form either: the converter warps write its hi / lo parts straight into TENSOR MEMORY (tcgen05.st) and the
+// MMAs read it from there (tcgen05.mma [d_tmem], [a_tmem], b_desc).
 //
-// Warp roles (256 threads, 1 CTA/SM):
-//   warp 0    TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) into a 2-4 stage smem ring
-//   warps 4-7 converters: turn the fp32 tiles into hi / lo tiles in place (fusing act' and the bias-gradient
-//             column sums), fence.proxy.async, arrive; afterwards the same warps run the epilogue
-//             (tcgen05.ld from TMEM -> bias + activation -> global)
-//   warp 1    MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 products) per stage and
-//             tcgen05.commit's the stage back to the producer
-//   warp 2    TMEM allocator
+// Warp roles (512 threads, persistent, 1 CTA/SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor (SWIZZLE_128B boxes) into a 2-4 stage shared-memory ring
+//   warp 1      MMA issuer: one thread issues 12 tcgen05.mma (4 k-steps x 3 products) per stage and tcgen05.commit's the
+//               stage back to the producer
+//   warp 2      TMEM allocator (accumulators + a ring of 64-column A slots, one per stage)
+//   warps 4-7   converters: fp32 tile -> hi / lo (act' and the bias-gradient column sums fused) -> TMEM slot;
+//               DW: warps 8-11 are a second converter group (alternate k-blocks)
+//   warps 8-15  epilogue (DW: warps 12-15): tcgen05.ld -> bias + activation -> 32x32 transpose in smem -> full-line stores
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -121,11 +123,8 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
 }
 
 // PERSISTENT kernel: grid = min(#tiles, #SMs); every role loops over this CTA's tiles.  The fp32 accumulator is
-// double-buffered in TMEM (2 x BN columns) so the epilogue warps drain tile t while TMA / converters / MMA already
-// work on tile t+1.
-//   warp 0      TMA producer        warp 1   MMA issuer        warp 2   TMEM allocator
-//   warps 4-7   converters (fp32 -> hi / lo tf32 tiles in place, act' and bias-gradient sums fused)
-//   warps 8-15  epilogue (tcgen05.ld -> bias + activation -> per-warp 32x32 transpose in smem -> full-line stores)
+// double-buffered in TMEM (2 x BN columns, BN <= 128) so the epilogue warps drain tile t while TMA / converters / MMA
+// already work on tile t+1 (DW with a 256-wide tile keeps a single accumulator).
 template <int MODE, int ACT>
 __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_constant__ TcParams p) {
   constexpr bool A_MN = (MODE == kDw), B_MN = (MODE != kFwd), HAS_S = (MODE != kFwd) && (ACT != 0), CONV_B = (MODE == kDw);
