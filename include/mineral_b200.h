@@ -556,6 +556,24 @@ int mnr_post_step(const float* rewards, const void* dones, const void* time_outs
 int mnr_episode_scores(const float* rewards, const void* dones, float* cur_rewards, int64_t* cur_lengths,
                        float* win_rewards, float* win_lengths, int64_t* counters, int N, int window, mnr_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * 8(f)-2  SAC / DDPG update math on top of the fused replay sample (bit-identical to the reference's CPU torch
+ *      evaluation: every op rounded separately, in the reference's order).
+ *      mnr_soft_update:      target = target * (1 - tau) + current * tau  over a flat buffer
+ *                            (soft_update, mineral/agents/ddpg/utils.py:8-11); one_minus_tau = (float)(1.0 - tau).
+ *      mnr_td_target:        out = reward + (1 - done) * gamma_n * (min_k q_k [- alpha * log_prob])  (rows)
+ *                            (mineral/agents/sac/sac.py:293-297, ddpg.py:292-293); qs->pred[0..n_q) are the ensemble's
+ *                            Q values, log_prob may be NULL (DDPG / backup_entropy off); gamma_n = (float)(gamma ** nstep).
+ *      mnr_distl_projection: C51 categorical projection of next_dist (rows, n_atoms) onto the fixed support
+ *                            (distl_projection, mineral/agents/ddpg/utils.py:14-31); delta_z = (float)((v_max - v_min) /
+ *                            (n_atoms - 1)); n_atoms <= 128.
+ * ------------------------------------------------------------------------------------ */
+int mnr_soft_update(float* target, const float* current, int64_t n, float one_minus_tau, float tau, mnr_stream_t stream);
+int mnr_td_target(const mnr_critic_set_t* qs /*host*/, int n_q, const float* log_prob, const float* reward, const float* done,
+                  float alpha, float gamma_n, float* out, int64_t rows, mnr_stream_t stream);
+int mnr_distl_projection(const float* next_dist, const float* reward, const float* done, const float* support, float gamma,
+                         float v_min, float v_max, float delta_z, int n_atoms, float* out, int64_t rows, mnr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

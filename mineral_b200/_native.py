@@ -158,6 +158,9 @@ SIGNATURES = {
     "mnr_ln_act_bwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, i32, vp, sz, vp]),
     "mnr_policy_step": (i32, [vp] * 11 + [f32, f32] + [vp] * 6 + [i32, i32, i32, C.POINTER(PPOLossCfg), vp]),
     "mnr_post_step": (i32, [vp, vp, vp, vp, f32, f32, vp, vp, i32, vp]),
+    "mnr_soft_update": (i32, [vp, vp, i64, f32, f32, vp]),
+    "mnr_td_target": (i32, [C.POINTER(CriticSet), i32, vp, vp, vp, f32, f32, vp, i64, vp]),
+    "mnr_distl_projection": (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i64, vp]),
     "mnr_episode_scores": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "mnr_fused_adam_workspace_bytes": (sz, []),
     "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),

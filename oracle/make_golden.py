@@ -188,6 +188,62 @@ def gen_shac_critic():
     save("shac_critic", cases)
 
 
+# ---- 8(f)-2: SAC / DDPG update math (soft_update, distl_projection, the SAC critic target) ------------------------
+def gen_offpolicy():
+    import torch.nn as nn
+    import torch.nn.functional as F_
+    from mineral.agents.ddpg.utils import distl_projection, soft_update
+    from mineral.agents.sac import sac as sac_mod
+
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    # Polyak: two small nets
+    tar, cur = nn.Linear(7, 5), nn.Linear(7, 5)
+    before = clone_tree(tar.state_dict())
+    soft_update(tar, cur, 0.05)
+    out["soft_update"] = dict(tau=0.05, target_before=before, current=clone_tree(cur.state_dict()), target_after=clone_tree(tar.state_dict()))
+    # C51 projection
+    B, N = 37, 51
+    nd = torch.softmax(torch.randn(B, N, generator=g), dim=1)
+    rew = 3 * torch.randn(B, 1, generator=g)
+    rew[0, 0], rew[1, 0] = 40.0, -40.0                      # clamped at both ends
+    done = (torch.rand(B, 1, generator=g) < 0.3).float()
+    support = torch.linspace(-10, 10, N)
+    rew[2, 0], done[2, 0] = 0.0, 1.0                        # lands exactly on an atom (l == u fix-ups)
+    out["distl"] = dict(next_dist=nd, reward=rew, done=done, gamma=0.99 ** 3, v_min=-10, v_max=10, num_atoms=N, support=support,
+                        proj=distl_projection(nd, rew, done, 0.99 ** 3, -10, 10, N, support))
+    # SAC critic target: the real SAC.update_critic on a namespace, target_Q captured at F.mse_loss
+    B = 64
+    q1, q2 = torch.randn(B, 1, generator=g) * 5, torch.randn(B, 1, generator=g) * 5
+    logp = torch.randn(B, 1, generator=g) - 4
+    rew, done = torch.randn(B, 1, generator=g), (torch.rand(B, 1, generator=g) < 0.2).float()
+    cases = []
+    for backup_entropy, alpha in [(True, 0.2), (False, 0.2), (True, 0.013)]:
+        seen = {}
+        real_mse = F_.mse_loss
+
+        def spy_mse(a, b, *args, **kw):
+            seen["target"] = b.clone()
+            return real_mse(a, b, *args, **kw)
+
+        ns = types.SimpleNamespace(
+            normalize_input=False, encoder_target=lambda o: o, encoder=lambda o: o,
+            get_actions=lambda z=None, logprob=False: (None, None, logp),
+            critic_target=types.SimpleNamespace(get_q_min=lambda z, a: torch.min(torch.stack([q1, q2]), dim=0).values),
+            critic=types.SimpleNamespace(get_q_values=lambda z, a: [torch.zeros(B, 1), torch.zeros(B, 1)]),
+            sac_config=rs.to_attr(dict(backup_entropy=backup_entropy, gamma=0.99, nstep=3, alpha=alpha)),
+            critic_optim=None, optimizer_update=lambda opt, loss: torch.zeros(()))
+        ns.get_alpha = lambda detach=True, scalar=False: sac_mod.SAC.get_alpha(ns, detach, scalar)
+        sac_mod.F.mse_loss = spy_mse   # (sac.py's `F` IS torch.nn.functional: restored right below)
+        try:
+            sac_mod.SAC.update_critic(ns, {"obs": torch.zeros(B, 3)}, torch.zeros(B, 2), rew, {"obs": torch.zeros(B, 3)}, done)
+        finally:
+            sac_mod.F.mse_loss = real_mse
+        cases.append(dict(backup_entropy=backup_entropy, alpha=alpha, gamma=0.99, nstep=3, target=seen["target"]))
+    out["sac_target"] = dict(q=[q1, q2], log_prob=logp, reward=rew, done=done, cases=cases)
+    save("offpolicy", out)
+
+
 # ---- K3c/K3d: ReplayBuffer --------------------------------------------------------------------------
 def gen_replay():
     g = torch.Generator().manual_seed(7)
@@ -336,6 +392,7 @@ if __name__ == "__main__":
     gen_tdlambda()
     gen_critic_dataset()
     gen_shac_critic()
+    gen_offpolicy()
     gen_replay()
     gen_nstep()
     gen_losses()

@@ -244,6 +244,43 @@ def shac_update_critic(params, prefixes, optim, obs_flat, target_flat, batch_siz
 
 
 # --------------------------------------------------------------------------
+# 8(f)-2  SAC / DDPG update math     mineral/agents/ddpg/utils.py:8-31,
+#         mineral/agents/sac/sac.py:293-297, mineral/agents/ddpg/ddpg.py:292-293
+# --------------------------------------------------------------------------
+
+
+def soft_update(target, current, tau):
+    """tar.mul_(1.0 - tau).add_(cur * tau) on one tensor (ddpg/utils.py:8-11); returns the new target."""
+    return target.clone().mul_(1.0 - tau).add_(current * tau)
+
+
+def td_target(q_values, reward, done, gamma, nstep=1, alpha=None, log_prob=None):
+    """sac.py:293-297 / ddpg.py:292-293."""
+    target_q = torch.min(torch.stack(list(q_values)), dim=0).values
+    if alpha is not None:
+        target_q = target_q - alpha * log_prob
+    return reward + (1 - done) * (gamma ** nstep) * target_q
+
+
+def distl_projection(next_dist, reward, done, gamma, v_min=-10, v_max=10, num_atoms=51, support=None):
+    """C51 projection (ddpg/utils.py:14-31) as explicit per-row loops in the reference's accumulation order."""
+    delta_z = (v_max - v_min) / (num_atoms - 1)
+    target_z = (reward + (1 - done) * gamma * support).clamp(min=v_min, max=v_max)
+    b = (target_z - v_min) / delta_z
+    l, u = b.floor().long(), b.ceil().long()
+    l[torch.logical_and(u > 0, l == u)] -= 1
+    u[torch.logical_and(l < (num_atoms - 1), l == u)] += 1
+    out = torch.zeros_like(next_dist)
+    lo_w, up_w = next_dist * (u.float() - b), next_dist * (b - l.float())
+    for i in range(next_dist.shape[0]):
+        for j in range(num_atoms):
+            out[i, l[i, j]] += lo_w[i, j]
+        for j in range(num_atoms):
+            out[i, u[i, j]] += up_w[i, j]
+    return out
+
+
+# --------------------------------------------------------------------------
 # K3c/K3d  circular replay          mineral/buffers/simple_replay.py:19-85
 # --------------------------------------------------------------------------
 

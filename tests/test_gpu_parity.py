@@ -694,6 +694,43 @@ def test_episode_accounting_on_device(N, L, done_p):
     assert [ring_l[i] for i in order] == [float(v) for v in win_l]
 
 
+def test_offpolicy_math_matches_reference_golden():
+    """8(f)-2: Polyak update, SAC / DDPG TD target and the C51 projection on the B200 kernels, BIT-exact against the
+    reference's own functions (goldens), plus larger seeded cases against the oracle."""
+    import torch.nn as nn
+
+    from mineral_b200.agents.ddpg import utils as du
+
+    c = load_golden("offpolicy")
+    su = c["soft_update"]
+    tar, cur = nn.Linear(7, 5).to(DEV), nn.Linear(7, 5).to(DEV)
+    tar.load_state_dict(su["target_before"]), cur.load_state_dict(su["current"])
+    du.soft_update(tar, cur, su["tau"])
+    for k, v in su["target_after"].items():
+        eq(tar.state_dict()[k], v, f"soft_update {k}")
+    d = c["distl"]
+    got = du.distl_projection(cu(d["next_dist"]), cu(d["reward"]), cu(d["done"]), d["gamma"], d["v_min"], d["v_max"], d["num_atoms"], d["support"])
+    eq(got, d["proj"], "distl_projection")
+    s = c["sac_target"]
+    for case in s["cases"]:
+        got = du.td_target([cu(q) for q in s["q"]], cu(s["reward"]), cu(s["done"]), case["gamma"], case["nstep"],
+                           case["alpha"] if case["backup_entropy"] else None, cu(s["log_prob"]))
+        eq(got, case["target"], f"sac target {case['backup_entropy']} {case['alpha']}")
+    # larger seeded cases vs the oracle (SAC batch 8192 of cfg4; flat Polyak over a 400k-parameter buffer)
+    g = torch.Generator().manual_seed(9)
+    B = 8192
+    qs = [5 * torch.randn(B, 1, generator=g) for _ in range(3)]
+    lp, rew, dn = torch.randn(B, 1, generator=g) - 3, torch.randn(B, 1, generator=g), (torch.rand(B, 1, generator=g) < 0.1).float()
+    eq(du.td_target([cu(q) for q in qs], cu(rew), cu(dn), 0.99, 3, 0.07, cu(lp)), oc.td_target(qs, rew, dn, 0.99, 3, 0.07, lp), "td_target 8192")
+    eq(du.td_target([cu(q) for q in qs[:1]], cu(rew), cu(dn), 0.99, 1), oc.td_target(qs[:1], rew, dn, 0.99, 1), "ddpg target")
+    t, cflat = torch.randn(400_003, generator=g), torch.randn(400_003, generator=g)
+    eq(du.soft_update_flat(cu(t.clone()), cu(cflat), 0.005), oc.soft_update(t, cflat, 0.005), "flat polyak")
+    nd = torch.softmax(torch.randn(300, 51, generator=g), dim=1)
+    rew2, dn2 = 4 * torch.randn(300, 1, generator=g), (torch.rand(300, 1, generator=g) < 0.2).float()
+    sup = torch.linspace(-10, 10, 51)
+    eq(du.distl_projection(cu(nd), cu(rew2), cu(dn2), 0.99, -10, 10, 51, sup), oc.distl_projection(nd, rew2, dn2, 0.99, -10, 10, 51, sup), "distl 300")
+
+
 def test_ppo_first_step_gradients_vs_oracle():
     """Gradients of the first optimizer step (before any parameter moved) within 1e-5 of scale."""
     for c in load_golden("ppo_e2e"):

@@ -170,3 +170,19 @@ def test_shac_update_critic_matches_reference():
             assert torch.equal(torch.stack(res[k]), v), k
         for k, v in c["final_state_dict"].items():
             assert torch.equal(params[k].detach(), v), k
+
+
+def test_offpolicy_math_matches_reference():
+    """8(f)-2: oracle restatements of soft_update / distl_projection / the SAC critic target == the reference's own."""
+    c = load_golden("offpolicy")
+    su = c["soft_update"]
+    for k in su["target_before"]:
+        assert torch.equal(oc.soft_update(su["target_before"][k], su["current"][k], su["tau"]), su["target_after"][k]), k
+    d = c["distl"]
+    assert torch.equal(oc.distl_projection(d["next_dist"], d["reward"], d["done"], d["gamma"], d["v_min"], d["v_max"], d["num_atoms"],
+                                           d["support"]), d["proj"])
+    s = c["sac_target"]
+    for case in s["cases"]:
+        got = oc.td_target(s["q"], s["reward"], s["done"], case["gamma"], case["nstep"], case["alpha"] if case["backup_entropy"] else None,
+                           s["log_prob"])
+        assert torch.equal(got, case["target"]), case
