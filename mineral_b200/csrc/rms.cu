@@ -7,7 +7,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 256;           // columns per CTA (gridDim.z chunks when cols > 256)
-constexpr int kElemsPerThread = 48;   // slab sizing
+constexpr int kElemsPerThread = 64;   // slab sizing (4 rounds of 16 loads in flight)
 
 struct MomentsPlan {
   int n_groups, slabs, chunks;
@@ -22,8 +22,15 @@ MomentsPlan plan_moments(int64_t rows, int cols, int64_t group_rows) {
   int64_t slab_rows = ((int64_t)kThreads * kElemsPerThread) / cw;
   if (slab_rows < 1) slab_rows = 1;
   if (slab_rows > group_rows) slab_rows = group_rows;
-  p.slab_rows = slab_rows;
   p.slabs = (int)((group_rows + slab_rows - 1) / slab_rows);
+  // no more CTAs than ~4 per SM over all (group, chunk) pairs: every extra slab is one more partial for the final merge
+  const int64_t max_slabs = ((int64_t)mnr_sm_count() * 4 + (int64_t)p.n_groups * p.chunks - 1) / ((int64_t)p.n_groups * p.chunks);
+  if (p.slabs > max_slabs) {
+    p.slabs = (int)(max_slabs < 1 ? 1 : max_slabs);
+    slab_rows = (group_rows + p.slabs - 1) / p.slabs;
+    p.slabs = (int)((group_rows + slab_rows - 1) / slab_rows);
+  }
+  p.slab_rows = slab_rows;
   return p;
 }
 
@@ -54,7 +61,16 @@ __global__ void __launch_bounds__(kThreads) batch_moments_kernel(const float* __
   if (active) {
     const float* p = x + col0 + c;
     int64_t r = r_begin + r_local;
-    for (; r + 3 * (int64_t)rpar < r_end; r += 4 * (int64_t)rpar) {  // 4 independent loads in flight
+    // 16 independent loads in flight per thread: with 4 the kernel sat at 5 % of the HBM peak, bound by
+    // bytes-in-flight (Little's law), not by the Welford arithmetic
+    for (; r + 15 * (int64_t)rpar < r_end; r += 16 * (int64_t)rpar) {
+      float a[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) a[u] = mnr::ld_stream(p + (r + (int64_t)u * rpar) * cols);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) w.push(a[u]);
+    }
+    for (; r + 3 * (int64_t)rpar < r_end; r += 4 * (int64_t)rpar) {
       const float a0 = mnr::ld_stream(p + r * cols), a1 = mnr::ld_stream(p + (r + rpar) * cols);
       const float a2 = mnr::ld_stream(p + (r + 2 * rpar) * cols), a3 = mnr::ld_stream(p + (r + 3 * rpar) * cols);
       w.push(a0), w.push(a1), w.push(a2), w.push(a3);
@@ -75,11 +91,32 @@ __global__ void __launch_bounds__(kThreads) batch_moments_kernel(const float* __
 
   unsigned int* ticket = tickets + (size_t)group * gridDim.z + chunk;
   if (!mnr::last_block_ticket(ticket, (unsigned int)slabs)) return;
+  // last CTA of the (group, chunk): merge the slabs' partials.  Thread (r_local, c) takes slabs r_local, r_local + rpar, ..
+  // (independent loads, short dependent chain of f64 Chan merges), then the same fixed-order tree over r_local as above:
+  // a single thread per column walking all slabs was a serial chain of `slabs` L2 round trips + f64 divisions and took
+  // most of the kernel's time.
+  mnr::Moments m{0, 0, 0};
+  if (active) {
+    const mnr::Moments* pp = partials + (size_t)group * slabs * cols + col0 + c;
+    int s = r_local;
+    for (; s + 3 * rpar < slabs; s += 4 * rpar) {  // 4 partials in flight, merged in slab order
+      const mnr::Moments p0 = pp[(size_t)s * cols], p1 = pp[(size_t)(s + rpar) * cols];
+      const mnr::Moments p2 = pp[(size_t)(s + 2 * rpar) * cols], p3 = pp[(size_t)(s + 3 * rpar) * cols];
+      m = mnr::moments_merge(mnr::moments_merge(mnr::moments_merge(mnr::moments_merge(m, p0), p1), p2), p3);
+    }
+    for (; s < slabs; s += rpar) m = mnr::moments_merge(m, pp[(size_t)s * cols]);
+  }
+  __syncthreads();
+  sm[tid] = m;
+  __syncthreads();
+  for (int s = top >> 1; s > 0; s >>= 1) {
+    if (active && r_local < s && r_local + s < rpar) sm[tid] = mnr::moments_merge(sm[tid], sm[tid + s * cw]);
+    __syncthreads();
+  }
   if (tid < cw) {
-    mnr::Moments m{0, 0, 0};
-    for (int s = 0; s < slabs; ++s) m = mnr::moments_merge(m, partials[((size_t)group * slabs + s) * cols + col0 + tid]);
-    mean_out[(size_t)group * cols + col0 + tid] = (float)m.mean;
-    var_out[(size_t)group * cols + col0 + tid] = (float)(m.m2 / (m.n - (double)correction));
+    const mnr::Moments t = sm[tid];
+    mean_out[(size_t)group * cols + col0 + tid] = (float)t.mean;
+    var_out[(size_t)group * cols + col0 + tid] = (float)(t.m2 / (t.n - (double)correction));
   }
 }
 
