@@ -644,17 +644,16 @@ class _UpdateEngine:
         m = self.metrics
         res = collections.defaultdict(list)
         names = ('loss/total', 'loss/actor', 'loss/critic', 'loss/bounds', 'loss/entropy', 'clip_frac', 'explained_var')
-        for s in range(self.steps):
-            for j, k in enumerate(names):
-                res[k].append(m[s, j])
-            res['kl'].append(m[s, 7])
-            # column means (1, A): torch.cat(...).mean(0) over them equals the reference's value
-            res['mu'].append(self.mu_mean[s:s + 1])
-            res['sigma'].append(self.sigma_mean[s:s + 1])
-            if a.truncate_grads:
-                res['grad_norm/all'].append(self.grad_norms[s])
-        for ep in range(a.mini_epochs):
-            res['avg_kl'].append(self.avg_kl[ep])
+        # per-step 0-dim views, one unbind per key (the reference's lists of per-step scalars, without 12 x steps indexing ops)
+        for j, k in enumerate(names):
+            res[k] = list(m[:, j].unbind(0))
+        res['kl'] = list(m[:, 7].unbind(0))
+        # column means (1, A): torch.cat(...).mean(0) over them equals the reference's value
+        res['mu'] = list(self.mu_mean.unsqueeze(1).unbind(0))
+        res['sigma'] = list(self.sigma_mean.unsqueeze(1).unbind(0))
+        if a.truncate_grads:
+            res['grad_norm/all'] = list(self.grad_norms.unbind(0))
+        res['avg_kl'] = list(self.avg_kl.unbind(0))
         return res
 
 
