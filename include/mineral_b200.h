@@ -183,6 +183,8 @@ typedef struct {
   const float* mean;  /* kind 4 only */
   const float* denom; /* kind 4 only */
   float clamp_lo, clamp_hi;
+  int32_t dst_ld;     /* row stride of dst in elements; 0 = width (lets a gather write into a column block of a wider buffer) */
+  int32_t _pad;
 } mnr_row_field_t;
 
 #define MNR_MAX_ROW_FIELDS 12
@@ -573,6 +575,57 @@ int mnr_td_target(const mnr_critic_set_t* qs /*host*/, int n_q, const float* log
                   float alpha, float gamma_n, float* out, int64_t rows, mnr_stream_t stream);
 int mnr_distl_projection(const float* next_dist, const float* reward, const float* done, const float* support, float gamma,
                          float v_min, float v_max, float delta_z, int n_atoms, float* out, int64_t rows, mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * 8(f)-2 (agents)  row-wise math of the SAC / DDPG agents around the tower GEMMs (mineral/agents/sac/sac.py,
+ *      mineral/agents/ddpg/ddpg.py, mineral/agents/ddpg/models.py, mineral/nets/dist.py, mineral/nets/distributions.py).
+ *      mnr_copy_cols_f32:    dst[r, 0:cols) = src[r, 0:cols) with row strides (the `torch.cat((state, action), 1)` of
+ *                            EnsembleQ.forward, ddpg/models.py:102-106, written into a padded critic-input buffer).
+ *      mnr_squashed_sample:  SAC.get_actions (sac.py:119-136): sigma from logstd per Dist.forward (dist.py:37-52;
+ *                            logstd (rows,A), or (A) when logstd_broadcast), u = mu + sigma * eps, actions = tanh(u) written
+ *                            with row stride act_ld, log_prob (rows) = sum_j [Normal.log_prob(u) - log|d tanh/du|]
+ *                            (distributions.py:10-37).  eps NULL: actions = mu (the deterministic branch), log_prob untouched.
+ *      mnr_squashed_bwd:     gradient of (alpha/rows) * sum log_prob + <g_actions, actions> w.r.t. (mu, logstd) through the
+ *                            reparameterised sample; alpha = exp(*log_alpha) read on the device, or alpha_host when NULL.
+ *      mnr_tanh_action(_bwd): DDPG / TD3 actor output a = tanh(mu) [+ clamp(noise)] [clamped] (ddpg/models.py:55-58,
+ *                            noise.py:22-38; lo > hi disables a clamp) and d/dmu = g (1 - tanh^2).
+ *      mnr_td_target_stats:  mnr_td_target with the temperature on the device + {mean, std (unbiased), max, min} of the
+ *                            target (sac.py:306-311) into stats[4] (may be NULL).  One CTA, deterministic.
+ *      mnr_actor_seed:       q_min over qs->pred[0..n_q) (first minimum on ties), d actor_loss / d Q_k = -1/rows at the
+ *                            argmin into qs->grad[k]; out4 = {actor_loss = mean(alpha*log_prob - q_min), entropy =
+ *                            mean(-log_prob), alpha_loss = alpha * mean(-log_prob - target_entropy), alpha};
+ *                            *log_alpha_grad = d alpha_loss / d log_alpha (sac.py:313-332; log_prob NULL = DDPG, ddpg.py:299-310).
+ *      mnr_critic_mse_sum_fwd_bwd: mnr_critic_mse_fwd_bwd with the SUM over critics (sac.py:303, ddpg.py:296).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  int32_t dist_type;       /* 0 squashed_normal, 1 dreamerv3_squashed_normal */
+  int32_t has_minlogstd, has_maxlogstd;
+  float minlogstd, maxlogstd; /* squashed_normal: torch.clamp bounds on logstd */
+  float minstd, maxstd;       /* dreamerv3_squashed_normal */
+  int32_t _pad;
+} mnr_squash_cfg_t;
+int mnr_copy_cols_f32(const float* src, int src_ld, float* dst, int dst_ld, int64_t rows, int cols, mnr_stream_t stream);
+int mnr_squashed_sample(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, int64_t rows, int A,
+                        const mnr_squash_cfg_t* cfg /*host*/, float* actions, int act_ld, float* log_prob, mnr_stream_t stream);
+int mnr_squashed_bwd(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, const float* g_actions, int g_ld,
+                     const float* log_alpha, float alpha_host, int64_t rows, int A, const mnr_squash_cfg_t* cfg /*host*/, float* g_mu,
+                     float* g_logstd, mnr_stream_t stream);
+int mnr_tanh_action(const float* mu, const float* noise, int64_t rows, int A, float noise_lo, float noise_hi, float out_lo,
+                    float out_hi, float* actions, int act_ld, mnr_stream_t stream);
+int mnr_tanh_action_bwd(const float* mu, const float* g_actions, int g_ld, int64_t rows, int A, float* g_mu, mnr_stream_t stream);
+int mnr_td_target_stats(const mnr_critic_set_t* qs /*host*/, int n_q, const float* log_prob, const float* reward, const float* done,
+                        const float* log_alpha, float alpha_host, float gamma_n, float* out, int64_t rows, float* stats,
+                        mnr_stream_t stream);
+int mnr_actor_seed(const mnr_critic_set_t* qs /*host*/, int n_q, const float* log_prob, const float* log_alpha, float alpha_host,
+                   float target_entropy, int64_t rows, float* out4, float* log_alpha_grad, mnr_stream_t stream);
+/* One env step of SAC/DDPG.explore_env (sac.py:163-177, ddpg.py:176-190) into the (N, T, .) trajectory tensors at step t:
+ * obs / next_obs (N,O), actions (N,A), rewards (N) * reward_scale (RewardShaper 'scale'), dones (u8/bool) masked by
+ * time_outs (u8/bool, may be NULL; Agent._handle_timeout, agent.py:158-167) stored as f32 0/1. */
+int mnr_traj_store_step(const float* obs, const float* next_obs, const float* actions, const float* rewards, const void* dones,
+                        const void* time_outs, int N, int O, int A, int T, int t, float reward_scale, float* traj_obs,
+                        float* traj_next_obs, float* traj_actions, float* traj_rewards, float* traj_dones, mnr_stream_t stream);
+int mnr_critic_mse_sum_fwd_bwd(const mnr_critic_set_t* set /*host*/, int n_critics, const float* target, int64_t rows,
+                               float* loss_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -41,7 +41,8 @@ class WideField(C.Structure):
 
 class RowField(C.Structure):
     _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("width", C.c_int32), ("kind", C.c_int32),
-                ("mean", C.c_void_p), ("denom", C.c_void_p), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float)]
+                ("mean", C.c_void_p), ("denom", C.c_void_p), ("clamp_lo", C.c_float), ("clamp_hi", C.c_float),
+                ("dst_ld", C.c_int32), ("_pad", C.c_int32)]
 
 
 class NStepIn(C.Structure):
@@ -89,6 +90,11 @@ class TcReduceJob(C.Structure):
 
 class CriticSet(C.Structure):
     _fields_ = [("pred", C.c_void_p * 4), ("grad", C.c_void_p * 4)]
+
+
+class SquashCfg(C.Structure):
+    _fields_ = [("dist_type", C.c_int32), ("has_minlogstd", C.c_int32), ("has_maxlogstd", C.c_int32), ("minlogstd", C.c_float),
+                ("maxlogstd", C.c_float), ("minstd", C.c_float), ("maxstd", C.c_float), ("_pad", C.c_int32)]
 
 
 class PeerCommStruct(C.Structure):
@@ -166,6 +172,15 @@ SIGNATURES = {
     "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),
     "mnr_critic_mse_workspace_bytes": (sz, [i64]),
     "mnr_critic_mse_fwd_bwd": (i32, [C.POINTER(CriticSet), i32, vp, i64, vp, vp, sz, vp]),
+    "mnr_critic_mse_sum_fwd_bwd": (i32, [C.POINTER(CriticSet), i32, vp, i64, vp, vp, sz, vp]),
+    "mnr_traj_store_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
+    "mnr_copy_cols_f32": (i32, [vp, i32, vp, i32, i64, i32, vp]),
+    "mnr_squashed_sample": (i32, [vp, vp, i32, vp, i64, i32, C.POINTER(SquashCfg), vp, i32, vp, vp]),
+    "mnr_squashed_bwd": (i32, [vp, vp, i32, vp, vp, i32, vp, f32, i64, i32, C.POINTER(SquashCfg), vp, vp, vp]),
+    "mnr_tanh_action": (i32, [vp, vp, i64, i32, f32, f32, f32, f32, vp, i32, vp]),
+    "mnr_tanh_action_bwd": (i32, [vp, vp, i32, i64, i32, vp, vp]),
+    "mnr_td_target_stats": (i32, [C.POINTER(CriticSet), i32, vp, vp, vp, vp, f32, f32, vp, i64, vp, vp]),
+    "mnr_actor_seed": (i32, [C.POINTER(CriticSet), i32, vp, vp, f32, f32, i64, vp, vp, vp]),
     "mnr_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),
     "mnr_peer_open": (i32, [vp, C.POINTER(vp)]),
     "mnr_peer_close": (i32, [vp]),
@@ -233,6 +248,20 @@ def ptr(t, dtype=None, name="tensor", allow_none=False):
         if not ok:
             raise MineralB200Error(f"{name} has dtype {t.dtype}, expected {dtype}")
     return C.c_void_p(t.data_ptr())
+
+
+def ptr_view(t, name="tensor"):
+    """Device pointer of a CUDA view with unit stride in its last dimension (rows may be strided; the caller passes the stride)."""
+    if t is None or not t.is_cuda or t.stride(-1) != 1:
+        raise MineralB200Error(f"{name} must be a CUDA view with unit column stride")
+    return C.c_void_p(t.data_ptr())
+
+
+def ptr_strided(t, name="tensor"):
+    """Device pointer + row stride (floats) of a 2-D f32 CUDA view whose rows are contiguous (e.g. a column slice of a padded buffer)."""
+    if t is None or not t.is_cuda or t.dtype != torch.float32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise MineralB200Error(f"{name} must be a 2-D f32 CUDA tensor with unit column stride")
+    return C.c_void_p(t.data_ptr()), int(t.stride(0))
 
 
 _WS = {}

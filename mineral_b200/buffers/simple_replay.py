@@ -67,7 +67,7 @@ class ReplayBuffer:
         self.cur_capacity = self.capacity if self.if_full else self.next_p
 
     @torch.no_grad()
-    def sample_batch(self, batch_size, device='cuda', indices=None, obs_rms=None):
+    def sample_batch(self, batch_size, device='cuda', indices=None, obs_rms=None, out=None):
         """Uniform sample with replacement (simple_replay.py:73-85): indices from torch.randint on
         `device`, then ONE gather launch for obs / action / reward / next_obs / done->f32.
 
@@ -78,11 +78,18 @@ class ReplayBuffer:
             indices = torch.randint(self.cur_capacity, size=(batch_size,), device=device)
         n = indices.numel()
         f32 = dict(dtype=torch.float32, device=self.buf_action.device)
-        obs = {k: torch.empty((n, *self.obs_space[k]), **f32) for k in self.buf_obs}
-        next_obs = {k: torch.empty((n, *self.obs_space[k]), **f32) for k in self.buf_next_obs}
-        action = torch.empty((n, self.action_dim), **f32)
-        reward = torch.empty((n, 1), **f32)
-        done = torch.empty((n, 1), **f32)
+        out = {} if out is None else out
+        # `out`: destination views for 'obs' / 'next_obs' ({key: view}), 'action', 'reward', 'done' - e.g. column blocks of the
+        # padded (batch, obs+act) critic-input buffers, so the `torch.cat((state, action), 1)` of EnsembleQ.forward
+        # (mineral/agents/ddpg/models.py:102-106) costs nothing.  Views need unit column stride; rows may be strided.
+        obs = {k: out['obs'][k] if 'obs' in out else torch.empty((n, *self.obs_space[k]), **f32) for k in self.buf_obs}
+        next_obs = {k: out['next_obs'][k] if 'next_obs' in out else torch.empty((n, *self.obs_space[k]), **f32) for k in self.buf_next_obs}
+        action = out['action'] if 'action' in out else torch.empty((n, self.action_dim), **f32)
+        reward = out['reward'] if 'reward' in out else torch.empty((n, 1), **f32)
+        done = out['done'] if 'done' in out else torch.empty((n, 1), **f32)
+
+        def ld(t):
+            return 0 if t.is_contiguous() else int(t.stride(0))
         kind = ROW_F32
         fields = []
         for k in self.buf_obs:
@@ -90,12 +97,12 @@ class ReplayBuffer:
             if obs_rms is not None and hasattr(obs_rms[k], 'running_mean'):
                 m, d = obs_rms[k]._prepare()
                 lo, hi = obs_rms[k].clamp_range if obs_rms[k].with_clamp else (1.0, -1.0)
-                fields.append((self.buf_obs[k], obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi))
-                fields.append((self.buf_next_obs[k], next_obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi))
+                fields.append((self.buf_obs[k], obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(obs[k])))
+                fields.append((self.buf_next_obs[k], next_obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(next_obs[k])))
             else:
-                fields.append((self.buf_obs[k], obs[k], w, kind))
-                fields.append((self.buf_next_obs[k], next_obs[k], w, kind))
-        fields.append((self.buf_action, action, self.action_dim, ROW_F32))
+                fields.append((self.buf_obs[k], obs[k], w, kind, None, None, None, None, ld(obs[k])))
+                fields.append((self.buf_next_obs[k], next_obs[k], w, kind, None, None, None, None, ld(next_obs[k])))
+        fields.append((self.buf_action, action, self.action_dim, ROW_F32, None, None, None, None, ld(action)))
         fields.append((self.buf_reward, reward, 1, ROW_F32))
         fields.append((self.buf_done, done, 1, ROW_BOOL_TO_F32))
         ops.gather_rows(fields, idx=indices.to(self.buf_action.device))

@@ -29,7 +29,7 @@ __device__ __forceinline__ float clamp_nan(float y, float lo, float hi) {
 }
 
 __device__ __forceinline__ void move_elem(const mnr_row_field_t& fd, int64_t src_row, int64_t dst_row, int e) {
-  const int64_t si = src_row * fd.width + e, di = dst_row * fd.width + e;
+  const int64_t si = src_row * fd.width + e, di = dst_row * (fd.dst_ld > 0 ? fd.dst_ld : fd.width) + e;
   switch (fd.kind) {
     case MNR_ROW_F32:
       static_cast<float*>(fd.dst)[di] = __ldg(static_cast<const float*>(fd.src) + si);
@@ -96,7 +96,7 @@ int pack_fields(const mnr_row_field_t* fields, int n_fields, RowFields* out) {
   out->start[0] = 0;
   for (int k = 0; k < n_fields; ++k) {
     if (!fields[k].src || !fields[k].dst) return MNR_ENULL;
-    if (fields[k].width <= 0) return MNR_ESHAPE;
+    if (fields[k].width <= 0 || (fields[k].dst_ld != 0 && fields[k].dst_ld < fields[k].width)) return MNR_ESHAPE;
     if (fields[k].kind < 0 || fields[k].kind > MNR_ROW_F32_NORMALIZE) return MNR_EUNSUP;
     if (fields[k].kind == MNR_ROW_F32_NORMALIZE && (!fields[k].mean || !fields[k].denom)) return MNR_ENULL;
     out->f[k] = fields[k];

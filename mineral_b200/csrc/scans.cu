@@ -104,8 +104,11 @@ extern "C" int mnr_critic_targets_f32(const float* rew, const float* done_mask, 
 namespace {
 constexpr int kMseThreads = 256;
 __global__ void __launch_bounds__(kMseThreads) critic_mse_kernel(const mnr_critic_set_t set, int n_critics, const float* __restrict__ target,
-                                                                 int64_t rows, float* __restrict__ loss_out, unsigned char* __restrict__ workspace) {
-  const float gscale = 2.0f / ((float)rows * (float)n_critics);
+                                                                 int64_t rows, float* __restrict__ loss_out, unsigned char* __restrict__ workspace,
+                                                                 int sum_over_critics) {
+  // mean over critics (SHAC, shac.py:869-875) or sum over critics (SAC / DDPG, sac.py:303, ddpg.py:296)
+  const float n_div = sum_over_critics ? 1.0f : (float)n_critics;
+  const float gscale = 2.0f / ((float)rows * n_div);
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * kMseThreads + threadIdx.x; i < rows; i += (int64_t)gridDim.x * kMseThreads) {
     const float t = __ldg(target + i);
@@ -124,7 +127,7 @@ __global__ void __launch_bounds__(kMseThreads) critic_mse_kernel(const mnr_criti
   double mine = 0.0;
   for (unsigned int x = threadIdx.x; x < gridDim.x; x += kMseThreads) mine += parts[x];
   const double all = mnr::block_sum(mine);
-  if (threadIdx.x == 0) *loss_out = (float)(all / ((double)rows * (double)n_critics));
+  if (threadIdx.x == 0) *loss_out = (float)(all / ((double)rows * (double)n_div));
 }
 int mse_grid(int64_t rows) {
   int64_t g = (rows + kMseThreads - 1) / kMseThreads;
@@ -138,14 +141,25 @@ extern "C" size_t mnr_critic_mse_workspace_bytes(int64_t rows) {
   return 256 + (size_t)mnr_sm_count() * 4 * sizeof(double);
 }
 
-extern "C" int mnr_critic_mse_fwd_bwd(const mnr_critic_set_t* set, int n_critics, const float* target, int64_t rows, float* loss_out,
-                                      void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
+static int critic_mse_launch(const mnr_critic_set_t* set, int n_critics, const float* target, int64_t rows, float* loss_out,
+                             void* workspace, size_t workspace_bytes, mnr_stream_t stream, int sum_over_critics) {
   MNR_CHECK_PTR(set); MNR_CHECK_PTR(target); MNR_CHECK_PTR(loss_out); MNR_CHECK_PTR(workspace);
   if (n_critics <= 0 || n_critics > MNR_MAX_CRITICS || rows <= 0) return MNR_ESHAPE;
   if (workspace_bytes < mnr_critic_mse_workspace_bytes(rows)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 8)) return MNR_EALIGN;
   for (int k = 0; k < n_critics; ++k)
     if (!set->pred[k] || !set->grad[k]) return MNR_ENULL;
-  critic_mse_kernel<<<mse_grid(rows), kMseThreads, 0, mnr_cs(stream)>>>(*set, n_critics, target, rows, loss_out, (unsigned char*)workspace);
+  critic_mse_kernel<<<mse_grid(rows), kMseThreads, 0, mnr_cs(stream)>>>(*set, n_critics, target, rows, loss_out, (unsigned char*)workspace,
+                                                                        sum_over_critics);
   MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_critic_mse_fwd_bwd(const mnr_critic_set_t* set, int n_critics, const float* target, int64_t rows, float* loss_out,
+                                      void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
+  return critic_mse_launch(set, n_critics, target, rows, loss_out, workspace, workspace_bytes, stream, 0);
+}
+
+extern "C" int mnr_critic_mse_sum_fwd_bwd(const mnr_critic_set_t* set, int n_critics, const float* target, int64_t rows, float* loss_out,
+                                          void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
+  return critic_mse_launch(set, n_critics, target, rows, loss_out, workspace, workspace_bytes, stream, 1);
 }

@@ -151,9 +151,12 @@ class TowerStack:
                                      mean=self.mean[i][g], rstd=self.rstd[i][g]) for g in range(G)], M, n, self.norm[0][i].eps, self.act)
             inp = self.Y[i]
 
-    def backward(self, x, rows=None):
+    def backward(self, x, rows=None, weight_grads=True, input_grad=None):
         """Layers top first, from self.dY[-1]; writes every .grad.  Without a norm, act'(.) is applied on the fly from the
-        saved outputs inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta)."""
+        saved outputs inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta).
+        weight_grads=False skips the weight-gradient GEMMs (a frozen network that is only differentiated through, e.g. the
+        critics inside SAC.update_actor, sac.py:313-326; LayerNorm's dgamma / dbeta are still written and are garbage to
+        the caller).  input_grad: contiguous (rows, in_dim) tensor receiving d loss / d x summed over the towers."""
         M = self.M if rows is None else rows
         G, top = self.G, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
@@ -170,13 +173,20 @@ class TowerStack:
             saved = [None] * G if self.normed else self.Y[i]
             wg = [dict(a=self.dY[i][g], b=src[g], c=self.lin[g][i].weight.grad, saved=saved[g], bias_grad=self.lin[g][i].bias.grad, N=n, K=k,
                        ldb=ldb) for g in range(G)]
-            if tc:
+            if not weight_grads:
+                pass
+            elif tc:
                 pending.append(ops.tc_linear_bwd_weight_partials(wg, M, self.gemm_act, self.tc_ws[i]))
                 if len(pending) == 4:
                     ops.tc_reduce_partials(pending)
                     pending = []
             else:
                 ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
+            if i == 0 and input_grad is not None:
+                # the first layer's K is the raw input width (not a tensor-core shape): SIMT kernel, contiguous (rows, K) output
+                for g in range(G):  # one launch per tower: the second accumulates onto the first's result
+                    ops.linear_bwd_input([dict(a=self.dY[0][g], b=self.lin[g][0].weight.data, c=input_grad, saved=saved[g], N=n, K=k)],
+                                         M, self.gemm_act, accumulate=g > 0)
             if i > 0:
                 if self.use_tc:
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],

@@ -152,14 +152,20 @@ def rms_apply(x, mean_f32, denom_f32, clamp=None, inverse=False, out=None):
 # K3  rows
 # ---------------------------------------------------------------------------------------------
 def _row_fields(fields):
-    """fields: list of (src, dst, width, kind[, mean, denom, lo, hi])."""
+    """fields: list of (src, dst, width, kind[, mean, denom, lo, hi[, dst_ld]]).  With dst_ld, dst may be a column block of a
+    wider row-major buffer (rows dst_ld elements apart)."""
     arr = (nv.RowField * len(fields))()
     for i, f in enumerate(fields):
         src, dst, width, kind = f[:4]
         mean = ptr(f[4], F32).value if len(f) > 4 and f[4] is not None else None
         denom = ptr(f[5], F32).value if len(f) > 5 and f[5] is not None else None
-        lo, hi = (f[6], f[7]) if len(f) > 7 else (1.0, -1.0)
-        arr[i] = nv.RowField(ptr(src, name="row src").value, ptr(dst, name="row dst").value, width, kind, mean, denom, lo, hi)
+        lo, hi = (f[6], f[7]) if len(f) > 7 and f[6] is not None else (1.0, -1.0)
+        dst_ld = int(f[8]) if len(f) > 8 and f[8] else 0
+        if dst_ld:
+            dptr = nv.ptr_view(dst, "strided row dst").value
+        else:
+            dptr = ptr(dst, name="row dst").value
+        arr[i] = nv.RowField(ptr(src, name="row src").value, dptr, width, kind, mean, denom, lo, hi, dst_ld, 0)
     return arr
 
 
@@ -437,3 +443,97 @@ def episode_scores(rewards, dones, cur_rewards, cur_lengths, win_rewards, win_le
     check(lib.mnr_episode_scores(ptr(rewards, F32, "rewards"), ptr(dones, (U8, BOOL), "dones"), ptr(cur_rewards, F32), ptr(cur_lengths, I64),
                                  ptr(win_rewards, F32), ptr(win_lengths, F32), ptr(counters, I64), rewards.numel(), win_rewards.numel(),
                                  stream()), "mnr_episode_scores")
+
+
+# ---------------------------------------------------------------------------------------------
+# 8(f)-2  SAC / DDPG agents: row-wise math around the tower GEMMs (csrc/offpolicy.cu)
+# ---------------------------------------------------------------------------------------------
+def _critic_set(preds, grads=None):
+    cs = nv.CriticSet()
+    for k, p_ in enumerate(preds):
+        cs.pred[k] = ptr(p_, F32, "pred").value
+        if grads is not None:
+            cs.grad[k] = ptr(grads[k], F32, "grad").value
+    return cs
+
+
+def critic_mse_sum_fwd_bwd(preds, target, grads, loss_out, ws):
+    """sum_k MSE(Q_k, target) (sac.py:303, ddpg.py:296) and its gradient w.r.t. every Q_k, one launch."""
+    cs = _critic_set(preds, grads)
+    check(lib.mnr_critic_mse_sum_fwd_bwd(C.byref(cs), len(preds), ptr(target, F32, "target"), target.numel(), ptr(loss_out, F32),
+                                         ptr(ws, U8), ws.numel(), stream()), "mnr_critic_mse_sum_fwd_bwd")
+
+
+def make_squash_cfg(dist_type="squashed_normal", minlogstd=None, maxlogstd=None, minstd=1.0, maxstd=1.0):
+    kinds = {"squashed_normal": 0, "dreamerv3_squashed_normal": 1}
+    if dist_type not in kinds:
+        raise nv.MineralB200Error(f"dist_type {dist_type!r} has no squashed-sample kernel")
+    return nv.SquashCfg(kinds[dist_type], int(minlogstd is not None), int(maxlogstd is not None), float(minlogstd or 0.0), float(maxlogstd or 0.0),
+                        float(minstd), float(maxstd), 0)
+
+
+def copy_cols(src, dst):
+    """dst[:, :] = src[:, :] for 2-D f32 views with unit column stride (torch.cat((state, action), 1) into a padded buffer)."""
+    sp, sld = nv.ptr_strided(src, "src")
+    dp, dld = nv.ptr_strided(dst, "dst")
+    assert src.shape == dst.shape
+    check(lib.mnr_copy_cols_f32(sp, sld, dp, dld, src.shape[0], src.shape[1], stream()), "mnr_copy_cols_f32")
+
+
+def squashed_sample(mu, logstd, eps, cfg, actions, log_prob=None, rows=None):
+    """SAC.get_actions after the heads: actions = tanh(mu + sigma * eps) into the (strided) `actions` view, log_prob (rows)."""
+    rows = mu.shape[0] if rows is None else rows
+    A = mu.shape[1]
+    ap, ald = nv.ptr_strided(actions, "actions")
+    check(lib.mnr_squashed_sample(ptr(mu, F32, "mu"), ptr(logstd, F32, "logstd", allow_none=eps is None), int(logstd is not None and logstd.dim() == 1),
+                                  ptr(eps, F32, "eps", allow_none=True), rows, A, C.byref(cfg), ap, ald, ptr(log_prob, F32, allow_none=True),
+                                  stream()), "mnr_squashed_sample")
+
+
+def squashed_bwd(mu, logstd, eps, g_actions, log_alpha, alpha_host, cfg, g_mu, g_logstd, rows=None):
+    rows = mu.shape[0] if rows is None else rows
+    A = mu.shape[1]
+    gp, gld = nv.ptr_strided(g_actions, "g_actions") if g_actions is not None else (None, 0)
+    check(lib.mnr_squashed_bwd(ptr(mu, F32, "mu"), ptr(logstd, F32, "logstd"), int(logstd.dim() == 1), ptr(eps, F32, "eps"), gp, gld,
+                               ptr(log_alpha, F32, allow_none=True), float(alpha_host), rows, A, C.byref(cfg), ptr(g_mu, F32), ptr(g_logstd, F32),
+                               stream()), "mnr_squashed_bwd")
+
+
+def tanh_action(mu, noise, actions, noise_bounds=None, out_bounds=None, rows=None):
+    rows = mu.shape[0] if rows is None else rows
+    nlo, nhi = noise_bounds if noise_bounds is not None else (1.0, -1.0)
+    olo, ohi = out_bounds if out_bounds is not None else (1.0, -1.0)
+    ap, ald = nv.ptr_strided(actions, "actions")
+    check(lib.mnr_tanh_action(ptr(mu, F32, "mu"), ptr(noise, F32, "noise", allow_none=True), rows, mu.shape[1], nlo, nhi, olo, ohi, ap, ald,
+                              stream()), "mnr_tanh_action")
+
+
+def tanh_action_bwd(mu, g_actions, g_mu, rows=None):
+    rows = mu.shape[0] if rows is None else rows
+    gp, gld = nv.ptr_strided(g_actions, "g_actions")
+    check(lib.mnr_tanh_action_bwd(ptr(mu, F32, "mu"), gp, gld, rows, mu.shape[1], ptr(g_mu, F32), stream()), "mnr_tanh_action_bwd")
+
+
+def td_target_stats(q_values, log_prob, reward, done, log_alpha, alpha_host, gamma_n, out, stats=None):
+    cs = _critic_set(q_values)
+    check(lib.mnr_td_target_stats(C.byref(cs), len(q_values), ptr(log_prob, F32, allow_none=True), ptr(reward, F32, "reward"), ptr(done, F32, "done"),
+                                  ptr(log_alpha, F32, allow_none=True), float(alpha_host), float(gamma_n), ptr(out, F32), reward.numel(),
+                                  ptr(stats, F32, allow_none=True), stream()), "mnr_td_target_stats")
+
+
+def actor_seed(q_values, q_grads, log_prob, log_alpha, alpha_host, target_entropy, out4, log_alpha_grad=None):
+    cs = _critic_set(q_values, q_grads)
+    check(lib.mnr_actor_seed(C.byref(cs), len(q_values), ptr(log_prob, F32, allow_none=True), ptr(log_alpha, F32, allow_none=True),
+                             float(alpha_host), float(target_entropy), q_values[0].numel(), ptr(out4, F32), ptr(log_alpha_grad, F32, allow_none=True),
+                             stream()), "mnr_actor_seed")
+
+
+def traj_store_step(obs, next_obs, actions, rewards, dones, time_outs, t, reward_scale, traj_obs, traj_next_obs, traj_actions,
+                    traj_rewards, traj_dones):
+    """One explore_env step into the (N, T, .) trajectory tensors (strided rows), dones masked by time-outs, rewards scaled."""
+    N, T = traj_rewards.shape[0], traj_rewards.shape[1]
+    O, A = obs.shape[1], actions.shape[1]
+    check(lib.mnr_traj_store_step(ptr(obs, F32, "obs"), ptr(next_obs, F32, "next_obs"), ptr(actions, F32, "actions"), ptr(rewards, F32, "rewards"),
+                                  ptr(dones, (U8, BOOL), "dones"), ptr(time_outs, (U8, BOOL), "time_outs", allow_none=True), N, O, A, T, t,
+                                  float(reward_scale), ptr(traj_obs, F32), ptr(traj_next_obs, F32), ptr(traj_actions, F32),
+                                  ptr(traj_rewards, F32), ptr(traj_dones, F32), stream()), "mnr_traj_store_step")

@@ -386,6 +386,143 @@ def gen_ppo_e2e():
     save("ppo_e2e", cases)
 
 
+# ---- 8(f)-2 agents: the real SAC / DDPG agents (explore_env + update_net), random draws recorded -----------------------
+def offpolicy_cfg(algo, N, units, batch_size, mini_epochs, variant):
+    if algo == "sac":
+        mlp = dict(units=units, norm_type="LayerNorm", act_type="SiLU") if variant == "ln_silu" else dict(units=units, act_type="ELU")
+        network = dict(normalize_input=True, encoder=None, actor="Actor", critic="EnsembleQ",
+                       actor_kwargs=dict(mlp_kwargs=mlp, weight_init="orthogonal", tanh_policy=False, fixed_sigma=False,
+                                         dist_kwargs=dict(dist_type="squashed_normal", minlogstd=-5.0, maxlogstd=2.0)),
+                       critic_kwargs=dict(n_critics=2, mlp_kwargs=mlp, weight_init="orthogonal"))
+        algo_cfg = dict(multi_gpu=False, num_actors=N, reward_shaper=dict(fn="scale", scale=0.5), max_agent_steps=1e6, horizon_len=4,
+                        memory_size=1000, batch_size=batch_size, nstep=3, tau=0.05, gamma=0.99, warm_up=8, no_tgt_actor=True, handle_timeout=True,
+                        update_actor_interval=1, update_targets_interval=1, mini_epochs=mini_epochs, init_alpha=1.0, alpha=None,
+                        alpha_optim_kwargs=dict(lr=5e-3), backup_entropy=True, optim_type="AdamW", actor_optim_kwargs=dict(lr=5e-4),
+                        critic_optim_kwargs=dict(lr=5e-4), max_grad_norm=0.5)
+    else:  # AllegroHandDDPG.yaml (TD3-style intervals in the second variant)
+        mlp = dict(units=units, act_type="ELU")
+        td3 = variant == "td3"
+        network = dict(normalize_input=True, encoder=None, actor="Actor", critic="EnsembleQ",
+                       actor_kwargs=dict(tanh_policy=True, mlp_kwargs=mlp), critic_kwargs=dict(n_critics=2, mlp_kwargs=mlp))
+        algo_cfg = dict(multi_gpu=False, num_actors=N, reward_shaper=dict(fn="scale", scale=0.5), max_agent_steps=1e6, horizon_len=4,
+                        memory_size=1000, batch_size=batch_size, nstep=3, tau=0.05, gamma=0.99, warm_up=8, no_tgt_actor=not td3,
+                        handle_timeout=True, update_actor_interval=2 if td3 else 1, update_targets_interval=2 if td3 else 1,
+                        mini_epochs=mini_epochs, optim_type="AdamW", actor_optim_kwargs=dict(lr=5e-4), critic_optim_kwargs=dict(lr=5e-4),
+                        max_grad_norm=0.5, exp_decay_rate=0.99,
+                        noise=dict(type="fixed" if td3 else "mixed", decay=None, exp_decay_rate=0.99, lin_decay_iters=10000, std_max=0.8,
+                                   std_min=0.05, tgt_pol_std=0.8, tgt_pol_noise_bound=0.2))
+    return rs.to_attr(dict(rl_device="cpu", multi_gpu=False, env_render=False, run="train", seed=0, task=dict(env_autoresets=True),
+                           agent={"tracker_len": 100, "metrics_kwargs": {}, "print_every": -1, "ckpt_every": -1, "network": network, algo: algo_cfg}))
+
+
+class _Recorder:
+    """Wraps torch's random entry points the agents use and records every draw, in call order per stream."""
+
+    def __init__(self):
+        import torch.distributions.normal as tdn
+        self.tdn = tdn
+        self.streams = dict(rand=[], randint=[], std_normal=[], normal=[])
+        self.orig = dict(rand=torch.rand, randint=torch.randint, std_normal=tdn._standard_normal, normal=torch.normal)
+
+    def __enter__(self):
+        def wrap(name):
+            def f(*a, **kw):
+                if kw.get("device") == "cuda":   # DDPG samples with sample_batch's default device='cuda' (ddpg.py:244): no GPU here
+                    kw["device"] = "cpu"
+                out = self.orig[name](*a, **kw)
+                self.streams[name].append(out.detach().clone())
+                return out
+            return f
+        torch.rand, torch.randint, torch.normal = wrap("rand"), wrap("randint"), wrap("normal")
+        self.tdn._standard_normal = wrap("std_normal")
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand, torch.randint, torch.normal = self.orig["rand"], self.orig["randint"], self.orig["normal"]
+        self.tdn._standard_normal = self.orig["std_normal"]
+
+
+def gen_offpolicy_e2e():
+    from mineral.agents.ddpg.ddpg import DDPG
+    from mineral.agents.sac.sac import SAC
+    cases = []
+    for algo, variant in (("sac", "ln_silu"), ("sac", "elu"), ("ddpg", "mixed"), ("ddpg", "td3")):
+        N, O, A, units, B, mini_epochs, epochs = 16, 11, 3, [32, 16], 64, 3, 2
+        torch.manual_seed(50)
+        env = rs.SynthEnv(N, O, A, 64, seed=51, done_p=0.08, timeout_p=0.05)
+        cfg = offpolicy_cfg(algo, N, units, B, mini_epochs, variant)
+        Cls = SAC if algo == "sac" else DDPG
+        with open(os.devnull, "w") as devnull:
+            stdout, sys.stdout = sys.stdout, devnull
+            try:
+                agent = Cls(cfg, logdir=tempfile.mkdtemp(), env=env)
+            finally:
+                sys.stdout = stdout
+        acfg = cfg.agent[algo]
+        if algo == "ddpg":   # ddpg.py:244 samples with sample_batch's default device='cuda'; this container has no GPU
+            sample_cpu = agent.memory.sample_batch
+            agent.memory.sample_batch = lambda bs, device="cpu": sample_cpu(bs, device="cpu")
+        init = dict(actor=clone_tree(agent.actor.state_dict()), critic=clone_tree(agent.critic.state_dict()))
+        per_epoch = []
+        with _Recorder() as rec:
+            agent.obs = agent._convert_obs(env.reset())
+            agent.dones = torch.ones(N, dtype=torch.bool)
+            agent.epoch = 0
+            agent.set_eval()
+            traj, steps = agent.explore_env(env, acfg.warm_up, random=True)
+            agent.memory.add_to_buffer(traj)
+            warm = dict(trajectory=clone_tree(traj), next_p=agent.memory.next_p, cur_capacity=agent.memory.cur_capacity)
+            for _ in range(epochs):
+                agent.epoch += 1
+                agent.set_eval()
+                traj, steps = agent.explore_env(env, acfg.horizon_len, sample=True)
+                agent.memory.add_to_buffer(traj)
+                agent.set_train()
+                res = agent.update_net(agent.memory)
+                per_epoch.append(dict(
+                    trajectory=clone_tree(traj), results={k: torch.stack([x.detach() for x in v]) for k, v in res.items()},
+                    actor=clone_tree(agent.actor.state_dict()), critic=clone_tree(agent.critic.state_dict()),
+                    critic_target=clone_tree(agent.critic_target.state_dict()),
+                    actor_target=clone_tree(agent.actor_target.state_dict()),
+                    log_alpha=agent.log_alpha.detach().clone() if algo == "sac" else None,
+                    obs_rms=clone_tree(agent.obs_rms.state_dict()), next_p=agent.memory.next_p, cur_capacity=agent.memory.cur_capacity))
+            streams = {k: [x.clone() for x in v] for k, v in rec.streams.items()}
+        cases.append(dict(algo=algo, variant=variant, shape=(N, O, A), cfg=rs.to_plain(cfg), init=init, warm=warm, epochs=per_epoch,
+                          streams=streams, env=dict(horizon=64, seed=51, done_p=0.08, timeout_p=0.05)))
+    save("offpolicy_e2e", cases)
+
+
+# ---- SAC policy head: Dist + SquashedNormal rsample / log_prob and autograd's gradients (the oracle restatement is pinned on these)
+def gen_sac_policy():
+    from mineral.nets.dist import Dist
+    cases = []
+    g = torch.Generator().manual_seed(60)
+    for dist_kwargs in (dict(dist_type="squashed_normal", minlogstd=-5.0, maxlogstd=2.0), dict(dist_type="squashed_normal"),
+                        dict(dist_type="dreamerv3_squashed_normal", minstd=0.1, maxstd=1.0)):
+        for B, A in ((64, 8), (33, 21)):
+            mu = (torch.randn(B, A, generator=g) * 1.5).requires_grad_()
+            ls = (torch.randn(B, A, generator=g) * 2.5).requires_grad_()   # wide enough to hit both clamp bounds
+            eps = torch.randn(B, A, generator=g)
+            g_act = torch.randn(B, A, generator=g) / B
+            alpha = 0.37
+            dist = Dist(**dist_kwargs)
+            _, sigma, distr = dist(mu, ls)
+            import torch.distributions.normal as tdn
+            orig = tdn._standard_normal
+            tdn._standard_normal = lambda shape, dtype, device: eps.clone()
+            try:
+                actions = distr.rsample()
+            finally:
+                tdn._standard_normal = orig
+            log_prob = distr.log_prob(actions).sum(-1, keepdim=True)
+            objective = (alpha * log_prob).mean() + (g_act * actions).sum()
+            objective.backward()
+            cases.append(dict(dist_kwargs=dist_kwargs, mu=mu.detach().clone(), logstd=ls.detach().clone(), eps=eps, g_act=g_act, alpha=alpha,
+                              sigma=sigma.detach().clone(), actions=actions.detach().clone(), log_prob=log_prob.detach().clone(),
+                              g_mu=mu.grad.clone(), g_logstd=ls.grad.clone()))
+    save("sac_policy", cases)
+
+
 if __name__ == "__main__":
     gen_experience()
     gen_rms()
@@ -397,3 +534,5 @@ if __name__ == "__main__":
     gen_nstep()
     gen_losses()
     gen_ppo_e2e()
+    gen_offpolicy_e2e()
+    gen_sac_policy()

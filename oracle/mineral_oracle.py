@@ -285,6 +285,70 @@ def distl_projection(next_dist, reward, done, gamma, v_min=-10, v_max=10, num_at
 # --------------------------------------------------------------------------
 
 
+# ---- SAC policy head (8(f)-2 agents): Dist + SquashedNormal (mineral/nets/dist.py:37-52, mineral/nets/distributions.py:10-58) ----
+def squashed_sigma(logstd, dist_type="squashed_normal", minlogstd=None, maxlogstd=None, minstd=1.0, maxstd=1.0):
+    """-> (sigma, d sigma / d logstd).  squashed_normal: exp(clamp(logstd)) (clamp's gradient is 1 on the closed range);
+    dreamerv3_squashed_normal: (hi - lo) * sigmoid(logstd + 2) + lo."""
+    if dist_type == "squashed_normal":
+        ls, inside = logstd, torch.ones_like(logstd, dtype=torch.bool)
+        if minlogstd is not None or maxlogstd is not None:
+            ls = torch.clamp(logstd, minlogstd, maxlogstd)
+            if minlogstd is not None:
+                inside &= logstd >= minlogstd
+            if maxlogstd is not None:
+                inside &= logstd <= maxlogstd
+        sigma = ls.exp()
+        return sigma, sigma * inside
+    s = torch.sigmoid(logstd + 2.0)
+    return (maxstd - minstd) * s + minstd, (maxstd - minstd) * s * (1.0 - s)
+
+
+def squashed_sample(mu, logstd, eps, **dist_kwargs):
+    """SAC.get_actions(sample=True, logprob=True) after the heads (mineral/agents/sac/sac.py:126-134): u = mu + sigma * eps
+    (Normal.rsample), actions = tanh(u), log_prob = sum_j [Normal.log_prob(u) - 2 (log 2 - u - softplus(-2u))] (B,1)."""
+    sigma, _ = squashed_sigma(logstd, **dist_kwargs)
+    u = mu + eps * sigma
+    base = -((u - mu) ** 2) / (2 * sigma ** 2) - sigma.log() - math.log(math.sqrt(2 * math.pi))
+    ladj = 2.0 * (math.log(2.0) - u - F.softplus(-2.0 * u))
+    return u.tanh(), (base - ladj).sum(-1, keepdim=True)
+
+
+def squashed_bwd(mu, logstd, eps, g_act, c_logp, **dist_kwargs):
+    """Gradient of  c_logp * sum_rows log_prob + <g_act, actions>  w.r.t. (mu, logstd) through the reparameterised sample,
+    in closed form: the Normal.log_prob contributions through u and through (mu, sigma) cancel to -1/sigma.
+    (what autograd does for sac.py:318-324 with c_logp = alpha / B and g_act = d(-mean Q_min)/d actions.)"""
+    sigma, dsig = squashed_sigma(logstd, **dist_kwargs)
+    a = (mu + eps * sigma).tanh()
+    g_u = c_logp * 2.0 * a + g_act * (1.0 - a * a)
+    return g_u, (g_u * eps - c_logp / sigma) * dsig
+
+
+def tanh_action(mu, noise=None, noise_bounds=None, out_bounds=None):
+    """DDPG actor output + exploration / target-smoothing noise (mineral/agents/ddpg/models.py:55-58, noise.py:22-38)."""
+    a = mu.tanh()
+    if noise is not None:
+        if noise_bounds is not None:
+            noise = noise.clamp(noise_bounds[0], noise_bounds[1])
+        a = a + noise
+        if out_bounds is not None:
+            a = a.clamp(out_bounds[0], out_bounds[1])
+    return a
+
+
+def actor_objective(q_values, log_prob, alpha, target_entropy):
+    """SAC.update_actor's scalars (sac.py:320-331) and the seeds d actor_loss / d Q_k (-1/B at the first minimum):
+    -> (actor_loss, entropy, alpha_loss, seeds list)."""
+    qs = torch.stack(q_values)
+    q_min, arg = torch.min(qs, dim=0)
+    B = q_min.shape[0]
+    lp = log_prob if log_prob is not None else torch.zeros_like(q_min)
+    actor_loss = (alpha * lp - q_min).mean()
+    entropy = (-lp).mean()
+    alpha_loss = (alpha * (-lp - target_entropy)).mean()
+    seeds = [torch.where(arg == k, -1.0 / B, 0.0).to(q_min.dtype) for k in range(len(q_values))]
+    return actor_loss, entropy, alpha_loss, seeds
+
+
 class RingOracle:
     """Row store with the reference's wrap rule: on overflow the head
     [next_p:C] receives the FIRST C-next_p incoming rows and the tail [0:p]

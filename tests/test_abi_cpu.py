@@ -42,10 +42,10 @@ def test_struct_layouts_match_c():
 #include <stdio.h>
 #include "mineral_b200.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mnr_wide_field_t), sizeof(mnr_row_field_t), sizeof(mnr_nstep_in_t),
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mnr_wide_field_t), sizeof(mnr_row_field_t), sizeof(mnr_nstep_in_t),
          sizeof(mnr_nstep_out_t), sizeof(mnr_ppo_loss_cfg_t), sizeof(mnr_optim_state_t), sizeof(mnr_linear_group_t),
          sizeof(mnr_split_job_t), sizeof(mnr_ln_group_t), sizeof(mnr_critic_set_t), sizeof(mnr_peer_comm_t),
-         sizeof(mnr_tc_reduce_job_t));
+         sizeof(mnr_tc_reduce_job_t), sizeof(mnr_squash_cfg_t));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -55,7 +55,7 @@ int main(void) {
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
     mine = [ctypes.sizeof(x) for x in (nv.WideField, nv.RowField, nv.NStepIn, nv.NStepOut, nv.PPOLossCfg, nv.OptimState, nv.LinearGroup,
-                                       nv.SplitJob, nv.LnGroup, nv.CriticSet, nv.PeerCommStruct, nv.TcReduceJob)]
+                                       nv.SplitJob, nv.LnGroup, nv.CriticSet, nv.PeerCommStruct, nv.TcReduceJob, nv.SquashCfg)]
     assert sizes == mine
 
 

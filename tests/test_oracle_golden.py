@@ -186,3 +186,28 @@ def test_offpolicy_math_matches_reference():
         got = oc.td_target(s["q"], s["reward"], s["done"], case["gamma"], case["nstep"], case["alpha"] if case["backup_entropy"] else None,
                            s["log_prob"])
         assert torch.equal(got, case["target"]), case
+
+
+def test_sac_policy_head_matches_reference_autograd():
+    """The squashed-normal sample / log-prob restatement and its CLOSED-FORM gradient against the reference's own
+    Dist + SquashedNormal run under autograd (golden sac_policy.pt)."""
+    for c in load_golden("sac_policy"):
+        kw = c["dist_kwargs"]
+        act, lp = oc.squashed_sample(c["mu"], c["logstd"], c["eps"], **kw)
+        scale_close(act, c["actions"], 1e-6, "actions")
+        scale_close(lp, c["log_prob"], 1e-6, "log_prob")
+        sigma, _ = oc.squashed_sigma(c["logstd"], **kw)
+        assert torch.equal(sigma, c["sigma"])
+        B = c["mu"].shape[0]
+        g_mu, g_ls = oc.squashed_bwd(c["mu"], c["logstd"], c["eps"], c["g_act"], c["alpha"] / B, **kw)
+        # autograd forms d/dmu as (-d/sigma^2 + ...) + d/sigma^2: two terms of size c*eps/sigma (up to 1e3 x the result when
+        # sigma = e^-5) that cancel, so the REFERENCE's f32 gradient carries their rounding (the closed form is ~100x closer
+        # to the f64 value).  Tolerance: 1e-5 of scale + 2 ulp of the cancelling terms.
+        floor = (c["alpha"] / B * c["eps"] / sigma).abs().max().item() * 2.0 ** -24
+        for name, mine, ref, extra in (("g_mu", g_mu, c["g_mu"], 2 * floor), ("g_logstd", g_ls, c["g_logstd"], 2 * floor * sigma.max().item())):
+            err = (mine - ref).abs().max().item()
+            assert err <= 1e-5 * ref.abs().max().item() + extra, f"{name}: {err:.3e}"
+        d = {k: v.double() for k, v in c.items() if torch.is_tensor(v)}   # and against the same formula in f64
+        t_mu, t_ls = oc.squashed_bwd(d["mu"], d["logstd"], d["eps"], d["g_act"], c["alpha"] / B, **kw)
+        scale_close(g_mu, t_mu, 2e-6, "g_mu vs f64")
+        scale_close(g_ls, t_ls, 2e-6, "g_logstd vs f64")
