@@ -14,7 +14,6 @@ Reference line -> here (no autograd, no cuBLAS, no torch elementwise op on the u
 The categorical critic (`DistributionalEnsembleQ`, ddpg.py:276-290) is not on the fused path; its projection kernel is
 `mineral_b200.agents.ddpg.utils.distl_projection`."""
 
-import collections
 import os
 from copy import deepcopy
 
@@ -26,7 +25,6 @@ from ..agent import cfg_get
 from ..sac.sac import OffPolicyAgent, make_optim
 from . import models
 from .schedule_util import ExponentialSchedule, LinearSchedule
-from .utils import soft_update_flat
 
 
 class DDPG(OffPolicyAgent):
@@ -82,6 +80,9 @@ class DDPG(OffPolicyAgent):
         raise NotImplementedError(noise.type)
 
     def _target_noise(self, rows):
+        pre = self._pre
+        if pre is not None:
+            return pre['eps'][pre['i'], 0]
         return self._randn((rows, self.action_dim)) * self.ddpg_config.noise.tgt_pol_std
 
     def get_noise_std(self):
@@ -142,26 +143,22 @@ class DDPG(OffPolicyAgent):
             self.writer.write()
         self.save(os.path.join(self.ckpt_dir, 'final.pth'))
 
-    @torch.no_grad()
-    def update_net(self, memory):
-        """ddpg.py:239-264."""
-        cfg = self.ddpg_config
-        results = collections.defaultdict(list)
-        for _ in range(cfg.mini_epochs):
-            self.mini_epoch += 1
-            self._sample_into_inputs(memory, self.batch_size)
-            critic_loss, critic_grad_norm = self.update_critic()
-            results['loss/critic'].append(critic_loss)
-            results['grad_norm/critic'].append(critic_grad_norm)
-            if self.mini_epoch % cfg.update_actor_interval == 0:
-                actor_loss, actor_grad_norm = self.update_actor()
-                results['loss/actor'].append(actor_loss)
-                results['grad_norm/actor'].append(actor_grad_norm)
-            if self.mini_epoch % cfg.update_targets_interval == 0:
-                soft_update_flat(self.critic_target_flat, self.critic_optim.flat, cfg.tau)
-                if not cfg.no_tgt_actor:
-                    soft_update_flat(self.actor_target_flat, self.actor_optim.flat, cfg.tau)
-        return results
+    noise_draws = 1   # per mini-epoch: the target-policy smoothing noise
+
+    def _draw_noise(self, buf):
+        buf.normal_(0.0, float(self.ddpg_config.noise.tgt_pol_std))
+
+    def _mini_epoch(self, results, do_actor, do_targets):
+        """One iteration of the loop in DDPG.update_net (ddpg.py:241-263) on the batch already gathered into xc / xn."""
+        critic_loss, critic_grad_norm = self.update_critic()
+        results['loss/critic'].append(critic_loss)
+        results['grad_norm/critic'].append(critic_grad_norm)
+        if do_actor:
+            actor_loss, actor_grad_norm = self.update_actor()
+            results['loss/actor'].append(actor_loss)
+            results['grad_norm/actor'].append(actor_grad_norm)
+        if do_targets:
+            self._soft_updates()
 
     @torch.no_grad()
     def update_critic(self):

@@ -94,8 +94,9 @@ class OffPolicyAgent(Agent):
         self.reward_b = torch.empty(self.batch_size, 1, **f32)
         self.done_b = torch.empty(self.batch_size, 1, **f32)
         self.target_q = torch.empty(self.batch_size, 1, **f32)
-        self._act_out = torch.empty(self.num_actors, A, **f32)
         self._actor_dirty = True   # actor weights changed since the tensor-core (hi, lo) copies were last refreshed
+        self.use_cuda_graph = bool(cfg_get(cfg, 'cuda_graph', True))
+        self._graphs, self._graph_warm, self._pre, self._pre_buf = {}, {}, None, None
 
     def _create_metrics(self, tracker_len):
         scores = {'rewards': torch.zeros(self.num_actors, dtype=torch.float32, device=self.device),
@@ -127,7 +128,7 @@ class OffPolicyAgent(Agent):
         """memory.sample_batch (sac.py:255) fused with the three `obs_rms.normalize` calls downstream and the cat with the
         action: one gather into xc = [norm(obs) | action] and xn[:, :O] = norm(next_obs)."""
         B, O, A = batch_size, self.obs_dim, self.action_dim
-        idx = self._sample_indices(memory, B)
+        idx = self._next_indices(memory, B)
         out = dict(obs={'obs': self.xc[:B, :O]}, next_obs={'obs': self.xn[:B, :O]}, action=self.xc[:B, O:O + A],
                    reward=self.reward_b[:B], done=self.done_b[:B])
         rms = self.obs_rms if self.normalize_input else None
@@ -187,6 +188,82 @@ class OffPolicyAgent(Agent):
         return {'train_scores/episode_rewards': self.metrics.episode_trackers['rewards'].mean(),
                 'train_scores/episode_lengths': self.metrics.episode_trackers['lengths'].mean(),
                 'train_scores/num_episodes': self.metrics.num_episodes, **self.metrics.result(prefix='train')}
+
+    # --- update_net: eager launches, or ONE CUDA graph per (actor / target update pattern) once warm -----------------------
+    def _draw_indices(self, memory, buf):
+        """Replay indices of all mini-epochs of one update_net call, drawn up front: buf (mini_epochs, B) int64."""
+        buf.random_(0, memory.cur_capacity)
+
+    def _draw_noise(self, buf):
+        """Standard-normal noise of all mini-epochs, drawn up front: buf (mini_epochs, draws_per_mini_epoch, B, A)."""
+        buf.normal_()
+
+    def _next_indices(self, memory, batch_size):
+        pre = self._pre
+        return pre['idx'][pre['i']] if pre is not None else self._sample_indices(memory, batch_size)
+
+    def _next_eps(self, rows, slot):
+        pre = self._pre
+        if pre is not None and rows == self.batch_size:
+            return pre['eps'][pre['i'], slot]
+        return self._randn((rows, self.action_dim))
+
+    @torch.no_grad()
+    def update_net(self, memory):
+        """sac.py:251-274 / ddpg.py:239-264.  Returns the reference's results dict: lists of 0-dim device tensors, nothing
+        synced.  With `cuda_graph` (default) the replay indices and the noise of all mini-epochs are drawn first (two torch RNG
+        launches) and everything else - sampling gather, every network pass, losses, optimizer steps, Polyak updates - replays as
+        one CUDA graph of our own kernels."""
+        cfg = self.algo_config
+        flags = []
+        for _ in range(cfg.mini_epochs):
+            self.mini_epoch += 1
+            flags.append((self.mini_epoch % cfg.update_actor_interval == 0, self.mini_epoch % cfg.update_targets_interval == 0))
+        flags = tuple(flags)
+        if not self.use_cuda_graph:
+            self._pre = None
+            return self._enqueue_update(memory, flags)
+        n, B, A = cfg.mini_epochs, self.batch_size, self.action_dim
+        if self._pre_buf is None:
+            self._pre_buf = dict(idx=torch.zeros(n, B, dtype=torch.int64, device=self.device),
+                                 eps=torch.zeros(n, self.noise_draws, B, A, dtype=torch.float32, device=self.device), i=0)
+        self._draw_indices(memory, self._pre_buf['idx'])
+        self._draw_noise(self._pre_buf['eps'])
+        self._pre = self._pre_buf
+        self._actor_dirty = True   # the captured sequence must not depend on what ran before it
+        try:
+            entry = self._graphs.get(flags)
+            if entry is None and self._graph_warm.get(flags, 0) >= 1:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    results = self._enqueue_update(memory, flags)
+                entry = self._graphs[flags] = (graph, results)
+            if entry is not None:
+                entry[0].replay()
+                results = collections.defaultdict(list, {k: list(v) for k, v in entry[1].items()})
+            else:
+                results = self._enqueue_update(memory, flags)
+                self._graph_warm[flags] = self._graph_warm.get(flags, 0) + 1
+        finally:
+            self._pre = None
+            self._actor_dirty = True
+        return results
+
+    def _enqueue_update(self, memory, flags):
+        results = collections.defaultdict(list)
+        for i, (do_actor, do_targets) in enumerate(flags):
+            if self._pre is not None:
+                self._pre['i'] = i
+            self._sample_into_inputs(memory, self.batch_size)
+            self._mini_epoch(results, do_actor, do_targets)
+        return results
+
+    def _soft_updates(self):
+        cfg = self.algo_config
+        soft_update_flat(self.critic_target_flat, self.critic_optim.flat, cfg.tau)
+        if not cfg.no_tgt_actor:
+            soft_update_flat(self.actor_target_flat, self.actor_optim.flat, cfg.tau)
 
     def optimizer_update(self, optimizer, grad_norm_out):
         """sac.py:334-345: clip_grad_norm_ + step (+ zero_grad), one launch; the total norm lands in grad_norm_out."""
@@ -260,12 +337,12 @@ class SAC(OffPolicyAgent):
             return alpha
         return self.sac_config.alpha
 
-    def _policy(self, x, rows, sample, log_prob, actions_out):
+    def _policy(self, x, rows, sample, log_prob, actions_out, slot=0):
         """actor(z) -> Dist -> rsample / mean [-> log_prob] on rows of the padded input buffer x (z in columns [0, O))."""
         fa = self._fa
         fa.forward(x, self.x_ld, rows, split=self._actor_dirty)
         self._actor_dirty = False
-        eps = self._randn((rows, self.action_dim)) if sample else None
+        eps = self._next_eps(rows, slot) if sample else None
         ops.squashed_sample(fa.mu_raw, fa.logstd, eps, self._squash, actions_out, self.log_prob if log_prob else None, rows)
         return eps
 
@@ -309,30 +386,23 @@ class SAC(OffPolicyAgent):
                       f'ep_rewards {metrics["train_scores/episode_rewards"]:.2f}, ep_lengths {metrics["train_scores/episode_lengths"]:.2f}')
         self.save(os.path.join(self.ckpt_dir, 'final.pth'))
 
-    @torch.no_grad()
-    def update_net(self, memory):
-        """sac.py:251-274.  Returns the reference's results dict: lists of 0-dim device tensors, nothing synced."""
-        cfg = self.sac_config
-        results = collections.defaultdict(list)
-        for _ in range(cfg.mini_epochs):
-            self.mini_epoch += 1
-            self._sample_into_inputs(memory, self.batch_size)
-            critic_loss, critic_grad_norm, target_values = self.update_critic()
-            results['loss/critic'].append(critic_loss)
-            results['grad_norm/critic'].append(critic_grad_norm)
-            for k, v in target_values.items():
-                results[k].append(v)
-            if self.mini_epoch % cfg.update_actor_interval == 0:
-                actor_loss, alpha_loss, entropy, actor_grad_norm = self.update_actor()
-                results['loss/actor'].append(actor_loss)
-                results['loss/alpha'].append(alpha_loss)
-                results['entropy'].append(entropy)
-                results['grad_norm/actor'].append(actor_grad_norm)
-            if self.mini_epoch % cfg.update_targets_interval == 0:
-                soft_update_flat(self.critic_target_flat, self.critic_optim.flat, cfg.tau)
-                if not cfg.no_tgt_actor:
-                    soft_update_flat(self.actor_target_flat, self.actor_optim.flat, cfg.tau)
-        return results
+    noise_draws = 2   # per mini-epoch: a' ~ pi(.|s') for the target, a ~ pi(.|s) for the actor step
+
+    def _mini_epoch(self, results, do_actor, do_targets):
+        """One iteration of the loop in SAC.update_net (sac.py:253-273) on the batch already gathered into xc / xn."""
+        critic_loss, critic_grad_norm, target_values = self.update_critic()
+        results['loss/critic'].append(critic_loss)
+        results['grad_norm/critic'].append(critic_grad_norm)
+        for k, v in target_values.items():
+            results[k].append(v)
+        if do_actor:
+            actor_loss, alpha_loss, entropy, actor_grad_norm = self.update_actor()
+            results['loss/actor'].append(actor_loss)
+            results['loss/alpha'].append(alpha_loss)
+            results['entropy'].append(entropy)
+            results['grad_norm/actor'].append(actor_grad_norm)
+        if do_targets:
+            self._soft_updates()
 
     @torch.no_grad()
     def update_critic(self, obs=None, action=None, reward=None, next_obs=None, done=None):
@@ -360,7 +430,7 @@ class SAC(OffPolicyAgent):
         fa, fq = self._fa, self._fq
         if obs is not None:
             self._normalize_into(obs['obs'] if isinstance(obs, dict) else obs, self.xc, B)
-        eps = self._policy(self.xc, B, True, True, self.xc[:B, O:O + A])
+        eps = self._policy(self.xc, B, True, True, self.xc[:B, O:O + A], slot=1)
         fq.forward(self.xc, B)                       # the critic step just changed the weights: fresh (hi, lo) split
         log_alpha, alpha_host = self._alpha_args()
         out = torch.empty(5, dtype=torch.float32, device=self.device)   # actor loss, entropy, alpha loss, alpha, grad norm

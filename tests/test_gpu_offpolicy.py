@@ -181,8 +181,9 @@ class _Replay:
         return cu(t)
 
 
+@pytest.mark.parametrize("cuda_graph", [False, True])
 @pytest.mark.parametrize("case_index", [0, 1, 2, 3])
-def test_offpolicy_agents_match_reference_run(case_index):
+def test_offpolicy_agents_match_reference_run(case_index, cuda_graph):
     """SAC (LayerNorm+SiLU and ELU towers) and DDPG (mixed exploration noise; TD3 with target actor, delayed updates) through
     warm-up, two explore_env + update_net epochs: trajectories, every logged scalar and every parameter against the real
     reference agents' run on the same env streams and random draws."""
@@ -194,6 +195,7 @@ def test_offpolicy_agents_match_reference_run(case_index):
     N, O, A = c["shape"]
     cfg = to_attr(c["cfg"])
     cfg.rl_device = DEV
+    cfg.agent[algo]["cuda_graph"] = cuda_graph   # True: update_net warms up eagerly once, then replays as ONE CUDA graph
     cpu_env = SynthEnv(N, O, A, c["env"]["horizon"], seed=c["env"]["seed"], done_p=c["env"]["done_p"], timeout_p=c["env"]["timeout_p"])
 
     class OnDevice:
@@ -222,6 +224,19 @@ def test_offpolicy_agents_match_reference_run(case_index):
     else:  # torch.normal draws are recorded already scaled by their std (noise.py:30-33,48-49)
         agent._exploration_noise = lambda rows: rp.pop("normal", (rows, A))
         agent._target_noise = lambda rows: rp.pop("normal", (rows, A))
+
+    B = acfg.batch_size
+
+    def draw_indices(memory, buf):   # graph mode draws all mini-epochs of one update_net call up front
+        for i in range(buf.shape[0]):
+            buf[i].copy_(rp.pop("randint", (B,)))
+
+    def draw_noise(buf):
+        for i in range(buf.shape[0]):
+            for j in range(buf.shape[1]):
+                buf[i, j].copy_(rp.pop("std_normal" if algo == "sac" else "normal", (B, A)))
+
+    agent._draw_indices, agent._draw_noise = draw_indices, draw_noise
 
     def check_traj(got, ref, tag):
         eq(got[0]["obs"], ref[0]["obs"], f"{tag} obs")

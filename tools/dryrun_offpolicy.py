@@ -50,7 +50,7 @@ t.DEV = "cpu"
 t.scale_close = lambda *a, **k: None
 t.eq = lambda *a, **k: None
 for i in range(4):
-    t.test_offpolicy_agents_match_reference_run(i)
+    t.test_offpolicy_agents_match_reference_run(i, False)
     print("case", i, "host logic ok")
 for fn in (t.test_squashed_normal_kernels_match_reference_golden_and_oracle, t.test_offpolicy_row_kernels_vs_oracle):
     try:
