@@ -18,13 +18,63 @@ import torch.nn.functional as F
 
 from ... import ops
 from ...nets.fused_towers import FusedCritics
+from ..agent import cfg_get
 from ..ppo.ppo import FusedAdam
 from .models import Critic, EnsembleCritic
 from .utils import CriticDataset, grad_norm
 
 
 class SHAC:
-    def __init__(self, num_envs, num_obs, num_actions, horizon_len, device, gamma=0.99, lam=0.95, critic_method='td-lambda',
+    def __new__(cls, *args, **kwargs):
+        """Drop-in construction (mineral/scripts/run.py:140-144): `SHAC(full_cfg, logdir=, accelerator=, datasets=, env=)` with
+        the reference's config keys (`full_cfg.agent.{network,shac}`, mineral/cfgs/agent/DFlexAnt{SHAC,SHAC2,SAPO}.yaml) is
+        translated into the explicit-argument form below."""
+        self = object.__new__(cls)
+        if args and hasattr(args[0], 'agent'):
+            self._from_cfg = cls._cfg_to_kwargs(args[0], kwargs.get('env'))
+            self._cfg_ctx = (args[0], kwargs)
+        return self
+
+    @staticmethod
+    def _cfg_to_kwargs(full_cfg, env):
+        """shac.py:31-75,124-150,192-194: the keys the critic half reads, with the reference's defaults."""
+        net, cfg = full_cfg.agent.network, full_cfg.agent.shac
+        if env is None:
+            raise ValueError('SHAC needs env= (num_envs / num_obs / num_actions are read from it, shac.py:38-41)')
+        if cfg_get(net, 'encoder', None) is not None:
+            raise NotImplementedError('encoders are outside the rollout->update hot path (SURVEY.md section 8)')
+        critic_name = cfg_get(net, 'critic', 'Critic')
+        if critic_name not in ('Critic', 'EnsembleCritic'):
+            raise NotImplementedError(f'critic {critic_name}')
+        ck = dict(cfg_get(net, 'critic_kwargs', {}) or {})
+        ok = dict(cfg_get(cfg, 'critic_optim_kwargs', {}) or {})
+        return dict(
+            num_envs=env.num_envs, num_obs=env.num_obs, num_actions=env.num_actions, horizon_len=cfg.horizon_len, device=full_cfg.rl_device,
+            gamma=cfg_get(cfg, 'gamma', 0.99), lam=cfg_get(cfg, 'lambda', 0.95), critic_method=cfg_get(cfg, 'critic_method', 'one-step'),
+            critic_iterations=cfg_get(cfg, 'critic_iterations', 16), num_critic_batches=cfg_get(cfg, 'num_critic_batches', 4),
+            num_critics=ck.get('n_critics', 1) if critic_name == 'EnsembleCritic' else 1,
+            critic_mlp_kwargs=ck.get('mlp_kwargs', None), optim_type=cfg.optim_type, critic_lr=ok.get('lr', 1e-3),
+            critic_betas=tuple(ok.get('betas', (0.9, 0.999))), max_grad_norm=cfg_get(cfg, 'max_grad_norm', None),
+            truncate_grads=bool(cfg_get(cfg, 'truncate_grads', False)), with_logprobs=cfg_get(cfg, 'with_logprobs', False),
+            use_distr_ent=cfg_get(cfg, 'use_distr_ent', False), entropy_coef=cfg_get(cfg, 'entropy_coef', None),
+            offset_by_target_entropy=cfg_get(cfg, 'offset_by_target_entropy', False),
+            scale_by_target_entropy=cfg_get(cfg, 'scale_by_target_entropy', False),
+            target_entropy_scalar=cfg_get(cfg, 'target_entropy_scalar', 1.0), cuda_graph=cfg_get(cfg, 'cuda_graph', True))
+
+    def __init__(self, *args, **kwargs):
+        if getattr(self, '_from_cfg', None) is not None:
+            full_cfg, kw = self._cfg_ctx
+            self._init(**self._from_cfg)
+            # the Agent-level attributes run.py and the writers read (agent.py:14-81)
+            self.full_cfg, self.env, self.logdir = full_cfg, kw.get('env'), kw.get('logdir')
+            self.network_config, self.shac_config = full_cfg.agent.network, full_cfg.agent.shac
+            self.num_actors = self.shac_config.num_actors
+            self.max_agent_steps = int(self.shac_config.max_agent_steps)
+            self.epoch, self.mini_epoch, self.agent_steps = -1, -1, 0
+        else:
+            self._init(*args, **kwargs)
+
+    def _init(self, num_envs, num_obs, num_actions, horizon_len, device, gamma=0.99, lam=0.95, critic_method='td-lambda',
                  critic_iterations=16, num_critic_batches=4, critic_units=(64, 64), num_critics=1, critic_lr=2e-3,
                  critic_betas=(0.7, 0.95), critic_mlp_kwargs=None, optim_type='Adam', max_grad_norm=1.0, truncate_grads=True,
                  with_logprobs=False, use_distr_ent=True, entropy_coef=None, offset_by_target_entropy=False,

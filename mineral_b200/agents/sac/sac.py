@@ -34,6 +34,7 @@ from ... import ops
 from ...buffers import NStepReplay, ReplayBuffer
 from ...common import normalizers
 from ...common.reward_shaper import RewardShaper
+from ...common.timer import Timer
 from ...nets.fused_offpolicy import FusedActor, FusedQ, flatten_like, pad4
 from ..agent import Agent, DeviceMetrics, cfg_get
 from ..ddpg import models
@@ -316,6 +317,13 @@ class SAC(OffPolicyAgent):
         self._squash = ops.make_squash_cfg(dk.get('dist_type', 'normal'), dk.get('minlogstd'), dk.get('maxlogstd'),
                                            self.actor.dist.minstd, self.actor.dist.maxstd)
         f32 = dict(dtype=torch.float32, device=dev)
+        # --- Timing (sac.py:111-117): same scopes, device time from CUDA events (common/timer.py) ---
+        self.timer = Timer()
+        self.timer.wrap('agent', self, ['explore_env', 'update_net'])
+        self.timer.wrap('memory', self.memory, ['add_to_buffer'])
+        if hasattr(self.env, 'step'):
+            self.timer.wrap('env', self.env, ['step'])
+        self.timer_total_names = ('agent.explore_env', 'memory.add_to_buffer', 'agent.update_net')
         self.log_prob = torch.empty(max(B, self.num_actors), **f32)
         self._eps_actor = None
         self._scalars = torch.zeros(16, **f32)   # scratch for per-step scalar outputs that nobody keeps
@@ -377,6 +385,8 @@ class SAC(OffPolicyAgent):
             metrics = {k: torch.mean(torch.stack(v)).item() for k, v in results.items()}
             metrics.update({'epoch': self.epoch, 'mini_epoch': self.mini_epoch, 'alpha': self.get_alpha(scalar=True)})
             metrics = {f'train_stats/{k}': v for k, v in metrics.items()}
+            timings = self.timer.stats(step=self.agent_steps, total_names=self.timer_total_names, reset=False)
+            metrics.update({f'train_timings/{k}': v for k, v in timings.items()})
             metrics.update(self._episode_metrics())
             self.writer.add(self.agent_steps, metrics)
             self.writer.write()

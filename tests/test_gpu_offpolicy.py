@@ -288,3 +288,53 @@ def test_offpolicy_agents_match_reference_run(case_index, cuda_graph):
         agent.load(f)
         for k, v in before.items():
             eq(agent.actor.state_dict()[k], v.cpu(), f"reloaded actor.{k}")
+
+
+@pytest.mark.parametrize("algo", ["sac", "ddpg"])
+def test_train_loop_runs_like_the_reference(algo):
+    """`train()` end to end (sac.py:190-249, ddpg.py:201-237): warm-up, explore / insert / update_net epochs until
+    max_agent_steps, metrics rows with the reference's keys, the final checkpoint; SAC also `eval()`."""
+    import os
+
+    from mineral_b200.agents import DDPG, SAC
+    from oracle.reference_shim import SynthEnv, to_attr
+
+    c = load_golden("offpolicy_e2e")[0 if algo == "sac" else 2]
+    N, O, A = c["shape"]
+    cfg = to_attr(c["cfg"])
+    cfg.rl_device = DEV
+    acfg = cfg.agent[algo]
+    epochs = 4
+    acfg["max_agent_steps"] = N * (acfg.warm_up + epochs * acfg.horizon_len)
+    cfg.agent["ckpt_every"] = 2
+    cpu_env = SynthEnv(N, O, A, 4096, seed=3, done_p=0.1, timeout_p=0.05)
+
+    class OnDevice:
+        observation_space, action_space = cpu_env.observation_space, cpu_env.action_space
+
+        def reset(self):
+            return cu(cpu_env.reset())
+
+        def step(self, actions):
+            o, r, d, info = cpu_env.step(actions)
+            return cu(o), cu(r), cu(d), cu(info)
+
+    torch.manual_seed(0)
+    agent = (SAC if algo == "sac" else DDPG)(cfg, env=OnDevice())
+    agent.train()
+    assert agent.epoch == epochs - 1 and agent.agent_steps == acfg.max_agent_steps and agent.mini_epoch == epochs * acfg.mini_epochs - 1
+    rows = agent.writer.rows
+    assert len(rows) == epochs
+    last = rows[-1][1]
+    need = {"train_stats/loss/critic", "train_stats/loss/actor", "train_stats/grad_norm/critic", "train_stats/grad_norm/actor", "train_stats/epoch",
+            "train_scores/episode_rewards", "train_scores/episode_lengths", "train_scores/num_episodes"}
+    if algo == "sac":
+        need |= {"train_stats/alpha", "train_stats/entropy", "train_stats/loss/alpha", "train_stats/target_values/mean",
+                 "train_timings/agent.update_net/avg", "train_timings/agent.explore_env/avg", "train_timings/totalrate"}
+    assert need <= set(last), sorted(need - set(last))
+    assert all(v == v for k, v in last.items() if isinstance(v, float)), "NaN in the metrics"
+    assert last["train_scores/num_episodes"] > 0
+    if algo == "sac":
+        assert os.path.exists(os.path.join(agent.ckpt_dir, "final.pth"))
+        ev = agent.eval()
+        assert ev["eval_scores/num_episodes"] >= 2 * N
