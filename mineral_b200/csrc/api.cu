@@ -1,5 +1,16 @@
 // Host-side odds and ends of the C ABI.
+#include <stdlib.h>
+
 #include "common.cuh"
+
+bool mnr_pdl_enabled() {
+  static int cached = -1;
+  if (cached < 0) {
+    const char* e = getenv("MNR_PDL");
+    cached = (e && e[0] == '0') ? 0 : 1;
+  }
+  return cached == 1;
+}
 
 extern "C" int mnr_abi_version(void) { return MNR_ABI_VERSION; }
 

@@ -22,7 +22,30 @@ static inline bool mnr_aligned(const void* p, size_t a) { return (reinterpret_ca
 
 __device__ __forceinline__ bool mnr_aligned_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// Kernels of the update chain are launched with cudaLaunchAttributeProgrammaticStreamSerialization: the next kernel of the
+// stream may be scheduled - and run its prologue (barrier init, TMEM allocation, descriptor prefetch) - while this one is
+// still draining, SM by SM.  Contract for a kernel launched this way: call mnr::pdl_wait() BEFORE its first global-memory
+// access (it returns once every preceding grid has completed and its writes are visible; a no-op under a plain launch), and
+// mnr::pdl_trigger() as early as it likes (dependents still wait for this grid's completion inside their own pdl_wait).
+// MNR_PDL=0 in the environment falls back to plain launches.
+bool mnr_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mnr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = mnr_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 namespace mnr {
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 constexpr int kWarp = 32;
 

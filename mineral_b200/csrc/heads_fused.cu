@@ -69,6 +69,8 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   const int Ar = a.A;  // real action dimension, Ar <= A
   extern __shared__ __align__(16) float sh[];
   __shared__ double s_red[6][kWarpsHF];
+  mnr::pdl_trigger();   // PDL: see common.cuh
+  mnr::pdl_wait();
   __shared__ mnr::Moments s_mom[2][kWarpsHF];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a, then Y3v tile, then dY3v
@@ -445,8 +447,8 @@ int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap,
   int grid = mnr_sm_count() * occ_cached;  // every CTA resident: the grid barrier needs it
   if (grid > grid_cap) grid = grid_cap;
   if (grid > a.n_tiles) grid = a.n_tiles;
-  kern<<<grid, kThreadsHF, smem, stream>>>(a, cfg);
-  const cudaError_t e = cudaPeekAtLastError();
+  cudaError_t e = mnr_launch_pdl(kern, dim3(grid), dim3(kThreadsHF), smem, stream, a, cfg);
+  if (e == cudaSuccess) e = cudaPeekAtLastError();
   return e == cudaSuccess ? MNR_OK : (int)e;
 }
 

@@ -93,6 +93,8 @@ struct Row {
 
 template <int E, bool VEC, int ACT>
 __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const __grid_constant__ LnArgs a) {
+  mnr::pdl_trigger();   // PDL: see common.cuh
+  mnr::pdl_wait();
   const mnr_ln_group_t& g = a.g[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = a.N;
@@ -123,6 +125,8 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const __grid_const
 template <int E, bool VEC, int ACT>
 __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_constant__ LnArgs a) {
   extern __shared__ __align__(16) float s_fold[];  // [kWarps][2N]
+  mnr::pdl_trigger();   // PDL: see common.cuh
+  mnr::pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = a.N;
   const float invN = 1.f / (float)N;
@@ -235,7 +239,7 @@ extern "C" int mnr_ln_act_fwd(const mnr_ln_group_t* groups, int n_groups, int64_
   int64_t want = (M + kWarps - 1) / kWarps;
   const int64_t cap = (int64_t)mnr_sm_count() * 8;
   dim3 grid((unsigned)(want > cap ? cap : want), n_groups);
-#define MNR_LN_GO(KERNEL, EV, VV, AV, ...) KERNEL<EV, VV, AV><<<grid, kThreads, 0, mnr_cs(stream)>>>(a);
+#define MNR_LN_GO(KERNEL, EV, VV, AV, ...) mnr_launch_pdl(KERNEL<EV, VV, AV>, grid, dim3(kThreads), 0, mnr_cs(stream), a);
   MNR_LN_DISPATCH(ln_act_fwd_kernel, 0);
 #undef MNR_LN_GO
   MNR_LAUNCH_RESULT();
@@ -265,7 +269,7 @@ extern "C" int mnr_ln_act_bwd(const mnr_ln_group_t* groups, int n_groups, int64_
     auto kern = KERNEL<EV, VV, AV>;                                                                            \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
     if (e != cudaSuccess) return (int)e;                                                                       \
-    kern<<<grid, kThreads, smem, mnr_cs(stream)>>>(a);                                                         \
+    mnr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, mnr_cs(stream), a);                                 \
   }
   MNR_LN_DISPATCH(ln_act_bwd_kernel, 0);
 #undef MNR_LN_GO

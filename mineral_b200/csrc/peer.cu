@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   __shared__ double s_w[kThreads / 32];
   __shared__ float s_bcast[4];
   __shared__ float s_tail[32];
+  mnr::pdl_trigger();   // PDL: see common.cuh
+  mnr::pdl_wait();
   const int world = WORLD == 1 ? 1 : c.world;
   const int tid = threadIdx.x;
   const int64_t n4 = a.n >> 2;
@@ -402,7 +404,8 @@ extern "C" int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, fl
   Comm c;
   for (int r = 0; r < kMaxPeers; ++r) c.base[r] = nullptr;
   c.rank = 0, c.world = 1;
-  reduce_clip_adam_kernel<1><<<adam_grid(n), kThreads, 0, mnr_cs(stream)>>>(c, a);
+  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<1>, dim3(adam_grid(n)), dim3(kThreads), 0, mnr_cs(stream), c, a);
+  if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
 }
 
@@ -423,6 +426,7 @@ extern "C" int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm, size_t gra
   if (!mnr_aligned(reduced, 16)) return MNR_EALIGN;
   a.reduced = reduced, a.grad_offset = grad_offset, a.n_tail = n_tail, a.tail_out = tail_out, a.kl_index = kl_index;
   a.grad = reinterpret_cast<float*>(c.base[c.rank] + grad_offset);
-  reduce_clip_adam_kernel<0><<<adam_grid(n), kThreads, 0, mnr_cs(stream)>>>(c, a);
+  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<0>, dim3(adam_grid(n)), dim3(kThreads), 0, mnr_cs(stream), c, a);
+  if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
 }

@@ -233,6 +233,8 @@ __global__ void __launch_bounds__(kThreads) rms_apply_ld_kernel(const float* __r
                                                                 int64_t total, int cols, int y_ld,
                                                                 const float* __restrict__ mean,
                                                                 const float* __restrict__ denom, float lo, float hi) {
+  mnr::pdl_trigger();   // PDL: see common.cuh
+  mnr::pdl_wait();
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < total; i += stride) {
     const int64_t r = i / cols;
@@ -345,7 +347,8 @@ extern "C" int mnr_rms_apply_ld_f32(const float* x, float* y, int64_t rows, int 
   if (rows < 0 || cols <= 0 || y_ld < cols) return MNR_ESHAPE;
   if (rows == 0) return MNR_OK;
   const int64_t total = rows * cols;
-  rms_apply_ld_kernel<<<apply_grid(total), kThreads, 0, mnr_cs(stream)>>>(x, y, total, cols, y_ld, mean_f32, denom_f32,
-                                                                         clamp_lo, clamp_hi);
+  const cudaError_t le = mnr_launch_pdl(rms_apply_ld_kernel, dim3(apply_grid(total)), dim3(kThreads), 0, mnr_cs(stream), x, y, total, cols,
+                                        y_ld, mean_f32, denom_f32, clamp_lo, clamp_hi);
+  if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
 }

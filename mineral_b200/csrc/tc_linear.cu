@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  // PDL: everything above touched only shared / tensor memory and overlapped the previous kernel's tail
+  mnr::pdl_trigger();
+  mnr::pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer ==========================================================================
@@ -450,6 +453,8 @@ struct ReduceJobs {
 };
 __global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
   __shared__ float4 s_part[8][32];
+  mnr::pdl_trigger();
+  mnr::pdl_wait();
   const ReduceJob& jb = jobs.j[blockIdx.y / kMaxGroups];
   const int gi = blockIdx.y % kMaxGroups;
   if (gi >= jb.n_groups || (int)blockIdx.x >= jb.wblocks + (jb.I + 31) / 32) return;
@@ -505,6 +510,8 @@ struct SplitJobs {
   int n;
 };
 __global__ void __launch_bounds__(256) split_kernel(const __grid_constant__ SplitJobs js) {
+  mnr::pdl_trigger();
+  mnr::pdl_wait();
   const SplitJob& jb = js.j[blockIdx.y];
   const int total = jb.rows * jb.dst_ld;
   for (int idx = blockIdx.x * 256 + threadIdx.x; idx < total; idx += gridDim.x * 256) {
@@ -571,7 +578,7 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   cudaError_t e = cudaSuccess;
 #define MNR_TC_LAUNCH(ACTV)                                                                                              \
   e = cudaFuncSetAttribute(tc_linear_kernel<MODE, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
-  if (e == cudaSuccess) tc_linear_kernel<MODE, ACTV><<<grid, kThreads, smem, stream>>>(p);
+  if (e == cudaSuccess) e = mnr_launch_pdl(tc_linear_kernel<MODE, ACTV>, grid, dim3(kThreads), smem, stream, p);
   switch (p.act) {
     case 1: MNR_TC_LAUNCH(1) break;
     case 2: MNR_TC_LAUNCH(2) break;
@@ -725,7 +732,7 @@ int reduce_launch(const ReduceJobs& jobs, int n_jobs, cudaStream_t stream) {
     max_x = x > max_x ? x : max_x;
   }
   dim3 rgrid(max_x, n_jobs * kMaxGroups);
-  tc_reduce_kernel<<<rgrid, 256, 0, stream>>>(jobs);
+  mnr_launch_pdl(tc_reduce_kernel, rgrid, dim3(256), 0, stream, jobs);
   MNR_LAUNCH_RESULT();
 }
 }  // namespace
@@ -771,7 +778,7 @@ extern "C" int mnr_split_tf32(const mnr_split_job_t* jobs, int n_jobs, mnr_strea
     max_total = total > max_total ? total : max_total;
   }
   dim3 grid((max_total + 255) / 256 > 64 ? 64 : (max_total + 255) / 256, n_jobs);
-  split_kernel<<<grid, 256, 0, mnr_cs(stream)>>>(js);
+  mnr_launch_pdl(split_kernel, grid, dim3(256), 0, mnr_cs(stream), js);
   MNR_LAUNCH_RESULT();
 }
 
