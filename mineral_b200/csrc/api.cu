@@ -7,7 +7,7 @@ bool mnr_pdl_enabled() {
   static int cached = -1;
   if (cached < 0) {
     const char* e = getenv("MNR_PDL");
-    cached = (e && e[0] == '0') ? 0 : 1;
+    cached = (e && e[0] == '1') ? 1 : 0;   // measured on B200 (profiles/r01_summary.md section 10): 1-5 % SLOWER inside the update graph -> opt-in
   }
   return cached == 1;
 }
