@@ -242,6 +242,175 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   }
 }
 
+// ---- thin layers: N <= 32 output features (policy / value / Q heads, mineral/agents/ppo/models.py:136-151,
+// mineral/agents/ddpg/models.py:29-71,84-111) ----------------------------------------------------------------------------
+// The 128x64 tile kernel above leaves 7/8 of a tile idle on an 8-wide head and spends its time in the tile prologue; these
+// are row-streaming kernels instead (a head moves M*K*4 bytes and does 2*M*K*N flops: HBM / latency-bound): W (padded to NP
+// rows of zeros) sits in shared memory, a warp owns a row at a time, lanes own float4 chunks of the K dimension.
+// Identity activation only (heads are plain Linear layers); anything else stays on the tile kernel.
+constexpr int kThinThreads = 256, kThinWarps = kThinThreads / 32;
+
+__device__ __forceinline__ float dot4f(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc), acc = fmaf(a.y, b.y, acc), acc = fmaf(a.z, b.z, acc), acc = fmaf(a.w, b.w, acc);
+  return acc;
+}
+
+template <int NP>
+__device__ __forceinline__ void thin_stage_w(const Group& g, float4* s_w) {
+  const int K4 = g.K >> 2;
+  for (int i = threadIdx.x; i < NP * K4; i += kThinThreads)
+    s_w[i] = i < g.N * K4 ? __ldg(reinterpret_cast<const float4*>(g.b) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+}
+
+// Y[m][n] = sum_k X[m][k] W[n][k] + b[n]
+template <int NP>
+__global__ void __launch_bounds__(kThinThreads) thin_fwd_kernel(const __grid_constant__ Groups gs, int M) {
+  extern __shared__ __align__(16) float4 s_w4[];  // [NP][K/4]
+  const Group g = gs.g[blockIdx.y];
+  thin_stage_w<NP>(g, s_w4);
+  const int K4 = g.K >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float bias = (g.bias && lane < g.N) ? __ldg(g.bias + lane) : 0.f;
+  for (int m = blockIdx.x * kThinWarps + warp; m < M; m += gridDim.x * kThinWarps) {
+    float acc[NP];
+#pragma unroll
+    for (int n = 0; n < NP; ++n) acc[n] = 0.f;
+    const float4* row = reinterpret_cast<const float4*>(g.a + (size_t)m * g.lda);
+    for (int c = lane; c < K4; c += 32) {
+      const float4 y = __ldg(row + c);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) acc[n] = dot4f(y, s_w4[n * K4 + c], acc[n]);
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int n = 0; n < NP; ++n) {
+      float v = acc[n];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == n) mine = v;
+    }
+    if (lane < g.N) g.c[(size_t)m * g.N + lane] = mine + bias;
+  }
+}
+
+// dX[m][k] (+)= sum_n dY[m][n] W[n][k]
+template <int NP>
+__global__ void __launch_bounds__(kThinThreads) thin_dx_kernel(const __grid_constant__ Groups gs, int M, int accumulate) {
+  extern __shared__ __align__(16) float4 s_w4[];
+  const Group g = gs.g[blockIdx.y];
+  thin_stage_w<NP>(g, s_w4);
+  const int K4 = g.K >> 2, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int m = blockIdx.x * kThinWarps + warp; m < M; m += gridDim.x * kThinWarps) {
+    const float gl = lane < g.N ? __ldg(g.a + (size_t)m * g.N + lane) : 0.f;
+    float4* dst = reinterpret_cast<float4*>(g.c + (size_t)m * g.K);
+    for (int c0 = 0; c0 < K4; c0 += 32) {   // uniform trip count: the shuffles below need the whole warp
+      const int c = c0 + lane;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float gn = __shfl_sync(0xffffffffu, gl, n);
+        if (c < K4) {
+          const float4 w = s_w4[n * K4 + c];
+          acc.x = fmaf(gn, w.x, acc.x), acc.y = fmaf(gn, w.y, acc.y), acc.z = fmaf(gn, w.z, acc.z), acc.w = fmaf(gn, w.w, acc.w);
+        }
+      }
+      if (c < K4) {
+        if (accumulate) {
+          const float4 o = dst[c];
+          acc.x += o.x, acc.y += o.y, acc.z += o.z, acc.w += o.w;
+        }
+        dst[c] = acc;
+      }
+    }
+  }
+}
+
+// dW[n][k] = sum_m dY[m][n] X[m][k], db[n] = sum_m dY[m][n]: CTA (split, group) walks its slab of rows; thread = (float4 chunk
+// of K, row phase).  Output: the final tensors when splits == 1, else split partials in linear_kernel<kDw>'s layout
+// (summed in fixed order by reduce_splits_kernel).
+template <int NP>
+__global__ void __launch_bounds__(kThinThreads) thin_dw_kernel(const __grid_constant__ Groups gs, int M, int splits, float* __restrict__ partials) {
+  __shared__ __align__(16) float4 s_red[kThinThreads];
+  __shared__ float s_b[kThinThreads];
+  const int gi = blockIdx.y, split = blockIdx.x;
+  const Group g = gs.g[gi];
+  const int N = g.N, K = g.K, K4 = K >> 2;
+  const int phases = kThinThreads / K4, chunk = threadIdx.x % K4, phase = threadIdx.x / K4;
+  const bool active = phase < phases;
+  const int per = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+  const int r0 = split * per, r1 = min(M, r0 + per);
+  float4 acc[NP];
+  float bacc[NP];
+#pragma unroll
+  for (int n = 0; n < NP; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f), bacc[n] = 0.f;
+  if (active)
+    for (int m = r0 + phase; m < r1; m += phases) {
+      const float4 x = __ldg(reinterpret_cast<const float4*>(g.b + (size_t)m * g.ldb) + chunk);
+#pragma unroll
+      for (int n = 0; n < NP; ++n) {
+        const float gn = n < N ? __ldg(g.a + (size_t)m * N + n) : 0.f;
+        acc[n].x = fmaf(gn, x.x, acc[n].x), acc[n].y = fmaf(gn, x.y, acc[n].y), acc[n].z = fmaf(gn, x.z, acc[n].z), acc[n].w = fmaf(gn, x.w, acc[n].w);
+        bacc[n] += gn;   // every chunk of a phase sees the same dY values; chunk 0's copy is the one that is kept
+      }
+    }
+  float* w_out = splits == 1 ? g.c : partials + ((size_t)gi * splits + split) * N * K;
+  float* b_out = splits == 1 ? g.bias_grad : partials + (size_t)gs.n * splits * N * K + ((size_t)gi * splits + split) * N;
+#pragma unroll
+  for (int n = 0; n < NP; ++n) {
+    if (n >= N) break;
+    __syncthreads();
+    s_red[threadIdx.x] = acc[n];
+    s_b[threadIdx.x] = bacc[n];
+    __syncthreads();
+    if (threadIdx.x < K4) {
+      float4 t = s_red[threadIdx.x];
+      for (int q = 1; q < phases; ++q) {
+        const float4 o = s_red[q * K4 + threadIdx.x];
+        t.x += o.x, t.y += o.y, t.z += o.z, t.w += o.w;
+      }
+      reinterpret_cast<float4*>(w_out + (size_t)n * K)[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0 && (splits > 1 || g.bias_grad)) {
+      float t = 0.f;
+      for (int q = 0; q < phases; ++q) t += s_b[q * K4];
+      b_out[n] = t;
+    }
+  }
+}
+
+int thin_np(int max_n) { return max_n <= 1 ? 1 : (max_n <= 4 ? 4 : (max_n <= 8 ? 8 : (max_n <= 16 ? 16 : 32))); }
+
+// all groups: identity activation, N <= n_cap, K a multiple of 4 with 16 B-aligned rows; `b` (W) dense (N,K)
+bool thin_ok(const Groups& gs, int mode, int act, int n_cap) {
+  for (int k = 0; k < gs.n; ++k) {
+    const Group& g = gs.g[k];
+    if (g.N > n_cap || g.K % 4 != 0 || g.K > 1024 || g.s != nullptr) return false;
+    if (mode == kDw) {   // a = dY (M,N) scalar loads, b = X rows (ldb), c = dW (N,K)
+      if (g.ldb % 4 != 0 || !mnr_aligned(g.b, 16) || !mnr_aligned(g.c, 16) || g.K / 4 > kThinThreads) return false;
+    } else {
+      if (g.ldb != g.K || !mnr_aligned(g.b, 16)) return false;
+      if (mode == kFwd && (g.lda % 4 != 0 || !mnr_aligned(g.a, 16))) return false;
+      if (mode == kDx && !mnr_aligned(g.c, 16)) return false;
+    }
+  }
+  (void)act;
+  return true;
+}
+
+int thin_grid(int M) {
+  const int want = (M + kThinWarps - 1) / kThinWarps, cap = mnr_sm_count() * 8;
+  return want < cap ? (want < 1 ? 1 : want) : cap;
+}
+
+#define MNR_THIN_DISPATCH(NPV, CALL)                 \
+  switch (NPV) {                                      \
+    case 1: { constexpr int NP = 1; CALL; } break;    \
+    case 4: { constexpr int NP = 4; CALL; } break;    \
+    case 8: { constexpr int NP = 8; CALL; } break;    \
+    case 16: { constexpr int NP = 16; CALL; } break;  \
+    default: { constexpr int NP = 32; CALL; } break;  \
+  }
+
 int pack_groups(const mnr_linear_group_t* groups, int n_groups, int mode, Groups* out) {
   if (n_groups <= 0 || n_groups > kMaxGroups) return MNR_ESHAPE;
   if (!groups) return MNR_ENULL;
@@ -271,8 +440,14 @@ extern "C" int mnr_linear_fwd(const mnr_linear_group_t* groups, int n_groups, in
   if (rc != MNR_OK) return rc;
   if (M <= 0) return MNR_ESHAPE;
   if (act < 0 || act > 2) return MNR_EUNSUP;
-  int maxN = 0;
-  for (int k = 0; k < n_groups; ++k) maxN = gs.g[k].N > maxN ? gs.g[k].N : maxN;
+  int maxN = 0, maxK = 0;
+  for (int k = 0; k < n_groups; ++k) maxN = gs.g[k].N > maxN ? gs.g[k].N : maxN, maxK = gs.g[k].K > maxK ? gs.g[k].K : maxK;
+  if (act == 0 && thin_ok(gs, kFwd, act, 32) && (size_t)thin_np(maxN) * maxK * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)thin_np(maxN) * maxK * 4;
+    dim3 tgrid(thin_grid(M), n_groups);
+    MNR_THIN_DISPATCH(thin_np(maxN), (thin_fwd_kernel<NP><<<tgrid, kThinThreads, smem, mnr_cs(stream)>>>(gs, M)));
+    MNR_LAUNCH_RESULT();
+  }
   dim3 grid((M + BM - 1) / BM, (maxN + BN - 1) / BN, n_groups);
   linear_kernel<kFwd><<<grid, kThreads, 0, mnr_cs(stream)>>>(gs, M, act, 0, 1, nullptr);
   MNR_LAUNCH_RESULT();
@@ -285,8 +460,14 @@ extern "C" int mnr_linear_bwd_input(const mnr_linear_group_t* groups, int n_grou
   if (rc != MNR_OK) return rc;
   if (M <= 0) return MNR_ESHAPE;
   if (act < 0 || act > 2) return MNR_EUNSUP;
-  int maxK = 0;
-  for (int k = 0; k < n_groups; ++k) maxK = gs.g[k].K > maxK ? gs.g[k].K : maxK;
+  int maxK = 0, maxN = 0;
+  for (int k = 0; k < n_groups; ++k) maxK = gs.g[k].K > maxK ? gs.g[k].K : maxK, maxN = gs.g[k].N > maxN ? gs.g[k].N : maxN;
+  if (thin_ok(gs, kDx, act, 32) && (size_t)thin_np(maxN) * maxK * 4 <= 48 * 1024) {
+    const size_t smem = (size_t)thin_np(maxN) * maxK * 4;
+    dim3 tgrid(thin_grid(M), n_groups);
+    MNR_THIN_DISPATCH(thin_np(maxN), (thin_dx_kernel<NP><<<tgrid, kThinThreads, smem, mnr_cs(stream)>>>(gs, M, accumulate)));
+    MNR_LAUNCH_RESULT();
+  }
   dim3 grid((M + BM - 1) / BM, (maxK + BN - 1) / BN, n_groups);
   linear_kernel<kDx><<<grid, kThreads, 0, mnr_cs(stream)>>>(gs, M, act, accumulate, 1, nullptr);
   MNR_LAUNCH_RESULT();
@@ -310,8 +491,13 @@ extern "C" int mnr_linear_bwd_weight(const mnr_linear_group_t* groups, int n_gro
     MNR_CHECK_PTR(workspace);
     if (workspace_bytes < mnr_linear_bwd_weight_workspace_bytes(n_groups, M, N, K)) return MNR_EWORKSPACE;
   }
-  dim3 grid((N + BM - 1) / BM, (K + BN - 1) / BN, n_groups * splits);
-  linear_kernel<kDw><<<grid, kThreads, 0, mnr_cs(stream)>>>(gs, M, act, 0, splits, (float*)workspace);
+  if (thin_ok(gs, kDw, act, 16)) {
+    dim3 tgrid(splits, n_groups);
+    MNR_THIN_DISPATCH(thin_np(N), (thin_dw_kernel<NP><<<tgrid, kThinThreads, 0, mnr_cs(stream)>>>(gs, M, splits, (float*)workspace)));
+  } else {
+    dim3 grid((N + BM - 1) / BM, (K + BN - 1) / BN, n_groups * splits);
+    linear_kernel<kDw><<<grid, kThreads, 0, mnr_cs(stream)>>>(gs, M, act, 0, splits, (float*)workspace);
+  }
   if (splits > 1) {
     dim3 rgrid((N * K + N + 255) / 256, n_groups);
     reduce_splits_kernel<<<rgrid, 256, 0, mnr_cs(stream)>>>(gs, splits, (const float*)workspace);
