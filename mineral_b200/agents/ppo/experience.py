@@ -56,6 +56,8 @@ class ExperienceBuffer:
             obs_dict[k] = torch.zeros((T, N, *v), **f32)
         self.storage_dict['obses'] = obs_dict
 
+        self._stage = None   # double-buffered host upload (stage_from_host / commit_staged)
+
         self.batch_size = batch_size
         self.minibatch_size = minibatch_size
         self.length = self.batch_size // self.minibatch_size
@@ -105,6 +107,49 @@ class ExperienceBuffer:
         A = self.act_dim
         ops.scatter_rows([(mu.contiguous(), self.data_dict['mu'], A, 0), (sigma.contiguous(), self.data_dict['sigma'], A, 0)],
                          idx=None, row0=start, n=end - start)
+
+    # ---- host-resident rollouts (a simulator on the CPU, a remote actor): double-buffered upload ---------------------------
+    def stage_from_host(self, host):
+        """Start uploading a rollout from pinned host tensors ({name: (T,N,..)}; observations under 'obs' or 'obses': {key: ..})
+        into device STAGING buffers on a dedicated copy stream and return at once: the copy engines run while the compute
+        stream is still busy with the previous update.  `commit_staged()` makes the staged rollout the current one."""
+        if self._stage is None:
+            self._stage = dict(bufs={}, stream=torch.cuda.Stream(device=self.device), ready=torch.cuda.Event(), free=torch.cuda.Event())
+            self._stage['free'].record(torch.cuda.current_stream())
+        st = self._stage
+        st['stream'].wait_event(st['free'])   # the previous commit has finished reading the staging buffers
+        with torch.cuda.stream(st['stream']):
+            for name, src in self._host_fields(host):
+                dst = st['bufs'].get(name)
+                if dst is None:
+                    dst = st['bufs'][name] = torch.empty_like(self._storage_field(name))
+                dst.copy_(src, non_blocking=True)
+            st['ready'].record(st['stream'])
+        st['names'] = [name for name, _ in self._host_fields(host)]
+
+    def commit_staged(self):
+        """storage_dict <- staged rollout (device-to-device, on the current stream, after the upload has landed).  The storage
+        tensors keep their addresses, so a captured update graph stays valid."""
+        st = self._stage
+        cur = torch.cuda.current_stream()
+        cur.wait_event(st['ready'])
+        for name in st['names']:
+            self._storage_field(name).copy_(st['bufs'][name], non_blocking=True)
+        st['free'].record(cur)
+
+    @staticmethod
+    def _host_fields(host):
+        for k, v in host.items():
+            if k == 'obses':
+                for kk, vv in v.items():
+                    yield ('obses', kk), vv
+            elif k == 'obs':
+                yield ('obses', 'obs'), v
+            else:
+                yield k, v
+
+    def _storage_field(self, name):
+        return self.storage_dict['obses'][name[1]] if isinstance(name, tuple) else self.storage_dict[name]
 
     def update_data(self, name, index, val):
         """Rollout insert storage[name][t, :] = val (experience.py:89-94).  A contiguous device copy:

@@ -876,3 +876,31 @@ def test_fused_heads_loss_vs_unfused(rows, A, H, fixed_sigma, dist_type):
         scale_close(t, r, 1e-5, "dY3")
     for n in head_names:
         scale_close(dict(model.named_parameters())[n].grad, ref_grads[n], 2e-5, f"head grad {n}")
+
+
+def test_staged_host_upload_round_trip():
+    """ExperienceBuffer.stage_from_host / commit_staged (double-buffered upload of a host-resident rollout): the committed
+    storage equals the host rollout bit for bit, storage addresses do not move, and a second staged rollout does not
+    disturb the committed one until it is committed itself."""
+    from mineral_b200.agents.ppo.experience import ExperienceBuffer
+
+    T, N, O, A = 8, 96, 37, 8
+    buf = ExperienceBuffer(N, T, N * T, 256, {"obs": (O,)}, A, DEV)
+    ptrs = {k: (v["obs"] if k == "obses" else v).data_ptr() for k, v in buf.storage_dict.items()}
+    rollouts = []
+    for seed in (0, 1):
+        st, _ = oc.synth_rollout(T, N, O, A, seed=seed)
+        host = {k: v.pin_memory() for k, v in st.items() if k not in ("returns", "obses")}
+        host["obs"] = st["obses"]["obs"].pin_memory()
+        rollouts.append(host)
+    buf.stage_from_host(rollouts[0])
+    buf.commit_staged()
+    buf.stage_from_host(rollouts[1])          # in flight / landed in the staging buffers only
+    torch.cuda.synchronize()
+    for k, v in rollouts[0].items():
+        eq(buf.storage_dict["obses"]["obs"] if k == "obs" else buf.storage_dict[k], v, f"first rollout {k}")
+    buf.commit_staged()
+    torch.cuda.synchronize()
+    for k, v in rollouts[1].items():
+        eq(buf.storage_dict["obses"]["obs"] if k == "obs" else buf.storage_dict[k], v, f"second rollout {k}")
+    assert ptrs == {k: (v["obs"] if k == "obses" else v).data_ptr() for k, v in buf.storage_dict.items()}
