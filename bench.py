@@ -59,15 +59,16 @@ def make_cfg(w, device, multi_gpu, cuda_graph, peer=True):
                             truncate_grads=True, cuda_graph=cuda_graph, peer_allreduce=peer))))
 
 
-def oracle_setup(w, seed=0):
-    """Parameters / optimizer / normaliser states of the CPU port for workload w."""
+def oracle_setup(w, seed=0, device="cpu"):
+    """Parameters / optimizer / normaliser states of the oracle port for workload w (on the host, or - for the
+    'reference op sequence on the GPU' baseline - on `device`)."""
     import torch
 
     from oracle import mineral_oracle as oc
 
     norm = w["variant"] != "elu_normal_fixed"
     params = oc.init_actor_critic_params(w["O"], w["A"], w["units"], norm, not norm, seed)
-    params = {k: v.requires_grad_(True) for k, v in params.items()}
+    params = {k: v.to(device).requires_grad_(True) for k, v in params.items()}
     if norm:
         optim = torch.optim.AdamW(list(params.values()), lr=5e-4, eps=1e-5)
         net = dict(n_layers=len(w["units"]), norm=True, act="SiLU", fixed_sigma=False, dist_type="dreamerv3_normal", minstd=0.1, maxstd=1.0)
@@ -79,9 +80,33 @@ def oracle_setup(w, seed=0):
     hp = dict(gamma=0.99, tau=0.95, e_clip=0.2, critic_coef=4, entropy_coef=0.0, bounds_loss_coef=1e-4, bounds_type="bound",
               clip_value_loss=False, use_smooth_clamp=False, mini_epochs=w["mini_epochs"], minibatch_size=w["T"] * w["N"] // w["minibatches"],
               truncate_grads=True, max_grad_norm=mgn, lr_schedule="kl", kl_threshold=0.008)
-    obs_rms = oc.rms_init((w["O"],), 1e-5, 1, torch.float64)
-    value_rms = oc.rms_init((1,), 1e-5, 1, torch.float64)
+    obs_rms = [t.to(device) for t in oc.rms_init((w["O"],), 1e-5, 1, torch.float64)]
+    value_rms = [t.to(device) for t in oc.rms_init((1,), 1e-5, 1, torch.float64)]
     return params, optim, net, hp, obs_rms, value_rms
+
+
+def time_oracle_on_gpu(w, n_updates, warmup, device):
+    """The reference's op sequence (eager torch ops + autograd + torch.optim, ~490 ATen ops per optimizer step, a Python loop over
+    the horizon for GAE, one .item() per mini-epoch: SURVEY.md section 8a) on the SAME GPU: what the unmodified reference would
+    cost on a B200 ('also time reference-on-B200').  Baseline only - nothing of it is on the product path."""
+    import torch
+
+    from oracle import mineral_oracle as oc
+
+    params, optim, net, hp, obs_rms, value_rms = oracle_setup(w, device=device)
+    st0, last = oc.synth_rollout(w["T"], w["N"], w["O"], w["A"], seed=0)
+    st0 = {k: ({kk: vv.to(device) for kk, vv in v.items()} if isinstance(v, dict) else v.to(device)) for k, v in st0.items()}
+    last = last.to(device)
+    lr, times = 5e-4, []
+    for i in range(warmup + n_updates):
+        st = {k: (dict(v) if isinstance(v, dict) else v.clone()) for k, v in st0.items()}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        _, _, lr = oc.ppo_update(st, last, params, optim, obs_rms, value_rms, hp, net, lr)
+        torch.cuda.synchronize()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
 
 
 def time_oracle(w, n_updates, warmup, budget_s):
@@ -460,6 +485,18 @@ def main():
             byts = row * n_env * T + 4 * n_env + (row + 8) * n_env * T
             sweep.append({"envs": n_env, "ms": m, "GB/s": byts / m / 1e6, "frac": byts / m / 1e6 / peak})
 
+    # ---- the reference's op sequence as eager torch on this GPU (reported baseline, not the target) ----
+    torch_gpu = None
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            tg = time_oracle_on_gpu(w, 3, 2, dev)
+            per_g = statistics.mean(tg)
+            torch_gpu = {"value": B / per_g, "unit": "samples/s", "ms_per_step": per_g * 1e3, "kind": "port",
+                         "what": "oracle/mineral_oracle.py:ppo_update with every tensor on cuda:0 - the reference's eager torch op "
+                                 "sequence (autograd, torch.optim, Python GAE loop) on the same B200; 3 timed updates after 2 warm-ups"}
+        except Exception as e:  # a baseline must never take the bench line down
+            torch_gpu = {"unavailable": repr(e)[:200]}
+
     # ---- CPU baseline: the oracle port on this box's host cores, bounded sample ----
     cpu = None
     if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only (the reference arm covers every N)
@@ -488,6 +525,7 @@ def main():
         "roofline": roofline,
         "roofline_tensor": roofline_tensor,
         "cpu_baseline": cpu,
+        "torch_ops_on_gpu": torch_gpu,
         "gae_normalise_hbm_gbs": achieved,
     }
     if sweep:

@@ -399,6 +399,14 @@ def offpolicy_cfg(algo, N, units, batch_size, mini_epochs, variant):
                         update_actor_interval=1, update_targets_interval=1, mini_epochs=mini_epochs, init_alpha=1.0, alpha=None,
                         alpha_optim_kwargs=dict(lr=5e-3), backup_entropy=True, optim_type="AdamW", actor_optim_kwargs=dict(lr=5e-4),
                         critic_optim_kwargs=dict(lr=5e-4), max_grad_norm=0.5)
+        if variant == "fixed":   # the other branches: sigma parameter, dreamerv3 std, no entropy back-up, raw
+            # observations, a target actor, one-step returns, Adam, no time-out handling, a single critic
+            network["normalize_input"] = False
+            network["actor_kwargs"].update(fixed_sigma=True, dist_kwargs=dict(dist_type="dreamerv3_squashed_normal", minstd=0.1, maxstd=1.0))
+            network["critic_kwargs"]["n_critics"] = 1
+            # (a fixed temperature `alpha: 0.2` crashes the reference itself: sac.py:332 returns an unbound `alpha_loss`)
+            algo_cfg.update(backup_entropy=False, no_tgt_actor=False, nstep=1, optim_type="Adam", handle_timeout=False,
+                            update_targets_interval=2, target_entropy_scalar=0.5)
     else:  # AllegroHandDDPG.yaml (TD3-style intervals in the second variant)
         mlp = dict(units=units, act_type="ELU")
         td3 = variant == "td3"
@@ -446,7 +454,7 @@ def gen_offpolicy_e2e():
     from mineral.agents.ddpg.ddpg import DDPG
     from mineral.agents.sac.sac import SAC
     cases = []
-    for algo, variant in (("sac", "ln_silu"), ("sac", "elu"), ("ddpg", "mixed"), ("ddpg", "td3")):
+    for algo, variant in (("sac", "ln_silu"), ("sac", "elu"), ("ddpg", "mixed"), ("ddpg", "td3"), ("sac", "fixed")):
         N, O, A, units, B, mini_epochs, epochs = 16, 11, 3, [32, 16], 64, 3, 2
         torch.manual_seed(50)
         env = rs.SynthEnv(N, O, A, 64, seed=51, done_p=0.08, timeout_p=0.05)
@@ -485,7 +493,7 @@ def gen_offpolicy_e2e():
                     critic_target=clone_tree(agent.critic_target.state_dict()),
                     actor_target=clone_tree(agent.actor_target.state_dict()),
                     log_alpha=agent.log_alpha.detach().clone() if algo == "sac" else None,
-                    obs_rms=clone_tree(agent.obs_rms.state_dict()), next_p=agent.memory.next_p, cur_capacity=agent.memory.cur_capacity))
+                    obs_rms=clone_tree(agent.obs_rms.state_dict()) if agent.obs_rms is not None else {}, next_p=agent.memory.next_p, cur_capacity=agent.memory.cur_capacity))
             streams = {k: [x.clone() for x in v] for k, v in rec.streams.items()}
         cases.append(dict(algo=algo, variant=variant, shape=(N, O, A), cfg=rs.to_plain(cfg), init=init, warm=warm, epochs=per_epoch,
                           streams=streams, env=dict(horizon=64, seed=51, done_p=0.08, timeout_p=0.05)))

@@ -182,9 +182,10 @@ class _Replay:
 
 
 @pytest.mark.parametrize("cuda_graph", [False, True])
-@pytest.mark.parametrize("case_index", [0, 1, 2, 3])
+@pytest.mark.parametrize("case_index", [0, 1, 2, 3, 4])
 def test_offpolicy_agents_match_reference_run(case_index, cuda_graph):
-    """SAC (LayerNorm+SiLU and ELU towers) and DDPG (mixed exploration noise; TD3 with target actor, delayed updates) through
+    """SAC (LayerNorm+SiLU and ELU towers; case 4: sigma parameter, dreamerv3 std, single critic, target actor, raw observations,
+    one-step returns, Adam) and DDPG (mixed exploration noise; TD3 with target actor, delayed updates) through
     warm-up, two explore_env + update_net epochs: trajectories, every logged scalar and every parameter against the real
     reference agents' run on the same env streams and random draws."""
     from mineral_b200.agents import DDPG, SAC
