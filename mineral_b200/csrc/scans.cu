@@ -10,6 +10,7 @@
 namespace {
 
 constexpr int kScanThreads = 128;
+constexpr int kScanChunk = 16;   // horizon steps whose inputs are loaded together
 
 // mineral/agents/ppo/experience.py:96-108
 __global__ void __launch_bounds__(kScanThreads) gae_kernel(const float* __restrict__ rewards,
@@ -52,23 +53,41 @@ __global__ void __launch_bounds__(kScanThreads) critic_targets_kernel(
   const int n = blockIdx.x * kScanThreads + threadIdx.x;
   if (n >= N) return;
   float Ai = 0.f, Bi = 0.f, w = 1.f;
-#pragma unroll 4
-  for (int t = T - 1; t >= 0; --t) {
-    const size_t i = (size_t)t * N + n;
-    float r = __ldg(rew + i);
-    const float nv = __ldg(next_values + i);
-    if (entropy) r = __fadd_rn(r, __fmul_rn(alpha, entropy_term(__ldg(entropy + i), ent_flags, abs_t, inv_abs_t)));
-    if (method == 0) {  // one-step
-      target[i] = __fadd_rn(r, __fmul_rn(gamma, nv));
-      continue;
+  // The scan is sequential in t but its INPUTS are not: every chunk's loads are issued together (one DRAM round trip per
+  // kScanChunk steps instead of one per step: 36.9 -> 12.2 us at cfg3), then the recurrence runs out of registers.  (The GAE
+  // kernel above gets the same effect from `#pragma unroll 8`: its body has no branch that stops the hoisting.)
+  for (int t_hi = T - 1; t_hi >= 0; t_hi -= kScanChunk) {
+    float rr[kScanChunk], nvv[kScanChunk], dd[kScanChunk], hh[kScanChunk];
+#pragma unroll
+    for (int k = 0; k < kScanChunk; ++k) {
+      const int t = t_hi - k;
+      if (t >= 0) {
+        const size_t i = (size_t)t * N + n;
+        rr[k] = __ldg(rew + i), nvv[k] = __ldg(next_values + i);
+        dd[k] = method == 0 ? 0.f : __ldg(done_mask + i);
+        hh[k] = entropy ? __ldg(entropy + i) : 0.f;
+      }
     }
-    const float d = __ldg(done_mask + i);
-    const float live = __fsub_rn(1.0f, d);
-    w = __fadd_rn(__fmul_rn(__fmul_rn(w, lam), live), d);
-    const float adj = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, w), one_minus_lam), r);
-    Ai = __fmul_rn(live, __fadd_rn(__fadd_rn(__fmul_rn(lam_gamma, Ai), __fmul_rn(gamma, nv)), adj));
-    Bi = __fadd_rn(__fmul_rn(gamma, __fadd_rn(__fmul_rn(nv, d), __fmul_rn(Bi, live))), r);
-    target[i] = __fadd_rn(__fmul_rn(one_minus_lam, Ai), __fmul_rn(w, Bi));
+#pragma unroll
+    for (int k = 0; k < kScanChunk; ++k) {
+      const int t = t_hi - k;
+      if (t < 0) continue;
+      const size_t i = (size_t)t * N + n;
+      float r = rr[k];
+      const float nv = nvv[k];
+      if (entropy) r = __fadd_rn(r, __fmul_rn(alpha, entropy_term(hh[k], ent_flags, abs_t, inv_abs_t)));
+      if (method == 0) {  // one-step
+        target[i] = __fadd_rn(r, __fmul_rn(gamma, nv));
+        continue;
+      }
+      const float d = dd[k];
+      const float live = __fsub_rn(1.0f, d);
+      w = __fadd_rn(__fmul_rn(__fmul_rn(w, lam), live), d);
+      const float adj = __fmul_rn(__fdiv_rn(__fsub_rn(1.0f, w), one_minus_lam), r);
+      Ai = __fmul_rn(live, __fadd_rn(__fadd_rn(__fmul_rn(lam_gamma, Ai), __fmul_rn(gamma, nv)), adj));
+      Bi = __fadd_rn(__fmul_rn(gamma, __fadd_rn(__fmul_rn(nv, d), __fmul_rn(Bi, live))), r);
+      target[i] = __fadd_rn(__fmul_rn(one_minus_lam, Ai), __fmul_rn(w, Bi));
+    }
   }
 }
 
