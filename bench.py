@@ -210,7 +210,10 @@ def run_reference(args, w, rank, world):
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    }), file=_RESULT_OUT, flush=True)
+
+
+_RESULT_OUT = sys.stdout
 
 
 def main():
@@ -226,6 +229,12 @@ def main():
                                                         "the fused peer-memory kernels (comparison only)")
     ap.add_argument("--no-kernel-sweep", action="store_true", help="skip timing the fused post-rollout kernel over rollout sizes")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
+    # communicator): keep the real stdout aside for the result line and point fd 1 at stderr for everything else.
+    global _RESULT_OUT
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    sys.stdout.flush()
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     w = WORKLOADS[args.workload]
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -530,7 +539,7 @@ def main():
     }
     if sweep:
         line["post_rollout_sweep"] = sweep
-    print(json.dumps(line))
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
