@@ -343,8 +343,55 @@ class PPO(Agent):
         self.mini_epoch += self.mini_epochs
         return results
 
+    @torch.no_grad()
     def eval(self):
-        raise NotImplementedError('evaluation roll-outs are simulator-bound and out of scope of the update path')
+        """ppo.py:352-408: roll the (sampling) policy until 2 x num_actors episodes have finished, on the same kernels as
+        `play_steps` (obs normalise -> tower GEMMs -> policy-step kernel; episode accounting on the device), write the
+        reference's `eval_scores/*` metrics and `scores.json`."""
+        import json
+        from ..agent import DeviceMetrics
+        self.set_eval()
+        obs = self._convert_obs(self.env.reset())
+        total_eval_episodes = self.num_actors * 2
+        if self._rollout is None and cfg_get(self.ppo_config, 'fused_rollout', True) and _RolloutEngine.supported(self):
+            self._rollout = _RolloutEngine(self)
+        ro = self._rollout
+        scores = {'rewards': torch.zeros(self.num_actors, dtype=torch.float32, device=self.device),
+                  'lengths': torch.zeros(self.num_actors, dtype=torch.int64, device=self.device)}
+        eval_metrics = DeviceMetrics(scores, total_eval_episodes)
+        if ro is not None:
+            ro.begin_rollout()
+            sink = dict(actions=torch.empty(self.num_actors, self.action_dim, device=self.device), neglogp=torch.empty(self.num_actors, device=self.device),
+                        values=torch.empty(self.num_actors, device=self.device), mu=torch.empty(self.num_actors, self.action_dim, device=self.device),
+                        sigma=torch.empty(self.num_actors, self.action_dim, device=self.device))
+        steps, check_every = 0, 16   # the episode counter lives on the device: read it every few steps, not every step
+        while True:
+            if not self.env_autoresets:
+                raise NotImplementedError
+            if ro is not None:
+                ro._forward(obs)
+                ro.eps.normal_()
+                ro._policy(ro.eps, sink['actions'], sink['neglogp'], sink['values'], sink['mu'], sink['sigma'], ro.clamped)
+                actions = ro.clamped
+            else:
+                actions = torch.clamp(self.model_act(obs, sample=True)['actions'], -1.0, 1.0)
+            obs, r, dones, infos = self.env.step(actions)
+            obs = self._convert_obs(obs)
+            r, dones = torch.as_tensor(r, device=self.device), torch.as_tensor(dones, device=self.device)
+            eval_metrics.update(self.epoch, self.env, obs, r.reshape(-1).float(), dones.reshape(-1), infos)
+            steps += 1
+            if steps % check_every == 0 and eval_metrics.num_episodes >= total_eval_episodes:
+                break
+        metrics = {'eval_scores/num_episodes': eval_metrics.num_episodes,
+                   'eval_scores/episode_rewards': eval_metrics.episode_trackers['rewards'].mean(),
+                   'eval_scores/episode_lengths': eval_metrics.episode_trackers['lengths'].mean()}
+        self.writer.add(self.agent_steps, metrics)
+        self.writer.write()
+        out = dict(metrics, epoch=self.epoch, mini_epoch=self.mini_epoch, agent_steps=self.agent_steps)
+        out['eval_scores/episode_rewards'] = eval_metrics.win['rewards'].tolist()
+        out['eval_scores/episode_lengths'] = eval_metrics.win['lengths'].tolist()
+        json.dump(out, open(os.path.join(self.logdir, 'scores.json'), 'w'), indent=4)
+        return metrics
 
     def set_train(self):
         self.model.train()

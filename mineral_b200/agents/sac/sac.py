@@ -214,7 +214,8 @@ class OffPolicyAgent(Agent):
         """sac.py:251-274 / ddpg.py:239-264.  Returns the reference's results dict: lists of 0-dim device tensors, nothing
         synced.  With `cuda_graph` (default) the replay indices and the noise of all mini-epochs are drawn first (two torch RNG
         launches) and everything else - sampling gather, every network pass, losses, optimizer steps, Polyak updates - replays as
-        one CUDA graph of our own kernels."""
+        one CUDA graph of our own kernels.  The result tensors of a replayed call live in the graph's memory pool: read them
+        (the agents' `train()` takes their means right away) before the next `update_net` overwrites them."""
         cfg = self.algo_config
         flags = []
         for _ in range(cfg.mini_epochs):

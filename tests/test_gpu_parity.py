@@ -904,3 +904,52 @@ def test_staged_host_upload_round_trip():
     for k, v in rollouts[1].items():
         eq(buf.storage_dict["obses"]["obs"] if k == "obs" else buf.storage_dict[k], v, f"second rollout {k}")
     assert ptrs == {k: (v["obs"] if k == "obses" else v).data_ptr() for k, v in buf.storage_dict.items()}
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_ppo_eval_runs_and_accounts_episodes(fused):
+    """PPO.eval (ppo.py:352-408): rolls the sampling policy until 2 x num_actors episodes finished; the device-side episode
+    accounting must agree with a host recount of the same done / reward streams."""
+    import json
+    import os
+
+    from mineral_b200.agents import PPO
+    from oracle.reference_shim import SynthEnv, to_attr
+
+    c = load_golden("ppo_e2e")[0]
+    T, N, O, A = c["shape"]
+    cfg = to_attr(c["cfg"])
+    cfg.rl_device = DEV
+    cfg.agent.ppo["fused_rollout"] = fused
+    cpu_env = SynthEnv(N, O, A, 400, seed=7, done_p=0.1, timeout_p=0.0)
+    log = []
+
+    class OnDevice:
+        observation_space, action_space = cpu_env.observation_space, cpu_env.action_space
+
+        def reset(self):
+            return cu(cpu_env.reset())
+
+        def step(self, actions):
+            assert actions.shape == (N, A) and float(actions.abs().max()) <= 1.0     # clamped actions reach the simulator
+            o, r, d, info = cpu_env.step(actions)
+            log.append((r.clone(), d.clone()))
+            return cu(o), cu(r), cu(d), cu(info)
+
+    agent = PPO(cfg, env=OnDevice())
+    agent.model.load_state_dict(c["init_state_dict"])
+    m = agent.eval()
+    # host recount (Metrics._update_scores, mineral/common/metrics.py:59-67)
+    cur_r, cur_l, ep_r, ep_l = torch.zeros(N), torch.zeros(N), [], []
+    for r, d in log:
+        cur_r += r
+        cur_l += 1
+        for i in torch.where(d)[0].tolist():
+            ep_r.append(cur_r[i].item()), ep_l.append(cur_l[i].item())
+            cur_r[i], cur_l[i] = 0, 0
+    assert m["eval_scores/num_episodes"] == len(ep_r) >= 2 * N
+    W = 2 * N
+    scale_close(torch.tensor(m["eval_scores/episode_rewards"]), torch.tensor(ep_r[-W:]).mean() if len(ep_r) >= W else torch.tensor(sum(ep_r) / W), 1e-5, "mean reward")
+    scale_close(torch.tensor(m["eval_scores/episode_lengths"]), torch.tensor(ep_l[-W:]).mean(), 1e-6, "mean length")
+    sc = json.load(open(os.path.join(agent.logdir, "scores.json")))
+    assert sc["eval_scores/num_episodes"] == len(ep_r) and len(sc["eval_scores/episode_rewards"]) == W
