@@ -193,6 +193,8 @@ def run_reference(args, w, rank, world):
         return
     import torch
 
+    # all the host threads this process may use - also under torchrun, which exports OMP_NUM_THREADS=1 to every rank
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     ws, est = shrink_for_cpu(w)
     times = time_oracle(ws, args.steps, args.warmup, budget_s=240)

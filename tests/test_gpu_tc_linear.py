@@ -111,3 +111,45 @@ def test_tc_bwd_weight(M, N, K, act):
     for grp, (rw, rb) in zip(groups, refs):
         scale_close(grp["c"], rw, 5e-6, f"dw {M}x{N}x{K}")
         scale_close(grp["bias_grad"], rb, 3e-5, f"db {M}x{N}x{K}")
+
+
+# ---- SIMT linear entry points (csrc/mlp.cu): the thin-layer kernels (N <= 32: heads) and the tile kernel, same API ----------
+THIN = [(8192, 8, 128), (33, 1, 64), (1000, 21, 64), (257, 16, 128), (4096, 32, 256), (77, 4, 512), (512, 3, 16), (64, 12, 36)]
+WIDE = [(300, 48, 37), (129, 64, 45)]   # not thin (N > 32 or K % 4 != 0): the 128x64 tile kernel
+
+
+@pytest.mark.parametrize("M,N,K", THIN + WIDE)
+def test_simt_linear_fwd_dx_dw_thin_and_tile(M, N, K):
+    """mnr_linear_fwd / _bwd_input (+accumulate) / _bwd_weight for head-shaped layers against float64 torch; two groups per
+    launch with different N in the forward (policy + value heads share a launch), padded input row stride."""
+    from mineral_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(M * 7 + N * 3 + K)
+    ld = (K + 3) // 4 * 4 + 4
+    x = _pad(torch.randn(M, K, device=DEV, generator=g), ld)
+    xs = x[:, :K]
+    w1, b1 = torch.randn(N, K, device=DEV, generator=g) / K**0.5, torch.randn(N, device=DEV, generator=g)
+    w2, b2 = torch.randn(1, K, device=DEV, generator=g) / K**0.5, torch.randn(1, device=DEV, generator=g)
+    y1, y2 = torch.full((M, N), float("nan"), device=DEV), torch.full((M, 1), float("nan"), device=DEV)
+    ops.linear_fwd([dict(a=x, b=w1, c=y1, bias=b1, N=N, K=K, lda=ld), dict(a=x, b=w2, c=y2, bias=b2, N=1, K=K, lda=ld)], M, 0)
+    scale_close(y1, xs.double() @ w1.double().T + b1.double(), 2e-6, "fwd head 1")
+    scale_close(y2, xs.double() @ w2.double().T + b2.double(), 2e-6, "fwd head 2")
+    # input gradient, then accumulate a second head's contribution onto it
+    g1, g2 = torch.randn(M, N, device=DEV, generator=g), torch.randn(M, 1, device=DEV, generator=g)
+    dx = torch.full((M, K), float("nan"), device=DEV)
+    ops.linear_bwd_input([dict(a=g1, b=w1, c=dx, N=N, K=K)], M, 0)
+    scale_close(dx, g1.double() @ w1.double(), 2e-6, "dx")
+    ops.linear_bwd_input([dict(a=g2, b=w2, c=dx, N=1, K=K)], M, 0, accumulate=True)
+    scale_close(dx, g1.double() @ w1.double() + g2.double() @ w2.double(), 3e-6, "dx accumulate")
+    # weight / bias gradients (split over row slabs above 512 rows, fixed-order reduce)
+    ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(2, M, N, K), 256), dtype=torch.uint8, device=DEV)
+    ga, gb = g1, torch.randn(M, N, device=DEV, generator=g)
+    dwa, dba = torch.full((N, K), float("nan"), device=DEV), torch.full((N,), float("nan"), device=DEV)
+    dwb, dbb = torch.full((N, K), float("nan"), device=DEV), torch.full((N,), float("nan"), device=DEV)
+    ops.linear_bwd_weight([dict(a=ga, b=x, c=dwa, bias_grad=dba, N=N, K=K, ldb=ld), dict(a=gb, b=x, c=dwb, bias_grad=dbb, N=N, K=K, ldb=ld)], M, 0, ws)
+    for gg, dw, db in ((ga, dwa, dba), (gb, dwb, dbb)):
+        scale_close(dw, gg.double().T @ xs.double(), 3e-6, "dw")
+        scale_close(db, gg.double().sum(0), 3e-6, "db")
+    again = torch.empty_like(dwa)
+    ops.linear_bwd_weight([dict(a=ga, b=x, c=again, bias_grad=dba, N=N, K=K, ldb=ld)], M, 0, ws)
+    assert torch.equal(again, dwa), "weight gradient is not deterministic"
