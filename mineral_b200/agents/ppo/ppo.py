@@ -143,6 +143,20 @@ class FusedAdam:
 class PPO(Agent):
     r"""Proximal Policy Optimization."""
 
+    @property
+    def last_lr(self):
+        """ppo.py:338-345 keeps the last learning rate as a Python float; here it is device-resident and fetched lazily."""
+        if getattr(self, '_lr_stale', False):
+            st = self.optim.read_state()   # device -> host read (synchronises)
+            self._last_lr = st.lr
+            self.optim.param_groups[0]['lr'] = st.lr
+            self._lr_stale = False
+        return self._last_lr
+
+    @last_lr.setter
+    def last_lr(self, value):
+        self._last_lr, self._lr_stale = value, False
+
     def __init__(self, full_cfg, **kwargs):
         self.network_config = full_cfg.agent.network
         self.ppo_config = full_cfg.agent.ppo
@@ -682,9 +696,9 @@ class _UpdateEngine:
 
     def _results(self):
         a = self.a
-        st = a.optim.read_state()  # the one device->host read of the update
-        a.last_lr = st.lr
-        a.optim.param_groups[0]['lr'] = st.lr
+        # The learning rate lives on the device (KL schedule, mnr_kl_lr_update).  `agent.last_lr` reads it back ON DEMAND, so an
+        # update ends without a host synchronisation and the host-side assembly below overlaps the GPU's work.
+        a._lr_stale = True
         if a.lr_schedule == 'linear':
             a.last_lr = a.scheduler.update(a.agent_steps)
             a.optim.set_lr(a.last_lr)
