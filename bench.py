@@ -343,27 +343,55 @@ def main():
     def e2e_stage():
         agent.storage.stage_from_host(host)
 
-    def e2e_step(stage_next):
+    # The metrics of step i are snapshotted on the compute stream and copied to pinned host memory on a side stream; the host
+    # picks them up one step later (a training loop logs asynchronously), so it never blocks on the GPU and launches step i+1
+    # while step i is still running.  Every step's result does land on the host inside the timed loop (the last one inside
+    # the last interval).
+    res_host = [torch.empty(4, dtype=torch.float32).pin_memory() for _ in range(2)]
+    res_done = [torch.cuda.Event(), torch.cuda.Event()]
+    d2h_stream = torch.cuda.Stream(device=dev)
+    snap_ready = torch.cuda.Event()
+    seen = []
+
+    def e2e_step(i, stage_next):
         agent.storage.commit_staged()
         dev_last.copy_(host_last, non_blocking=True)
         if stage_next:
             e2e_stage()
         res = one_update()
-        return torch.stack([torch.stack(res[k]).mean() for k in ("loss/total", "loss/actor", "loss/critic", "avg_kl")]).cpu()
+        snap = torch.stack([torch.stack(res[k]).mean() for k in ("loss/total", "loss/actor", "loss/critic", "avg_kl")])
+        snap_ready.record()
+        d2h_stream.wait_event(snap_ready)
+        with torch.cuda.stream(d2h_stream):
+            res_host[i & 1].copy_(snap, non_blocking=True)
+            res_done[i & 1].record(d2h_stream)
+        snap.record_stream(d2h_stream)
 
-    for _ in range(2):  # untimed: the first pass through the result read-back pays one-off lazy initialisation (~100 ms)
+    def e2e_collect(i):
+        res_done[i & 1].synchronize()
+        seen.append(res_host[i & 1].clone())
+
+    for w_i in range(2):  # untimed: the first pass through the result read-back pays one-off lazy initialisation (~100 ms)
         e2e_stage()
-        e2e_step(False)
+        e2e_step(w_i, False)
+        e2e_collect(w_i)
+    seen.clear()
     barrier()
+    n_steps = len(e_evs)
     for i, (s0, s1) in enumerate(e_evs):
         flush.zero_()
         s0.record()
         if i == 0:
             e2e_stage()
-        out = e2e_step(i + 1 < len(e_evs))
-        d2h = out.numel() * 4
+        e2e_step(i, i + 1 < n_steps)
+        if i > 0:
+            e2e_collect(i - 1)       # the previous step's metrics, now on the host
+        if i + 1 == n_steps:
+            e2e_collect(i)           # the last step's: wait for it inside its own interval
         s1.record()
     barrier()
+    assert len(seen) == n_steps and all(torch.isfinite(t).all() for t in seen), "e2e: a step's metrics did not reach the host"
+    d2h = 4 * 4
     e_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in e_evs)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
@@ -530,7 +558,8 @@ def main():
                    "l2": "256 MiB read-flush between timed steps", "parallelism": f"env-sharded dp{world}"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "pipeline": "every step uploads its own rollout from pinned host memory (ExperienceBuffer.stage_from_host -> commit_staged) and "
-                            "reads its metrics back; the upload of step i+1 runs on the copy engines under step i's update"},
+                            "copies its metrics to pinned host memory; the upload of step i+1 runs on the copy engines under step i's update and "
+                            "the host collects step i's metrics one step later, so it never blocks on the GPU"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
