@@ -465,6 +465,12 @@ int mnr_ln_act_bwd(const mnr_ln_group_t* groups /*host*/, int n_groups, int64_t 
  * mineral/agents/diffrl/shac.py:841-843); clipped_norm_out (may be NULL) = norm * clip coefficient, the
  * "grad_norm_after_clip" SHAC logs (shac.py:846-856). */
 size_t mnr_fused_adam_workspace_bytes(void);
+/* Optional: a table of up to 8 weight matrices inside the (zero-initialised) optimizer workspace, at this byte offset:
+ *   { int32 count; int32 pad[3]; { int64 off; int32 n, K, ld, pad; float* hi; float* lo; } entry[8]; }
+ * off = first element of the matrix in the flat parameter buffer (multiple of 4), n = rows*K, ld = row stride of hi / lo.
+ * When count > 0, mnr_fused_clip_adam / mnr_peer_reduce_clip_adam also write the tf32 (hi, lo) split of every new weight
+ * (what mnr_split_tf32 computes), so the update chain has no separate split launch per optimizer step. */
+size_t mnr_fused_adam_split_table_offset(void);
 int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm,
                         float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
                         mnr_optim_state_t* st, const float* kl, float* grad_norm_out, int nan_to_num,

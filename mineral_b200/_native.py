@@ -169,6 +169,7 @@ SIGNATURES = {
     "mnr_distl_projection": (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i64, vp]),
     "mnr_episode_scores": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, vp]),
     "mnr_fused_adam_workspace_bytes": (sz, []),
+    "mnr_fused_adam_split_table_offset": (sz, []),
     "mnr_fused_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i32, i32, vp, vp, vp, i32, vp, vp, sz, vp]),
     "mnr_critic_mse_workspace_bytes": (sz, [i64]),
     "mnr_critic_mse_fwd_bwd": (i32, [C.POINTER(CriticSet), i32, vp, i64, vp, vp, sz, vp]),

@@ -101,6 +101,23 @@ class FusedAdam:
             ops.adam_step(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, self.betas[0], self.betas[1], self.eps,
                           self.weight_decay, self.decoupled, True, self.state)
 
+    def attach_splits(self, jobs):
+        """jobs: [(weight Parameter living in this optimizer's flat buffer, hi, lo, ld)] for up to 8 tensor-core layers: the
+        fused step kernel then also writes the tf32 (hi, lo) copies of the updated weights (the table of
+        mnr_fused_adam_split_table_offset in include/mineral_b200.h), so no separate split launch is needed per step."""
+        import struct
+        assert len(jobs) <= 8
+        base, blob = self.flat.data_ptr(), struct.pack('<4i', len(jobs), 0, 0, 0)
+        for w, hi, lo, ld in jobs:
+            off = (w.data.data_ptr() - base) // 4
+            n, k = w.shape
+            assert 0 <= off and off + n * k <= self.flat.numel() and off % 4 == 0 and hi.is_contiguous() and lo.is_contiguous()
+            blob += struct.pack('<q4i2Q', off, n * k, k, ld, 0, hi.data_ptr(), lo.data_ptr())
+        o = ops.lib.mnr_fused_adam_split_table_offset()
+        self.fused_ws[o:o + len(blob)].copy_(torch.frombuffer(bytearray(blob), dtype=torch.uint8))
+        self._split_refs = jobs   # keep the (hi, lo) buffers alive
+        self.splits_attached = len(jobs) > 0
+
     def zero_grad(self):
         self.flat_grad.zero_()
 
@@ -580,6 +597,9 @@ class _UpdateEngine:
             self.towers = FusedTowers(a.model, self.mb, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
             if self.towers.fused_heads_ok:
                 self.heads_ws = ops.ppo_heads_workspace(self.mb, self.A, self.towers.widths[-1], dev)
+                jobs = self.towers.stack.split_jobs()
+                if 0 < len(jobs) <= 8 and cfg_get(a.ppo_config, 'fused_split', True):
+                    a.optim.attach_splits(jobs)
         self.graph = None
         self._warm = 0
         self.graph_launches = 0  # kernels of ours inside one captured update
@@ -603,6 +623,11 @@ class _UpdateEngine:
         x_ld = None
         peer = a.comm is not None
         fused_opt = cfg_get(a.ppo_config, 'fused_optimizer', True)
+        # tf32 (hi, lo) weight copies: split ONCE here (whatever changed the weights since the last update), afterwards the
+        # fused optimizer kernel keeps them current (FusedAdam.attach_splits)
+        opt_splits = (self.towers is not None and self.towers.use_tc and (peer or fused_opt) and getattr(a.optim, 'splits_attached', False))
+        if opt_splits:
+            self.towers.stack._split_weights()
 
         def optimizer_step(step):
             m = self.metrics[step]
@@ -634,7 +659,7 @@ class _UpdateEngine:
                         x_ld = None
                 if self.towers is not None and self.towers.fused_heads_ok:
                     # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward: no torch op, no autograd
-                    self.towers.forward_towers(obs['obs'], x_ld)
+                    self.towers.forward_towers(obs['obs'], x_ld, split=not opt_splits)
                     self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1),
                                                    a.optim.tail if peer else self.metrics[step], self.loss_cfg,
                                                    self.heads_ws, self.mu_mean[step], self.sigma_mean[step])

@@ -93,6 +93,24 @@ __device__ __forceinline__ void peer_barrier(const Comm& c, uint32_t flag) {
   __syncthreads();
 }
 
+constexpr size_t kWsHeader = 256;
+
+// Optional table in the optimizer workspace (after the per-CTA partials; zero = absent): weight matrices whose tf32 (hi, lo)
+// copies the tensor-core linear kernels read (csrc/tc_linear.cu).  The Adam phase rewrites them right where it writes the new
+// parameter, so the update chain needs no separate split launch per optimizer step.
+constexpr int kMaxSplit = 8;
+struct SplitEntry {
+  long long off;   // first element of the matrix in the flat parameter buffer (multiple of 4)
+  int n, K, ld, pad;  // elements (rows * K), row length, row stride of hi / lo
+  float* hi;
+  float* lo;
+};
+struct SplitTable {
+  int count, pad[3];
+  SplitEntry e[kMaxSplit];
+};
+constexpr size_t kSplitTableOffset = kWsHeader + 160 * sizeof(double);
+
 struct AdamArgs {
   float* param;
   float* m;
@@ -113,6 +131,7 @@ struct AdamArgs {
   float* clipped_norm_out; // norm * clip coefficient (the "after clip" norm SHAC logs), may be NULL
   double* parts;                // gridDim.x doubles
   unsigned long long* counter;  // grid barrier
+  const SplitTable* split;      // in the workspace; count == 0: nothing to split
 };
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float clip, float beta1, float beta2, float eps,
@@ -138,10 +157,13 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   __shared__ double s_w[kThreads / 32];
   __shared__ float s_bcast[4];
   __shared__ float s_tail[32];
+  __shared__ SplitTable s_split;
   mnr::pdl_trigger();   // PDL: see common.cuh
   mnr::pdl_wait();
   const int world = WORLD == 1 ? 1 : c.world;
   const int tid = threadIdx.x;
+  for (int w = tid; w < (int)(sizeof(SplitTable) / 4); w += kThreads)   // visible after the barriers below
+    reinterpret_cast<uint32_t*>(&s_split)[w] = reinterpret_cast<const uint32_t*>(a.split)[w];
   const int64_t n4 = a.n >> 2;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
   const int64_t first = (int64_t)blockIdx.x * kThreads + tid;
@@ -241,6 +263,36 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     adam1(P.z, G.z, M.z, V.z, clip, a.beta1, a.beta2, a.eps, a.wd, a.decoupled, lr32, step_size, bc2s);
     adam1(P.w, G.w, M.w, V.w, clip, a.beta1, a.beta2, a.eps, a.wd, a.decoupled, lr32, step_size, bc2s);
     p4[i] = P, m4[i] = M, v4[i] = V;
+    // tf32 (hi, lo) copies of the tensor-core layers' weights (what mnr_split_tf32 would produce from the new parameters)
+    const int n_split = s_split.count;
+    if (n_split > 0) {
+      const long long f = (long long)i * 4;
+      for (int q = 0; q < n_split; ++q) {
+        const SplitEntry& se = s_split.e[q];
+        if (f < se.off || f >= se.off + se.n) continue;
+        const int e0 = (int)(f - se.off);
+        const float pv[4] = {P.x, P.y, P.z, P.w};
+        if (se.ld == se.K) {   // dense rows: the four elements are contiguous in hi / lo too (off and K are multiples of 4)
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(P.x) & 0xffffe000u), h.y = __uint_as_float(__float_as_uint(P.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(P.z) & 0xffffe000u), h.w = __uint_as_float(__float_as_uint(P.w) & 0xffffe000u);
+          l.x = P.x - h.x, l.y = P.y - h.y, l.z = P.z - h.z, l.w = P.w - h.w;
+          *reinterpret_cast<float4*>(se.hi + e0) = h;
+          *reinterpret_cast<float4*>(se.lo + e0) = l;
+        } else {               // padded rows (K not a multiple of 4): element-wise
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int e = e0 + j;
+            if (e >= se.n) break;
+            const int r = e / se.K, cc = e - r * se.K;
+            const float h = __uint_as_float(__float_as_uint(pv[j]) & 0xffffe000u);
+            se.hi[(size_t)r * se.ld + cc] = h;
+            se.lo[(size_t)r * se.ld + cc] = pv[j] - h;
+          }
+        }
+        break;
+      }
+    }
   }
 
   // ---- phase 4: peers are done reading my gradient -> it may be cleared / rewritten ----
@@ -291,8 +343,6 @@ int adam_grid(int64_t n) {
   if (g > cap) g = cap;
   return (int)(g < 1 ? 1 : g);
 }
-
-constexpr size_t kWsHeader = 256;
 
 }  // namespace
 
@@ -369,7 +419,9 @@ extern "C" int mnr_peer_allgather(const mnr_peer_comm_t* comm, size_t stage_offs
 }
 
 // ---- fused optimizer step ------------------------------------------------------------------------------
-extern "C" size_t mnr_fused_adam_workspace_bytes(void) { return kWsHeader + (size_t)kMaxBlocks * sizeof(double); }
+extern "C" size_t mnr_fused_adam_workspace_bytes(void) { return kSplitTableOffset + sizeof(SplitTable); }
+extern "C" size_t mnr_fused_adam_split_table_offset(void) { return kSplitTableOffset; }
+static_assert(kSplitTableOffset == kWsHeader + (size_t)kMaxBlocks * sizeof(double), "table sits right after the partials");
 
 namespace {
 int fill_adam(AdamArgs& a, float* param, float* exp_avg, float* exp_avg_sq, int64_t n, float max_norm, float beta1, float beta2, float eps,
@@ -385,6 +437,7 @@ int fill_adam(AdamArgs& a, float* param, float* exp_avg, float* exp_avg_sq, int6
   a.st = st, a.norm_out = norm_out, a.nan_to_num = 0, a.clipped_norm_out = nullptr;
   a.counter = reinterpret_cast<unsigned long long*>(workspace);
   a.parts = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + kWsHeader);
+  a.split = reinterpret_cast<const SplitTable*>(static_cast<unsigned char*>(workspace) + kSplitTableOffset);
   a.reduced = nullptr, a.grad = nullptr, a.grad_offset = 0, a.n_tail = 0, a.tail_out = nullptr, a.kl_index = -1, a.kl = nullptr;
   return MNR_OK;
 }

@@ -125,6 +125,12 @@ class TowerStack:
         for s in range(0, len(jobs), 8):
             ops.split_tf32(jobs[s:s + 8])
 
+    def split_jobs(self):
+        """[(weight Parameter, hi, lo, ld)] of every tensor-core layer (FusedAdam.attach_splits)."""
+        if not self.use_tc:
+            return []
+        return [(self.lin[g][i].weight, self.w_hi[i][g], self.w_lo[i][g], self.w_ld[i]) for i in range(self.L) for g in range(self.G)]
+
     def forward(self, x, x_ld=None, rows=None, split=True):
         """x (rows, in_dim) [row stride x_ld floats] -> self.Y[-1][g] for every tower g.  split=False: the hi / lo weight
         copies are current (the weights did not change since the last forward, e.g. inside a rollout)."""
@@ -247,9 +253,9 @@ class FusedTowers:
         self.forward_towers(x, x_ld)
         return self.heads_forward()
 
-    def forward_towers(self, x, x_ld=None):
-        """Both towers up to their last activation (self.Y[-1])."""
-        self.stack.forward(x, x_ld)
+    def forward_towers(self, x, x_ld=None, split=True):
+        """Both towers up to their last activation (self.Y[-1]).  split=False: the (hi, lo) weight copies are current."""
+        self.stack.forward(x, x_ld, split=split)
 
     def backward_towers(self, x):
         self.stack.backward(x)
