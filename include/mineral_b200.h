@@ -613,12 +613,14 @@ typedef struct {
 int mnr_copy_cols_f32(const float* src, int src_ld, float* dst, int dst_ld, int64_t rows, int cols, mnr_stream_t stream);
 int mnr_squashed_sample(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, int64_t rows, int A,
                         const mnr_squash_cfg_t* cfg /*host*/, float* actions, int act_ld, float* log_prob, mnr_stream_t stream);
-int mnr_squashed_bwd(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, const float* g_actions, int g_ld,
+int mnr_squashed_bwd(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, const float* g_actions,
+                     const float* g_actions2 /* optional second addend, same layout (two critic towers) */, int g_ld,
                      const float* log_alpha, float alpha_host, int64_t rows, int A, const mnr_squash_cfg_t* cfg /*host*/, float* g_mu,
                      float* g_logstd, mnr_stream_t stream);
 int mnr_tanh_action(const float* mu, const float* noise, int64_t rows, int A, float noise_lo, float noise_hi, float out_lo,
                     float out_hi, float* actions, int act_ld, mnr_stream_t stream);
-int mnr_tanh_action_bwd(const float* mu, const float* g_actions, int g_ld, int64_t rows, int A, float* g_mu, mnr_stream_t stream);
+int mnr_tanh_action_bwd(const float* mu, const float* g_actions, const float* g_actions2 /* optional */, int g_ld, int64_t rows, int A,
+                        float* g_mu, mnr_stream_t stream);
 int mnr_td_target_stats(const mnr_critic_set_t* qs /*host*/, int n_q, const float* log_prob, const float* reward, const float* done,
                         const float* log_alpha, float alpha_host, float gamma_n, float* out, int64_t rows, float* stats,
                         mnr_stream_t stream);

@@ -177,9 +177,9 @@ SIGNATURES = {
     "mnr_traj_store_step": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp, vp]),
     "mnr_copy_cols_f32": (i32, [vp, i32, vp, i32, i64, i32, vp]),
     "mnr_squashed_sample": (i32, [vp, vp, i32, vp, i64, i32, C.POINTER(SquashCfg), vp, i32, vp, vp]),
-    "mnr_squashed_bwd": (i32, [vp, vp, i32, vp, vp, i32, vp, f32, i64, i32, C.POINTER(SquashCfg), vp, vp, vp]),
+    "mnr_squashed_bwd": (i32, [vp, vp, i32, vp, vp, vp, i32, vp, f32, i64, i32, C.POINTER(SquashCfg), vp, vp, vp]),
     "mnr_tanh_action": (i32, [vp, vp, i64, i32, f32, f32, f32, f32, vp, i32, vp]),
-    "mnr_tanh_action_bwd": (i32, [vp, vp, i32, i64, i32, vp, vp]),
+    "mnr_tanh_action_bwd": (i32, [vp, vp, vp, i32, i64, i32, vp, vp]),
     "mnr_td_target_stats": (i32, [C.POINTER(CriticSet), i32, vp, vp, vp, vp, f32, f32, vp, i64, vp, vp]),
     "mnr_actor_seed": (i32, [C.POINTER(CriticSet), i32, vp, vp, f32, f32, i64, vp, vp, vp]),
     "mnr_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),

@@ -184,7 +184,7 @@ class DDPG(OffPolicyAgent):
         out = torch.empty(5, dtype=torch.float32, device=self.device)
         ops.actor_seed([q.view(-1)[:B] for q in fq.pred], [g.view(-1)[:B] for g in fq.g_pred], None, None, 0.0, 0.0, out[0:4], None)
         dx = fq.input_grad(self.xc, B)
-        ops.tanh_action_bwd(fa.mu_raw, dx[:B, O:O + A], fa.g_mu, B)
+        ops.tanh_action_bwd(fa.mu_raw, dx[0][:B, O:O + A], fa.g_mu, B, g_actions2=dx[1][:B, O:O + A] if len(dx) > 1 else None)
         fa.backward(self.xc, B)
         self.optimizer_update(self.actor_optim, out[4:5])
         self._actor_dirty = True

@@ -448,8 +448,9 @@ class SAC(OffPolicyAgent):
         learn_alpha = cfg.alpha is None
         ops.actor_seed([q.view(-1)[:B] for q in fq.pred], [g.view(-1)[:B] for g in fq.g_pred], self.log_prob[:B], log_alpha, alpha_host,
                        self.target_entropy, out[0:4], self.log_alpha.grad.view(1) if learn_alpha else None)
-        dx = fq.input_grad(self.xc, B)               # d(-mean Q_min)/d(z, a); only the action block is used (z is data)
-        ops.squashed_bwd(fa.mu_raw, fa.logstd, eps, dx[:B, O:O + A], log_alpha, alpha_host, self._squash, fa.g_mu, fa.g_ls, B)
+        dx = fq.input_grad(self.xc, B)               # d(-mean Q_min)/d(z, a) per tower; only the action block is used (z is data)
+        ops.squashed_bwd(fa.mu_raw, fa.logstd, eps, dx[0][:B, O:O + A], log_alpha, alpha_host, self._squash, fa.g_mu, fa.g_ls, B,
+                         g_actions2=dx[1][:B, O:O + A] if len(dx) > 1 else None)
         fa.backward(self.xc, B)
         self.optimizer_update(self.actor_optim, out[4:5])
         self._actor_dirty = True

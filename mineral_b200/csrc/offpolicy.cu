@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(kThreads) squashed_sample_kernel(const float* 
 // (the Normal.log_prob terms through u and through (mu, sigma) cancel to -1/sigma; checked against autograd in the oracle).
 // c_logp = alpha / rows with alpha = exp(*log_alpha) (sac.py:323: actor_loss = (alpha * log_prob - Q).mean()) or alpha_host.
 __global__ void __launch_bounds__(kThreads) squashed_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ logstd, int ls_bcast,
-                                                                const float* __restrict__ eps, const float* __restrict__ g_act, int g_ld,
+                                                                const float* __restrict__ eps, const float* __restrict__ g_act,
+                                                                const float* __restrict__ g_act2, int g_ld,
                                                                 const float* __restrict__ log_alpha, float alpha_host, int64_t rows, int A,
                                                                 SquashCfg cfg, float* __restrict__ g_mu, float* __restrict__ g_ls) {
   const int64_t r = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -152,7 +153,8 @@ __global__ void __launch_bounds__(kThreads) squashed_bwd_kernel(const float* __r
     const float sig = squash_sigma(cfg, __ldg(logstd + (ls_bcast ? j : r * A + j)), &dsig);
     const float u = __fadd_rn(m, __fmul_rn(e, sig));
     const float a = tanhf(u);
-    const float ga = g_act ? __ldg(g_act + r * g_ld + j) : 0.f;
+    float ga = g_act ? __ldg(g_act + r * g_ld + j) : 0.f;
+    if (g_act2) ga += __ldg(g_act2 + r * g_ld + j);   // the second critic tower's input gradient (same layout)
     const float gu = c * 2.0f * a + ga * (1.0f - a * a);
     g_mu[r * A + j] = gu;
     g_ls[r * A + j] = (gu * e - c / sig) * dsig;
@@ -178,14 +180,17 @@ __global__ void __launch_bounds__(kThreads) tanh_action_kernel(const float* __re
     act[r * act_ld + j] = a;
   }
 }
-__global__ void __launch_bounds__(kThreads) tanh_action_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ g_act, int g_ld,
-                                                                   int64_t rows, int A, float* __restrict__ g_mu) {
+__global__ void __launch_bounds__(kThreads) tanh_action_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ g_act,
+                                                                   const float* __restrict__ g_act2, int g_ld, int64_t rows, int A,
+                                                                   float* __restrict__ g_mu) {
   const int64_t n = rows * A, stride = (int64_t)gridDim.x * kThreads;
   for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
     const int64_t r = i / A;
     const int j = (int)(i - r * A);
     const float a = tanhf(__ldg(mu + i));
-    g_mu[i] = __ldg(g_act + r * g_ld + j) * (1.0f - a * a);
+    float ga = __ldg(g_act + r * g_ld + j);
+    if (g_act2) ga += __ldg(g_act2 + r * g_ld + j);
+    g_mu[i] = ga * (1.0f - a * a);
   }
 }
 
@@ -381,14 +386,15 @@ extern "C" int mnr_squashed_sample(const float* mu, const float* logstd, int log
   MNR_LAUNCH_RESULT();
 }
 
-extern "C" int mnr_squashed_bwd(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, const float* g_actions, int g_ld,
-                                const float* log_alpha, float alpha_host, int64_t rows, int A, const mnr_squash_cfg_t* cfg, float* g_mu,
+extern "C" int mnr_squashed_bwd(const float* mu, const float* logstd, int logstd_broadcast, const float* eps, const float* g_actions,
+                                const float* g_actions2, int g_ld, const float* log_alpha, float alpha_host, int64_t rows, int A, const mnr_squash_cfg_t* cfg, float* g_mu,
                                 float* g_logstd, mnr_stream_t stream) {
   MNR_CHECK_PTR(mu); MNR_CHECK_PTR(logstd); MNR_CHECK_PTR(eps); MNR_CHECK_PTR(cfg); MNR_CHECK_PTR(g_mu); MNR_CHECK_PTR(g_logstd);
   if (rows <= 0 || A <= 0 || A > kMaxAct || (g_actions && g_ld < A)) return MNR_ESHAPE;
   if (cfg->dist_type < 0 || cfg->dist_type > 1) return MNR_EUNSUP;
   squashed_bwd_kernel<<<(unsigned)((rows + kThreads - 1) / kThreads), kThreads, 0, mnr_cs(stream)>>>(
-      mu, logstd, logstd_broadcast, eps, g_actions, g_ld, log_alpha, alpha_host, rows, A, pack_squash(cfg), g_mu, g_logstd);
+      mu, logstd, logstd_broadcast, eps, g_actions, g_actions ? g_actions2 : nullptr, g_ld, log_alpha, alpha_host, rows, A, pack_squash(cfg), g_mu,
+      g_logstd);
   MNR_LAUNCH_RESULT();
 }
 
@@ -401,11 +407,11 @@ extern "C" int mnr_tanh_action(const float* mu, const float* noise, int64_t rows
   MNR_LAUNCH_RESULT();
 }
 
-extern "C" int mnr_tanh_action_bwd(const float* mu, const float* g_actions, int g_ld, int64_t rows, int A, float* g_mu,
-                                   mnr_stream_t stream) {
+extern "C" int mnr_tanh_action_bwd(const float* mu, const float* g_actions, const float* g_actions2, int g_ld, int64_t rows, int A,
+                                   float* g_mu, mnr_stream_t stream) {
   MNR_CHECK_PTR(mu); MNR_CHECK_PTR(g_actions); MNR_CHECK_PTR(g_mu);
   if (rows <= 0 || A <= 0 || g_ld < A) return MNR_ESHAPE;
-  tanh_action_bwd_kernel<<<grid_for(rows * A), kThreads, 0, mnr_cs(stream)>>>(mu, g_actions, g_ld, rows, A, g_mu);
+  tanh_action_bwd_kernel<<<grid_for(rows * A), kThreads, 0, mnr_cs(stream)>>>(mu, g_actions, g_actions2, g_ld, rows, A, g_mu);
   MNR_LAUNCH_RESULT();
 }
 

@@ -42,7 +42,8 @@ class FusedQ:
         f32 = dict(dtype=torch.float32, device=device)
         self.pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
         self.g_pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
-        self.dx = torch.empty(rows, self.in_dim, **f32)
+        # d objective / d input per critic tower (tensor-core path: one launch, the consumer adds the towers) or summed (SIMT)
+        self.dx = [torch.empty(rows, self.in_dim, **f32) for _ in range(self.G if self.stack.use_tc else 1)]
         h = self.stack.widths[-1]
         self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(self.G, rows, 1, h), 256), dtype=torch.uint8, device=device)
         self.mse_ws = torch.zeros(ops.lib.mnr_critic_mse_workspace_bytes(rows), dtype=torch.uint8, device=device)
@@ -69,12 +70,13 @@ class FusedQ:
         st.backward(x, rows)
 
     def input_grad(self, x, rows=None):
-        """After forward(x) and with d objective / d Q_k in self.g_pred: d objective / d x -> self.dx (rows, in_dim), summed over
-        the critics.  No parameter gradient is formed (the critic is frozen here: `critic.requires_grad_(False)`)."""
+        """After forward(x) and with d objective / d Q_k in self.g_pred: d objective / d x -> self.dx, a list of (rows, in_dim)
+        tensors whose SUM is the gradient (one per critic on the tensor-core path, a single summed one otherwise).  No parameter
+        gradient is formed (the critic is frozen here: `critic.requires_grad_(False)`)."""
         rows = self.M if rows is None else rows
         st, h = self.stack, self.stack.widths[-1]
         ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=1, K=h) for g in range(self.G)], rows, 0)
-        st.backward(x, rows, weight_grads=False, input_grad=self.dx)
+        st.backward(x, rows, weight_grads=False, input_grad=self.dx if st.use_tc else self.dx[0])
         return self.dx
 
 

@@ -162,7 +162,8 @@ class TowerStack:
         saved outputs inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta).
         weight_grads=False skips the weight-gradient GEMMs (a frozen network that is only differentiated through, e.g. the
         critics inside SAC.update_actor, sac.py:313-326; LayerNorm's dgamma / dbeta are still written and are garbage to
-        the caller).  input_grad: contiguous (rows, in_dim) tensor receiving d loss / d x summed over the towers."""
+        the caller).  input_grad: contiguous (rows, in_dim) tensor receiving d loss / d x summed over the towers, or a list of G
+        such tensors, one per tower (tensor-core path, one launch)."""
         M = self.M if rows is None else rows
         G, top = self.G, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
@@ -189,10 +190,16 @@ class TowerStack:
             else:
                 ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
             if i == 0 and input_grad is not None:
-                # the first layer's K is the raw input width (not a tensor-core shape): SIMT kernel, contiguous (rows, K) output
-                for g in range(G):  # one launch per tower: the second accumulates onto the first's result
-                    ops.linear_bwd_input([dict(a=self.dY[0][g], b=self.lin[g][0].weight.data, c=input_grad, saved=saved[g], N=n, K=k)],
-                                         M, self.gemm_act, accumulate=g > 0)
+                if isinstance(input_grad, (list, tuple)):
+                    # one tensor-core launch for all towers, each into its own contiguous (rows, K) tensor (the caller adds them)
+                    assert self.use_tc and len(input_grad) == G
+                    ops.tc_linear_bwd_input([dict(a=self.dY[0][g], b=self.w_hi[0][g], b_lo=self.w_lo[0][g], c=input_grad[g], saved=saved[g],
+                                                  N=n, K=k, ldb=self.w_ld[0]) for g in range(G)], M, self.gemm_act)
+                else:
+                    # SIMT kernel, one launch per tower: the second accumulates onto the first's result
+                    for g in range(G):
+                        ops.linear_bwd_input([dict(a=self.dY[0][g], b=self.lin[g][0].weight.data, c=input_grad, saved=saved[g], N=n, K=k)],
+                                             M, self.gemm_act, accumulate=g > 0)
             if i > 0:
                 if self.use_tc:
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],

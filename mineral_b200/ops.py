@@ -490,11 +490,20 @@ def squashed_sample(mu, logstd, eps, cfg, actions, log_prob=None, rows=None):
                                   stream()), "mnr_squashed_sample")
 
 
-def squashed_bwd(mu, logstd, eps, g_actions, log_alpha, alpha_host, cfg, g_mu, g_logstd, rows=None):
+def _second_grad(g_actions2, gld):
+    if g_actions2 is None:
+        return None
+    gp2, gld2 = nv.ptr_strided(g_actions2, "g_actions2")
+    assert gld2 == gld, "both action-gradient views must share a row stride"
+    return gp2
+
+
+def squashed_bwd(mu, logstd, eps, g_actions, log_alpha, alpha_host, cfg, g_mu, g_logstd, rows=None, g_actions2=None):
     rows = mu.shape[0] if rows is None else rows
     A = mu.shape[1]
     gp, gld = nv.ptr_strided(g_actions, "g_actions") if g_actions is not None else (None, 0)
-    check(lib.mnr_squashed_bwd(ptr(mu, F32, "mu"), ptr(logstd, F32, "logstd"), int(logstd.dim() == 1), ptr(eps, F32, "eps"), gp, gld,
+    check(lib.mnr_squashed_bwd(ptr(mu, F32, "mu"), ptr(logstd, F32, "logstd"), int(logstd.dim() == 1), ptr(eps, F32, "eps"), gp,
+                               _second_grad(g_actions2, gld), gld,
                                ptr(log_alpha, F32, allow_none=True), float(alpha_host), rows, A, C.byref(cfg), ptr(g_mu, F32), ptr(g_logstd, F32),
                                stream()), "mnr_squashed_bwd")
 
@@ -508,10 +517,11 @@ def tanh_action(mu, noise, actions, noise_bounds=None, out_bounds=None, rows=Non
                               stream()), "mnr_tanh_action")
 
 
-def tanh_action_bwd(mu, g_actions, g_mu, rows=None):
+def tanh_action_bwd(mu, g_actions, g_mu, rows=None, g_actions2=None):
     rows = mu.shape[0] if rows is None else rows
     gp, gld = nv.ptr_strided(g_actions, "g_actions")
-    check(lib.mnr_tanh_action_bwd(ptr(mu, F32, "mu"), gp, gld, rows, mu.shape[1], ptr(g_mu, F32), stream()), "mnr_tanh_action_bwd")
+    check(lib.mnr_tanh_action_bwd(ptr(mu, F32, "mu"), gp, _second_grad(g_actions2, gld), gld, rows, mu.shape[1], ptr(g_mu, F32), stream()),
+          "mnr_tanh_action_bwd")
 
 
 def td_target_stats(q_values, log_prob, reward, done, log_alpha, alpha_host, gamma_n, out, stats=None):

@@ -72,6 +72,13 @@ def test_squashed_normal_kernels_match_reference_golden_and_oracle():
     o_mu, o_ls = oc.squashed_bwd(mu, ls, eps, g_act, 0.2 / B, **kw)
     scale_close(act, o_act, 2e-6, "actions 8192"), scale_close(lp, o_lp, 2e-6, "log_prob 8192")
     scale_close(g_mu, o_mu, 3e-6, "g_mu 8192"), scale_close(g_ls, o_ls, 3e-6, "g_logstd 8192")
+    # the action gradient given as two addends (one per critic tower)
+    from mineral_b200 import ops as _ops
+    part = torch.randn(B, A, generator=g) / B
+    g2_mu, g2_ls = torch.empty(B, A, device=DEV), torch.empty(B, A, device=DEV)
+    _ops.squashed_bwd(cu(mu), cu(ls), cu(eps), cu(g_act - part), torch.tensor([0.2], device=DEV).log(), 0.0, _squash_cfg(kw), g2_mu, g2_ls,
+                      g_actions2=cu(part))
+    scale_close(g2_mu, o_mu, 3e-6, "g_mu, two towers"), scale_close(g2_ls, o_ls, 3e-6, "g_logstd, two towers")
     # fixed sigma: the (A,) parameter is broadcast; deterministic branch returns the un-squashed mean
     ls1 = torch.randn(A, generator=g) * 0.3
     cfg = _squash_cfg(kw)
@@ -98,6 +105,9 @@ def test_offpolicy_row_kernels_vs_oracle():
     g_mu = torch.empty(B, A, device=DEV)
     ops.tanh_action_bwd(cu(mu), cu(ga), g_mu)
     scale_close(g_mu, ga * (1 - mu.tanh() ** 2), 2e-6, "tanh_action_bwd")
+    gb = torch.randn(B, A, generator=g)   # two addends (one input gradient per critic tower)
+    ops.tanh_action_bwd(cu(mu), cu(ga), g_mu, g_actions2=cu(gb))
+    scale_close(g_mu, (ga + gb) * (1 - mu.tanh() ** 2), 2e-6, "tanh_action_bwd, two towers")
     # actor objective + seeds (SAC with a device temperature, DDPG without log-prob)
     q = [5 * torch.randn(B, generator=g) for _ in range(2)]
     q[1][:100] = q[0][:100]                              # ties: torch.min picks the first critic
