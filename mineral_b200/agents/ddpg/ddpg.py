@@ -66,6 +66,7 @@ class DDPG(OffPolicyAgent):
         self._fa_t = FusedActor(self.actor_target, B, dev) if not cfg.no_tgt_actor else self._fa
         self._fq = FusedQ(self.critic, B, dev)
         self._fq_t = FusedQ(self.critic_target, B, dev)
+        self._attach_optimizer_splits()
 
     # --- noise draws (hooks; torch.normal(0, std) == std * standard normal) ---
     def _exploration_noise(self, rows):
@@ -169,7 +170,7 @@ class DDPG(OffPolicyAgent):
         out = torch.empty(2, dtype=torch.float32, device=self.device)
         ops.td_target_stats([q.view(-1)[:B] for q in q_t], None, self.reward_b.view(-1), self.done_b.view(-1), None, 0.0,
                             cfg.gamma ** cfg.nstep, self.target_q.view(-1), None)
-        self._fq.loss_fwd_bwd(self.xc, self.target_q, out[0:1])
+        self._fq.loss_fwd_bwd(self.xc, self.target_q, out[0:1], split=self._split_needed())
         self.optimizer_update(self.critic_optim, out[1:2])
         return out[0], out[1]
 
@@ -180,14 +181,14 @@ class DDPG(OffPolicyAgent):
         fa, fq = self._fa, self._fq
         fa.forward(self.xc, self.x_ld, B, split=self._actor_dirty)
         ops.tanh_action(fa.mu_raw, None, self.xc[:B, O:O + A], None, None, B)
-        fq.forward(self.xc, B)
+        fq.forward(self.xc, B, split=self._split_needed())
         out = torch.empty(5, dtype=torch.float32, device=self.device)
         ops.actor_seed([q.view(-1)[:B] for q in fq.pred], [g.view(-1)[:B] for g in fq.g_pred], None, None, 0.0, 0.0, out[0:4], None)
         dx = fq.input_grad(self.xc, B)
         ops.tanh_action_bwd(fa.mu_raw, dx[0][:B, O:O + A], fa.g_mu, B, g_actions2=dx[1][:B, O:O + A] if len(dx) > 1 else None)
         fa.backward(self.xc, B)
         self.optimizer_update(self.actor_optim, out[4:5])
-        self._actor_dirty = True
+        self._actor_dirty = self._split_needed()
         return out[0], out[4]
 
     def eval(self):

@@ -252,13 +252,36 @@ class OffPolicyAgent(Agent):
             self._actor_dirty = True
         return results
 
+    def _attach_optimizer_splits(self):
+        """The optimizer kernels keep the tf32 (hi, lo) copies of the actor's / critics' tensor-core weights current
+        (FusedAdam.attach_splits): inside update_net no forward pass of a trained network needs its own split launch."""
+        self._splits_attached = False
+        fa, fq = self._fa.stack, self._fq.stack
+        if fa.use_tc and fq.use_tc and len(fa.split_jobs()) <= 8 and len(fq.split_jobs()) <= 8:
+            self.actor_optim.attach_splits(fa.split_jobs())
+            self.critic_optim.attach_splits(fq.split_jobs())
+            self._splits_attached = True
+        self._in_update = False
+
+    def _split_needed(self):
+        """Does a forward of the critic need a fresh (hi, lo) split?  Not inside update_net once the optimizers write them."""
+        return not (self._splits_attached and self._in_update)
+
     def _enqueue_update(self, memory, flags):
         results = collections.defaultdict(list)
-        for i, (do_actor, do_targets) in enumerate(flags):
-            if self._pre is not None:
-                self._pre['i'] = i
-            self._sample_into_inputs(memory, self.batch_size)
-            self._mini_epoch(results, do_actor, do_targets)
+        if self._splits_attached:   # whatever changed the weights since the last call (load_state_dict, ...): split once
+            self._fa.stack._split_weights()
+            self._fq.stack._split_weights()
+            self._actor_dirty = False
+        self._in_update = True
+        try:
+            for i, (do_actor, do_targets) in enumerate(flags):
+                if self._pre is not None:
+                    self._pre['i'] = i
+                self._sample_into_inputs(memory, self.batch_size)
+                self._mini_epoch(results, do_actor, do_targets)
+        finally:
+            self._in_update = False
         return results
 
     def _soft_updates(self):
@@ -325,6 +348,7 @@ class SAC(OffPolicyAgent):
         if hasattr(self.env, 'step'):
             self.timer.wrap('env', self.env, ['step'])
         self.timer_total_names = ('agent.explore_env', 'memory.add_to_buffer', 'agent.update_net')
+        self._attach_optimizer_splits()
         self.log_prob = torch.empty(max(B, self.num_actors), **f32)
         self._eps_actor = None
         self._scalars = torch.zeros(16, **f32)   # scratch for per-step scalar outputs that nobody keeps
@@ -429,7 +453,7 @@ class SAC(OffPolicyAgent):
         ops.td_target_stats([q.view(-1)[:B] for q in q_t], self.log_prob[:B] if cfg.backup_entropy else None, self.reward_b.view(-1),
                             self.done_b.view(-1), log_alpha, alpha_host, cfg.gamma ** cfg.nstep, self.target_q.view(-1), out[0:4])
         # regression of both critics on the shared target + clip + optimizer step
-        self._fq.loss_fwd_bwd(self.xc, self.target_q, out[4:5])
+        self._fq.loss_fwd_bwd(self.xc, self.target_q, out[4:5], split=self._split_needed())
         self.optimizer_update(self.critic_optim, out[5:6])
         target_values = {'target_values/mean': out[0], 'target_values/std': out[1], 'target_values/max': out[2], 'target_values/min': out[3]}
         return out[4], out[5], target_values
@@ -442,7 +466,7 @@ class SAC(OffPolicyAgent):
         if obs is not None:
             self._normalize_into(obs['obs'] if isinstance(obs, dict) else obs, self.xc, B)
         eps = self._policy(self.xc, B, True, True, self.xc[:B, O:O + A], slot=1)
-        fq.forward(self.xc, B)                       # the critic step just changed the weights: fresh (hi, lo) split
+        fq.forward(self.xc, B, split=self._split_needed())   # the critic step just changed the weights
         log_alpha, alpha_host = self._alpha_args()
         out = torch.empty(5, dtype=torch.float32, device=self.device)   # actor loss, entropy, alpha loss, alpha, grad norm
         learn_alpha = cfg.alpha is None
@@ -453,7 +477,7 @@ class SAC(OffPolicyAgent):
                          g_actions2=dx[1][:B, O:O + A] if len(dx) > 1 else None)
         fa.backward(self.xc, B)
         self.optimizer_update(self.actor_optim, out[4:5])
-        self._actor_dirty = True
+        self._actor_dirty = self._split_needed()
         if learn_alpha:
             self.optimizer_update(self.alpha_optim, self._scalars[0:1])
         return out[0], out[2], out[1], out[4]

@@ -57,11 +57,11 @@ class FusedQ:
                         for g in range(self.G)], rows, 0)
         return self.pred
 
-    def loss_fwd_bwd(self, x, target, loss_out):
+    def loss_fwd_bwd(self, x, target, loss_out, split=True):
         """sum_k MSE(Q_k(x), target) (sac.py:301-303, ddpg.py:295-296) -> loss_out (1 float) and every critic parameter's .grad."""
         rows, st, G = target.numel(), self.stack, self.G
         h = st.widths[-1]
-        self.forward(x, rows)
+        self.forward(x, rows, split)
         ops.critic_mse_sum_fwd_bwd([p.view(-1)[:rows] for p in self.pred], target.view(-1), [g_.view(-1)[:rows] for g_ in self.g_pred],
                                    loss_out, self.mse_ws)
         ops.linear_bwd_weight([dict(a=self.g_pred[g], b=st.Y[-1][g], c=self.last[g].weight.grad, bias_grad=self.last[g].bias.grad, N=1, K=h)
