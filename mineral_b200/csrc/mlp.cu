@@ -205,16 +205,31 @@ __global__ void __launch_bounds__(256) reduce_splits_kernel(const __grid_constan
   const Group g = gs.g[gi];
   const int NK = g.N * g.K;
   const int idx = blockIdx.x * 256 + threadIdx.x;
+  // four independent accumulation chains, 16 loads in flight (the thin path uses hundreds of splits: a single chain of
+  // dependent adds behind L2 latency took 23 us); fixed order => deterministic
   if (idx < NK) {
-    float s = 0.f;
-    for (int z = 0; z < splits; ++z) s += __ldg(partials + ((size_t)gi * splits + z) * NK + idx);
-    g.c[idx] = s;
+    const float* p = partials + (size_t)gi * splits * NK + idx;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+#pragma unroll 4
+    for (; z + 3 < splits; z += 4) {
+      s0 += __ldg(p + (size_t)z * NK), s1 += __ldg(p + (size_t)(z + 1) * NK);
+      s2 += __ldg(p + (size_t)(z + 2) * NK), s3 += __ldg(p + (size_t)(z + 3) * NK);
+    }
+    for (; z < splits; ++z) s0 += __ldg(p + (size_t)z * NK);
+    g.c[idx] = (s0 + s1) + (s2 + s3);
   } else if (idx < NK + g.N && g.bias_grad) {
     const int n = idx - NK;
-    float s = 0.f;
-    const float* bp = partials + (size_t)gs.n * splits * NK;
-    for (int z = 0; z < splits; ++z) s += __ldg(bp + ((size_t)gi * splits + z) * g.N + n);
-    g.bias_grad[n] = s;
+    const float* bp = partials + (size_t)gs.n * splits * NK + (size_t)gi * splits * g.N + n;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int z = 0;
+#pragma unroll 4
+    for (; z + 3 < splits; z += 4) {
+      s0 += __ldg(bp + (size_t)z * g.N), s1 += __ldg(bp + (size_t)(z + 1) * g.N);
+      s2 += __ldg(bp + (size_t)(z + 2) * g.N), s3 += __ldg(bp + (size_t)(z + 3) * g.N);
+    }
+    for (; z < splits; ++z) s0 += __ldg(bp + (size_t)z * g.N);
+    g.bias_grad[n] = (s0 + s1) + (s2 + s3);
   }
 }
 
