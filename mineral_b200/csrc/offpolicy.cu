@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(kThreads) tanh_action_bwd_kernel(const float* 
 }
 
 constexpr int kOneCta = 1024;
+constexpr int kRowChunk = 4;   // rows per thread whose inputs are loaded together in the one-CTA kernels
 __device__ __forceinline__ float block_minmax(float v, bool want_max) {
   __shared__ float s_mm[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -220,15 +221,37 @@ __global__ void __launch_bounds__(kOneCta) td_target_stats_kernel(const QSet qs,
   const float alpha = log_alpha ? expf(__ldg(log_alpha)) : alpha_host;
   double sum = 0.0;
   float mx = -INFINITY, mn = INFINITY;
-  for (int64_t i = threadIdx.x; i < rows; i += kOneCta) {
-    float t = __ldg(qs.q[0] + i);
-    for (int k = 1; k < n_q; ++k) t = fminf(t, __ldg(qs.q[k] + i));
-    if (log_prob) t = __fsub_rn(t, __fmul_rn(alpha, __ldg(log_prob + i)));
-    const float nd = __fsub_rn(1.0f, __ldg(done + i));
-    const float y = __fadd_rn(__ldg(reward + i), __fmul_rn(__fmul_rn(nd, gamma_n), t));
-    out[i] = y;
-    sum += (double)y;
-    mx = fmaxf(mx, y), mn = fminf(mn, y);
+  // one CTA, so a thread owns rows/1024 rows: their inputs are loaded kRowChunk rows at a time BEFORE any of them is used
+  // (otherwise every row is its own DRAM round trip: 15.6 us for 8192 rows)
+  for (int64_t i0 = threadIdx.x; i0 < rows; i0 += (int64_t)kOneCta * kRowChunk) {
+    float q[kRowChunk][MNR_MAX_CRITICS], lp[kRowChunk], rw[kRowChunk], dn[kRowChunk];
+#pragma unroll
+    for (int u = 0; u < kRowChunk; ++u) {
+      const int64_t i = i0 + (int64_t)u * kOneCta;
+      if (i < rows) {
+#pragma unroll
+        for (int k = 0; k < MNR_MAX_CRITICS; ++k)
+          if (k < n_q) q[u][k] = __ldg(qs.q[k] + i);
+        lp[u] = log_prob ? __ldg(log_prob + i) : 0.f;
+        rw[u] = __ldg(reward + i), dn[u] = __ldg(done + i);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kRowChunk; ++u) {
+      const int64_t i = i0 + (int64_t)u * kOneCta;
+      if (i < rows) {
+        float t = q[u][0];
+#pragma unroll
+        for (int k = 1; k < MNR_MAX_CRITICS; ++k)
+          if (k < n_q) t = fminf(t, q[u][k]);
+        if (log_prob) t = __fsub_rn(t, __fmul_rn(alpha, lp[u]));
+        const float nd = __fsub_rn(1.0f, dn[u]);
+        const float y = __fadd_rn(rw[u], __fmul_rn(__fmul_rn(nd, gamma_n), t));
+        out[i] = y;
+        sum += (double)y;
+        mx = fmaxf(mx, y), mn = fminf(mn, y);
+      }
+    }
   }
   if (!stats) return;
   __shared__ double s_mean;
@@ -261,17 +284,34 @@ __global__ void __launch_bounds__(kOneCta) actor_seed_kernel(const QSet qs, int 
   const float alpha = log_alpha ? expf(__ldg(log_alpha)) : alpha_host;
   const float seed = -1.0f / (float)rows;
   double s_loss = 0.0, s_lp = 0.0;
-  for (int64_t i = threadIdx.x; i < rows; i += kOneCta) {
-    float q = __ldg(qs.q[0] + i);
-    int arg = 0;
-    for (int k = 1; k < n_q; ++k) {
-      const float v = __ldg(qs.q[k] + i);
-      if (v < q) q = v, arg = k;
+  for (int64_t i0 = threadIdx.x; i0 < rows; i0 += (int64_t)kOneCta * kRowChunk) {   // chunked loads, see td_target_stats_kernel
+    float qv[kRowChunk][MNR_MAX_CRITICS], lpv[kRowChunk];
+#pragma unroll
+    for (int u = 0; u < kRowChunk; ++u) {
+      const int64_t i = i0 + (int64_t)u * kOneCta;
+      if (i < rows) {
+#pragma unroll
+        for (int k = 0; k < MNR_MAX_CRITICS; ++k)
+          if (k < n_q) qv[u][k] = __ldg(qs.q[k] + i);
+        lpv[u] = log_prob ? __ldg(log_prob + i) : 0.f;
+      }
     }
-    for (int k = 0; k < n_q; ++k) gs.g[k][i] = k == arg ? seed : 0.f;
-    const float lp = log_prob ? __ldg(log_prob + i) : 0.f;
-    s_loss += (double)(alpha * lp - q);
-    s_lp += (double)lp;
+#pragma unroll
+    for (int u = 0; u < kRowChunk; ++u) {
+      const int64_t i = i0 + (int64_t)u * kOneCta;
+      if (i < rows) {
+        float q = qv[u][0];
+        int arg = 0;
+#pragma unroll
+        for (int k = 1; k < MNR_MAX_CRITICS; ++k)
+          if (k < n_q && qv[u][k] < q) q = qv[u][k], arg = k;
+#pragma unroll
+        for (int k = 0; k < MNR_MAX_CRITICS; ++k)
+          if (k < n_q) gs.g[k][i] = k == arg ? seed : 0.f;
+        s_loss += (double)(alpha * lpv[u] - q);
+        s_lp += (double)lpv[u];
+      }
+    }
   }
   const double t_loss = mnr::block_sum(s_loss);
   const double t_lp = mnr::block_sum(s_lp);
