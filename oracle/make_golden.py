@@ -531,6 +531,48 @@ def gen_sac_policy():
     save("sac_policy", cases)
 
 
+# ---- DDPG action noise (mineral/agents/ddpg/noise.py:22-55) and the actor objectives' seeds (sac.py:320-331, ddpg.py:305-307) --------
+def gen_offpolicy_small():
+    from mineral.agents.ddpg import noise as noise_mod
+    g = torch.Generator().manual_seed(80)
+    out = dict(noise=[], objective=[])
+    B, A = 96, 5
+    mu = torch.randn(B, A, generator=g) * 2
+    for kind, kw in (("fixed", dict(std=0.8, out_bounds=[-1.0, 1.0])),
+                     ("fixed", dict(std=0.8, noise_bounds=[-0.2, 0.2], out_bounds=[-1.0, 1.0])),
+                     ("mixed", dict(std_min=0.05, std_max=0.8, out_bounds=[-1.0, 1.0]))):
+        drawn = {}
+        real_normal = torch.normal
+
+        def spy(mean, std, *a, **k):
+            drawn["noise"] = real_normal(mean, std, *a, **k)
+            return drawn["noise"]
+
+        noise_mod.torch.normal = spy   # (noise.py's `torch` IS torch: restored right below)
+        try:
+            fn = noise_mod.add_normal_noise if kind == "fixed" else noise_mod.add_mixed_normal_noise
+            res = fn(mu.tanh(), **kw)
+        finally:
+            torch.normal = real_normal
+        out["noise"].append(dict(kind=kind, kwargs=kw, mu=mu.clone(), noise=drawn["noise"].clone(), actions=res.clone()))
+    # actor objectives through the reference's own expressions + autograd
+    for use_lp in (True, False):
+        qs = [(5 * torch.randn(B, 1, generator=g)).requires_grad_() for _ in range(2)]
+        with torch.no_grad():
+            qs[1][:10] = qs[0][:10]   # ties
+        lp = torch.randn(B, 1, generator=g) - 3
+        alpha, te = 0.37, -float(A)
+        q_min = torch.min(torch.stack(qs), dim=0).values                      # EnsembleQ.get_q_min (ddpg/models.py:108-110)
+        actor_loss = (alpha * lp - q_min).mean() if use_lp else -q_min.mean()  # sac.py:323 / ddpg.py:306
+        actor_loss.backward()
+        entropy = -lp
+        alpha_loss = (alpha * (entropy - te)).mean()                           # sac.py:329-330 (value; d/dlog_alpha equals it)
+        out["objective"].append(dict(use_lp=use_lp, q=[q.detach().clone() for q in qs], log_prob=lp, alpha=alpha, target_entropy=te,
+                                     actor_loss=actor_loss.detach().clone(), entropy=entropy.mean(), alpha_loss=alpha_loss,
+                                     seeds=[q.grad.clone() for q in qs]))
+    save("offpolicy_small", out)
+
+
 if __name__ == "__main__":
     gen_experience()
     gen_rms()
@@ -544,3 +586,4 @@ if __name__ == "__main__":
     gen_ppo_e2e()
     gen_offpolicy_e2e()
     gen_sac_policy()
+    gen_offpolicy_small()

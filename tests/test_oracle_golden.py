@@ -211,3 +211,21 @@ def test_sac_policy_head_matches_reference_autograd():
         t_mu, t_ls = oc.squashed_bwd(d["mu"], d["logstd"], d["eps"], d["g_act"], c["alpha"] / B, **kw)
         scale_close(g_mu, t_mu, 2e-6, "g_mu vs f64")
         scale_close(g_ls, t_ls, 2e-6, "g_logstd vs f64")
+
+
+def test_ddpg_noise_and_actor_objectives_match_reference():
+    """oc.tanh_action against the reference's add_normal_noise / add_mixed_normal_noise (its own torch.normal draw recorded),
+    oc.actor_objective against the reference's expressions under autograd (first-minimum tie rule of torch.min included)."""
+    c = load_golden("offpolicy_small")
+    for n in c["noise"]:
+        kw = n["kwargs"]
+        got = oc.tanh_action(n["mu"], n["noise"], kw.get("noise_bounds"), kw.get("out_bounds"))
+        assert torch.equal(got, n["actions"]), n["kind"]
+    for o in c["objective"]:
+        a_loss, ent, al_loss, seeds = oc.actor_objective([q.view(-1) for q in o["q"]], o["log_prob"].view(-1) if o["use_lp"] else None,
+                                                         o["alpha"] if o["use_lp"] else 0.0, o["target_entropy"])
+        scale_close(a_loss, o["actor_loss"], 1e-6, "actor_loss")
+        for s_, r_ in zip(seeds, o["seeds"]):
+            assert torch.equal(s_, r_.view(-1)), "seeds (argmin / tie rule)"
+        if o["use_lp"]:
+            scale_close(ent, o["entropy"], 1e-6, "entropy"), scale_close(al_loss, o["alpha_loss"], 1e-6, "alpha_loss")
