@@ -432,6 +432,13 @@ int mnr_adam_step(float* param, float* grad, float* exp_avg, float* exp_avg_sq, 
 int mnr_kl_lr_update(mnr_optim_state_t* st, double kl_threshold, double min_lr, double max_lr,
                      float* avg_kl_out, double* lr_out, mnr_stream_t stream);
 
+/* End of a mini-epoch under lr_schedule 'cos' / 'linear' (mineral/agents/ppo/ppo.py:339-348,
+ * ppo/utils.py:23-37): those rules depend on host counters only (mini-epoch index, agent_steps), so the
+ * host uploads the value that takes effect after each mini-epoch (*lr_new, f64 device) and this call
+ * installs it; avg_kl = kl_sum/kl_count is reported and the accumulator reset as in mnr_kl_lr_update. */
+int mnr_lr_table_update(mnr_optim_state_t* st, const double* lr_new, float* avg_kl_out, double* lr_out,
+                        mnr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * a10  LayerNorm + activation between the tower GEMMs (mineral/nets/mlp.py:66-71; the shipped PPO recipes
  *      mineral/cfgs/agent/DFlexAntPPO.yaml:17-21 and AllegroHandPPO.yaml:18-28 use Linear -> LayerNorm -> SiLU).

@@ -159,6 +159,7 @@ SIGNATURES = {
     "mnr_grad_norm_prepare": (i32, [vp, i64, f32, f32, f32, vp, vp, vp, vp, sz, vp]),
     "mnr_adam_step": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, i32, i32, vp, vp]),
     "mnr_kl_lr_update": (i32, [vp, f64, f64, f64, vp, vp, vp]),
+    "mnr_lr_table_update": (i32, [vp, vp, vp, vp, vp]),
     "mnr_ln_act_fwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, f32, i32, vp]),
     "mnr_ln_act_bwd_workspace_bytes": (sz, [i32, i64, i32]),
     "mnr_ln_act_bwd": (i32, [C.POINTER(LnGroup), i32, i64, i32, i32, vp, sz, vp]),

@@ -171,7 +171,7 @@ class Agent:
                 os.unlink(latest)
             os.symlink(name, latest)
         better = True if self.best_stat is None else (stat > self.best_stat if higher_better else stat < self.best_stat)
-        if better and self.ckpt_every > 0:
+        if better:   # unconditional, as in the reference (agent.py:133-142): the rolling best does not depend on ckpt_every
             if self.best_stat is not None:
                 prev = os.path.join(self.ckpt_dir, f'best_{stat_name}{sep}{self.best_stat:.2f}.pth')
                 if os.path.exists(prev):

@@ -5,19 +5,24 @@
 same module-level loss functions, so `getattr(mineral_b200.agents, cfg.agent.algo)` drops in for
 `mineral.agents.PPO` (mineral/scripts/run.py:140-144).
 
-What runs where during an update (reference line -> here):
+What runs where during an update (reference line -> here); every compute launch is one of this repo's kernels:
   ppo.py:172-183 compute_return + prepare_training + value RMS -> ExperienceBuffer.compute_return_and_prepare
                                                                   (mnr_post_rollout_fused + _finalize)
   ppo.py:258-262 obs_rms.update + normalize per minibatch       -> mnr_rms_batch_moments_f32 once per rollout,
                                                                   mnr_rms_schedule (all steps' statistics up
-                                                                  front), mnr_rms_apply_f32 per step
-  ppo.py:270     model(batch)                                    -> torch/cuBLAS GEMMs (library) up to the
-                                                                  pre-distribution heads
-  ppo.py:271-285,302-303,313 dist/entropy/neglogp/losses/KL/write-back -> mnr_ppo_loss_fwd_bwd (one kernel)
-  ppo.py:291-300 zero_grad/backward/clip/step                    -> autograd through the GEMMs, then
-                                                                  mnr_grad_norm_prepare + mnr_adam_step
-  ppo.py:335-345 avg_kl.item() + AdaptiveScheduler               -> mnr_kl_lr_update (device-resident lr)
-No value is read on the host inside `train_epoch` until the results are assembled at its end.
+                                                                  front), mnr_rms_apply_ld_f32 per step
+  ppo.py:270     model(batch)                                    -> mnr_tc_linear_fwd per tower layer (tcgen05 3xTF32,
+                                                                  both towers in one launch; mnr_linear_fwd for shapes
+                                                                  the tensor-core kernel cannot take; mnr_ln_act_fwd
+                                                                  behind a LayerNorm)
+  ppo.py:271-285,302-303,313 heads/dist/entropy/neglogp/losses/KL/write-back + the head gradients and d loss / d Y
+                                                                 -> mnr_ppo_heads_loss_fwd_bwd (one kernel)
+  ppo.py:291-292 zero_grad / backward                            -> mnr_tc_linear_bwd_weight_partials + mnr_tc_linear_bwd_input
+                                                                  per layer, mnr_tc_reduce_partials once (no autograd graph)
+  ppo.py:294-300 clip_grad_norm_ + optimizer.step                -> mnr_fused_clip_adam / mnr_peer_reduce_clip_adam (one launch)
+  ppo.py:335-348 avg_kl.item() + LR schedule                     -> mnr_kl_lr_update ('kl') / mnr_lr_table_update ('cos', 'linear')
+No value is read on the host inside `train_epoch` until the results are assembled at its end.  There is no torch-module /
+autograd / NCCL data path: a network `FusedTowers.supported()` rejects is an error at construction.
 """
 
 import collections
@@ -47,9 +52,14 @@ class FusedAdam:
     Exposes `param_groups`, `state_dict()`, `load_state_dict()` in torch.optim.Adam's format so PPO
     checkpoints (ppo.py:416-446) stay interchangeable."""
 
-    def __init__(self, params, decoupled, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, comm=None, **unused):
+    def __init__(self, params, decoupled, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=None, comm=None, **other):
         """comm: optional `mineral_b200.peer.PeerComm` whose 'grad' region ((n + 32) floats) holds the flat gradient, so
-        the peers can read it over NVLink (multi-GPU); the step is then ONE fused all-reduce + clip + Adam kernel."""
+        the peers can read it over NVLink (multi-GPU); the step is then ONE fused all-reduce + clip + Adam kernel.
+        Any torch.optim keyword this kernel does not implement (amsgrad, maximize, ...) is an error unless it is switched
+        off: a config must not silently train differently from the reference."""
+        unsupported = {k: v for k, v in other.items() if v not in (False, None) and k not in ('foreach', 'fused', 'capturable')}
+        if unsupported:
+            raise NotImplementedError(f'optim_kwargs not implemented by the fused Adam/AdamW kernel: {sorted(unsupported)}')
         self.params = list(params)
         self.comm = comm
         dev = self.params[0].device
@@ -211,14 +221,24 @@ class PPO(Agent):
         if cfg.optim_type not in ('Adam', 'AdamW'):
             raise NotImplementedError(f'optim_type {cfg.optim_type}: only Adam / AdamW have a fused kernel')
 
-        # --- Multi-GPU: one process per GPU; data path over NVLink peer memory (mineral_b200/peer.py), torch.distributed
-        #     (NCCL) only for set-up, or for everything with `ppo.peer_allreduce: False` ---
+        # --- Networks the kernels cannot run are an error HERE, not a silent torch-module / autograd path ---
+        from ...nets.fused_towers import FusedTowers
+        if not FusedTowers.supported(self.model) or list(self.obs_space) != ['obs'] or len(self.obs_space['obs']) != 1:
+            raise NotImplementedError(
+                'mineral_b200 PPO runs separate actor / value MLP towers of equal shape (Linear [-> LayerNorm] -> ELU | ReLU | SiLU, '
+                'no dropout) on a flat `obs` vector; shared trunks, encoders and dict observations are outside the hot path '
+                '(SURVEY.md section 2 rows 5, 18)')
+        if self.action_dim > 32:
+            raise NotImplementedError('action_dim > 32: the policy-step / heads kernels hold one action vector per thread')
+
+        # --- Multi-GPU: one process per GPU; the data path runs over NVLink peer memory with our own kernels
+        #     (mineral_b200/peer.py, csrc/peer.cu); torch.distributed (NCCL) only carries the set-up handshake ---
         self.world, self.comm = 1, None
         if self.multi_gpu:
             import torch.distributed as dist
             assert dist.is_initialized(), 'multi_gpu=True needs torch.distributed initialised (torchrun)'
             self.world = dist.get_world_size()
-            if self.world > 1 and cfg_get(cfg, 'peer_allreduce', True):
+            if self.world > 1:
                 from ...peer import PeerComm, TAIL_FLOATS
                 n_flat = sum((p.numel() + 3) // 4 * 4 for p in self.model.parameters())
                 self.comm = PeerComm({'grad': (n_flat + TAIL_FLOATS) * 4, 'stage': 1 << 20}, self.device)
@@ -247,8 +267,10 @@ class PPO(Agent):
         self.mini_epochs = cfg['mini_epochs']
         assert self.batch_size % self.minibatch_size == 0 or 'train' not in cfg_get(full_cfg, 'run', 'train')
 
-        # --- LR schedule (ppo.py:85-93) ---
+        # --- LR schedule (ppo.py:85-93): 'fixed' | 'linear' | 'kl' | 'cos' (mineral/cfgs/agent/DFlexAntPPO.yaml:63) ---
         self.lr_schedule = cfg['lr_schedule']
+        if self.lr_schedule not in ('fixed', 'constant', 'linear', 'kl', 'cos'):
+            raise NotImplementedError(f'lr_schedule {self.lr_schedule!r}')
         self.min_lr, self.max_lr = cfg_get(cfg, 'min_lr', 1e-6), cfg_get(cfg, 'max_lr', 1e-2)
         if self.lr_schedule == 'kl':
             self.kl_threshold = cfg['kl_threshold']
@@ -267,52 +289,39 @@ class PPO(Agent):
         self.use_cuda_graph = bool(cfg_get(cfg, 'cuda_graph', False))
 
     # -------------------------------------------------------------------------------------------
+    @torch.no_grad()
     def model_act(self, obs_dict, sample=True, **kwargs):
-        """ppo.py:125-131."""
-        if self.normalize_input:
-            obs_dict = {k: self.obs_rms[k].normalize(v) for k, v in obs_dict.items()}
-        out = self.model.act(obs_dict, sample=sample, **kwargs)
-        if self.normalize_value and sample:
-            out['values'] = self.value_rms.unnormalize(out['values'])
+        """ppo.py:125-131 on the rollout kernels: obs normalise -> tower GEMMs -> policy-step kernel (heads, sample,
+        neglogp, un-normalised value).  Returns the reference's keys `actions / neglogp / values / mu / sigma`."""
+        ro = self._rollout_engine()
+        ro.begin_rollout()
+        N, A = self.num_actors, self.action_dim
+        assert obs_dict['obs'].shape[0] == N, 'model_act expects one observation per actor'
+        f32 = dict(dtype=torch.float32, device=self.device)
+        out = dict(actions=torch.empty(N, A, **f32), neglogp=torch.empty(N, **f32), values=torch.empty(N, 1, **f32),
+                   mu=torch.empty(N, A, **f32), sigma=torch.empty(N, A, **f32))
+        ro._forward(obs_dict)
+        if not sample:   # models.py:113-114: the raw `mu` head output, nothing else
+            return ro.towers.heads_forward()[0].clone()
+        ro.eps.normal_()
+        ro._policy(ro.eps, out['actions'], out['neglogp'], out['values'].view(-1), out['mu'], out['sigma'], None,
+                   unnormalize_value=self.normalize_value)
         return out
+
+    def _rollout_engine(self):
+        if self._rollout is None:
+            if not _RolloutEngine.supported(self):
+                raise NotImplementedError('the rollout kernels need a heads input of <= 512 features and a `scale` reward shaper')
+            self._rollout = _RolloutEngine(self)
+        return self._rollout
 
     @torch.no_grad()
     def play_steps(self):
-        """ppo.py:133-183.  Agent side of every env step on our kernels when the network allows it (`_RolloutEngine`:
-        obs normalise -> tower GEMMs -> one policy-step kernel writing into the storage rows -> env.step -> one
-        post-step kernel), else the reference's torch op sequence; the tail is the fused
-        post-rollout pass either way."""
-        if self._rollout is None and cfg_get(self.ppo_config, 'fused_rollout', True) and _RolloutEngine.supported(self):
-            self._rollout = _RolloutEngine(self)
-        if self._rollout is not None:
-            return self._play_steps_fused()
-        for n in range(self.horizon_len):
-            if not self.env_autoresets and any(self.dones):
-                done_indices = torch.where(self.dones)[0].tolist()
-                obs_reset = self._convert_obs(self.env.reset_idx(done_indices))
-                for k, v in obs_reset.items():
-                    self.obs[k][done_indices] = v
-            model_out = self.model_act(self.obs)
-            self.storage.update_data('obses', n, self.obs)
-            for k in ['actions', 'neglogp', 'values', 'mu', 'sigma']:
-                self.storage.update_data(k, n, model_out[k])
-            actions = torch.clamp(model_out['actions'], -1.0, 1.0)
-            obs, r, self.dones, infos = self.env.step(actions)
-            self.obs = self._convert_obs(obs)
-            r, self.dones = torch.as_tensor(r, device=self.device), torch.as_tensor(self.dones, device=self.device)
-            rewards = r.reshape(-1, 1)
-            self.storage.update_data('dones', n, self.dones)
-            shaped_rewards = self.reward_shaper(rewards.clone())
-            if self.value_bootstrap and 'time_outs' in infos:
-                time_outs = torch.as_tensor(infos['time_outs'], device=self.device).reshape(-1, 1)
-                shaped_rewards += self.gamma * model_out['values'] * time_outs.float()
-            self.storage.update_data('rewards', n, shaped_rewards)
-            done_indices = torch.where(self.dones)[0].tolist()
-            self.metrics.update(self.epoch, self.env, self.obs, rewards.squeeze(-1), done_indices, infos)
-        self.metrics.flush_video(self.epoch)
-
-        last_values = self.model_act(self.obs)['values']
-        self.finish_rollout(last_values)
+        """ppo.py:133-183.  The agent side of every env step runs on our kernels (`_RolloutEngine`: obs normalise -> tower
+        GEMMs -> one policy-step kernel writing into the storage rows -> env.step -> one post-step kernel; SURVEY.md
+        section 8f row 1); the tail is the fused post-rollout pass."""
+        self._rollout_engine()
+        return self._play_steps_fused()
 
     @torch.no_grad()
     def _play_steps_fused(self):
@@ -352,6 +361,9 @@ class PPO(Agent):
             self.set_train()
             results = self.train_epoch()
             self.storage.data_dict = None
+            if self.comm is not None and self.comm.error():   # host read; the metrics below synchronise anyway
+                raise RuntimeError(f'rank {self.rank}: a cross-GPU wait timed out (peer {self.comm.error() - 1} died or diverged); '
+                                   'the optimizer skipped the affected steps and left the parameters untouched')
             if not self.multi_gpu or self.rank == 0:
                 metrics = {f'train_stats/{k}': torch.mean(torch.stack(v)).item() for k, v in results.items() if v[0].dim() == 0}
                 metrics['train_stats/last_lr'] = self.last_lr
@@ -384,28 +396,22 @@ class PPO(Agent):
         self.set_eval()
         obs = self._convert_obs(self.env.reset())
         total_eval_episodes = self.num_actors * 2
-        if self._rollout is None and cfg_get(self.ppo_config, 'fused_rollout', True) and _RolloutEngine.supported(self):
-            self._rollout = _RolloutEngine(self)
-        ro = self._rollout
+        ro = self._rollout_engine()
         scores = {'rewards': torch.zeros(self.num_actors, dtype=torch.float32, device=self.device),
                   'lengths': torch.zeros(self.num_actors, dtype=torch.int64, device=self.device)}
         eval_metrics = DeviceMetrics(scores, total_eval_episodes)
-        if ro is not None:
-            ro.begin_rollout()
-            sink = dict(actions=torch.empty(self.num_actors, self.action_dim, device=self.device), neglogp=torch.empty(self.num_actors, device=self.device),
-                        values=torch.empty(self.num_actors, device=self.device), mu=torch.empty(self.num_actors, self.action_dim, device=self.device),
-                        sigma=torch.empty(self.num_actors, self.action_dim, device=self.device))
+        ro.begin_rollout()
+        sink = dict(actions=torch.empty(self.num_actors, self.action_dim, device=self.device), neglogp=torch.empty(self.num_actors, device=self.device),
+                    values=torch.empty(self.num_actors, device=self.device), mu=torch.empty(self.num_actors, self.action_dim, device=self.device),
+                    sigma=torch.empty(self.num_actors, self.action_dim, device=self.device))
         steps, check_every = 0, 16   # the episode counter lives on the device: read it every few steps, not every step
         while True:
             if not self.env_autoresets:
                 raise NotImplementedError
-            if ro is not None:
-                ro._forward(obs)
-                ro.eps.normal_()
-                ro._policy(ro.eps, sink['actions'], sink['neglogp'], sink['values'], sink['mu'], sink['sigma'], ro.clamped)
-                actions = ro.clamped
-            else:
-                actions = torch.clamp(self.model_act(obs, sample=True)['actions'], -1.0, 1.0)
+            ro._forward(obs)
+            ro.eps.normal_()
+            ro._policy(ro.eps, sink['actions'], sink['neglogp'], sink['values'], sink['mu'], sink['sigma'], ro.clamped)
+            actions = ro.clamped
             obs, r, dones, infos = self.env.step(actions)
             obs = self._convert_obs(obs)
             r, dones = torch.as_tensor(r, device=self.device), torch.as_tensor(dones, device=self.device)
@@ -467,15 +473,14 @@ class _RolloutEngine:
     @staticmethod
     def supported(agent):
         from ...nets.fused_towers import FusedTowers
-        return (FusedTowers.supported(agent.model) and list(agent.obs_space) == ['obs'] and len(agent.obs_space['obs']) == 1 and
-                agent.action_dim <= 32 and agent.model.mu.weight.shape[1] <= 512 and agent.reward_shaper.fn == 'scale')
+        return agent.model.mu.weight.shape[1] <= 512 and agent.reward_shaper.fn == 'scale'   # the rest: PPO.__init__
 
     def __init__(self, agent):
         from ...nets.fused_towers import FusedTowers
         a = self.a = agent
         dev, N, A = a.device, a.num_actors, a.action_dim
         self.N, self.A = N, A
-        self.towers = FusedTowers(a.model, N, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
+        self.towers = FusedTowers(a.model, N, dev)
         f32 = dict(dtype=torch.float32, device=dev)
         self.in_dim = a.obs_space['obs'][0]
         self.x_ld = (self.in_dim + 3) // 4 * 4
@@ -512,13 +517,14 @@ class _RolloutEngine:
             self.x[:, :self.in_dim].copy_(o)
         tw.stack.forward(self.x, self.x_ld, rows=self.N, split=False)
 
-    def _policy(self, eps, actions, neglogp, values, mu, sigma, clamped):
+    def _policy(self, eps, actions, neglogp, values, mu, sigma, clamped, unnormalize_value=True):
         a, m, tw = self.a, self.a.model, self.towers
         fixed = m.fixed_sigma
-        clamp = tuple(a.value_rms.clamp_range) if (a.normalize_value and a.value_rms.with_clamp) else None
+        val_tab = self.val_tab if unnormalize_value else (None, None)
+        clamp = tuple(a.value_rms.clamp_range) if (val_tab[0] is not None and a.value_rms.with_clamp) else None
         ops.policy_step(tw.Y[-1][0], tw.Y[-1][1], m.mu.weight.data, m.mu.bias.data, m.value.weight.data, m.value.bias.data,
                         None if fixed else m.sigma.weight.data, m.sigma.data if fixed else m.sigma.bias.data, eps,
-                        self.val_tab[0], self.val_tab[1], clamp, actions, neglogp, values, mu, sigma, clamped, self.cfg, rows=self.N)
+                        val_tab[0], val_tab[1], clamp, actions, neglogp, values, mu, sigma, clamped, self.cfg, rows=self.N)
 
     def act(self, t, obs):
         sd = self.a.storage.storage_dict
@@ -590,16 +596,21 @@ class _UpdateEngine:
                     mean_tab=torch.zeros(self.steps, cols, **f32), denom_tab=torch.zeros(self.steps, cols, **f32),
                     x=torch.zeros(self.mb, (cols + 3) // 4 * 4, **f32), x_ld=(cols + 3) // 4 * 4,
                     ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
-        # actor/critic towers: explicit fwd/bwd on the hand-written linear kernels when the architecture allows
+        # actor / value towers: explicit forward / backward on the hand-written linear kernels (tcgen05 where the widths
+        # allow, SIMT twins otherwise); PPO.__init__ has already rejected networks FusedTowers cannot run
         from ...nets.fused_towers import FusedTowers
-        self.towers = None
-        if cfg_get(a.ppo_config, 'fused_mlp', True) and FusedTowers.supported(a.model) and list(a.obs_space) == ['obs']:
-            self.towers = FusedTowers(a.model, self.mb, dev, use_tc=cfg_get(a.ppo_config, 'tensor_cores', True))
-            if self.towers.fused_heads_ok:
-                self.heads_ws = ops.ppo_heads_workspace(self.mb, self.A, self.towers.widths[-1], dev)
-                jobs = self.towers.stack.split_jobs()
-                if 0 < len(jobs) <= 8 and cfg_get(a.ppo_config, 'fused_split', True):
-                    a.optim.attach_splits(jobs)
+        self.towers = FusedTowers(a.model, self.mb, dev)
+        if self.towers.fused_heads_ok:
+            self.heads_ws = ops.ppo_heads_workspace(self.mb, self.A, self.towers.widths[-1], dev)
+        jobs = self.towers.stack.split_jobs()
+        if 0 < len(jobs) <= 8:   # the optimizer kernel keeps the tf32 (hi, lo) weight copies current
+            a.optim.attach_splits(jobs)
+        if not self.norm_keys:
+            cols = a.obs_space['obs'][0]
+            self._raw_x = torch.zeros(self.mb, (cols + 3) // 4 * 4, **f32)
+        # 'cos' / 'linear': the learning rate that takes effect after each mini-epoch, uploaded by run() before the launches
+        self.lr_table = torch.zeros(a.mini_epochs, dtype=torch.float64, device=dev)
+        self.lr_table_host = torch.zeros(a.mini_epochs, dtype=torch.float64).pin_memory()
         self.graph = None
         self._warm = 0
         self.graph_launches = 0  # kernels of ours inside one captured update
@@ -620,85 +631,82 @@ class _UpdateEngine:
                              self.B * a.world, self.steps, rms.eps, n['mean_tab'], n['denom_tab'])
         max_norm = float(a.max_grad_norm) if a.truncate_grads else 0.0
         step = 0
-        x_ld = None
         peer = a.comm is not None
-        fused_opt = cfg_get(a.ppo_config, 'fused_optimizer', True)
-        # tf32 (hi, lo) weight copies: split ONCE here (whatever changed the weights since the last update), afterwards the
-        # fused optimizer kernel keeps them current (FusedAdam.attach_splits)
-        opt_splits = (self.towers is not None and self.towers.use_tc and (peer or fused_opt) and getattr(a.optim, 'splits_attached', False))
+        # tf32 (hi, lo) weight copies: split ONCE here (whatever changed the weights since the last update: a checkpoint
+        # load, a test poking parameters); afterwards the optimizer kernel keeps them current (FusedAdam.attach_splits)
+        opt_splits = self.towers.use_tc and getattr(a.optim, 'splits_attached', False)
         if opt_splits:
             self.towers.stack._split_weights()
-
-        def optimizer_step(step):
-            m = self.metrics[step]
-            if peer:      # gradient + metrics all-reduce, clip, Adam: one kernel over peer memory
-                a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7)
-                return
-            if a.world > 1:
-                import torch.distributed as dist
-                dist.all_reduce(a.optim.flat_grad)  # grads were pre-scaled by 1/world in the loss kernel
-                dist.all_reduce(m)                  # metrics likewise
-            a.optim.step(max_norm, kl=m[7:8], grad_norm_out=self.grad_norms[step:step + 1], fused=fused_opt)
+        n, rms = (getattr(self, f'_n_{self.norm_keys[0]}'), a.obs_rms[self.norm_keys[0]]) if self.norm_keys else (None, None)
+        clamp = tuple(rms.clamp_range) if (rms is not None and rms.with_clamp) else None
+        if n is None:   # no obs normalisation: the towers read the rows through the same padded stride
+            x_buf, x_ld = self._raw_x, self._raw_x.shape[1]
+        else:
+            x_buf, x_ld = n['x'], n['x_ld']
 
         for ep in range(a.mini_epochs):
             for i in range(self.num_mb):
                 s, e = i * mb, (i + 1) * mb
-                obs = {}
-                for k, v in d['obses'].items():
-                    if k in self.norm_keys:
-                        n, rms = getattr(self, f'_n_{k}'), a.obs_rms[k]
-                        clamp = tuple(rms.clamp_range) if rms.with_clamp else None
-                        if self.towers is not None:  # padded row stride (TMA-friendly); pad columns stay zero
-                            obs[k] = ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, n['x'], n['x_ld'])
-                            x_ld = n['x_ld']
-                        else:
-                            obs[k] = ops.rms_apply(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp,
-                                                   out=n['x'].view(-1)[:self.mb * n['cols']].view(self.mb, *a.obs_space[k]))
-                    else:
-                        obs[k] = v[s:e]
-                        x_ld = None
-                if self.towers is not None and self.towers.fused_heads_ok:
-                    # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward: no torch op, no autograd
-                    self.towers.forward_towers(obs['obs'], x_ld, split=not opt_splits)
-                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1),
-                                                   a.optim.tail if peer else self.metrics[step], self.loss_cfg,
-                                                   self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
-                    self.towers.backward_towers(obs['obs'])
-                    optimizer_step(step)
-                    step += 1
-                    continue
-                if self.towers is not None:
-                    mu_raw, logstd, value = self.towers.forward(obs['obs'], x_ld)
+                v = d['obses']['obs']
+                if n is not None:   # normalise + clamp into the padded (TMA-friendly) row stride; pad columns stay zero
+                    ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, x_buf, x_ld)
                 else:
-                    with torch.enable_grad():
-                        mu_raw, logstd, value = a.model._actor_critic(obs)
-                ops.ppo_loss_fwd_bwd(mu_raw.detach(), logstd.detach().contiguous(), value.detach(), d['actions'][s:e],
-                                     d['neglogp'][s:e], d['advantages'][s:e], d['values'][s:e], d['returns'][s:e],
-                                     d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls, self.g_v,
-                                     a.optim.tail if peer else self.metrics[step], self.loss_cfg, self.loss_ws, True, self.mu_mean[step], self.sigma_mean[step])
-                if self.towers is not None:
-                    self.towers.backward(obs['obs'], self.g_mu, self.g_ls, self.g_v)
+                    x_buf[:, :v.shape[1]].copy_(v[s:e])
+                m = self.metrics[step]
+                if self.towers.fused_heads_ok:
+                    # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward
+                    self.towers.forward_towers(x_buf, x_ld, split=not opt_splits)
+                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), a.optim.tail if peer else m,
+                                                   self.loss_cfg, self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
+                    self.towers.backward_towers(x_buf)
                 else:
-                    torch.autograd.backward([mu_raw, logstd, value], [self.g_mu, self.g_ls, self.g_v])
-                optimizer_step(step)
+                    # heads wider than the fused kernel takes: thin-layer head kernels + the row-wise loss kernel
+                    self.towers.stack.forward(x_buf, x_ld, split=not opt_splits)
+                    mu_raw, logstd, value = self.towers.heads_forward()
+                    ops.ppo_loss_fwd_bwd(mu_raw, logstd.contiguous(), value, d['actions'][s:e], d['neglogp'][s:e], d['advantages'][s:e],
+                                         d['values'][s:e], d['returns'][s:e], d['mu'][s:e], d['sigma'][s:e], self.g_mu, self.g_ls,
+                                         self.g_v, a.optim.tail if peer else m, self.loss_cfg, self.loss_ws, True,
+                                         self.mu_mean[step], self.sigma_mean[step])
+                    self.towers.backward(x_buf, self.g_mu, self.g_ls, self.g_v)
+                # clip_grad_norm_ + Adam(W) + zero_grad: one launch; with peers also the gradient + metrics all-reduce over NVLink
+                if peer:
+                    a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7)
+                else:
+                    a.optim.step(max_norm, kl=m[7:8], grad_norm_out=self.grad_norms[step:step + 1])
                 step += 1
             if a.lr_schedule == 'kl':
                 ops.kl_lr_update(a.optim.state, a.kl_threshold, a.min_lr, a.max_lr, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
+            elif a.lr_schedule in ('cos', 'linear'):
+                ops.lr_table_update(a.optim.state, self.lr_table[ep:ep + 1], self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
             else:
-                # NaN threshold: both comparisons of the rule are false, so it only averages the KL and reports lr
+                # 'fixed': a NaN threshold makes both comparisons of the KL rule false, so it only averages the KL and reports lr
                 ops.kl_lr_update(a.optim.state, float('nan'), 0.0, 1.0, self.avg_kl[ep:ep + 1], self.lr_out[ep:ep + 1])
 
     def _merge_moments_across_ranks(self, n):
-        """Global minibatch i = union of the ranks' local minibatch i."""
+        """Global minibatch i = union of the ranks' local minibatch i; peer-memory all-gather."""
         from ... import distributed as mdist
         mdist.merge_group_moments(n['gm'], n['gv'], self.mb, self.a.obs_rms[self.norm_keys[0]].correction, comm=self.a.comm)
 
-    def run(self):
+    def _upload_lr_table(self):
+        """ppo.py:339-348.  'cos': lr after mini-epoch k = adjust_learning_rate_cos(init_lr, k, mini_epochs, agent_steps,
+        max_agent_steps).  'linear': the reference re-installs `last_lr` (the value its scheduler produced at the END of the
+        previous train_epoch) after every mini-epoch and only then computes the next one, so the new value takes effect one
+        mini-epoch into the next update - reproduced by installing the same `last_lr` after every mini-epoch."""
         a = self.a
         if a.lr_schedule == 'cos':
-            raise NotImplementedError("lr_schedule 'cos' changes lr from the host every mini-epoch; use 'kl', 'linear' or 'fixed'")
+            vals = [adjust_learning_rate_cos(a.init_lr, k, a.mini_epochs, a.agent_steps, a.max_agent_steps) for k in range(a.mini_epochs)]
+        else:
+            vals = [float(a._last_lr)] * a.mini_epochs
+        self.lr_table_host.copy_(torch.tensor(vals, dtype=torch.float64))
+        self.lr_table.copy_(self.lr_table_host, non_blocking=True)   # stream-ordered before the launches / the graph replay
+        return vals
+
+    def run(self):
+        a = self.a
+        if a.lr_schedule in ('cos', 'linear'):
+            self._host_lr = self._upload_lr_table()[-1]
         with torch.no_grad():
-            if a.use_cuda_graph and (a.world == 1 or a.comm is not None):  # NCCL-free => capturable at any world size
+            if a.use_cuda_graph:  # no NCCL call inside the update: capturable at any world size
                 if self.graph is None and self._warm >= 1:
                     torch.cuda.synchronize()
                     from ... import _native as nv
@@ -724,9 +732,10 @@ class _UpdateEngine:
         # The learning rate lives on the device (KL schedule, mnr_kl_lr_update).  `agent.last_lr` reads it back ON DEMAND, so an
         # update ends without a host synchronisation and the host-side assembly below overlaps the GPU's work.
         a._lr_stale = True
-        if a.lr_schedule == 'linear':
-            a.last_lr = a.scheduler.update(a.agent_steps)
-            a.optim.set_lr(a.last_lr)
+        if a.lr_schedule == 'cos':
+            a.last_lr = self._host_lr                       # known on the host: no read-back needed
+        elif a.lr_schedule == 'linear':
+            a.last_lr = a.scheduler.update(a.agent_steps)   # ppo.py:347-348 (takes effect after the next mini-epoch)
         m = self.metrics
         res = collections.defaultdict(list)
         names = ('loss/total', 'loss/actor', 'loss/critic', 'loss/bounds', 'loss/entropy', 'clip_frac', 'explained_var')

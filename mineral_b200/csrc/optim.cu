@@ -153,6 +153,27 @@ extern "C" int mnr_adam_step(float* param, float* grad, float* exp_avg, float* e
   MNR_LAUNCH_RESULT();
 }
 
+// 'cos' / 'linear' schedules (ppo.py:339-348): the learning rate that takes effect after this mini-epoch is a function of
+// host-known counters only (mini-epoch index, agent_steps), so the host uploads one value per mini-epoch before the update
+// and the device installs it here - the update stays one CUDA graph with no host read.
+__global__ void lr_table_kernel(mnr_optim_state_t* st, const double* lr_new, float* avg_kl_out, double* lr_out) {
+  const float avg = st->kl_count > 0 ? (float)(st->kl_sum / (double)st->kl_count) : 0.f;
+  const double lr = *lr_new;
+  st->lr = lr;
+  st->lr_f32 = (float)lr;
+  st->kl_sum = 0.0;
+  st->kl_count = 0;
+  if (avg_kl_out) *avg_kl_out = avg;
+  if (lr_out) *lr_out = lr;
+}
+
+extern "C" int mnr_lr_table_update(mnr_optim_state_t* st, const double* lr_new, float* avg_kl_out, double* lr_out,
+                                   mnr_stream_t stream) {
+  MNR_CHECK_PTR(st); MNR_CHECK_PTR(lr_new);
+  lr_table_kernel<<<1, 1, 0, mnr_cs(stream)>>>(st, lr_new, avg_kl_out, lr_out);
+  MNR_LAUNCH_RESULT();
+}
+
 extern "C" int mnr_kl_lr_update(mnr_optim_state_t* st, double kl_threshold, double min_lr, double max_lr, float* avg_kl_out,
                                 double* lr_out, mnr_stream_t stream) {
   MNR_CHECK_PTR(st);

@@ -175,6 +175,10 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   uint32_t flag = 0;
   if (WORLD != 1) {
     SignalPad* mine = reinterpret_cast<SignalPad*>(c.base[c.rank]);
+    // A spin that timed out in an EARLIER launch left the sticky error word set: the peers are gone (or diverged), so this
+    // and every later step is a no-op - parameters, moments and the optimizer state stay as they were (PPO.train polls
+    // PeerComm.error() once per epoch and raises).  Every CTA reads the same word, so all of them leave together.
+    if (__ldcg(&mine->error) != 0u) return;
     flag = mine->flag[blockIdx.x] + 1u;
     peer_barrier<false>(c, flag);  // every rank's backward has finished writing its gradient
   }
@@ -218,6 +222,17 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     a.parts[blockIdx.x] = s;
   }
   mnr::grid_barrier(a.counter);
+
+  // A barrier spin of THIS launch timed out in some CTA (a dead or diverged peer): the sums above hold stale or partial
+  // peer data.  The error word was written before the grid barrier, so every CTA sees it here and skips phases 2-4:
+  // no optimizer state, parameter or moment is touched and the local gradient is left in place.
+  if (WORLD != 1) {
+    if (tid == 0) s_bcast[0] = __ldcg(&reinterpret_cast<SignalPad*>(c.base[c.rank])->error) != 0u ? 1.f : 0.f;
+    __syncthreads();
+    const bool failed = s_bcast[0] != 0.f;
+    __syncthreads();
+    if (failed) return;
+  }
 
   // ---- phase 2: every CTA derives the same clip coefficient and Adam scalars ----
   if (tid < 32) {

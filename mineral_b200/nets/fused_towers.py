@@ -350,13 +350,21 @@ class FusedCritics:
         self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(self.G, rows, 1, h), 256), dtype=torch.uint8, device=device)
         self.mse_ws = torch.zeros(ops.lib.mnr_critic_mse_workspace_bytes(rows), dtype=torch.uint8, device=device)
 
+    def forward(self, x, x_ld=None, rows=None):
+        """x (rows, in_dim) [row stride x_ld floats] -> self.pred[g] (rows, 1) for every critic g."""
+        rows = self.M if rows is None else rows
+        st = self.stack
+        h = st.widths[-1]
+        st.forward(x, x_ld, rows)
+        ops.linear_fwd([dict(a=st.Y[-1][g], b=self.last[g].weight.data, c=self.pred[g], bias=self.last[g].bias.data, N=1, K=h)
+                        for g in range(self.G)], rows, 0)
+        return self.pred
+
     def loss_fwd_bwd(self, x, target, loss_out, x_ld=None):
         """x (rows, in_dim), target (rows) -> loss_out (1 float), every critic parameter's .grad."""
         rows, G, st = target.numel(), self.G, self.stack
         h = st.widths[-1]
-        st.forward(x, x_ld, rows)
-        ops.linear_fwd([dict(a=st.Y[-1][g], b=self.last[g].weight.data, c=self.pred[g], bias=self.last[g].bias.data, N=1, K=h)
-                        for g in range(G)], rows, 0)
+        self.forward(x, x_ld, rows)
         ops.critic_mse_fwd_bwd([p.view(-1)[:rows] for p in self.pred], target, [g_.view(-1)[:rows] for g_ in self.g_pred], loss_out, self.mse_ws)
         ops.linear_bwd_weight([dict(a=self.g_pred[g], b=st.Y[-1][g], c=self.last[g].weight.grad, bias_grad=self.last[g].bias.grad, N=1, K=h)
                                for g in range(G)], rows, 0, self.ws)

@@ -409,6 +409,12 @@ def critic_mse_fwd_bwd(preds, target, grads, loss_out, ws):
                                      ptr(ws, U8), ws.numel(), stream()), "mnr_critic_mse_fwd_bwd")
 
 
+def lr_table_update(st, lr_new, avg_kl_out=None, lr_out=None):
+    """lr_new: (1,) f64 device tensor holding the learning rate that takes effect after this mini-epoch."""
+    check(lib.mnr_lr_table_update(ptr(st, U8), ptr(lr_new, F64), ptr(avg_kl_out, F32, allow_none=True),
+                                  ptr(lr_out, F64, allow_none=True), stream()), "mnr_lr_table_update")
+
+
 def kl_lr_update(st, kl_threshold, min_lr, max_lr, avg_kl_out=None, lr_out=None):
     check(lib.mnr_kl_lr_update(ptr(st, U8), kl_threshold, min_lr, max_lr, ptr(avg_kl_out, F32, allow_none=True),
                                ptr(lr_out, F64, allow_none=True), stream()), "mnr_kl_lr_update")

@@ -232,7 +232,7 @@ def test_shac_targets_match_reference_golden():
 
     for c in load_golden("tdlambda"):
         T, N = c["rew"].shape
-        ag = SHAC(N, 4, 4, T, DEV, gamma=c["gamma"], lam=c["lam"], critic_method=c["method"], with_logprobs=True)
+        ag = SHAC.from_shapes(N, 4, 4, T, DEV, gamma=c["gamma"], lam=c["lam"], critic_method=c["method"], with_logprobs=True)
         ag.rew_buf.copy_(c["rew"]), ag.done_mask.copy_(c["done_mask"]), ag.next_values.copy_(c["next_values"])
         ag.distr_ent.copy_(c["distr_ent"]), ag.logprobs.copy_(c["logprobs"])
         ag.compute_target_values()
@@ -265,9 +265,8 @@ def test_shac_update_critic_matches_reference_golden(cuda_graph):
     for c in load_golden("shac_critic"):
         T, B, O = c["shape"]
         obs, tv = oc.shac_critic_inputs(c["seed"], T, B, O, c["wild"])
-        ag = SHAC(B, O, 21, T, DEV, critic_iterations=c["iterations"], num_critics=c["n_critics"], critic_lr=c["lr"],
-                  critic_betas=c["betas"], max_grad_norm=c["max_grad_norm"], cuda_graph=cuda_graph)
-        assert ag.fused
+        ag = SHAC.from_shapes(B, O, 21, T, DEV, critic_iterations=c["iterations"], num_critics=c["n_critics"], critic_lr=c["lr"],
+                              critic_betas=c["betas"], max_grad_norm=c["max_grad_norm"], cuda_graph=cuda_graph)
         ag.critic_batch_size = c["batch_size"]
         ag.obs_buf["obs"].copy_(obs), ag.target_values.copy_(tv)
         snap = ag.critic_optim.state_dict()
