@@ -36,7 +36,7 @@ WORKLOADS = {
 }
 
 
-def make_cfg(w, device, multi_gpu, cuda_graph, peer=True):
+def make_cfg(w, device, multi_gpu, cuda_graph):
     from oracle.reference_shim import to_attr
 
     mb = w["T"] * w["N"] // w["minibatches"]
@@ -56,7 +56,7 @@ def make_cfg(w, device, multi_gpu, cuda_graph, peer=True):
                             gamma=0.99, tau=0.95, entropy_coef=0.0, e_clip=0.2, use_smooth_clamp=False, critic_coef=4,
                             bounds_loss_coef=1e-4, bounds_type="bound", mini_epochs=w["mini_epochs"], optim_type=optim_type,
                             optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008, max_grad_norm=mgn,
-                            truncate_grads=True, cuda_graph=cuda_graph, peer_allreduce=peer))))
+                            truncate_grads=True, cuda_graph=cuda_graph))))
 
 
 def oracle_setup(w, seed=0, device="cpu"):
@@ -131,6 +131,67 @@ def time_oracle(w, n_updates, warmup, budget_s):
     return times
 
 
+def reference_cfg(w):
+    """The workload as the REFERENCE's own config (same keys as oracle/make_golden.py:ppo_cfg, which generated the goldens)."""
+    cfg = make_cfg(w, "cpu", False, cuda_graph=False)
+    cfg["env_render"], cfg["run"], cfg["seed"] = False, "train", 0
+    cfg.agent.update(tracker_len=100, metrics_kwargs={}, print_every=-1, ckpt_every=-1)
+    cfg.agent.ppo["multi_gpu"] = False
+    cfg.agent.ppo.pop("cuda_graph", None)
+    return cfg
+
+
+def time_reference(w, n_updates, warmup, budget_s):
+    """Time the UNMODIFIED reference (mineral.agents.ppo.PPO from oracle/_ref or /root/reference) on host cores: its own
+    ExperienceBuffer.compute_return + prepare_training + value-RMS block (ppo.py:172-183, the tail of play_steps, which the
+    reference cannot run without a simulator rollout in front of it: those seven lines are driven from here, every call in
+    them is the reference's own method) + PPO.train_epoch() on a synthetic rollout written into its storage_dict."""
+    import contextlib
+    import io
+    import tempfile
+
+    import torch
+
+    from oracle import mineral_oracle as oc
+    from oracle import reference_shim as rs
+
+    rs.install()
+    from mineral.agents.ppo.ppo import PPO as RefPPO
+
+    T, N, O, A = w["T"], w["N"], w["O"], w["A"]
+    torch.manual_seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        agent = RefPPO(reference_cfg(w), logdir=tempfile.mkdtemp(prefix="mineral_ref_"), env=rs.SynthEnv(N, O, A, 1))
+    st0, last = oc.synth_rollout(T, N, O, A, seed=0)
+    sd = agent.storage.storage_dict
+    times, t_begin = [], time.perf_counter()
+    for i in range(warmup + n_updates):
+        for k, v in st0.items():
+            if k == "obses":
+                sd["obses"]["obs"].copy_(v["obs"])
+            elif k != "returns":
+                sd[k].copy_(v)
+        t0 = time.perf_counter()
+        agent.storage.compute_return(last, agent.gamma, agent.tau)          # ppo.py:172
+        agent.storage.prepare_training()                                     # ppo.py:173
+        values, returns = agent.storage.data_dict["values"], agent.storage.data_dict["returns"]
+        if agent.normalize_value:                                            # ppo.py:175-183
+            agent.value_rms.update(values)
+            values = agent.value_rms.normalize(values)
+            agent.value_rms.update(returns)
+            returns = agent.value_rms.normalize(returns)
+        agent.storage.data_dict["values"], agent.storage.data_dict["returns"] = values, returns
+        agent.set_train()
+        agent.train_epoch()                                                  # ppo.py:248-350
+        agent.storage.data_dict = None                                       # ppo.py:199
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+            break
+    return times
+
+
 def shrink_for_cpu(w, target_s_per_update=4.0):
     """Bounded CPU sample: same workload structure, fewer envs if one full update would take too long."""
     probe = dict(w, N=max(64, w["N"] // 16))
@@ -140,6 +201,95 @@ def shrink_for_cpu(w, target_s_per_update=4.0):
         return dict(w), est_full
     n = max(64, int(w["N"] * target_s_per_update / est_full) // 64 * 64)
     return dict(w, N=n), est_full * n / w["N"]
+
+
+def multi_gpu_parity(agent, rank, world, dev):
+    """What the driver cannot otherwise see at N > 1 ('N ranks on env shards == 1 rank on the union'):
+    (1) after the timed loop every rank holds BIT-identical parameters; (2) a small env-sharded update (T 8 x 64 envs per rank,
+    obs 11, act 3, towers [32,16] LayerNorm+SiLU, learned sigma, 2 epochs x 4 minibatches, AdamW, KL schedule) run on `world`
+    ranks over the peer-memory kernels equals the same update run by rank 0 alone on the concatenated rollout whose
+    minibatch i is the union of the ranks' local minibatch i.  Same construction as tests/test_gpu_multirank.py."""
+    import torch
+    import torch.distributed as dist
+
+    from mineral_b200.agents import PPO
+    from oracle import mineral_oracle as oc
+    from oracle.reference_shim import SynthEnv, to_attr
+
+    flat = agent.optim.flat
+    every = torch.empty(world, flat.numel(), dtype=flat.dtype, device=dev)
+    dist.all_gather_into_tensor(every, flat.contiguous())
+    identical = bool(all(torch.equal(every[0], every[r]) for r in range(1, world)))
+
+    T, NL, O, A, NUM_MB, EPOCHS = 8, 64, 11, 3, 4, 2
+
+    def cfg(n_envs, mb, multi):
+        return to_attr(dict(
+            rl_device=dev, multi_gpu=multi, task=dict(env_autoresets=True),
+            agent=dict(network=dict(normalize_input=True, actor_critic="ActorCritic",
+                                    actor_critic_kwargs=dict(mlp_kwargs=dict(units=[32, 16], norm_type="LayerNorm", act_type="SiLU"), fixed_sigma=False,
+                                                             actor_dist_kwargs=dict(dist_type="dreamerv3_normal", minstd=0.1, maxstd=1.0))),
+                       ppo=dict(num_actors=n_envs, reward_shaper=dict(fn="scale", scale=1.0), max_agent_steps=1e9, horizon_len=T, minibatch_size=mb,
+                                normalize_value=True, value_bootstrap=True, clip_value_loss=True, normalize_advantage=True, gamma=0.99, tau=0.95,
+                                entropy_coef=0.001, e_clip=0.2, use_smooth_clamp=False, critic_coef=4, bounds_loss_coef=1e-4, bounds_type="bound",
+                                mini_epochs=EPOCHS, optim_type="AdamW", optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008,
+                                max_grad_norm=0.5, truncate_grads=True, cuda_graph=False))))
+
+    def take(st, last, envs):
+        return {k: ({"obs": v["obs"][:, envs]} if k == "obses" else v[:, envs]) for k, v in st.items()}, last[envs]
+
+    def load(a, st):
+        for k, v in st.items():
+            if k == "obses":
+                a.storage.storage_dict["obses"]["obs"].copy_(v["obs"])
+            elif k != "returns":
+                a.storage.storage_dict[k].copy_(v)
+
+    def run(a, last):
+        a.finish_rollout(last.to(dev))
+        a.set_train()
+        res = a.train_epoch()
+        torch.cuda.synchronize()
+        return dict(loss=torch.stack(res["loss/total"]).cpu(), gn=torch.stack(res["grad_norm/all"]).cpu(), kl=torch.stack(res["avg_kl"]).cpu(),
+                    params=a.optim.flat.cpu(), obs_mean=a.obs_rms["obs"].running_mean.cpu(), val_var=a.value_rms.running_var.cpu(), lr=a.last_lr)
+
+    st, last = oc.synth_rollout(T, NL * world, O, A, seed=3, done_p=0.05)
+    torch.manual_seed(1234)
+    shard = PPO(cfg(NL, NL * T // NUM_MB, True), env=SynthEnv(4, O, A, 1))
+    dist.broadcast(shard.optim.flat, 0)
+    init_flat = shard.optim.flat.clone()
+    st_r, last_r = take(st, last, torch.arange(rank * NL, (rank + 1) * NL))
+    load(shard, st_r)
+    got = run(shard, last_r)
+    err = shard.comm.error()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(got, comm_error=err))
+    out = {"ranks_bit_identical_after_timed_loop": identical, "world": world}
+    if rank == 0:
+        single = PPO(cfg(NL * world, world * NL * T // NUM_MB, False), env=SynthEnv(4, O, A, 1))
+        single.optim.flat.copy_(init_flat)
+        E = NL // NUM_MB
+        order = torch.cat([torch.arange(r * NL + i * E, r * NL + (i + 1) * E) for i in range(NUM_MB) for r in range(world)])
+        st_u, last_u = take(st, last, order)
+        load(single, st_u)
+        ref = run(single, last_u)
+
+        def rel(a, b):
+            return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+        worst = {k: max(rel(g[k], ref[k]) for g in gathered) for k in ("loss", "gn", "params", "obs_mean", "val_var")}
+        kl_abs = max(float((g["kl"] - ref["kl"]).abs().max()) for g in gathered)
+        ok = (worst["loss"] <= 2e-5 and worst["gn"] <= 2e-5 and worst["params"] <= 1e-4 and worst["obs_mean"] <= 1e-6 and worst["val_var"] <= 1e-6
+              and kl_abs <= 1e-5 * float(ref["kl"].abs().max()) + 2e-7 and all(g["lr"] == ref["lr"] for g in gathered)
+              and all(torch.equal(g["params"], gathered[0]["params"]) for g in gathered) and all(g["comm_error"] == 0 for g in gathered))
+        out["union_check"] = {"shape": f"{world} ranks x ({T} steps x {NL} envs), obs {O}, act {A}, [32,16] LayerNorm+SiLU, {EPOCHS} epochs x {NUM_MB} minibatches",
+                              "max_rel_diff_vs_single_rank_on_union": worst, "avg_kl_max_abs_diff": kl_abs,
+                              "lr_decisions_equal": all(g["lr"] == ref["lr"] for g in gathered),
+                              "shard_ranks_bit_identical": all(torch.equal(g["params"], gathered[0]["params"]) for g in gathered),
+                              "comm_errors": [g["comm_error"] for g in gathered], "pass": bool(ok)}
+        out["pass"] = bool(identical and ok)
+    shard.comm.close()
+    return out
 
 
 class ClockSampler(threading.Thread):
@@ -187,29 +337,43 @@ class ClockSampler(threading.Thread):
 
 
 def run_reference(args, w, rank, world):
-    """--impl reference: the reference's CPU implementation of the path (its algorithm restated over the same
-    torch ops, oracle/mineral_oracle.py) on this box's host cores, all threads."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores, all threads: the
+    UNMODIFIED reference package (oracle/_ref, staged by oracle/build_ref.py; kind "reference") when it is there, else the
+    oracle port of its algorithm over the same torch ops (oracle/mineral_oracle.py; kind "port")."""
     if rank != 0:
         return
     import torch
+
+    from oracle import reference_shim as rs
 
     # all the host threads this process may use - also under torchrun, which exports OMP_NUM_THREADS=1 to every rank
     torch.set_num_threads(len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     ws, est = shrink_for_cpu(w)
-    times = time_oracle(ws, args.steps, args.warmup, budget_s=240)
+    kind = "port"
+    if rs.reference_available():
+        try:
+            times = time_reference(ws, args.steps, args.warmup, budget_s=240)
+            kind = "reference"
+        except Exception as e:  # an import problem on the box must not take the arm down: fall back to the port and say so
+            print(f"reference arm: real reference unavailable ({e!r}); timing the oracle port", file=sys.stderr)
+    if kind == "port":
+        times = time_oracle(ws, args.steps, args.warmup, budget_s=240)
     per = statistics.mean(times)
     samples = ws["T"] * ws["N"]
     value = samples / per
+    what = ("the unmodified reference's PPO agent (mineral.agents.ppo.PPO from oracle/_ref)" if kind == "reference"
+            else "the oracle port of the reference's algorithm")
     sample = (f"{len(times)} timed full updates of {ws['N']} envs x {ws['T']} steps ({samples} samples, {ws['mini_epochs']} epochs x "
-              f"{ws['minibatches']} minibatches) on {cores} host threads" + ("" if ws["N"] == w["N"] else f"; envs reduced from {w['N']} to bound CPU time"))
+              f"{ws['minibatches']} minibatches) by {what} on {cores} host threads"
+              + ("" if ws["N"] == w["N"] else f"; envs reduced from {w['N']} to bound CPU time"))
     print(json.dumps({
         "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "envs_per_gpu": w["N"], "horizon": w["T"], "obs": w["O"], "act": w["A"], "mlp": w["units"],
                    "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "device": "cpu"},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), file=_RESULT_OUT, flush=True)
@@ -227,9 +391,8 @@ def main():
     ap.add_argument("--workload", default="ppo_ant_4096x32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying one CUDA graph per update")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--nccl", action="store_true", help="N > 1: exchange gradients / statistics with torch.distributed (NCCL) calls instead of "
-                                                        "the fused peer-memory kernels (comparison only)")
     ap.add_argument("--no-kernel-sweep", action="store_true", help="skip timing the fused post-rollout kernel over rollout sizes")
+    ap.add_argument("--no-recipes", action="store_true", help="skip the second entry (the reference's shipped yaml recipe)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on the first
     # communicator): keep the real stdout aside for the result line and point fd 1 at stderr for everything else.
@@ -263,7 +426,7 @@ def main():
     T, N, O, A = w["T"], w["N"], w["O"], w["A"]
     B = T * N
     torch.manual_seed(0)
-    agent = PPO(make_cfg(w, dev, world > 1, cuda_graph=not args.no_graph, peer=not args.nccl), env=SynthEnv(4, O, A, 1))
+    agent = PPO(make_cfg(w, dev, world > 1, cuda_graph=not args.no_graph), env=SynthEnv(4, O, A, 1))
     agent.set_train()
     if world > 1:  # identical initial weights on every rank
         dist.broadcast(agent.optim.flat, 0)
@@ -397,12 +560,56 @@ def main():
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / (e_ms.item() / 1e3)
 
+    # ---- N > 1: numerical self-check of the multi-GPU path (untimed) ----
+    mgp = None
+    if world > 1:
+        try:
+            mgp = multi_gpu_parity(agent, rank, world, dev)
+        except Exception as e:   # reported, never silently dropped
+            mgp = {"pass": False, "error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant hand-written kernel: the fused post-rollout pass (HBM-bound) ----
+    # ---- the reference's SHIPPED Ant recipe as a second entry (mineral/cfgs/agent/DFlexAntPPO.yaml:17-21,33-66: towers
+    #      [512,256,128] LayerNorm+SiLU, learned sigma, 64 minibatches of 2048 rows x 5 epochs = 320 optimizer steps) ----
+    recipes = None
+    if world == 1 and not args.no_recipes and args.workload == "ppo_ant_4096x32":
+        recipes = []
+        for name in ("ppo_ant_4096x32_yaml",):
+            try:
+                wr = WORKLOADS[name]
+                ar = PPO(make_cfg(wr, dev, False, cuda_graph=not args.no_graph), env=SynthEnv(4, wr["O"], wr["A"], 1))
+                ar.set_train()
+                str_, lastr = oc.synth_rollout(wr["T"], wr["N"], wr["O"], wr["A"], seed=0)
+                for k, v in str_.items():
+                    if k == "obses":
+                        ar.storage.storage_dict["obses"]["obs"].copy_(v["obs"])
+                    elif k != "returns":
+                        ar.storage.storage_dict[k].copy_(v)
+                lastr = lastr.to(dev)
+                for _ in range(3):
+                    ar.finish_rollout(lastr); ar.train_epoch()
+                torch.cuda.synchronize()
+                tsr = []
+                for _ in range(5):
+                    flush.zero_()
+                    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ea.record(); ar.finish_rollout(lastr); ar.train_epoch(); eb.record(); torch.cuda.synchronize()
+                    tsr.append(ea.elapsed_time(eb))
+                msr = statistics.mean(tsr)
+                steps_r = wr["mini_epochs"] * wr["minibatches"]
+                recipes.append({"workload": name, "value": wr["T"] * wr["N"] / (msr * 1e-3), "unit": "samples/s", "ms_per_update": msr,
+                                "optimizer_steps_per_update": steps_r, "us_per_optimizer_step": msr * 1e3 / steps_r,
+                                "minibatch_rows": wr["T"] * wr["N"] // wr["minibatches"], "mlp": wr["units"], "variant": wr["variant"],
+                                "timing": "5 timed updates after 3 warm-ups, CUDA events, L2 read-flushed between updates"})
+                del ar
+            except Exception as e:
+                recipes.append({"workload": name, "unavailable": repr(e)[:200]})
+
+    # ---- roofline of the dominant HBM-bound kernel: the fused post-rollout pass ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -477,30 +684,85 @@ def main():
     except Exception:
         pass
 
-    # ---- tensor-bound leg: the tcgen05 3xTF32 linear kernel on the widest hidden layer (forward) ----
+    # ---- roofline of the DOMINANT kernel: the tcgen05 3xTF32 linear kernel (tc_linear_kernel<FWD|DX|DW>), all the tower
+    #      GEMMs of one optimizer step (both towers per launch): L forward + L weight-gradient + (L - 1) input-gradient ----
     roofline_tensor = None
     tw = getattr(agent._engine, "towers", None)
-    if tw is not None and tw.use_tc and tw.L >= 2:
+    if tw is not None and tw.use_tc:
         from mineral_b200 import ops
-        n, k = tw.la[1].weight.shape
-        out = tw.Z[1] if tw.normed else tw.Y[1]
-        groups = [dict(a=tw.Y[0][t], b=tw.w_hi[1][t], b_lo=tw.w_lo[1][t], c=out[t], bias=l.bias.data, N=n, K=k, lda=k, ldb=tw.w_ld[1])
-                  for t, l in enumerate((tw.la[1], tw.lv[1]))]
-        ts = []
-        for _ in range(20):
-            flush.zero_()
-            torch.cuda._sleep(400_000)
-            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ea.record(); ops.tc_linear_fwd(groups, tw.M, tw.gemm_act); eb.record(); torch.cuda.synchronize()
-            ts.append(ea.elapsed_time(eb))
-        t_ms = statistics.mean(sorted(ts)[:15])
-        flops = 2 * 2.0 * tw.M * n * k
+        eng = agent._engine
+        x_buf = getattr(eng, f"_n_{eng.norm_keys[0]}")["x"] if eng.norm_keys else eng._raw_x
+        x_ld = x_buf.shape[1]
+        widths, in_dim, M, L = tw.widths, tw.in_dim, tw.M, tw.L
+        ks = [in_dim] + widths[:-1]
+        f_fwd = sum(2.0 * 2 * M * k * n for k, n in zip(ks, widths))          # 2 towers
+        f_dx = sum(2.0 * 2 * M * k * n for k, n in zip(ks[1:], widths[1:]))
+        flops = 2 * f_fwd + f_dx                                               # forward + dW + dX
+        n_launch = 2 * L + (L - 1)
+        # the split-partials reduce (tc_reduce_kernel) is not a tensor-core kernel: it is taken out of the timed sequence; behind a
+        # LayerNorm the LN passes (mnr_ln_act_fwd / _bwd) sit between the GEMMs and are timed separately and subtracted
+        real_reduce = ops.tc_reduce_partials
+        tw.forward_towers(x_buf, x_ld, split=True)
+
+        def gemm_set(with_ln=True):
+            tw.forward_towers(x_buf, x_ld, split=False)
+            tw.backward_towers(x_buf)
+
+        def timed(fn, n_iter=12):
+            ts = []
+            for _ in range(n_iter):
+                flush.zero_()
+                torch.cuda._sleep(2_000_000)   # ~1 ms of GPU-side spin: the CPU enqueues the whole set behind it
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ea.record(); fn(); eb.record(); torch.cuda.synchronize()
+                ts.append(ea.elapsed_time(eb))
+            return statistics.mean(sorted(ts)[: max(1, len(ts) * 3 // 4)])
+
+        ops.tc_reduce_partials = lambda pending: None
+        try:
+            t_ms = timed(gemm_set)
+            t_ln = 0.0
+            if tw.normed:   # the LayerNorm + activation passes alone, same order
+                st = tw.stack
+
+                def ln_only():
+                    G = st.G
+                    for i in range(L):
+                        ops.ln_act_fwd([dict(z=st.Z[i][g], y=st.Y[i][g], gamma=st.norm[g][i].weight.data, beta=st.norm[g][i].bias.data,
+                                             mean=st.mean[i][g], rstd=st.rstd[i][g]) for g in range(G)], M, widths[i], st.norm[0][i].eps, st.act)
+                    for i in range(L - 1, -1, -1):
+                        ops.ln_act_bwd([dict(z=st.Z[i][g], gamma=st.norm[g][i].weight.data, beta=st.norm[g][i].bias.data, mean=st.mean[i][g],
+                                             rstd=st.rstd[i][g], dy=st.dY[i][g], dz=st.dY[i][g], dgamma=st.norm[g][i].weight.grad,
+                                             dbeta=st.norm[g][i].bias.grad) for g in range(G)], M, widths[i], st.act, st.ln_ws[i])
+                t_ln = timed(ln_only)
+        finally:
+            ops.tc_reduce_partials = real_reduce
+        agent.optim.zero_grad()
+        t_gemm = max(t_ms - t_ln, 1e-6)
         tpeak = peaks.get("bf16_tflops", 1590.0)
-        roofline_tensor = {"kernel": f"tc_linear_kernel<FWD> 2 x ({tw.M}x{n}x{k}) tcgen05 kind::tf32, 3 MMAs per product (3xTF32)",
-                           "bound": "tensor", "achieved": flops / (t_ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
-                           "frac": flops / (t_ms * 1e-3) / 1e12 / tpeak, "launch_ms": t_ms,
-                           "note": "achieved counts fp32-equivalent FLOPs (2MNK); the tensor pipe executes 3x that in tf32, whose dense "
-                                   "peak is half the bf16 figure used as `peak`"}
+        tpeak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback (B200_PROFILING.md)"
+        roofline_tensor = {
+            "kernel": f"tc_linear_kernel<FWD|DX|DW> (tcgen05 kind::tf32, TMEM accumulators, TMA operands): the {n_launch} tower GEMM launches of one "
+                      f"optimizer step, 2 towers x ({M} rows, {in_dim}->" + "->".join(str(x) for x in widths) + ")",
+            "bound": "tensor", "achieved": flops / (t_gemm * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+            "frac": flops / (t_gemm * 1e-3) / 1e12 / tpeak, "traffic": None, "peak_source": tpeak_src,
+            "algorithmic_flops": flops, "launches": n_launch, "set_ms": t_gemm, "launch_ms": t_gemm / n_launch,
+            "timing": "CUDA events on the launching stream around the whole forward + backward GEMM sequence of one optimizer step (the split-"
+                      "partials reduce taken out" + ("; the LayerNorm passes timed alone in the same order and subtracted" if tw.normed else "") +
+                      "), L2 read-flushed before every repetition; mean of the fastest 9 of 12",
+            "note": "achieved counts fp32-EQUIVALENT FLOPs (2MNK per GEMM with the real K); the tensor pipe executes 3x that in tf32 (3xTF32 "
+                    "split: the 1e-5 parity bar rules out single-pass tf32 / bf16), and tf32 runs at half the bf16 rate used as `peak`, so a "
+                    "perfect 3xTF32 kernel reads frac = 1/6 = 0.167",
+            "frac_of_3xtf32_ceiling": flops / (t_gemm * 1e-3) / 1e12 / (tpeak / 6.0)}
+
+    # ---- share of the update each kernel takes, from the committed ncu launch list of this command (profiles/) ----
+    shares = None
+    try:
+        sh = json.load(open(os.path.join(ROOT, "profiles", "r02_shares.json")))
+        if sh.get("workload") == args.workload:
+            shares = sh
+    except Exception:
+        pass
 
     sweep = None
     if not args.no_kernel_sweep:
@@ -553,8 +815,7 @@ def main():
         "config": {"workload": args.workload, "envs_per_gpu": N, "horizon": T, "obs": O, "act": A, "mlp": w["units"], "variant": w["variant"],
                    "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "minibatch_rows": B // w["minibatches"],
                    "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": agent._engine.graph is not None,
-                   "exchange": ("none (1 GPU)" if world == 1 else "fused peer-memory all-reduce + clip + Adam kernel over NVLink (csrc/peer.cu)"
-                                if agent.comm is not None else "torch.distributed NCCL all-reduce"),
+                   "exchange": "none (1 GPU)" if world == 1 else "fused peer-memory all-reduce + clip + Adam kernel over NVLink (csrc/peer.cu)",
                    "l2": "256 MiB read-flush between timed steps", "parallelism": f"env-sharded dp{world}"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "pipeline": "every step uploads its own rollout from pinned host memory (ExperienceBuffer.stage_from_host -> commit_staged) and "
@@ -562,14 +823,21 @@ def main():
                             "the host collects step i's metrics one step later, so it never blocks on the GPU"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": roofline,
-        "roofline_tensor": roofline_tensor,
+        # `roofline` = the dominant kernel of the step by time (the tcgen05 tower GEMMs, ~70 % of an update: see `shares`);
+        # `roofline_hbm` = the dominant HBM-bound kernel (the fused post-rollout pass that BASELINE.json's second metric names)
+        "roofline": roofline_tensor if roofline_tensor is not None else roofline,
+        "roofline_hbm": roofline,
+        "shares": shares,
         "cpu_baseline": cpu,
         "torch_ops_on_gpu": torch_gpu,
         "gae_normalise_hbm_gbs": achieved,
     }
     if sweep:
         line["post_rollout_sweep"] = sweep
+    if recipes:
+        line["recipes"] = recipes
+    if mgp is not None:
+        line["multi_gpu_parity"] = mgp
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

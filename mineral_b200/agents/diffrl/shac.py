@@ -280,8 +280,11 @@ class SHAC(Agent):
             self.episode_lengths += 1
             self.episode_discounted_rewards += self.episode_gamma * raw_rew
             self.episode_gamma *= self.gamma
-            obs = self.rollout_observe(obs)
-            nv_min, nv_avg = self._bootstrap_values(obs)
+            prev_obs, obs = obs, self.rollout_observe(obs)
+            # shac.py:702-709: with the (default) shared encoder the reference bootstraps from `z`, the encoding it computed
+            # BEFORE env.step - i.e. from the pre-step observation - and only a separate target encoder sees the new one.
+            # Parity copies that quirk (SURVEY.md Appendix B style).
+            nv_min, nv_avg = self._bootstrap_values(prev_obs if self.share_encoder else obs)
             done_ids = done.nonzero(as_tuple=False).squeeze(-1)
             if len(done_ids) > 0:
                 terminal = self._convert_obs(info['obs_before_reset'])

@@ -1,8 +1,8 @@
 """MLP tower container.  Mirrors mineral/nets/mlp.py:25-77 closely enough that `state_dict()` keys
 (`mlp.<i>.weight` ...) and layer order (Linear -> [Dropout] -> [Norm] -> [Act]) are identical, so
-reference checkpoints load.  It is the parameter container and the rollout-time (`act`) forward; the
-GEMMs run in cuBLAS through torch (library), the hot update path feeds its outputs to the fused loss
-kernel."""
+reference checkpoints load.  It is a PARAMETER CONTAINER (initialisation, checkpoint keys): the agents run
+these layers on the hand-written kernels (nets/fused_towers.py); `forward` is the plain torch composition,
+kept for inspection and for the tests' autograd comparisons."""
 
 import torch.nn as nn
 

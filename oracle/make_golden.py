@@ -573,7 +573,149 @@ def gen_offpolicy_small():
     save("offpolicy_small", out)
 
 
+# ---- f4: a checkpoint WRITTEN BY THE REFERENCE (ppo.py:416-427) and what the reference does after it -------------------
+def gen_ppo_ckpt():
+    """Reference PPO: rollout + update #1 -> agent.save() -> rollout + update #2.  The fixture holds the checkpoint file's
+    content, rollout #2's storage and update #2's results: loading the checkpoint into another implementation and feeding
+    it rollout #2 must reproduce update #2 (model, Adam moments / step / lr, obs and value statistics all matter)."""
+    cases = []
+    for variant in ("elu_normal_fixed", "ln_silu_dreamer_learned"):
+        N, T, O, A, mb, units, epochs = 16, 8, 11, 3, 32, [32, 16], 2
+        torch.manual_seed(70)
+        env = rs.SynthEnv(N, O, A, 2 * T + 2, seed=71, done_p=0.08, timeout_p=0.05)
+        cfg = ppo_cfg(N, T, mb, units, variant, epochs)
+        with open(os.devnull, "w") as devnull:
+            stdout, sys.stdout = sys.stdout, devnull
+            try:
+                agent = PPO(cfg, logdir=tempfile.mkdtemp(), env=env)
+            finally:
+                sys.stdout = stdout
+        agent.obs = agent._convert_obs(env.reset())
+        agent.dones = torch.zeros(N, dtype=torch.bool)
+        agent.epoch, agent.mini_epoch, agent.agent_steps = 0, -1, 0
+        agent.set_eval(); agent.play_steps(); agent.agent_steps += agent.batch_size
+        agent.set_train(); agent.train_epoch(); agent.storage.data_dict = None
+        agent.epoch = 1
+        f = os.path.join(tempfile.mkdtemp(), "ref.pth")
+        agent.save(f)
+        ckpt = torch.load(f, weights_only=False)
+        rec = {}
+        orig = agent.storage.compute_return
+
+        def spy(last_values, gamma, tau):
+            rec["last_values"] = last_values.clone()
+            rec["storage"] = clone_tree({k: v for k, v in agent.storage.storage_dict.items() if k != "returns"})
+            return orig(last_values, gamma, tau)
+
+        agent.storage.compute_return = spy
+        agent.set_eval(); agent.play_steps()
+        agent.set_train()
+        res = agent.train_epoch()
+        cases.append(dict(variant=variant, shape=(T, N, O, A), cfg=rs.to_plain(cfg), ckpt=clone_tree(ckpt), **rec,
+                          results={k: torch.stack(v) for k, v in res.items() if v[0].dim() == 0},
+                          final_state_dict=clone_tree(agent.model.state_dict()), last_lr=agent.last_lr,
+                          optim_after=clone_tree(agent.optim.state_dict()), obs_rms_after=clone_tree(agent.obs_rms.state_dict()),
+                          value_rms_after=clone_tree(agent.value_rms.state_dict())))
+    save("ppo_ckpt", cases)
+
+
+# ---- a17 + rollout bookkeeping: the REAL SHAC.compute_actor_loss on a synthetic differentiable env -----------------------
+class SynthDiffEnv:
+    """Differentiable toy simulator with the interface shac.py:38-43,345,645,688,714 consumes: linear dynamics in torch,
+    pre-drawn early terminations, time-outs at `max_episode_length`, `info['obs_before_reset']`, one NaN terminal observation."""
+
+    def __init__(self, N, O, A, max_episode_length, seed, T):
+        g = torch.Generator().manual_seed(seed)
+        self.num_envs, self.num_obs, self.num_actions, self.max_episode_length = N, O, A, max_episode_length
+        self.observation_space, self.action_space = rs._Space((O,)), rs._Space((A,))
+        self.scale = torch.empty(O).uniform_(0.1, 4.0, generator=g)
+        self.shift = torch.empty(O).uniform_(-2.0, 2.0, generator=g)
+        self.M = 0.3 * torch.randn(A, O, generator=g)
+        self.fresh = torch.randn(T + 2, N, O, generator=g) * self.scale + self.shift
+        self.noise = 0.05 * torch.randn(T + 2, N, O, generator=g)
+        self.term = torch.rand(T + 2, N, generator=g) < 0.12
+        self.state = self.fresh[0].clone()
+        self.progress = torch.zeros(N, dtype=torch.long)
+        self.t = 0
+        self.log = []
+
+    def clear_grad(self):
+        self.state = self.state.detach()
+
+    def reset(self):
+        return self.state.clone()
+
+    def initialize_trajectory(self):
+        self.state = self.state.detach()
+        return self.state.clone()
+
+    def step(self, actions):
+        self.t += 1
+        t = self.t
+        self.state = 0.9 * self.state + actions @ self.M + self.noise[t]
+        rew = -0.01 * (self.state ** 2).mean(1) + 0.1 * actions.sum(1)
+        self.progress += 1
+        done = self.term[t] | (self.progress >= self.max_episode_length)
+        before = self.state.detach().clone()
+        if t == 3 and done.any():   # a non-finite terminal observation (shac.py:720-731)
+            before[done.nonzero()[0, 0], 0] = float("nan")
+        self.state = torch.where(done[:, None], self.fresh[t], self.state)
+        self.progress[done] = 0
+        obs = self.state.clone()
+        self.log.append(dict(actions=actions.detach().clone(), obs=obs.detach().clone(), rew=rew.detach().clone(), done=done.clone(),
+                             obs_before_reset=before.clone()))
+        return obs, rew, done, {"obs_before_reset": before}
+
+
+def gen_shac_rollout():
+    cases = []
+    for variant in ("legacy_tanh_clamp", "f64_ensemble"):
+        N, T, O, A, max_len = 12, 8, 7, 3, 5
+        legacy = variant == "legacy_tanh_clamp"
+        mlp = dict(units=[16, 8], norm_type="LayerNorm", act_type="ELU")
+        critic = dict(critic="Critic", critic_kwargs=dict(mlp_kwargs=mlp)) if legacy else \
+            dict(critic="EnsembleCritic", critic_kwargs=dict(n_critics=2, mlp_kwargs=mlp))
+        cfg = rs.to_attr(dict(
+            rl_device="cpu", multi_gpu=False, env_render=False, run="train", seed=0, task=dict(env_autoresets=True),
+            agent=dict(tracker_len=100, metrics_kwargs={}, print_every=-1, ckpt_every=-1,
+                       network=dict(normalize_input=True, encoder=None, tanh_clamp=legacy, actor="Actor",
+                                    actor_kwargs=dict(mlp_kwargs=dict(units=[16, 8], norm_type="LayerNorm", act_type="ELU")), **critic),
+                       shac=dict(multi_gpu=False, num_actors=N, reward_shaper=dict(fn="scale", scale=0.5), max_epochs=10, max_agent_steps=1e6,
+                                 horizon_len=T, num_critic_batches=4, gamma=0.99, critic_method="td-lambda", **{"lambda": 0.95},
+                                 critic_iterations=2, normalize_ret=False, optim_type="Adam", actor_optim_kwargs=dict(lr=2e-3, betas=[0.7, 0.95]),
+                                 critic_optim_kwargs=dict(lr=2e-3, betas=[0.7, 0.95]), lr_schedule="linear", target_critic_alpha=0.2,
+                                 no_target_critic=False, max_grad_norm=1.0, truncate_grads=True, with_logprobs=not legacy))))
+        torch.manual_seed(90)
+        env = SynthDiffEnv(N, O, A, max_len, seed=91, T=2 * T)
+        with open(os.devnull, "w") as devnull:
+            stdout, sys.stdout = sys.stdout, devnull
+            try:
+                agent = SHAC(cfg, logdir=tempfile.mkdtemp(), env=env)
+                rollouts = []
+                for _ in range(2):   # two consecutive rollouts: the second starts from non-trivial statistics
+                    env.log = []
+                    rms_before = clone_tree(agent.obs_rms.state_dict())
+                    first_obs = env.state.detach().clone()
+                    agent.compute_actor_loss()
+                    rollouts.append(dict(
+                        first_obs=first_obs, log=env.log, obs_rms_before=rms_before, obs_rms_after=clone_tree(agent.obs_rms.state_dict()),
+                        obs_buf=clone_tree(agent.obs_buf), action_buf=agent.action_buf.detach().clone(), rew_buf=agent.rew_buf.clone(),
+                        done_mask=agent.done_mask.clone(), next_values=agent.next_values.detach().clone(),
+                        avg_next_values=agent.avg_next_values.detach().clone(), episode_lengths=agent.episode_lengths.clone(),
+                        episode_rewards=agent.episode_rewards.clone(), num_episodes=int(agent.num_episodes), agent_steps=agent.agent_steps))
+            finally:
+                sys.stdout = stdout
+        cases.append(dict(variant=variant, shape=(T, N, O, A), max_episode_length=max_len, cfg=rs.to_plain(cfg),
+                          critic_target=clone_tree(agent.critic_target.state_dict()), critic=clone_tree(agent.critic.state_dict()),
+                          actor=clone_tree(agent.actor.state_dict()), rollouts=rollouts))
+    save("shac_rollout", cases)
+
+
 if __name__ == "__main__":
+    gen_shac_rollout() if "shac_rollout" in sys.argv[1:] else None
+    gen_ppo_ckpt() if "ppo_ckpt" in sys.argv[1:] else None
+    if len(sys.argv) > 1:
+        sys.exit(0)
     gen_experience()
     gen_rms()
     gen_tdlambda()
@@ -587,3 +729,5 @@ if __name__ == "__main__":
     gen_offpolicy_e2e()
     gen_sac_policy()
     gen_offpolicy_small()
+    gen_shac_rollout()
+    gen_ppo_ckpt()

@@ -215,14 +215,14 @@ def shac_critic_loss(params, prefixes, obs, target, n_hidden, norm, act):
 
 
 def shac_update_critic(params, prefixes, optim, obs_flat, target_flat, batch_size, iterations, n_hidden, norm, act,
-                       truncate_grads=True, max_grad_norm=1.0):
+                       truncate_grads=True, max_grad_norm=1.0, drop_last=False):
     """update_critic (shac.py:824-867) over the time-major flattened dataset (CriticDataset, no shuffle, keep the
     short last batch).  params: dict name -> leaf tensor (requires_grad) that `optim` steps.  Returns the results dict."""
     results = {"value_loss": [], "grad_norm_before_clip/critic": [], "grad_norm_after_clip/critic": []}
     leaves = list(params.values())
     for _ in range(iterations):
         total, before, after = 0.0, [], []
-        slices = critic_dataset_slices(target_flat.shape[0], batch_size, drop_last=False)
+        slices = critic_dataset_slices(target_flat.shape[0], batch_size, drop_last=drop_last)   # B = len(dataset), shac.py:832-835
         for s, e in slices:
             optim.zero_grad()
             loss = shac_critic_loss(params, prefixes, obs_flat[s:e], target_flat[s:e], n_hidden, norm, act)
@@ -636,6 +636,8 @@ def ppo_update(storage, last_values, params, optim, obs_rms, value_rms, hp, net,
         results["avg_kl"].append(avg_kl)
         if hp["lr_schedule"] == "kl":
             lr = kl_lr_update(lr, avg_kl.item(), hp["kl_threshold"], hp.get("min_lr", 1e-6), hp.get("max_lr", 1e-2))
+        elif hp["lr_schedule"] == "cos":   # ppo.py:339-342, ppo/utils.py:35-37
+            lr = hp["init_lr"] * 0.5 * (1.0 + math.cos(math.pi * (hp["agent_steps"] + _ep / hp["mini_epochs"]) / hp["max_agent_steps"]))
         for g in optim.param_groups:
             g["lr"] = lr
         results["lr"].append(lr)

@@ -13,7 +13,17 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MINERAL_REFERENCE_ROOT", "/root/reference")
+def _find_reference():
+    """$MINERAL_REFERENCE_ROOT, else /root/reference (build container), else the staged copy oracle/_ref (GPU box;
+    made by oracle/build_ref.py, git-ignored)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    for root in (os.environ.get("MINERAL_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "_ref")):
+        if root and os.path.isdir(os.path.join(root, "mineral")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():

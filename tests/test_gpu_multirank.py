@@ -1,4 +1,4 @@
-"""2-GPU equivalence (NCCL): an env-sharded 2-rank PPO update equals the 1-rank update on the
+"""2-GPU equivalence: an env-sharded 2-rank PPO update equals the 1-rank update on the
 concatenated rollout whose minibatch i is the union of the ranks' local minibatch i (SURVEY.md
 section 8e).  Needs >= 2 visible GPUs (`gpurun --gpus 2`); skipped otherwise."""
 
@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 T, NL, O, A, NUM_MB, EPOCHS = 8, 64, 11, 3, 4, 2   # NL envs per rank
 
 
-def _cfg(n_envs, mb, device, multi_gpu, peer=True, graph=False):
+def _cfg(n_envs, mb, device, multi_gpu, graph=False):
     from oracle.reference_shim import to_attr
 
     return to_attr(dict(
@@ -28,7 +28,7 @@ def _cfg(n_envs, mb, device, multi_gpu, peer=True, graph=False):
                             normalize_value=True, value_bootstrap=True, clip_value_loss=True, normalize_advantage=True, gamma=0.99, tau=0.95,
                             entropy_coef=0.001, e_clip=0.2, use_smooth_clamp=False, critic_coef=4, bounds_loss_coef=1e-4, bounds_type="bound",
                             mini_epochs=EPOCHS, optim_type="AdamW", optim_kwargs=dict(lr=5e-4, eps=1e-5), lr_schedule="kl", kl_threshold=0.008,
-                            max_grad_norm=0.5, truncate_grads=True, peer_allreduce=peer, cuda_graph=graph))))
+                            max_grad_norm=0.5, truncate_grads=True, cuda_graph=graph))))
 
 
 def _load(agent, st):
@@ -76,7 +76,7 @@ def _restore(agent, snap):
     sd["mu"].copy_(snap["mu"]), sd["sigma"].copy_(snap["sigma"])
 
 
-def _worker(rank, world, port, init_sd, ret, peer, graph):
+def _worker(rank, world, port, init_sd, ret, graph):
     from mineral_b200.agents import PPO
     from oracle import mineral_oracle as oc
     from oracle.reference_shim import SynthEnv
@@ -88,23 +88,22 @@ def _worker(rank, world, port, init_sd, ret, peer, graph):
         st, last = oc.synth_rollout(T, NL * world, O, A, seed=3, done_p=0.05)
         envs = torch.arange(rank * NL, (rank + 1) * NL)
         st_r, last_r = _take(st, last, envs)
-        agent = PPO(_cfg(NL, NL * T // NUM_MB, f"cuda:{rank}", True, peer, graph), env=SynthEnv(4, O, A, 1))
-        assert (agent.comm is not None) == peer
+        agent = PPO(_cfg(NL, NL * T // NUM_MB, f"cuda:{rank}", True, graph), env=SynthEnv(4, O, A, 1))
+        assert agent.comm is not None
         agent.model.load_state_dict(init_sd)
         _load(agent, st_r)
         ret[rank] = _run(agent, last_r, repeats=3 if graph else 1)
-        if peer:
-            assert agent.comm.error() == 0
-            assert agent._engine.graph is not None or not graph
+        assert agent.comm.error() == 0
+        assert agent._engine.graph is not None or not graph
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("peer,graph", [(True, False), (True, True), (False, False)])
-def test_two_rank_update_equals_single_rank_on_union(peer, graph):
-    """peer=True: gradient/metrics/statistics exchanged by our own kernels over NVLink peer memory (csrc/peer.cu), optionally
-    with the whole update replayed as one CUDA graph; peer=False: the torch.distributed (NCCL) path."""
+@pytest.mark.parametrize("graph", [False, True])
+def test_two_rank_update_equals_single_rank_on_union(graph):
+    """Gradient / metrics / statistics exchanged by our own kernels over NVLink peer memory (csrc/peer.cu), optionally with
+    the whole update replayed as one CUDA graph."""
     from mineral_b200.agents import PPO
     from oracle import mineral_oracle as oc
     from oracle.reference_shim import SynthEnv
@@ -124,7 +123,7 @@ def test_two_rank_update_equals_single_rank_on_union(peer, graph):
 
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(world, 29571 + 2 * int(peer) + int(graph), init_sd, ret, peer, graph), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, 29571 + int(graph), init_sd, ret, graph), nprocs=world, join=True)
     for r in range(world):
         got = ret[r]
         scale_close(got["loss"], ref["loss"], 2e-5, f"rank{r} losses")

@@ -580,21 +580,21 @@ def test_ppo_update_matches_reference_agent(cuda_graph):
             scale_close(data["sigma"], c["data_after_train"]["sigma"], 1e-4, "sigma write-back")
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_play_steps_matches_reference_rollout(fused):
+def test_play_steps_matches_reference_rollout():
     """PPO.play_steps on our kernels (obs normalise -> tower GEMMs -> mnr_policy_step -> env.step ->
     mnr_post_step, then the fused post-rollout pass) against the REAL reference agent's rollout recorded in the ppo_e2e
     golden: same synthetic env streams, the reference's own sampling noise (recovered from its stored actions / mu /
-    sigma) injected step by step.  fused=False runs the reference's torch op sequence on the same inputs."""
+    sigma) injected step by step."""
     from mineral_b200.agents import PPO
     from mineral_b200.agents.ppo.ppo import _RolloutEngine
     from oracle.reference_shim import SynthEnv, to_attr
+
+    fused = True
 
     for c in load_golden("ppo_e2e"):
         T, N, O, A = c["shape"]
         cfg = to_attr(c["cfg"])
         cfg.rl_device = DEV
-        cfg.agent.ppo["fused_rollout"] = fused
         cpu_env = SynthEnv(N, O, A, T, seed=41, done_p=0.08, timeout_p=0.05)  # oracle/make_golden.py:gen_ppo_e2e
 
         class OnDevice:  # the agents expect the simulator to hand out device tensors (mineral/agents/agent.py:144-156)
@@ -614,23 +614,9 @@ def test_play_steps_matches_reference_rollout(fused):
         agent.obs_rms.load_state_dict(c["obs_rms_before"])
         ref = c["storage"]
         eps = (ref["actions"] - ref["mu"]) / ref["sigma"]
-        if fused:
-            assert _RolloutEngine.supported(agent)
-            agent._rollout = _RolloutEngine(agent)
-            agent._rollout.eps_source = lambda t: cu(eps[t])
-        else:  # torch path: make Normal.sample() return the reference's actions
-            step = {"t": 0}
-            orig_act = agent.model.act
-
-            def act(obs_dict, sample=True, **kw):
-                out = orig_act(obs_dict, sample=sample, **kw)
-                if sample and step["t"] < T:
-                    out["actions"] = out["mu"] + out["sigma"] * cu(eps[step["t"]])
-                    out["neglogp"] = -out["distr"].log_prob(out["actions"]).sum(1)
-                    step["t"] += 1
-                return out
-
-            agent.model.act = act
+        assert _RolloutEngine.supported(agent)
+        agent._rollout = _RolloutEngine(agent)
+        agent._rollout.eps_source = lambda t: cu(eps[t])
         seen = {}
         orig_finish = agent.finish_rollout
 
@@ -905,8 +891,7 @@ def test_staged_host_upload_round_trip():
     assert ptrs == {k: (v["obs"] if k == "obses" else v).data_ptr() for k, v in buf.storage_dict.items()}
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_ppo_eval_runs_and_accounts_episodes(fused):
+def test_ppo_eval_runs_and_accounts_episodes():
     """PPO.eval (ppo.py:352-408): rolls the sampling policy until 2 x num_actors episodes finished; the device-side episode
     accounting must agree with a host recount of the same done / reward streams."""
     import json
@@ -919,7 +904,6 @@ def test_ppo_eval_runs_and_accounts_episodes(fused):
     T, N, O, A = c["shape"]
     cfg = to_attr(c["cfg"])
     cfg.rl_device = DEV
-    cfg.agent.ppo["fused_rollout"] = fused
     cpu_env = SynthEnv(N, O, A, 400, seed=7, done_p=0.1, timeout_p=0.0)
     log = []
 

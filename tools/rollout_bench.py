@@ -42,11 +42,38 @@ class DeviceEnv:
         return self.obs[t], self.rew[t], self.done[t], {"time_outs": self.tout[t]}
 
 
+def torch_play_steps(agent):
+    """The reference's op sequence (mineral/agents/ppo/ppo.py:133-183) on the agent's torch modules: the comparison arm of
+    this tool only - the product has no such path."""
+    a = agent
+    for n in range(a.horizon_len):
+        obs_n = {k: a.obs_rms[k].normalize(v) for k, v in a.obs.items()} if a.normalize_input else a.obs
+        model_out = a.model.act(obs_n)
+        if a.normalize_value:
+            model_out['values'] = a.value_rms.unnormalize(model_out['values'])
+        a.storage.update_data('obses', n, a.obs)
+        for k in ['actions', 'neglogp', 'values', 'mu', 'sigma']:
+            a.storage.update_data(k, n, model_out[k])
+        actions = torch.clamp(model_out['actions'], -1.0, 1.0)
+        obs, r, a.dones, infos = a.env.step(actions)
+        a.obs = a._convert_obs(obs)
+        rewards = r.reshape(-1, 1)
+        a.storage.update_data('dones', n, a.dones)
+        shaped = a.reward_shaper(rewards.clone())
+        if a.value_bootstrap and 'time_outs' in infos:
+            shaped += a.gamma * model_out['values'] * infos['time_outs'].reshape(-1, 1).float()
+        a.storage.update_data('rewards', n, shaped)
+        done_indices = torch.where(a.dones)[0].tolist()   # the reference's per-step host round trip (ppo.py:165)
+        a._host_metrics.update(a.epoch, a.env, a.obs, rewards.squeeze(-1), done_indices, infos)
+    obs_n = {k: a.obs_rms[k].normalize(v) for k, v in a.obs.items()} if a.normalize_input else a.obs
+    last = a.model.act(obs_n)['values']
+    a.finish_rollout(a.value_rms.unnormalize(last) if a.normalize_value else last)
+
+
 def run(workload, fused, reps=5):
     w = WORKLOADS[workload]
     dev = "cuda:0"
     cfg = make_cfg(w, dev, False, cuda_graph=False)
-    cfg.agent.ppo["fused_rollout"] = fused
     env = DeviceEnv(w["N"], w["O"], w["A"], w["T"], dev)
     torch.manual_seed(0)
     agent = PPO(cfg, env=env)
@@ -55,13 +82,16 @@ def run(workload, fused, reps=5):
     agent.obs = agent._convert_obs(env.reset())
     agent.dones = torch.zeros(w["N"], dtype=torch.bool, device=dev)
     agent.set_eval()
+    from mineral_b200.agents.agent import Metrics
+    agent._host_metrics = Metrics({'rewards': torch.zeros(w["N"], device=dev), 'lengths': torch.zeros(w["N"], dtype=torch.int64, device=dev)}, 100)
+    play = agent.play_steps if fused else (lambda: torch_play_steps(agent))
     for _ in range(2):
-        agent.play_steps()
+        play()
     torch.cuda.synchronize()
     nv.LAUNCHES = 0
     t0 = time.perf_counter()
     for _ in range(reps):
-        agent.play_steps()
+        play()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
     steps = w["T"] * w["N"]
