@@ -13,7 +13,7 @@ import subprocess
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmineral_b200.so")
+LIB_PATH = os.environ.get("MINERAL_B200_LIB") or os.path.join(_HERE, "lib", "libmineral_b200.so")   # env: A/B builds (tools/)
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 c_f32p = C.c_void_p

@@ -265,6 +265,7 @@ class SHAC(Agent):
         for i in range(T):
             for k, v in obs.items():
                 self.obs_buf[k][i] = v
+            pre_step_obs = obs   # normalised observation the actor saw (the reference's `z`, shac.py:668)
             out = act_fn(i, obs)
             if not isinstance(out, dict):
                 out = dict(actions=out)
@@ -280,11 +281,11 @@ class SHAC(Agent):
             self.episode_lengths += 1
             self.episode_discounted_rewards += self.episode_gamma * raw_rew
             self.episode_gamma *= self.gamma
-            prev_obs, obs = obs, self.rollout_observe(obs)
+            obs = self.rollout_observe(obs)
             # shac.py:702-709: with the (default) shared encoder the reference bootstraps from `z`, the encoding it computed
             # BEFORE env.step - i.e. from the pre-step observation - and only a separate target encoder sees the new one.
-            # Parity copies that quirk (SURVEY.md Appendix B style).
-            nv_min, nv_avg = self._bootstrap_values(prev_obs if self.share_encoder else obs)
+            # Parity copies that quirk (SURVEY.md Appendix B style; verified against the recorded reference rollout).
+            nv_min, nv_avg = self._bootstrap_values(pre_step_obs if self.share_encoder else obs)
             done_ids = done.nonzero(as_tuple=False).squeeze(-1)
             if len(done_ids) > 0:
                 terminal = self._convert_obs(info['obs_before_reset'])

@@ -32,7 +32,7 @@ constexpr int kBM = 128, kBK = 32;
 constexpr int kTileA = kBM * kBK * 4;  // 16 KiB
 constexpr int kChunk = 32 * 32 * 4;    // 4 KiB: one MN-major chunk (32 reduction rows x 32 floats)
 constexpr int kMaxGroups = 2;
-constexpr int kMaxStages = 4;
+constexpr int kMaxStages = 6;
 
 enum Mode { kFwd = 0, kDx = 1, kDw = 2 };
 
@@ -65,11 +65,21 @@ struct TcParams {
   int tiles_i, tiles_j;
 };
 
-// expm1(z) for z <= 0, accurate to ~1e-7 RELATIVE like torch's ELU (which calls expm1): `__expf(z) - 1` loses the low bits
-// of small |z| to cancellation (1e-7 absolute is 1e-3 relative at z = -1e-4).  |z| < 1/4: degree-7 Taylor polynomial
-// (remainder z^8 / 8! < 4e-10 there); below that the result is <= -0.22 and the 1e-7 absolute error of ex2.approx is
-// < 5e-7 of it.  11 instructions against ~30 for expm1f: the epilogue is instruction-bound.
+// ELU's negative branch, expm1(z) for z <= 0.  Default (variant 0): `__expf(z) - 1` = one MUFU.EX2 + 2 FP32 ops; its ABSOLUTE
+// error is <= 1.2e-7 (one ulp of 1.0, the same rounding any f32 value next to 1 carries), i.e. 1e-7 of the activation scale
+// against the 1e-5 parity bar - but its RELATIVE error grows as z -> 0- (1e-3 at z = -1e-4), where torch's expm1 stays at
+// 1e-7.  Variants 1 / 2 restore the relative accuracy with a Taylor polynomial below |z| = 1/4 (degree 7) / 1/16 (degree 4).
+// MEASURED on B200 (profiles/r02_summary.md, same box back to back, whole PPO update at cfg2): variant 0 5.63 ms, variant 2
+// 6.36 ms, variant 1 6.50 ms - the epilogue is LSU / issue-bound, 4-8 extra instructions per output element cost 13-15 % of
+// the update.  The full-shape parity tests (tests/test_gpu_fullshape.py) pass at 1e-5 with every variant, so the fast form
+// is the default; build with -DMNR_ELU_VARIANT=2 for expm1-grade relative accuracy.
+#ifndef MNR_ELU_VARIANT
+#define MNR_ELU_VARIANT 0
+#endif
 __device__ __forceinline__ float expm1_neg(float z) {
+#if MNR_ELU_VARIANT == 0
+  return __expf(z) - 1.f;
+#elif MNR_ELU_VARIANT == 1
   float p = fmaf(z, 1.f / 5040.f, 1.f / 720.f);
   p = fmaf(p, z, 1.f / 120.f);
   p = fmaf(p, z, 1.f / 24.f);
@@ -77,6 +87,12 @@ __device__ __forceinline__ float expm1_neg(float z) {
   p = fmaf(p, z, 0.5f);
   p = fmaf(p, z, 1.f);
   return z > -0.25f ? p * z : __expf(z) - 1.f;
+#else
+  float p = fmaf(z, 1.f / 24.f, 1.f / 6.f);
+  p = fmaf(p, z, 0.5f);
+  p = fmaf(p, z, 1.f);
+  return z > -0.0625f ? p * z : __expf(z) - 1.f;
+#endif
 }
 
 template <int ACT>
@@ -403,6 +419,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 #pragma unroll
         for (int q = 0; q < 32; ++q) stg[lane * 33 + q] = __uint_as_float(r[q]);
         __syncwarp();
+        // (Round 2 measured the alternative without this transpose - lane = row keeps its 32 columns and writes them as four
+        // 256-bit stores, ~6 instead of ~10 instructions per element: 6.05 ms per update against 5.61 ms.  Every such store
+        // instruction touches 32 different 128 B lines = 32 LSU wavefronts, 128 per chunk against 96 here: the epilogue is
+        // bound by LSU wavefronts, not by issue slots.  profiles/r02_summary.md.)
         // lane = column: every store instruction writes one full 128 B line of one output row.  Batches of 8 rows:
         // 8 independent LDS, then the math, then 8 stores (a guarded one-row-at-a-time loop runs as one long
         // dependent chain: ~100 cycles per row).
@@ -577,6 +597,10 @@ int pick_stages(int mode, int act, int BN) {
   const int stage = stage_bytes_of(mode, act, BN);
   int s = (227 * 1024 - 2048 - kEpiStageBytes) / stage;
   if (s > kMaxStages) s = kMaxStages;
+  // tensor memory: accumulators (two of BN columns, one above 128) + one 64-column A slot per stage <= 512 columns
+  const int acc_cols = (BN > 128 ? 1 : 2) * ((BN + 31) / 32 * 32);
+  const int tmem_s = (512 - acc_cols) / 64;
+  if (s > tmem_s) s = tmem_s;
   return s;
 }
 

@@ -134,10 +134,14 @@ def test_full_update_at_benchmark_shape_vs_oracle(workload, cuda_graph):
         for i, k in enumerate(("running_mean", "running_var", "running_count")):
             _check(t, f"obs_rms.{k}", getattr(agent.obs_rms["obs"], k), r32["obs_rms"][i], r64["obs_rms"][i], tol=2e-6)
             _check(t, f"value_rms.{k}", getattr(agent.value_rms, k), r32["value_rms"][i], r64["value_rms"][i], tol=2e-6)
-        # parameters after all optimizer steps, mu / sigma write-back of the last mini-epoch
+        # parameters after all optimizer steps.  Scale: the tensor's own magnitude PLUS what the optimizer could have moved it
+        # (Adam moves an element by ~lr per step whatever the gradient's size, so a 1e-5 relative error in one step's direction
+        # is 1e-5 * lr absolute): a bias that started at zero and oscillates around it has max|b| ~ 1e-4 and no meaningful
+        # "relative to its own magnitude" (SURVEY.md section 0 makes the same point about element-wise rtol next to zero)
         msd = agent.model.state_dict()
+        travel = sum(float(x) for x in r32["res"]["lr"]) * (w["minibatches"])   # sum over optimizer steps of that step's lr
         for k, v in r32["final"].items():
-            _check(t, f"param {k}", msd[k], v, r64["final"][k])
+            _check(t, f"param {k}", msd[k], v, r64["final"][k], abs_floor=1e-5 * travel)
         _check(t, "mu write-back", data["mu"], r32["mu"], r64["mu"])
         _check(t, "sigma write-back", data["sigma"], r32["sigma"], r64["sigma"])
     assert (agent._engine.graph is not None) == cuda_graph
