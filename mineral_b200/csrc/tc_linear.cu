@@ -21,6 +21,8 @@
 //   warps 4-7   converters: fp32 tile -> hi / lo (act' and the bias-gradient column sums fused) -> TMEM slot;
 //               DW: warps 8-11 are a second converter group (alternate k-blocks)
 //   warps 8-15  epilogue (DW: warps 12-15): tcgen05.ld -> bias + activation -> 32x32 transpose in smem -> full-line stores
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -46,6 +48,7 @@ __device__ int g_trace_on = 0;
 
 struct alignas(64) TcGroup {
   CUtensorMap a, s, b0, b1;  // b0: B (hi, or raw when converted in-kernel), b1: B lo (pre-split modes)
+  CUtensorMap cmap;          // FWD / DX with tma_store: C as [32 x 32] SWIZZLE_128B boxes
   float* c;
   const float* bias;
 };
@@ -63,6 +66,7 @@ struct TcParams {
   int want_bias;
   int n_groups;
   int tiles_i, tiles_j;
+  int tma_store;  // FWD / DX: the epilogue leaves through TMA tensor stores (C rows 16 B-multiple apart), else plain stores
 };
 
 // ELU's negative branch, expm1(z) for z <= 0.  Default (variant 0): `__expf(z) - 1` = one MUFU.EX2 + 2 FP32 ops; its ABSOLUTE
@@ -76,9 +80,18 @@ struct TcParams {
 #ifndef MNR_ELU_VARIANT
 #define MNR_ELU_VARIANT 0
 #endif
+// exp(z) as ONE multiply + MUFU.EX2 with flush-to-zero: `__expf` compiles to the non-ftz ex2.approx, whose denormal-input
+// guard costs an FSETP, a PLOP3 and two predicated FMULs per element (4 of the ~17 instructions per output element the ncu
+// source page of the forward epilogue showed).  Flushing is exact for ELU: a denormal z gives exp(z) - 1 = z ~ 0 either way
+// and exp(z) underflows only below z = -87, where the result is -1.
+__device__ __forceinline__ float exp_ftz(float z) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(z * 1.4426950408889634f));
+  return y;
+}
 __device__ __forceinline__ float expm1_neg(float z) {
 #if MNR_ELU_VARIANT == 0
-  return __expf(z) - 1.f;
+  return exp_ftz(z) - 1.f;
 #elif MNR_ELU_VARIANT == 1
   float p = fmaf(z, 1.f / 5040.f, 1.f / 720.f);
   p = fmaf(p, z, 1.f / 120.f);
@@ -86,12 +99,12 @@ __device__ __forceinline__ float expm1_neg(float z) {
   p = fmaf(p, z, 1.f / 6.f);
   p = fmaf(p, z, 0.5f);
   p = fmaf(p, z, 1.f);
-  return z > -0.25f ? p * z : __expf(z) - 1.f;
+  return z > -0.25f ? p * z : exp_ftz(z) - 1.f;
 #else
   float p = fmaf(z, 1.f / 24.f, 1.f / 6.f);
   p = fmaf(p, z, 0.5f);
   p = fmaf(p, z, 1.f);
-  return z > -0.0625f ? p * z : __expf(z) - 1.f;
+  return z > -0.0625f ? p * z : exp_ftz(z) - 1.f;
 #endif
 }
 
@@ -180,7 +193,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   const int bytesB = BN * kBK * 4;
   const int offBlo = offB + bytesB;
   const int stage_bytes = offBlo + bytesB;
-  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // 8 warps x [32][33] floats
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);  // 8 warps x [32][33] floats, or (TMA
+                                                                                     // store) 8 x 4 KiB swizzled [32][32] boxes
+  // (TMA store, FWD) behind the 8 boxes: 32 bias floats per epilogue warp, rewritten per chunk
+  float* s_bias_all = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(epi_stage) + 8 * 4096);
 
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
@@ -274,8 +290,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           // descriptor = constant high word | (start address >> 4) in the low word: only the address changes
           const uint32_t b_lo32 = ((base + offB) >> 4) | b_desc_lo_const, blo_lo32 = ((base + offBlo) >> 4) | b_desc_lo_const;
           const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u;  // A ring slot: hi at +0, lo at +32
+          // k-steps of 8 that hold real reduction elements: a ragged last k-block (first-layer K = 37 -> 40: one of its four
+          // k-steps) does not issue MMAs over TMA's zero fill (9 of the 24 MMAs of a K = 40 tile)
+          const int r_left = (MODE == kDw ? min(p.R, tc.r_begin + p.rows_per_split) : p.R) - (tc.r_begin + kb * kBK);
+          const int ksteps = r_left >= kBK ? kBK / 8 : (r_left + 7) / 8;
 #pragma unroll
           for (int k = 0; k < kBK / 8; ++k) {
+            if (k >= ksteps) break;
             // B K-major: step 8 floats (32 B) inside the 128 B swizzle row; MN-major: step 8 reduction rows (1 KiB)
             const uint32_t b_step = (B_MN ? k * 1024 : k * 32) >> 4;
             const uint64_t b_hi = b_desc_hi | (uint64_t)(b_lo32 + b_step), b_lo = b_desc_hi | (uint64_t)(blo_lo32 + b_step);
@@ -404,6 +425,59 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       if (MODE == kDw) cbase = p.partials + ((size_t)tc.gi * p.splits + tc.split) * p.I * p.J, ldo = p.J;
       else cbase = g.c, ldo = p.ldc;
       const int row_base = tc.i0 + 32 * quarter;
+      if (MODE != kDw && p.tma_store) {
+        // ---- TMA-store epilogue: lane = output row keeps its 32 accumulator columns, applies bias + activation on the
+        // registers (bias columns from this warp's shared-memory row, broadcast LDS.128), parks the row as eight 16 B pieces
+        // in a [32 rows][128 B] box with the 128 B swizzle (piece c of row r at c ^ (r & 7): conflict-free), and ONE
+        // cp.async.bulk.tensor store moves the box to C.  ~215 instructions and 32 LSU wavefronts per 32x32 chunk against
+        // ~430 and 96 for the transpose + full-line stores below; the box is reused once the previous store has read it.
+        const uint32_t box = ptx::smem_u32(reinterpret_cast<uint8_t*>(epi_stage) + (size_t)(warp - kEpi0) * 4096);
+        float* s_bias = s_bias_all + (warp - kEpi0) * 32;
+        for (int cc = half; cc < (BN + 31) / 32; cc += kEpi / 4) {
+          if (MODE == kFwd) {   // this chunk's bias columns -> the warp's shared-memory row (read back as broadcast LDS.128)
+            __syncwarp();
+            s_bias[lane] = cc == half ? bias_c[0] : bias_c[1];
+            __syncwarp();
+          }
+          uint32_t r[32];
+          if (tc.num_kb > 0) {
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + acc * acc_stride + (uint32_t)(cc * 32), r);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = 0u;
+          }
+          float v[32];
+          if (MODE == kFwd) {
+            const float4* b4 = reinterpret_cast<const float4*>(s_bias);
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 b = b4[q4];
+              v[4 * q4] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4]) + b.x), v[4 * q4 + 1] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 1]) + b.y);
+              v[4 * q4 + 2] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 2]) + b.z), v[4 * q4 + 3] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 3]) + b.w);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
+          }
+          if (lane == 0) ptx::bulk_wait_read0();   // the previous store of this warp has finished reading the box
+          __syncwarp();
+          const uint32_t row_addr = box + (uint32_t)lane * 128u;
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(row_addr + (uint32_t)((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            ptx::tma_store_2d(&g.cmap, reinterpret_cast<const uint8_t*>(epi_stage) + (size_t)(warp - kEpi0) * 4096, tc.j0 + cc * 32, row_base);
+            ptx::bulk_commit();
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&tmem_empty[acc]);
+        if (tid == kEpi0 * 32) TC_TRACE(3, it, 1);
+        continue;
+      }
       for (int cc = half; cc < (BN + 31) / 32; cc += kEpi / 4) {
         uint32_t r[32];
         if (tc.num_kb > 0) {
@@ -461,6 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     }
   }
 
+  if (MODE != kDw && p.tma_store && warp >= 8 && lane == 0) ptx::bulk_wait0();  // this warp's C boxes have landed
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -589,7 +664,17 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
   return r == CUDA_SUCCESS ? MNR_OK : MNR_EUNSUP;
 }
 
-constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;
+constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;   // >= 8 x 4 KiB boxes of the TMA-store epilogue
+
+// MNR_TC_TMA_STORE=0 selects the transpose + full-line-store epilogue (A/B measurements); read once
+int tma_store_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MNR_TC_TMA_STORE");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v;
+}
 
 int stage_bytes_of(int mode, int act, int BN) { return ((mode == kFwd || act == 0) ? 1 : 2) * kTileA + 2 * BN * kBK * 4; }
 
@@ -641,6 +726,7 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
   const int N = groups[0].N, K = groups[0].K;
   if (N <= 0 || K <= 0 || N % 16 != 0) return MNR_ESHAPE;
   TcParams p;
+  int tma_store = tma_store_enabled();
   p.BN = N <= 128 ? N : 128;  // 2 accumulators + the A ring share the 512 TMEM columns
   if (N > 128 && N % 128 != 0) return MNR_ESHAPE;
   for (int k = 0; k < n_groups; ++k) {
@@ -653,7 +739,9 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
     if (rc != MNR_OK) return rc;
     p.g[k].s = p.g[k].a;
     p.g[k].c = s.c, p.g[k].bias = s.bias;
+    if (make_map(&p.g[k].cmap, s.c, M, N, N, 32) != MNR_OK) tma_store = 0;   // C (M,N) as [32 x 32] boxes
   }
+  p.tma_store = tma_store;
   p.I = M, p.J = N, p.R = K, p.ldc = N, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
   p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kFwd, act, p.BN);
   dim3 grid((M + kBM - 1) / kBM, (N + p.BN - 1) / p.BN, n_groups);
@@ -668,6 +756,7 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
   const int N = groups[0].N, K = groups[0].K;
   if (N <= 0 || K <= 0 || N % 4 != 0) return MNR_ESHAPE;
   TcParams p;
+  int tma_store = tma_store_enabled();
   const int Kr = (K + 31) / 32 * 32;
   p.BN = Kr <= 128 ? Kr : 128;
   for (int k = 0; k < n_groups; ++k) {
@@ -680,7 +769,10 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
     if (rc == MNR_OK) rc = make_map(&p.g[k].b1, s.b_lo, N, K, ld_or(s.ldb, K), 32, true);
     if (rc != MNR_OK) return rc;
     p.g[k].c = s.c, p.g[k].bias = nullptr;
+    // dX (M,K): the tensor map needs a 16 B-multiple row stride; otherwise (K % 4 != 0) the plain-store epilogue runs
+    if (make_map(&p.g[k].cmap, s.c, M, K, K, 32) != MNR_OK) tma_store = 0;
   }
+  p.tma_store = tma_store;
   p.I = M, p.J = K, p.R = N, p.ldc = K, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
   p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kDx, act, p.BN);
   dim3 grid((M + kBM - 1) / kBM, (K + p.BN - 1) / p.BN, n_groups);
@@ -758,6 +850,7 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
   p.I = N, p.J = K, p.R = M, p.ldc = K, p.act = act, p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 31) / 32 * 32;
   p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = pick_stages(kDw, act, p.BN);
+  p.tma_store = 0;
   dim3 grid(ti, tj, n_groups * splits);
   return launch<kDw>(p, grid, stream);
 }
