@@ -590,6 +590,27 @@ int mnr_distl_projection(const float* next_dist, const float* reward, const floa
                          float v_min, float v_max, float delta_z, int n_atoms, float* out, int64_t rows, mnr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * 8(f)-2  categorical (C51) critic of DDPG: `DistributionalEnsembleQ` (mineral/agents/ddpg/models.py:117-170) inside
+ *      DDPG.update_critic / update_actor (mineral/agents/ddpg/ddpg.py:266-310).  `logits->pred[k]`: (rows, n_atoms) outputs
+ *      of critic k's last linear layer, `->grad[k]`: d loss / d logits written by the call; n_atoms <= 128, n_q <= 4.
+ *      mnr_distl_target:      target (rows, n_atoms) = min_k distl_projection(softmax(target_logits_k), reward, done,
+ *                             gamma_n = gamma^nstep, v_min, v_max, support)   (ddpg.py:275-290, ddpg/utils.py:14-31);
+ *      mnr_distl_bce_fwd_bwd: *loss_out = sum_k F.binary_cross_entropy(softmax(logits_k), target) (mean reduction,
+ *                             logs clamped at -100) and its gradient through the softmax   (ddpg.py:267-269,295-296);
+ *      mnr_distl_actor_seed:  Q = min_k sum_a softmax(logits_k)_a * support_a (get_q_min, models.py:160-163; first
+ *                             minimum on ties), *loss_out = -mean(Q) and d loss / d logits_k  (ddpg.py:306-307).
+ *      workspace: mnr_distl_workspace_bytes() bytes, zero-initialised once, 8 B aligned.  Deterministic.
+ * ------------------------------------------------------------------------------------ */
+size_t mnr_distl_workspace_bytes(void);
+int mnr_distl_target(const mnr_critic_set_t* target_logits /*host*/, int n_q, const float* reward, const float* done,
+                     const float* support, float gamma_n, float v_min, float v_max, float delta_z, int n_atoms,
+                     float* target_out, int64_t rows, mnr_stream_t stream);
+int mnr_distl_bce_fwd_bwd(const mnr_critic_set_t* logits /*host*/, int n_q, const float* target, int64_t rows, int n_atoms,
+                          float* loss_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+int mnr_distl_actor_seed(const mnr_critic_set_t* logits /*host*/, int n_q, const float* support, int64_t rows, int n_atoms,
+                         float* loss_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * 8(f)-2 (agents)  row-wise math of the SAC / DDPG agents around the tower GEMMs (mineral/agents/sac/sac.py,
  *      mineral/agents/ddpg/ddpg.py, mineral/agents/ddpg/models.py, mineral/nets/dist.py, mineral/nets/distributions.py).
  *      mnr_copy_cols_f32:    dst[r, 0:cols) = src[r, 0:cols) with row strides (the `torch.cat((state, action), 1)` of

@@ -11,8 +11,9 @@ Reference line -> here (no autograd, no cuBLAS, no torch elementwise op on the u
   ddpg.py:299-310 actor step                            -> critic fwd + input gradient only, mnr_actor_seed, mnr_tanh_action_bwd,
                                                            actor bwd, mnr_fused_clip_adam
   ddpg.py:260-263 soft_update                           -> mnr_soft_update over flat buffers
-The categorical critic (`DistributionalEnsembleQ`, ddpg.py:276-290) is not on the fused path; its projection kernel is
-`mineral_b200.agents.ddpg.utils.distl_projection`."""
+  ddpg.py:267-290 categorical critic (DistributionalEnsembleQ) -> n_atoms-wide critic heads on the same towers, mnr_distl_target
+                                                           (softmax + C51 projection + ensemble min), mnr_distl_bce_fwd_bwd,
+                                                           mnr_distl_actor_seed (csrc/distl.cu)"""
 
 import os
 from copy import deepcopy
@@ -67,6 +68,14 @@ class DDPG(OffPolicyAgent):
         self._fq = FusedQ(self.critic, B, dev)
         self._fq_t = FusedQ(self.critic_target, B, dev)
         self._attach_optimizer_splits()
+        self.distl = bool(getattr(self.critic, 'distl', False))   # ddpg.py:267
+        if self.distl:
+            n = self.critic.num_atoms
+            self._z_atoms = self.critic.z_atoms.to(device=dev, dtype=torch.float32).contiguous()
+            self._target_dist = torch.empty(B, n, dtype=torch.float32, device=dev)
+            self._distl_ws = ops.distl_workspace(dev)
+        elif self._fq.n_out != 1:
+            raise NotImplementedError('a scalar-Q critic must end in a 1-wide layer')
 
     # --- noise draws (hooks; torch.normal(0, std) == std * standard normal) ---
     def _exploration_noise(self, rows):
@@ -168,6 +177,16 @@ class DDPG(OffPolicyAgent):
         self.get_tgt_policy_actions()
         q_t = self._fq_t.forward(self.xn, B)
         out = torch.empty(2, dtype=torch.float32, device=self.device)
+        if self.distl:   # ddpg.py:275-290,295-296: projected target distribution, BCE against every critic's softmax
+            ct, n = self.critic_target, self.critic.num_atoms
+            ops.distl_target(q_t, self.reward_b.view(-1), self.done_b.view(-1), self._z_atoms, cfg.gamma ** cfg.nstep, float(ct.v_min),
+                             float(ct.v_max), n, self._target_dist)
+            fq = self._fq
+            fq.forward(self.xc, B, split=self._split_needed())
+            ops.distl_bce_fwd_bwd(fq.pred, self._target_dist, fq.g_pred, out[0:1], self._distl_ws, B, n)
+            fq.backward_from_seeds(self.xc, B)
+            self.optimizer_update(self.critic_optim, out[1:2])
+            return out[0], out[1]
         ops.td_target_stats([q.view(-1)[:B] for q in q_t], None, self.reward_b.view(-1), self.done_b.view(-1), None, 0.0,
                             cfg.gamma ** cfg.nstep, self.target_q.view(-1), None)
         self._fq.loss_fwd_bwd(self.xc, self.target_q, out[0:1], split=self._split_needed())
@@ -183,7 +202,10 @@ class DDPG(OffPolicyAgent):
         ops.tanh_action(fa.mu_raw, None, self.xc[:B, O:O + A], None, None, B)
         fq.forward(self.xc, B, split=self._split_needed())
         out = torch.empty(5, dtype=torch.float32, device=self.device)
-        ops.actor_seed([q.view(-1)[:B] for q in fq.pred], [g.view(-1)[:B] for g in fq.g_pred], None, None, 0.0, 0.0, out[0:4], None)
+        if self.distl:   # Q = min_k E_k[z] (models.py:160-163); seeds through the minimal critic's softmax
+            ops.distl_actor_seed(fq.pred, self._z_atoms, fq.g_pred, out[0:1], self._distl_ws, B, self.critic.num_atoms)
+        else:
+            ops.actor_seed([q.view(-1)[:B] for q in fq.pred], [g.view(-1)[:B] for g in fq.g_pred], None, None, 0.0, 0.0, out[0:4], None)
         dx = fq.input_grad(self.xc, B)
         ops.tanh_action_bwd(fa.mu_raw, dx[0][:B, O:O + A], fa.g_mu, B, g_actions2=dx[1][:B, O:O + A] if len(dx) > 1 else None)
         fa.backward(self.xc, B)

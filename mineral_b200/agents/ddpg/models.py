@@ -100,3 +100,37 @@ class EnsembleQ(nn.Module):
 
     def get_q_values(self, state, action):
         return self.forward(state, action)
+
+
+class DistributionalEnsembleQ(nn.Module):
+    """Categorical (C51) critics (mineral/agents/ddpg/models.py:117-170): every critic ends in `num_atoms` logits over the fixed
+    support linspace(v_min, v_max, num_atoms).  Parameter container like the classes above; DDPG runs it through
+    `FusedQ` (n_out = num_atoms) and the row-wise kernels of csrc/distl.cu."""
+
+    def __init__(self, state_dim, action_dim, v_min=-10, v_max=10, num_atoms=51, n_critics=2, mlp_kwargs=None, weight_init=None):
+        super().__init__()
+        mlp_kwargs = dict(units=[512, 256, 128], act_type='ELU') if mlp_kwargs is None else dict(mlp_kwargs)
+        self.v_min, self.v_max, self.num_atoms = v_min, v_max, num_atoms
+        self.z_atoms = torch.linspace(v_min, v_max, num_atoms)
+        self.n_critics = n_critics
+        self.critics = nn.ModuleList([MLP(state_dim + action_dim, out_dim=num_atoms, plain_last=True, **mlp_kwargs) for _ in range(n_critics)])
+        self.weight_init = weight_init
+        if weight_init is not None:
+            raise NotImplementedError(weight_init)   # models.py:152-154
+
+    @property
+    def distl(self):
+        return True
+
+    def forward(self, state, action):
+        if isinstance(state, dict):
+            state = state['z']
+        x = torch.cat((state, action), dim=1)
+        return [critic(x) for critic in self.critics]
+
+    def get_q_values(self, state, action):
+        return [torch.softmax(q, dim=1) for q in self.forward(state, action)]
+
+    def get_q_min(self, state, action):
+        qs = [torch.sum(q * self.z_atoms.to(q.device), dim=1) for q in self.get_q_values(state, action)]
+        return torch.min(torch.stack(qs), dim=0).values

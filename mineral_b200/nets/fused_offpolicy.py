@@ -16,8 +16,9 @@ def pad4(n):
 
 
 class FusedQ:
-    """EnsembleQ with 1 or 2 critics: Q_k(cat(z, a)).  The input is read from a (rows, x_ld) buffer whose columns
-    [0, obs_dim) hold z and [obs_dim, obs_dim + act_dim) the action (pad columns zero)."""
+    """EnsembleQ / DistributionalEnsembleQ with 1 or 2 critics: Q_k(cat(z, a)).  The input is read from a (rows, x_ld) buffer
+    whose columns [0, obs_dim) hold z and [obs_dim, obs_dim + act_dim) the action (pad columns zero).  The last linear layer
+    is n_out wide: 1 (scalar Q, mineral/agents/ddpg/models.py:70-111) or num_atoms (categorical critic, models.py:117-170)."""
 
     @staticmethod
     def parse(module):
@@ -26,8 +27,6 @@ class FusedQ:
             return None
         parsed = [_tower_layers(m, plain_last=True) for m in mlps]
         if any(p is None for p in parsed) or any(not _same_shape(parsed[0], p) for p in parsed[1:]):
-            return None
-        if parsed[0][0][-1][0].weight.shape[0] != 1:
             return None
         return parsed
 
@@ -38,36 +37,44 @@ class FusedQ:
         self.module, self.G, self.M = module, len(parsed), rows
         self.stack = TowerStack([p[0][:-1] for p in parsed], parsed[0][1], rows, device, use_tc)
         self.last = [p[0][-1][0] for p in parsed]
+        self.n_out = n_out = self.last[0].weight.shape[0]
         self.in_dim, self.x_ld = self.stack.in_dim, pad4(self.stack.in_dim)
         f32 = dict(dtype=torch.float32, device=device)
-        self.pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
-        self.g_pred = [torch.empty(rows, 1, **f32) for _ in range(self.G)]
+        self.pred = [torch.empty(rows, n_out, **f32) for _ in range(self.G)]
+        self.g_pred = [torch.empty(rows, n_out, **f32) for _ in range(self.G)]
         # d objective / d input per critic tower (tensor-core path: one launch, the consumer adds the towers) or summed (SIMT)
         self.dx = [torch.empty(rows, self.in_dim, **f32) for _ in range(self.G if self.stack.use_tc else 1)]
         h = self.stack.widths[-1]
-        self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(self.G, rows, 1, h), 256), dtype=torch.uint8, device=device)
+        self.ws = torch.zeros(max(ops.lib.mnr_linear_bwd_weight_workspace_bytes(self.G, rows, n_out, h), 256), dtype=torch.uint8, device=device)
         self.mse_ws = torch.zeros(ops.lib.mnr_critic_mse_workspace_bytes(rows), dtype=torch.uint8, device=device)
 
     def forward(self, x, rows=None, split=True):
-        """-> self.pred[k] (rows, 1).  split=False: the weights did not change since the last forward of THIS object."""
+        """-> self.pred[k] (rows, n_out).  split=False: the weights did not change since the last forward of THIS object."""
         rows = self.M if rows is None else rows
         st, h = self.stack, self.stack.widths[-1]
         st.forward(x, self.x_ld, rows, split)
-        ops.linear_fwd([dict(a=st.Y[-1][g], b=self.last[g].weight.data, c=self.pred[g], bias=self.last[g].bias.data, N=1, K=h)
+        ops.linear_fwd([dict(a=st.Y[-1][g], b=self.last[g].weight.data, c=self.pred[g], bias=self.last[g].bias.data, N=self.n_out, K=h)
                         for g in range(self.G)], rows, 0)
         return self.pred
 
+    def backward_from_seeds(self, x, rows=None):
+        """With d loss / d output of every critic in self.g_pred (rows, n_out): every critic parameter's .grad."""
+        rows = self.M if rows is None else rows
+        st, G, n = self.stack, self.G, self.n_out
+        h = st.widths[-1]
+        ops.linear_bwd_weight([dict(a=self.g_pred[g], b=st.Y[-1][g], c=self.last[g].weight.grad, bias_grad=self.last[g].bias.grad, N=n, K=h)
+                               for g in range(G)], rows, 0, self.ws)
+        ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=n, K=h) for g in range(G)], rows, 0)
+        st.backward(x, rows)
+
     def loss_fwd_bwd(self, x, target, loss_out, split=True):
         """sum_k MSE(Q_k(x), target) (sac.py:301-303, ddpg.py:295-296) -> loss_out (1 float) and every critic parameter's .grad."""
-        rows, st, G = target.numel(), self.stack, self.G
-        h = st.widths[-1]
+        assert self.n_out == 1
+        rows = target.numel()
         self.forward(x, rows, split)
         ops.critic_mse_sum_fwd_bwd([p.view(-1)[:rows] for p in self.pred], target.view(-1), [g_.view(-1)[:rows] for g_ in self.g_pred],
                                    loss_out, self.mse_ws)
-        ops.linear_bwd_weight([dict(a=self.g_pred[g], b=st.Y[-1][g], c=self.last[g].weight.grad, bias_grad=self.last[g].bias.grad, N=1, K=h)
-                               for g in range(G)], rows, 0, self.ws)
-        ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=1, K=h) for g in range(G)], rows, 0)
-        st.backward(x, rows)
+        self.backward_from_seeds(x, rows)
 
     def input_grad(self, x, rows=None):
         """After forward(x) and with d objective / d Q_k in self.g_pred: d objective / d x -> self.dx, a list of (rows, in_dim)
@@ -75,7 +82,7 @@ class FusedQ:
         gradient is formed (the critic is frozen here: `critic.requires_grad_(False)`)."""
         rows = self.M if rows is None else rows
         st, h = self.stack, self.stack.widths[-1]
-        ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=1, K=h) for g in range(self.G)], rows, 0)
+        ops.linear_bwd_input([dict(a=self.g_pred[g], b=self.last[g].weight.data, c=st.dY[-1][g], N=self.n_out, K=h) for g in range(self.G)], rows, 0)
         st.backward(x, rows, weight_grads=False, input_grad=self.dx if st.use_tc else self.dx[0])
         return self.dx
 

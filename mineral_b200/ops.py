@@ -470,6 +470,33 @@ def critic_mse_sum_fwd_bwd(preds, target, grads, loss_out, ws):
                                          ptr(ws, U8), ws.numel(), stream()), "mnr_critic_mse_sum_fwd_bwd")
 
 
+def distl_workspace(device):
+    return torch.zeros(lib.mnr_distl_workspace_bytes(), dtype=U8, device=device)
+
+
+def distl_target(target_logits, reward, done, support, gamma_n, v_min, v_max, n_atoms, out):
+    """min_k distl_projection(softmax(target_logits_k), reward, done, gamma_n) -> out (rows, n_atoms)  (ddpg.py:275-290)."""
+    cs = _critic_set(target_logits, None)
+    delta_z = (v_max - v_min) / (n_atoms - 1)
+    check(lib.mnr_distl_target(C.byref(cs), len(target_logits), ptr(reward, F32, "reward"), ptr(done, F32, "done"), ptr(support, F32, "support"),
+                               gamma_n, v_min, v_max, delta_z, n_atoms, ptr(out, F32, "out"), reward.numel(), stream()), "mnr_distl_target")
+    return out
+
+
+def distl_bce_fwd_bwd(logits, target, grads, loss_out, ws, rows, n_atoms):
+    """sum_k BCE(softmax(logits_k), target) and d loss / d logits_k  (ddpg.py:267-269,295-296)."""
+    cs = _critic_set(logits, grads)
+    check(lib.mnr_distl_bce_fwd_bwd(C.byref(cs), len(logits), ptr(target, F32, "target"), rows, n_atoms, ptr(loss_out, F32), ptr(ws, U8),
+                                    ws.numel(), stream()), "mnr_distl_bce_fwd_bwd")
+
+
+def distl_actor_seed(logits, support, grads, loss_out, ws, rows, n_atoms):
+    """-mean(min_k E_k[z]) and its gradient w.r.t. the logits of the minimal critic  (models.py:160-163, ddpg.py:306-307)."""
+    cs = _critic_set(logits, grads)
+    check(lib.mnr_distl_actor_seed(C.byref(cs), len(logits), ptr(support, F32, "support"), rows, n_atoms, ptr(loss_out, F32), ptr(ws, U8),
+                                   ws.numel(), stream()), "mnr_distl_actor_seed")
+
+
 def make_squash_cfg(dist_type="squashed_normal", minlogstd=None, maxlogstd=None, minstd=1.0, maxstd=1.0):
     kinds = {"squashed_normal": 0, "dreamerv3_squashed_normal": 1}
     if dist_type not in kinds:

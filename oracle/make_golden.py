@@ -409,9 +409,12 @@ def offpolicy_cfg(algo, N, units, batch_size, mini_epochs, variant):
                             update_targets_interval=2, target_entropy_scalar=0.5)
     else:  # AllegroHandDDPG.yaml (TD3-style intervals in the second variant)
         mlp = dict(units=units, act_type="ELU")
-        td3 = variant == "td3"
+        td3 = variant in ("td3", "distl_td3")
         network = dict(normalize_input=True, encoder=None, actor="Actor", critic="EnsembleQ",
                        actor_kwargs=dict(tanh_policy=True, mlp_kwargs=mlp), critic_kwargs=dict(n_critics=2, mlp_kwargs=mlp))
+        if variant.startswith("distl"):   # AllegroHandDDPG.yaml:34 (commented alternative): categorical critics on a fixed support
+            network.update(critic="DistributionalEnsembleQ",
+                           critic_kwargs=dict(v_min=-4.0, v_max=4.0, num_atoms=21 if td3 else 51, n_critics=2, mlp_kwargs=mlp))
         algo_cfg = dict(multi_gpu=False, num_actors=N, reward_shaper=dict(fn="scale", scale=0.5), max_agent_steps=1e6, horizon_len=4,
                         memory_size=1000, batch_size=batch_size, nstep=3, tau=0.05, gamma=0.99, warm_up=8, no_tgt_actor=not td3,
                         handle_timeout=True, update_actor_interval=2 if td3 else 1, update_targets_interval=2 if td3 else 1,
@@ -450,11 +453,11 @@ class _Recorder:
         self.tdn._standard_normal = self.orig["std_normal"]
 
 
-def gen_offpolicy_e2e():
+def gen_offpolicy_e2e(spec=(("sac", "ln_silu"), ("sac", "elu"), ("ddpg", "mixed"), ("ddpg", "td3"), ("sac", "fixed")), name="offpolicy_e2e"):
     from mineral.agents.ddpg.ddpg import DDPG
     from mineral.agents.sac.sac import SAC
     cases = []
-    for algo, variant in (("sac", "ln_silu"), ("sac", "elu"), ("ddpg", "mixed"), ("ddpg", "td3"), ("sac", "fixed")):
+    for algo, variant in spec:
         N, O, A, units, B, mini_epochs, epochs = 16, 11, 3, [32, 16], 64, 3, 2
         torch.manual_seed(50)
         env = rs.SynthEnv(N, O, A, 64, seed=51, done_p=0.08, timeout_p=0.05)
@@ -497,7 +500,12 @@ def gen_offpolicy_e2e():
             streams = {k: [x.clone() for x in v] for k, v in rec.streams.items()}
         cases.append(dict(algo=algo, variant=variant, shape=(N, O, A), cfg=rs.to_plain(cfg), init=init, warm=warm, epochs=per_epoch,
                           streams=streams, env=dict(horizon=64, seed=51, done_p=0.08, timeout_p=0.05)))
-    save("offpolicy_e2e", cases)
+    save(name, cases)
+
+
+def gen_offpolicy_distl():
+    """DDPG with the categorical critic (DistributionalEnsembleQ, ddpg.py:267-290): mixed-noise and TD3-style variants."""
+    gen_offpolicy_e2e(spec=(("ddpg", "distl"), ("ddpg", "distl_td3")), name="offpolicy_distl")
 
 
 # ---- SAC policy head: Dist + SquashedNormal rsample / log_prob and autograd's gradients (the oracle restatement is pinned on these)
@@ -714,6 +722,7 @@ def gen_shac_rollout():
 if __name__ == "__main__":
     gen_shac_rollout() if "shac_rollout" in sys.argv[1:] else None
     gen_ppo_ckpt() if "ppo_ckpt" in sys.argv[1:] else None
+    gen_offpolicy_distl() if "offpolicy_distl" in sys.argv[1:] else None
     if len(sys.argv) > 1:
         sys.exit(0)
     gen_experience()
@@ -731,3 +740,4 @@ if __name__ == "__main__":
     gen_offpolicy_small()
     gen_shac_rollout()
     gen_ppo_ckpt()
+    gen_offpolicy_distl()

@@ -192,8 +192,17 @@ class _Replay:
 
 
 @pytest.mark.parametrize("cuda_graph", [False, True])
+@pytest.mark.parametrize("case_index", [0, 1])
+def test_ddpg_categorical_critic_matches_reference_run(case_index, cuda_graph):
+    """DDPG with `DistributionalEnsembleQ` (mineral/agents/ddpg/models.py:117-170, ddpg.py:267-290; 51 atoms with mixed noise,
+    21 atoms TD3-style): softmax + C51 projection + ensemble min, BCE regression of every critic, actor through the minimal
+    critic's expected value - against the real reference agent's recorded run (golden offpolicy_distl.pt)."""
+    test_offpolicy_agents_match_reference_run(case_index, cuda_graph, golden="offpolicy_distl")
+
+
+@pytest.mark.parametrize("cuda_graph", [False, True])
 @pytest.mark.parametrize("case_index", [0, 1, 2, 3, 4])
-def test_offpolicy_agents_match_reference_run(case_index, cuda_graph):
+def test_offpolicy_agents_match_reference_run(case_index, cuda_graph, golden="offpolicy_e2e"):
     """SAC (LayerNorm+SiLU and ELU towers; case 4: sigma parameter, dreamerv3 std, single critic, target actor, raw observations,
     one-step returns, Adam) and DDPG (mixed exploration noise; TD3 with target actor, delayed updates) through
     warm-up, two explore_env + update_net epochs: trajectories, every logged scalar and every parameter against the real
@@ -201,7 +210,7 @@ def test_offpolicy_agents_match_reference_run(case_index, cuda_graph):
     from mineral_b200.agents import DDPG, SAC
     from oracle.reference_shim import SynthEnv, to_attr
 
-    c = load_golden("offpolicy_e2e")[case_index]
+    c = load_golden(golden)[case_index]
     algo = c["algo"]
     N, O, A = c["shape"]
     cfg = to_attr(c["cfg"])
