@@ -206,6 +206,21 @@ int mnr_scatter_rows(const mnr_row_field_t* fields /*host*/, int n_fields, const
 int mnr_replay_insert(const mnr_row_field_t* fields /*host*/, int n_fields, int64_t n_rows,
                       int64_t next_p, int64_t capacity, mnr_stream_t stream);
 
+/* The replay ring as ONE array of 128 B-aligned transition records (C, rec_floats), rec_floats % 32 == 0: field k (obs,
+ * next_obs, action, reward, done ...) occupies floats [rec_offsets[k], rec_offsets[k] + width) of every record, offsets
+ * multiples of 4; a 1-wide bool field keeps its byte in byte 0 of its slot.  The reference's five arrays
+ * (mineral/buffers/simple_replay.py:4-16) become strided views of this array, so a uniform sample reads whole cache lines.
+ *   mnr_replay_insert_records: fields[k].src = incoming (n_rows, width) array, kind MNR_ROW_F32 | MNR_ROW_U8 (bool done) |
+ *       MNR_ROW_F32_TO_BOOL; ring slots by the reference's wrap rule (simple_replay.py:32-71) like mnr_replay_insert.
+ *   mnr_replay_sample_records: out rows i < n_idx <- record idx[i] (simple_replay.py:73-85): fields[k].dst (+ dst_ld) with
+ *       kind MNR_ROW_F32 | MNR_ROW_BOOL_TO_F32 (done.float()) | MNR_ROW_F32_NORMALIZE (fused obs normalise + clamp);
+ *       records are staged in shared memory by one cp.async.bulk per row (TMA), 32 rows per CTA. */
+int mnr_replay_insert_records(const mnr_row_field_t* fields /*host*/, const int* rec_offsets /*host*/, int n_fields,
+                              float* records, int rec_floats, int64_t n_rows, int64_t next_p, int64_t capacity,
+                              mnr_stream_t stream);
+int mnr_replay_sample_records(const mnr_row_field_t* fields /*host*/, const int* rec_offsets /*host*/, int n_fields,
+                              const float* records, int rec_floats, const int64_t* idx, int64_t n_idx, mnr_stream_t stream);
+
 /* N-step FIFO push (mineral/buffers/nstep_replay.py:29-94) as a true window, no re-concatenation.
  * in_*: (N,S,..) this call's transitions (obs/next_obs width O, action width A, reward 1, done 1).
  * win_*_in: previous window (N,n,..) oldest first; win_*_out: window after the call (distinct memory).

@@ -168,6 +168,8 @@ SIGNATURES = {
     "mnr_soft_update": (i32, [vp, vp, i64, f32, f32, vp]),
     "mnr_td_target": (i32, [C.POINTER(CriticSet), i32, vp, vp, vp, f32, f32, vp, i64, vp]),
     "mnr_distl_projection": (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i32, vp, i64, vp]),
+    "mnr_replay_insert_records": (i32, [vp, vp, i32, vp, i32, i64, i64, i64, vp]),
+    "mnr_replay_sample_records": (i32, [vp, vp, i32, vp, i32, vp, i64, vp]),
     "mnr_distl_workspace_bytes": (sz, []),
     "mnr_distl_target": (i32, [C.POINTER(CriticSet), i32, vp, vp, vp, f32, f32, f32, f32, i32, vp, i64, vp]),
     "mnr_distl_bce_fwd_bwd": (i32, [C.POINTER(CriticSet), i32, vp, i64, i32, vp, vp, sz, vp]),

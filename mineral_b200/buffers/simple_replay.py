@@ -1,6 +1,12 @@
 """Circular replay buffer on the C-ABI row kernels.  Mirrors mineral/buffers/simple_replay.py:4-85
 (same ctor, attributes `next_p / if_full / cur_capacity / capacity / buf_*`, same wrap rule, indices
-drawn with `torch.randint` so sampling is bit-identical given the same generator state)."""
+drawn with `torch.randint` so sampling is bit-identical given the same generator state).
+
+Layout (round 2): ONE ring of 128 B-aligned transition records `(C, R)` f32 -
+`[obs (pad4) | next_obs (pad4) | action (pad4) | reward | done | pad]`, Ant: 96 floats = three cache lines - and the
+reference's five arrays `buf_obs / buf_action / buf_next_obs / buf_reward / buf_done` are strided VIEWS of it with the
+reference's shapes and dtypes (`(C, *shape)` f32, `(C, 1)` bool), so indexing them works as before while a uniform sample
+reads whole lines (csrc/replay_records.cu: one TMA bulk copy per sampled row, staged in shared memory)."""
 
 import math
 
@@ -10,20 +16,46 @@ from .. import ops
 from .._native import ROW_BOOL_TO_F32, ROW_F32, ROW_F32_NORMALIZE, ROW_F32_TO_BOOL, ROW_U8
 
 
-def create_buffer(capacity, obs_space, action_dim, device='cuda'):
-    """simple_replay.py:4-16: f32 obs/action/reward/next_obs, BOOL done."""
-    if isinstance(capacity, int):
-        capacity = (capacity,)
-    buf_obs = {k: torch.empty((*capacity, *v), dtype=torch.float32, device=device) for k, v in obs_space.items()}
-    buf_action = torch.empty((*capacity, int(action_dim)), dtype=torch.float32, device=device)
-    buf_reward = torch.empty((*capacity, 1), dtype=torch.float32, device=device)
-    buf_next_obs = {k: torch.empty((*capacity, *v), dtype=torch.float32, device=device) for k, v in obs_space.items()}
-    buf_done = torch.empty((*capacity, 1), dtype=torch.bool, device=device)
-    return buf_obs, buf_action, buf_next_obs, buf_reward, buf_done
-
-
 def _width(shape):
     return int(math.prod(shape)) if len(shape) else 1
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+def record_layout(obs_space, action_dim):
+    """-> (offsets {('obs', k) | ('next_obs', k) | 'action' | 'reward' | 'done': first float}, floats per record)."""
+    off, o = {}, 0
+    for part in ('obs', 'next_obs'):
+        for k, v in obs_space.items():
+            off[(part, k)] = o
+            o += _pad4(_width(v))
+        if part == 'obs':
+            pass
+    off['action'] = o
+    o += _pad4(int(action_dim))
+    off['reward'] = o
+    o += 4
+    off['done'] = o
+    o += 4
+    return off, (o + 31) // 32 * 32
+
+
+def create_buffer(capacity, obs_space, action_dim, device='cuda', return_records=False):
+    """simple_replay.py:4-16: f32 obs / action / reward / next_obs, BOOL done - as views of one record ring."""
+    if not isinstance(capacity, int):
+        (capacity,) = capacity
+    off, R = record_layout(obs_space, action_dim)
+    rec = torch.zeros((capacity, R), dtype=torch.float32, device=device)
+    buf_obs = {k: rec[:, off[('obs', k)]:off[('obs', k)] + _width(v)].unflatten(1, tuple(v)) for k, v in obs_space.items()}
+    buf_next_obs = {k: rec[:, off[('next_obs', k)]:off[('next_obs', k)] + _width(v)].unflatten(1, tuple(v)) for k, v in obs_space.items()}
+    buf_action = rec[:, off['action']:off['action'] + int(action_dim)]
+    buf_reward = rec[:, off['reward']:off['reward'] + 1]
+    d = off['done'] * 4
+    buf_done = rec.view(torch.uint8)[:, d:d + 1].view(torch.bool)   # byte 0 of the done slot
+    out = (buf_obs, buf_action, buf_next_obs, buf_reward, buf_done)
+    return out + (rec, off) if return_records else out
 
 
 class ReplayBuffer:
@@ -35,29 +67,31 @@ class ReplayBuffer:
         self.if_full = False
         self.cur_capacity = 0
         self.capacity = int(capacity)
-        ret = create_buffer(self.capacity, obs_space, action_dim, device=device)
-        self.buf_obs, self.buf_action, self.buf_next_obs, self.buf_reward, self.buf_done = ret
+        ret = create_buffer(self.capacity, obs_space, action_dim, device=device, return_records=True)
+        self.buf_obs, self.buf_action, self.buf_next_obs, self.buf_reward, self.buf_done, self.records, self._off = ret
 
     @torch.no_grad()
     def add_to_buffer(self, trajectory):
         """Ring insert, one launch for all fields (simple_replay.py:32-71)."""
         obs, actions, rewards, next_obs, dones = trajectory
         n = rewards.numel()
-        fields = []
+        rec, off = self.records, self._off
+        fields, offsets = [], []
         for k in self.buf_obs:
-            fields.append((obs[k].contiguous(), self.buf_obs[k], _width(self.obs_space[k]), ROW_F32))
-        fields.append((actions.contiguous(), self.buf_action, self.action_dim, ROW_F32))
-        fields.append((rewards.contiguous(), self.buf_reward, 1, ROW_F32))
+            fields.append((obs[k].contiguous(), rec, _width(self.obs_space[k]), ROW_F32)), offsets.append(off[('obs', k)])
+        fields.append((actions.contiguous(), rec, self.action_dim, ROW_F32)), offsets.append(off['action'])
+        fields.append((rewards.contiguous(), rec, 1, ROW_F32)), offsets.append(off['reward'])
         for k in self.buf_next_obs:
-            fields.append((next_obs[k].contiguous(), self.buf_next_obs[k], _width(self.obs_space[k]), ROW_F32))
+            fields.append((next_obs[k].contiguous(), rec, _width(self.obs_space[k]), ROW_F32)), offsets.append(off[('next_obs', k)])
         dones = dones.contiguous()
         if dones.dtype == torch.float32:
-            fields.append((dones, self.buf_done, 1, ROW_F32_TO_BOOL))  # dones.bool(), simple_replay.py:39
+            fields.append((dones, rec, 1, ROW_F32_TO_BOOL))  # dones.bool(), simple_replay.py:39
         elif dones.dtype in (torch.bool, torch.uint8):
-            fields.append((dones, self.buf_done, 1, ROW_U8))
+            fields.append((dones, rec, 1, ROW_U8))
         else:
             raise TypeError(f'dones dtype {dones.dtype}')
-        ops.replay_insert(fields, n, self.next_p, self.capacity)
+        offsets.append(off['done'])
+        ops.replay_insert_records(fields, offsets, rec, n, self.next_p, self.capacity)
 
         p = self.next_p + n
         if p > self.capacity:
@@ -90,20 +124,21 @@ class ReplayBuffer:
 
         def ld(t):
             return 0 if t.is_contiguous() else int(t.stride(0))
-        kind = ROW_F32
-        fields = []
+        rec, off = self.records, self._off
+        fields, offsets = [], []
         for k in self.buf_obs:
             w = _width(self.obs_space[k])
             if obs_rms is not None and hasattr(obs_rms[k], 'running_mean'):
                 m, d = obs_rms[k]._prepare()
                 lo, hi = obs_rms[k].clamp_range if obs_rms[k].with_clamp else (1.0, -1.0)
-                fields.append((self.buf_obs[k], obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(obs[k])))
-                fields.append((self.buf_next_obs[k], next_obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(next_obs[k])))
+                fields.append((rec, obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(obs[k])))
+                fields.append((rec, next_obs[k], w, ROW_F32_NORMALIZE, m, d, lo, hi, ld(next_obs[k])))
             else:
-                fields.append((self.buf_obs[k], obs[k], w, kind, None, None, None, None, ld(obs[k])))
-                fields.append((self.buf_next_obs[k], next_obs[k], w, kind, None, None, None, None, ld(next_obs[k])))
-        fields.append((self.buf_action, action, self.action_dim, ROW_F32, None, None, None, None, ld(action)))
-        fields.append((self.buf_reward, reward, 1, ROW_F32))
-        fields.append((self.buf_done, done, 1, ROW_BOOL_TO_F32))
-        ops.gather_rows(fields, idx=indices.to(self.buf_action.device))
+                fields.append((rec, obs[k], w, ROW_F32, None, None, None, None, ld(obs[k])))
+                fields.append((rec, next_obs[k], w, ROW_F32, None, None, None, None, ld(next_obs[k])))
+            offsets += [off[('obs', k)], off[('next_obs', k)]]
+        fields.append((rec, action, self.action_dim, ROW_F32, None, None, None, None, ld(action))), offsets.append(off['action'])
+        fields.append((rec, reward, 1, ROW_F32)), offsets.append(off['reward'])
+        fields.append((rec, done, 1, ROW_BOOL_TO_F32)), offsets.append(off['done'])
+        ops.replay_sample_records(fields, offsets, rec, indices.to(rec.device))
         return obs, action, reward, next_obs, done

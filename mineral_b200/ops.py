@@ -185,6 +185,20 @@ def replay_insert(fields, n_rows, next_p, capacity):
     check(lib.mnr_replay_insert(_row_fields(fields), len(fields), n_rows, next_p, capacity, stream()), "mnr_replay_insert")
 
 
+def replay_insert_records(fields, offsets, records, n_rows, next_p, capacity):
+    """fields as in replay_insert (dst ignored: pass the records tensor); offsets: first float of each field in a record."""
+    arr = (C.c_int32 * len(offsets))(*offsets)
+    check(lib.mnr_replay_insert_records(_row_fields(fields), arr, len(fields), ptr(records, F32, "records"), records.shape[1], n_rows, next_p,
+                                        capacity, stream()), "mnr_replay_insert_records")
+
+
+def replay_sample_records(fields, offsets, records, idx):
+    """fields as in gather_rows (src ignored: pass the records tensor); one TMA-staged launch for the whole batch."""
+    arr = (C.c_int32 * len(offsets))(*offsets)
+    check(lib.mnr_replay_sample_records(_row_fields(fields), arr, len(fields), ptr(records, F32, "records"), records.shape[1],
+                                        ptr(idx, I64, "idx"), idx.numel(), stream()), "mnr_replay_sample_records")
+
+
 def nstep_push(inp, win_in, win_out, out, gammas, N, S, O, A, nstep, count_before):
     def _in(d, f32_done):
         return nv.NStepIn(ptr(d["obs"], F32).value, ptr(d["act"], F32).value, ptr(d["rew"], F32).value,

@@ -327,3 +327,51 @@ def test_unsupported_configs_fail_at_construction():
         mutate(cfg)
         with pytest.raises(err):
             PPO(cfg, env=SynthEnv(N, O, A, T))
+
+
+# ------------------------------------------------------------------------------------------------
+# K3c / K3d at cfg4: a 4 M-transition ring of 128 B-aligned records
+# ------------------------------------------------------------------------------------------------
+def test_replay_ring_cfg4_four_million_transitions():
+    """BASELINE.json configs[3]: 4 M transitions (1.54 GB of 384 B records), inserts of 64x32 and 4096x1 rows across the wrap
+    point, uniform samples of 8192 with the obs normalisation fused - bit-exact against indexing the reference-shaped views."""
+    from mineral_b200.buffers import ReplayBuffer
+    from mineral_b200.common.normalizers import RunningMeanStd
+
+    O, A, C = 37, 8, 4_000_000
+    rb = ReplayBuffer({"obs": (O,)}, A, C, device=DEV)
+    assert rb.records.shape == (C, 96) and rb.buf_obs["obs"].shape == (C, O) and rb.buf_done.dtype == torch.bool
+    g = torch.Generator(device=DEV).manual_seed(1)
+    rb.records.normal_(generator=g)
+    rb.buf_done.copy_(torch.rand(C, 1, device=DEV, generator=g) < 0.1)
+    rb.next_p, rb.if_full, rb.cur_capacity = C - 1000, True, C          # a full ring about to wrap
+    for rows in (64 * 32, 4096):
+        tr = ({"obs": torch.randn(rows, O, device=DEV, generator=g) * 3 + 1}, torch.randn(rows, A, device=DEV, generator=g),
+              torch.randn(rows, 1, device=DEV, generator=g), {"obs": torch.randn(rows, O, device=DEV, generator=g)},
+              (torch.rand(rows, 1, device=DEV, generator=g) < 0.1).float())   # float dones, as SAC passes them
+        before = rb.next_p
+        rb.add_to_buffer(tr)
+        slots = (before + torch.arange(rows, device=DEV)) % C
+        assert rb.next_p == (before + rows) % C
+        assert torch.equal(rb.buf_obs["obs"][slots], tr[0]["obs"]) and torch.equal(rb.buf_next_obs["obs"][slots], tr[3]["obs"])
+        assert torch.equal(rb.buf_action[slots], tr[1]) and torch.equal(rb.buf_reward[slots], tr[2])
+        assert torch.equal(rb.buf_done[slots], tr[4].bool())
+    rms = torch.nn.ModuleDict({"obs": RunningMeanStd((O,), eps=1e-4, with_clamp=True, initial_count="eps")}).to(DEV)
+    rms["obs"].update(rb.buf_obs["obs"][:65536])
+    ld = (O + A + 3) // 4 * 4
+    for seed in range(8):
+        torch.manual_seed(seed)
+        idx = torch.randint(rb.cur_capacity, (8192,), device=DEV)
+        torch.manual_seed(seed)
+        obs, act, rew, nobs, done = rb.sample_batch(8192, device=DEV, obs_rms=rms)      # draws the same indices itself
+        eq(obs["obs"], rms["obs"].normalize(rb.buf_obs["obs"][idx]).cpu(), "fused normalised obs")
+        eq(nobs["obs"], rms["obs"].normalize(rb.buf_next_obs["obs"][idx]).cpu(), "fused normalised next_obs")
+        eq(act, rb.buf_action[idx].cpu(), "action"), eq(rew, rb.buf_reward[idx].cpu(), "reward")
+        eq(done, rb.buf_done[idx].float().cpu(), "done")
+        plain = rb.sample_batch(8192, device=DEV, indices=idx)                           # raw observations
+        eq(plain[0]["obs"], rb.buf_obs["obs"][idx].cpu(), "raw obs")
+    # straight into the padded critic-input buffers (SAC / DDPG): obs | action column blocks, pad columns untouched
+    xc, xn = torch.zeros(8192, ld, device=DEV), torch.zeros(8192, ld, device=DEV)
+    rb.sample_batch(8192, device=DEV, indices=idx, obs_rms=rms, out=dict(obs={"obs": xc[:, :O]}, next_obs={"obs": xn[:, :O]}, action=xc[:, O:O + A]))
+    eq(xc[:, :O].contiguous(), obs["obs"].cpu(), "strided obs"), eq(xc[:, O:O + A].contiguous(), act.cpu(), "strided action")
+    assert xc[:, O + A:].abs().max().item() == 0 and xn[:, O:].abs().max().item() == 0

@@ -17,6 +17,7 @@ sys.path.insert(0, ROOT)
 from mineral_b200 import ops  # noqa: E402
 from mineral_b200.agents.ppo.experience import ExperienceBuffer  # noqa: E402
 from mineral_b200.buffers import NStepReplay, ReplayBuffer  # noqa: E402
+from mineral_b200.common.normalizers import RunningMeanStd  # noqa: E402
 
 DEV = "cuda:0"
 try:
@@ -119,9 +120,15 @@ def main():
         def ins():
             rb.next_p = C - n // 2
             rb.add_to_buffer(traj)
-        row("row_move_kernel<ring> insert", f"cfg4 {n} rows", 2 * (8 * O + 4 * A + 8) * n, ins)
+        row("insert_records_kernel (ring insert)", f"cfg4 {n} rows", 2 * (8 * O + 4 * A + 8) * n, ins,
+            "algorithmic bytes as SURVEY 8(d) (666 B/row); the ring stores 384 B records")
+    rms = torch.nn.ModuleDict({"obs": RunningMeanStd((O,), eps=1e-4, with_clamp=True, initial_count="eps")}).to(DEV)
+    rms["obs"].update(rb.buf_obs["obs"][:65536])
     for bs in (8192, 65536):
-        row("row_move_kernel<gather> sample", f"cfg4 batch {bs}", 677 * bs, lambda: rb.sample_batch(bs, DEV), "random 148 B rows out of 1.33 GB; includes torch.randint")
+        idx = torch.randint(C, (bs,), device=DEV)
+        row("sample_records_kernel (uniform sample + normalise)", f"cfg4 batch {bs}", 677 * bs, lambda: rb.sample_batch(bs, DEV, indices=idx, obs_rms=rms),
+            "random 384 B records (three 128 B lines) out of 1.54 GB, one TMA bulk copy per row; index tensor given (torch.randint excluded); "
+            "algorithmic bytes as SURVEY 8(d) (677 B/row)")
     json.dump(dict(peak_gbs=PEAK, peak_source=PEAK_SRC, timing="CUDA events, 256 MiB L2 read-flush before every launch, mean of best 75%", rows=ROWS), sys.stdout, indent=1)
 
 
