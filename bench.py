@@ -413,6 +413,14 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: mineral_b200 has no CPU path"
     torch.cuda.set_device(local_rank)
+    numa = None
+    try:   # pin this rank's host threads (and so its pinned staging buffers) to the CPUs next to its GPU: with N ranks uploading
+        import pynvml   # their rollouts at once, a remote-socket staging buffer is what the e2e number pays for
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        numa = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
     dev = f"cuda:{local_rank}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -559,6 +567,21 @@ def main():
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / (e_ms.item() / 1e3)
+
+    # ---- N > 1: where the fused exchange kernel spends its time (MNR_PEER_TRACE=1: globaltimer stamps of CTA 0) ----
+    peer_breakdown = None
+    if world > 1 and getattr(agent.optim, "trace", None) is not None:
+        tr = agent.optim.trace.cpu().view(64, 8).double()
+        ok = (tr[:, 5] > tr[:, 0]) & (tr[:, 0] > 0)
+        if ok.any():
+            d = tr[ok]
+            peer_breakdown = {"steps_sampled": int(ok.sum()), "unit": "us", "rank": rank,
+                              "start_barrier_wait": float((d[:, 1] - d[:, 0]).mean() / 1e3), "peer_reads_and_norm": float((d[:, 2] - d[:, 1]).mean() / 1e3),
+                              "grid_barrier": float((d[:, 3] - d[:, 2]).mean() / 1e3), "adam": float((d[:, 4] - d[:, 3]).mean() / 1e3),
+                              "end_barrier_and_clear": float((d[:, 5] - d[:, 4]).mean() / 1e3), "whole_kernel": float((d[:, 5] - d[:, 0]).mean() / 1e3),
+                              "nvlink_bytes_read_per_step": (world - 1) * (agent.optim.flat.numel() + 32) * 4,
+                              "how": "%globaltimer of CTA 0, thread 0 inside reduce_clip_adam_kernel<0> over the last 64 optimizer steps; ncu cannot wrap "
+                                     "a multi-rank command (its kernel replay would re-enter the cross-GPU spin barriers)"}
 
     # ---- N > 1: numerical self-check of the multi-GPU path (untimed) ----
     mgp = None
@@ -838,6 +861,11 @@ def main():
         line["recipes"] = recipes
     if mgp is not None:
         line["multi_gpu_parity"] = mgp
+    if peer_breakdown is not None:
+        line["peer_kernel_breakdown"] = peer_breakdown
+    if world > 1:
+        line["config"]["exchange_barriers_per_step"] = 2 if os.environ.get("MNR_PEER_END_BARRIER", "0") == "1" else 1
+        line["config"]["host_threads_pinned_near_gpu"] = numa
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -557,6 +557,18 @@ int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm /*host*/, size_t grad_
                               mnr_optim_state_t* st, float* tail_out, int kl_index, float* grad_norm_out,
                               void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
+/* Same with PING-PONG gradient buffers: consecutive optimizer steps write their gradients into two regions of the peer
+ * buffer in turn.  A rank that has passed this step's start barrier has left the previous step's kernel, so nobody still
+ * reads the previous step's region: it is cleared here (`zero_offset`, 0 = none) and the second cross-GPU barrier of the
+ * step is skipped (`end_barrier` = 0; it must be 1 - with zero_grad as wanted - on the last step of an update, whose
+ * region the next update's first backward overwrites).  `trace` (may be NULL): 8 x 64 u64 of globaltimer stamps of CTA 0 -
+ * kernel start, after the start barrier, after the peer reads, after the grid barrier, after Adam, end; slot = step % 64. */
+int mnr_peer_reduce_clip_adam_pp(const mnr_peer_comm_t* comm /*host*/, size_t grad_offset, size_t zero_offset, int end_barrier,
+                                 int64_t n, int n_tail, float* reduced, float* param, float* exp_avg, float* exp_avg_sq,
+                                 float max_norm, float beta1, float beta2, float eps, float weight_decay, int decoupled,
+                                 int zero_grad, mnr_optim_state_t* st, float* tail_out, int kl_index, float* grad_norm_out,
+                                 unsigned long long* trace, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
+
 /* ------------------------------------------------------------------------------------
  * 8(f)-1  rollout-side policy step (between two simulator steps).  mnr_policy_step: policy / value heads on the
  *      towers' last activations y3a / y3v (N,H) (weights as in mnr_ppo_heads_loss_fwd_bwd), Dist

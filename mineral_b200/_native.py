@@ -197,6 +197,8 @@ SIGNATURES = {
     "mnr_peer_allgather": (i32, [C.POINTER(PeerCommStruct), sz, vp, sz, vp, vp]),
     "mnr_peer_reduce_clip_adam": (i32, [C.POINTER(PeerCommStruct), sz, i64, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, i32, vp,
                                         vp, i32, vp, vp, sz, vp]),
+    "mnr_peer_reduce_clip_adam_pp": (i32, [C.POINTER(PeerCommStruct), sz, sz, i32, i64, i32, vp, vp, vp, vp, f32, f32, f32, f32, f32, i32, i32,
+                                           vp, vp, i32, vp, vp, vp, sz, vp]),
 }
 
 

@@ -76,11 +76,20 @@ class FusedAdam:
             self.flat_grad = torch.zeros(n, dtype=torch.float32, device=dev)
             self.tail = self.reduced = None
         else:
-            region = comm.tensor('grad')
-            assert region.numel() >= n + peer_tail_floats(), 'peer gradient region too small'
-            self.flat_grad = region[:n]
-            self.tail = region[n:n + peer_tail_floats()]   # this rank's loss metrics, summed by the fused kernel
+            # PING-PONG gradient regions ('grad', 'grad1'): consecutive optimizer steps write their gradients in turn, so a
+            # region is only rewritten two steps after the peers read it and the fused kernel needs ONE cross-GPU barrier per
+            # step instead of two (use_grad_buffer / step(end_barrier=...); csrc/peer.cu)
+            self._regions = [r for r in ('grad', 'grad1') if r in comm.offsets]
+            self._grad_bufs, self._tails = [], []
+            for r in self._regions:
+                region = comm.tensor(r)
+                assert region.numel() >= n + peer_tail_floats(), 'peer gradient region too small'
+                self._grad_bufs.append(region[:n])
+                self._tails.append(region[n:n + peer_tail_floats()])   # this rank's loss metrics, summed by the fused kernel
+            self._cur = 0
+            self.flat_grad, self.tail = self._grad_bufs[0], self._tails[0]
             self.reduced = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.trace = torch.zeros(512, dtype=torch.int64, device=dev) if os.environ.get('MNR_PEER_TRACE') else None
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         for p, o in zip(self.params, self.offsets):
@@ -88,20 +97,35 @@ class FusedAdam:
             view.copy_(p.data)
             p.data = view
             p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
+        if comm is not None and len(self._grad_bufs) > 1:   # the `.grad` views of both regions, built once
+            self._grad_views = [[buf[o:o + p.numel()].view_as(p) for p, o in zip(self.params, self.offsets)] for buf in self._grad_bufs]
         self.state = ops.optim_state_tensor(lr, dev)
         self.ws = torch.zeros(ops.lib.mnr_grad_norm_workspace_bytes(n), dtype=torch.uint8, device=dev)
         self.fused_ws = torch.zeros(ops.lib.mnr_fused_adam_workspace_bytes(), dtype=torch.uint8, device=dev)
         self.param_groups = [dict(lr=float(lr), betas=betas, eps=eps, weight_decay=self.weight_decay)]
 
+    def use_grad_buffer(self, i):
+        """Multi-GPU: point every parameter's `.grad` (and `flat_grad` / `tail`) at ping-pong region i & 1 for the NEXT backward
+        pass.  Host-side pointer bookkeeping only (done while the launch sequence is enqueued / captured)."""
+        if self.comm is None or len(self._grad_bufs) < 2:
+            return
+        self._prev, self._cur = self._cur, i & 1
+        self.flat_grad, self.tail = self._grad_bufs[self._cur], self._tails[self._cur]
+        for p, g in zip(self.params, self._grad_views[self._cur]):
+            p.grad = g
+
     def step(self, max_grad_norm, kl=None, grad_norm_out=None, metrics_out=None, kl_index=-1, fused=True, nan_to_num=False,
-             clipped_norm_out=None):
+             clipped_norm_out=None, end_barrier=True):
         """clip_grad_norm_ + optimizer.step + zero_grad with no host sync: ONE launch (csrc/peer.cu), which with a peer
         communicator also all-reduces the gradient and the metrics tail over NVLink (`metrics_out` receives the sums,
         the metric at `kl_index` feeds the KL accumulator).  fused=False: the two-launch form (csrc/optim.cu)."""
         if self.comm is not None:
+            pp = len(self._grad_bufs) > 1
             self.comm.reduce_clip_adam(self.flat.numel(), self.reduced, self.flat, self.exp_avg, self.exp_avg_sq, max_grad_norm,
                                        self.betas[0], self.betas[1], self.eps, self.weight_decay, self.decoupled, True, self.state,
-                                       metrics_out, kl_index, grad_norm_out, self.fused_ws)
+                                       metrics_out, kl_index, grad_norm_out, self.fused_ws, region=self._regions[self._cur],
+                                       zero_region=self._regions[1 - self._cur] if pp else None,
+                                       end_barrier=end_barrier or not pp, trace=self.trace)
         elif fused:
             ops.fused_clip_adam(self.flat, self.flat_grad, self.exp_avg, self.exp_avg_sq, max_grad_norm, self.betas[0], self.betas[1],
                                 self.eps, self.weight_decay, self.decoupled, True, self.state, kl, grad_norm_out, self.fused_ws,
@@ -241,7 +265,7 @@ class PPO(Agent):
             if self.world > 1:
                 from ...peer import PeerComm, TAIL_FLOATS
                 n_flat = sum((p.numel() + 3) // 4 * 4 for p in self.model.parameters())
-                self.comm = PeerComm({'grad': (n_flat + TAIL_FLOATS) * 4, 'stage': 1 << 20}, self.device)
+                self.comm = PeerComm({'grad': (n_flat + TAIL_FLOATS) * 4, 'grad1': (n_flat + TAIL_FLOATS) * 4, 'stage': 1 << 20}, self.device)
         self.optim = FusedAdam(self.model.parameters(), decoupled=(cfg.optim_type == 'AdamW'), comm=self.comm, **optim_kwargs)
 
         # --- PPO train params (ppo.py:63-76) ---
@@ -644,9 +668,12 @@ class _UpdateEngine:
         else:
             x_buf, x_ld = n['x'], n['x_ld']
 
+        pingpong = peer and os.environ.get('MNR_PEER_END_BARRIER', '0') != '1'   # =1: two barriers per step (A/B measurements)
         for ep in range(a.mini_epochs):
             for i in range(self.num_mb):
                 s, e = i * mb, (i + 1) * mb
+                if peer:   # this step's backward writes ping-pong gradient region step & 1
+                    a.optim.use_grad_buffer(step)
                 v = d['obses']['obs']
                 if n is not None:   # normalise + clamp into the padded (TMA-friendly) row stride; pad columns stay zero
                     ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, x_buf, x_ld)
@@ -669,8 +696,9 @@ class _UpdateEngine:
                                          self.mu_mean[step], self.sigma_mean[step])
                     self.towers.backward(x_buf, self.g_mu, self.g_ls, self.g_v)
                 # clip_grad_norm_ + Adam(W) + zero_grad: one launch; with peers also the gradient + metrics all-reduce over NVLink
-                if peer:
-                    a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7)
+                if peer:   # the last step of the update keeps the second barrier: its region is the next update's first target
+                    a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7,
+                                 end_barrier=(not pingpong) or step == self.steps - 1)
                 else:
                     a.optim.step(max_norm, kl=m[7:8], grad_norm_out=self.grad_norms[step:step + 1])
                 step += 1

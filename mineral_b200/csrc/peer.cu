@@ -132,6 +132,13 @@ struct AdamArgs {
   double* parts;                // gridDim.x doubles
   unsigned long long* counter;  // grid barrier
   const SplitTable* split;      // in the workspace; count == 0: nothing to split
+  // world > 1, ping-pong gradient buffers (mnr_peer_reduce_clip_adam_pp): the buffer of the PREVIOUS step is cleared here
+  // (every peer passed this step's start barrier, so it has finished reading it) and the end barrier can be skipped
+  float* zero_other;            // n floats (+ tail) of the local buffer used one step earlier, or NULL
+  int end_barrier;              // 1: peers-done-reading barrier before this step's buffer is released (needed on the last
+                                // step of an update, whose buffer the next update's first backward may overwrite)
+  unsigned long long* trace;    // optional: 8 x 64 globaltimer stamps of CTA 0 (start, after start barrier, after the
+                                // peer reads, after the grid barrier, after Adam, end), slot = step % 64
 };
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, float clip, float beta1, float beta2, float eps,
@@ -172,6 +179,8 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   const int step = a.st->step + 1;
   const double lr = a.st->lr;
 
+  unsigned long long* tr = (WORLD != 1 && a.trace && blockIdx.x == 0 && tid == 0) ? a.trace + (size_t)((step - 1) & 63) * 8 : nullptr;
+  if (tr) tr[0] = globaltimer_ns();
   uint32_t flag = 0;
   if (WORLD != 1) {
     SignalPad* mine = reinterpret_cast<SignalPad*>(c.base[c.rank]);
@@ -181,6 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     if (__ldcg(&mine->error) != 0u) return;
     flag = mine->flag[blockIdx.x] + 1u;
     peer_barrier<false>(c, flag);  // every rank's backward has finished writing its gradient
+    if (tr) tr[1] = globaltimer_ns();
   }
 
   // ---- phase 1: sum over ranks (fixed order), park the result, accumulate the squared norm ----
@@ -213,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
       if (a.tail_out) a.tail_out[tid] = s;
     }
   }
+  if (tr) tr[2] = globaltimer_ns();
   const double wsum = mnr::warp_sum((double)acc);
   if ((tid & 31) == 0) s_w[tid >> 5] = wsum;
   __syncthreads();
@@ -222,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     a.parts[blockIdx.x] = s;
   }
   mnr::grid_barrier(a.counter);
+  if (tr) tr[3] = globaltimer_ns();
 
   // A barrier spin of THIS launch timed out in some CTA (a dead or diverged peer): the sums above hold stale or partial
   // peer data.  The error word was written before the grid barrier, so every CTA sees it here and skips phases 2-4:
@@ -310,15 +322,21 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     }
   }
 
+  if (tr) tr[4] = globaltimer_ns();
   // ---- phase 4: peers are done reading my gradient -> it may be cleared / rewritten ----
   if (WORLD != 1) {
-    peer_barrier<true>(c, flag);
+    if (a.end_barrier) peer_barrier<true>(c, flag);
     if (tid == 0) reinterpret_cast<SignalPad*>(c.base[c.rank])->flag[blockIdx.x] = flag;
   }
   if (a.zero_grad) {
     float4* g4 = reinterpret_cast<float4*>(a.grad);
     for (int64_t i = first; i < n4; i += stride) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (WORLD != 1 && a.zero_other) {   // the previous step's buffer: every peer left that step before this one's start barrier
+    float4* g4 = reinterpret_cast<float4*>(a.zero_other);
+    for (int64_t i = first; i < n4; i += stride) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tr) tr[5] = globaltimer_ns();
 }
 
 // all-gather of a small payload: block b moves slice b of every rank
@@ -454,6 +472,7 @@ int fill_adam(AdamArgs& a, float* param, float* exp_avg, float* exp_avg_sq, int6
   a.parts = reinterpret_cast<double*>(static_cast<unsigned char*>(workspace) + kWsHeader);
   a.split = reinterpret_cast<const SplitTable*>(static_cast<unsigned char*>(workspace) + kSplitTableOffset);
   a.reduced = nullptr, a.grad = nullptr, a.grad_offset = 0, a.n_tail = 0, a.tail_out = nullptr, a.kl_index = -1, a.kl = nullptr;
+  a.zero_other = nullptr, a.end_barrier = 1, a.trace = nullptr;
   return MNR_OK;
 }
 }  // namespace
@@ -477,11 +496,11 @@ extern "C" int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, fl
   MNR_LAUNCH_RESULT();
 }
 
-extern "C" int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm, size_t grad_offset, int64_t n, int n_tail, float* reduced,
-                                         float* param, float* exp_avg, float* exp_avg_sq, float max_norm, float beta1, float beta2,
-                                         float eps, float weight_decay, int decoupled, int zero_grad, mnr_optim_state_t* st,
-                                         float* tail_out, int kl_index, float* grad_norm_out, void* workspace,
-                                         size_t workspace_bytes, mnr_stream_t stream) {
+extern "C" int mnr_peer_reduce_clip_adam_pp(const mnr_peer_comm_t* comm, size_t grad_offset, size_t zero_offset, int end_barrier, int64_t n,
+                                            int n_tail, float* reduced, float* param, float* exp_avg, float* exp_avg_sq, float max_norm,
+                                            float beta1, float beta2, float eps, float weight_decay, int decoupled, int zero_grad,
+                                            mnr_optim_state_t* st, float* tail_out, int kl_index, float* grad_norm_out,
+                                            unsigned long long* trace, void* workspace, size_t workspace_bytes, mnr_stream_t stream) {
   MNR_CHECK_PTR(comm); MNR_CHECK_PTR(reduced);
   AdamArgs a;
   int rc = fill_adam(a, param, exp_avg, exp_avg_sq, n, max_norm, beta1, beta2, eps, weight_decay, decoupled, zero_grad, st,
@@ -491,10 +510,24 @@ extern "C" int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm, size_t gra
   rc = make_comm(comm, c);
   if (rc != MNR_OK) return rc;
   if (grad_offset % 16 != 0 || grad_offset < MNR_PEER_SIGNAL_BYTES || n_tail < 0 || n_tail > 32 || kl_index >= n_tail) return MNR_ESHAPE;
-  if (!mnr_aligned(reduced, 16)) return MNR_EALIGN;
+  if (zero_offset != 0 && (zero_offset % 16 != 0 || zero_offset < MNR_PEER_SIGNAL_BYTES || zero_offset == grad_offset)) return MNR_ESHAPE;
+  if (!end_barrier && zero_grad) return MNR_ESHAPE;   // this step's buffer may only be cleared once the peers have read it
+  if (!mnr_aligned(reduced, 16) || (trace && !mnr_aligned(trace, 8))) return MNR_EALIGN;
   a.reduced = reduced, a.grad_offset = grad_offset, a.n_tail = n_tail, a.tail_out = tail_out, a.kl_index = kl_index;
   a.grad = reinterpret_cast<float*>(c.base[c.rank] + grad_offset);
+  a.zero_other = zero_offset ? reinterpret_cast<float*>(c.base[c.rank] + zero_offset) : nullptr;
+  a.end_barrier = end_barrier ? 1 : 0, a.trace = trace;
   const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<0>, dim3(adam_grid(n)), dim3(kThreads), 0, mnr_cs(stream), c, a);
   if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_peer_reduce_clip_adam(const mnr_peer_comm_t* comm, size_t grad_offset, int64_t n, int n_tail, float* reduced,
+                                         float* param, float* exp_avg, float* exp_avg_sq, float max_norm, float beta1, float beta2,
+                                         float eps, float weight_decay, int decoupled, int zero_grad, mnr_optim_state_t* st,
+                                         float* tail_out, int kl_index, float* grad_norm_out, void* workspace,
+                                         size_t workspace_bytes, mnr_stream_t stream) {
+  return mnr_peer_reduce_clip_adam_pp(comm, grad_offset, 0, 1, n, n_tail, reduced, param, exp_avg, exp_avg_sq, max_norm, beta1, beta2, eps,
+                                      weight_decay, decoupled, zero_grad, st, tail_out, kl_index, grad_norm_out, nullptr, workspace,
+                                      workspace_bytes, stream);
 }

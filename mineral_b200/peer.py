@@ -95,13 +95,16 @@ class PeerComm:
         return out
 
     def reduce_clip_adam(self, n, reduced, param, exp_avg, exp_avg_sq, max_norm, beta1, beta2, eps, weight_decay, decoupled,
-                         zero_grad, st, tail_out, kl_index, norm_out, ws, region="grad"):
-        check(lib.mnr_peer_reduce_clip_adam(
-            C.byref(self.comm), self.offsets[region][0], n, TAIL_FLOATS, ptr(reduced, torch.float32), ptr(param, torch.float32),
-            ptr(exp_avg, torch.float32), ptr(exp_avg_sq, torch.float32), max_norm, beta1, beta2, eps, weight_decay,
-            1 if decoupled else 0, 1 if zero_grad else 0, ptr(st, torch.uint8), ptr(tail_out, torch.float32, allow_none=True),
-            kl_index, ptr(norm_out, torch.float32, allow_none=True), ptr(ws, torch.uint8), ws.numel(), stream()),
-            "mnr_peer_reduce_clip_adam")
+                         zero_grad, st, tail_out, kl_index, norm_out, ws, region="grad", zero_region=None, end_barrier=True, trace=None):
+        """region: where this step's gradients sit; zero_region: the region of the previous step (ping-pong), cleared after
+        the start barrier; end_barrier=False skips the second cross-GPU barrier (legal with ping-pong regions, except on the
+        last step of an update); trace: optional (512,) int64 device tensor receiving globaltimer stamps of CTA 0."""
+        check(lib.mnr_peer_reduce_clip_adam_pp(
+            C.byref(self.comm), self.offsets[region][0], self.offsets[zero_region][0] if zero_region else 0, 1 if end_barrier else 0, n,
+            TAIL_FLOATS, ptr(reduced, torch.float32), ptr(param, torch.float32), ptr(exp_avg, torch.float32), ptr(exp_avg_sq, torch.float32),
+            max_norm, beta1, beta2, eps, weight_decay, 1 if decoupled else 0, 1 if (zero_grad and end_barrier) else 0, ptr(st, torch.uint8),
+            ptr(tail_out, torch.float32, allow_none=True), kl_index, ptr(norm_out, torch.float32, allow_none=True),
+            ptr(trace, torch.int64, allow_none=True), ptr(ws, torch.uint8), ws.numel(), stream()), "mnr_peer_reduce_clip_adam_pp")
 
     def error(self):
         """Synchronous host read: non-zero if a cross-GPU wait timed out (a peer died or diverged)."""
