@@ -666,6 +666,17 @@ int make_map(CUtensorMap* m, const float* base, int rows, int cols, int ld, int 
 
 constexpr int kEpiStageBytes = 8 * 32 * 33 * 4;   // >= 8 x 4 KiB boxes of the TMA-store epilogue
 
+// MNR_TC_SMALLK_BN64=1: 64-column tiles for short reductions.  MEASURED slower (round 2, whole update at cfg2: 5.76 ms against
+// 5.60 ms): twice the tiles re-read the A rows twice as often and the per-tile fixed costs double; kept as an opt-in knob.
+int small_k_bn64() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MNR_TC_SMALLK_BN64");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 // MNR_TC_TMA_STORE=0 selects the transpose + full-line-store epilogue (A/B measurements); read once
 int tma_store_enabled() {
   static int v = -1;
@@ -728,6 +739,9 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
   TcParams p;
   int tma_store = tma_store_enabled();
   p.BN = N <= 128 ? N : 128;  // 2 accumulators + the A ring share the 512 TMEM columns
+  // short reductions (first layer: K = 37 -> two k-blocks per tile) are bound by the depth of the operand ring, which tensor
+  // memory caps at 4 A slots beside two 128-column accumulators: 64-column tiles leave room for 6 stages of 32 KB
+  if (small_k_bn64() && K <= 64 && N % 64 == 0 && N >= 128) p.BN = 64;
   if (N > 128 && N % 128 != 0) return MNR_ESHAPE;
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
@@ -759,6 +773,7 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
   int tma_store = tma_store_enabled();
   const int Kr = (K + 31) / 32 * 32;
   p.BN = Kr <= 128 ? Kr : 128;
+  if (small_k_bn64() && N <= 64 && Kr % 64 == 0 && Kr >= 128) p.BN = 64;   // reduction over N <= 64: as in the forward launcher
   for (int k = 0; k < n_groups; ++k) {
     const mnr_linear_group_t& s = groups[k];
     if (!s.a || !s.b || !s.b_lo || !s.c || (act != 0 && !s.saved)) return MNR_ENULL;
