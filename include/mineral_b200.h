@@ -387,6 +387,26 @@ typedef struct {
 } mnr_tc_reduce_job_t;
 int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
 
+/* A whole 3-layer tower forward in ONE launch (csrc/tc_tower.cu): y[l] = act(y[l-1] . W_l^T + bias_l), y[-1] = x, for every
+ * group (tower), replacing MLP.forward (mineral/nets/mlp.py:25-77; both PPO towers: mineral/agents/ppo/models.py:136-151).
+ * Layer outputs go from one GEMM to the next through tensor memory; every y[l] is also written (the backward pass needs it).
+ * Same numerics as three mnr_tc_linear_fwd calls (3xTF32).  Shapes: K0 <= 64 (row strides multiples of 4 floats),
+ * widths[0] in {128, 256}, widths[1], widths[2] multiples of 32 and <= 128; anything else returns MNR_EUNSUP and
+ * mnr_tc_tower_fwd_supported() == 0 (the caller then runs the per-layer kernels). */
+typedef struct {
+  const float* x;        /* (M, K0), row stride ldx */
+  const float* w_hi[3];  /* W_l (N_l, K_l) high tf32 part, row stride ldw[l] (mnr_split_tf32) */
+  const float* w_lo[3];  /* remainder */
+  const float* bias[3];
+  float* y[3];           /* (M, N_l) contiguous */
+  int32_t ldx;           /* 0 = K0 */
+  int32_t ldw[3];        /* 0 = K_l */
+} mnr_tower_group_t;
+int mnr_tc_tower_fwd_supported(int K0, const int32_t* widths, int n_layers, int act);
+int mnr_tc_tower_fwd(const mnr_tower_group_t* groups /*host*/, int n_groups, int M, int K0, const int32_t* widths /*host*/,
+                     int n_layers, int act, mnr_stream_t stream);
+int mnr_tc_tower_trace(int enable, long long* host_out);
+
 /* Profiling aid: enable != 0 makes CTA 0 of the tensor-core kernels record clock64() at every role's wait / done
  * points; host_out (4 roles x 256 events x 2 tags int64, may be NULL) receives the last timeline. Synchronous. */
 int mnr_tc_trace(int enable, long long* host_out);

@@ -88,6 +88,11 @@ class TcReduceJob(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class TowerGroup(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("w_hi", C.c_void_p * 3), ("w_lo", C.c_void_p * 3), ("bias", C.c_void_p * 3), ("y", C.c_void_p * 3),
+                ("ldx", C.c_int32), ("ldw", C.c_int32 * 3)]
+
+
 class CriticSet(C.Structure):
     _fields_ = [("pred", C.c_void_p * 4), ("grad", C.c_void_p * 4)]
 
@@ -151,6 +156,9 @@ SIGNATURES = {
     "mnr_tc_linear_bwd_weight_partials": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
     "mnr_tc_reduce_partials": (i32, [C.POINTER(TcReduceJob), i32, vp]),
     "mnr_tc_trace": (i32, [i32, vp]),
+    "mnr_tc_tower_fwd_supported": (i32, [i32, C.POINTER(C.c_int32), i32, i32]),
+    "mnr_tc_tower_fwd": (i32, [C.POINTER(TowerGroup), i32, i32, i32, C.POINTER(C.c_int32), i32, i32, vp]),
+    "mnr_tc_tower_trace": (i32, [i32, vp]),
     "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
     "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),
     "mnr_colsum_workspace_bytes": (sz, [i32]),

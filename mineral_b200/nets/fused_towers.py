@@ -114,6 +114,9 @@ class TowerStack:
             # one split-partials workspace per layer: the split reduce of all layers is ONE launch after the last layer
             self.tc_ws = [torch.zeros(max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape), 256),
                                       dtype=torch.uint8, device=device) for l in self.lin[0]]
+        # whole-tower forward kernel: three plain (Linear -> act) layers of the shapes csrc/tc_tower.cu takes
+        self.fused_fwd = (self.use_tc and not self.normed and self.L == 3
+                          and ops.tc_tower_fwd_supported(self.in_dim, widths, self.gemm_act))
 
     def _split_weights(self):
         """W -> (hi, lo) tf32 parts for every layer of every tower, one launch per 8 matrices."""
@@ -141,6 +144,12 @@ class TowerStack:
         tc0 = self.use_tc and x_ld % 4 == 0  # TMA needs 16 B-multiple row strides for the first layer's input
         if self.use_tc and split:
             self._split_weights()
+        if tc0 and self.fused_fwd:
+            # the whole tower in one launch: layer outputs travel through tensor memory (csrc/tc_tower.cu)
+            ops.tc_tower_fwd([dict(x=x, ldx=x_ld, w_hi=[self.w_hi[i][g] for i in range(3)], w_lo=[self.w_lo[i][g] for i in range(3)],
+                                   ldw=self.w_ld, bias=[self.lin[g][i].bias.data for i in range(3)], y=[self.Y[i][g] for i in range(3)])
+                              for g in range(G)], M, self.in_dim, self.widths, self.gemm_act)
+            return
         inp = [x] * G
         for i in range(self.L):
             n, k = self.lin[0][i].weight.shape

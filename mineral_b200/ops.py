@@ -318,6 +318,23 @@ def tc_reduce_partials(jobs):
     check(lib.mnr_tc_reduce_partials(arr, len(jobs), stream()), "mnr_tc_reduce_partials")
 
 
+def tc_tower_fwd_supported(K0, widths, act):
+    w = (C.c_int32 * len(widths))(*widths)
+    return bool(lib.mnr_tc_tower_fwd_supported(K0, w, len(widths), act))
+
+
+def tc_tower_fwd(groups, M, K0, widths, act):
+    """A whole 3-layer tower forward per launch.  groups: list of dict(x=, ldx=, w_hi=[3], w_lo=[3], ldw=[3], bias=[3], y=[3])."""
+    arr = (nv.TowerGroup * len(groups))()
+    P3 = C.c_void_p * 3
+    for i, g in enumerate(groups):
+        arr[i] = nv.TowerGroup(ptr(g["x"], F32, "x").value, P3(*[ptr(t, F32).value for t in g["w_hi"]]), P3(*[ptr(t, F32).value for t in g["w_lo"]]),
+                               P3(*[ptr(t, F32).value for t in g["bias"]]), P3(*[ptr(t, F32).value for t in g["y"]]), g.get("ldx", 0),
+                               (C.c_int32 * 3)(*g.get("ldw", (0, 0, 0))))
+    w = (C.c_int32 * len(widths))(*widths)
+    check(lib.mnr_tc_tower_fwd(arr, len(groups), M, K0, w, len(widths), act, stream()), "mnr_tc_tower_fwd")
+
+
 def split_tf32(jobs):
     """jobs: list of (src (rows, cols) view with row stride src_ld, hi, lo (rows, dst_ld))."""
     arr = (nv.SplitJob * len(jobs))()

@@ -153,3 +153,49 @@ def test_simt_linear_fwd_dx_dw_thin_and_tile(M, N, K):
     again = torch.empty_like(dwa)
     ops.linear_bwd_weight([dict(a=ga, b=x, c=again, bias_grad=dba, N=N, K=K, ldb=ld)], M, 0, ws)
     assert torch.equal(again, dwa), "weight gradient is not deterministic"
+
+
+TOWER_CASES = [(4096, 37, (256, 128, 64), 1), (300, 37, (256, 128, 64), 1), (1024, 64, (128, 64, 32), 2), (2048, 20, (256, 96, 128), 0),
+               (32768, 37, (256, 128, 64), 1)]
+
+
+@pytest.mark.parametrize("M,K0,widths,act", TOWER_CASES)
+def test_tc_tower_fwd_vs_float64_and_per_layer(M, K0, widths, act):
+    """csrc/tc_tower.cu (whole tower forward in one launch, activations handed on through tensor memory) against float64
+    torch and against three mnr_tc_linear_fwd launches on the same split weights."""
+    from mineral_b200 import ops
+
+    if not ops.tc_supported() or not ops.tc_tower_fwd_supported(K0, list(widths), act):
+        pytest.skip("fused tower forward unavailable")
+    g = torch.Generator(device=DEV).manual_seed(M + K0 + sum(widths))
+    ldx = (K0 + 3) // 4 * 4
+    x = torch.randn(M, K0, device=DEV, generator=g) * 2
+    xp = _pad(x, ldx)
+    groups, refs, layered = [], [], []
+    for t in range(2):
+        k, ws, bs, his, los, lds, ys, ys2 = K0, [], [], [], [], [], [], []
+        ref = x.double()
+        for n in widths:
+            w = torch.randn(n, k, device=DEV, generator=g) / k**0.5
+            b = torch.randn(n, device=DEV, generator=g) * 0.5
+            ld = (k + 3) // 4 * 4
+            hi, lo = _split(w, ld)
+            ws.append(w), bs.append(b), his.append(hi), los.append(lo), lds.append(ld)
+            ys.append(torch.full((M, n), float("nan"), device=DEV)), ys2.append(torch.full((M, n), float("nan"), device=DEV))
+            ref = _act(ref @ w.double().T + b.double(), act)
+            refs.append(ref)
+            k = n
+        groups.append(dict(x=xp, ldx=ldx, w_hi=his, w_lo=los, ldw=lds, bias=bs, y=ys))
+        layered.append((his, los, lds, bs, ys2))
+    ops.tc_tower_fwd(groups, M, K0, list(widths), act)
+    for i, n in enumerate(widths):   # the per-layer kernels on the same operands
+        k = K0 if i == 0 else widths[i - 1]
+        ops.tc_linear_fwd([dict(a=xp if i == 0 else L[4][i - 1], b=L[0][i], b_lo=L[1][i], c=L[4][i], bias=L[3][i], N=n, K=k,
+                                lda=ldx if i == 0 else k, ldb=L[2][i]) for L in layered], M, act)
+    torch.cuda.synchronize()
+    for t in range(2):
+        for i in range(3):
+            y = groups[t]["y"][i]
+            assert torch.isfinite(y).all(), f"tower {t} layer {i}: non-finite output"
+            scale_close(y, refs[3 * t + i], 5e-6, f"tower fwd {M}x{K0}->{widths} layer {i}")
+            scale_close(y, layered[t][4][i], 2e-6, f"tower fwd vs per-layer, layer {i}")
