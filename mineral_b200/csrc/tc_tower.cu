@@ -10,15 +10,17 @@
 // AND writes its (hi, lo) tf32 parts into the ring of TMEM slots layer l+1's MMAs read their A operand from - the same
 // slots the converter warps of tc_linear.cu fill from shared memory.
 //
-// Tensor memory (512 columns):   [0,128) ACC1: one 128-column half of layer 1
-//                                [128,256) ACC2: layer 2 (N2 <= 128); layer 3's accumulator aliases it (N3 <= 128)
-//                                [256,512) A ring: 4 slots x (32 hi | 32 lo) columns = one 32-wide reduction block each
+// Tensor memory (512 columns):   [0,256)   two 128-column buffers: layer-1 half h of the CTA's t-th tile accumulates in buffer
+//                                          (h + t) & 1, layer 3 of that tile in buffer t & 1 (N3 <= 128)
+//                                [256,384) ACC2: layer 2 (N2 <= 128)
+//                                [384,512) A ring: 2 slots x (32 hi | 32 lo) columns = one 32-wide reduction block each
 // Shared memory: X tile as (hi, lo) K-major SWIZZLE_128B tiles (split in place by the converter warps; layer 1's A operand
-// is the only one read from shared memory), a 4-slot ring of 32 KiB weight blocks (hi | lo of [<=128 rows][32 floats],
-// streamed from L2 by TMA for every tile: W2 alone is 256 KiB as a split pair), 8 x 4 KiB epilogue boxes for the TMA stores.
+// is the only one read from shared memory), a 3-slot ring of 32 KiB weight blocks (hi | lo of [<=128 rows][32 floats],
+// streamed from L2 by TMA for every tile: W2 alone is 256 KiB as a split pair), 16 x 4 KiB epilogue boxes for the TMA stores.
 //
-// Order of the MMAs of one tile (h1 = N1 / 128 halves):  for each half h: L1(h) -> ACC1, then L2's reduction blocks
-// 4h..4h+3 (their A slots come from the epilogue of L1(h)) -> ACC2;  then L3's blocks (A slots from the epilogue of L2).
+// The epilogue warps bound the kernel (8 warps drain 128 x (N1 + N2 + N3) accumulator elements per tile), so the MMA
+// issue order keeps them fed: L1(t, half 1), L2(t)'s blocks as their A slots arrive from the epilogue of L1(t), then
+// L1(t+1, half 0) - its accumulator buffer is free and its epilogue can start the moment layer 3's is done -, then L3(t).
 // Warp roles (512 threads, persistent, 1 CTA/SM): 0 weight producer, 1 MMA issuer, 2 TMEM allocator, 3 X producer,
 // 4-7 X converters, 8-15 epilogue (two warps per TMEM lane quarter, alternate 32-column chunks).
 #include "tc_common.cuh"
@@ -29,12 +31,12 @@ constexpr int kThreads = 512;
 constexpr int kBM = 128, kBK = 32;
 constexpr int kTile = kBM * kBK * 4;   // 16 KiB: [128][32] f32, SWIZZLE_128B
 constexpr int kWSlot = 2 * kTile;      // weight ring slot: hi at +0, lo at +kTile
-constexpr int kWStages = 4;
-constexpr int kASlots = 4;
+constexpr int kWStages = 3;
+constexpr int kASlots = 2;
 constexpr int kMaxXkb = 2;             // K0 <= 64
 constexpr int kMaxGroups = 2;
 constexpr int kLayers = 3;
-constexpr uint32_t kAcc1 = 0, kAcc2 = 128, kARing = 256, kTmemCols = 512;
+constexpr uint32_t kAccB = 0, kAcc2 = 256, kARing = 384, kTmemCols = 512;   // two 128-column buffers | ACC2 | A ring
 constexpr int kEpiWarps = 8, kEpi0 = 8;
 
 __device__ long long g_ttrace[4 * 256 * 2];
@@ -49,6 +51,8 @@ struct alignas(64) TowerGroup {
   CUtensorMap w_hi[kLayers], w_lo[kLayers];  // W_l (N_l, K_l) pre-split: boxes [min(N_l,128) rows][32 floats]
   CUtensorMap y[kLayers];                    // Y_l (M, N_l): store boxes [32 rows][32 floats]
   const float* bias[kLayers];
+  const float* w_ptr[2 * kLayers];           // the same weight buffers as plain pointers (L2 prefetch at kernel start)
+  uint32_t w_bytes[kLayers];
 };
 
 struct TowerParams {
@@ -56,36 +60,47 @@ struct TowerParams {
   int M, K0;
   int N[kLayers];
   int n_groups, tiles_i;
+  int flags;   // bit 0: L2 prefetch of the weights at kernel start (MNR_TOWER_FLAGS, A/B measurements)
 };
 
-template <int ACT>
+// L2 prefetch of the weight buffers (one 128 B line per thread and step), kept out of line: inlined into the kernel it changed
+// the register allocation of the epilogue warps (61 -> 72 us per launch at cfg2)
+__device__ __noinline__ void prefetch_weights(const TowerParams& p, uint32_t gt, uint32_t gn) {
+  for (int gi = 0; gi < p.n_groups; ++gi)
+    for (int q = 0; q < 2 * kLayers; ++q) {
+      const char* base = reinterpret_cast<const char*>(p.g[gi].w_ptr[q]);
+      const uint32_t lines = (p.g[gi].w_bytes[q >> 1] + 127u) >> 7;
+      for (uint32_t l = gt; l < lines; l += gn) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
+    }
+}
+
+template <int ACT, bool PREFETCH>
 __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_constant__ TowerParams p) {
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t x_full, x_conv, x_empty;
   __shared__ __align__(8) uint64_t w_full[kWStages], w_empty[kWStages];
   __shared__ __align__(8) uint64_t a_full[kASlots], a_empty[kASlots];
-  __shared__ __align__(8) uint64_t acc1_full, acc1_empty, acc2_full, acc3_full, acc3_empty;
+  __shared__ __align__(8) uint64_t b_full[2], b_empty[2], acc2_full;
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias_all[kEpiWarps * 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N1 = p.N[0], N2 = p.N[1], N3 = p.N[2];
   const int h1 = N1 / 128, nkb1 = (p.K0 + kBK - 1) / kBK, nkb3 = N2 / kBK;
-  const int uses_per_tile = 4 * h1 + nkb3;            // A-slot uses: layer 2's 4*h1 reduction blocks, then layer 3's
+  const int uses_per_tile = 4 * h1 + nkb3;   // A-slot uses: layer 2's 4*h1 reduction blocks, then layer 3's
   const int n_tiles = p.tiles_i * p.n_groups;
 
   uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint8_t* xs = smem;                                   // [kb][hi 16 KiB | lo 16 KiB]
   uint8_t* ring = smem + kMaxXkb * 2 * kTile;           // kWStages x 32 KiB
-  uint8_t* boxes = ring + kWStages * kWSlot;            // 8 x 4 KiB
+  uint8_t* boxes = ring + kWStages * kWSlot;            // 8 warps x 2 x 4 KiB
 
   if (tid == 0) {
     ptx::mbar_init(&x_full, 1), ptx::mbar_init(&x_conv, 128), ptx::mbar_init(&x_empty, 1);
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&w_full[s], 1), ptx::mbar_init(&w_empty[s], 1);
     for (int s = 0; s < kASlots; ++s) ptx::mbar_init(&a_full[s], 128), ptx::mbar_init(&a_empty[s], 1);
-    ptx::mbar_init(&acc1_full, 1), ptx::mbar_init(&acc1_empty, kEpiWarps * 32);
+    for (int b = 0; b < 2; ++b) ptx::mbar_init(&b_full[b], 1), ptx::mbar_init(&b_empty[b], kEpiWarps * 32);
     ptx::mbar_init(&acc2_full, 1);
-    ptx::mbar_init(&acc3_full, 1), ptx::mbar_init(&acc3_empty, kEpiWarps * 32);
     ptx::fence_mbar_init();
   }
   if (warp == 2) ptx::tmem_alloc(&tmem_slot, kTmemCols);
@@ -95,25 +110,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
   const uint32_t tmem_base = tmem_slot;
   mnr::pdl_trigger();
   mnr::pdl_wait();
+  // Cold start: the split weights (0.4 MB per tower) were written by the optimizer kernel a whole backward pass ago and have
+  // left L2; through the 3-slot ring every first-tile block would pay a DRAM round trip.  The converter warps of all CTAs
+  // (idle until the first X tile lands) pull distinct 128 B lines of every weight buffer into L2 now.
+  if (PREFETCH && warp >= 4 && warp < 8) prefetch_weights(p, blockIdx.x * 128 + (tid - 128), gridDim.x * 128);
 
   if (warp == 0) {
     // ===== weight producer: the ring items in the order the MMA issuer consumes them ================================
     if (lane == 0) {
       uint32_t wi = 0;
+      auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int rows, int c0, int r0) {
+        const int st = wi % kWStages;
+        ptx::mbar_wait(&w_empty[st], ((wi / kWStages) & 1) ^ 1);
+        uint8_t* base = ring + (size_t)st * kWSlot;
+        ptx::mbar_expect_tx(&w_full[st], 2u * (uint32_t)rows * 128u);
+        ptx::tma_load_2d(base, hi, c0, r0, &w_full[st]);
+        ptx::tma_load_2d(base + kTile, lo, c0, r0, &w_full[st]);
+        ++wi;
+      };
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TowerGroup& g = p.g[tile / p.tiles_i];
-        auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int rows, int c0, int r0) {
-          const int st = wi % kWStages;
-          ptx::mbar_wait(&w_empty[st], ((wi / kWStages) & 1) ^ 1);
-          uint8_t* base = ring + (size_t)st * kWSlot;
-          ptx::mbar_expect_tx(&w_full[st], 2u * (uint32_t)rows * 128u);
-          ptx::tma_load_2d(base, hi, c0, r0, &w_full[st]);
-          ptx::tma_load_2d(base + kTile, lo, c0, r0, &w_full[st]);
-          ++wi;
-        };
-        for (int h = 0; h < h1; ++h) {
-          for (int kb = 0; kb < nkb1; ++kb) put(&g.w_hi[0], &g.w_lo[0], 128, kb * kBK, h * 128);
-          for (int j = 0; j < 4; ++j) put(&g.w_hi[1], &g.w_lo[1], N2, (4 * h + j) * kBK, 0);
+        if (tile == (int)blockIdx.x)
+          for (int kb = 0; kb < nkb1; ++kb) put(&g.w_hi[0], &g.w_lo[0], 128, kb * kBK, 0);
+        if (h1 == 2)
+          for (int kb = 0; kb < nkb1; ++kb) put(&g.w_hi[0], &g.w_lo[0], 128, kb * kBK, 128);
+        for (int j = 0; j < 4 * h1; ++j) put(&g.w_hi[1], &g.w_lo[1], N2, j * kBK, 0);
+        const int nxt = tile + gridDim.x;
+        if (nxt < n_tiles) {
+          const TowerGroup& gn = p.g[nxt / p.tiles_i];
+          for (int kb = 0; kb < nkb1; ++kb) put(&gn.w_hi[0], &gn.w_lo[0], 128, kb * kBK, 0);
         }
         for (int j = 0; j < nkb3; ++j) put(&g.w_hi[2], &g.w_lo[2], N3, j * kBK, 0);
       }
@@ -132,6 +157,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ===== MMA issuer ===============================================================================================
+    // Issue order: L1(0,h=0) | per tile t: L1(t,h=1), L2(t) blocks as their A slots arrive, L1(t+1,h=0), L3(t) blocks.
+    // Layer-1 half h of tile t accumulates in buffer (h + t) & 1; layer 3 of tile t in buffer t & 1 (drained by then).
     if (lane == 0) {
       const uint32_t idesc1 = ptx::idesc_tf32(kBM, 128, 0, 0), idesc2 = ptx::idesc_tf32(kBM, N2, 0, 0), idesc3 = ptx::idesc_tf32(kBM, N3, 0, 0);
       // K-major SWIZZLE_128B operand tiles (A of layer 1 and every B): 8-row groups 1 KiB apart (SBO), LBO unused (16 B)
@@ -139,74 +166,69 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
       const uint32_t desc_lo_const = (16u >> 4) << 16;
       auto kdesc = [&](uint32_t addr, int k) { return desc_hi | (uint64_t)((((addr) >> 4) | desc_lo_const) + (uint32_t)(k * 2)); };
       const uint32_t xs_u = ptx::smem_u32(xs), ring_u = ptx::smem_u32(ring);
-      const uint32_t acc1 = tmem_base + kAcc1, acc2 = tmem_base + kAcc2, aring = tmem_base + kARing;
-      uint32_t wi = 0, u = 0, it = 0, n1 = 0;   // ring item, A-slot use, tile, layer-1 half counters
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-        for (int h = 0; h < h1; ++h, ++n1) {
-          // ---- layer 1, half h -> ACC1 (A = X hi / lo from shared memory) ----
-          ptx::mbar_wait(&acc1_empty, (n1 & 1) ^ 1);
-          if (h == 0) ptx::mbar_wait(&x_conv, it & 1);
-          ptx::tc_fence_after();
-          TT_TRACE(0, it * 4 + h, 0);
-          for (int kb = 0; kb < nkb1; ++kb, ++wi) {
-            const int st = wi % kWStages;
-            ptx::mbar_wait(&w_full[st], (wi / kWStages) & 1);
-            ptx::tc_fence_after();
-            const uint32_t a_u = xs_u + (uint32_t)kb * 2u * kTile, b_u = ring_u + (uint32_t)st * kWSlot;
-            const int r_left = p.K0 - kb * kBK;
-            const int ksteps = r_left >= kBK ? kBK / 8 : (r_left + 7) / 8;   // no MMAs over TMA's zero fill
-            for (int k = 0; k < ksteps; ++k) {
-              ptx::mma_tf32(acc1, kdesc(a_u + kTile, k), kdesc(b_u, k), idesc1, (kb | k) != 0 ? 1u : 0u);  // small terms first
-              ptx::mma_tf32(acc1, kdesc(a_u, k), kdesc(b_u + kTile, k), idesc1, 1u);
-              ptx::mma_tf32(acc1, kdesc(a_u, k), kdesc(b_u, k), idesc1, 1u);
-            }
-            ptx::tc_commit(&w_empty[st]);
-          }
-          ptx::tc_commit(&acc1_full);
-          if (h == h1 - 1) ptx::tc_commit(&x_empty);
-          TT_TRACE(0, it * 4 + h, 1);
-          // ---- layer 2, reduction blocks 4h .. 4h+3 -> ACC2 (A = Y1 hi / lo from the TMEM ring) ----
-          if (h == 0) {
-            ptx::mbar_wait(&acc3_empty, (it & 1) ^ 1);   // the previous tile's layer-3 epilogue has drained ACC2 / ACC3
-            ptx::tc_fence_after();
-          }
-          for (int j = 0; j < 4; ++j, ++wi, ++u) {
-            const int as = u % kASlots, st = wi % kWStages;
-            ptx::mbar_wait(&a_full[as], (u / kASlots) & 1);
-            ptx::mbar_wait(&w_full[st], (wi / kWStages) & 1);
-            ptx::tc_fence_after();
-            if (j == 0) TT_TRACE(1, it * 4 + h, 0);
-            const uint32_t a_t = aring + (uint32_t)as * 64u, b_u = ring_u + (uint32_t)st * kWSlot;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              ptx::mma_tf32_ts(acc2, a_t + 32u + 8u * k, kdesc(b_u, k), idesc2, (h | j | k) != 0 ? 1u : 0u);
-              ptx::mma_tf32_ts(acc2, a_t + 8u * k, kdesc(b_u + kTile, k), idesc2, 1u);
-              ptx::mma_tf32_ts(acc2, a_t + 8u * k, kdesc(b_u, k), idesc2, 1u);
-            }
-            ptx::tc_commit(&w_empty[st]);
-            ptx::tc_commit(&a_empty[as]);
-          }
-          TT_TRACE(1, it * 4 + h, 1);
-        }
-        ptx::tc_commit(&acc2_full);
-        // ---- layer 3 -> ACC3 (= ACC2's columns: every chunk of ACC2 must have been drained, i.e. all its A slots are full) ----
-        for (int j = 0; j < nkb3; ++j) ptx::mbar_wait(&a_full[(u + j) % kASlots], ((u + j) / kASlots) & 1);
-        TT_TRACE(2, it, 0);
-        for (int j = 0; j < nkb3; ++j, ++wi, ++u) {
-          const int as = u % kASlots, st = wi % kWStages;
+      const uint32_t acc2 = tmem_base + kAcc2, aring = tmem_base + kARing;
+      uint32_t wi = 0, u = 0, it = 0, bc0 = 0, bc1 = 0;   // ring item, A-slot use, tile, per-buffer use counters
+      auto layer1 = [&](uint32_t t, int h) {   // layer 1, half h of this CTA's t-th tile (A = X hi / lo from shared memory)
+        const int b = (h + t) & 1;
+        ptx::mbar_wait(&b_empty[b], ((b ? bc1 : bc0) & 1) ^ 1);
+        b ? ++bc1 : ++bc0;
+        if (h == 0) ptx::mbar_wait(&x_conv, t & 1);
+        ptx::tc_fence_after();
+        TT_TRACE(0, t * 4 + h, 0);
+        const uint32_t acc = tmem_base + kAccB + 128u * b;
+        for (int kb = 0; kb < nkb1; ++kb, ++wi) {
+          const int st = wi % kWStages;
           ptx::mbar_wait(&w_full[st], (wi / kWStages) & 1);
           ptx::tc_fence_after();
-          const uint32_t a_t = aring + (uint32_t)as * 64u, b_u = ring_u + (uint32_t)st * kWSlot;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            ptx::mma_tf32_ts(acc2, a_t + 32u + 8u * k, kdesc(b_u, k), idesc3, (j | k) != 0 ? 1u : 0u);
-            ptx::mma_tf32_ts(acc2, a_t + 8u * k, kdesc(b_u + kTile, k), idesc3, 1u);
-            ptx::mma_tf32_ts(acc2, a_t + 8u * k, kdesc(b_u, k), idesc3, 1u);
+          const uint32_t a_u = xs_u + (uint32_t)kb * 2u * kTile, b_u = ring_u + (uint32_t)st * kWSlot;
+          const int r_left = p.K0 - kb * kBK;
+          const int ksteps = r_left >= kBK ? kBK / 8 : (r_left + 7) / 8;   // no MMAs over TMA's zero fill
+          for (int k = 0; k < ksteps; ++k) {
+            ptx::mma_tf32(acc, kdesc(a_u + kTile, k), kdesc(b_u, k), idesc1, (kb | k) != 0 ? 1u : 0u);  // small terms first
+            ptx::mma_tf32(acc, kdesc(a_u, k), kdesc(b_u + kTile, k), idesc1, 1u);
+            ptx::mma_tf32(acc, kdesc(a_u, k), kdesc(b_u, k), idesc1, 1u);
           }
           ptx::tc_commit(&w_empty[st]);
-          ptx::tc_commit(&a_empty[as]);
         }
-        ptx::tc_commit(&acc3_full);
+        ptx::tc_commit(&b_full[b]);
+        if (h == h1 - 1) ptx::tc_commit(&x_empty);
+        TT_TRACE(0, t * 4 + h, 1);
+      };
+      // A (hi | lo) from TMEM slot, B from the weight ring; `first`: the block that initialises the accumulator
+      auto block_ts = [&](uint32_t acc, uint32_t idesc, bool first) {
+        const int as = u % kASlots, st = wi % kWStages;
+        ptx::mbar_wait(&a_full[as], (u / kASlots) & 1);
+        ptx::mbar_wait(&w_full[st], (wi / kWStages) & 1);
+        ptx::tc_fence_after();
+        const uint32_t a_t = aring + (uint32_t)as * 64u, b_u = ring_u + (uint32_t)st * kWSlot;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ptx::mma_tf32_ts(acc, a_t + 32u + 8u * k, kdesc(b_u, k), idesc, (!first || k != 0) ? 1u : 0u);
+          ptx::mma_tf32_ts(acc, a_t + 8u * k, kdesc(b_u + kTile, k), idesc, 1u);
+          ptx::mma_tf32_ts(acc, a_t + 8u * k, kdesc(b_u, k), idesc, 1u);
+        }
+        ptx::tc_commit(&w_empty[st]);
+        ptx::tc_commit(&a_empty[as]);
+        ++wi, ++u;
+      };
+      if ((int)blockIdx.x < n_tiles) layer1(0, 0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        if (h1 == 2) layer1(it, 1);
+        // ---- layer 2 -> ACC2 (A = Y1 hi / lo from the TMEM ring).  ACC2 was drained by the previous tile's layer-2 epilogue:
+        //      every one of its chunks filled an A slot that the layer-3 blocks issued before this point have waited for ----
+        TT_TRACE(1, it, 0);
+        for (int j = 0; j < 4 * h1; ++j) block_ts(acc2, idesc2, j == 0);
+        ptx::tc_commit(&acc2_full);
+        TT_TRACE(1, it, 1);
+        if (tile + (int)gridDim.x < n_tiles) layer1(it + 1, 0);
+        // ---- layer 3 -> buffer it & 1 (layer 1, half 0 of this tile: drained long ago) ----
+        const int b = it & 1;
+        ptx::mbar_wait(&b_empty[b], ((b ? bc1 : bc0) & 1) ^ 1);
+        b ? ++bc1 : ++bc0;
+        ptx::tc_fence_after();
+        TT_TRACE(2, it, 0);
+        for (int j = 0; j < nkb3; ++j) block_ts(tmem_base + kAccB + 128u * b, idesc3, j == 0);
+        ptx::tc_commit(&b_full[b]);
         TT_TRACE(2, it, 1);
       }
     }
@@ -231,14 +253,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
     }
   } else if (warp >= kEpi0) {
     // ===== epilogue: TMEM chunk -> bias + activation -> (hi, lo) into the next layer's A slot, and the chunk itself to
-    //       HBM through a swizzled [32][32] box and one TMA tensor store ================================================
+    //       HBM through a swizzled [32][32] box and one TMA tensor store (two boxes per warp, used alternately) ==========
     const int quarter = warp & 3, half = (warp - kEpi0) >> 2, ew = warp - kEpi0;
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
-    uint8_t* box_ptr = boxes + (size_t)ew * 4096;
-    const uint32_t box = ptx::smem_u32(box_ptr);
+    uint8_t* box_ptr = boxes + (size_t)ew * 8192;
     float* s_bias = s_bias_all + ew * 32;
-    uint32_t it = 0, n1 = 0;
-    // one 32-column chunk of an accumulator.  TO_A: (hi, lo) -> A slot `use` first (the MMA issuer waits for it), store after.
+    uint32_t it = 0, nbox = 0, bc0 = 0, bc1 = 0;
+    // one 32-column chunk of an accumulator.  to_a: its (hi, lo) parts -> A slot of use `use`.
     auto chunk = [&](uint32_t acc_col, float bias_v, const CUtensorMap* ymap, int col, int row, bool to_a, uint32_t use, uint64_t* drained) {
       __syncwarp();
       s_bias[lane] = bias_v;
@@ -258,8 +279,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
         v[4 * q4] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4]) + b.x), v[4 * q4 + 1] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 1]) + b.y);
         v[4 * q4 + 2] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 2]) + b.z), v[4 * q4 + 3] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 3]) + b.w);
       }
-      if (to_a) {
-        const int as = use % kASlots;
+      const int as = use % kASlots;
+      if (to_a) {   // the two tcgen05.st complete while the box is being written below
         ptx::mbar_wait(&a_empty[as], ((use / kASlots) & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t a_t = tmem_base + lane_off + kARing + (uint32_t)as * 64u;
@@ -269,20 +290,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
 #pragma unroll
         for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(v[q] - __uint_as_float(r[q]));
         ptx::tmem_st_32x32(a_t + 32u, r);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(&a_full[as]);
       }
-      if (lane == 0) ptx::bulk_wait_read0();   // the previous store of this warp has finished reading the box
+      uint8_t* bp = box_ptr + (nbox & 1) * 4096;
+      ++nbox;
+      if (lane == 0) ptx::bulk_wait_read1();   // the store issued from this box two chunks ago has finished reading it
       __syncwarp();
-      const uint32_t row_addr = box + (uint32_t)lane * 128u;
+      const uint32_t row_addr = ptx::smem_u32(bp) + (uint32_t)lane * 128u;
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         ptx::st_shared_v4(row_addr + (uint32_t)((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
       ptx::fence_proxy_async_smem();
+      if (to_a) {
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(&a_full[as]);
+      }
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_2d(ymap, box_ptr, col, row);
+        ptx::tma_store_2d(ymap, bp, col, row);
         ptx::bulk_commit();
       }
     };
@@ -291,13 +316,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
       const int row = (tile % p.tiles_i) * kBM + 32 * quarter;
       const uint32_t u0 = it * (uint32_t)uses_per_tile;
       // ---- layer 1 halves ----
-      for (int h = 0; h < h1; ++h, ++n1) {
+      for (int h = 0; h < h1; ++h) {
+        const int b = (h + it) & 1;
         const float b0 = __ldg(g.bias[0] + h * 128 + half * 32 + lane), b1 = __ldg(g.bias[0] + h * 128 + (half + 2) * 32 + lane);
-        ptx::mbar_wait(&acc1_full, n1 & 1);
+        ptx::mbar_wait(&b_full[b], (b ? bc1 : bc0) & 1);
+        b ? ++bc1 : ++bc0;
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + h, 0);
-        chunk(kAcc1 + half * 32, b0, &g.y[0], h * 128 + half * 32, row, true, u0 + 4 * h + half, nullptr);
-        chunk(kAcc1 + (half + 2) * 32, b1, &g.y[0], h * 128 + (half + 2) * 32, row, true, u0 + 4 * h + half + 2, &acc1_empty);
+        const uint32_t acc = kAccB + 128u * b;
+        chunk(acc + half * 32, b0, &g.y[0], h * 128 + half * 32, row, true, u0 + 4 * h + half, nullptr);
+        chunk(acc + (half + 2) * 32, b1, &g.y[0], h * 128 + (half + 2) * 32, row, true, u0 + 4 * h + half + 2, &b_empty[b]);
         if (ew == 0) TT_TRACE(3, it * 4 + h, 1);
       }
       // ---- layer 2 ----
@@ -311,18 +339,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
         if (c1 < n2c) chunk(kAcc2 + c1 * 32, b1, &g.y[1], c1 * 32, row, true, u0 + 4 * h1 + c1, nullptr);
         if (ew == 0) TT_TRACE(3, it * 4 + 2, 1);
       }
-      // ---- layer 3 ----
+      // ---- layer 3 (accumulated in buffer it & 1) ----
       {
+        const int b = it & 1;
         const int c0 = half, c1 = half + 2, n3c = N3 / 32;
         const float b0 = c0 < n3c ? __ldg(g.bias[2] + c0 * 32 + lane) : 0.f, b1 = c1 < n3c ? __ldg(g.bias[2] + c1 * 32 + lane) : 0.f;
-        ptx::mbar_wait(&acc3_full, it & 1);
+        ptx::mbar_wait(&b_full[b], (b ? bc1 : bc0) & 1);
+        b ? ++bc1 : ++bc0;
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + 3, 0);
-        if (c0 < n3c) chunk(kAcc2 + c0 * 32, b0, &g.y[2], c0 * 32, row, false, 0u, c1 < n3c ? nullptr : &acc3_empty);
-        if (c1 < n3c) chunk(kAcc2 + c1 * 32, b1, &g.y[2], c1 * 32, row, false, 0u, &acc3_empty);
+        const uint32_t acc = kAccB + 128u * b;
+        if (c0 < n3c) chunk(acc + c0 * 32, b0, &g.y[2], c0 * 32, row, false, 0u, c1 < n3c ? nullptr : &b_empty[b]);
+        if (c1 < n3c) chunk(acc + c1 * 32, b1, &g.y[2], c1 * 32, row, false, 0u, &b_empty[b]);
         if (c0 >= n3c) {   // a warp without a chunk of this layer still counts on the barrier
           ptx::tc_fence_before();
-          ptx::mbar_arrive(&acc3_empty);
+          ptx::mbar_arrive(&b_empty[b]);
         }
         if (ew == 0) TT_TRACE(3, it * 4 + 3, 1);
       }
@@ -338,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
   }
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kMaxXkb * 2 * kTile + (size_t)kWStages * kWSlot + 8 * 4096;
+constexpr size_t kSmemBytes = 1024 + (size_t)kMaxXkb * 2 * kTile + (size_t)kWStages * kWSlot + 8 * 8192;
 
 bool tower_shape_ok(int K0, const int32_t* widths, int n_layers, int act) {
   if (n_layers != kLayers || act < 0 || act > 2) return false;
@@ -375,6 +406,10 @@ extern "C" int mnr_tc_tower_fwd(const mnr_tower_group_t* groups, int n_groups, i
   if (!tower_shape_ok(K0, widths, n_layers, act)) return MNR_EUNSUP;
   TowerParams p;
   p.M = M, p.K0 = K0, p.n_groups = n_groups, p.tiles_i = (M + kBM - 1) / kBM;
+  {
+    const char* e = getenv("MNR_TOWER_FLAGS");
+    p.flags = e ? atoi(e) : 3;
+  }
   int kin = K0;
   for (int l = 0; l < kLayers; ++l) p.N[l] = widths[l];
   for (int k = 0; k < n_groups; ++k) {
@@ -389,6 +424,7 @@ extern "C" int mnr_tc_tower_fwd(const mnr_tower_group_t* groups, int n_groups, i
       if (rc == MNR_OK) rc = make_map(&p.g[k].w_lo[l], s.w_lo[l], N, kin, ldw, box);
       if (rc == MNR_OK) rc = make_map(&p.g[k].y[l], s.y[l], M, N, N, 32);
       p.g[k].bias[l] = s.bias[l];
+      p.g[k].w_ptr[2 * l] = s.w_hi[l], p.g[k].w_ptr[2 * l + 1] = s.w_lo[l], p.g[k].w_bytes[l] = (uint32_t)((size_t)N * ldw * sizeof(float));
       kin = N;
     }
     if (rc != MNR_OK) return rc;
@@ -397,8 +433,13 @@ extern "C" int mnr_tc_tower_fwd(const mnr_tower_group_t* groups, int n_groups, i
   dim3 grid(n_tiles < sms ? n_tiles : sms);
   cudaError_t e = cudaSuccess;
 #define MNR_TOWER_LAUNCH(ACTV)                                                                                                 \
-  e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);           \
-  if (e == cudaSuccess) e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV>, grid, dim3(kThreads), kSmemBytes, mnr_cs(stream), p);
+  if (p.flags & 1) {                                                                                                            \
+    e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);    \
+    if (e == cudaSuccess) e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV, true>, grid, dim3(kThreads), kSmemBytes, mnr_cs(stream), p); \
+  } else {                                                                                                                      \
+    e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);   \
+    if (e == cudaSuccess) e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV, false>, grid, dim3(kThreads), kSmemBytes, mnr_cs(stream), p); \
+  }
   switch (act) {
     case 1: MNR_TOWER_LAUNCH(1) break;
     case 2: MNR_TOWER_LAUNCH(2) break;

@@ -71,11 +71,11 @@ lib.mnr_tc_tower_trace(0, buf)
 tr = np.array(buf[:]).reshape(4, 256, 2)
 t0 = tr[0, 0, 0]
 rel = lambda v: (v - t0) / 1.9  # ~ns at 1.9 GHz
-print("ns from the first layer-1 MMA issue of CTA 0; per tile: L1(h) issue [start end] | L2 blocks 4h..4h+3 [first-ready end] | epilogue L1(h) [start end]")
+print("ns from the first layer-1 MMA issue of CTA 0 (issue times; the epilogue stamps are warp 8's)")
 for it in range(8):
     if tr[2, it, 1] <= 0:
         break
     for h in range(widths[0] // 128):
         i = it * 4 + h
-        print(f"tile {it} h{h}: L1 {rel(tr[0,i,0]):7.0f} {rel(tr[0,i,1]):7.0f} | L2 {rel(tr[1,i,0]):7.0f} {rel(tr[1,i,1]):7.0f} | epi1 {rel(tr[3,i,0]):7.0f} {rel(tr[3,i,1]):7.0f}")
-    print(f"tile {it}   : L3 {rel(tr[2,it,0]):7.0f} {rel(tr[2,it,1]):7.0f} | epi2 {rel(tr[3,it*4+2,0]):7.0f} {rel(tr[3,it*4+2,1]):7.0f} | epi3 {rel(tr[3,it*4+3,0]):7.0f} {rel(tr[3,it*4+3,1]):7.0f}")
+        print(f"tile {it} h{h}: L1 issue {rel(tr[0,i,0]):7.0f} {rel(tr[0,i,1]):7.0f} | epi1 {rel(tr[3,i,0]):7.0f} {rel(tr[3,i,1]):7.0f}")
+    print(f"tile {it}   : L2 {rel(tr[1,it,0]):7.0f} {rel(tr[1,it,1]):7.0f} | epi2 {rel(tr[3,it*4+2,0]):7.0f} {rel(tr[3,it*4+2,1]):7.0f} | L3 {rel(tr[2,it,0]):7.0f} {rel(tr[2,it,1]):7.0f} | epi3 {rel(tr[3,it*4+3,0]):7.0f} {rel(tr[3,it*4+3,1]):7.0f}")
