@@ -19,7 +19,7 @@
 //               stage back to the producer
 //   warp 2      TMEM allocator (accumulators + a ring of 64-column A slots, one per stage)
 //   warps 4-7   converters: fp32 tile -> hi / lo (act' and the bias-gradient column sums fused) -> TMEM slot;
-//               DW: warps 8-11 are a second converter group (alternate k-blocks)
+//               DW: warps 8-11 are a second converter group (each group converts half of every k-block)
 //   warps 8-15  epilogue (DW: warps 12-15): tcgen05.ld -> bias + activation -> 32x32 transpose in smem -> full-line stores
 #include "tc_common.cuh"
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   if (tid == 0) {
     for (int s = 0; s < stages; ++s) {
       ptx::mbar_init(&full_tma[s], 1);
-      ptx::mbar_init(&full_conv[s], 128);
+      ptx::mbar_init(&full_conv[s], MODE == kDw ? 256 : 128);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -238,8 +238,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   } else if (warp >= 4 && warp < (MODE == kDw ? 12 : 8)) {
     // ===== converters ====================================================================================
     // DW is bound by this role (a [32][128] tile of dY and of Y per k-block, element-wise transposed into TMEM lanes by one
-    // warp per scheduler), and its epilogue is small: warps 8-11 form a SECOND converter group there; the groups take
-    // alternate k-blocks and each keeps its own bias-gradient partial.
+    // warp per scheduler), and its epilogue is small: warps 8-11 form a SECOND converter group there; the two groups share
+    // every k-block (half of the reduction rows each) and each keeps its own bias-gradient partial.
     const int cgroup = (warp - 4) >> 2;  // 0: warps 4-7, 1: warps 8-11 (DW only)
     const int t = tid - 128 - 128 * cgroup;
     uint32_t kbg = 0;
@@ -249,10 +249,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
       for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
         const int st = kbg % stages;
         ptx::mbar_wait(&full_tma[st], (kbg / stages) & 1);
-        // the other converter group's k-block.  The wait above is NOT optional: a parity wait only distinguishes
-        // consecutive phases, and with an odd stage count a group that skipped a use of the stage would mistake the
-        // phase before it for the one after it (and convert a stage whose TMA has not landed).
-        if (MODE == kDw && (int)(kbg & 1u) != cgroup) continue;
         if (t == 0) TC_TRACE(1, kbg, 0);
         uint8_t* base = smem + (size_t)st * stage_bytes;
         float4* A4 = reinterpret_cast<float4*>(base);
@@ -285,25 +281,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           // MN-major A tile = 4 chunks of [32 reduction rows][32 features]; thread = feature i = 32 * chunk + lane.
           // SWIZZLE_128B_ATOM_32B keeps the 32 B piece (l >> 3) of row r at piece (l >> 3) ^ (r & 3): the 32 lanes of a
           // warp read one whole 128 B row per LDS -> conflict-free.  The bias gradient (column sum of dZ) is a
-          // per-thread scalar now.
+          // per-thread scalar.  BOTH converter groups work on every k-block - group g takes the reduction rows
+          // [16 g, 16 g + 16) of the A tile (16 TMEM columns of hi and of lo) and half of the B tile's split - so the
+          // conversion latency on the TMA -> convert -> MMA chain of a stage is half of what one group per k-block
+          // took (measured 1.15 us per k-block at N = 128, K = 256 against 1.13 us of MMAs, three 64 KB stages deep).
           const int c = warp & 3, l = lane;
           const float* Af = reinterpret_cast<const float*>(base) + c * (kChunk / 4);
           const float* Sf = reinterpret_cast<const float*>(base + offAlo) + c * (kChunk / 4);
-          uint32_t hi[32], lo[32];
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int r = 0; r < 32; ++r) {
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = 16 * cgroup + rr;
             const int q = r * 32 + ((((l >> 3) ^ (r & 3)) << 3) | (l & 7));
             const float a = HAS_S ? Af[q] * act_bwd_t<ACT>(Sf[q]) : Af[q];
             bsum.x += a;
             const float h = tf32_hi(a);
-            hi[r] = __float_as_uint(h), lo[r] = __float_as_uint(a - h);
+            hi[rr] = __float_as_uint(h), lo[rr] = __float_as_uint(a - h);
           }
-          const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u + ((uint32_t)(32 * c) << 16);
-          ptx::tmem_st_32x32(a_t, hi);
-          ptx::tmem_st_32x32(a_t + 32u, lo);
+          const uint32_t a_t = tmem_base + a_slots + (uint32_t)st * 64u + ((uint32_t)(32 * c) << 16) + 16u * (uint32_t)cgroup;
+          ptx::tmem_st_32x16(a_t, hi);
+          ptx::tmem_st_32x16(a_t + 32u, lo);
           float4* B4 = reinterpret_cast<float4*>(base + offB);
           float4* Blo4 = reinterpret_cast<float4*>(base + offBlo);
-          for (int q = t; q < bytesB / 16; q += 128) {
+          for (int q = t + 128 * cgroup; q < bytesB / 16; q += 256) {
             float4 h4, l4;
             split4(B4[q], h4, l4);
             B4[q] = h4, Blo4[q] = l4;

@@ -24,10 +24,18 @@ for t in range(2):
         x = torch.zeros(M, ld, device=DEV)
         x[:, :K] = torch.randn(M, K, device=DEV, generator=g)
         groups.append(dict(a=x, b=hi, b_lo=lo, c=torch.empty(M, N, device=DEV), bias=torch.randn(N, device=DEV, generator=g), N=N, K=K, lda=ld, ldb=ld))
-    else:
+    elif mode == "dx":
         dy, y = torch.randn(M, N, device=DEV, generator=g), torch.randn(M, N, device=DEV, generator=g)
         groups.append(dict(a=dy, saved=y, b=hi, b_lo=lo, c=torch.empty(M, ld, device=DEV), N=N, K=ld, ldb=ld))
-run = (lambda: ops.tc_linear_fwd(groups, M, 1)) if mode == "fwd" else (lambda: ops.tc_linear_bwd_input(groups, M, 1))
+    else:   # dw: dW (N,K) = (dY * act'(Y))^T X
+        dy, y = torch.randn(M, N, device=DEV, generator=g), torch.randn(M, N, device=DEV, generator=g)
+        x = torch.zeros(M, ld, device=DEV)
+        x[:, :K] = torch.randn(M, K, device=DEV, generator=g)
+        groups.append(dict(a=dy, saved=y, b=x, c=torch.empty(N, K, device=DEV), bias_grad=torch.empty(N, device=DEV), N=N, K=K, ldb=ld))
+if mode == "dw":
+    ws = torch.zeros(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(2, M, N, K), dtype=torch.uint8, device=DEV)
+run = {"fwd": lambda: ops.tc_linear_fwd(groups, M, 1), "dx": lambda: ops.tc_linear_bwd_input(groups, M, 1),
+       "dw": lambda: ops.tc_linear_bwd_weight_partials(groups, M, 1, ws)}[mode]
 for _ in range(3):
     run()
 torch.cuda.synchronize()
@@ -39,7 +47,15 @@ lib.mnr_tc_trace(0, buf)
 tr = np.array(buf[:]).reshape(4, 256, 2)
 t0 = tr[0, 0, 0]
 rel = lambda x: (x - t0) / 1.9  # ~ns at 1.9 GHz
-print(f"{mode} M={M} N={N} K={K}")
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=DEV)
+ts = []
+for _ in range(8):
+    flush.sum()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(); b.record()
+    torch.cuda.synchronize()
+    ts.append(a.elapsed_time(b) * 1e3)
+print(f"{mode} M={M} N={N} K={K}: {sorted(ts)[len(ts) // 2]:.1f} us per launch (CUDA events, L2 flushed)")
 print("kb : prod_issue | conv_start conv_done | mma_start mma_issued   (ns from first TMA issue)")
 for kb in range(40):
     if tr[2, kb, 1] <= 0:
