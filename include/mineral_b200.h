@@ -406,6 +406,8 @@ int mnr_tc_tower_fwd_supported(int K0, const int32_t* widths, int n_layers, int 
 int mnr_tc_tower_fwd(const mnr_tower_group_t* groups /*host*/, int n_groups, int M, int K0, const int32_t* widths /*host*/,
                      int n_layers, int act, mnr_stream_t stream);
 int mnr_tc_tower_trace(int enable, long long* host_out);
+/* same for the fused heads + loss kernel (csrc/heads_fused.cu): 16 phase boundaries of CTA 0, globaltimer ns (32 int64) */
+int mnr_heads_trace(int enable, long long* host_out);
 
 /* Profiling aid: enable != 0 makes CTA 0 of the tensor-core kernels record clock64() at every role's wait / done
  * points; host_out (4 roles x 256 events x 2 tags int64, may be NULL) receives the last timeline. Synchronous. */

@@ -159,6 +159,7 @@ SIGNATURES = {
     "mnr_tc_tower_fwd_supported": (i32, [i32, C.POINTER(C.c_int32), i32, i32]),
     "mnr_tc_tower_fwd": (i32, [C.POINTER(TowerGroup), i32, i32, i32, C.POINTER(C.c_int32), i32, i32, vp]),
     "mnr_tc_tower_trace": (i32, [i32, vp]),
+    "mnr_heads_trace": (i32, [i32, vp]),
     "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
     "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),
     "mnr_colsum_workspace_bytes": (sz, [i32]),

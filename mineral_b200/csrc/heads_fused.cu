@@ -22,6 +22,18 @@
 namespace {
 using namespace mnr_loss;
 
+// optional timeline of CTA 0 (debug aid): globaltimer at the phase boundaries of its first tile
+__device__ long long g_htrace[32];
+__device__ int g_htrace_on = 0;
+#define HF_TRACE(i)                                                                            \
+  do {                                                                                         \
+    if (g_htrace_on && blockIdx.x == 0 && threadIdx.x == 0) {                                  \
+      long long t_;                                                                            \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                   \
+      g_htrace[i] = t_;                                                                        \
+    }                                                                                          \
+  } while (0)
+
 constexpr int kRows = 128;     // rows per tile
 constexpr int kThreadsHF = 256;  // 2 threads per row: thread (r, h) takes the float4 columns c = h, h + 2, ... of row r
 
@@ -41,6 +53,41 @@ struct FusedHeadsArgs {
   int64_t M;
   int A, write_back, n_tiles;
 };
+
+// 16 B asynchronous global -> shared copy (LDGSTS), zero fill when !valid
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int n = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// CTA-wide sums of NV doubles per thread, all reduced together: warp shuffles, one slot per (value, warp), NV threads add
+// the warps in order; every thread receives the totals.  s_buf: NV x NW doubles.  Fixed order => deterministic.
+template <int NV, int NW>
+__device__ __forceinline__ void block_sum_n(double (&v)[NV], double* s_buf, int tid, double* totals_out = nullptr) {
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = mnr::warp_sum(v[k]);
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) s_buf[k * NW + warp] = v[k];
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double t = 0.0;
+    for (int w = 0; w < NW; ++w) t += s_buf[tid * NW + w];
+    s_buf[tid * NW] = t;
+    if (totals_out) totals_out[tid] = t;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; ++k) v[k] = s_buf[k * NW];
+  __syncthreads();
+}
 
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc), acc = fmaf(a.y, b.y, acc), acc = fmaf(a.z, b.z, acc), acc = fmaf(a.w, b.w, acc);
@@ -65,20 +112,25 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   constexpr int UV = NY * 4 <= 64 ? 4 : (NY * 2 <= 64 ? 2 : 1);  // hidden columns per thread in the weight-gradient phase
   constexpr int HU = H / UV, NRG = kThreadsHF / HU, RPG = kRows / NRG;  // threads per row group, row groups, rows per group
   constexpr int kWarpsHF = kThreadsHF / 32;
+  constexpr int CS = kThreadsHF / GW, CSR = (kRows + CS - 1) / CS;   // column sums: CS row slices of CSR rows
   static_assert(A % 4 == 0 && A <= 32 && NRG >= 1 && RPG >= 1 && NY * UV <= 64, "unsupported head shape");
   const int Ar = a.A;  // real action dimension, Ar <= A
   extern __shared__ __align__(16) float sh[];
-  __shared__ double s_red[6][kWarpsHF];
+  __shared__ double s_red[kThreadsHF], s_fin[16];
   mnr::pdl_trigger();   // PDL: see common.cuh
   mnr::pdl_wait();
-  __shared__ mnr::Moments s_mom[2][kWarpsHF];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a, then Y3v tile, then dY3v
-  float* s_wmu = s_y + kRows * P;                    // (A,H)
+  // PREF_V (H <= 64): the Y3v tile has its own buffer and is requested (cp.async) together with the Y3a tile at the top of
+  // the tile, so the DRAM round trip in the middle of the tile is gone; wider towers keep one buffer (2 CTAs per SM).
+  constexpr bool PREF_V = H <= 64;
+  float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a (!PREF_V: then Y3v tile, then dY3v)
+  float* s_yv = s_y + (PREF_V ? kRows * P : 0);      // [128][P]: Y3v tile, then dY3v
+  float* s_wmu = s_yv + kRows * P;                   // (A,H)
   float* s_wsig = s_wmu + A * H;                     // (A,H), learned only
   float* s_wv = s_wsig + (LEARNED ? A * H : 0);      // (H)
   float* s_g = s_wv + H;                             // [128][GP]
 
+  HF_TRACE(0);
   for (int i = tid; i < A * H; i += kThreadsHF) {
     const bool real = i < Ar * H;
     s_wmu[i] = real ? __ldg(a.w_mu + i) : 0.f;
@@ -106,6 +158,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   for (int q = 0; q < UV; ++q) accv[q] = 0.f;
 
   float4* s_y4 = reinterpret_cast<float4*>(s_y);
+  float4* s_v4 = reinterpret_cast<float4*>(s_yv);   // == s_y4 without PREF_V
   const float4* s_wmu4 = reinterpret_cast<const float4*>(s_wmu);
   const float4* s_wsig4 = reinterpret_cast<const float4*>(s_wsig);
   const float4* s_wv4 = reinterpret_cast<const float4*>(s_wv);
@@ -120,7 +173,25 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 
     // =========================== actor tower ===========================================================
     __syncthreads();  // previous tile's stores out of s_y are done (and the weights are staged)
-    {
+    if (PREF_V) {
+      const float4* gya = reinterpret_cast<const float4*>(a.y3a);
+      const float4* gyv = reinterpret_cast<const float4*>(a.y3v);
+#pragma unroll 4
+      for (int i = tid; i < kRows * H4; i += kThreadsHF) {
+        const int rr = i / H4, c = i - rr * H4;
+        const bool ok = rr < rows_here;
+        cp_async16(&s_y4[rr * P4 + c], gya + (row0 + (ok ? rr : 0)) * H4 + c, ok);
+      }
+      cp_async_commit();
+#pragma unroll 4
+      for (int i = tid; i < kRows * H4; i += kThreadsHF) {
+        const int rr = i / H4, c = i - rr * H4;
+        const bool ok = rr < rows_here;
+        cp_async16(&s_v4[rr * P4 + c], gyv + (row0 + (ok ? rr : 0)) * H4 + c, ok);
+      }
+      cp_async_commit();
+      cp_async_wait<1>();   // the Y3a tile has landed; Y3v keeps flying
+    } else {
       const float4* gy = reinterpret_cast<const float4*>(a.y3a);
 #pragma unroll 8
       for (int i = tid; i < kRows * H4; i += kThreadsHF) {
@@ -129,6 +200,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
     __syncthreads();
+    HF_TRACE(1);
     // ---- thread = (row, half): mu / logstd heads ------------------------------------------------------------
     float mu_raw[A], ls[A];
 #pragma unroll
@@ -156,6 +228,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
         grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
         if (j >= Ar) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;  // pad columns: defined (and ignored) in the column sums
       }
+    HF_TRACE(2);
     float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
     const float* act_row = a.actions + (size_t)row * Ar;
 #pragma unroll 1
@@ -172,6 +245,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     }
     nlp += __shfl_xor_sync(0xffffffffu, nlp, 1), ent += __shfl_xor_sync(0xffffffffu, ent, 1);
     bsum += __shfl_xor_sync(0xffffffffu, bsum, 1), kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+    HF_TRACE(3);
     float dl_dnlp, clipped;
     const float a_loss = actor_row(__ldg(a.old_nlp + row), nlp, __ldg(a.adv + row), cfg.e_clip, cfg.use_smooth_clamp, &dl_dnlp, &clipped);
     if (valid && h == 0) t_a += a_loss, t_b += bsum, t_h += ent, t_clip += clipped, t_kl += kl;
@@ -195,6 +269,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       grow[j] = gm, grow[A + j] = gl;
       if (!valid) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;
     }
+    HF_TRACE(4);
     __syncwarp();  // the pair's halves of the row are both in shared memory now
     if (valid && (Ar & 3) == 0) {  // row-contiguous float4 copies of the finished row pieces (half h takes every other piece)
 #pragma unroll
@@ -216,6 +291,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
     __syncthreads();
+    HF_TRACE(5);
     // ---- thread = (uu, rg): dW_mu / dW_sig outer products over this group's rows -----------------------------------
 #pragma unroll 2
     for (int k = 0; k < RPG; ++k) {
@@ -240,6 +316,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
     __syncthreads();
+    HF_TRACE(6);
     // ---- thread = (row, half): dY3a = g_mu Wmu + g_ls Wsig over the tile in place, then coalesced stores --------------
     {
       float gm[A], gl[A];
@@ -261,6 +338,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
     __syncthreads();
+    HF_TRACE(7);
     {
       float4* oa = reinterpret_cast<float4*>(a.dy3a);
       const float4* gy = reinterpret_cast<const float4*>(a.y3v);
@@ -268,14 +346,16 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       for (int i = tid; i < kRows * H4; i += kThreadsHF) {  // dY3a out, Y3v in: every thread reuses exactly the slots it just read
         const int rr = i / H4, c = i - rr * H4;
         if (rr < rows_here) oa[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
-        s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!PREF_V) s_y4[rr * P4 + c] = rr < rows_here ? __ldg(gy + (row0 + rr) * H4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+    if (PREF_V) cp_async_wait<0>();
     __syncthreads();
+    HF_TRACE(8);
     // =========================== value tower ===========================================================
     float value = 0.f;
 #pragma unroll 4
-    for (int c = h; c < H4; c += 2) value = dot4(s_y4[r * P4 + c], s_wv4[c], value);
+    for (int c = h; c < H4; c += 2) value = dot4(s_v4[r * P4 + c], s_wv4[c], value);
     value += __shfl_xor_sync(0xffffffffu, value, 1);
     value += b_v;
     float dl_dv;
@@ -289,29 +369,32 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     }
     if (h == 0) grow[4 * A] = g_v;
     __syncthreads();
+    HF_TRACE(9);
 #pragma unroll 4
     for (int k = 0; k < RPG; ++k) {
       const int rr = rg * RPG + k;
       const float gv = s_g[rr * GP + 4 * A];
       if (UV == 4) {
-        const float4 t = *reinterpret_cast<const float4*>(s_y + rr * P + uu);
+        const float4 t = *reinterpret_cast<const float4*>(s_yv + rr * P + uu);
         accv[0] = fmaf(gv, t.x, accv[0]), accv[1] = fmaf(gv, t.y, accv[1]), accv[2] = fmaf(gv, t.z, accv[2]), accv[3] = fmaf(gv, t.w, accv[3]);
       } else {
-        const float2 t = *reinterpret_cast<const float2*>(s_y + rr * P + uu);
+        const float2 t = *reinterpret_cast<const float2*>(s_yv + rr * P + uu);
         accv[0] = fmaf(gv, t.x, accv[0]), accv[1] = fmaf(gv, t.y, accv[1]);
       }
     }
-    if (tid < GW) {  // column sums of the g tile: db_mu | colsum g_ls | mu, sigma sums | db_v
+    if (tid < CS * GW) {  // column sums of the g tile: db_mu | colsum g_ls | mu, sigma sums | db_v.  thread = (row slice, column)
+      const int cs = tid / GW, cc = tid - cs * GW;
       float sum = 0.f;
-#pragma unroll 8
-      for (int rr = 0; rr < kRows; ++rr) sum += s_g[rr * GP + tid];
+#pragma unroll 4
+      for (int rr = cs * CSR; rr < min(kRows, (cs + 1) * CSR); ++rr) sum += s_g[rr * GP + cc];
       acc_col += sum;
     }
     __syncthreads();
+    HF_TRACE(10);
 #pragma unroll 4
     for (int c = h; c < H4; c += 2) {
       const float4 wv = s_wv4[c];
-      s_y4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
+      s_v4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
     }
     __syncthreads();
     {
@@ -319,59 +402,64 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 #pragma unroll 8
       for (int i = tid; i < kRows * H4; i += kThreadsHF) {
         const int rr = i / H4, c = i - rr * H4;
-        if (rr < rows_here) ov[(row0 + rr) * H4 + c] = s_y4[rr * P4 + c];
+        if (rr < rows_here) ov[(row0 + rr) * H4 + c] = s_v4[rr * P4 + c];
       }
     }
   }
 
+  HF_TRACE(11);
   // ---- fold the row groups (through the tile buffer), park the per-CTA partials ------------------------------------------
   const int PW = (2 * A + 1) * H + GW;
   float* part = a.partials + (size_t)blockIdx.x * PW;
-  float* s_fold = s_y;  // [NRG][H]
+  // every thread parks its accumulators of as many gradient rows as the tile buffer holds ([row][row group][H]), ONE barrier,
+  // then all threads sum the row groups of their outputs in a fixed order (was: one gradient row per pass, two barriers each)
+  float* s_fold = s_y;
+  constexpr int FR_MAX = (kRows * P) / (NRG * H), FR = FR_MAX < NY + 1 ? FR_MAX : NY + 1, NPASS = (NY + 1 + FR - 1) / FR;
+  static_assert(FR >= 1, "tile buffer too small for the fold");
 #pragma unroll
-  for (int j = 0; j <= NY; ++j) {
+  for (int pass = 0; pass < NPASS; ++pass) {
     __syncthreads();
 #pragma unroll
-    for (int x = 0; x < UV; ++x) s_fold[rg * H + uu + x] = j < NY ? accw[j < NY ? j : 0][x] : accv[x];
+    for (int j = 0; j <= NY; ++j) {
+      if (j / FR != pass) continue;
+#pragma unroll
+      for (int x = 0; x < UV; ++x) s_fold[((j - pass * FR) * NRG + rg) * H + uu + x] = j < NY ? accw[j < NY ? j : 0][x] : accv[x];
+    }
     __syncthreads();
-    if (rg == 0) {
+    const int nj = min(FR, NY + 1 - pass * FR);
+    for (int o = tid; o < nj * H; o += kThreadsHF) {
+      const int jr = o / H, u2 = o - jr * H, j = pass * FR + jr;
+      float t = 0.f;
 #pragma unroll
-      for (int x = 0; x < UV; ++x) {
-        float t = 0.f;
-#pragma unroll
-        for (int q = 0; q < NRG; ++q) t += s_fold[q * H + uu + x];
-        part[(j < NY ? j : 2 * A) * H + uu + x] = t;
-      }
+      for (int q = 0; q < NRG; ++q) t += s_fold[(jr * NRG + q) * H + u2];
+      part[(j < NY ? j : 2 * A) * H + u2] = t;
     }
   }
   if (!LEARNED)  // sigma rows of the layout stay defined
     for (int i = tid; i < A * H; i += kThreadsHF) part[A * H + i] = 0.f;
-  if (tid < GW) part[(2 * A + 1) * H + tid] = acc_col;
-
-  float vals[6] = {t_a, t_c, t_b, t_h, t_clip, t_kl};
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const float sum = mnr::warp_sum(vals[k]);
-    if (lane == 0) s_red[k][warp] = (double)sum;
-  }
-  const mnr::Moments md = mnr::moments_warp_reduce(w_d.to_moments());
-  const mnr::Moments mr = mnr::moments_warp_reduce(w_ret.to_moments());
-  if (lane == 0) s_mom[0][warp] = md, s_mom[1][warp] = mr;
   __syncthreads();
-  if (tid == 0) {
-    LossPartial p;
-    double ac[6];
-    for (int k = 0; k < 6; ++k) {
-      ac[k] = 0;
-      for (int x = 0; x < kWarpsHF; ++x) ac[k] += s_red[k][x];
-    }
-    p.a = ac[0], p.c = ac[1], p.b = ac[2], p.h = ac[3], p.clip = ac[4], p.kl = ac[5];
-    p.d = s_mom[0][0], p.ret = s_mom[1][0];
-    for (int x = 1; x < kWarpsHF; ++x) p.d = mnr::moments_merge(p.d, s_mom[0][x]), p.ret = mnr::moments_merge(p.ret, s_mom[1][x]);
-    a.loss_parts[blockIdx.x] = p;
+  if (tid < CS * GW) s_fold[tid] = acc_col;   // [slice][column]
+  __syncthreads();
+  if (tid < GW) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < CS; ++q) t += s_fold[q * GW + tid];
+    part[(2 * A + 1) * H + tid] = t;
   }
 
+  // per-CTA loss partial (12 doubles, layout at the metrics code below): all threads' values reduced together in f64
+  HF_TRACE(16);
+  {
+    const double nd = (double)w_d.n, md_ = (double)w_d.mean, nr = (double)w_ret.n, mr_ = (double)w_ret.mean;
+    double v1[12] = {(double)t_a, (double)t_c, (double)t_b, (double)t_h, (double)t_clip, (double)t_kl,
+                     nd, nd * md_, (double)w_d.m2 + nd * md_ * md_, nr, nr * mr_, (double)w_ret.m2 + nr * mr_ * mr_};
+    block_sum_n<12, kWarpsHF>(v1, s_red, tid, s_fin);
+    if (tid < 12) reinterpret_cast<double*>(a.loss_parts)[(size_t)blockIdx.x * 12 + tid] = s_fin[tid];
+  }
+
+  HF_TRACE(12);
   mnr::grid_barrier(a.barrier);
+  HF_TRACE(13);
 
   // ---- every CTA reduces its share of the PW outputs over all CTAs (warp per output, fixed order) ----------------
   const int n_cta = gridDim.x;
@@ -396,38 +484,55 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
   }
+  HF_TRACE(14);
   if (blockIdx.x != 0) return;
 
   // ---- CTA 0: the ten loss metrics ---------------------------------------------------------------------------------
-  double acc2[6] = {0, 0, 0, 0, 0, 0};
-  mnr::Moments md2{0, 0, 0}, mr2{0, 0, 0};
-  for (int x = tid; x < n_cta; x += kThreadsHF) {
-    const LossPartial p = a.loss_parts[x];
-    acc2[0] += p.a, acc2[1] += p.c, acc2[2] += p.b, acc2[3] += p.h, acc2[4] += p.clip, acc2[5] += p.kl;
-    md2 = mnr::moments_merge(md2, p.d), mr2 = mnr::moments_merge(mr2, p.ret);
-  }
-  double tot[6];
+  // loss_parts[x] = 12 doubles {a, c, b, h, clip, kl, n_d, S_d, Q_d, n_r, S_r, Q_r} with S = sum x, Q = sum x^2 (in f64, from
+  // the threads' Welford triples): the variances follow from the totals, var = (Q - S^2 / n) / (n - 1), without the chain
+  // of Chan merges (one f64 division each) that took 16 us of this kernel's 49 when thread 0 ran it alone.
+  // thread = (value k = tid & 15, slice = tid >> 4): 16 slices x n_cta / 16 partials, loads independent, fixed order.
+  {
+    const int k = tid & 15, sl = tid >> 4;
+    double acc = 0.0;
+    if (k < 12) {
+      const double* lp = reinterpret_cast<const double*>(a.loss_parts);
+#pragma unroll 4
+      for (int x = sl; x < n_cta; x += kThreadsHF / 16) acc += __ldcg(lp + (size_t)x * 12 + k);
+    }
+    s_red[sl * 16 + k] = acc;
+    __syncthreads();
+    if (tid < 12) {
+      double t = 0.0;
 #pragma unroll
-  for (int k = 0; k < 6; ++k) tot[k] = mnr::block_sum(acc2[k]);
-  const mnr::Moments td = mnr::block_merge(md2), tr = mnr::block_merge(mr2);
+      for (int q = 0; q < kThreadsHF / 16; ++q) t += s_red[q * 16 + tid];
+      s_fin[tid] = t;
+    }
+    __syncthreads();
+  }
+  HF_TRACE(17);
   if (tid == 0) {
-    const double n = (double)a.M;
-    const float av = (float)(tot[0] / n), c = (float)(tot[1] / n), b = (float)(tot[2] / n), h = (float)(tot[3] / n);
+    const double n = (double)a.M, inv_n = 1.0 / n;
+    double tot[6];
+    for (int k = 0; k < 6; ++k) tot[k] = s_fin[k];
+    const mnr::Moments td{s_fin[6], 0.0, s_fin[8] - s_fin[7] * s_fin[7] / s_fin[6]}, tr{s_fin[9], 0.0, s_fin[11] - s_fin[10] * s_fin[10] / s_fin[9]};
+    const float av = (float)(tot[0] * inv_n), c = (float)(tot[1] * inv_n), b = (float)(tot[2] * inv_n), h = (float)(tot[3] * inv_n);
     float m[MNR_PPO_METRICS];
     m[0] = av + 0.5f * c * cfg.critic_coef - h * cfg.entropy_coef + b * cfg.bounds_loss_coef;
     m[1] = av, m[2] = c, m[3] = b, m[4] = h;
-    m[5] = (float)(tot[4] / n);
+    m[5] = (float)(tot[4] * inv_n);
     const float var_d = (float)(td.m2 / (td.n - 1.0)), var_r = (float)(tr.m2 / (tr.n - 1.0));
     m[6] = fminf(fmaxf(1.f - var_d / (var_r + 1e-8f), 0.f), 1.f);
-    m[7] = (float)(tot[5] / n);
+    m[7] = (float)(tot[5] * inv_n);
     m[8] = 0.f, m[9] = 0.f;
     for (int k = 0; k < MNR_PPO_METRICS; ++k) a.metrics[k] = m[k] * cfg.metric_scale;
+    HF_TRACE(15);
   }
 }
 
 template <int A, int H, bool LEARNED>
 size_t fused_smem_bytes() {
-  return (size_t)(kRows * (H + 8) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
+  return (size_t)((H <= 64 ? 2 : 1) * kRows * (H + 8) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
 }
 
 template <int A, int H, bool LEARNED>
@@ -482,6 +587,17 @@ int launch_by_a(FusedHeadsArgs& a, int H, const mnr_ppo_loss_cfg_t& cfg, int gri
 }
 
 }  // namespace
+
+// debug: enable / read the CTA-0 timeline (globaltimer ns at 16 phase boundaries)
+extern "C" int mnr_heads_trace(int enable, long long* host_out) {
+  cudaError_t e = cudaMemcpyToSymbol(g_htrace_on, &enable, sizeof(int));
+  if (e != cudaSuccess) return (int)e;
+  if (host_out) {
+    e = cudaMemcpyFromSymbol(host_out, g_htrace, sizeof(long long) * 32);
+    if (e != cudaSuccess) return (int)e;
+  }
+  return MNR_OK;
+}
 
 // ---- internal interface used by mnr_ppo_heads_loss_fwd_bwd (csrc/ppo_loss.cu) ----------------------------------------
 int mnr_heads_fused_grid_cap() { return mnr_sm_count() * 4; }
