@@ -267,7 +267,9 @@ typedef struct {
   float soft_bound;       /* 1.1 */
   float grad_scale;       /* d(total)/d(loss): 1.0, or 1/world_size before a SUM gradient all-reduce */
   float metric_scale;     /* metrics_out *= metric_scale (1.0, or 1/world_size before a SUM all-reduce) */
-  float _pad;
+  int32_t dz_act;         /* mnr_ppo_heads_loss_fwd_bwd, single-kernel form only: 0 -> dy3a / dy3v receive d loss / d Y3 (default);
+                             1 (ELU) / 2 (ReLU) -> they receive dZ3 = dY3 * act'(Y3), taken from the Y3 tile the kernel has
+                             staged anyway, so the top layer's backward GEMMs run with act = 0 and load no saved-output tile */
 } mnr_ppo_loss_cfg_t;
 
 #define MNR_PPO_METRICS 10

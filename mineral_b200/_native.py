@@ -59,7 +59,7 @@ class PPOLossCfg(C.Structure):
     _fields_ = [("dist_type", C.c_int32), ("bounds_type", C.c_int32), ("use_smooth_clamp", C.c_int32),
                 ("clip_value_loss", C.c_int32), ("minstd", C.c_float), ("maxstd", C.c_float), ("e_clip", C.c_float),
                 ("critic_coef", C.c_float), ("entropy_coef", C.c_float), ("bounds_loss_coef", C.c_float),
-                ("soft_bound", C.c_float), ("grad_scale", C.c_float), ("metric_scale", C.c_float), ("_pad", C.c_float)]
+                ("soft_bound", C.c_float), ("grad_scale", C.c_float), ("metric_scale", C.c_float), ("dz_act", C.c_int32)]
 
 
 class LinearGroup(C.Structure):

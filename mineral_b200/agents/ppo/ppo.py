@@ -619,6 +619,7 @@ class _UpdateEngine:
                     cols=cols, gm=torch.zeros(self.num_mb, cols, **f32), gv=torch.zeros(self.num_mb, cols, **f32),
                     mean_tab=torch.zeros(self.steps, cols, **f32), denom_tab=torch.zeros(self.steps, cols, **f32),
                     x=torch.zeros(self.mb, (cols + 3) // 4 * 4, **f32), x_ld=(cols + 3) // 4 * 4,
+                    x2=torch.zeros(self.mb, (cols + 3) // 4 * 4, **f32),   # second buffer: step s + 1 is normalised under step s
                     ws=ops.rms_moments_workspace(self.B, cols, self.mb, dev)))
         # actor / value towers: explicit forward / backward on the hand-written linear kernels (tcgen05 where the widths
         # allow, SIMT twins otherwise); PPO.__init__ has already rejected networks FusedTowers cannot run
@@ -626,6 +627,9 @@ class _UpdateEngine:
         self.towers = FusedTowers(a.model, self.mb, dev)
         if self.towers.fused_heads_ok:
             self.heads_ws = ops.ppo_heads_workspace(self.mb, self.A, self.towers.widths[-1], dev)
+            # ELU / ReLU towers: the heads kernel writes dZ3 = dY3 * act'(Y3) (it holds the Y3 tiles), the top layer's
+            # backward GEMMs then skip their saved-output loads
+            self.loss_cfg.dz_act = self.towers.heads_dz_act()
         jobs = self.towers.stack.split_jobs()
         if 0 < len(jobs) <= 8:   # the optimizer kernel keeps the tf32 (hi, lo) weight copies current
             a.optim.attach_splits(jobs)
@@ -669,13 +673,43 @@ class _UpdateEngine:
             x_buf, x_ld = n['x'], n['x_ld']
 
         pingpong = peer and os.environ.get('MNR_PEER_END_BARRIER', '0') != '1'   # =1: two barriers per step (A/B measurements)
+        # MNR_RMS_FORK=1 (A/B measurements): the normalised input of step s + 1 depends only on the statistics tables computed
+        # above, so its launch can be forked onto a side stream at the top of step s (two input buffers) and join before the
+        # forward of step s + 1.  MEASURED SLOWER (round 2, cfg2: 5.02 ms per update against 4.87 ms in line): the persistent
+        # GEMM kernels own every SM, so the forked kernel's CTAs only delay their tiles, and the cross-stream graph edges
+        # cost more than the 7 us launch they hide.  Default: in line.
+        fork = n is not None and os.environ.get('MNR_RMS_FORK', '0') == '1'
+        main = torch.cuda.current_stream()
+        if fork:
+            if getattr(self, '_side', None) is None:
+                self._side = torch.cuda.Stream(device=a.device)
+            xs = (n['x'], n['x2'])
+        v = d['obses']['obs']
+        total = a.mini_epochs * self.num_mb
+
+        def normalise(st_, buf):
+            j = st_ % self.num_mb
+            ops.rms_apply_ld(v[j * mb:(j + 1) * mb], n['mean_tab'][st_], n['denom_tab'][st_], clamp, buf, x_ld)
+
+        ready = None
+        if fork:
+            normalise(0, xs[0])
         for ep in range(a.mini_epochs):
             for i in range(self.num_mb):
                 s, e = i * mb, (i + 1) * mb
                 if peer:   # this step's backward writes ping-pong gradient region step & 1
                     a.optim.use_grad_buffer(step)
-                v = d['obses']['obs']
-                if n is not None:   # normalise + clamp into the padded (TMA-friendly) row stride; pad columns stay zero
+                if fork:
+                    x_buf = xs[step & 1]
+                    if ready is not None:
+                        main.wait_event(ready)
+                    if step + 1 < total:   # xs[(step + 1) & 1] was last read by step - 1, which is complete in `main` order
+                        self._side.wait_stream(main)
+                        with torch.cuda.stream(self._side):
+                            normalise(step + 1, xs[(step + 1) & 1])
+                            ready = torch.cuda.Event()
+                            ready.record(self._side)
+                elif n is not None:   # normalise + clamp into the padded (TMA-friendly) row stride; pad columns stay zero
                     ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, x_buf, x_ld)
                 else:
                     x_buf[:, :v.shape[1]].copy_(v[s:e])

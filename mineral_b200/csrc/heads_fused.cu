@@ -89,6 +89,11 @@ __device__ __forceinline__ void block_sum_n(double (&v)[NV], double* s_buf, int 
   __syncthreads();
 }
 
+// act'(y) from the layer OUTPUT y (cfg.dz_act: 1 ELU with alpha = 1, 2 ReLU) - the same forms as tc_common.cuh's act_bwd_from_y
+__device__ __forceinline__ float dz_factor(float y, int act) {
+  return y > 0.f ? 1.f : (act == 1 ? y + 1.f : 0.f);
+}
+
 __device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
   acc = fmaf(a.x, b.x, acc), acc = fmaf(a.y, b.y, acc), acc = fmaf(a.z, b.z, acc), acc = fmaf(a.w, b.w, acc);
   return acc;
@@ -334,6 +339,10 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
             da.x = fmaf(gl[j], ws.x, da.x), da.y = fmaf(gl[j], ws.y, da.y), da.z = fmaf(gl[j], ws.z, da.z), da.w = fmaf(gl[j], ws.w, da.w);
           }
         }
+        if (cfg.dz_act) {   // dZ3 = dY3 * act'(Y3): the Y3a value is still in the slot that is about to be overwritten
+          const float4 y = s_y4[r * P4 + c];
+          da.x *= dz_factor(y.x, cfg.dz_act), da.y *= dz_factor(y.y, cfg.dz_act), da.z *= dz_factor(y.z, cfg.dz_act), da.w *= dz_factor(y.w, cfg.dz_act);
+        }
         s_y4[r * P4 + c] = da;
       }
     }
@@ -394,7 +403,12 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 #pragma unroll 4
     for (int c = h; c < H4; c += 2) {
       const float4 wv = s_wv4[c];
-      s_v4[r * P4 + c] = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
+      float4 dv = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
+      if (cfg.dz_act) {
+        const float4 y = s_v4[r * P4 + c];
+        dv.x *= dz_factor(y.x, cfg.dz_act), dv.y *= dz_factor(y.y, cfg.dz_act), dv.z *= dz_factor(y.z, cfg.dz_act), dv.w *= dz_factor(y.w, cfg.dz_act);
+      }
+      s_v4[r * P4 + c] = dv;
     }
     __syncthreads();
     {

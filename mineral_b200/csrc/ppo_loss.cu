@@ -849,6 +849,8 @@ extern "C" int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, co
   if (cfg->bounds_type != MNR_BOUNDS_BOUND && cfg->bounds_type != MNR_BOUNDS_REG) return MNR_EUNSUP;
   if (workspace_bytes < mnr_ppo_heads_workspace_bytes(M, A, H)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
+  if (cfg->dz_act < 0 || cfg->dz_act > 2) return MNR_EUNSUP;
+  if (cfg->dz_act != 0 && !mnr_heads_fused_supported(A, H)) return MNR_EUNSUP;   // dZ3 output: single-kernel form only
   if (mnr_heads_fused_supported(A, H))
     return mnr_heads_fused_launch(y3a, y3v, w_mu, b_mu, w_v, b_v, w_sig, b_sig, actions, old_neglogp, advantages, old_values,
                                   returns, old_mu, old_sigma, write_back, dy3a, dy3v, g_mu, g_ls, g_v, dw_mu, db_mu, dw_v, db_v,

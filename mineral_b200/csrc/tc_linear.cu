@@ -64,6 +64,9 @@ struct TcParams {
   int n_groups;
   int tiles_i, tiles_j;
   int tma_store;  // FWD / DX: the epilogue leaves through TMA tensor stores (C rows 16 B-multiple apart), else plain stores
+  // weight-gradient kernel, second form (tc_dw2_kernel): K_in features per work item (128 or 256 = n_mt lane tiles of 128),
+  // depth of the TMEM A-slot ring, 32-feature chunks of X per k-block
+  int kt, n_mt, a_ring, nxc;
 };
 
 // work item -> (group, split, tile row, tile column); consecutive items of one CTA walk the i tiles first
@@ -152,6 +155,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   // PDL: everything above touched only shared / tensor memory and overlapped the previous kernel's tail
   mnr::pdl_trigger();
   mnr::pdl_wait();
+  if (warp == 3 && lane < p.n_groups) {   // (otherwise idle warp) descriptor fetches off the first loads' / stores' critical path
+    const TcGroup& g = p.g[lane];
+    ptx::prefetch_tmap(&g.a), ptx::prefetch_tmap(&g.b0);
+    if (HAS_S) ptx::prefetch_tmap(&g.s);
+    if (!CONV_B) ptx::prefetch_tmap(&g.b1);
+    if (MODE != kDw && p.tma_store) ptx::prefetch_tmap(&g.cmap);
+  }
 
   if (warp == 0) {
     // ===== TMA producer ==========================================================================
@@ -469,6 +479,301 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
   }
 }
 
+// ---- weight gradient, second form -------------------------------------------------------------------------------------
+// dW (N_out, K_in) = dZ^T X with dZ = dY * act'(Y), computed as  dW^T = X^T dZ  so that the operand roles swap:
+//   * the RAW operand X (a [32 rows][K_in] block per k-block) goes to TENSOR MEMORY - the converter warps transpose it on the
+//     way (TMEM lane = input feature, the 32 rows of the k-block = 32 columns; hi | lo slots as in the other modes);
+//   * the operand that needs the product is converted IN PLACE in shared memory: the hi part of dZ over the dY tile, the lo
+//     part over the Y tile, element for element - and that pair is the MN-major B operand of the MMAs (N = N_out).
+// A stage therefore holds exactly the bytes TMA brought and nothing else (the first form keeps a second copy of X for its lo
+// part: 96 KB per stage at 128 x 256, two stages, a TMA -> convert -> MMA chain of 3.8 us per two k-blocks against 2.3 us of
+// MMAs).  Here 128 x 256 runs three 64 KB stages, 64 x 128 six of 32 KB, 256 x 40 three of 72 KB, the transposition handles
+// K_in values instead of N_out, and dY / Y are read once per K_in tile of 256 instead of once per 128 output rows.
+// The accumulator tile [K_in lanes][N_out columns] leaves transposed - every store instruction writes 32 consecutive floats
+// of one dW row - into the same [split][N_out][K_in] partial slabs the first form writes, so tc_reduce_kernel is unchanged.
+// Roles: warp 0 TMA producer, 1 MMA issuer, 2 TMEM allocator, 4-11 converters (256 threads), 12-15 epilogue.
+struct Dw2Coord {
+  int gi, split, i0, j0, r_begin, num_kb, nxc, n_mt;
+};
+__device__ __forceinline__ Dw2Coord decode_dw2(const TcParams& p, int tile) {
+  Dw2Coord c;
+  const int ti = tile % p.tiles_i;
+  int rest = tile / p.tiles_i;
+  const int tj = rest % p.tiles_j;
+  rest /= p.tiles_j;
+  c.split = rest % p.splits;
+  c.gi = rest / p.splits;
+  c.i0 = ti * p.kt, c.j0 = tj * p.BN;
+  c.r_begin = c.split * p.rows_per_split;
+  const int r_end = min(p.R, c.r_begin + p.rows_per_split);
+  c.num_kb = r_end > c.r_begin ? (r_end - c.r_begin + kBK - 1) / kBK : 0;
+  c.nxc = (min(p.kt, p.J - c.i0) + 31) / 32;
+  c.n_mt = (c.nxc + 3) / 4;
+  return c;
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(kThreads, 1) tc_dw2_kernel(const __grid_constant__ TcParams p) {
+  constexpr bool HAS_S = ACT != 0;
+  extern __shared__ uint8_t smem_dyn[];
+  __shared__ __align__(8) uint64_t full_tma[kMaxStages], full_conv[kMaxStages], empty_bar[kMaxStages], a_empty[kMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full, tmem_empty;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int BN = p.BN, stages = p.stages, a_ring = p.a_ring;
+  const int n_tiles = p.tiles_i * p.tiles_j * p.n_groups * p.splits;
+  uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
+  const int bytesZ = BN * kBK * 4;             // dY tile (-> dZ hi) and Y tile (-> dZ lo): BN / 32 chunks of 4 KiB each
+  const int offS = bytesZ, offX = 2 * bytesZ;
+  const int stage_bytes = offX + p.nxc * kChunk;
+  float* s_bias = reinterpret_cast<float*>(smem + (size_t)stages * stage_bytes);   // [8 converter warps][256]
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) {
+      ptx::mbar_init(&full_tma[s], 1);
+      ptx::mbar_init(&full_conv[s], 256);
+      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&a_empty[s], 1);
+    }
+    ptx::mbar_init(&tmem_full, 1);
+    ptx::mbar_init(&tmem_empty, 4 * 32);
+    ptx::fence_mbar_init();
+  }
+  // tensor memory: n_mt accumulators of BN columns (lane tile mt = features [128 mt, 128 mt + 128)), then the A ring:
+  // a_ring k-blocks x n_mt lane tiles x (32 hi | 32 lo) columns
+  const uint32_t a_base = (uint32_t)(p.n_mt * BN);
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < a_base + (uint32_t)(a_ring * p.n_mt) * 64u) tmem_cols <<= 1;
+  if (warp == 2) ptx::tmem_alloc(&tmem_slot, tmem_cols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  mnr::pdl_trigger();
+  mnr::pdl_wait();
+  if (warp == 3 && lane < p.n_groups) {
+    const TcGroup& g = p.g[lane];
+    ptx::prefetch_tmap(&g.a), ptx::prefetch_tmap(&g.b0);
+    if (HAS_S) ptx::prefetch_tmap(&g.s);
+  }
+
+  if (warp == 0) {
+    // ===== TMA producer: MN-major boxes [32 reduction rows][32 floats] ================================================
+    if (lane == 0) {
+      uint32_t kbg = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const Dw2Coord tc = decode_dw2(p, tile);
+        const TcGroup& g = p.g[tc.gi];
+        const uint32_t tx_bytes = (uint32_t)bytesZ * (HAS_S ? 2u : 1u) + (uint32_t)tc.nxc * kChunk;
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+          const int st = kbg % stages;
+          ptx::mbar_wait(&empty_bar[st], ((kbg / stages) & 1) ^ 1);
+          TC_TRACE(0, kbg, 0);
+          uint8_t* base = smem + (size_t)st * stage_bytes;
+          ptx::mbar_expect_tx(&full_tma[st], tx_bytes);
+          const int r0 = tc.r_begin + kb * kBK;
+          for (int c = 0; c < tc.nxc; ++c) ptx::tma_load_2d(base + offX + c * kChunk, &g.b0, tc.i0 + 32 * c, r0, &full_tma[st]);
+          for (int c = 0; c < BN / 32; ++c) {
+            ptx::tma_load_2d(base + c * kChunk, &g.a, tc.j0 + 32 * c, r0, &full_tma[st]);
+            if (HAS_S) ptx::tma_load_2d(base + offS + c * kChunk, &g.s, tc.j0 + 32 * c, r0, &full_tma[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: D[mt] (+)= A[mt] (TMEM: X^T hi | lo) * B (smem: dZ hi / lo, MN-major) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::idesc_tf32(kBM, BN, 0, 1);
+      const uint64_t b_desc_hi = ptx::smem_desc(0, 0, 512, 1);
+      const uint32_t b_desc_lo_const = ((uint32_t)kChunk >> 4) << 16;
+      uint32_t kbg = 0, it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+        const Dw2Coord tc = decode_dw2(p, tile);
+        ptx::mbar_wait(&tmem_empty, (it & 1) ^ 1);   // the epilogue has drained the accumulators
+        ptx::tc_fence_after();
+        for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+          const int st = kbg % stages, ar = kbg % a_ring;
+          ptx::mbar_wait(&full_conv[st], (kbg / stages) & 1);
+          TC_TRACE(2, kbg, 0);
+          ptx::tc_fence_after();
+          const uint32_t base = ptx::smem_u32(smem + (size_t)st * stage_bytes);
+          const uint32_t bh32 = (base >> 4) | b_desc_lo_const, bl32 = ((base + offS) >> 4) | b_desc_lo_const;
+          const int r_left = min(p.R, tc.r_begin + p.rows_per_split) - (tc.r_begin + kb * kBK);
+          const int ksteps = r_left >= kBK ? kBK / 8 : (r_left + 7) / 8;
+          for (int mt = 0; mt < tc.n_mt; ++mt) {
+            const uint32_t tmem_d = tmem_base + (uint32_t)(mt * BN);
+            const uint32_t a_t = tmem_base + a_base + (uint32_t)(ar * p.n_mt + mt) * 64u;
+#pragma unroll
+            for (int k = 0; k < kBK / 8; ++k) {
+              if (k >= ksteps) break;
+              const uint32_t b_step = (uint32_t)(k * 1024) >> 4;   // 8 reduction rows = 1 KiB inside every 4 KiB chunk
+              const uint64_t b_hi = b_desc_hi | (uint64_t)(bh32 + b_step), b_lo = b_desc_hi | (uint64_t)(bl32 + b_step);
+              ptx::mma_tf32_ts(tmem_d, a_t + 32u + 8u * k, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);  // small terms first
+              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_lo, idesc, 1u);
+              ptx::mma_tf32_ts(tmem_d, a_t + 8u * k, b_hi, idesc, 1u);
+            }
+          }
+          ptx::tc_commit(&empty_bar[st]);   // the stage's shared memory may be refilled
+          ptx::tc_commit(&a_empty[ar]);     // ... and its A slots rewritten
+          TC_TRACE(2, kbg, 1);
+        }
+        ptx::tc_commit(&tmem_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===== converters =====================================================================================================
+    const int t = tid - 128;                       // 0..255
+    const int quarter = warp & 3, grp = (warp - 4) >> 2;
+    uint32_t kbg = 0;
+    float4 bsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const Dw2Coord tc = decode_dw2(p, tile);
+      for (int kb = 0; kb < tc.num_kb; ++kb, ++kbg) {
+        const int st = kbg % stages, ar = kbg % a_ring;
+        ptx::mbar_wait(&full_tma[st], (kbg / stages) & 1);
+        ptx::mbar_wait(&a_empty[ar], ((kbg / a_ring) & 1) ^ 1);   // the MMAs that read this A slot have completed
+        ptx::tc_fence_after();
+        if (t == 0) TC_TRACE(1, kbg, 0);
+        uint8_t* base = smem + (size_t)st * stage_bytes;
+        // (a) X^T -> tensor memory.  Thread = input feature 32 * chunk + lane; the chunk is [32 rows][32 floats] with
+        //     SWIZZLE_128B_ATOM_32B (the 32 B piece (l >> 3) of row r sits at piece (l >> 3) ^ (r & 3)): a warp reads one whole
+        //     128 B row per LDS.  Two lane tiles: converter group g owns lane tile g; one: the groups split the 32 rows.
+        const uint32_t a_slot = tmem_base + a_base + (uint32_t)(ar * p.n_mt) * 64u + ((uint32_t)(32 * quarter) << 16);
+        if (tc.n_mt == 2) {
+          const int chunk = grp * 4 + quarter;
+          if (chunk < tc.nxc) {
+            const float* Xf = reinterpret_cast<const float*>(base + offX) + chunk * (kChunk / 4);
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const float x = Xf[r * 32 + ((((lane >> 3) ^ (r & 3)) << 3) | (lane & 7))];
+              const float h = tf32_hi(x);
+              hi[r] = __float_as_uint(h), lo[r] = __float_as_uint(x - h);
+            }
+            ptx::tmem_st_32x32(a_slot + (uint32_t)grp * 64u, hi);
+            ptx::tmem_st_32x32(a_slot + (uint32_t)grp * 64u + 32u, lo);
+          }
+        } else if (quarter < tc.nxc) {
+          const float* Xf = reinterpret_cast<const float*>(base + offX) + quarter * (kChunk / 4);
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int rr = 0; rr < 16; ++rr) {
+            const int r = 16 * grp + rr;
+            const float x = Xf[r * 32 + ((((lane >> 3) ^ (r & 3)) << 3) | (lane & 7))];
+            const float h = tf32_hi(x);
+            hi[rr] = __float_as_uint(h), lo[rr] = __float_as_uint(x - h);
+          }
+          ptx::tmem_st_32x16(a_slot + 16u * (uint32_t)grp, hi);
+          ptx::tmem_st_32x16(a_slot + 32u + 16u * (uint32_t)grp, lo);
+        }
+        // (b) dZ = dY * act'(Y) -> (hi over dY, lo over Y), element-wise: the swizzle is the same for both tiles.  A thread
+        //     keeps the same 4 logical columns in every chunk and every k-block: its running sums are the bias gradient.
+        float4* Z4 = reinterpret_cast<float4*>(base);
+        float4* S4 = reinterpret_cast<float4*>(base + offS);
+        const int nq = BN * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = t + 256 * j;
+          if (q < nq) {
+            float4 a = Z4[q];
+            if (HAS_S) {
+              const float4 s = S4[q];
+              a.x *= act_bwd_t<ACT>(s.x), a.y *= act_bwd_t<ACT>(s.y), a.z *= act_bwd_t<ACT>(s.z), a.w *= act_bwd_t<ACT>(s.w);
+            }
+            bsum[j].x += a.x, bsum[j].y += a.y, bsum[j].z += a.z, bsum[j].w += a.w;
+            float4 h, l;
+            split4(a, h, l);
+            Z4[q] = h, S4[q] = l;
+          }
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&full_conv[st]);
+        if (t == 0) TC_TRACE(1, kbg, 1);
+      }
+      // bias gradient of this work item: thread (row r = t >> 3, 16 B position t & 7) holds logical columns
+      // 8 * ((pos >> 1) ^ (r & 3)) + 4 * (pos & 1) + [0, 4) of every chunk; the 4 rows of a warp meet by two xor shuffles
+      // (lane ^ 10, lane ^ 20 keep the logical piece), the 8 warps in shared memory, summed in warp order.
+      if (p.want_bias && tc.i0 == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (j * 32 < BN) {
+            float4 v = bsum[j];
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, 10), v.y += __shfl_xor_sync(0xffffffffu, v.y, 10);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, 10), v.w += __shfl_xor_sync(0xffffffffu, v.w, 10);
+            v.x += __shfl_xor_sync(0xffffffffu, v.x, 20), v.y += __shfl_xor_sync(0xffffffffu, v.y, 20);
+            v.z += __shfl_xor_sync(0xffffffffu, v.z, 20), v.w += __shfl_xor_sync(0xffffffffu, v.w, 20);
+            if (lane < 8) *reinterpret_cast<float4*>(s_bias + (warp - 4) * 256 + j * 32 + (lane >> 1) * 8 + (lane & 1) * 4) = v;
+          }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (t < BN) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += s_bias[w * 256 + t];
+          float* bp = p.partials + (size_t)p.n_groups * p.splits * p.I * p.J + ((size_t)tc.gi * p.splits + tc.split) * 2 * p.I;
+          if (tc.j0 + t < p.I) bp[tc.j0 + t] = sum, bp[p.I + tc.j0 + t] = 0.f;   // (the first form writes two slabs per split)
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bsum[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (warp >= 12) {
+    // ===== epilogue: accumulator lane = input feature k, columns = output features n -> partial[n][k] ===================
+    const int quarter = warp & 3;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const Dw2Coord tc = decode_dw2(p, tile);
+      ptx::mbar_wait(&tmem_full, it & 1);
+      if (tid == 12 * 32) TC_TRACE(3, it, 0);
+      ptx::tc_fence_after();
+      float* slab = p.partials + ((size_t)tc.gi * p.splits + tc.split) * p.I * p.J;
+      for (int mt = 0; mt < tc.n_mt; ++mt) {
+        const int k_first = tc.i0 + mt * 128 + 32 * quarter;
+        if (k_first >= p.J) continue;   // warp-uniform
+        const int kf = k_first + lane;
+        for (int cc = 0; cc < BN / 32; ++cc) {
+          uint32_t r[32];
+          if (tc.num_kb > 0) {
+            ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(32 * quarter) << 16) + (uint32_t)(mt * BN + cc * 32), r);
+            ptx::tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) r[q] = 0u;
+          }
+          if (kf < p.J) {
+            float* out = slab + (size_t)(tc.j0 + cc * 32) * p.J + kf;
+            const int n_valid = min(32, p.I - (tc.j0 + cc * 32));
+            if (n_valid == 32) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) out[(size_t)q * p.J] = __uint_as_float(r[q]);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q)
+                if (q < n_valid) out[(size_t)q * p.J] = __uint_as_float(r[q]);
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty);
+      if (tid == 12 * 32) TC_TRACE(3, it, 1);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
 // dW / db = sum over splits (fixed order)
 // block = 32 element slots x 8 split slices: every thread sums splits z = slice, slice + 8, .. (independent loads, all in
 // flight), the 8 slices meet in shared memory and are added in slice order -> deterministic, one latency round.
@@ -708,13 +1013,57 @@ int tc_dw_splits(int M, int tiles) {
   if (s > max_s) s = max_s;
   return s < 1 ? 1 : s;
 }
+
+// MNR_TC_DW2=0 keeps the first form of the weight-gradient kernel for every shape (A/B measurements); read once
+int dw2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MNR_TC_DW2");
+    v = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;   // 2: also for K_in < 64 (tests)
+  }
+  return v;
+}
+
+constexpr int kDw2BiasBytes = 8 * 256 * 4;
+
+// tile / split / pipeline plan of one layer's weight-gradient launch.  v2: tc_dw2_kernel (X^T in tensor memory, dZ converted
+// in place as the shared-memory operand) for N_out % 32 == 0; otherwise the first form (dZ^T in tensor memory).
+struct DwPlan {
+  bool v2;
+  int BN, kt, n_mt, nxc, tiles_i, tiles_j, splits, stages, a_ring;
+};
+DwPlan dw_plan(int n_groups, int M, int N, int K, int act) {
+  DwPlan d = {};
+  // (K_in < 64, the first layer: measured 35.8 us (first form) against 37.9 us at 32768 x 256 x 37 - both at the HBM
+  // bound of the dY / Y stream, the first form with the smaller conversion share)
+  if (dw2_enabled() && N % 32 == 0 && (K >= 64 || dw2_enabled() == 2)) {
+    d.kt = K > 128 ? 256 : 128, d.n_mt = d.kt / 128;
+    d.BN = d.n_mt == 2 ? (N < 128 ? N : 128) : (N < 256 ? N : 256);
+    if (N % d.BN == 0) {
+      d.nxc = ((K < d.kt ? K : d.kt) + 31) / 32;
+      d.tiles_i = (K + d.kt - 1) / d.kt, d.tiles_j = N / d.BN;
+      const int stage = 2 * d.BN * kBK * 4 + d.nxc * kChunk;
+      d.stages = (227 * 1024 - 2048 - kDw2BiasBytes) / stage;
+      if (d.stages > kMaxStages) d.stages = kMaxStages;
+      d.a_ring = (512 - d.n_mt * d.BN) / (d.n_mt * 64);
+      if (d.a_ring > d.stages) d.a_ring = d.stages;
+      d.v2 = d.stages >= 2 && d.a_ring >= 2;
+    }
+  }
+  if (!d.v2) {
+    d.BN = dw_bn(K);
+    d.tiles_i = (N + kBM - 1) / kBM, d.tiles_j = (K + d.BN - 1) / d.BN;
+    d.stages = pick_stages(kDw, act, d.BN);
+  }
+  d.splits = tc_dw_splits(M, d.tiles_i * d.tiles_j * n_groups);
+  return d;
+}
 }  // namespace
 
 extern "C" size_t mnr_tc_linear_bwd_weight_workspace_bytes(int n_groups, int M, int N, int K) {
   if (n_groups <= 0 || M <= 0 || N <= 0 || K <= 0) return 0;
-  const int BN = dw_bn(K);
-  const int tiles = ((N + kBM - 1) / kBM) * ((K + BN - 1) / BN) * n_groups;
-  return (size_t)n_groups * tc_dw_splits(M, tiles) * ((size_t)N * K + 2 * (size_t)N) * sizeof(float);  // dW + 2 db slabs per split
+  const DwPlan d = dw_plan(n_groups, M, N, K, 1);
+  return (size_t)n_groups * d.splits * ((size_t)N * K + 2 * (size_t)N) * sizeof(float);  // dW + 2 db slabs per split
 }
 
 namespace {
@@ -730,7 +1079,8 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
   if (workspace_bytes < mnr_tc_linear_bwd_weight_workspace_bytes(n_groups, M, N, K)) return MNR_EWORKSPACE;
   if (!mnr_aligned(workspace, 16)) return MNR_EALIGN;
   TcParams p;
-  p.BN = dw_bn(K);
+  const DwPlan d = dw_plan(n_groups, M, N, K, act);
+  p.BN = d.BN;
   bool want_bias = false;
   for (int k = 0; k < kMaxGroups; ++k) job->w[k] = nullptr, job->b[k] = nullptr;
   for (int k = 0; k < n_groups; ++k) {
@@ -749,17 +1099,37 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
     job->w[k] = s.c, job->b[k] = s.bias_grad;
     want_bias = want_bias || s.bias_grad != nullptr;
   }
-  const int ti = (N + kBM - 1) / kBM, tj = (K + p.BN - 1) / p.BN;
-  const int splits = tc_dw_splits(M, ti * tj * n_groups);
+  const int splits = d.splits;
   // (N % 4 == 0 was checked above, so N*K is a multiple of 4 and every dW / partial slab is 16 B aligned)
   job->partials = (const float*)workspace, job->n_groups = n_groups, job->splits = splits, job->I = N, job->J = K;
   job->wblocks = (N * K / 4 + 31) / 32;
   if (!launch_it) return MNR_OK;
   p.I = N, p.J = K, p.R = M, p.ldc = K, p.act = act, p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 31) / 32 * 32;
-  p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = pick_stages(kDw, act, p.BN);
+  p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = d.stages;
   p.tma_store = 0;
-  dim3 grid(ti, tj, n_groups * splits);
+  if (d.v2) {
+    p.kt = d.kt, p.n_mt = d.n_mt, p.a_ring = d.a_ring, p.nxc = d.nxc;
+    p.tiles_i = d.tiles_i, p.tiles_j = d.tiles_j;
+    const int n_tiles = d.tiles_i * d.tiles_j * n_groups * splits;
+    const int sms = mnr_sm_count();
+    dim3 grid(n_tiles < sms ? n_tiles : sms);
+    const size_t smem = (size_t)d.stages * (2 * d.BN * kBK * 4 + d.nxc * kChunk) + kDw2BiasBytes + 1024;
+    cudaError_t e = cudaSuccess;
+#define MNR_DW2_LAUNCH(ACTV)                                                                                        \
+  e = cudaFuncSetAttribute(tc_dw2_kernel<ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+  if (e == cudaSuccess) e = mnr_launch_pdl(tc_dw2_kernel<ACTV>, grid, dim3(kThreads), smem, stream, p);
+    switch (act) {
+      case 1: MNR_DW2_LAUNCH(1) break;
+      case 2: MNR_DW2_LAUNCH(2) break;
+      default: MNR_DW2_LAUNCH(0) break;
+    }
+#undef MNR_DW2_LAUNCH
+    if (e != cudaSuccess) return (int)e;
+    e = cudaPeekAtLastError();
+    return e == cudaSuccess ? MNR_OK : (int)e;
+  }
+  dim3 grid(d.tiles_i, d.tiles_j, n_groups * splits);
   return launch<kDw>(p, grid, stream);
 }
 

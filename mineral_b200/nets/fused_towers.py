@@ -117,6 +117,9 @@ class TowerStack:
         # whole-tower forward kernel: three plain (Linear -> act) layers of the shapes csrc/tc_tower.cu takes
         self.fused_fwd = (self.use_tc and not self.normed and self.L == 3
                           and ops.tc_tower_fwd_supported(self.in_dim, widths, self.gemm_act))
+        # set by the owner when the producer of dY[-1] already applied act'(Y[-1]) (the fused heads + loss kernel with
+        # cfg.dz_act): the top layer's backward GEMMs then take dZ directly and load no saved-output tile
+        self.top_is_dz = False
 
     def _split_weights(self):
         """W -> (hi, lo) tf32 parts for every layer of every tower, one launch per 8 matrices."""
@@ -186,36 +189,38 @@ class TowerStack:
                 ops.ln_act_bwd([dict(z=self.Z[i][g], gamma=self.norm[g][i].weight.data, beta=self.norm[g][i].bias.data, mean=self.mean[i][g],
                                      rstd=self.rstd[i][g], dy=self.dY[i][g], dz=self.dY[i][g], dgamma=self.norm[g][i].weight.grad,
                                      dbeta=self.norm[g][i].bias.grad) for g in range(G)], M, n, self.act, self.ln_ws[i])
-            saved = [None] * G if self.normed else self.Y[i]
+            dz_in = self.normed or (i == top and self.top_is_dz)
+            saved = [None] * G if dz_in else self.Y[i]
+            act_i = 0 if dz_in else self.gemm_act
             wg = [dict(a=self.dY[i][g], b=src[g], c=self.lin[g][i].weight.grad, saved=saved[g], bias_grad=self.lin[g][i].bias.grad, N=n, K=k,
                        ldb=ldb) for g in range(G)]
             if not weight_grads:
                 pass
             elif tc:
-                pending.append(ops.tc_linear_bwd_weight_partials(wg, M, self.gemm_act, self.tc_ws[i]))
+                pending.append(ops.tc_linear_bwd_weight_partials(wg, M, act_i, self.tc_ws[i]))
                 if len(pending) == 4:
                     ops.tc_reduce_partials(pending)
                     pending = []
             else:
-                ops.linear_bwd_weight(wg, M, self.gemm_act, self.ws)
+                ops.linear_bwd_weight(wg, M, act_i, self.ws)
             if i == 0 and input_grad is not None:
                 if isinstance(input_grad, (list, tuple)):
                     # one tensor-core launch for all towers, each into its own contiguous (rows, K) tensor (the caller adds them)
                     assert self.use_tc and len(input_grad) == G
                     ops.tc_linear_bwd_input([dict(a=self.dY[0][g], b=self.w_hi[0][g], b_lo=self.w_lo[0][g], c=input_grad[g], saved=saved[g],
-                                                  N=n, K=k, ldb=self.w_ld[0]) for g in range(G)], M, self.gemm_act)
+                                                  N=n, K=k, ldb=self.w_ld[0]) for g in range(G)], M, act_i)
                 else:
                     # SIMT kernel, one launch per tower: the second accumulates onto the first's result
                     for g in range(G):
                         ops.linear_bwd_input([dict(a=self.dY[0][g], b=self.lin[g][0].weight.data, c=input_grad, saved=saved[g], N=n, K=k)],
-                                             M, self.gemm_act, accumulate=g > 0)
+                                             M, act_i, accumulate=g > 0)
             if i > 0:
                 if self.use_tc:
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],
-                                                  saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, self.gemm_act)
+                                                  saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, act_i)
                 else:
                     ops.linear_bwd_input([dict(a=self.dY[i][g], b=self.lin[g][i].weight.data, c=self.dY[i - 1][g], saved=saved[g], N=n, K=k)
-                                          for g in range(G)], M, self.gemm_act)
+                                          for g in range(G)], M, act_i)
         if pending:
             ops.tc_reduce_partials(pending)
 
@@ -296,6 +301,14 @@ class FusedTowers:
     def fused_heads_ok(self):
         h = self.widths[-1]
         return h % 8 == 0 and h <= 128 and self.A <= 32
+
+    def heads_dz_act(self):
+        """Activation code the fused heads kernel should fold into its dY3 output (cfg.dz_act), or 0.  Enables
+        `stack.top_is_dz` as a side effect so that the towers' backward matches."""
+        ok = (self.fused_heads_ok and not self.normed and self.gemm_act in (1, 2)
+              and bool(ops.lib.mnr_ppo_heads_is_fused(self.A, self.widths[-1])))
+        self.stack.top_is_dz = ok
+        return self.gemm_act if ok else 0
 
     def heads_loss_fwd_bwd(self, d, s, e, g_mu, g_ls, g_v, metrics, cfg, ws, mu_mean, sigma_mean):
         """Heads forward + PPO loss + its backward + head parameter gradients + d loss / d Y[-1] (csrc/heads_fused.cu,

@@ -225,7 +225,8 @@ def ppo_loss_workspace(mb, A, device):
 
 
 def make_loss_cfg(dist_type="normal", minstd=1.0, maxstd=1.0, e_clip=0.2, use_smooth_clamp=False, clip_value_loss=False,
-                  critic_coef=1.0, entropy_coef=0.0, bounds_loss_coef=0.0, bounds_type="bound", soft_bound=1.1, grad_scale=1.0, metric_scale=1.0):
+                  critic_coef=1.0, entropy_coef=0.0, bounds_loss_coef=0.0, bounds_type="bound", soft_bound=1.1, grad_scale=1.0, metric_scale=1.0,
+                  dz_act=0):
     dt = {"normal": nv.DIST_NORMAL, "dreamerv3_normal": nv.DIST_DREAMERV3_NORMAL}.get(dist_type)
     if dt is None:
         raise NotImplementedError(f"dist_type {dist_type!r} is not on the accelerated PPO path")
@@ -233,7 +234,7 @@ def make_loss_cfg(dist_type="normal", minstd=1.0, maxstd=1.0, e_clip=0.2, use_sm
     if bt is None:
         raise NotImplementedError(bounds_type)
     return nv.PPOLossCfg(dt, bt, int(bool(use_smooth_clamp)), int(bool(clip_value_loss)), minstd, maxstd, e_clip,
-                         critic_coef, entropy_coef, bounds_loss_coef, soft_bound, grad_scale, metric_scale, 0.0)
+                         critic_coef, entropy_coef, bounds_loss_coef, soft_bound, grad_scale, metric_scale, int(dz_act))
 
 
 def ppo_loss_fwd_bwd(mu_raw, logstd, value, actions, old_neglogp, advantages, old_values, returns, old_mu, old_sigma,

@@ -87,7 +87,13 @@ def test_tc_bwd_input(M, N, K, act):
         scale_close(grp["c"], ref, 5e-6, f"dx {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("M,N,K,act", CASES[:5] + [(32768, 128, 256, 1)])
+# both forms of the weight-gradient kernel: N % 32 == 0 -> tc_dw2_kernel (X^T in tensor memory, one / two lane tiles, K and N
+# tiling, ragged K, ragged M), else the first form
+DW_CASES = CASES[:5] + [(32768, 128, 256, 1), (32768, 64, 128, 1), (32768, 256, 37, 1), (2048, 512, 88, 0), (2048, 256, 512, 0),
+                        (1000, 48, 100, 1), (200, 96, 200, 1), (70, 32, 300, 2)]
+
+
+@pytest.mark.parametrize("M,N,K,act", DW_CASES)
 def test_tc_bwd_weight(M, N, K, act):
     from mineral_b200 import ops
 
