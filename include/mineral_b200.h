@@ -522,6 +522,14 @@ int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, float* exp_av
                         mnr_optim_state_t* st, const float* kl, float* grad_norm_out, int nan_to_num,
                         float* clipped_norm_out, void* workspace, size_t workspace_bytes, mnr_stream_t stream);
 
+/* Ride-along job for the NEXT mnr_fused_clip_adam / mnr_peer_reduce_clip_adam[_pp] launch issued by this host thread: extra CTAs
+ * of that launch (the optimizer's own cover one float4 per thread and leave most SMs idle for the PPO towers) compute
+ * y[r * y_ld + c] = clamp((x[r * cols + c] - mean[c]) / denom[c]) - exactly mnr_rms_apply_ld_f32 (RunningMeanStd.normalize,
+ * mineral/common/normalizers.py:57-68) - for the following optimizer step's minibatch, so that launch leaves the step's
+ * chain.  The job is consumed (and cleared) by that launch; x / y must not alias anything the optimizer step touches. */
+int mnr_optim_queue_normalise(const float* x, float* y, int64_t rows, int cols, int y_ld, const float* mean_f32,
+                              const float* denom_f32, float clamp_lo, float clamp_hi);
+
 /* ------------------------------------------------------------------------------------
  * a16  SHAC / SAPO critic regression loss (SHAC.compute_critic_loss, mineral/agents/diffrl/shac.py:869-875):
  *      loss = mean_k mean_rows (pred_k - target)^2 and its gradient g_k = 2 (pred_k - target) / (rows * n_critics).

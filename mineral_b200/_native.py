@@ -162,6 +162,7 @@ SIGNATURES = {
     "mnr_heads_trace": (i32, [i32, vp]),
     "mnr_split_tf32": (i32, [C.POINTER(SplitJob), i32, vp]),
     "mnr_rms_apply_ld_f32": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32, vp]),
+    "mnr_optim_queue_normalise": (i32, [vp, vp, i64, i32, i32, vp, vp, f32, f32]),
     "mnr_colsum_workspace_bytes": (sz, [i32]),
     "mnr_colsum_f32": (i32, [vp, i64, i32, vp, vp, sz, vp]),
     "mnr_grad_norm_workspace_bytes": (sz, [i64]),

@@ -679,6 +679,10 @@ class _UpdateEngine:
         # GEMM kernels own every SM, so the forked kernel's CTAs only delay their tiles, and the cross-stream graph edges
         # cost more than the 7 us launch they hide.  Default: in line.
         fork = n is not None and os.environ.get('MNR_RMS_FORK', '0') == '1'
+        # Default: the normalisation of step s + 1's rows rides along in step s's optimizer launch (extra CTAs beside the
+        # optimizer's own, mnr_optim_queue_normalise): only the first step of an update has its own launch.
+        # MNR_RMS_RIDE=0: one mnr_rms_apply_ld_f32 launch per step (A/B measurements).
+        ride = n is not None and not fork and os.environ.get('MNR_RMS_RIDE', '1') != '0'
         main = torch.cuda.current_stream()
         if fork:
             if getattr(self, '_side', None) is None:
@@ -710,7 +714,8 @@ class _UpdateEngine:
                             ready = torch.cuda.Event()
                             ready.record(self._side)
                 elif n is not None:   # normalise + clamp into the padded (TMA-friendly) row stride; pad columns stay zero
-                    ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, x_buf, x_ld)
+                    if not ride or step == 0:
+                        ops.rms_apply_ld(v[s:e], n['mean_tab'][step], n['denom_tab'][step], clamp, x_buf, x_ld)
                 else:
                     x_buf[:, :v.shape[1]].copy_(v[s:e])
                 m = self.metrics[step]
@@ -729,6 +734,9 @@ class _UpdateEngine:
                                          self.g_v, a.optim.tail if peer else m, self.loss_cfg, self.loss_ws, True,
                                          self.mu_mean[step], self.sigma_mean[step])
                     self.towers.backward(x_buf, self.g_mu, self.g_ls, self.g_v)
+                if ride and step + 1 < total:   # x_buf was last read by this step's first-layer weight gradient: done by then
+                    j = (step + 1) % self.num_mb
+                    ops.optim_queue_normalise(v[j * mb:(j + 1) * mb], n['mean_tab'][step + 1], n['denom_tab'][step + 1], clamp, x_buf, x_ld)
                 # clip_grad_norm_ + Adam(W) + zero_grad: one launch; with peers also the gradient + metrics all-reduce over NVLink
                 if peer:   # the last step of the update keeps the second barrier: its region is the next update's first target
                     a.optim.step(max_norm, grad_norm_out=self.grad_norms[step:step + 1], metrics_out=m, kl_index=7,

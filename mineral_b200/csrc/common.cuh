@@ -152,13 +152,14 @@ __device__ __forceinline__ bool last_block_ticket(unsigned int* counter, unsigne
 // Grid-wide barrier among the CTAs of one launch, ALL of which must be resident (grid <= SMs x occupancy).
 // `state` = two zero-initialised 64-bit words {arrivals, generation}; the last CTA to arrive resets the arrivals and
 // bumps the generation, so the words need no reset between launches / graph replays and any grid size may use them.
-__device__ __forceinline__ void grid_barrier(unsigned long long* state) {
+// `n_ctas`: how many CTAs take part (default: the whole grid).
+__device__ __forceinline__ void grid_barrier(unsigned long long* state, unsigned int n_ctas = 0) {
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long gen, v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(gen) : "l"(state + 1) : "memory");
     __threadfence();
-    if (atomicAdd(state, 1ull) == (unsigned long long)gridDim.x - 1ull) {
+    if (atomicAdd(state, 1ull) == (unsigned long long)(n_ctas ? n_ctas : gridDim.x) - 1ull) {
       state[0] = 0ull;
       __threadfence();
       asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(state + 1), "l"(gen + 1ull) : "memory");

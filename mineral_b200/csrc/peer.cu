@@ -111,7 +111,23 @@ struct SplitTable {
 };
 constexpr size_t kSplitTableOffset = kWsHeader + 160 * sizeof(double);
 
+// Ride-along job of the optimizer launch (mnr_optim_queue_normalise): CTAs behind the optimizer's own (which fill only a third of
+// the GPU for the PPO towers: one float4 per thread) normalise + clamp the NEXT optimizer step's input rows into the padded buffer
+// the first tower layer reads - mnr_rms_apply_ld_f32's arithmetic, element for element - so that 7 us launch leaves the step.
+struct AuxNormalise {
+  const float* x;
+  float* y;
+  int64_t total;   // rows * cols; 0 = no job
+  int cols, y_ld;
+  const float* mean;
+  const float* denom;
+  float lo, hi;
+  int blocks;
+};
+
 struct AdamArgs {
+  AuxNormalise aux;
+  int main_blocks;   // CTAs [0, main_blocks) run the optimizer step (and its grid barrier), the rest the ride-along job
   float* param;
   float* m;
   float* v;
@@ -169,10 +185,22 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   mnr::pdl_wait();
   const int world = WORLD == 1 ? 1 : c.world;
   const int tid = threadIdx.x;
+  if ((int)blockIdx.x >= a.main_blocks) {   // ride-along CTAs: independent of everything below, no barrier
+    const AuxNormalise& x = a.aux;
+    const int64_t astride = (int64_t)x.blocks * kThreads;
+    for (int64_t i = (int64_t)((int)blockIdx.x - a.main_blocks) * kThreads + tid; i < x.total; i += astride) {
+      const int64_t r = i / x.cols;
+      const int cc = (int)(i - r * x.cols);
+      float y = __fdiv_rn(__fsub_rn(mnr::ld_stream(x.x + i), __ldg(x.mean + cc)), __ldg(x.denom + cc));   // normalizers.py:65-68
+      if (x.lo <= x.hi) y = fminf(fmaxf(y, x.lo), x.hi);
+      x.y[r * x.y_ld + cc] = y;
+    }
+    return;
+  }
   for (int w = tid; w < (int)(sizeof(SplitTable) / 4); w += kThreads)   // visible after the barriers below
     reinterpret_cast<uint32_t*>(&s_split)[w] = reinterpret_cast<const uint32_t*>(a.split)[w];
   const int64_t n4 = a.n >> 2;
-  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  const int64_t stride = (int64_t)a.main_blocks * kThreads;
   const int64_t first = (int64_t)blockIdx.x * kThreads + tid;
 
   // optimizer scalars of the PREVIOUS step, read before anyone (block 0, after the grid barrier) updates them
@@ -232,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
     for (int x = 0; x < kThreads / 32; ++x) s += s_w[x];
     a.parts[blockIdx.x] = s;
   }
-  mnr::grid_barrier(a.counter);
+  mnr::grid_barrier(a.counter, (unsigned int)a.main_blocks);
   if (tr) tr[3] = globaltimer_ns();
 
   // A barrier spin of THIS launch timed out in some CTA (a dead or diverged peer): the sums above hold stale or partial
@@ -249,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   // ---- phase 2: every CTA derives the same clip coefficient and Adam scalars ----
   if (tid < 32) {
     double mine = 0;
-    for (unsigned int x = tid; x < gridDim.x; x += 32) mine += __ldcg(a.parts + x);
+    for (int x = tid; x < a.main_blocks; x += 32) mine += __ldcg(a.parts + x);
     // fixed-order tree over the 32 lanes: identical in every CTA (and on every rank)
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, d);
@@ -367,6 +395,26 @@ int make_comm(const mnr_peer_comm_t* comm, Comm& c) {
   }
   c.rank = comm->rank, c.world = comm->world;
   return MNR_OK;
+}
+
+// the job queued by mnr_optim_queue_normalise for the next optimizer launch of this host thread
+thread_local AuxNormalise t_aux_pending = {};
+
+// grid = optimizer CTAs + ride-along CTAs; fills a.aux / a.main_blocks and clears the pending job
+int adam_grid(int64_t n);
+dim3 adam_launch_grid(AdamArgs& a, int64_t n) {
+  a.main_blocks = adam_grid(n);
+  a.aux = t_aux_pending;
+  t_aux_pending = AuxNormalise{};
+  int extra = 0;
+  if (a.aux.total > 0) {
+    int64_t want = (a.aux.total + (int64_t)kThreads * 8 - 1) / ((int64_t)kThreads * 8);   // >= 8 elements per thread
+    const int cap = mnr_sm_count();
+    extra = (int)(want > cap ? cap : want);
+    if (extra < 1) extra = 1;
+  }
+  a.aux.blocks = extra;
+  return dim3(a.main_blocks + extra);
 }
 
 int adam_grid(int64_t n) {
@@ -491,9 +539,17 @@ extern "C" int mnr_fused_clip_adam(float* param, float* grad, float* exp_avg, fl
   Comm c;
   for (int r = 0; r < kMaxPeers; ++r) c.base[r] = nullptr;
   c.rank = 0, c.world = 1;
-  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<1>, dim3(adam_grid(n)), dim3(kThreads), 0, mnr_cs(stream), c, a);
+  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<1>, adam_launch_grid(a, n), dim3(kThreads), 0, mnr_cs(stream), c, a);
   if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
+}
+
+extern "C" int mnr_optim_queue_normalise(const float* x, float* y, int64_t rows, int cols, int y_ld, const float* mean_f32,
+                                         const float* denom_f32, float clamp_lo, float clamp_hi) {
+  MNR_CHECK_PTR(x); MNR_CHECK_PTR(y); MNR_CHECK_PTR(mean_f32); MNR_CHECK_PTR(denom_f32);
+  if (rows < 0 || cols <= 0 || y_ld < cols) return MNR_ESHAPE;
+  t_aux_pending = AuxNormalise{x, y, rows * cols, cols, y_ld, mean_f32, denom_f32, clamp_lo, clamp_hi, 0};
+  return MNR_OK;
 }
 
 extern "C" int mnr_peer_reduce_clip_adam_pp(const mnr_peer_comm_t* comm, size_t grad_offset, size_t zero_offset, int end_barrier, int64_t n,
@@ -517,7 +573,7 @@ extern "C" int mnr_peer_reduce_clip_adam_pp(const mnr_peer_comm_t* comm, size_t 
   a.grad = reinterpret_cast<float*>(c.base[c.rank] + grad_offset);
   a.zero_other = zero_offset ? reinterpret_cast<float*>(c.base[c.rank] + zero_offset) : nullptr;
   a.end_barrier = end_barrier ? 1 : 0, a.trace = trace;
-  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<0>, dim3(adam_grid(n)), dim3(kThreads), 0, mnr_cs(stream), c, a);
+  const cudaError_t le = mnr_launch_pdl(reduce_clip_adam_kernel<0>, adam_launch_grid(a, n), dim3(kThreads), 0, mnr_cs(stream), c, a);
   if (le != cudaSuccess) return (int)le;
   MNR_LAUNCH_RESULT();
 }

@@ -353,6 +353,15 @@ def rms_apply_ld(x, mean_f32, denom_f32, clamp, out, out_ld):
     return out
 
 
+def optim_queue_normalise(x, mean_f32, denom_f32, clamp, out, out_ld):
+    """rms_apply_ld as a ride-along job of the NEXT fused optimizer launch of this thread (mnr_optim_queue_normalise)."""
+    cols = mean_f32.numel()
+    rows = x.numel() // cols
+    lo, hi = clamp if clamp is not None else (1.0, -1.0)
+    check(lib.mnr_optim_queue_normalise(ptr(x, F32, "x"), ptr(out, F32, "out"), rows, cols, out_ld, ptr(mean_f32, F32), ptr(denom_f32, F32),
+                                        lo, hi), "mnr_optim_queue_normalise", kernels=0)
+
+
 def linear_fwd(groups, M, act):
     check(lib.mnr_linear_fwd(_linear_groups(groups), len(groups), M, act, stream()), "mnr_linear_fwd")
 
