@@ -721,7 +721,20 @@ def main():
         f_fwd = sum(2.0 * 2 * M * k * n for k, n in zip(ks, widths))          # 2 towers
         f_dx = sum(2.0 * 2 * M * k * n for k, n in zip(ks[1:], widths[1:]))
         flops = 2 * f_fwd + f_dx                                               # forward + dW + dX
-        n_launch = 2 * L + (L - 1)
+        fused_fwd = bool(getattr(tw.stack, "fused_fwd", False))   # whole-tower forward kernel (csrc/tc_tower.cu): one launch
+        n_launch = (1 if fused_fwd else L) + L + (L - 1)
+        # The same launches against the HBM roofline: what every launch must move when each layer is its own kernel (operands read
+        # once, result written once, f32): forward X + all Y_l; dW_l reads dY_l, Y_l (act' from the saved output; not for a top layer
+        # that receives dZ from the heads kernel, nor behind a LayerNorm) and Y_{l-1}; dX_l reads dY_l, Y_l and writes dY_{l-1}.
+        G2 = 2
+        top_dz = bool(getattr(tw.stack, "top_is_dz", False))
+        by = 4.0 * M * (x_ld + G2 * sum(widths))
+        for li in range(L):
+            saved = 0 if (tw.normed or (li == L - 1 and top_dz)) else widths[li]
+            k_in = x_ld if li == 0 else widths[li - 1]
+            by += 4.0 * M * G2 * (widths[li] + saved + k_in) - (4.0 * M * x_ld if li == 0 else 0)   # X is shared by both towers
+            if li > 0:
+                by += 4.0 * M * G2 * (widths[li] + saved + widths[li - 1])
         # the split-partials reduce (tc_reduce_kernel) is not a tensor-core kernel: it is taken out of the timed sequence; behind a
         # LayerNorm the LN passes (mnr_ln_act_fwd / _bwd) sit between the GEMMs and are timed separately and subtracted
         real_reduce = ops.tc_reduce_partials
@@ -765,7 +778,8 @@ def main():
         tpeak = peaks.get("bf16_tflops", 1590.0)
         tpeak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback (B200_PROFILING.md)"
         roofline_tensor = {
-            "kernel": f"tc_linear_kernel<FWD|DX|DW> (tcgen05 kind::tf32, TMEM accumulators, TMA operands): the {n_launch} tower GEMM launches of one "
+            "kernel": ("tc_tower_fwd_kernel + tc_dw2_kernel / tc_linear_kernel<DX|DW>" if fused_fwd else "tc_linear_kernel<FWD|DX|DW> + tc_dw2_kernel") +
+                      f" (tcgen05 kind::tf32, TMEM accumulators, TMA operands): the {n_launch} tower GEMM launches of one "
                       f"optimizer step, 2 towers x ({M} rows, {in_dim}->" + "->".join(str(x) for x in widths) + ")",
             "bound": "tensor", "achieved": flops / (t_gemm * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
             "frac": flops / (t_gemm * 1e-3) / 1e12 / tpeak, "traffic": None, "peak_source": tpeak_src,
@@ -776,7 +790,13 @@ def main():
             "note": "achieved counts fp32-EQUIVALENT FLOPs (2MNK per GEMM with the real K); the tensor pipe executes 3x that in tf32 (3xTF32 "
                     "split: the 1e-5 parity bar rules out single-pass tf32 / bf16), and tf32 runs at half the bf16 rate used as `peak`, so a "
                     "perfect 3xTF32 kernel reads frac = 1/6 = 0.167",
-            "frac_of_3xtf32_ceiling": flops / (t_gemm * 1e-3) / 1e12 / (tpeak / 6.0)}
+            "frac_of_3xtf32_ceiling": flops / (t_gemm * 1e-3) / 1e12 / (tpeak / 6.0),
+            # the same launches are HBM-bound at this network size (27 fp32 FLOP per byte, ridge of the 3xTF32 pipe ~ 40): their
+            # per-layer compulsory traffic over the same time, against the measured copy bandwidth
+            "hbm_view": {"bound": "hbm", "algorithmic_bytes": by, "achieved": by / (t_gemm * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": by / (t_gemm * 1e-3) / 1e9 / peak,
+                         "what": "sum over the launches of operands read once + result written once (f32); layer outputs are saved for "
+                                 "the backward pass, so every layer boundary crosses HBM unless L2 still holds it"}}
 
     # ---- share of the update each kernel takes, from the committed ncu launch list of this command (profiles/) ----
     shares = None

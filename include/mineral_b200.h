@@ -386,7 +386,14 @@ typedef struct {
   int32_t n_groups, M;
   void* workspace;
   size_t workspace_bytes;
+  int32_t grid_cap;                 /* the mnr_tc_grid_cap value in force when _partials was launched (0 = none) */
+  int32_t _pad;
 } mnr_tc_reduce_job_t;
+/* CTAs the following mnr_tc_linear_* launches of this host thread may use (0 = one per SM, the default); returns the previous
+ * value.  A layer's input-gradient and weight-gradient launches do not depend on each other: capped to complementary shares of
+ * the SMs and issued on two streams they run side by side.  mnr_tc_linear_bwd_weight_workspace_bytes depends on the cap in
+ * force (the split count follows the CTA count): size the workspace under the same cap as the launch. */
+int mnr_tc_grid_cap(int ctas);
 int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
 
 /* A whole 3-layer tower forward in ONE launch (csrc/tc_tower.cu): y[l] = act(y[l-1] . W_l^T + bias_l), y[-1] = x, for every

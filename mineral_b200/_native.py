@@ -85,7 +85,7 @@ class LnGroup(C.Structure):
 
 class TcReduceJob(C.Structure):
     _fields_ = [("groups", C.POINTER(LinearGroup)), ("n_groups", C.c_int32), ("M", C.c_int32), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t)]
+                ("workspace_bytes", C.c_size_t), ("grid_cap", C.c_int32), ("_pad", C.c_int32)]
 
 
 class TowerGroup(C.Structure):
@@ -156,6 +156,7 @@ SIGNATURES = {
     "mnr_tc_linear_bwd_weight_partials": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
     "mnr_tc_reduce_partials": (i32, [C.POINTER(TcReduceJob), i32, vp]),
     "mnr_tc_trace": (i32, [i32, vp]),
+    "mnr_tc_grid_cap": (i32, [i32]),
     "mnr_tc_tower_fwd_supported": (i32, [i32, C.POINTER(C.c_int32), i32, i32]),
     "mnr_tc_tower_fwd": (i32, [C.POINTER(TowerGroup), i32, i32, i32, C.POINTER(C.c_int32), i32, i32, vp]),
     "mnr_tc_tower_trace": (i32, [i32, vp]),

@@ -35,6 +35,14 @@ constexpr int kMaxStages = 6;
 
 enum Mode { kFwd = 0, kDx = 1, kDw = 2 };
 
+// mnr_tc_grid_cap: CTAs the NEXT launches of this host thread may use (0 = one per SM).  Two launches that do not depend on
+// each other (a layer's input-gradient and weight-gradient kernels) can then run side by side on disjoint SMs from two streams.
+thread_local int t_grid_cap = 0;
+int eff_sms() {
+  const int s = mnr_sm_count();
+  return (t_grid_cap > 0 && t_grid_cap < s) ? t_grid_cap : s;
+}
+
 // optional timeline of CTA 0 (debug / profiling aid): [role][event][tag] = clock64()
 __device__ long long g_trace[4 * 256 * 2];
 __device__ int g_trace_on = 0;
@@ -902,7 +910,7 @@ template <int MODE>
 int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   p.tiles_i = (int)tiles.x, p.tiles_j = (int)tiles.y;
   const int n_tiles = (int)(tiles.x * tiles.y * tiles.z);
-  const int sms = mnr_sm_count();
+  const int sms = eff_sms();
   dim3 grid(n_tiles < sms ? n_tiles : sms);  // persistent: one CTA per SM walks the tiles
   const int stage = stage_bytes_of(MODE, p.act, p.BN);
   const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
@@ -924,6 +932,12 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
 int ld_or(int ld, int dflt) { return ld > 0 ? ld : dflt; }
 
 }  // namespace
+
+extern "C" int mnr_tc_grid_cap(int ctas) {
+  const int prev = t_grid_cap;
+  t_grid_cap = ctas > 0 ? ctas : 0;
+  return prev;
+}
 
 extern "C" int mnr_tc_supported(void) { return encode_fn() != nullptr ? 1 : 0; }
 
@@ -1003,7 +1017,7 @@ int tc_dw_splits(int M, int tiles) {
   // Split the reduction (the minibatch rows) so that (a) one accumulation chain in TMEM covers <= 512 rows: the tensor
   // core's fp32 accumulate error grows with the chain length and the parity bar is 1e-5; (b) tiles x splits fills whole
   // waves of the persistent grid (a CTA then walks 2+ work items back to back with double-buffered accumulators).
-  const int sms = mnr_sm_count();
+  const int sms = eff_sms();
   int s_min = (M + 511) / 512;
   if (s_min < 1) s_min = 1;
   const int waves = (tiles * s_min + sms - 1) / sms;
@@ -1112,7 +1126,7 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
     p.kt = d.kt, p.n_mt = d.n_mt, p.a_ring = d.a_ring, p.nxc = d.nxc;
     p.tiles_i = d.tiles_i, p.tiles_j = d.tiles_j;
     const int n_tiles = d.tiles_i * d.tiles_j * n_groups * splits;
-    const int sms = mnr_sm_count();
+    const int sms = eff_sms();
     dim3 grid(n_tiles < sms ? n_tiles : sms);
     const size_t smem = (size_t)d.stages * (2 * d.BN * kBK * 4 + d.nxc * kChunk) + kDw2BiasBytes + 1024;
     cudaError_t e = cudaSuccess;
@@ -1163,9 +1177,12 @@ extern "C" int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs_in, int n_
   MNR_CHECK_PTR(jobs_in);
   if (n_jobs <= 0 || n_jobs > kMaxReduceJobs) return MNR_ESHAPE;
   ReduceJobs jobs;
+  const int cap_now = t_grid_cap;
   for (int q = 0; q < n_jobs; ++q) {
     const mnr_tc_reduce_job_t& in = jobs_in[q];
+    t_grid_cap = in.grid_cap > 0 ? in.grid_cap : 0;   // the split plan of the launch that wrote these partials
     const int rc = dw_launch(in.groups, in.n_groups, in.M, 0, in.workspace, in.workspace_bytes, false, &jobs.j[q], mnr_cs(stream));
+    t_grid_cap = cap_now;
     if (rc != MNR_OK) return rc;
   }
   return reduce_launch(jobs, n_jobs, mnr_cs(stream));

@@ -16,6 +16,8 @@ Supported towers (separate value tower, both towers of the same shape, no dropou
                                                        GEMMs on dZ.
 """
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -111,9 +113,23 @@ class TowerStack:
                 self.w_hi.append([torch.zeros(w, ld, **f32) for _ in range(G)])
                 self.w_lo.append([torch.zeros(w, ld, **f32) for _ in range(G)])
                 k = w
+            # MNR_BWD_FORK=1: a layer's input-gradient and weight-gradient kernels run SIDE BY SIDE on disjoint SMs (two streams,
+            # mnr_tc_grid_cap); MNR_BWD_SPLIT = share of the SMs the input-gradient kernel gets, per layer from the top
+            self.bwd_fork = os.environ.get('MNR_BWD_FORK', '0') == '1'
+            self.bwd_split = [float(v) for v in os.environ.get('MNR_BWD_SPLIT', '0.42,0.53,0.5,0.5').split(',')]
+            self._side = None
+            sms = ops.lib.mnr_sm_count()
+
+            def ws_bytes(l):
+                sizes = [ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape)]
+                if self.bwd_fork:   # the split count follows the CTA count: size for every cap this stack may launch under
+                    for f in self.bwd_split:
+                        ops.tc_grid_cap(sms - max(1, min(sms - 1, round(sms * f))))
+                        sizes.append(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape))
+                    ops.tc_grid_cap(0)
+                return max(max(sizes), 256)
             # one split-partials workspace per layer: the split reduce of all layers is ONE launch after the last layer
-            self.tc_ws = [torch.zeros(max(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(G, rows, *l.weight.shape), 256),
-                                      dtype=torch.uint8, device=device) for l in self.lin[0]]
+            self.tc_ws = [torch.zeros(ws_bytes(l), dtype=torch.uint8, device=device) for l in self.lin[0]]
         # whole-tower forward kernel: three plain (Linear -> act) layers of the shapes csrc/tc_tower.cu takes
         self.fused_fwd = (self.use_tc and not self.normed and self.L == 3
                           and ops.tc_tower_fwd_supported(self.in_dim, widths, self.gemm_act))
@@ -194,6 +210,27 @@ class TowerStack:
             act_i = 0 if dz_in else self.gemm_act
             wg = [dict(a=self.dY[i][g], b=src[g], c=self.lin[g][i].weight.grad, saved=saved[g], bias_grad=self.lin[g][i].bias.grad, N=n, K=k,
                        ldb=ldb) for g in range(G)]
+            fork = self.use_tc and getattr(self, 'bwd_fork', False) and tc and weight_grads and i > 0
+            if fork:   # dX_i on a side stream with its share of the SMs, dW_i on this stream with the rest; joined below
+                sms = ops.lib.mnr_sm_count()
+                f = self.bwd_split[min(top - i, len(self.bwd_split) - 1)]
+                cap_dx = max(1, min(sms - 1, round(sms * f)))
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=self.dY[0][0].device)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    ops.tc_grid_cap(cap_dx)
+                    ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],
+                                                  saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, act_i)
+                ops.tc_grid_cap(sms - cap_dx)
+                pending.append(ops.tc_linear_bwd_weight_partials(wg, M, act_i, self.tc_ws[i]))
+                ops.tc_grid_cap(0)
+                main.wait_stream(self._side)
+                if len(pending) == 4:
+                    ops.tc_reduce_partials(pending)
+                    pending = []
+                continue
             if not weight_grads:
                 pass
             elif tc:

@@ -303,19 +303,29 @@ def tc_linear_bwd_weight(groups, M, act, ws):
           "mnr_tc_linear_bwd_weight", kernels=2)
 
 
+_TC_GRID_CAP = 0
+
+
+def tc_grid_cap(ctas):
+    """CTAs the following tensor-core linear launches of this thread may use (0 = all SMs); returns the previous value."""
+    global _TC_GRID_CAP
+    _TC_GRID_CAP = int(ctas) if ctas and ctas > 0 else 0
+    return lib.mnr_tc_grid_cap(_TC_GRID_CAP)
+
+
 def tc_linear_bwd_weight_partials(groups, M, act, ws):
     """Tensor-core dW / db split partials into `ws` (no reduce); returns the job record for tc_reduce_partials."""
     arr = _linear_groups(groups)
     check(lib.mnr_tc_linear_bwd_weight_partials(arr, len(groups), M, act, ptr(ws, U8), ws.numel(), stream()),
           "mnr_tc_linear_bwd_weight_partials")
-    return (arr, len(groups), M, ws)
+    return (arr, len(groups), M, ws, _TC_GRID_CAP)
 
 
 def tc_reduce_partials(jobs):
     """One launch: sum the split partials of up to 4 layers (records from tc_linear_bwd_weight_partials)."""
     arr = (nv.TcReduceJob * len(jobs))()
-    for i, (groups, n_groups, M, ws) in enumerate(jobs):
-        arr[i] = nv.TcReduceJob(groups, n_groups, M, ptr(ws, U8).value, ws.numel())
+    for i, (groups, n_groups, M, ws, cap) in enumerate(jobs):
+        arr[i] = nv.TcReduceJob(groups, n_groups, M, ptr(ws, U8).value, ws.numel(), cap, 0)
     check(lib.mnr_tc_reduce_partials(arr, len(jobs), stream()), "mnr_tc_reduce_partials")
 
 

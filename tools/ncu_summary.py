@@ -42,6 +42,30 @@ def launches(path):
         print(f'"{k}",{n},{t:.1f},{100 * t / tot:.1f},{t / n:.1f}')
 
 
+def shares(path, workload="ppo_ant_4096x32"):
+    """profiles/rNN_shares.json: what bench.py embeds as `shares` (kernel -> share of the summed kernel time of the launch list)."""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    agg = collections.OrderedDict()
+    for row in csv.DictReader(io.StringIO("".join(lines))):
+        if row.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(row["Metric Value"].replace(",", ""))
+        v = {"ns": v / 1e3, "us": v, "ms": v * 1e3, "s": v * 1e6}[row["Metric Unit"]]
+        name = row["Kernel Name"].split("(")[0].replace("void ", "").replace("<unnamed>::", "")
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += v
+    tot = sum(t for _, t in agg.values())
+    out = {"workload": workload,
+           "source": "ncu --metrics gpu__time_duration.sum --clock-control none launch list of `python bench.py --steps 2 --warmup 3 "
+                     "--no-cpu-baseline --no-kernel-sweep --no-recipes` (cold-cache, serialised launches: shares, not absolute times)",
+           "total_us": round(tot, 1),
+           "kernels": {k: {"launches": n, "total_us": round(t, 1), "share": round(t / tot, 4), "avg_us": round(t / n, 2)}
+                       for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]) if t / tot >= 0.001}}
+    print(json.dumps(out, indent=1))
+
+
 def full(path):
     raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
@@ -56,4 +80,4 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "shares": shares}[sys.argv[1]](*sys.argv[2:])
