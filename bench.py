@@ -36,6 +36,17 @@ WORKLOADS = {
 }
 
 
+def workload_config(name, w, world):
+    """The `config` object of the JSON line: what defines the workload, identical in both arms (`--impl b200` / `--impl reference`)
+    so that the driver can compare them key by key; implementation details (CUDA graph, exchange) go to `impl_config`."""
+    B = w["T"] * w["N"]
+    return {"workload": name, "envs_per_gpu": w["N"], "horizon": w["T"], "obs": w["O"], "act": w["A"], "mlp": w["units"],
+            "variant": w["variant"], "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"],
+            "minibatch_rows": B // w["minibatches"], "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"],
+            "l2": "GPU arm: 256 MiB read-flush between timed steps; CPU arm: not applicable",
+            "parallelism": f"env-sharded dp{world}"}
+
+
 def make_cfg(w, device, multi_gpu, cuda_graph):
     from oracle.reference_shim import to_attr
 
@@ -371,8 +382,8 @@ def run_reference(args, w, rank, world):
         "impl": "reference", "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "envs_per_gpu": w["N"], "horizon": w["T"], "obs": w["O"], "act": w["A"], "mlp": w["units"],
-                   "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "device": "cpu"},
+        "config": workload_config(args.workload, w, args.gpus),
+        "impl_config": {"device": "cpu", "host_threads": cores, "envs_timed": ws["N"]},
         "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -855,11 +866,9 @@ def main():
         "metric": "ppo_update_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "envs_per_gpu": N, "horizon": T, "obs": O, "act": A, "mlp": w["units"], "variant": w["variant"],
-                   "mini_epochs": w["mini_epochs"], "minibatches": w["minibatches"], "minibatch_rows": B // w["minibatches"],
-                   "optimizer_steps_per_update": w["mini_epochs"] * w["minibatches"], "cuda_graph": agent._engine.graph is not None,
-                   "exchange": "none (1 GPU)" if world == 1 else "fused peer-memory all-reduce + clip + Adam kernel over NVLink (csrc/peer.cu)",
-                   "l2": "256 MiB read-flush between timed steps", "parallelism": f"env-sharded dp{world}"},
+        "config": workload_config(args.workload, w, world),
+        "impl_config": {"cuda_graph": agent._engine.graph is not None,
+                        "exchange": "none (1 GPU)" if world == 1 else "fused peer-memory all-reduce + clip + Adam kernel over NVLink (csrc/peer.cu)"},
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "pipeline": "every step uploads its own rollout from pinned host memory (ExperienceBuffer.stage_from_host -> commit_staged) and "
                             "copies its metrics to pinned host memory; the upload of step i+1 runs on the copy engines under step i's update and "
@@ -884,8 +893,8 @@ def main():
     if peer_breakdown is not None:
         line["peer_kernel_breakdown"] = peer_breakdown
     if world > 1:
-        line["config"]["exchange_barriers_per_step"] = 2 if os.environ.get("MNR_PEER_END_BARRIER", "0") == "1" else 1
-        line["config"]["host_threads_pinned_near_gpu"] = numa
+        line["impl_config"]["exchange_barriers_per_step"] = 2 if os.environ.get("MNR_PEER_END_BARRIER", "0") == "1" else 1
+        line["impl_config"]["host_threads_pinned_near_gpu"] = numa
     print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
