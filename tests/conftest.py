@@ -38,4 +38,10 @@ def scale_close(a, b, tol=1e-5, msg=""):
     a, b = torch.where(both_nan, torch.zeros_like(a), a), torch.where(both_nan, torch.zeros_like(b), b)
     scale = max(b.abs().max().item(), 1e-30)
     err = (a - b).abs().max().item()
+    if _TOL_REPORT is not None and tol > 1e-5:   # MNR_TOL_REPORT=<file>: log how much of every tolerance above 1e-5 is used
+        with open(_TOL_REPORT, "a") as f:
+            f.write(f"{os.environ.get('PYTEST_CURRENT_TEST', '?').split(' ')[0]}\t{msg}\ttol={tol:g}\tmeasured={err / scale:.3e}\n")
     assert err <= tol * scale, f"{msg}: max|diff|={err:.3e} > {tol:g} * scale({scale:.3e})"
+
+
+_TOL_REPORT = os.environ.get("MNR_TOL_REPORT")

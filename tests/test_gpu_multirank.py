@@ -126,11 +126,11 @@ def test_two_rank_update_equals_single_rank_on_union(graph):
     mp.spawn(_worker, args=(world, 29571 + int(graph), init_sd, ret, graph), nprocs=world, join=True)
     for r in range(world):
         got = ret[r]
-        scale_close(got["loss"], ref["loss"], 2e-5, f"rank{r} losses")
-        scale_close(got["gn"], ref["gn"], 2e-5, f"rank{r} grad norms")
+        scale_close(got["loss"], ref["loss"], 1e-5, f"rank{r} losses")
+        scale_close(got["gn"], ref["gn"], 1e-5, f"rank{r} grad norms")
         assert (got["kl"] - ref["kl"]).abs().max().item() <= 1e-5 * ref["kl"].abs().max().item() + 2e-7
         assert got["lr"] == ref["lr"]
-        scale_close(got["params"], ref["params"], 1e-4, f"rank{r} params")
+        scale_close(got["params"], ref["params"], 1e-5, f"rank{r} params")
         for k in ("obs_mean", "obs_var", "val_mean", "val_var"):
             scale_close(got[k], ref[k], 1e-6, f"rank{r} {k}")
     assert torch.equal(ret[0]["params"], ret[1]["params"]), "ranks diverged"

@@ -276,9 +276,9 @@ def test_shac_update_critic_matches_reference_golden(cuda_graph):
             res = ag.update_critic()
             tag = f"critics={c['n_critics']} graph={cuda_graph} rep={rep}"
             for k, v in c["results"].items():
-                scale_close(torch.stack(res[k]), v, 2e-5, f"{tag} {k}")
+                scale_close(torch.stack(res[k]), v, 1e-5, f"{tag} {k}")
             for k, v in c["final_state_dict"].items():
-                scale_close(ag.critic.state_dict()[k], v, 1e-4, f"{tag} param {k}")
+                scale_close(ag.critic.state_dict()[k], v, 1e-5, f"{tag} param {k}")
         assert (ag._critic_engine.graph is not None) == cuda_graph
 
 
@@ -448,7 +448,7 @@ def test_fused_loss_vs_oracle_autograd(dist_type, fixed_sigma, mb, A, clip_value
                              cu(ret), d_mu, d_sig, g_mu, g_ls, g_v, metrics, cfg, ws, True, mm, sm)
     ref_metrics = torch.stack([total.detach(), a.mean().detach(), c.mean().detach(), b.mean().detach(), ent.mean().detach(), frac, ev, kl])
     for i, name in enumerate(("total", "actor", "critic", "bounds", "entropy", "clip_frac", "explained_var", "kl")):
-        scale_close(metrics[i], ref_metrics[i], 2e-5 if name in ("clip_frac", "explained_var") else 1e-5, name)
+        scale_close(metrics[i], ref_metrics[i], 1e-5, name)
     scale_close(g_mu, mu_raw.grad, 1e-5, "d/d mu_raw")
     scale_close(g_v, value.grad, 1e-5, "d/d value")
     scale_close(g_ls.sum(0) if fixed_sigma else g_ls, ls.grad, 1e-5, "d/d logstd")
@@ -562,22 +562,22 @@ def test_ppo_update_matches_reference_agent(cuda_graph):
             ref = c["results"]
             tag = f"{c['variant']} graph={cuda_graph} rep={rep}"
             for k in ("loss/total", "loss/actor", "loss/critic", "loss/bounds", "loss/entropy", "explained_var", "grad_norm/all"):
-                scale_close(torch.stack(res[k]), ref[k], 2e-5, f"{tag} {k}")
+                scale_close(torch.stack(res[k]), ref[k], 1e-5, f"{tag} {k}")
             # KL is a sum of O(1) terms that cancel to ~1e-3 (log ratio + quadratic - 1/2 per action dim): its
             # rounding floor is ~1e-7 * A absolute in ANY f32 evaluation order, so it gets an absolute tolerance
             kl_err = (torch.stack(res["avg_kl"]).cpu() - ref["avg_kl"]).abs().max().item()
             assert kl_err <= 1e-5 * ref["avg_kl"].abs().max().item() + 2e-7, f"{tag} avg_kl {kl_err:.3e}"
             scale_close(torch.stack(res["clip_frac"]), ref["clip_frac"], 1.01 / c["minibatch_size"], f"{tag} clip_frac")
             assert agent.last_lr == c["last_lr"], (agent.last_lr, c["last_lr"])
-            scale_close(torch.cat(res["mu"]).mean(0), c["results_mu_mean"], 1e-4, "mu mean")
+            scale_close(torch.cat(res["mu"]).mean(0), c["results_mu_mean"], 1e-5, "mu mean")
             for k, v in c["final_state_dict"].items():
-                scale_close(agent.model.state_dict()[k], v, 1e-4, f"{tag} param {k}")
+                scale_close(agent.model.state_dict()[k], v, 1e-5, f"{tag} param {k}")
             for k, v in c["obs_rms_after"].items():
                 scale_close(agent.obs_rms.state_dict()[k], v, 2e-6, f"{tag} obs_rms {k}")
             for k, v in c["value_rms_after"].items():
                 scale_close(agent.value_rms.state_dict()[k], v, 2e-6, f"{tag} value_rms {k}")
-            scale_close(data["mu"], c["data_after_train"]["mu"], 1e-4, "mu write-back")
-            scale_close(data["sigma"], c["data_after_train"]["sigma"], 1e-4, "sigma write-back")
+            scale_close(data["mu"], c["data_after_train"]["mu"], 1e-5, "mu write-back")
+            scale_close(data["sigma"], c["data_after_train"]["sigma"], 1e-5, "sigma write-back")
 
 
 def test_play_steps_matches_reference_rollout():
@@ -636,11 +636,11 @@ def test_play_steps_matches_reference_rollout():
         eq(sd["dones"], ref["dones"], f"{tag} dones")
         for k in ("actions", "mu", "sigma", "values", "rewards"):
             scale_close(sd[k], ref[k], 1e-5, f"{tag} storage {k}")
-        scale_close(sd["neglogp"], ref["neglogp"], 2e-5, f"{tag} storage neglogp")
+        scale_close(sd["neglogp"], ref["neglogp"], 1e-5, f"{tag} storage neglogp")
         scale_close(seen["last_values"], c["last_values"], 1e-5, f"{tag} last_values")
         data = agent.storage.data_dict
         for k in ("advantages", "values", "returns"):
-            scale_close(data[k], c["data_after_play"][k], 2e-5, f"{tag} data {k}")
+            scale_close(data[k], c["data_after_play"][k], 1e-5, f"{tag} data {k}")
         assert (agent._rollout is not None) == fused
 
 
@@ -796,7 +796,10 @@ def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, norm, use
     for k, p in model.named_parameters():
         # bias gradients here are sums of `rows` N(0,1) seeds that cancel to O(sqrt(rows)): both f32 summation orders
         # carry ~rows * 2^-24 absolute error, so they get a looser bound than the weights
-        scale_close(p.grad, ref[k], 5e-5 if k.endswith("bias") or k == "sigma" else 1e-5, f"grad {k}")
+        # A bias gradient is the plain sum of 32768 dZ values: torch's f32 autograd and the kernels (per-thread partial sums, fixed
+        # tree) add them in different orders, and the sum cancels to ~1e-2 of its largest terms.  Measured 1.1e-5 at worst
+        # (profiles/r02_tolerances.tsv); everything else in this test sits below 1e-5.
+        scale_close(p.grad, ref[k], 2e-5 if k.endswith("bias") or k == "sigma" else 1e-5, f"grad {k}")
 
 
 @pytest.mark.parametrize("rows,A,H,fixed_sigma,dist_type", [(512, 8, 64, True, "normal"), (2048, 8, 64, False, "dreamerv3_normal"),
@@ -860,7 +863,7 @@ def test_fused_heads_loss_vs_unfused(rows, A, H, fixed_sigma, dist_type):
     for t, r in zip(ft.dY[-1], ref_dy):
         scale_close(t, r, 1e-5, "dY3")
     for n in head_names:
-        scale_close(dict(model.named_parameters())[n].grad, ref_grads[n], 2e-5, f"head grad {n}")
+        scale_close(dict(model.named_parameters())[n].grad, ref_grads[n], 1e-5, f"head grad {n}")
 
 
 def test_staged_host_upload_round_trip():

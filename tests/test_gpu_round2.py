@@ -150,9 +150,9 @@ def test_shac_update_critic_iterates_len_dataset(drop_last):
     ref = oc.shac_update_critic(params, ["critic_mlp"], optim, obs.view(-1, O), tv.view(-1), 64, 3, 2, True, "ELU", drop_last=drop_last)
     assert ag._critic_engine.n_batches == len(ds)
     for k, v in ref.items():
-        scale_close(torch.stack(res[k]), torch.stack(v), 2e-5, f"drop_last={drop_last} {k}")
+        scale_close(torch.stack(res[k]), torch.stack(v), 1e-5, f"drop_last={drop_last} {k}")
     for k, v in params.items():
-        scale_close(ag.critic.state_dict()[k], v.detach(), 1e-4, f"drop_last={drop_last} param {k}")
+        scale_close(ag.critic.state_dict()[k], v.detach(), 1e-5, f"drop_last={drop_last} param {k}")
 
 
 def test_shac_target_update_and_checkpoint_on_device():
@@ -214,10 +214,10 @@ def test_ppo_loads_reference_checkpoint_and_continues(cuda_graph):
             agent.set_train()
             res = agent.train_epoch()
             for k in ("loss/total", "loss/actor", "loss/critic", "loss/entropy", "grad_norm/all"):
-                scale_close(torch.stack(res[k]), c["results"][k], 2e-5, f"{tag} rep={rep} {k}")
+                scale_close(torch.stack(res[k]), c["results"][k], 1e-5, f"{tag} rep={rep} {k}")
             assert agent.last_lr == c["last_lr"]
             for k, v in c["final_state_dict"].items():
-                scale_close(agent.model.state_dict()[k], v, 1e-4, f"{tag} param {k}")
+                scale_close(agent.model.state_dict()[k], v, 1e-5, f"{tag} param {k}")
             for k, v in c["obs_rms_after"].items():
                 scale_close(agent.obs_rms.state_dict()[k], v, 2e-6, f"{tag} obs_rms {k}")
             for k, v in c["value_rms_after"].items():
@@ -233,8 +233,9 @@ def test_ppo_loads_reference_checkpoint_and_continues(cuda_graph):
         opt.load_state_dict(ours["optim"])
         for i, s in ref_after["state"].items():
             assert float(opt.state_dict()["state"][i]["step"]) == float(s["step"])
-            scale_close(opt.state_dict()["state"][i]["exp_avg"], s["exp_avg"], 1e-4, f"{tag} exp_avg[{i}]")
-            scale_close(opt.state_dict()["state"][i]["exp_avg_sq"], s["exp_avg_sq"], 1e-4, f"{tag} exp_avg_sq[{i}]")
+            scale_close(opt.state_dict()["state"][i]["exp_avg"], s["exp_avg"], 1e-5, f"{tag} exp_avg[{i}]")
+            # second moments hold SQUARED gradients: a relative gradient error e shows up as 2e (measured 1.8e-5 at worst)
+            scale_close(opt.state_dict()["state"][i]["exp_avg_sq"], s["exp_avg_sq"], 3e-5, f"{tag} exp_avg_sq[{i}]")
         assert ours["optim"]["param_groups"][0]["lr"] == ref_after["param_groups"][0]["lr"]
 
 
@@ -291,9 +292,9 @@ def test_cos_lr_schedule_matches_oracle(cuda_graph):
         want = [init_lr * 0.5 * (1.0 + math.cos(math.pi * (steps + k / hp["mini_epochs"]) / 4096.0)) for k in range(hp["mini_epochs"])]
         assert agent._engine.lr_out.cpu().tolist() == want == [float(x) for x in ref["lr"]]
         assert agent.last_lr == want[-1] == lr
-        scale_close(torch.stack(res["loss/total"]), torch.stack(ref["loss"]), 2e-5, f"cos rep={rep} losses")
+        scale_close(torch.stack(res["loss/total"]), torch.stack(ref["loss"]), 1e-5, f"cos rep={rep} losses")
         for k, v in params.items():
-            scale_close(agent.model.state_dict()[k], v.detach(), 1e-4, f"cos rep={rep} param {k}")
+            scale_close(agent.model.state_dict()[k], v.detach(), 1e-5, f"cos rep={rep} param {k}")
 
 
 def test_linear_lr_schedule_takes_effect_like_the_reference():

@@ -116,7 +116,7 @@ def test_tc_bwd_weight(M, N, K, act):
     torch.cuda.synchronize()
     for grp, (rw, rb) in zip(groups, refs):
         scale_close(grp["c"], rw, 5e-6, f"dw {M}x{N}x{K}")
-        scale_close(grp["bias_grad"], rb, 3e-5, f"db {M}x{N}x{K}")
+        scale_close(grp["bias_grad"], rb, 1e-5, f"db {M}x{N}x{K}")
 
 
 # ---- SIMT linear entry points (csrc/mlp.cu): the thin-layer kernels (N <= 32: heads) and the tile kernel, same API ----------
