@@ -394,6 +394,11 @@ typedef struct {
  * the SMs and issued on two streams they run side by side.  mnr_tc_linear_bwd_weight_workspace_bytes depends on the cap in
  * force (the split count follows the CTA count): size the workspace under the same cap as the launch. */
 int mnr_tc_grid_cap(int ctas);
+/* L2 cache hints for the following mnr_tc_linear_* launches of this host thread (returns the previous value; 0 = none): bit 0 -
+ * the result (dX) is read by the very next launches: its TMA stores ask for evict_last; bit 1 - the launch is the LAST reader
+ * of its dY / saved-output operands in this optimizer step: their TMA loads ask for evict_first.  One optimizer step of the PPO
+ * towers touches ~470 MB of activations and gradients against 126 MB of L2: the hints keep what is about to be re-read. */
+int mnr_tc_cache_hints(int flags);
 int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
 
 /* A whole 3-layer tower forward in ONE launch (csrc/tc_tower.cu): y[l] = act(y[l-1] . W_l^T + bias_l), y[-1] = x, for every

@@ -157,6 +157,7 @@ SIGNATURES = {
     "mnr_tc_reduce_partials": (i32, [C.POINTER(TcReduceJob), i32, vp]),
     "mnr_tc_trace": (i32, [i32, vp]),
     "mnr_tc_grid_cap": (i32, [i32]),
+    "mnr_tc_cache_hints": (i32, [i32]),
     "mnr_tc_tower_fwd_supported": (i32, [i32, C.POINTER(C.c_int32), i32, i32]),
     "mnr_tc_tower_fwd": (i32, [C.POINTER(TowerGroup), i32, i32, i32, C.POINTER(C.c_int32), i32, i32, vp]),
     "mnr_tc_tower_trace": (i32, [i32, vp]),

@@ -47,12 +47,36 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* m
       "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// the same with an L2 cache policy (createpolicy)
+__device__ __forceinline__ void tma_load_2d_hint(void* dst_smem, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
+}
 // 2-D tiled tensor-map STORE (shared -> global), bulk-group completion: the issuing thread commits a group and waits on
 // it with wait_group[.read] (.read: the shared-memory source may be overwritten; without: the global writes are done)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src_smem, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
                "r"(smem_u32(src_smem))
                : "memory");
+}
+// the same with an L2 cache policy (createpolicy): where the written tile should stand in L2's eviction order
+__device__ __forceinline__ void tma_store_2d_hint(const CUtensorMap* map, const void* src_smem, int c0, int c1, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(map), "r"(c0),
+               "r"(c1), "r"(smem_u32(src_smem)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

@@ -37,6 +37,7 @@ enum Mode { kFwd = 0, kDx = 1, kDw = 2 };
 
 // mnr_tc_grid_cap: CTAs the NEXT launches of this host thread may use (0 = one per SM).  Two launches that do not depend on
 // each other (a layer's input-gradient and weight-gradient kernels) can then run side by side on disjoint SMs from two streams.
+thread_local int t_cache_hints = 0;
 thread_local int t_grid_cap = 0;
 int eff_sms() {
   const int s = mnr_sm_count();
@@ -75,6 +76,9 @@ struct TcParams {
   // weight-gradient kernel, second form (tc_dw2_kernel): K_in features per work item (128 or 256 = n_mt lane tiles of 128),
   // depth of the TMEM A-slot ring, 32-feature chunks of X per k-block
   int kt, n_mt, a_ring, nxc;
+  // L2 cache hints (mnr_tc_cache_hints): bit 0 - the stored result is read by the next launches: evict_last; bit 1 - this launch is
+  // the last reader of its dY / saved-output operands: evict_first
+  int hints;
 };
 
 // work item -> (group, split, tile row, tile column); consecutive items of one CTA walk the i tiles first
@@ -186,7 +190,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           uint8_t* base = smem + (size_t)st * stage_bytes;
           ptx::mbar_expect_tx(&full_tma[st], tx_bytes);
           const int r0 = tc.r_begin + kb * kBK;
-          if (!A_MN) {  // box [128 rows][32 floats along the reduction]
+          if (p.hints & 2) {   // last reader of dY / Y: their lines may leave L2 first
+            const uint64_t pol = ptx::policy_evict_first();
+            if (!A_MN) {
+              ptx::tma_load_2d_hint(base, &g.a, r0, tc.i0, &full_tma[st], pol);
+              if (HAS_S) ptx::tma_load_2d_hint(base + offAlo, &g.s, r0, tc.i0, &full_tma[st], pol);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                ptx::tma_load_2d_hint(base + c * kChunk, &g.a, tc.i0 + 32 * c, r0, &full_tma[st], pol);
+                if (HAS_S) ptx::tma_load_2d_hint(base + offAlo + c * kChunk, &g.s, tc.i0 + 32 * c, r0, &full_tma[st], pol);
+              }
+            }
+          } else if (!A_MN) {  // box [128 rows][32 floats along the reduction]
             ptx::tma_load_2d(base, &g.a, r0, tc.i0, &full_tma[st]);
             if (HAS_S) ptx::tma_load_2d(base + offAlo, &g.s, r0, tc.i0, &full_tma[st]);
           } else {      // 4 chunks of [32 reduction rows][32 floats along i]
@@ -412,7 +428,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
           ptx::fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            ptx::tma_store_2d(&g.cmap, reinterpret_cast<const uint8_t*>(epi_stage) + (size_t)(warp - kEpi0) * 4096, tc.j0 + cc * 32, row_base);
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(epi_stage) + (size_t)(warp - kEpi0) * 4096;
+            if (p.hints & 1) ptx::tma_store_2d_hint(&g.cmap, src, tc.j0 + cc * 32, row_base, ptx::policy_evict_last());
+            else ptx::tma_store_2d(&g.cmap, src, tc.j0 + cc * 32, row_base);
             ptx::bulk_commit();
           }
         }
@@ -933,6 +951,12 @@ int ld_or(int ld, int dflt) { return ld > 0 ? ld : dflt; }
 
 }  // namespace
 
+extern "C" int mnr_tc_cache_hints(int flags) {
+  const int prev = t_cache_hints;
+  t_cache_hints = flags;
+  return prev;
+}
+
 extern "C" int mnr_tc_grid_cap(int ctas) {
   const int prev = t_grid_cap;
   t_grid_cap = ctas > 0 ? ctas : 0;
@@ -969,7 +993,7 @@ extern "C" int mnr_tc_linear_fwd(const mnr_linear_group_t* groups, int n_groups,
   }
   p.tma_store = tma_store;
   p.I = M, p.J = N, p.R = K, p.ldc = N, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
-  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kFwd, act, p.BN);
+  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kFwd, act, p.BN), p.hints = t_cache_hints;
   dim3 grid((M + kBM - 1) / kBM, (N + p.BN - 1) / p.BN, n_groups);
   return launch<kFwd>(p, grid, mnr_cs(stream));
 }
@@ -1001,7 +1025,7 @@ extern "C" int mnr_tc_linear_bwd_input(const mnr_linear_group_t* groups, int n_g
   }
   p.tma_store = tma_store;
   p.I = M, p.J = K, p.R = N, p.ldc = K, p.act = act, p.splits = 1, p.rows_per_split = 0, p.partials = nullptr;
-  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kDx, act, p.BN);
+  p.want_bias = 0, p.n_groups = n_groups, p.stages = pick_stages(kDx, act, p.BN), p.hints = t_cache_hints;
   dim3 grid((M + kBM - 1) / kBM, (K + p.BN - 1) / p.BN, n_groups);
   return launch<kDx>(p, grid, mnr_cs(stream));
 }
@@ -1121,7 +1145,7 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
   p.I = N, p.J = K, p.R = M, p.ldc = K, p.act = act, p.splits = splits;
   p.rows_per_split = ((M + splits - 1) / splits + 31) / 32 * 32;
   p.partials = (float*)workspace, p.want_bias = want_bias ? 1 : 0, p.n_groups = n_groups, p.stages = d.stages;
-  p.tma_store = 0;
+  p.tma_store = 0, p.hints = t_cache_hints;
   if (d.v2) {
     p.kt = d.kt, p.n_mt = d.n_mt, p.a_ring = d.a_ring, p.nxc = d.nxc;
     p.tiles_i = d.tiles_i, p.tiles_j = d.tiles_j;

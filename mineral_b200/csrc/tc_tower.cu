@@ -270,7 +270,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
     float* s_bias = s_bias_all + ew * 32;
     uint32_t it = 0, nbox = 0, bc0 = 0, bc1 = 0;
     // one 32-column chunk of an accumulator.  to_a: its (hi, lo) parts -> A slot of use `use`.
-    auto chunk = [&](uint32_t acc_col, float bias_v, const CUtensorMap* ymap, int col, int row, bool to_a, uint32_t use, uint64_t* drained) {
+    // L2 eviction order of the stored outputs (flags bit 2): the backward pass reads them top layer first, so Y3 and Y2 (50 MB for
+    // both towers at 32768 rows) are asked to stay and Y1 (67 MB, needed last, larger than what L2 can keep beside them) to go first
+    const bool hints = (p.flags & 4) != 0;
+    const uint64_t pol_keep = ptx::policy_evict_last(), pol_go = ptx::policy_evict_first();
+    auto chunk = [&](uint32_t acc_col, float bias_v, const CUtensorMap* ymap, int col, int row, bool to_a, uint32_t use, uint64_t* drained,
+                     bool keep = false) {
       __syncwarp();
       s_bias[lane] = bias_v;
       __syncwarp();
@@ -317,7 +322,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
       }
       __syncwarp();
       if (lane == 0) {
-        ptx::tma_store_2d(ymap, bp, col, row);
+        if (hints) ptx::tma_store_2d_hint(ymap, bp, col, row, keep ? pol_keep : pol_go);
+        else ptx::tma_store_2d(ymap, bp, col, row);
         ptx::bulk_commit();
       }
     };
@@ -345,8 +351,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
         ptx::mbar_wait(&acc2_full, it & 1);
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + 2, 0);
-        if (c0 < n2c) chunk(kAcc2 + c0 * 32, b0, &g.y[1], c0 * 32, row, true, u0 + 4 * h1 + c0, nullptr);
-        if (c1 < n2c) chunk(kAcc2 + c1 * 32, b1, &g.y[1], c1 * 32, row, true, u0 + 4 * h1 + c1, nullptr);
+        if (c0 < n2c) chunk(kAcc2 + c0 * 32, b0, &g.y[1], c0 * 32, row, true, u0 + 4 * h1 + c0, nullptr, true);
+        if (c1 < n2c) chunk(kAcc2 + c1 * 32, b1, &g.y[1], c1 * 32, row, true, u0 + 4 * h1 + c1, nullptr, true);
         if (ew == 0) TT_TRACE(3, it * 4 + 2, 1);
       }
       // ---- layer 3 (accumulated in buffer it & 1) ----
@@ -359,8 +365,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + 3, 0);
         const uint32_t acc = kAccB + 128u * b;
-        if (c0 < n3c) chunk(acc + c0 * 32, b0, &g.y[2], c0 * 32, row, false, 0u, c1 < n3c ? nullptr : &b_empty[b]);
-        if (c1 < n3c) chunk(acc + c1 * 32, b1, &g.y[2], c1 * 32, row, false, 0u, &b_empty[b]);
+        if (c0 < n3c) chunk(acc + c0 * 32, b0, &g.y[2], c0 * 32, row, false, 0u, c1 < n3c ? nullptr : &b_empty[b], true);
+        if (c1 < n3c) chunk(acc + c1 * 32, b1, &g.y[2], c1 * 32, row, false, 0u, &b_empty[b], true);
         if (c0 >= n3c) {   // a warp without a chunk of this layer still counts on the barrier
           ptx::tc_fence_before();
           ptx::mbar_arrive(&b_empty[b]);
@@ -418,7 +424,7 @@ extern "C" int mnr_tc_tower_fwd(const mnr_tower_group_t* groups, int n_groups, i
   p.M = M, p.K0 = K0, p.n_groups = n_groups, p.tiles_i = (M + kBM - 1) / kBM;
   {
     const char* e = getenv("MNR_TOWER_FLAGS");
-    p.flags = e ? atoi(e) : 3;
+    p.flags = e ? atoi(e) : 7;   // bit 0: weight prefetch, bit 1: (unused), bit 2: L2 eviction hints on the Y stores
   }
   int kin = K0;
   for (int l = 0; l < kLayers; ++l) p.N[l] = widths[l];

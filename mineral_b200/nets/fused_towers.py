@@ -196,6 +196,9 @@ class TowerStack:
         G, top = self.G, self.L - 1
         x_ld = getattr(self, '_x_ld', self.in_dim)
         pending = []  # tensor-core dW layers whose split partials still wait for the (single) reduce launch
+        # L2 hints (mnr_tc_cache_hints; MNR_TC_HINTS=0 disables): dX_i is the last reader of dY_i / Y_i and its result is read by the
+        # next two launches; dW_0 is the last reader of everything it loads
+        hints = self.use_tc and os.environ.get('MNR_TC_HINTS', '1') != '0'
         for i in range(top, -1, -1):
             n, k = self.lin[0][i].weight.shape
             src = self.Y[i - 1] if i > 0 else [x] * G
@@ -234,7 +237,11 @@ class TowerStack:
             if not weight_grads:
                 pass
             elif tc:
+                if hints and i == 0:
+                    ops.lib.mnr_tc_cache_hints(2)
                 pending.append(ops.tc_linear_bwd_weight_partials(wg, M, act_i, self.tc_ws[i]))
+                if hints and i == 0:
+                    ops.lib.mnr_tc_cache_hints(0)
                 if len(pending) == 4:
                     ops.tc_reduce_partials(pending)
                     pending = []
@@ -253,8 +260,12 @@ class TowerStack:
                                              M, act_i, accumulate=g > 0)
             if i > 0:
                 if self.use_tc:
+                    if hints:
+                        ops.lib.mnr_tc_cache_hints(3)
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],
                                                   saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, act_i)
+                    if hints:
+                        ops.lib.mnr_tc_cache_hints(0)
                 else:
                     ops.linear_bwd_input([dict(a=self.dY[i][g], b=self.lin[g][i].weight.data, c=self.dY[i - 1][g], saved=saved[g], N=n, K=k)
                                           for g in range(G)], M, act_i)
