@@ -261,7 +261,7 @@ class TowerStack:
             if i > 0:
                 if self.use_tc:
                     if hints:
-                        ops.lib.mnr_tc_cache_hints(3)
+                        ops.lib.mnr_tc_cache_hints(int(os.environ.get('MNR_TC_HINTS_DX', '3,0').split(',')[min(top - i, 1)]))
                     ops.tc_linear_bwd_input([dict(a=self.dY[i][g], b=self.w_hi[i][g], b_lo=self.w_lo[i][g], c=self.dY[i - 1][g],
                                                   saved=saved[g], N=n, K=k, ldb=self.w_ld[i]) for g in range(G)], M, act_i)
                     if hints:
