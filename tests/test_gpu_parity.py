@@ -864,6 +864,20 @@ def test_fused_heads_loss_vs_unfused(rows, A, H, fixed_sigma, dist_type):
         scale_close(t, r, 1e-5, "dY3")
     for n in head_names:
         scale_close(dict(model.named_parameters())[n].grad, ref_grads[n], 1e-5, f"head grad {n}")
+    # cfg.dz_act (single-kernel form): the emitted gradient is dY3 * ELU'(Y3), taken from the staged Y3 tiles - bit for bit the
+    # product of the dY3 above with act'(Y3); everything else is unchanged
+    if ops.lib.mnr_ppo_heads_is_fused(A, H):
+        dy_plain = [t.clone() for t in ft.dY[-1]]
+        grads_plain = {n: dict(model.named_parameters())[n].grad.clone() for n in head_names}
+        cfg.dz_act = 1
+        d3 = {k: v.clone() for k, v in d.items()}
+        m3 = torch.zeros(10, device=DEV)
+        ft.heads_loss_fwd_bwd(d3, 0, rows, g_mu, g_ls, g_v.view(-1), m3, cfg, ws, mm2, sm2)
+        for t, r, y3 in zip(ft.dY[-1], dy_plain, ft.Y[-1]):
+            assert torch.equal(t, r * torch.where(y3 > 0, torch.ones_like(y3), y3 + 1)), "dZ3 != dY3 * act'(Y3)"
+        assert torch.equal(m3, m2)
+        for n in head_names:
+            assert torch.equal(dict(model.named_parameters())[n].grad, grads_plain[n]), f"head grad {n} changed with dz_act"
 
 
 def test_staged_host_upload_round_trip():

@@ -376,3 +376,93 @@ def test_replay_ring_cfg4_four_million_transitions():
     rb.sample_batch(8192, device=DEV, indices=idx, obs_rms=rms, out=dict(obs={"obs": xc[:, :O]}, next_obs={"obs": xn[:, :O]}, action=xc[:, O:O + A]))
     eq(xc[:, :O].contiguous(), obs["obs"].cpu(), "strided obs"), eq(xc[:, O:O + A].contiguous(), act.cpu(), "strided action")
     assert xc[:, O + A:].abs().max().item() == 0 and xn[:, O:].abs().max().item() == 0
+
+
+
+# ------------------------------------------------------------------------------------------------
+# launch-level pieces added in round 2
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rows,cols,clamp", [(32768, 37, (-5.0, 5.0)), (2048, 88, None), (77, 5, (-1.0, 1.0))])
+def test_optimizer_ride_along_normalise_is_rms_apply(rows, cols, clamp):
+    """mnr_optim_queue_normalise: the job riding in the fused optimizer launch writes exactly what mnr_rms_apply_ld_f32 writes
+    (RunningMeanStd.normalize, mineral/common/normalizers.py:57-68), the optimizer step itself is unchanged, and the job is
+    consumed by ONE launch."""
+    from mineral_b200 import ops
+
+    g = torch.Generator(device=DEV).manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device=DEV, generator=g) * 3 + 1
+    mean, denom = torch.randn(cols, device=DEV, generator=g), torch.rand(cols, device=DEV, generator=g) + 0.5
+    ld = (cols + 3) // 4 * 4
+    ref = torch.zeros(rows, ld, device=DEV)
+    ops.rms_apply_ld(x, mean, denom, clamp, ref, ld)
+    n = 10_008
+
+    def run(with_job, out):
+        torch.manual_seed(0)
+        p, m, v = torch.randn(n, device=DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        st = ops.optim_state_tensor(5e-4, DEV)
+        fws = torch.zeros(ops.lib.mnr_fused_adam_workspace_bytes(), dtype=torch.uint8, device=DEV)
+        for step in range(2):
+            gd = torch.randn(n, device=DEV)
+            if with_job and step == 0:
+                ops.optim_queue_normalise(x, mean, denom, clamp, out, ld)
+            ops.fused_clip_adam(p, gd, m, v, 1.0, 0.9, 0.999, 1e-5, 0.0, False, True, st, None, None, fws)
+            if step == 0:
+                torch.cuda.synchronize()
+                first = out.clone()
+                out.fill_(-7.0)   # a second launch must NOT run the job again
+        torch.cuda.synchronize()
+        return p, first, out
+
+    out = torch.zeros(rows, ld, device=DEV)
+    p1, first, after = run(True, out)
+    p0, _, _ = run(False, torch.zeros(rows, ld, device=DEV))
+    eq(first, ref.cpu(), "ride-along output")
+    assert (after == -7.0).all(), "the job ran twice"
+    eq(p1, p0.cpu(), "parameters with / without the ride-along job")
+
+
+def test_tc_grid_cap_and_cache_hints_do_not_change_results():
+    """mnr_tc_grid_cap / mnr_tc_cache_hints are scheduling knobs: dX is bit-identical under any cap and hint (tiles are
+    independent), dW agrees with float64 under a cap (its split count follows the CTA count) and the reduce uses the plan
+    of the launch that wrote the partials."""
+    from mineral_b200 import ops
+
+    if not ops.tc_supported():
+        pytest.skip("tensor-map driver entry point unavailable")
+    M, N, K = 4096, 128, 256
+    g = torch.Generator(device=DEV).manual_seed(5)
+    dy, y = torch.randn(M, N, device=DEV, generator=g), torch.randn(M, N, device=DEV, generator=g)
+    w = torch.randn(N, K, device=DEV, generator=g) / N**0.5
+    x = torch.randn(M, K, device=DEV, generator=g)
+    hi, lo = torch.empty(N, K, device=DEV), torch.empty(N, K, device=DEV)
+    ops.split_tf32([(w, hi, lo, N, K, K, K)])
+
+    def dx(cap, hints):
+        out = torch.full((M, K), float("nan"), device=DEV)
+        ops.tc_grid_cap(cap)
+        ops.lib.mnr_tc_cache_hints(hints)
+        try:
+            ops.tc_linear_bwd_input([dict(a=dy, saved=y, b=hi, b_lo=lo, c=out, N=N, K=K)], M, 1)
+        finally:
+            ops.tc_grid_cap(0)
+            ops.lib.mnr_tc_cache_hints(0)
+        torch.cuda.synchronize()
+        return out.cpu()
+
+    base = dx(0, 0)
+    for cap, hints in ((40, 0), (0, 3), (97, 3)):
+        eq(dx(cap, hints), base, f"dX cap={cap} hints={hints}")
+
+    dz = dy.double() * torch.where(y > 0, torch.ones_like(y), y + 1).double()
+    ref_w, ref_b = dz.T @ x.double(), dz.sum(0)
+    for cap in (0, 61):
+        ops.tc_grid_cap(cap)
+        ws = torch.zeros(ops.lib.mnr_tc_linear_bwd_weight_workspace_bytes(1, M, N, K), dtype=torch.uint8, device=DEV)
+        dw, db = torch.full((N, K), float("nan"), device=DEV), torch.full((N,), float("nan"), device=DEV)
+        job = ops.tc_linear_bwd_weight_partials([dict(a=dy, saved=y, b=x, c=dw, bias_grad=db, N=N, K=K, ldb=K)], M, 1, ws)
+        ops.tc_grid_cap(0)            # the reduce is issued under another cap: it must follow the job's
+        ops.tc_reduce_partials([job])
+        torch.cuda.synchronize()
+        scale_close(dw, ref_w, 5e-6, f"dW cap={cap}")
+        scale_close(db, ref_b, 1e-5, f"db cap={cap}")
