@@ -44,6 +44,29 @@ static inline cudaError_t mnr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, di
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Opt-in ceiling of dynamic shared memory per CTA on sm_100a.  Kernels launched with a shape-dependent amount set the function
+// attribute to this CEILING, not to the amount of the launch at hand: the attribute belongs to the function, not to the launch,
+// so a later launch with a smaller request would lower it under the feet of an earlier one recorded in a CUDA graph (plain
+// graph replays keep working, but a profiler that re-launches graph kernel nodes one by one - ncu - gets LaunchFailed).
+constexpr int kMnrMaxDynSmem = 227 * 1024;
+
+// set `kernel`'s dynamic shared-memory ceiling to the most this device allows beside the kernel's static shared memory
+// (looked up once per function and host thread)
+template <typename K>
+static inline cudaError_t mnr_allow_max_dyn_smem(K kernel) {
+  static thread_local const void* done[64];
+  static thread_local int n_done = 0;
+  const void* key = reinterpret_cast<const void*>(kernel);
+  for (int i = 0; i < n_done; ++i)
+    if (done[i] == key) return cudaSuccess;
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMnrMaxDynSmem - (int)fa.sharedSizeBytes);
+  if (e == cudaSuccess && n_done < 64) done[n_done++] = key;
+  return e;
+}
+
 namespace mnr {
 
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

@@ -267,7 +267,7 @@ extern "C" int mnr_ln_act_bwd(const mnr_ln_group_t* groups, int n_groups, int64_
 #define MNR_LN_GO(KERNEL, EV, VV, AV, ...)                                                                     \
   {                                                                                                            \
     auto kern = KERNEL<EV, VV, AV>;                                                                            \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+    cudaError_t e = mnr_allow_max_dyn_smem(kern);                                                              \
     if (e != cudaSuccess) return (int)e;                                                                       \
     mnr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, mnr_cs(stream), a);                                 \
   }

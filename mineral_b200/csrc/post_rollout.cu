@@ -441,13 +441,13 @@ extern "C" int mnr_post_rollout_fused(const mnr_wide_field_t* wide, int n_wide, 
   const int grid = pl.n_scalar + pl.item0[n_wide];
   cudaError_t e;
   if (bulk_ok) {
-    e = cudaFuncSetAttribute(post_rollout_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    e = mnr_allow_max_dyn_smem(post_rollout_kernel<true>);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(post_rollout_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;
     post_rollout_kernel<true><<<grid, kThreads, pl.smem, mnr_cs(stream)>>>(p);
   } else {
-    e = cudaFuncSetAttribute(post_rollout_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    e = mnr_allow_max_dyn_smem(post_rollout_kernel<false>);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(post_rollout_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return (int)e;

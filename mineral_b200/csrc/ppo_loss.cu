@@ -886,7 +886,7 @@ extern "C" int mnr_ppo_heads_loss_fwd_bwd(const float* y3a, const float* y3v, co
   if (A <= 8) head_grads_kernel<8><<<grid2, 256, smem2, mnr_cs(stream)>>>(ga);
   else if (A <= 16) head_grads_kernel<16><<<grid2, 256, smem2, mnr_cs(stream)>>>(ga);
   else {
-    e = cudaFuncSetAttribute(head_grads_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    e = mnr_allow_max_dyn_smem(head_grads_kernel<32>);
     if (e != cudaSuccess) return (int)e;
     head_grads_kernel<32><<<grid2, 256, smem2, mnr_cs(stream)>>>(ga);
   }

@@ -223,7 +223,7 @@ extern "C" int mnr_replay_sample_records(const mnr_row_field_t* fields, const in
   const size_t smem = (size_t)(kRowsPerCta + 2) * rec_floats * sizeof(float);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    const cudaError_t e = cudaFuncSetAttribute(sample_records_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e = mnr_allow_max_dyn_smem(sample_records_kernel);
     if (e != cudaSuccess) return (int)e;
     smem_set = smem;
   }

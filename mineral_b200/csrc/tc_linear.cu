@@ -934,7 +934,7 @@ int launch(TcParams& p, dim3 tiles, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * stage + kEpiStageBytes + 1024;
   cudaError_t e = cudaSuccess;
 #define MNR_TC_LAUNCH(ACTV)                                                                                              \
-  e = cudaFuncSetAttribute(tc_linear_kernel<MODE, ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+  e = mnr_allow_max_dyn_smem(tc_linear_kernel<MODE, ACTV>);                                                                   \
   if (e == cudaSuccess) e = mnr_launch_pdl(tc_linear_kernel<MODE, ACTV>, grid, dim3(kThreads), smem, stream, p);
   switch (p.act) {
     case 1: MNR_TC_LAUNCH(1) break;
@@ -1155,7 +1155,7 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
     const size_t smem = (size_t)d.stages * (2 * d.BN * kBK * 4 + d.nxc * kChunk) + kDw2BiasBytes + 1024;
     cudaError_t e = cudaSuccess;
 #define MNR_DW2_LAUNCH(ACTV)                                                                                        \
-  e = cudaFuncSetAttribute(tc_dw2_kernel<ACTV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
+  e = mnr_allow_max_dyn_smem(tc_dw2_kernel<ACTV>);                                                                       \
   if (e == cudaSuccess) e = mnr_launch_pdl(tc_dw2_kernel<ACTV>, grid, dim3(kThreads), smem, stream, p);
     switch (act) {
       case 1: MNR_DW2_LAUNCH(1) break;
