@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 
   if (warp == 0) {
     // ===== TMA producer ==========================================================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t tx_bytes = kTileA * (HAS_S ? 2 : 1) + bytesB * (CONV_B ? 1 : 2);
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===== MMA issuer ===============================================================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_tf32(kBM, BN, 0, B_MN ? 1 : 0);
       // B descriptors.  K-major: SWIZZLE_128B (layout 2), 8-row groups 1 KiB apart (SBO), LBO unused (16 B).
       // MN-major (32-bit): SWIZZLE_128B_BASE32B (layout 1), 4-row reduction groups 512 B apart (SBO), 32-float
@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
 #pragma unroll
             for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(r[q]);
           }
-          if (lane == 0) ptx::bulk_wait_read0();   // the previous store of this warp has finished reading the box
+          if (ptx::elect_one()) ptx::bulk_wait_read0();   // the previous store of this warp has finished reading the box
           __syncwarp();
           const uint32_t row_addr = box + (uint32_t)lane * 128u;
 #pragma unroll
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
             ptx::st_shared_v4(row_addr + (uint32_t)((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
           ptx::fence_proxy_async_smem();
           __syncwarp();
-          if (lane == 0) {
+          if (ptx::elect_one()) {
             const uint8_t* src = reinterpret_cast<const uint8_t*>(epi_stage) + (size_t)(warp - kEpi0) * 4096;
             if (p.hints & 1) ptx::tma_store_2d_hint(&g.cmap, src, tc.j0 + cc * 32, row_base, ptx::policy_evict_last());
             else ptx::tma_store_2d(&g.cmap, src, tc.j0 + cc * 32, row_base);
@@ -496,7 +496,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_linear_kernel(const __grid_con
     }
   }
 
-  if (MODE != kDw && p.tma_store && warp >= 8 && lane == 0) ptx::bulk_wait0();  // this warp's C boxes have landed
+  if (MODE != kDw && p.tma_store && warp >= 8) {   // this warp's C boxes have landed
+    if (ptx::elect_one()) ptx::bulk_wait0();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -586,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dw2_kernel(const __grid_consta
 
   if (warp == 0) {
     // ===== TMA producer: MN-major boxes [32 reduction rows][32 floats] ================================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t kbg = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const Dw2Coord tc = decode_dw2(p, tile);
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_dw2_kernel(const __grid_consta
     }
   } else if (warp == 1) {
     // ===== MMA issuer: D[mt] (+)= A[mt] (TMEM: X^T hi | lo) * B (smem: dZ hi / lo, MN-major) ===========================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_tf32(kBM, BN, 0, 1);
       const uint64_t b_desc_hi = ptx::smem_desc(0, 0, 512, 1);
       const uint32_t b_desc_lo_const = ((uint32_t)kChunk >> 4) << 16;

@@ -27,7 +27,7 @@
 
 namespace {
 
-constexpr int kThreads = 512;
+constexpr int kBaseThreads = 256;   // warps 0-7: weight producer, MMA issuer, TMEM allocator, X producer, 4 X converters
 constexpr int kBM = 128, kBK = 32;
 constexpr int kTile = kBM * kBK * 4;   // 16 KiB: [128][32] f32, SWIZZLE_128B
 constexpr int kWSlot = 2 * kTile;      // weight ring slot: hi at +0, lo at +kTile
@@ -37,7 +37,8 @@ constexpr int kMaxXkb = 2;             // K0 <= 64
 constexpr int kMaxGroups = 2;
 constexpr int kLayers = 3;
 constexpr uint32_t kAccB = 0, kAcc2 = 256, kARing = 384, kTmemCols = 512;   // two 128-column buffers | ACC2 | A ring
-constexpr int kEpiWarps = 8, kEpi0 = 8;
+constexpr int kEpi0 = 8;            // epilogue warps 8 .. 8 + EPIW - 1 (EPIW = 8 or 16: two or four warps per TMEM lane quarter)
+constexpr int kBoxBytes = 64 * 1024; // TMA store boxes: EPIW warps x (64 KiB / EPIW)
 
 __device__ long long g_ttrace[4 * 256 * 2];
 __device__ int g_ttrace_on = 0;
@@ -74,15 +75,22 @@ __device__ __noinline__ void prefetch_weights(const TowerParams& p, uint32_t gt,
     }
 }
 
-template <int ACT, bool PREFETCH>
-__global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_constant__ TowerParams p) {
+template <int ACT, bool PREFETCH, int EPIW>
+__global__ void __launch_bounds__(kBaseThreads + EPIW * 32, 1) tc_tower_fwd_kernel(const __grid_constant__ TowerParams p) {
+  constexpr int kEpiWarps = EPIW;
   extern __shared__ uint8_t smem_dyn[];
   __shared__ __align__(8) uint64_t x_full, x_conv, x_empty;
   __shared__ __align__(8) uint64_t w_full[kWStages], w_empty[kWStages];
-  __shared__ __align__(8) uint64_t a_full[kASlots], a_empty[kASlots];
+  // a_empty[u & 3] completes when the MMAs of A-slot use u have read their slot (= slot u & 1).  FOUR barriers for two slots: a
+  // warp that fills use u waits for use u - 2, i.e. on barrier (u - 2) & 3, and the warps of one residue class of u (mod 4) are
+  // the only waiters of that barrier and see every one of its phases in order - a parity wait must never be two phases away
+  // from the barrier's current one (with one barrier per slot, a warp that handles only every fourth use would be).
+  __shared__ __align__(8) uint64_t a_full[kASlots], a_empty[4];
   __shared__ __align__(8) uint64_t b_full[2], b_empty[2], acc2_full;
   __shared__ uint32_t tmem_slot;
-  __shared__ __align__(16) float s_bias_all[kEpiWarps * 32];
+  // per-warp bias row (8 epilogue warps; the 16-warp form broadcasts the bias by shuffles: 2 KiB of static shared memory would
+  // push the CTA 160 B over the 227 KiB limit)
+  __shared__ __align__(16) float s_bias_all[(EPIW == 16 ? 1 : EPIW) * 32];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int N1 = p.N[0], N2 = p.N[1], N3 = p.N[2];
@@ -93,12 +101,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
   uint8_t* smem = smem_dyn + ((1024u - (ptx::smem_u32(smem_dyn) & 1023u)) & 1023u);
   uint8_t* xs = smem;                                   // [kb][hi 16 KiB | lo 16 KiB]
   uint8_t* ring = smem + kMaxXkb * 2 * kTile;           // kWStages x 32 KiB
-  uint8_t* boxes = ring + kWStages * kWSlot;            // 8 warps x 2 x 4 KiB
+  uint8_t* boxes = ring + kWStages * kWSlot;            // 64 KiB: 8 warps x 2 boxes, or 16 warps x 1 box, of 4 KiB
 
   if (tid == 0) {
     ptx::mbar_init(&x_full, 1), ptx::mbar_init(&x_conv, 128), ptx::mbar_init(&x_empty, 1);
     for (int s = 0; s < kWStages; ++s) ptx::mbar_init(&w_full[s], 1), ptx::mbar_init(&w_empty[s], 1);
-    for (int s = 0; s < kASlots; ++s) ptx::mbar_init(&a_full[s], 128), ptx::mbar_init(&a_empty[s], 1);
+    for (int s = 0; s < kASlots; ++s) ptx::mbar_init(&a_full[s], 128);
+    for (int s = 0; s < 4; ++s) ptx::mbar_init(&a_empty[s], 1);
     for (int b = 0; b < 2; ++b) ptx::mbar_init(&b_full[b], 1), ptx::mbar_init(&b_empty[b], kEpiWarps * 32);
     ptx::mbar_init(&acc2_full, 1);
     ptx::fence_mbar_init();
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
 
   if (warp == 0) {
     // ===== weight producer: the ring items in the order the MMA issuer consumes them ================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t wi = 0;
       auto put = [&](const CUtensorMap* hi, const CUtensorMap* lo, int rows, int c0, int r0) {
         const int st = wi % kWStages;
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
     }
   } else if (warp == 3) {
     // ===== X producer ===============================================================================================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
         const TowerGroup& g = p.g[tile / p.tiles_i];
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
     // ===== MMA issuer ===============================================================================================
     // Issue order: L1(0,h=0) | per tile t: L1(t,h=1), L2(t) blocks as their A slots arrive, L1(t+1,h=0), L3(t) blocks.
     // Layer-1 half h of tile t accumulates in buffer (h + t) & 1; layer 3 of tile t in buffer t & 1 (drained by then).
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       const uint32_t idesc1 = ptx::idesc_tf32(kBM, 128, 0, 0), idesc2 = ptx::idesc_tf32(kBM, N2, 0, 0), idesc3 = ptx::idesc_tf32(kBM, N3, 0, 0);
       // K-major SWIZZLE_128B operand tiles (A of layer 1 and every B): 8-row groups 1 KiB apart (SBO), LBO unused (16 B)
       const uint64_t desc_hi = ptx::smem_desc(0, 0, 1024, 2);
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
           ptx::mma_tf32_ts(acc, a_t + 8u * k, kdesc(b_u, k), idesc, 1u);
         }
         ptx::tc_commit(&w_empty[st]);
-        ptx::tc_commit(&a_empty[as]);
+        ptx::tc_commit(&a_empty[u & 3]);
         ++wi, ++u;
       };
       if ((int)blockIdx.x < n_tiles) layer1(0, 0);
@@ -264,117 +273,187 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
   } else if (warp >= kEpi0) {
     // ===== epilogue: TMEM chunk -> bias + activation -> (hi, lo) into the next layer's A slot, and the chunk itself to
     //       HBM through a swizzled [32][32] box and one TMA tensor store (two boxes per warp, used alternately) ==========
-    const int quarter = warp & 3, half = (warp - kEpi0) >> 2, ew = warp - kEpi0;
+    const int quarter = warp & 3, sub = (warp - kEpi0) >> 2, ew = warp - kEpi0;
+    constexpr int kPerQ = kEpiWarps / 4;             // warps per TMEM lane quarter: each takes the chunks sub, sub + kPerQ, ... of 4
+    constexpr int kBoxes = kBoxBytes / kEpiWarps / 4096;   // store boxes per warp, used in turn (2 with 8 warps, 1 with 16)
+    constexpr int W = kEpiWarps == 16 ? 16 : 32;     // accumulator columns per pass (16 epilogue warps live within 80 registers)
     const uint32_t lane_off = (uint32_t)(32 * quarter) << 16;
-    uint8_t* box_ptr = boxes + (size_t)ew * 8192;
-    float* s_bias = s_bias_all + ew * 32;
+    uint8_t* box_ptr = boxes + (size_t)ew * (kBoxes * 4096);
+    float* s_bias = s_bias_all + (W == 16 ? 0 : ew * 32);
     uint32_t it = 0, nbox = 0, bc0 = 0, bc1 = 0;
-    // one 32-column chunk of an accumulator.  to_a: its (hi, lo) parts -> A slot of use `use`.
     // L2 eviction order of the stored outputs (flags bit 2): the backward pass reads them top layer first, so Y3 and Y2 (50 MB for
     // both towers at 32768 rows) are asked to stay and Y1 (67 MB, needed last, larger than what L2 can keep beside them) to go first
     const bool hints = (p.flags & 4) != 0;
     const uint64_t pol_keep = ptx::policy_evict_last(), pol_go = ptx::policy_evict_first();
+    // fine-grained stamps of epilogue warp 0's chunks (trace mode only): role-1 slots 64.., 8 stamps per chunk
+    uint32_t fine = 0;
+#define TT_FINE()                                                                                                       \
+  do {                                                                                                                  \
+    if (g_ttrace_on && blockIdx.x == 0 && ew == 0 && lane == 0 && fine < 384) {                                         \
+      g_ttrace[(256 + 64 + (fine >> 1)) * 2 + (fine & 1)] = clock64();                                                  \
+      ++fine;                                                                                                           \
+    }                                                                                                                   \
+  } while (0)
+    // one 32-column chunk of an accumulator: bias + activation, to HBM through a swizzled [32][32] box and one TMA tensor store;
+    // to_a: its (hi, lo) parts also go to the A slot of use `use` (the next layer's operand).
     auto chunk = [&](uint32_t acc_col, float bias_v, const CUtensorMap* ymap, int col, int row, bool to_a, uint32_t use, uint64_t* drained,
                      bool keep = false) {
+      TT_FINE();
       __syncwarp();
-      s_bias[lane] = bias_v;
-      __syncwarp();
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + lane_off + acc_col, r);
-      ptx::tmem_ld_wait();
-      if (drained) {   // last read of this accumulator by this warp: the MMA issuer may overwrite it
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(drained);
-      }
-      float v[32];
-      const float4* b4 = reinterpret_cast<const float4*>(s_bias);
-#pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        const float4 b = b4[q4];
-        v[4 * q4] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4]) + b.x), v[4 * q4 + 1] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 1]) + b.y);
-        v[4 * q4 + 2] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 2]) + b.z), v[4 * q4 + 3] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 3]) + b.w);
-      }
-      const int as = use % kASlots;
-      if (to_a) {   // the two tcgen05.st complete while the box is being written below
-        ptx::mbar_wait(&a_empty[as], ((use / kASlots) & 1) ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t a_t = tmem_base + lane_off + kARing + (uint32_t)as * 64u;
-#pragma unroll
-        for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(v[q]) & 0xffffe000u;
-        ptx::tmem_st_32x32(a_t, r);
-#pragma unroll
-        for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(v[q] - __uint_as_float(r[q]));
-        ptx::tmem_st_32x32(a_t + 32u, r);
-      }
-      uint8_t* bp = box_ptr + (nbox & 1) * 4096;
+      if (W == 32) s_bias[lane] = bias_v;
+      uint8_t* bp = box_ptr + (nbox % kBoxes) * 4096;
       ++nbox;
-      if (lane == 0) ptx::bulk_wait_read1();   // the store issued from this box two chunks ago has finished reading it
       __syncwarp();
       const uint32_t row_addr = ptx::smem_u32(bp) + (uint32_t)lane * 128u;
+      const int as = use % kASlots;
+      const uint32_t a_t = tmem_base + lane_off + kARing + (uint32_t)as * 64u;
+      const float4* b4 = reinterpret_cast<const float4*>(s_bias);
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        ptx::st_shared_v4(row_addr + (uint32_t)((c ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+      for (int hh = 0; hh < 32 / W; ++hh) {
+        uint32_t r[W];
+        if (W == 32) ptx::tmem_ld_32x32(tmem_base + lane_off + acc_col, r);
+        else ptx::tmem_ld_32x16(tmem_base + lane_off + acc_col + (uint32_t)(hh * W), r);
+        ptx::tmem_ld_wait();
+        if (hh == 0) TT_FINE();
+        if (drained && hh == 32 / W - 1) {   // last read of this accumulator by this warp: the MMA issuer may overwrite it
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(drained);
+        }
+        float v[W];
+#pragma unroll
+        for (int q4 = 0; q4 < W / 4; ++q4) {
+          float4 b;
+          if (W == 32) {
+            b = b4[hh * (W / 4) + q4];
+          } else {   // column q's bias lives in lane q
+            b.x = __shfl_sync(0xffffffffu, bias_v, hh * W + 4 * q4), b.y = __shfl_sync(0xffffffffu, bias_v, hh * W + 4 * q4 + 1);
+            b.z = __shfl_sync(0xffffffffu, bias_v, hh * W + 4 * q4 + 2), b.w = __shfl_sync(0xffffffffu, bias_v, hh * W + 4 * q4 + 3);
+          }
+          v[4 * q4] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4]) + b.x), v[4 * q4 + 1] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 1]) + b.y);
+          v[4 * q4 + 2] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 2]) + b.z), v[4 * q4 + 3] = act_fwd_t<ACT>(__uint_as_float(r[4 * q4 + 3]) + b.w);
+        }
+        if (hh == 0) TT_FINE();
+        if (to_a) {   // the tcgen05.st complete while the box is being written below
+          if (hh == 0) {
+            if (use >= 2) ptx::mbar_wait(&a_empty[(use - 2) & 3], ((use - 2) >> 2) & 1);   // use - 2 (same slot) has been read
+            ptx::tc_fence_after();
+            TT_FINE();
+          }
+#pragma unroll
+          for (int q = 0; q < W; ++q) r[q] = __float_as_uint(v[q]) & 0xffffe000u;
+          if (W == 32) ptx::tmem_st_32x32(a_t, r);
+          else ptx::tmem_st_32x16(a_t + (uint32_t)(hh * W), r);
+#pragma unroll
+          for (int q = 0; q < W; ++q) r[q] = __float_as_uint(v[q] - __uint_as_float(r[q]));
+          if (W == 32) ptx::tmem_st_32x32(a_t + 32u, r);
+          else ptx::tmem_st_32x16(a_t + 32u + (uint32_t)(hh * W), r);
+        } else if (hh == 0) {
+          TT_FINE();
+        }
+        if (hh == 0) {
+          TT_FINE();
+          if (ptx::elect_one()) {   // the store last issued from this box has finished reading it
+            if (kBoxes == 2) ptx::bulk_wait_read1();
+            else ptx::bulk_wait_read0();
+          }
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < W / 4; ++c) {
+          const int piece = hh * (W / 4) + c;
+          ptx::st_shared_v4(row_addr + (uint32_t)((piece ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        }
+      }
       ptx::fence_proxy_async_smem();
+      TT_FINE();
       if (to_a) {
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&a_full[as]);
       }
+      TT_FINE();
       __syncwarp();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         if (hints) ptx::tma_store_2d_hint(ymap, bp, col, row, keep ? pol_keep : pol_go);
         else ptx::tma_store_2d(ymap, bp, col, row);
         ptx::bulk_commit();
       }
+      TT_FINE();
     };
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const TowerGroup& g = p.g[tile / p.tiles_i];
       const int row = (tile % p.tiles_i) * kBM + 32 * quarter;
       const uint32_t u0 = it * (uint32_t)uses_per_tile;
-      // ---- layer 1 halves ----
+      // ---- layer 1 halves (4 chunks each) ----
       for (int h = 0; h < h1; ++h) {
         const int b = (h + it) & 1;
-        const float b0 = __ldg(g.bias[0] + h * 128 + half * 32 + lane), b1 = __ldg(g.bias[0] + h * 128 + (half + 2) * 32 + lane);
+        float bv[2];
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) bv[k] = __ldg(g.bias[0] + h * 128 + (sub + k * kPerQ) * 32 + lane);
         ptx::mbar_wait(&b_full[b], (b ? bc1 : bc0) & 1);
         b ? ++bc1 : ++bc0;
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + h, 0);
         const uint32_t acc = kAccB + 128u * b;
-        chunk(acc + half * 32, b0, &g.y[0], h * 128 + half * 32, row, true, u0 + 4 * h + half, nullptr);
-        chunk(acc + (half + 2) * 32, b1, &g.y[0], h * 128 + (half + 2) * 32, row, true, u0 + 4 * h + half + 2, &b_empty[b]);
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) {
+          const int c = sub + k * kPerQ;
+          chunk(acc + c * 32, bv[k], &g.y[0], h * 128 + c * 32, row, true, u0 + 4 * h + c, k == 4 / kPerQ - 1 ? &b_empty[b] : nullptr);
+        }
         if (ew == 0) TT_TRACE(3, it * 4 + h, 1);
       }
       // ---- layer 2 ----
       {
-        const int c0 = half, c1 = half + 2, n2c = N2 / 32;
-        const float b0 = c0 < n2c ? __ldg(g.bias[1] + c0 * 32 + lane) : 0.f, b1 = c1 < n2c ? __ldg(g.bias[1] + c1 * 32 + lane) : 0.f;
+        const int n2c = N2 / 32;
+        float bv[2];
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) {
+          const int c = sub + k * kPerQ;
+          bv[k] = c < n2c ? __ldg(g.bias[1] + c * 32 + lane) : 0.f;
+        }
         ptx::mbar_wait(&acc2_full, it & 1);
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + 2, 0);
-        if (c0 < n2c) chunk(kAcc2 + c0 * 32, b0, &g.y[1], c0 * 32, row, true, u0 + 4 * h1 + c0, nullptr, true);
-        if (c1 < n2c) chunk(kAcc2 + c1 * 32, b1, &g.y[1], c1 * 32, row, true, u0 + 4 * h1 + c1, nullptr, true);
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) {
+          const int c = sub + k * kPerQ;
+          if (c < n2c) chunk(kAcc2 + c * 32, bv[k], &g.y[1], c * 32, row, true, u0 + 4 * h1 + c, nullptr, true);
+        }
         if (ew == 0) TT_TRACE(3, it * 4 + 2, 1);
       }
       // ---- layer 3 (accumulated in buffer it & 1) ----
       {
         const int b = it & 1;
-        const int c0 = half, c1 = half + 2, n3c = N3 / 32;
-        const float b0 = c0 < n3c ? __ldg(g.bias[2] + c0 * 32 + lane) : 0.f, b1 = c1 < n3c ? __ldg(g.bias[2] + c1 * 32 + lane) : 0.f;
+        const int n3c = N3 / 32;
+        float bv[2];
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) {
+          const int c = sub + k * kPerQ;
+          bv[k] = c < n3c ? __ldg(g.bias[2] + c * 32 + lane) : 0.f;
+        }
         ptx::mbar_wait(&b_full[b], (b ? bc1 : bc0) & 1);
         b ? ++bc1 : ++bc0;
         ptx::tc_fence_after();
         if (ew == 0) TT_TRACE(3, it * 4 + 3, 0);
         const uint32_t acc = kAccB + 128u * b;
-        if (c0 < n3c) chunk(acc + c0 * 32, b0, &g.y[2], c0 * 32, row, false, 0u, c1 < n3c ? nullptr : &b_empty[b], true);
-        if (c1 < n3c) chunk(acc + c1 * 32, b1, &g.y[2], c1 * 32, row, false, 0u, &b_empty[b], true);
-        if (c0 >= n3c) {   // a warp without a chunk of this layer still counts on the barrier
+        bool arrived = false;
+#pragma unroll
+        for (int k = 0; k < 4 / kPerQ; ++k) {
+          const int c = sub + k * kPerQ;
+          if (c < n3c) {
+            const bool last = c + kPerQ >= n3c || k == 4 / kPerQ - 1;   // this warp's last chunk of the buffer
+            chunk(acc + c * 32, bv[k], &g.y[2], c * 32, row, false, 0u, last ? &b_empty[b] : nullptr, true);
+            arrived = arrived || last;
+          }
+        }
+        if (!arrived) {   // a warp without a chunk of this layer still counts on the barrier
           ptx::tc_fence_before();
           ptx::mbar_arrive(&b_empty[b]);
         }
         if (ew == 0) TT_TRACE(3, it * 4 + 3, 1);
       }
     }
-    if (lane == 0) ptx::bulk_wait0();   // this warp's Y boxes have landed
+    if (ptx::elect_one()) ptx::bulk_wait0();   // this warp's Y boxes have landed
   }
 
   ptx::tc_fence_before();
@@ -385,16 +464,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc_tower_fwd_kernel(const __grid_
   }
 }
 
-constexpr size_t kSmemBytes = 1024 + (size_t)kMaxXkb * 2 * kTile + (size_t)kWStages * kWSlot + 8 * 8192;
+constexpr size_t kSmemBytes = 1024 + (size_t)kMaxXkb * 2 * kTile + (size_t)kWStages * kWSlot + kBoxBytes;
 
 bool tower_shape_ok(int K0, const int32_t* widths, int n_layers, int act) {
   if (n_layers != kLayers || act < 0 || act > 2) return false;
   if (K0 <= 0 || K0 > kMaxXkb * kBK) return false;
   const int N1 = widths[0], N2 = widths[1], N3 = widths[2];
   if (N1 != 128 && N1 != 256) return false;
-  if (N2 <= 0 || N2 > 128 || N2 % 32 != 0) return false;
+  if (N2 <= 0 || N2 > 128 || N2 % 64 != 0) return false;   // an even number of 32-column chunks (A-slot bookkeeping above)
   if (N3 <= 0 || N3 > 128 || N3 % 32 != 0) return false;
   return true;
+}
+
+// MNR_TOWER_EPI=8|16: epilogue warps of the kernel (two or four per TMEM lane quarter); read once
+int epi_warps() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MNR_TOWER_EPI");
+    v = (e && atoi(e) == 8) ? 8 : 16;   // measured: 4.50 ms per update with 16 against 4.53 with 8 (cfg2)
+  }
+  return v;
 }
 
 // MNR_TC_FUSED_FWD=0 keeps one launch per layer (A/B measurements); read once
@@ -448,19 +537,28 @@ extern "C" int mnr_tc_tower_fwd(const mnr_tower_group_t* groups, int n_groups, i
   const int n_tiles = p.tiles_i * n_groups, sms = mnr_sm_count();
   dim3 grid(n_tiles < sms ? n_tiles : sms);
   cudaError_t e = cudaSuccess;
-#define MNR_TOWER_LAUNCH(ACTV)                                                                                                 \
-  if (p.flags & 1) {                                                                                                            \
-    e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);    \
-    if (e == cudaSuccess) e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV, true>, grid, dim3(kThreads), kSmemBytes, mnr_cs(stream), p); \
-  } else {                                                                                                                      \
-    e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);   \
-    if (e == cudaSuccess) e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV, false>, grid, dim3(kThreads), kSmemBytes, mnr_cs(stream), p); \
+#define MNR_TOWER_GO(ACTV, PF, EW)                                                                                              \
+  {                                                                                                                             \
+    e = cudaFuncSetAttribute(tc_tower_fwd_kernel<ACTV, PF, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);  \
+    if (e == cudaSuccess)                                                                                                       \
+      e = mnr_launch_pdl(tc_tower_fwd_kernel<ACTV, PF, EW>, grid, dim3(kBaseThreads + EW * 32), kSmemBytes, mnr_cs(stream), p); \
+  }
+  // 16 epilogue warps: every warp owns one residue class of the A-slot uses (mod 4), which needs uses per tile % 4 == 0
+  const bool epi16 = epi_warps() == 16 && ((4 * (widths[0] / 128) + widths[1] / 32) % 4 == 0);
+#define MNR_TOWER_LAUNCH(ACTV)                    \
+  if (epi16) {                                    \
+    if (p.flags & 1) MNR_TOWER_GO(ACTV, true, 16) \
+    else MNR_TOWER_GO(ACTV, false, 16)            \
+  } else {                                        \
+    if (p.flags & 1) MNR_TOWER_GO(ACTV, true, 8)  \
+    else MNR_TOWER_GO(ACTV, false, 8)             \
   }
   switch (act) {
     case 1: MNR_TOWER_LAUNCH(1) break;
     case 2: MNR_TOWER_LAUNCH(2) break;
     default: MNR_TOWER_LAUNCH(0) break;
   }
+#undef MNR_TOWER_GO
 #undef MNR_TOWER_LAUNCH
   if (e != cudaSuccess) return (int)e;
   MNR_LAUNCH_RESULT();

@@ -161,7 +161,7 @@ def test_simt_linear_fwd_dx_dw_thin_and_tile(M, N, K):
     assert torch.equal(again, dwa), "weight gradient is not deterministic"
 
 
-TOWER_CASES = [(4096, 37, (256, 128, 64), 1), (300, 37, (256, 128, 64), 1), (1024, 64, (128, 64, 32), 2), (2048, 20, (256, 96, 128), 0),
+TOWER_CASES = [(4096, 37, (256, 128, 64), 1), (300, 37, (256, 128, 64), 1), (1024, 64, (128, 64, 32), 2), (2048, 20, (256, 64, 128), 0),
                (32768, 37, (256, 128, 64), 1)]
 
 

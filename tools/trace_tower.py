@@ -79,3 +79,12 @@ for it in range(8):
         i = it * 4 + h
         print(f"tile {it} h{h}: L1 issue {rel(tr[0,i,0]):7.0f} {rel(tr[0,i,1]):7.0f} | epi1 {rel(tr[3,i,0]):7.0f} {rel(tr[3,i,1]):7.0f}")
     print(f"tile {it}   : L2 {rel(tr[1,it,0]):7.0f} {rel(tr[1,it,1]):7.0f} | epi2 {rel(tr[3,it*4+2,0]):7.0f} {rel(tr[3,it*4+2,1]):7.0f} | L3 {rel(tr[2,it,0]):7.0f} {rel(tr[2,it,1]):7.0f} | epi3 {rel(tr[3,it*4+3,0]):7.0f} {rel(tr[3,it*4+3,1]):7.0f}")
+
+# fine-grained stamps of epilogue warp 0 (role-1 slots 64..): 8 per chunk
+names = ["entry", "tmem ld done", "math done", "A slot free", "tcgen05.st issued", "box written + fence", "st done + a_full", "TMA store issued"]
+fine = tr[1, 64:, :].reshape(-1)
+n = int((fine > 0).sum()) // 8
+print("epilogue warp 0, per chunk (ns since the chunk's entry; chunks in program order: L1h0 c0, c2, L1h1 c0, c2, L2 c0, c2, L3 c0, ...):")
+for c in range(min(n, 28)):
+    st = fine[8 * c: 8 * c + 8]
+    print(f"chunk {c:2d} @ {rel(st[0]):7.0f}: " + "  ".join(f"{names[k]} +{(st[k] - st[0]) / 1.9:.0f}" for k in range(1, 8)))
