@@ -188,12 +188,19 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_clip_adam_kernel(const __g
   if ((int)blockIdx.x >= a.main_blocks) {   // ride-along CTAs: independent of everything below, no barrier
     const AuxNormalise& x = a.aux;
     const int64_t astride = (int64_t)x.blocks * kThreads;
-    for (int64_t i = (int64_t)((int)blockIdx.x - a.main_blocks) * kThreads + tid; i < x.total; i += astride) {
-      const int64_t r = i / x.cols;
-      const int cc = (int)(i - r * x.cols);
+    int64_t i = (int64_t)((int)blockIdx.x - a.main_blocks) * kThreads + tid;
+    if (i >= x.total) return;
+    // (row, column) of the first element by one division, then stepped: no 64-bit division per element
+    int64_t r = i / x.cols;
+    int cc = (int)(i - r * x.cols);
+    const int64_t dr = astride / x.cols;
+    const int dc = (int)(astride - dr * x.cols);
+    for (; i < x.total; i += astride) {
       float y = __fdiv_rn(__fsub_rn(mnr::ld_stream(x.x + i), __ldg(x.mean + cc)), __ldg(x.denom + cc));   // normalizers.py:65-68
       if (x.lo <= x.hi) y = fminf(fmaxf(y, x.lo), x.hi);
       x.y[r * x.y_ld + cc] = y;
+      r += dr, cc += dc;
+      if (cc >= x.cols) cc -= x.cols, r += 1;
     }
     return;
   }

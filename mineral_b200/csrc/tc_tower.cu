@@ -364,13 +364,13 @@ __global__ void __launch_bounds__(kBaseThreads + EPIW * 32, 1) tc_tower_fwd_kern
           ptx::st_shared_v4(row_addr + (uint32_t)((piece ^ (lane & 7)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
         }
       }
-      ptx::fence_proxy_async_smem();
-      TT_FINE();
-      if (to_a) {
+      if (to_a) {   // hand the A slot on first: the next layer's MMAs wait for it, the store to HBM does not hurry
         ptx::tmem_st_wait();
         ptx::tc_fence_before();
         ptx::mbar_arrive(&a_full[as]);
       }
+      TT_FINE();
+      ptx::fence_proxy_async_smem();
       TT_FINE();
       __syncwarp();
       if (ptx::elect_one()) {
