@@ -161,8 +161,9 @@ def test_simt_linear_fwd_dx_dw_thin_and_tile(M, N, K):
     assert torch.equal(again, dwa), "weight gradient is not deterministic"
 
 
+# (256, 128, *) and (128, 128, *): 16 epilogue warps (A-slot uses per tile % 4 == 0); (*, 64, *): the 8-warp form; ragged M; K0 = 64
 TOWER_CASES = [(4096, 37, (256, 128, 64), 1), (300, 37, (256, 128, 64), 1), (1024, 64, (128, 64, 32), 2), (2048, 20, (256, 64, 128), 0),
-               (32768, 37, (256, 128, 64), 1)]
+               (32768, 37, (256, 128, 64), 1), (4096, 40, (256, 128, 128), 1), (1000, 37, (128, 128, 64), 2), (20000, 64, (256, 128, 32), 0)]
 
 
 @pytest.mark.parametrize("M,K0,widths,act", TOWER_CASES)
