@@ -34,8 +34,10 @@ __device__ int g_htrace_on = 0;
     }                                                                                          \
   } while (0)
 
-constexpr int kRows = 128;     // rows per tile
-constexpr int kThreadsHF = 256;  // 2 threads per row: thread (r, h) takes the float4 columns c = h, h + 2, ... of row r
+constexpr int kThreadsHF = 256;  // TPR threads per row: thread (r, h) takes the float4 columns c = h, h + TPR, ... of row r
+// rows per tile = kThreadsHF / TPR: TPR = 2 (128-row tiles) when the minibatch fills the GPU with them; TPR = 8 (32-row tiles)
+// for small minibatches (the reference's shipped recipes: 2048 rows = 16 tiles of 128 on 148 SMs), where the kernel is ONE
+// tile's dependent chain: 4x the CTAs, a quarter of the instructions per thread
 
 struct FusedHeadsArgs {
   const float *y3a, *y3v;                // (M,H)
@@ -106,9 +108,10 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 // bound by per-thread instruction latency (every instruction runs once or twice per warp), hence TWO threads per row:
 // each takes every other float4 column of the row in the dot-product / dY3 sweeps and every other action column in the
 // loss loops; partial sums meet through one __shfl_xor.
-template <int A, int H, bool LEARNED>
+template <int A, int H, bool LEARNED, int TPR>
 __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid_constant__ FusedHeadsArgs a,
                                                             const __grid_constant__ mnr_ppo_loss_cfg_t cfg) {
+  constexpr int kRows = kThreadsHF / TPR;
   constexpr int P = H + 8, P4 = P / 4, H4 = H / 4;  // pitch == 8 (mod 32): the 4 rows x 2 halves of an LDS.128 phase never collide
   constexpr int NY = (LEARNED ? 2 : 1) * A;          // gradient rows fed by Y3a: g_mu | g_ls
   constexpr int GP = 4 * A + 4;                      // s_g pitch: g_mu | g_ls | mu | sigma | g_v | pad  (float4-aligned groups,
@@ -119,6 +122,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   constexpr int kWarpsHF = kThreadsHF / 32;
   constexpr int CS = kThreadsHF / GW, CSR = (kRows + CS - 1) / CS;   // column sums: CS row slices of CSR rows
   static_assert(A % 4 == 0 && A <= 32 && NRG >= 1 && RPG >= 1 && NY * UV <= 64, "unsupported head shape");
+  static_assert(TPR >= 2 && TPR <= 32 && (TPR & (TPR - 1)) == 0, "a row's threads are an aligned group inside one warp");
   const int Ar = a.A;  // real action dimension, Ar <= A
   extern __shared__ __align__(16) float sh[];
   __shared__ double s_red[kThreadsHF], s_fin[16];
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // PREF_V (H <= 64): the Y3v tile has its own buffer and is requested (cp.async) together with the Y3a tile at the top of
   // the tile, so the DRAM round trip in the middle of the tile is gone; wider towers keep one buffer (2 CTAs per SM).
-  constexpr bool PREF_V = H <= 64;
+  constexpr bool PREF_V = H <= 64 || kRows <= 64;
   float* s_y = sh;                                   // [128][P]: Y3a tile, then dY3a (!PREF_V: then Y3v tile, then dY3v)
   float* s_yv = s_y + (PREF_V ? kRows * P : 0);      // [128][P]: Y3v tile, then dY3v
   float* s_wmu = s_yv + kRows * P;                   // (A,H)
@@ -136,15 +140,17 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   float* s_g = s_wv + H;                             // [128][GP]
 
   HF_TRACE(0);
-  for (int i = tid; i < A * H; i += kThreadsHF) {
-    const bool real = i < Ar * H;
-    s_wmu[i] = real ? __ldg(a.w_mu + i) : 0.f;
-    if (LEARNED) s_wsig[i] = real ? __ldg(a.w_sig + i) : 0.f;
-  }
-  for (int i = tid; i < H; i += kThreadsHF) s_wv[i] = __ldg(a.w_v + i);
-  float b_mu[A], b_sig[A];
-#pragma unroll
-  for (int j = 0; j < A; ++j) b_mu[j] = j < Ar ? __ldg(a.b_mu + j) : 0.f, b_sig[j] = j < Ar ? __ldg(a.b_sig + j) : 0.f;
+  auto stage_weights = [&]() {
+    for (int i = tid; i < A * H; i += kThreadsHF) {
+      const bool real = i < Ar * H;
+      s_wmu[i] = real ? __ldg(a.w_mu + i) : 0.f;
+      if (LEARNED) s_wsig[i] = real ? __ldg(a.w_sig + i) : 0.f;
+    }
+    for (int i = tid; i < H; i += kThreadsHF) s_wv[i] = __ldg(a.w_v + i);
+  };
+  if (!PREF_V) stage_weights();   // PREF_V: after the first tile's cp.async requests are in flight (below)
+  __shared__ float b_mu[A], b_sig[A];   // head biases (fixed sigma: b_sig = the sigma parameter): read once per row and tile
+  if (tid < A) b_mu[tid] = tid < Ar ? __ldg(a.b_mu + tid) : 0.f, b_sig[tid] = tid < Ar ? __ldg(a.b_sig + tid) : 0.f;
 
   const float w = cfg.grad_scale / (float)a.M;
   const float b_v = __ldg(a.b_v);
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const int64_t row0 = (int64_t)tile * kRows;
     const int rows_here = (int)min((int64_t)kRows, a.M - row0);
-    const int r = tid >> 1, h = tid & 1;
+    const int r = tid / TPR, h = tid % TPR;
     const bool valid = r < rows_here;
     const int64_t row = valid ? row0 + r : a.M - 1;
     float* grow = s_g + r * GP;
@@ -195,6 +201,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
         cp_async16(&s_v4[rr * P4 + c], gyv + (row0 + (ok ? rr : 0)) * H4 + c, ok);
       }
       cp_async_commit();
+      if (tile == (int)blockIdx.x) stage_weights();
       cp_async_wait<1>();   // the Y3a tile has landed; Y3v keeps flying
     } else {
       const float4* gy = reinterpret_cast<const float4*>(a.y3a);
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 #pragma unroll
     for (int j = 0; j < A; ++j) mu_raw[j] = 0.f, ls[j] = 0.f;
 #pragma unroll 2
-    for (int c = h; c < H4; c += 2) {
+    for (int c = h; c < H4; c += TPR) {
       const float4 ya = s_y4[r * P4 + c];
 #pragma unroll
       for (int j = 0; j < A; ++j) {
@@ -220,16 +227,18 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       }
     }
 #pragma unroll
-    for (int j = 0; j < A; ++j) {
-      mu_raw[j] += __shfl_xor_sync(0xffffffffu, mu_raw[j], 1);
-      if (LEARNED) ls[j] += __shfl_xor_sync(0xffffffffu, ls[j], 1);
-    }
+    for (int d = 1; d < TPR; d <<= 1)
+#pragma unroll
+      for (int j = 0; j < A; ++j) {
+        mu_raw[j] += __shfl_xor_sync(0xffffffffu, mu_raw[j], d);
+        if (LEARNED) ls[j] += __shfl_xor_sync(0xffffffffu, ls[j], d);
+      }
     // ---- per-element loss terms.  ROLLED loops over the action columns (half h takes j = h, h + 2, ..) with the row's
     //      values parked in its own s_g row (slots [0,A) raw mu, [A,2A) raw logstd -> later g_mu, g_ls; [2A,3A) mu;
     //      [3A,4A) sigma): keeps the transcendental-heavy body in the code once instead of A times.
 #pragma unroll
     for (int j = 0; j < A; ++j)
-      if ((j & 1) == h) {
+      if ((j % TPR) == h) {
         grow[j] = mu_raw[j] + b_mu[j], grow[A + j] = LEARNED ? ls[j] + b_sig[j] : b_sig[j];
         if (j >= Ar) grow[2 * A + j] = 0.f, grow[3 * A + j] = 0.f;  // pad columns: defined (and ignored) in the column sums
       }
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     float nlp = 0.f, ent = 0.f, bsum = 0.f, kl = 0.f;
     const float* act_row = a.actions + (size_t)row * Ar;
 #pragma unroll 1
-    for (int j = h; j < Ar; j += 2) {
+    for (int j = h; j < Ar; j += TPR) {
       float mu, sg, dmu, dsg, db;
       dist_fwd(cfg, grow[j], grow[A + j], mu, sg, dmu, dsg);
       const float diff = __ldg(act_row + j) - mu;
@@ -248,8 +257,11 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       kl += kl_elem(mu, sg, a.old_mu[(size_t)row * Ar + j], a.old_sigma[(size_t)row * Ar + j]);
       grow[2 * A + j] = mu, grow[3 * A + j] = sg;
     }
-    nlp += __shfl_xor_sync(0xffffffffu, nlp, 1), ent += __shfl_xor_sync(0xffffffffu, ent, 1);
-    bsum += __shfl_xor_sync(0xffffffffu, bsum, 1), kl += __shfl_xor_sync(0xffffffffu, kl, 1);
+#pragma unroll
+    for (int d = 1; d < TPR; d <<= 1) {
+      nlp += __shfl_xor_sync(0xffffffffu, nlp, d), ent += __shfl_xor_sync(0xffffffffu, ent, d);
+      bsum += __shfl_xor_sync(0xffffffffu, bsum, d), kl += __shfl_xor_sync(0xffffffffu, kl, d);
+    }
     HF_TRACE(3);
     float dl_dnlp, clipped;
     const float a_loss = actor_row(__ldg(a.old_nlp + row), nlp, __ldg(a.adv + row), cfg.e_clip, cfg.use_smooth_clamp, &dl_dnlp, &clipped);
@@ -257,7 +269,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     const float g_nlp = w * dl_dnlp;
     const float span = cfg.maxstd - cfg.minstd;
 #pragma unroll 1
-    for (int j = h; j < Ar; j += 2) {
+    for (int j = h; j < Ar; j += TPR) {
       const float mu = grow[2 * A + j], sg = grow[3 * A + j];
       const float diff = __ldg(act_row + j) - mu;
       float dmu = 1.f, dsg = sg;                                  // d mu / d mu_raw, d sigma / d logstd (dist.py:32-47)
@@ -279,7 +291,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     if (valid && (Ar & 3) == 0) {  // row-contiguous float4 copies of the finished row pieces (half h takes every other piece)
 #pragma unroll
       for (int j4 = 0; j4 < A / 4; ++j4) {
-        if ((j4 & 1) != h || 4 * j4 >= Ar) continue;
+        if ((j4 % TPR) != h || 4 * j4 >= Ar) continue;
         const float4 gm4 = reinterpret_cast<const float4*>(grow)[j4], gl4 = reinterpret_cast<const float4*>(grow + A)[j4];
         if (a.g_mu) reinterpret_cast<float4*>(a.g_mu + (size_t)row * Ar)[j4] = gm4;
         if (a.g_ls) reinterpret_cast<float4*>(a.g_ls + (size_t)row * Ar)[j4] = gl4;
@@ -289,7 +301,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
         }
       }
     } else if (valid) {  // action dimension not a multiple of 4: rows are not 16 B aligned, element-wise copies
-      for (int j = h; j < Ar; j += 2) {
+      for (int j = h; j < Ar; j += TPR) {
         if (a.g_mu) a.g_mu[(size_t)row * Ar + j] = grow[j];
         if (a.g_ls) a.g_ls[(size_t)row * Ar + j] = grow[A + j];
         if (a.write_back) a.old_mu[(size_t)row * Ar + j] = grow[2 * A + j], a.old_sigma[(size_t)row * Ar + j] = grow[3 * A + j];
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < A; ++j) gm[j] = grow[j], gl[j] = LEARNED ? grow[A + j] : 0.f;
 #pragma unroll 2
-      for (int c = h; c < H4; c += 2) {
+      for (int c = h; c < H4; c += TPR) {
         float4 da = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < A; ++j) {
@@ -364,8 +376,9 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     // =========================== value tower ===========================================================
     float value = 0.f;
 #pragma unroll 4
-    for (int c = h; c < H4; c += 2) value = dot4(s_v4[r * P4 + c], s_wv4[c], value);
-    value += __shfl_xor_sync(0xffffffffu, value, 1);
+    for (int c = h; c < H4; c += TPR) value = dot4(s_v4[r * P4 + c], s_wv4[c], value);
+#pragma unroll
+    for (int d = 1; d < TPR; d <<= 1) value += __shfl_xor_sync(0xffffffffu, value, d);
     value += b_v;
     float dl_dv;
     const float ret = __ldg(a.returns + row);
@@ -401,7 +414,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
     __syncthreads();
     HF_TRACE(10);
 #pragma unroll 4
-    for (int c = h; c < H4; c += 2) {
+    for (int c = h; c < H4; c += TPR) {
       const float4 wv = s_wv4[c];
       float4 dv = make_float4(g_v * wv.x, g_v * wv.y, g_v * wv.z, g_v * wv.w);
       if (cfg.dz_act) {
@@ -428,7 +441,8 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   // every thread parks its accumulators of as many gradient rows as the tile buffer holds ([row][row group][H]), ONE barrier,
   // then all threads sum the row groups of their outputs in a fixed order (was: one gradient row per pass, two barriers each)
   float* s_fold = s_y;
-  constexpr int FR_MAX = (kRows * P) / (NRG * H), FR = FR_MAX < NY + 1 ? FR_MAX : NY + 1, NPASS = (NY + 1 + FR - 1) / FR;
+  constexpr int FR_MAX = ((PREF_V ? 2 : 1) * kRows * P) / (NRG * H);   // PREF_V: the two tile buffers are contiguous
+  constexpr int FR = FR_MAX < NY + 1 ? FR_MAX : NY + 1, NPASS = (NY + 1 + FR - 1) / FR;
   static_assert(FR >= 1, "tile buffer too small for the fold");
 #pragma unroll
   for (int pass = 0; pass < NPASS; ++pass) {
@@ -477,25 +491,41 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
 
   // ---- every CTA reduces its share of the PW outputs over all CTAs (warp per output, fixed order) ----------------
   const int n_cta = gridDim.x;
-  for (int o = blockIdx.x * kWarpsHF + warp; o < PW; o += n_cta * kWarpsHF) {
-    float sum = 0.f;
-    for (int x = lane; x < n_cta; x += 32) sum += __ldcg(a.partials + (size_t)x * PW + o);
+  auto put = [&](int o, float sum) {
+    if (o < (2 * A + 1) * H) {
+      const int jrow = o / H, u2 = o - jrow * H;
+      if (jrow < A) { if (jrow < Ar) a.dw_mu[jrow * H + u2] = sum; }
+      else if (jrow < 2 * A) { if (LEARNED && jrow - A < Ar) a.dw_sig[(jrow - A) * H + u2] = sum; }
+      else a.dw_v[u2] = sum;
+    } else {
+      const int j = o - (2 * A + 1) * H;
+      if (j < A) { if (j < Ar) a.db_mu[j] = sum; }
+      else if (j < 2 * A) { if (j - A < Ar) a.db_sig[j - A] = sum; }  // learned: bias gradient; fixed: d sigma = colsum g_ls
+      else if (j < 3 * A) { if (a.mu_mean && j - 2 * A < Ar) a.mu_mean[j - 2 * A] = sum / (float)a.M; }
+      else if (j < 4 * A) { if (a.sigma_mean && j - 3 * A < Ar) a.sigma_mean[j - 3 * A] = sum / (float)a.M; }
+      else a.db_v[0] = sum;
+    }
+  };
+  if (n_cta <= 64) {
+    // few CTAs (small minibatches): the warp-per-output form below is a chain of PW / (8 n_cta) dependent L2 round trips
+    // per warp (11 us at 16 CTAs).
+    // 8 lanes per output (CTA partials x = q, q + 8, ..), the lanes' sums folded by three shuffles: <= 8 loads per lane
+    const int q = tid & 7;
+    for (int o0 = (blockIdx.x * kThreadsHF + tid) >> 3; o0 - ((tid >> 3) & 3) < PW; o0 += (n_cta * kThreadsHF) >> 3) {
+      const int o = o0 < PW ? o0 : PW - 1;   // whole warps stay in the loop (shuffles); the clamped lanes do not write
+      float sum = 0.f;
+#pragma unroll 8
+      for (int x = q; x < n_cta; x += 8) sum += __ldcg(a.partials + (size_t)x * PW + o);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1), sum += __shfl_xor_sync(0xffffffffu, sum, 2), sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      if (q == 0 && o0 < PW) put(o, sum);
+    }
+  } else {
+    for (int o = blockIdx.x * kWarpsHF + warp; o < PW; o += n_cta * kWarpsHF) {
+      float sum = 0.f;
+      for (int x = lane; x < n_cta; x += 32) sum += __ldcg(a.partials + (size_t)x * PW + o);
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    if (lane == 0) {
-      if (o < (2 * A + 1) * H) {
-        const int jrow = o / H, u2 = o - jrow * H;
-        if (jrow < A) { if (jrow < Ar) a.dw_mu[jrow * H + u2] = sum; }
-        else if (jrow < 2 * A) { if (LEARNED && jrow - A < Ar) a.dw_sig[(jrow - A) * H + u2] = sum; }
-        else a.dw_v[u2] = sum;
-      } else {
-        const int j = o - (2 * A + 1) * H;
-        if (j < A) { if (j < Ar) a.db_mu[j] = sum; }
-        else if (j < 2 * A) { if (j - A < Ar) a.db_sig[j - A] = sum; }  // learned: bias gradient; fixed: d sigma = colsum g_ls
-        else if (j < 3 * A) { if (a.mu_mean && j - 2 * A < Ar) a.mu_mean[j - 2 * A] = sum / (float)a.M; }
-        else if (j < 4 * A) { if (a.sigma_mean && j - 3 * A < Ar) a.sigma_mean[j - 3 * A] = sum / (float)a.M; }
-        else a.db_v[0] = sum;
-      }
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      if (lane == 0) put(o, sum);
     }
   }
   HF_TRACE(14);
@@ -544,15 +574,19 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   }
 }
 
-template <int A, int H, bool LEARNED>
-size_t fused_smem_bytes() {
-  return (size_t)((H <= 64 ? 2 : 1) * kRows * (H + 8) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
+template <int A, int H, bool LEARNED, int TPR>
+constexpr size_t fused_smem_bytes() {
+  constexpr int kRows = kThreadsHF / TPR;
+  return (size_t)((H <= 64 || kRows <= 64 ? 2 : 1) * kRows * (H + 8) + (LEARNED ? 2 : 1) * A * H + H + kRows * (4 * A + 4)) * sizeof(float);
 }
 
-template <int A, int H, bool LEARNED>
-int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
-  const size_t smem = fused_smem_bytes<A, H, LEARNED>();
-  auto kern = heads_fused_kernel<A, H, LEARNED>;
+// 32-row tiles while those still leave SMs idle (see kThreadsHF), else 128-row tiles
+bool small_tiles_for(int64_t M) { return (M + 31) / 32 <= (int64_t)mnr_sm_count() * 2; }
+
+template <int A, int H, bool LEARNED, int TPR>
+int launch_fused_t(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
+  const size_t smem = fused_smem_bytes<A, H, LEARNED, TPR>();
+  auto kern = heads_fused_kernel<A, H, LEARNED, TPR>;
   static int occ_cached = -1;   // per instantiation
   if (occ_cached < 0) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -569,6 +603,18 @@ int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap,
   cudaError_t e = mnr_launch_pdl(kern, dim3(grid), dim3(kThreadsHF), smem, stream, a, cfg);
   if (e == cudaSuccess) e = cudaPeekAtLastError();
   return e == cudaSuccess ? MNR_OK : (int)e;
+}
+
+template <int A, int H, bool LEARNED>
+int launch_fused(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_cap, cudaStream_t stream) {
+  // wide heads (AllegroHand: 16 actions, learned sigma, 128 hidden): a 128-row tile with its gradient rows needs > 113 KB of
+  // shared memory = ONE CTA of 8 warps per SM and two tiles back to back per CTA; 64-row tiles (4 threads per row) keep two
+  // CTAs per SM, prefetch the value tower's tile, and halve the per-thread chains
+  constexpr int TPR_BIG = fused_smem_bytes<A, H, LEARNED, 2>() > 113 * 1024 ? 4 : 2;
+  const int rows = kThreadsHF / (small_tiles_for(a.M) ? 8 : TPR_BIG);
+  a.n_tiles = (int)((a.M + rows - 1) / rows);
+  return rows == kThreadsHF / 8 ? launch_fused_t<A, H, LEARNED, 8>(a, cfg, grid_cap, stream)
+                                : launch_fused_t<A, H, LEARNED, TPR_BIG>(a, cfg, grid_cap, stream);
 }
 
 template <int A, bool LEARNED>
@@ -644,7 +690,7 @@ int mnr_heads_fused_launch(const float* y3a, const float* y3v, const float* w_mu
   a.barrier = reinterpret_cast<unsigned long long*>(ws);
   a.loss_parts = reinterpret_cast<mnr_loss::LossPartial*>(ws + 256);
   a.partials = reinterpret_cast<float*>(ws + 256 + (((size_t)cap * sizeof(mnr_loss::LossPartial) + 255) / 256) * 256);
-  a.M = M, a.A = A, a.write_back = write_back, a.n_tiles = (int)((M + kRows - 1) / kRows);
+  a.M = M, a.A = A, a.write_back = write_back, a.n_tiles = 0;   // set with the tile height (launch_fused)
   if (A % 4 == 0 && (!mnr_aligned(actions, 16) || !mnr_aligned(old_mu, 16) || !mnr_aligned(old_sigma, 16) ||
                      (g_mu && !mnr_aligned(g_mu, 16)) || (g_ls && !mnr_aligned(g_ls, 16))))
     return MNR_EALIGN;

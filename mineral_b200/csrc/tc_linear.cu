@@ -1051,6 +1051,13 @@ int tc_dw_splits(int M, int tiles) {
   if (s < s_min) s = s_min;
   const int max_s = (M + 63) / 64;  // >= 64 rows (2 k-blocks) per work item
   if (s > max_s) s = max_s;
+  // MNR_TC_DW_SPLIT_CAP (A/B measurements): fewer, longer splits = less partial traffic for the reduce launch, fewer CTAs
+  static int cap = -1;
+  if (cap < 0) {
+    const char* e = getenv("MNR_TC_DW_SPLIT_CAP");
+    cap = e ? atoi(e) : 0;
+  }
+  if (cap > 0 && s > cap) s = cap < s_min ? s_min : cap;
   return s < 1 ? 1 : s;
 }
 

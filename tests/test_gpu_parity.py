@@ -806,7 +806,10 @@ def test_fused_towers_vs_autograd(rows, O, A, units, act, fixed_sigma, norm, use
                                                              (333, 3, 16, True, "normal"), (1000, 16, 128, False, "dreamerv3_normal"),
                                                              (32768, 8, 64, True, "normal"), (300, 21, 64, True, "normal"),
                                                              (500, 6, 64, False, "dreamerv3_normal"), (260, 30, 128, False, "normal"),
-                                                             (129, 1, 32, True, "normal")])
+                                                             (129, 1, 32, True, "normal"),
+                                                             # above 9472 rows the kernel runs 128-row tiles (2 threads per row), below 32-row tiles (8)
+                                                             (12001, 16, 128, False, "dreamerv3_normal"), (9601, 8, 32, True, "normal"),
+                                                             (9472, 8, 128, False, "dreamerv3_normal")])
 def test_fused_heads_loss_vs_unfused(rows, A, H, fixed_sigma, dist_type):
     """ppo_heads_loss_kernel + head_grads_kernel == heads forward (SIMT) + ppo_loss_kernel + heads backward."""
     from mineral_b200 import ops
