@@ -401,6 +401,48 @@ int mnr_tc_grid_cap(int ctas);
 int mnr_tc_cache_hints(int flags);
 int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, mnr_stream_t stream);
 
+/* Deferred folds.  Two kernels of an optimizer step end with "every CTA parks a partial, grid barrier, fixed-order sum over
+ * the CTAs": the heads + loss kernel (head parameter gradients, mu / sigma means, the ten metrics; mnr_ppo_heads_loss_fwd_bwd)
+ * and LayerNorm's backward (dgamma / dbeta; mnr_ln_act_bwd).  Nothing reads those sums before the optimizer launch
+ * (autograd's .grad of mineral/agents/ppo/ppo.py:292-311), so while a fold list is registered with mnr_fold_defer() the two
+ * entry points stop after parking their partials - no grid barrier, no tail - and append a description of the outstanding
+ * sums to the list; mnr_tc_reduce_partials_folds() then computes them in extra blocks of the ONE split-reduce launch that
+ * precedes the optimizer anyway (fixed order: deterministic).  The list is host memory owned by the caller; the partials live
+ * in the workspaces given to the deferring calls, which must stay untouched until the reduce launch has run. */
+#define MNR_FOLD_MAX_SEGS 8
+#ifndef MNR_MAX_FOLDS
+#define MNR_MAX_FOLDS 8
+#endif
+typedef struct {
+  int32_t begin, end;   /* columns [begin, end) of the partial rows ... */
+  float* dst;           /* ... summed over the rows, times scale, to dst[0 .. end - begin) */
+  float scale;
+  int32_t _pad;
+} mnr_fold_seg_t;
+typedef struct {
+  const float* parts;   /* [n_parts][width] */
+  int32_t n_parts, width, n_segs, _pad;
+  mnr_fold_seg_t seg[MNR_FOLD_MAX_SEGS];
+} mnr_fold_job_t;
+typedef struct {        /* the ten PPO metrics from the per-CTA loss partials of the heads + loss kernel */
+  const double* loss_parts;   /* [n_parts][12] */
+  float* metrics;             /* (MNR_PPO_METRICS) */
+  int64_t M;
+  int32_t n_parts, _pad;
+  float critic_coef, entropy_coef, bounds_loss_coef, metric_scale;
+} mnr_heads_metrics_job_t;
+typedef struct {
+  mnr_fold_job_t folds[MNR_MAX_FOLDS];
+  mnr_heads_metrics_job_t metrics;
+  int32_t n_folds, has_metrics;
+} mnr_fold_list_t;
+/* Register (list != NULL: emptied, then appended to by the deferring calls of THIS host thread) or clear (NULL) the list. */
+int mnr_fold_defer(mnr_fold_list_t* list /*host*/);
+/* mnr_tc_reduce_partials + the folds of `list` (may be NULL or empty) in the same launch; n_jobs == 0 with a non-empty list
+ * launches the folds alone. */
+int mnr_tc_reduce_partials_folds(const mnr_tc_reduce_job_t* jobs /*host*/, int n_jobs, const mnr_fold_list_t* list /*host*/,
+                                 mnr_stream_t stream);
+
 /* A whole 3-layer tower forward in ONE launch (csrc/tc_tower.cu): y[l] = act(y[l-1] . W_l^T + bias_l), y[-1] = x, for every
  * group (tower), replacing MLP.forward (mineral/nets/mlp.py:25-77; both PPO towers: mineral/agents/ppo/models.py:136-151).
  * Layer outputs go from one GEMM to the next through tensor memory; every y[l] is also written (the backward pass needs it).

@@ -88,6 +88,24 @@ class TcReduceJob(C.Structure):
                 ("workspace_bytes", C.c_size_t), ("grid_cap", C.c_int32), ("_pad", C.c_int32)]
 
 
+class FoldSeg(C.Structure):
+    _fields_ = [("begin", C.c_int32), ("end", C.c_int32), ("dst", C.c_void_p), ("scale", C.c_float), ("_pad", C.c_int32)]
+
+
+class FoldJob(C.Structure):
+    _fields_ = [("parts", C.c_void_p), ("n_parts", C.c_int32), ("width", C.c_int32), ("n_segs", C.c_int32), ("_pad", C.c_int32),
+                ("seg", FoldSeg * 8)]
+
+
+class HeadsMetricsJob(C.Structure):
+    _fields_ = [("loss_parts", C.c_void_p), ("metrics", C.c_void_p), ("M", C.c_int64), ("n_parts", C.c_int32), ("_pad", C.c_int32),
+                ("critic_coef", C.c_float), ("entropy_coef", C.c_float), ("bounds_loss_coef", C.c_float), ("metric_scale", C.c_float)]
+
+
+class FoldList(C.Structure):
+    _fields_ = [("folds", FoldJob * 8), ("metrics", HeadsMetricsJob), ("n_folds", C.c_int32), ("has_metrics", C.c_int32)]
+
+
 class TowerGroup(C.Structure):
     _fields_ = [("x", C.c_void_p), ("w_hi", C.c_void_p * 3), ("w_lo", C.c_void_p * 3), ("bias", C.c_void_p * 3), ("y", C.c_void_p * 3),
                 ("ldx", C.c_int32), ("ldw", C.c_int32 * 3)]
@@ -155,6 +173,8 @@ SIGNATURES = {
     "mnr_tc_linear_bwd_weight": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
     "mnr_tc_linear_bwd_weight_partials": (i32, [C.POINTER(LinearGroup), i32, i32, i32, vp, sz, vp]),
     "mnr_tc_reduce_partials": (i32, [C.POINTER(TcReduceJob), i32, vp]),
+    "mnr_fold_defer": (i32, [C.POINTER(FoldList)]),
+    "mnr_tc_reduce_partials_folds": (i32, [C.POINTER(TcReduceJob), i32, C.POINTER(FoldList), vp]),
     "mnr_tc_trace": (i32, [i32, vp]),
     "mnr_tc_grid_cap": (i32, [i32]),
     "mnr_tc_cache_hints": (i32, [i32]),

@@ -722,9 +722,11 @@ class _UpdateEngine:
                 if self.towers.fused_heads_ok:
                     # towers -> fused heads + loss (+ head grads, d/dY3) -> towers backward
                     self.towers.forward_towers(x_buf, x_ld, split=not opt_splits)
+                    # the cross-CTA sums of the heads kernel and of LayerNorm's backward run inside the split-reduce launch
+                    folds = self.towers.stack.fold_begin()
                     self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), a.optim.tail if peer else m,
                                                    self.loss_cfg, self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
-                    self.towers.backward_towers(x_buf)
+                    self.towers.backward_towers(x_buf, folds=folds)
                 else:
                     # heads wider than the fused kernel takes: thin-layer head kernels + the row-wise loss kernel
                     self.towers.stack.forward(x_buf, x_ld, split=not opt_splits)

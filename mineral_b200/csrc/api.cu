@@ -12,6 +12,18 @@ bool mnr_pdl_enabled() {
   return cached == 1;
 }
 
+static thread_local mnr_fold_list_t* t_fold_list = nullptr;
+mnr_fold_list_t* mnr_fold_target() { return t_fold_list; }
+mnr_fold_job_t* mnr_fold_next() {
+  if (!t_fold_list || t_fold_list->n_folds >= MNR_MAX_FOLDS) return nullptr;
+  return &t_fold_list->folds[t_fold_list->n_folds];
+}
+extern "C" int mnr_fold_defer(mnr_fold_list_t* list) {
+  t_fold_list = list;
+  if (list) list->n_folds = 0, list->has_metrics = 0;
+  return MNR_OK;
+}
+
 extern "C" int mnr_abi_version(void) { return MNR_ABI_VERSION; }
 
 extern "C" const char* mnr_error_string(int code) {

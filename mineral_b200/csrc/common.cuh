@@ -17,6 +17,11 @@
     return e__ == cudaSuccess ? MNR_OK : (int)e__; \
   } while (0)
 
+// deferred folds (include/mineral_b200.h, mnr_fold_defer): the list registered by this host thread, or NULL (api.cu)
+mnr_fold_list_t* mnr_fold_target();
+// the next free fold slot of the registered list, or NULL when none is registered / the list is full
+mnr_fold_job_t* mnr_fold_next();
+
 static inline cudaStream_t mnr_cs(mnr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline bool mnr_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 

@@ -54,6 +54,7 @@ struct FusedHeadsArgs {
   float* partials;                       // [grid][PW]
   int64_t M;
   int A, write_back, n_tiles;
+  int defer;   // deferred fold (mnr_fold_defer): stop after parking the per-CTA partials
 };
 
 // 16 B asynchronous global -> shared copy (LDGSTS), zero fill when !valid
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
   }
 
   HF_TRACE(12);
+  if (a.defer) return;   // the sums over the CTAs run inside the split-reduce launch (tc_linear.cu, fold blocks)
   mnr::grid_barrier(a.barrier);
   HF_TRACE(13);
 
@@ -506,9 +508,9 @@ __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid
       else a.db_v[0] = sum;
     }
   };
-  if (n_cta <= 64) {
-    // few CTAs (small minibatches): the warp-per-output form below is a chain of PW / (8 n_cta) dependent L2 round trips
-    // per warp (11 us at 16 CTAs).
+  if (TPR >= 8) {
+    // small minibatches, few CTAs (a compile-time choice: each variant carries one form): the warp-per-output form below is
+    // a chain of PW / (8 n_cta) dependent L2 round trips per warp (11 us at 16 CTAs).
     // 8 lanes per output (CTA partials x = q, q + 8, ..), the lanes' sums folded by three shuffles: <= 8 loads per lane
     const int q = tid & 7;
     for (int o0 = (blockIdx.x * kThreadsHF + tid) >> 3; o0 - ((tid >> 3) & 3) < PW; o0 += (n_cta * kThreadsHF) >> 3) {
@@ -600,6 +602,30 @@ int launch_fused_t(FusedHeadsArgs& a, const mnr_ppo_loss_cfg_t& cfg, int grid_ca
   int grid = mnr_sm_count() * occ_cached;  // every CTA resident: the grid barrier needs it
   if (grid > grid_cap) grid = grid_cap;
   if (grid > a.n_tiles) grid = a.n_tiles;
+  // deferred fold: one job for the PW-wide partial rows (the layout the in-kernel reduce walks), one for the metrics
+  mnr_fold_list_t* fl = mnr_fold_target();
+  mnr_fold_job_t* fj = mnr_fold_next();
+  a.defer = (fl && fj && !fl->has_metrics) ? 1 : 0;
+  if (a.defer) {
+    const int Ar = a.A, PW = (2 * A + 1) * H + 4 * A + 1, c0 = (2 * A + 1) * H;
+    const float inv_m = 1.f / (float)a.M;
+    fj->parts = a.partials, fj->n_parts = grid, fj->width = PW, fj->n_segs = 0;
+    auto seg = [&](int begin, int n, float* dst, float scale) {
+      if (dst && n > 0) fj->seg[fj->n_segs++] = mnr_fold_seg_t{begin, begin + n, dst, scale, 0};
+    };
+    seg(0, Ar * H, a.dw_mu, 1.f);
+    if (LEARNED) seg(A * H, Ar * H, a.dw_sig, 1.f);
+    seg(2 * A * H, H, a.dw_v, 1.f);
+    seg(c0, Ar, a.db_mu, 1.f);
+    seg(c0 + A, Ar, a.db_sig, 1.f);
+    seg(c0 + 2 * A, Ar, a.mu_mean, inv_m);
+    seg(c0 + 3 * A, Ar, a.sigma_mean, inv_m);
+    seg(c0 + 4 * A, 1, a.db_v, 1.f);
+    fl->n_folds++;
+    fl->metrics = mnr_heads_metrics_job_t{reinterpret_cast<const double*>(a.loss_parts), a.metrics, a.M, grid, 0,
+                                          cfg.critic_coef, cfg.entropy_coef, cfg.bounds_loss_coef, cfg.metric_scale};
+    fl->has_metrics = 1;
+  }
   cudaError_t e = mnr_launch_pdl(kern, dim3(grid), dim3(kThreadsHF), smem, stream, a, cfg);
   if (e == cudaSuccess) e = cudaPeekAtLastError();
   return e == cudaSuccess ? MNR_OK : (int)e;
@@ -690,6 +716,7 @@ int mnr_heads_fused_launch(const float* y3a, const float* y3v, const float* w_mu
   a.barrier = reinterpret_cast<unsigned long long*>(ws);
   a.loss_parts = reinterpret_cast<mnr_loss::LossPartial*>(ws + 256);
   a.partials = reinterpret_cast<float*>(ws + 256 + (((size_t)cap * sizeof(mnr_loss::LossPartial) + 255) / 256) * 256);
+  a.defer = 0;
   a.M = M, a.A = A, a.write_back = write_back, a.n_tiles = 0;   // set with the tile height (launch_fused)
   if (A % 4 == 0 && (!mnr_aligned(actions, 16) || !mnr_aligned(old_mu, 16) || !mnr_aligned(old_sigma, 16) ||
                      (g_mu && !mnr_aligned(g_mu, 16)) || (g_ls && !mnr_aligned(g_ls, 16))))

@@ -25,6 +25,7 @@ struct LnArgs {
   float eps;
   float* partials;                // bwd: [groups][grid][2N]
   unsigned long long* barrier;    // bwd
+  int defer;                      // bwd: deferred fold (mnr_fold_defer): stop after parking the per-CTA partials
 };
 
 template <int ACT>
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
       part[c] = t;
     }
   }
+  if (a.defer) return;   // dgamma / dbeta are summed over the CTAs inside the split-reduce launch (tc_linear.cu, fold blocks)
   mnr::grid_barrier(a.barrier);
   const int n_cta = gridDim.x;
   for (int o = blockIdx.x * kWarps + warp; o < n_groups * 2 * N; o += n_cta * kWarps) {
@@ -198,7 +200,7 @@ int fill(LnArgs& a, const mnr_ln_group_t* groups, int n_groups, int64_t M, int N
     a.g[k] = g;
   }
   for (int k = n_groups; k < kMaxGroups; ++k) a.g[k] = groups[0];
-  a.M = M, a.N = N, a.n_groups = n_groups, a.partials = nullptr, a.barrier = nullptr;
+  a.M = M, a.N = N, a.n_groups = n_groups, a.partials = nullptr, a.barrier = nullptr, a.defer = 0;
   return MNR_OK;
 }
 
@@ -264,6 +266,17 @@ extern "C" int mnr_ln_act_bwd(const mnr_ln_group_t* groups, int n_groups, int64_
   a.partials = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 256);
   const int grid = bwd_grid(M);  // every CTA loops over the groups itself: one grid barrier for all of them
   const size_t smem = (size_t)kWarps * 2 * N * sizeof(float);
+  if (mnr_fold_list_t* fl = mnr_fold_target()) {   // deferred fold: one job per group, [grid][2N] partial rows -> dgamma | dbeta
+    if (fl->n_folds + n_groups <= MNR_MAX_FOLDS) {
+      a.defer = 1;
+      for (int gi = 0; gi < n_groups; ++gi) {
+        mnr_fold_job_t& fj = fl->folds[fl->n_folds++];
+        fj.parts = a.partials + (size_t)gi * grid * 2 * N, fj.n_parts = grid, fj.width = 2 * N, fj.n_segs = 2;
+        fj.seg[0] = mnr_fold_seg_t{0, N, groups[gi].dgamma, 1.f, 0};
+        fj.seg[1] = mnr_fold_seg_t{N, 2 * N, groups[gi].dbeta, 1.f, 0};
+      }
+    }
+  }
 #define MNR_LN_GO(KERNEL, EV, VV, AV, ...)                                                                     \
   {                                                                                                            \
     auto kern = KERNEL<EV, VV, AV>;                                                                            \

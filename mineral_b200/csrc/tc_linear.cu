@@ -816,13 +816,92 @@ struct ReduceJob {
 constexpr int kMaxReduceJobs = 4;
 struct ReduceJobs {
   ReduceJob j[kMaxReduceJobs];
+  int fold_rows;   // blockIdx.y < fold_rows: deferred folds (first, so that their blocks start in the grid's first wave)
 };
-__global__ void __launch_bounds__(256) tc_reduce_kernel(const __grid_constant__ ReduceJobs jobs) {
+
+// Deferred folds (include/mineral_b200.h, mnr_fold_defer): out[o] = scale * sum over the n_parts partial rows of column o, for
+// the columns a segment names.  Block = 8 columns (one 32 B sector per row) x 32 slices of the rows (row x = slice,
+// slice + 32, ..: <= 10 independent loads at 296 CTAs, all in flight), the slices added in order through shared memory.
+// blockIdx.y = fold index; the row after the last fold is the heads kernel's metrics job (one block); then the split reduce's rows.
+// __noinline__: the split reduce's own blocks must not pay (cold instruction cache) for code they never run - inlined, the
+// kernel grew 2.7x and its launch from 12.3 to 14.4 us.
+struct FoldJobs {
+  mnr_fold_job_t f[MNR_MAX_FOLDS];
+  mnr_heads_metrics_job_t m;
+  int n, has_m;
+};
+
+constexpr int kFoldCols = 8, kFoldSlices = 256 / kFoldCols;
+__device__ __noinline__ void fold_block(const FoldJobs& fj, int fi, float4 (*s_part)[32]) {
+  if (fi < fj.n) {
+    const mnr_fold_job_t& jb = fj.f[fi];
+    const int col = threadIdx.x % kFoldCols, slice = threadIdx.x / kFoldCols;
+    const int o = blockIdx.x * kFoldCols + col;
+    if ((int)blockIdx.x * kFoldCols >= jb.width) return;
+    float acc = 0.f;
+    if (o < jb.width) {
+      const float* src = jb.parts + o;
+#pragma unroll 10
+      for (int x = slice; x < jb.n_parts; x += kFoldSlices) acc += __ldcg(src + (size_t)x * jb.width);
+    }
+    float* s = reinterpret_cast<float*>(s_part);   // [32 slices][8 columns]
+    s[slice * kFoldCols + col] = acc;
+    __syncthreads();
+    if (slice != 0 || o >= jb.width) return;
+#pragma unroll
+    for (int q = 1; q < kFoldSlices; ++q) acc += s[q * kFoldCols + col];
+    for (int k = 0; k < jb.n_segs; ++k)
+      if (o >= jb.seg[k].begin && o < jb.seg[k].end) jb.seg[k].dst[o - jb.seg[k].begin] = acc * jb.seg[k].scale;
+    return;
+  }
+  if (fi != fj.n || !fj.has_m || blockIdx.x != 0) return;
+  // the ten loss metrics (csrc/heads_fused.cu, CTA-0 tail): partial rows of 12 doubles {a, c, b, h, clip, kl, n_d, S_d, Q_d,
+  // n_r, S_r, Q_r}; thread = (value k = tid & 15, slice = tid >> 4), fixed order
+  const mnr_heads_metrics_job_t& m = fj.m;
+  double* s_red = reinterpret_cast<double*>(s_part);   // 256 doubles = 2 KB of the 4 KB buffer
+  __shared__ double s_fin[16];
+  const int k = threadIdx.x & 15, sl = threadIdx.x >> 4;
+  double acc = 0.0;
+  if (k < 12) {
+#pragma unroll 8
+    for (int x = sl; x < m.n_parts; x += 16) acc += __ldcg(m.loss_parts + (size_t)x * 12 + k);
+  }
+  s_red[sl * 16 + k] = acc;
+  __syncthreads();
+  if (threadIdx.x < 12) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += s_red[q * 16 + threadIdx.x];
+    s_fin[threadIdx.x] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double inv_n = 1.0 / (double)m.M;
+    const double m2_d = s_fin[8] - s_fin[7] * s_fin[7] / s_fin[6], m2_r = s_fin[11] - s_fin[10] * s_fin[10] / s_fin[9];
+    const float av = (float)(s_fin[0] * inv_n), c = (float)(s_fin[1] * inv_n), b = (float)(s_fin[2] * inv_n), h = (float)(s_fin[3] * inv_n);
+    float out[MNR_PPO_METRICS];
+    out[0] = av + 0.5f * c * m.critic_coef - h * m.entropy_coef + b * m.bounds_loss_coef;
+    out[1] = av, out[2] = c, out[3] = b, out[4] = h;
+    out[5] = (float)(s_fin[4] * inv_n);
+    const float var_d = (float)(m2_d / (s_fin[6] - 1.0)), var_r = (float)(m2_r / (s_fin[9] - 1.0));
+    out[6] = fminf(fmaxf(1.f - var_d / (var_r + 1e-8f), 0.f), 1.f);
+    out[7] = (float)(s_fin[5] * inv_n);
+    out[8] = 0.f, out[9] = 0.f;
+    for (int q = 0; q < MNR_PPO_METRICS; ++q) m.metrics[q] = out[q] * m.metric_scale;
+  }
+}
+
+__global__ void __launch_bounds__(256, 8) tc_reduce_kernel(const __grid_constant__ ReduceJobs jobs, const __grid_constant__ FoldJobs folds) {
   __shared__ float4 s_part[8][32];
   mnr::pdl_trigger();
   mnr::pdl_wait();
-  const ReduceJob& jb = jobs.j[blockIdx.y / kMaxGroups];
-  const int gi = blockIdx.y % kMaxGroups;
+  if ((int)blockIdx.y < jobs.fold_rows) {
+    fold_block(folds, (int)blockIdx.y, s_part);
+    return;
+  }
+  const int by = (int)blockIdx.y - jobs.fold_rows;
+  const ReduceJob& jb = jobs.j[by / kMaxGroups];
+  const int gi = by % kMaxGroups;
   if (gi >= jb.n_groups || (int)blockIdx.x >= jb.wblocks + (jb.I + 31) / 32) return;
   const int splits = jb.splits, I = jb.I, wblocks = jb.wblocks;
   const int NK = I * jb.J;
@@ -1180,14 +1259,37 @@ int dw_launch(const mnr_linear_group_t* groups, int n_groups, int M, int act, vo
   return launch<kDw>(p, grid, stream);
 }
 
-int reduce_launch(const ReduceJobs& jobs, int n_jobs, cudaStream_t stream) {
+int reduce_launch(ReduceJobs& jobs, int n_jobs, cudaStream_t stream, const mnr_fold_list_t* list = nullptr) {
   int max_x = 1;
   for (int q = 0; q < n_jobs; ++q) {
     const int x = jobs.j[q].wblocks + (jobs.j[q].I + 31) / 32;
     max_x = x > max_x ? x : max_x;
   }
-  dim3 rgrid(max_x, n_jobs * kMaxGroups);
-  mnr_launch_pdl(tc_reduce_kernel, rgrid, dim3(256), 0, stream, jobs);
+  FoldJobs folds;
+  folds.n = 0, folds.has_m = 0;
+  if (list) {
+    if (list->n_folds < 0 || list->n_folds > MNR_MAX_FOLDS) return MNR_ESHAPE;
+    for (int q = 0; q < list->n_folds; ++q) {
+      const mnr_fold_job_t& f = list->folds[q];
+      if (!f.parts) return MNR_ENULL;
+      if (f.n_parts <= 0 || f.width <= 0 || f.n_segs < 0 || f.n_segs > MNR_FOLD_MAX_SEGS) return MNR_ESHAPE;
+      for (int k = 0; k < f.n_segs; ++k)
+        if (!f.seg[k].dst || f.seg[k].begin < 0 || f.seg[k].end > f.width || f.seg[k].end < f.seg[k].begin) return MNR_ESHAPE;
+      folds.f[q] = f;
+      const int x = (f.width + kFoldCols - 1) / kFoldCols;
+      max_x = x > max_x ? x : max_x;
+    }
+    folds.n = list->n_folds;
+    if (list->has_metrics) {
+      if (!list->metrics.loss_parts || !list->metrics.metrics) return MNR_ENULL;
+      if (list->metrics.n_parts <= 0 || list->metrics.M <= 0) return MNR_ESHAPE;
+      folds.m = list->metrics, folds.has_m = 1;
+    }
+  }
+  const int extra = folds.n + (folds.has_m ? 1 : 0);
+  jobs.fold_rows = extra;
+  dim3 rgrid(max_x, n_jobs * kMaxGroups + extra);
+  mnr_launch_pdl(tc_reduce_kernel, rgrid, dim3(256), 0, stream, jobs, folds);
   MNR_LAUNCH_RESULT();
 }
 }  // namespace
@@ -1207,8 +1309,14 @@ extern "C" int mnr_tc_linear_bwd_weight_partials(const mnr_linear_group_t* group
 }
 
 extern "C" int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs_in, int n_jobs, mnr_stream_t stream) {
-  MNR_CHECK_PTR(jobs_in);
-  if (n_jobs <= 0 || n_jobs > kMaxReduceJobs) return MNR_ESHAPE;
+  return mnr_tc_reduce_partials_folds(jobs_in, n_jobs, nullptr, stream);
+}
+
+extern "C" int mnr_tc_reduce_partials_folds(const mnr_tc_reduce_job_t* jobs_in, int n_jobs, const mnr_fold_list_t* list,
+                                            mnr_stream_t stream) {
+  const bool has_folds = list && (list->n_folds > 0 || list->has_metrics);
+  if (n_jobs < 0 || n_jobs > kMaxReduceJobs || (n_jobs == 0 && !has_folds)) return MNR_ESHAPE;   // folds alone are a valid launch
+  if (n_jobs > 0) MNR_CHECK_PTR(jobs_in);
   ReduceJobs jobs;
   const int cap_now = t_grid_cap;
   for (int q = 0; q < n_jobs; ++q) {
@@ -1218,7 +1326,7 @@ extern "C" int mnr_tc_reduce_partials(const mnr_tc_reduce_job_t* jobs_in, int n_
     t_grid_cap = cap_now;
     if (rc != MNR_OK) return rc;
   }
-  return reduce_launch(jobs, n_jobs, mnr_cs(stream));
+  return reduce_launch(jobs, n_jobs, mnr_cs(stream), list);
 }
 
 extern "C" int mnr_split_tf32(const mnr_split_job_t* jobs, int n_jobs, mnr_stream_t stream) {

@@ -185,8 +185,25 @@ class TowerStack:
                                      mean=self.mean[i][g], rstd=self.rstd[i][g]) for g in range(G)], M, n, self.norm[0][i].eps, self.act)
             inp = self.Y[i]
 
-    def backward(self, x, rows=None, weight_grads=True, input_grad=None):
-        """Layers top first, from self.dY[-1]; writes every .grad.  Without a norm, act'(.) is applied on the fly from the
+    def fold_begin(self):
+        """Start deferring the cross-CTA sums of the launches that follow (the heads + loss kernel, LayerNorm's backward) into
+        this step's split-reduce launch (ops.fold_defer; include/mineral_b200.h).  Returns the list to hand to backward(folds=),
+        or None when this stack's backward does not end in exactly one split-reduce launch (SIMT layers, forked streams) or
+        MNR_FOLD_DEFER=0.  The list object is reused: graph capture bakes its contents into the launch, eager calls refill it."""
+        x_ld = getattr(self, '_x_ld', self.in_dim)
+        ok = (self.use_tc and x_ld % 4 == 0 and self.L <= 3 and not getattr(self, 'bwd_fork', False)
+              and (not self.normed or self.G * self.L + 1 <= 8) and os.environ.get('MNR_FOLD_DEFER', '1') != '0')
+        if not ok:
+            return None
+        if getattr(self, '_folds', None) is None:
+            from .. import _native as nv
+            self._folds = nv.FoldList()
+        ops.fold_defer(self._folds)
+        return self._folds
+
+    def backward(self, x, rows=None, weight_grads=True, input_grad=None, folds=None):
+        """Layers top first, from self.dY[-1]; writes every .grad.  folds: the list fold_begin() returned - the deferred sums
+        run inside the final split-reduce launch.  Without a norm, act'(.) is applied on the fly from the
         saved outputs inside the GEMMs; with LayerNorm one pass turns dY into dZ in place (and emits dgamma / dbeta).
         weight_grads=False skips the weight-gradient GEMMs (a frozen network that is only differentiated through, e.g. the
         critics inside SAC.update_actor, sac.py:313-326; LayerNorm's dgamma / dbeta are still written and are garbage to
@@ -269,8 +286,11 @@ class TowerStack:
                 else:
                     ops.linear_bwd_input([dict(a=self.dY[i][g], b=self.lin[g][i].weight.data, c=self.dY[i - 1][g], saved=saved[g], N=n, K=k)
                                           for g in range(G)], M, act_i)
+        if folds is not None:
+            ops.fold_defer(None)
+            assert pending and weight_grads, "deferred folds need the split-reduce launch"
         if pending:
-            ops.tc_reduce_partials(pending)
+            ops.tc_reduce_partials(pending, folds)
 
 
 def _same_shape(a, v):
@@ -326,8 +346,8 @@ class FusedTowers:
         """Both towers up to their last activation (self.Y[-1]).  split=False: the (hi, lo) weight copies are current."""
         self.stack.forward(x, x_ld, split=split)
 
-    def backward_towers(self, x):
-        self.stack.backward(x)
+    def backward_towers(self, x, folds=None):
+        self.stack.backward(x, folds=folds)
 
     def heads_forward(self):
         M, m = self.M, self.model

@@ -321,12 +321,22 @@ def tc_linear_bwd_weight_partials(groups, M, act, ws):
     return (arr, len(groups), M, ws, _TC_GRID_CAP)
 
 
-def tc_reduce_partials(jobs):
-    """One launch: sum the split partials of up to 4 layers (records from tc_linear_bwd_weight_partials)."""
+def tc_reduce_partials(jobs, folds=None):
+    """One launch: sum the split partials of up to 4 layers (records from tc_linear_bwd_weight_partials) and, with `folds`
+    (a FoldList filled between fold_defer(list) and fold_defer(None)), the deferred cross-CTA sums of the heads + loss and
+    LayerNorm-backward launches."""
     arr = (nv.TcReduceJob * len(jobs))()
     for i, (groups, n_groups, M, ws, cap) in enumerate(jobs):
         arr[i] = nv.TcReduceJob(groups, n_groups, M, ptr(ws, U8).value, ws.numel(), cap, 0)
-    check(lib.mnr_tc_reduce_partials(arr, len(jobs), stream()), "mnr_tc_reduce_partials")
+    if folds is None:
+        check(lib.mnr_tc_reduce_partials(arr, len(jobs), stream()), "mnr_tc_reduce_partials")
+    else:
+        check(lib.mnr_tc_reduce_partials_folds(arr, len(jobs), C.byref(folds), stream()), "mnr_tc_reduce_partials_folds")
+
+
+def fold_defer(fold_list):
+    """Register (a nv.FoldList) or clear (None) this thread's deferred-fold list (include/mineral_b200.h, mnr_fold_defer)."""
+    check(lib.mnr_fold_defer(C.byref(fold_list) if fold_list is not None else None), "mnr_fold_defer")
 
 
 def tc_tower_fwd_supported(K0, widths, act):

@@ -42,6 +42,7 @@ def test_struct_layouts_match_c():
 #include <stdio.h>
 #include "mineral_b200.h"
 int main(void) {
+  printf("%zu %zu %zu %zu ", sizeof(mnr_fold_seg_t), sizeof(mnr_fold_job_t), sizeof(mnr_heads_metrics_job_t), sizeof(mnr_fold_list_t));
   printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(mnr_wide_field_t), sizeof(mnr_row_field_t), sizeof(mnr_nstep_in_t),
          sizeof(mnr_nstep_out_t), sizeof(mnr_ppo_loss_cfg_t), sizeof(mnr_optim_state_t), sizeof(mnr_linear_group_t),
          sizeof(mnr_split_job_t), sizeof(mnr_ln_group_t), sizeof(mnr_critic_set_t), sizeof(mnr_peer_comm_t),
@@ -54,7 +55,7 @@ int main(void) {
         exe = os.path.join(d, "s")
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
         sizes = [int(x) for x in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    mine = [ctypes.sizeof(x) for x in (nv.WideField, nv.RowField, nv.NStepIn, nv.NStepOut, nv.PPOLossCfg, nv.OptimState, nv.LinearGroup,
+    mine = [ctypes.sizeof(x) for x in (nv.FoldSeg, nv.FoldJob, nv.HeadsMetricsJob, nv.FoldList, nv.WideField, nv.RowField, nv.NStepIn, nv.NStepOut, nv.PPOLossCfg, nv.OptimState, nv.LinearGroup,
                                        nv.SplitJob, nv.LnGroup, nv.CriticSet, nv.PeerCommStruct, nv.TcReduceJob, nv.SquashCfg)]
     assert sizes == mine
 

@@ -466,3 +466,77 @@ def test_tc_grid_cap_and_cache_hints_do_not_change_results():
         torch.cuda.synchronize()
         scale_close(dw, ref_w, 5e-6, f"dW cap={cap}")
         scale_close(db, ref_b, 1e-5, f"db cap={cap}")
+
+
+@pytest.mark.parametrize("rows,O,A,units,act,norm,fixed_sigma,dist_type",
+                         [(2048, 37, 8, [512, 256, 128], "SiLU", "LayerNorm", False, "dreamerv3_normal"),   # the shipped Ant recipe's step
+                          (32768, 37, 8, [256, 128, 64], "ELU", None, True, "normal"),                      # cfg2's step
+                          (12001, 88, 16, [128, 128, 128], "SiLU", "LayerNorm", False, "dreamerv3_normal")])  # ragged, 64-row head tiles
+def test_deferred_folds_equal_the_in_kernel_sums(rows, O, A, units, act, norm, fixed_sigma, dist_type):
+    """mnr_fold_defer: the heads + loss kernel and LayerNorm's backward stop after parking their per-CTA partials and the
+    split-reduce launch finishes the sums.  Everything downstream (dY, dX) is bit-identical; the deferred sums differ from the
+    in-kernel ones only in the order the CTAs' partials are added (<= 2e-6 of scale)."""
+    from mineral_b200 import ops
+    from mineral_b200.agents.ppo.models import ActorCritic
+    from mineral_b200.nets.fused_towers import FusedTowers
+
+    if not ops.tc_supported():
+        pytest.skip("tensor-map driver entry point unavailable")
+    torch.manual_seed(rows)
+    dist_kwargs = dict(dist_type=dist_type, minstd=0.1, maxstd=1.0) if dist_type != "normal" else dict(dist_type="normal")
+    mlp_kwargs = dict(units=units, act_type=act)
+    if norm:
+        mlp_kwargs["norm_type"] = norm
+    model = ActorCritic({"obs": (O,)}, A, mlp_kwargs=mlp_kwargs, fixed_sigma=fixed_sigma, actor_dist_kwargs=dist_kwargs).to(DEV)
+    params = dict(model.named_parameters())
+    for p in params.values():
+        p.grad = torch.zeros_like(p)
+    ft = FusedTowers(model, rows, DEV, use_tc=True)
+    assert ft.use_tc and ft.fused_heads_ok
+    g = torch.Generator(device=DEV).manual_seed(2)
+    x_ld = (O + 3) // 4 * 4
+    x = torch.zeros(rows, x_ld, device=DEV)
+    x[:, :O] = torch.randn(rows, O, device=DEV, generator=g)
+    d = dict(actions=torch.randn(rows, A, device=DEV, generator=g), neglogp=torch.randn(rows, device=DEV, generator=g) + 8,
+             advantages=torch.randn(rows, device=DEV, generator=g), values=torch.randn(rows, 1, device=DEV, generator=g),
+             returns=torch.randn(rows, 1, device=DEV, generator=g), mu=torch.randn(rows, A, device=DEV, generator=g),
+             sigma=torch.rand(rows, A, device=DEV, generator=g) + 0.2)
+    cfg = ops.make_loss_cfg(dist_type, 0.1, 1.0, 0.2, False, True, 4.0, 0.002, 1e-3, "bound")
+    cfg.dz_act = ft.heads_dz_act()
+    g_mu, g_ls, g_v = torch.zeros(rows, A, device=DEV), torch.zeros(rows, A, device=DEV), torch.zeros(rows, device=DEV)
+    ws = ops.ppo_heads_workspace(rows, A, units[-1], DEV)
+
+    def run(defer):
+        for p in params.values():
+            p.grad.fill_(float("nan"))
+        dd = {k: v.clone() for k, v in d.items()}
+        m, mm, sm = torch.full((10,), float("nan"), device=DEV), torch.zeros(A, device=DEV), torch.zeros(A, device=DEV)
+        ft.forward_towers(x, x_ld)
+        folds = ft.stack.fold_begin() if defer else None
+        assert (folds is not None) == defer
+        ft.heads_loss_fwd_bwd(dd, 0, rows, g_mu, g_ls, g_v, m, cfg, ws, mm, sm)
+        if defer:   # the sums have not run yet: the heads' gradients still hold the NaN fill
+            torch.cuda.synchronize()
+            assert torch.isnan(params["mu.weight"].grad).all() and torch.isnan(m).all()
+        ft.backward_towers(x, folds=folds)
+        torch.cuda.synchronize()
+        if defer:
+            assert folds.n_folds == (1 + (2 * len(units) if norm else 0)) and folds.has_metrics == 1
+        return ({k: p.grad.clone() for k, p in params.items()}, m.clone(), mm.clone(), sm.clone(),
+                [t.clone() for t in ft.dY[0]], dd["mu"].clone())
+
+    base, again, deferred = run(False), run(False), run(True)
+    for k in base[0]:
+        eq(again[0][k], base[0][k].cpu(), f"in-kernel sums are deterministic: {k}")
+    for k in base[0]:
+        assert torch.isfinite(deferred[0][k]).all(), f"grad {k} not written by the deferred path"
+        scale_close(deferred[0][k], base[0][k], 2e-6, f"grad {k}")
+    scale_close(deferred[1][:8], base[1][:8], 2e-6, "metrics")
+    scale_close(deferred[2], base[2], 2e-6, "mu mean"), scale_close(deferred[3], base[3], 2e-6, "sigma mean")
+    for t, r in zip(deferred[4], base[4]):
+        eq(t, r.cpu(), "dZ1 (per-row work is untouched by the deferral)")
+    eq(deferred[5], base[5].cpu(), "mu write-back")
+    rerun = run(True)
+    for k in base[0]:
+        eq(rerun[0][k], deferred[0][k].cpu(), f"deferred sums are deterministic: {k}")
+    eq(rerun[1], deferred[1].cpu(), "deferred metrics are deterministic")
