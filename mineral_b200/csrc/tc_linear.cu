@@ -833,6 +833,37 @@ struct FoldJobs {
 
 constexpr int kFoldCols = 8, kFoldSlices = 256 / kFoldCols;
 __device__ __noinline__ void fold_block(const FoldJobs& fj, int fi, float4 (*s_part)[32]) {
+  if (fi < fj.n && fj.f[fi]._pad == 1) {
+    // float4 form (width % 4 == 0, 16 B-aligned partial rows - LayerNorm's [grid][2N] slabs): 8 float4 = one 128 B line per row
+    const mnr_fold_job_t& jb = fj.f[fi];
+    const int col = threadIdx.x % kFoldCols, slice = threadIdx.x / kFoldCols;
+    const int o = (blockIdx.x * kFoldCols + col) * 4;
+    if ((int)blockIdx.x * kFoldCols * 4 >= jb.width) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (o < jb.width) {
+      const float* src = jb.parts + o;
+#pragma unroll 10
+      for (int x = slice; x < jb.n_parts; x += kFoldSlices) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src + (size_t)x * jb.width));
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+    }
+    float4* s = reinterpret_cast<float4*>(s_part);   // [32 slices][8 columns]
+    s[slice * kFoldCols + col] = acc;
+    __syncthreads();
+    if (slice != 0 || o >= jb.width) return;
+#pragma unroll 8
+    for (int q = 1; q < kFoldSlices; ++q) {
+      const float4 v = s[q * kFoldCols + col];
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    for (int k = 0; k < jb.n_segs; ++k)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (o + e >= jb.seg[k].begin && o + e < jb.seg[k].end) jb.seg[k].dst[o + e - jb.seg[k].begin] = av[e] * jb.seg[k].scale;
+    return;
+  }
   if (fi < fj.n) {
     const mnr_fold_job_t& jb = fj.f[fi];
     const int col = threadIdx.x % kFoldCols, slice = threadIdx.x / kFoldCols;
@@ -1276,7 +1307,9 @@ int reduce_launch(ReduceJobs& jobs, int n_jobs, cudaStream_t stream, const mnr_f
       for (int k = 0; k < f.n_segs; ++k)
         if (!f.seg[k].dst || f.seg[k].begin < 0 || f.seg[k].end > f.width || f.seg[k].end < f.seg[k].begin) return MNR_ESHAPE;
       folds.f[q] = f;
-      const int x = (f.width + kFoldCols - 1) / kFoldCols;
+      const bool vec = f.width % 4 == 0 && mnr_aligned(f.parts, 16);
+      folds.f[q]._pad = vec ? 1 : 0;   // kernel-side flag: float4 form
+      const int x = vec ? (f.width + 4 * kFoldCols - 1) / (4 * kFoldCols) : (f.width + kFoldCols - 1) / kFoldCols;
       max_x = x > max_x ? x : max_x;
     }
     folds.n = list->n_folds;
