@@ -88,6 +88,15 @@ struct Row {
       }
     }
   }
+  // slots [4k, 4k + 4) (VEC) or slot k (scalar) of a row that lives in SHARED memory
+  __device__ __forceinline__ static void piece(const float* p, int k, int lane, float (&out)[4]) {
+    if (VEC) {
+      const float4 t = *reinterpret_cast<const float4*>(p + 4 * (lane + 32 * k));
+      out[0] = t.x, out[1] = t.y, out[2] = t.z, out[3] = t.w;
+    } else {
+      out[0] = p[lane + 32 * k];
+    }
+  }
   // column index of register slot i
   __device__ __forceinline__ static int col(int i, int lane) { return VEC ? 4 * (lane + 32 * (i / 4)) + (i & 3) : lane + 32 * i; }
 };
@@ -102,6 +111,8 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const __grid_const
   const float invN = 1.f / (float)N;
   Row<E, VEC> gam, bet;
   gam.load(g.gamma, N, lane), bet.load(g.beta, N, lane);
+  // (a software prefetch of the next row, as in the backward kernel, measured SLOWER here: 59 -> 76 us at 32768 x 512 - the
+  // extra registers cost a resident CTA - and unchanged for the narrower layers)
   for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < a.M; row += (int64_t)gridDim.x * kWarps) {
     Row<E, VEC> x;
     x.load(g.z + row * N, N, lane);
@@ -132,31 +143,75 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
   const int N = a.N;
   const float invN = 1.f / (float)N;
   const int n_groups = a.n_groups;
+  // gamma / beta of the group live in shared memory (conflict-free LDS.128 per piece), which frees their 2E registers for a
+  // software prefetch: the NEXT row's z / dy loads are issued before this row's arithmetic, so a warp keeps loads in flight
+  // through its compute phase (exp, two butterfly sums) instead of alternating between the two (0.64 -> of the HBM peak at cfg5)
+  constexpr int PK = VEC ? E / 4 : E, PW_ = VEC ? 4 : 1;   // pieces per lane, slots per piece
+  // 16 elements per lane (N = 512): prefetching both rows spills and prefetching z alone still measured slower than none
+  // (100.4 -> 104.4 us at 32768 rows): those rows keep the plain load -> compute -> store order
+  constexpr bool PF = E <= 8;
+  const int NP = VEC ? N : 32 * E;                          // padded row length in shared memory (scalar form: zero pad)
+  float* s_gam = s_fold + kWarps * 2 * N;
+  float* s_bet = s_gam + NP;
   for (int gi = 0; gi < n_groups; ++gi) {   // every CTA serves every group: one grid barrier for all of them
     const mnr_ln_group_t& g = a.g[gi];
-    Row<E, VEC> gam, bet, dgam, dbet;
-    gam.load(g.gamma, N, lane), bet.load(g.beta, N, lane);
+    Row<E, VEC> dgam, dbet, gam, bet;   // gam / bet: registers without the prefetch (as before), shared memory with it
 #pragma unroll
     for (int i = 0; i < E; ++i) dgam.v[i] = 0.f, dbet.v[i] = 0.f;
-    for (int64_t row = (int64_t)blockIdx.x * kWarps + warp; row < a.M; row += (int64_t)gridDim.x * kWarps) {
-      Row<E, VEC> z, dy;
-      z.load(g.z + row * N, N, lane), dy.load(g.dy + row * N, N, lane);
-      const float mean = __ldg(g.mean + row), rstd = __ldg(g.rstd + row);
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    int64_t row = (int64_t)blockIdx.x * kWarps + warp;
+    Row<E, VEC> z, dy;
+    float mean = 0.f, rstd = 0.f;
+    if (PF) {
+      if (row < a.M) {   // the first row's loads go out before gamma / beta are staged: one DRAM round trip for both
+        z.load(g.z + row * N, N, lane), dy.load(g.dy + row * N, N, lane);
+        mean = __ldg(g.mean + row), rstd = __ldg(g.rstd + row);
+      }
+      __syncthreads();   // the previous group's rows (s_gam / s_bet) and fold (s_fold) are done
+      for (int c = threadIdx.x; c < NP; c += kThreads) s_gam[c] = c < N ? __ldg(g.gamma + c) : 0.f, s_bet[c] = c < N ? __ldg(g.beta + c) : 0.f;
+      __syncthreads();
+    } else {
+      gam.load(g.gamma, N, lane), bet.load(g.beta, N, lane);
+    }
+    while (row < a.M) {
+      const int64_t nxt = row + stride;
+      Row<E, VEC> zn, dyn;
+      float mean_n = 0.f, rstd_n = 0.f;
+      if (!PF) {
+        z.load(g.z + row * N, N, lane), dy.load(g.dy + row * N, N, lane);
+        mean = __ldg(g.mean + row), rstd = __ldg(g.rstd + row);
+      } else if (nxt < a.M) {
+        zn.load(g.z + nxt * N, N, lane), dyn.load(g.dy + nxt * N, N, lane);
+        mean_n = __ldg(g.mean + nxt), rstd_n = __ldg(g.rstd + nxt);
+      }
       float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-      for (int i = 0; i < E; ++i) {
-        const bool in = Row<E, VEC>::col(i, lane) < N;
-        const float xh = in ? (z.v[i] - mean) * rstd : 0.f;
-        const float dn = in ? dy.v[i] * act_df<ACT>(fmaf(xh, gam.v[i], bet.v[i])) : 0.f;
-        dgam.v[i] = fmaf(dn, xh, dgam.v[i]), dbet.v[i] += dn;
-        const float gg = dn * gam.v[i];
-        s1 += gg, s2 = fmaf(gg, xh, s2);
-        z.v[i] = xh, dy.v[i] = gg;
+      for (int k = 0; k < PK; ++k) {
+        float gk[4], bk[4];
+        if (PF) {
+          Row<E, VEC>::piece(s_gam, k, lane, gk), Row<E, VEC>::piece(s_bet, k, lane, bk);
+        } else {
+#pragma unroll
+          for (int e = 0; e < PW_; ++e) gk[e] = gam.v[PW_ * k + e], bk[e] = bet.v[PW_ * k + e];
+        }
+#pragma unroll
+        for (int e = 0; e < PW_; ++e) {
+          const int i = PW_ * k + e;
+          const bool in = Row<E, VEC>::col(i, lane) < N;
+          const float xh = in ? (z.v[i] - mean) * rstd : 0.f;
+          const float dn = in ? dy.v[i] * act_df<ACT>(fmaf(xh, gk[e], bk[e])) : 0.f;
+          dgam.v[i] = fmaf(dn, xh, dgam.v[i]), dbet.v[i] += dn;
+          const float gg = dn * gk[e];
+          s1 += gg, s2 = fmaf(gg, xh, s2);
+          z.v[i] = xh, dy.v[i] = gg;
+        }
       }
       s1 = warp_allsum(s1) * invN, s2 = warp_allsum(s2) * invN;
 #pragma unroll
       for (int i = 0; i < E; ++i) dy.v[i] = rstd * (dy.v[i] - s1 - z.v[i] * s2);
       dy.store(g.dz + row * N, N, lane);
+      if (PF) z = zn, dy = dyn, mean = mean_n, rstd = rstd_n;
+      row = nxt;
     }
     // fold the CTA's warps, park the CTA partial
     __syncthreads();
@@ -265,7 +320,7 @@ extern "C" int mnr_ln_act_bwd(const mnr_ln_group_t* groups, int n_groups, int64_
   a.barrier = reinterpret_cast<unsigned long long*>(workspace);
   a.partials = reinterpret_cast<float*>(static_cast<unsigned char*>(workspace) + 256);
   const int grid = bwd_grid(M);  // every CTA loops over the groups itself: one grid barrier for all of them
-  const size_t smem = (size_t)kWarps * 2 * N * sizeof(float);
+  const size_t smem = ((size_t)kWarps * 2 * N + 2 * (size_t)(N % 128 == 0 ? N : 32 * ((N + 31) / 32 <= 4 ? 4 : 16))) * sizeof(float);
   if (mnr_fold_list_t* fl = mnr_fold_target()) {   // deferred fold: one job per group, [grid][2N] partial rows -> dgamma | dbeta
     if (fl->n_folds + n_groups <= MNR_MAX_FOLDS) {
       a.defer = 1;
