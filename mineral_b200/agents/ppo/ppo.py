@@ -724,9 +724,13 @@ class _UpdateEngine:
                     self.towers.forward_towers(x_buf, x_ld, split=not opt_splits)
                     # the cross-CTA sums of the heads kernel and of LayerNorm's backward run inside the split-reduce launch
                     folds = self.towers.stack.fold_begin()
-                    self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), a.optim.tail if peer else m,
-                                                   self.loss_cfg, self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
-                    self.towers.backward_towers(x_buf, folds=folds)
+                    try:
+                        self.towers.heads_loss_fwd_bwd(d, s, e, self.g_mu, self.g_ls, self.g_v.view(-1), a.optim.tail if peer else m,
+                                                       self.loss_cfg, self.heads_ws, self.mu_mean[step], self.sigma_mean[step])
+                        self.towers.backward_towers(x_buf, folds=folds)
+                    finally:   # never leave a fold list registered with the library (backward clears it on the normal path)
+                        if folds is not None:
+                            ops.fold_defer(None)
                 else:
                     # heads wider than the fused kernel takes: thin-layer head kernels + the row-wise loss kernel
                     self.towers.stack.forward(x_buf, x_ld, split=not opt_splits)

@@ -70,6 +70,19 @@ def test_argument_validation_without_gpu():
     assert lib.mnr_critic_targets_f32(one, one, one, None, one, 4, 4, 7, 0.99, 0.95, 0.05, 0.94, 0.0, 0, 1.0, 1.0, None) == -4
     assert lib.mnr_post_rollout_workspace_bytes(32, 4096) > 0
     assert lib.mnr_rms_moments_workspace_bytes(131072, 37, 32768) > 0
+    # deferred folds: registering empties the list; a reduce launch with neither jobs nor folds, or with a malformed fold, is refused
+    from mineral_b200 import _native as nv
+    fl = nv.FoldList()
+    fl.n_folds, fl.has_metrics = 3, 1
+    assert lib.mnr_fold_defer(ctypes.byref(fl)) == 0 and fl.n_folds == 0 and fl.has_metrics == 0
+    assert lib.mnr_fold_defer(None) == 0
+    assert lib.mnr_tc_reduce_partials_folds(None, 0, None, None) == -2
+    assert lib.mnr_tc_reduce_partials_folds(None, 0, ctypes.byref(fl), None) == -2   # empty list
+    fl.n_folds = 1   # parts == NULL
+    assert lib.mnr_tc_reduce_partials_folds(None, 0, ctypes.byref(fl), None) == -1
+    fl.folds[0].parts, fl.folds[0].n_parts, fl.folds[0].width, fl.folds[0].n_segs = 16, 4, 8, 1
+    fl.folds[0].seg[0].begin, fl.folds[0].seg[0].end, fl.folds[0].seg[0].dst = 0, 9, 16   # segment past the row width
+    assert lib.mnr_tc_reduce_partials_folds(None, 0, ctypes.byref(fl), None) == -2
 
 
 def test_product_refuses_cpu_tensors():
