@@ -809,6 +809,15 @@ def main():
                          "what": "sum over the launches of operands read once + result written once (f32); layer outputs are saved for "
                                  "the backward pass, so every layer boundary crosses HBM unless L2 still holds it"}}
 
+        # DRAM traffic of the same six launches from the committed ncu --set full capture (profiles/), per step like `achieved`
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_set_traffic.json")))
+            if prof.get("workload") == args.workload and fused_fwd:
+                roofline_tensor["traffic"] = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+                roofline_tensor["traffic_source"] = prof["source"]
+        except Exception:
+            pass
+
     # ---- share of the update each kernel takes, from the committed ncu launch list of this command (profiles/) ----
     shares = None
     try:

@@ -97,6 +97,10 @@ struct Row {
       out[0] = p[lane + 32 * k];
     }
   }
+  __device__ __forceinline__ static void piece_st(float* p, int k, int lane, const float (&v)[4]) {
+    if (VEC) *reinterpret_cast<float4*>(p + 4 * (lane + 32 * k)) = make_float4(v[0], v[1], v[2], v[3]);
+    else p[lane + 32 * k] = v[0];
+  }
   // column index of register slot i
   __device__ __forceinline__ static int col(int i, int lane) { return VEC ? 4 * (lane + 32 * (i / 4)) + (i & 3) : lane + 32 * i; }
 };
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(kThreads) ln_act_fwd_kernel(const __grid_const
   }
 }
 
-template <int E, bool VEC, int ACT>
+template <int E, bool VEC, int ACT, bool PFW>
 __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_constant__ LnArgs a) {
   extern __shared__ __align__(16) float s_fold[];  // [kWarps][2N]
   mnr::pdl_trigger();   // PDL: see common.cuh
@@ -147,9 +151,12 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
   // software prefetch: the NEXT row's z / dy loads are issued before this row's arithmetic, so a warp keeps loads in flight
   // through its compute phase (exp, two butterfly sums) instead of alternating between the two (0.64 -> of the HBM peak at cfg5)
   constexpr int PK = VEC ? E / 4 : E, PW_ = VEC ? 4 : 1;   // pieces per lane, slots per piece
-  // 16 elements per lane (N = 512): prefetching both rows spills and prefetching z alone still measured slower than none
-  // (100.4 -> 104.4 us at 32768 rows): those rows keep the plain load -> compute -> store order
-  constexpr bool PF = E <= 8;
+  // 16 elements per lane (N = 512): with dgamma / dbeta in registers the prefetch spills (measured slower, also when only z is
+  // prefetched), so those rows accumulate dgamma / dbeta in the warp's OWN slab of the fold buffer (a lane re-reads only what it
+  // wrote: no synchronisation; 16 LDS.128 + 16 STS.128 per row against 6 KB of DRAM traffic) whenever a warp has rows to overlap
+  // PFW (wide rows, chosen by the host): only when a warp owns more than one row
+  constexpr bool ACC_SMEM = E > 8 && PFW;
+  constexpr bool PF = E <= 8 || PFW;
   const int NP = VEC ? N : 32 * E;                          // padded row length in shared memory (scalar form: zero pad)
   float* s_gam = s_fold + kWarps * 2 * N;
   float* s_bet = s_gam + NP;
@@ -158,6 +165,8 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
     Row<E, VEC> dgam, dbet, gam, bet;   // gam / bet: registers without the prefetch (as before), shared memory with it
 #pragma unroll
     for (int i = 0; i < E; ++i) dgam.v[i] = 0.f, dbet.v[i] = 0.f;
+    float* slab = s_fold + warp * 2 * N;   // this warp's [dgamma | dbeta] slab
+    constexpr bool acc_smem = ACC_SMEM;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
     int64_t row = (int64_t)blockIdx.x * kWarps + warp;
     Row<E, VEC> z, dy;
@@ -169,6 +178,7 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
       }
       __syncthreads();   // the previous group's rows (s_gam / s_bet) and fold (s_fold) are done
       for (int c = threadIdx.x; c < NP; c += kThreads) s_gam[c] = c < N ? __ldg(g.gamma + c) : 0.f, s_bet[c] = c < N ? __ldg(g.beta + c) : 0.f;
+      if (acc_smem) dgam.store(slab, N, lane), dbet.store(slab + N, N, lane);   // zeros
       __syncthreads();
     } else {
       gam.load(g.gamma, N, lane), bet.load(g.beta, N, lane);
@@ -200,10 +210,18 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
           const bool in = Row<E, VEC>::col(i, lane) < N;
           const float xh = in ? (z.v[i] - mean) * rstd : 0.f;
           const float dn = in ? dy.v[i] * act_df<ACT>(fmaf(xh, gk[e], bk[e])) : 0.f;
-          dgam.v[i] = fmaf(dn, xh, dgam.v[i]), dbet.v[i] += dn;
           const float gg = dn * gk[e];
+          if (acc_smem) gk[e] = dn * xh, bk[e] = dn;   // gamma / beta are consumed: the slots carry this piece's dgamma / dbeta terms
+          else dgam.v[i] = fmaf(dn, xh, dgam.v[i]), dbet.v[i] += dn;
           s1 += gg, s2 = fmaf(gg, xh, s2);
           z.v[i] = xh, dy.v[i] = gg;
+        }
+        if (acc_smem) {
+          float dg[4], db[4];
+          Row<E, VEC>::piece(slab, k, lane, dg), Row<E, VEC>::piece(slab + N, k, lane, db);
+#pragma unroll
+          for (int e = 0; e < PW_; ++e) dg[e] += gk[e], db[e] += bk[e];
+          Row<E, VEC>::piece_st(slab, k, lane, dg), Row<E, VEC>::piece_st(slab + N, k, lane, db);
         }
       }
       s1 = warp_allsum(s1) * invN, s2 = warp_allsum(s2) * invN;
@@ -215,7 +233,7 @@ __global__ void __launch_bounds__(kThreads, 2) ln_act_bwd_kernel(const __grid_co
     }
     // fold the CTA's warps, park the CTA partial
     __syncthreads();
-    dgam.store(s_fold + warp * 2 * N, N, lane), dbet.store(s_fold + warp * 2 * N + N, N, lane);
+    if (!acc_smem) dgam.store(slab, N, lane), dbet.store(slab + N, N, lane);
     __syncthreads();
     float* part = a.partials + ((size_t)gi * gridDim.x + blockIdx.x) * 2 * N;
     for (int c = threadIdx.x; c < 2 * N; c += kThreads) {
@@ -332,9 +350,10 @@ extern "C" int mnr_ln_act_bwd(const mnr_ln_group_t* groups, int n_groups, int64_
       }
     }
   }
+  const bool pfw = M > (int64_t)grid * kWarps;   // wide rows: prefetch + shared-memory dgamma / dbeta when a warp owns several rows
 #define MNR_LN_GO(KERNEL, EV, VV, AV, ...)                                                                     \
   {                                                                                                            \
-    auto kern = KERNEL<EV, VV, AV>;                                                                            \
+    auto kern = (EV > 8 && pfw) ? KERNEL<EV, VV, AV, (EV > 8)> : KERNEL<EV, VV, AV, false>;                    \
     cudaError_t e = mnr_allow_max_dyn_smem(kern);                                                              \
     if (e != cudaSuccess) return (int)e;                                                                       \
     mnr_launch_pdl(kern, dim3(grid), dim3(kThreads), smem, mnr_cs(stream), a);                                 \
