@@ -8,14 +8,17 @@
 //   dWmu = g_mu^T Y3a, dbmu, dWsig / dsigma, dWv = g_v^T Y3v, dbv                         (head parameter gradients)
 //   mu / sigma write-back (mineral/agents/ppo/experience.py:83-87) and their column means (results['mu'|'sigma'])
 //
-// Layout of the work.  A CTA = 128 threads owns tiles of 128 rows; the Y3a tile (and afterwards, in the same buffer, the
-// Y3v tile) is staged ONCE in shared memory (coalesced float4 loads, row pitch H+4 floats so that "thread = row" LDS.128
-// sweeps are conflict-free) and is used three times: (1) thread-per-row dot products with the head weights (broadcast
-// LDS.128 from shared memory), (2) the weight-gradient outer products with thread = (4 hidden columns, row group)
-// walking its rows of the tile, accumulating in registers ACROSS tiles, (3) it is overwritten in place by dY3 and leaves
-// through coalesced float4 stores.  After the tile loop the per-CTA partials go to the workspace, the grid (all CTAs resident) meets at
-// a grid barrier and every CTA reduces its share of the outputs over all CTAs' partials in a fixed order
-// (deterministic, no atomics); CTA 0 also finalises the ten loss metrics.
+// Layout of the work.  A CTA = 256 threads owns tiles of 256 / TPR rows (TPR threads per row: 2, 4 or 8, chosen by the host
+// from the minibatch size and the head width - see kThreadsHF and launch_fused); the Y3a tile (and the Y3v tile: in its own
+// prefetched buffer, or afterwards in the same one) is staged ONCE in shared memory (coalesced float4 loads, row pitch H+8
+// floats so that "thread = row piece" LDS.128 sweeps are conflict-free) and is used three times: (1) per-row dot products
+// with the head weights (broadcast LDS.128 from shared memory), (2) the weight-gradient outer products with thread =
+// (UV hidden columns, row group) walking its rows of the tile, accumulating in registers ACROSS tiles, (3) it is
+// overwritten in place by dY3 and leaves through coalesced float4 stores.  After the tile loop the per-CTA partials go to
+// the workspace; then EITHER the kernel ends there and the sums over the CTAs run inside the split-reduce launch (deferred
+// folds, mnr_fold_defer: the PPO update's path) OR the grid (all CTAs resident) meets at a grid barrier and every CTA
+// reduces its share of the outputs over all CTAs' partials in a fixed order, CTA 0 also finalising the ten loss metrics.
+// Deterministic either way, no atomics.
 #include "common.cuh"
 #include "loss_math.cuh"
 
@@ -104,11 +107,10 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b, float ac
 
 // A (the action dimension padded to a multiple of 4; the real one is a.A at run time: pad rows of the head weights are
 // zero in shared memory and the rolled loss loops stop at a.A), H compile-time (no guards in the unrolled dot products);
-// one shared-memory tile buffer serves the actor tower
-// and then the value tower of the same 128 rows, so a CTA needs ~58 KB and 3 CTAs (24 warps) share an SM.  The kernel is
-// bound by per-thread instruction latency (every instruction runs once or twice per warp), hence TWO threads per row:
-// each takes every other float4 column of the row in the dot-product / dY3 sweeps and every other action column in the
-// loss loops; partial sums meet through one __shfl_xor.
+// two CTAs (16 warps) share an SM.  The kernel is bound by per-thread instruction latency (every instruction runs once or
+// twice per warp), hence TPR >= 2 threads per row: thread h of a row takes the float4 columns h, h + TPR, .. in the
+// dot-product / dY3 sweeps and the action columns h, h + TPR, .. in the loss loops; partial sums meet through log2(TPR)
+// __shfl_xor steps (a row's threads are an aligned group of one warp).
 template <int A, int H, bool LEARNED, int TPR>
 __global__ void __launch_bounds__(kThreadsHF, 2) heads_fused_kernel(const __grid_constant__ FusedHeadsArgs a,
                                                             const __grid_constant__ mnr_ppo_loss_cfg_t cfg) {
